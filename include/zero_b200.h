@@ -1,0 +1,245 @@
+/* zero_b200.h — C ABI of libzero_b200.so: the sm_100a kernels behind Zero's Transformer hot path.
+ *
+ * The reference (bzhangGo/zero @ d97e2c2) has no native code and no FFI: its hot path is TF1.x graph ops
+ * built by func.py / models/transformer*.py / search.py.  Each entry point below therefore cites the
+ * Python call site(s) it replaces; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; this library never allocates,
+ *     never synchronises, never throws);
+ *   - every call enqueues work on `stream` and returns 0 (ZB_OK) or a negative zb_status;
+ *     zb_last_error_string() gives a thread-local description;
+ *   - activations / compute weights are bf16 row-major, accumulation / statistics / gradients-of-parameters
+ *     are fp32 (mirrors the reference's mixed-precision contract, utils/dtype.py:55-69, with bf16 for fp16);
+ *   - token ids are int32 with pad = 0, unk = 1, eos = 2 (vocab.py:20-22).
+ */
+#ifndef ZERO_B200_H_
+#define ZERO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* zb_stream_t; /* == cudaStream_t */
+
+#define ZB_ABI_VERSION 1
+
+typedef enum {
+  ZB_OK = 0,
+  ZB_EINVAL = -1,       /* bad shape / alignment / null pointer */
+  ZB_EUNSUPPORTED = -2, /* dtype / size / device not supported */
+  ZB_ECUDA = -3         /* CUDA runtime or driver error, see zb_last_error_string() */
+} zb_status;
+
+typedef enum { ZB_BF16 = 0, ZB_F32 = 1 } zb_dtype;
+
+int zb_abi_version(void);
+const char* zb_last_error_string(void);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+int64_t zb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ K1
+ * zb_gemm: D[m,n] (+)= alpha * sum_k A(m,k) * B(n,k)  (+ bias[n]) (relu) (* (mask[m,n] > 0))
+ * bf16 operands, fp32 accumulation in TMEM (tcgen05.mma), TMA-fed 128B-swizzled smem ring.
+ * Replaces tf.matmul in func.linear (func.py:49, bias_add :59), the tied-softmax projection
+ * (models/transformer.py:194) and — as dgrad / wgrad — the tf.gradients of both (main.py:28).
+ *   a_layout ZB_K_MAJOR : A stored [m][k] (k contiguous), lda = row pitch in elements
+ *            ZB_MN_MAJOR: A stored [k][m] (m contiguous)
+ *   b_layout ZB_K_MAJOR : B stored [n][k];  ZB_MN_MAJOR: B stored [k][n]
+ *   y = x W      : A = x  K-major,  B = W  MN-major        (W is [in,out], func.py:48)
+ *   dx = dy W^T  : A = dy K-major,  B = W  K-major
+ *   dW = x^T dy  : A = x  MN-major, B = dy MN-major, ZB_EPI_ACCUM into the fp32 gradient arena
+ */
+typedef enum { ZB_K_MAJOR = 0, ZB_MN_MAJOR = 1 } zb_layout;
+enum {
+  ZB_EPI_BIAS = 1,      /* + bias[n] (fp32)                                   func.py:59           */
+  ZB_EPI_RELU = 2,      /* max(.,0)                                            func.py:332          */
+  ZB_EPI_ACCUM = 4,     /* D is fp32 and is atomically accumulated into (D += ...); needed by split-K */
+  ZB_EPI_RELU_MASK = 8  /* multiply by (mask[m,n] > 0): backward of relu through the saved activation */
+};
+typedef struct {
+  const void* a;
+  const void* b;
+  void* d;
+  int64_t m, n, k;
+  int64_t lda, ldb, ldd; /* pitches in elements */
+  int32_t a_layout, b_layout;
+  int32_t d_dtype; /* ZB_BF16 or ZB_F32 */
+  int32_t flags;
+  const float* bias;   /* [n] fp32 or NULL */
+  const void* mask;    /* bf16 [m, ldmask] or NULL */
+  int64_t ldmask;
+  float alpha;
+  int32_t split_k;     /* 0 = choose; >1 requires ZB_EPI_ACCUM */
+} zb_gemm_args;
+int zb_gemm(const zb_gemm_args* a, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K2/K3
+ * zb_attention_{fwd,bwd}: fused scaled-dot attention softmax(q k^T * scale + mask) v per (batch, head).
+ * Replaces func.dot_attention's split_heads/matmul/mask-add/softmax/matmul/combine_heads
+ * (func.py:218-256) and their gradients.  q/k/v/o are [batch, len, heads*dh] bf16 views with explicit
+ * row pitches (so the fused [B,L,3d] qkv buffer of func.py:196-197 is consumed in place).
+ * Masking follows func.attention_bias (func.py:372-388): additive -inf_value where key j is padding
+ * (key_len[b] <= j, "masking") and/or j > i + causal_offset ("causal").
+ * `lse` [batch, heads, lq] fp32 = log-sum-exp of the masked logits, saved for the backward.
+ * Optional relative-position terms (modules/rpr.py:10-75): rpr_k / rpr_v tables [2*max_rel+1, dh] bf16;
+ * distance = clip(i + q_offset - j, -max_rel, max_rel) + max_rel.
+ */
+typedef struct {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t ldq, ldk, ldv, ldo;         /* row pitch (elements) between consecutive positions */
+  int64_t bsq, bsk, bsv, bso;         /* batch stride (elements) */
+  int32_t batch, heads, lq, lk, dh;
+  const int32_t* key_len;             /* [batch] number of valid keys, or NULL = all valid */
+  int32_t causal;                     /* 1: key j visible to query i iff j <= i + q_offset */
+  int32_t q_offset;                   /* absolute position of query row 0 (cached decode: time) */
+  float scale;                        /* dh^-0.5, func.py:222 */
+  float inf_value;                    /* dtype.inf(), default 1e8 (utils/dtype.py:14) */
+  float* lse;                         /* [batch, heads, lq] fp32 (fwd: out; bwd: in) */
+  const void* rpr_k; const void* rpr_v; int32_t max_rel; /* NULL/0 when unused */
+  int32_t relu_attn;                  /* 1: ReLA — relu(logits * keep) instead of softmax (modules/rela.py:65-70) */
+  /* backward only */
+  const void* d_o; void* dq; void* dk; void* dv;
+  int64_t lddo, lddq, lddk, lddv, bsdo, bsdq, bsdk, bsdv;
+  float* d_rpr_k; float* d_rpr_v;     /* fp32 [2*max_rel+1, dh], accumulated */
+} zb_attention_args;
+int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream);
+int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K4
+ * zb_add_ln_{fwd,bwd}: out = scale * (s - mean(s)) * rsqrt(var(s) + eps) + offset with s = x (+ y).
+ * Replaces func.residual_fn + func.layer_norm (func.py:321-324, 289-303); biased variance, eps = 1e-8.
+ * fwd saves mean / rstd (fp32 [rows]).  bwd returns ds (bf16, the gradient wrt both x and y),
+ * optionally ds += extra (gradient arriving through the residual skip), and accumulates
+ * dscale / doffset (fp32 [cols]).
+ */
+typedef struct {
+  const void* x; const void* y; /* y may be NULL */
+  void* out; float* mean; float* rstd;
+  const float* scale; const float* offset;
+  int64_t rows, cols;
+  float eps;
+  /* backward */
+  const void* d_out; const void* s_hat_src; /* unused, reserved */
+  void* ds; float* dscale; float* doffset;
+} zb_add_ln_args;
+int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream);
+int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K5
+ * zb_embed_{fwd,bwd}: out[b,l,:] = table[ids[b,l-shift]] * mult + bias + timing(l or time)
+ * Replaces tf.gather * sqrt(d) + bias_add + add_timing_signal (models/transformer.py:29-31,104-117,
+ * func.py:341-369).  shift = 1 reproduces the decoder's right shift with a zero first row
+ * (models/transformer.py:108-111; the zero row still receives the timing signal).
+ * zero_if_all_pad = 1 reproduces the decode-time rule (models/transformer.py:113-115): if every id is pad
+ * the gathered+biased input is replaced by zeros before the timing signal.
+ * bwd scatter-adds d_out * mult into d_table (fp32) and sums d_out into d_bias (fp32).
+ */
+typedef struct {
+  const int32_t* ids; /* [batch, len] */
+  const void* table;  /* bf16 [vocab, dim] */
+  const float* bias;  /* fp32 [dim] */
+  void* out;          /* bf16 [batch, len, dim] */
+  int32_t batch, len, dim, vocab;
+  int32_t shift; int32_t zero_if_all_pad;
+  int32_t time;       /* >= 0: every row uses position `time` (cached decode); -1: position = l */
+  float mult;
+  const void* d_out; float* d_table; float* d_bias;
+} zb_embed_args;
+int zb_embed_fwd(const zb_embed_args* a, zb_stream_t stream);
+int zb_embed_bwd(const zb_embed_args* a, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K6
+ * zb_softmax_ce: label-smoothed cross-entropy over fp32 logits [rows, vocab]
+ * (util.label_smooth utils/util.py:88-103 + softmax_cross_entropy_with_logits_v2 + normaliser,
+ *  models/transformer.py:198-205).  Writes per-token nll (already minus the normalising constant) and,
+ * if d_logits != NULL, d_logits = (softmax - soft_label) * row_weight[row] in bf16 (in place allowed
+ * only when d_logits != logits).
+ */
+typedef struct {
+  const float* logits; int64_t ld;
+  const int32_t* labels;      /* [rows] */
+  const float* row_weight;    /* [rows] dLoss/dnll per token (mask / len / batch), may be NULL */
+  float* nll;                 /* [rows] */
+  float* lse;                 /* [rows] optional */
+  void* d_logits; int64_t ldd;/* bf16 [rows, ldd] or NULL */
+  int64_t rows; int32_t vocab;
+  float smooth;
+} zb_ce_args;
+int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ misc
+ * zb_colsum: out[n] += sum_m x[m,n] (bias gradients; tf.nn.bias_add grad).  x bf16, out fp32. */
+int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream);
+/* zb_cast_f32_bf16: bf16 compute copies of the fp32 master weights (utils/dtype.py:55-69). */
+int zb_cast_f32_bf16(const float* src, void* dst, int64_t n, zb_stream_t stream);
+int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K9
+ * zb_adam_tf: TensorFlow-semantics Adam on a flat fp32 arena (tf.train.AdamOptimizer, main.py:178-181):
+ *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps);  also refreshes the bf16 compute copy.
+ * grad_scale carries 1/world_size, 1/loss_scale and the clip_by_global_norm factor (utils/cycle.py:94-101).
+ * `scalars` (device, fp32[2]) = {lr_t (already bias-corrected), grad_scale}; read on the device so the
+ * step stays CUDA-graph capturable.
+ */
+typedef struct {
+  float* param; float* m; float* v; const float* grad; void* param_bf16;
+  int64_t n;
+  float beta1, beta2, eps;
+  const float* scalars;
+} zb_adam_args;
+int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream);
+/* zb_sumsq: out[0] += sum x^2 (tf.global_norm, utils/cycle.py:94). */
+int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K8
+ * zb_beam_step: one expansion step of search.beam_search (search.py:115-238) for a whole batch.
+ * See DESIGN.md for the state layout.  All scores fp32; indices int32; ties resolved to the lower
+ * flat index like tf.nn.top_k.
+ */
+typedef struct {
+  const float* logits;   /* [batch*beam, vocab] fp32 */
+  int32_t batch, beam, vocab;
+  int32_t time;          /* 0-based step */
+  int32_t eos_id, pad_id;
+  float alpha;           /* decode_alpha */
+  float temperature;     /* beam_search_temperature */
+  float inf_value;       /* dtype.inf() used to forbid EOS at t = 0 (search.py:152-155) */
+  const int32_t* max_len;/* [batch] int32: src_len + decode_length */
+  int32_t seq_cap;       /* allocated length of the seq buffers */
+  /* alive state, in/out */
+  int32_t* alive_seq;    /* [batch, beam, seq_cap]; positions [0, time] valid on entry */
+  float* alive_logp;     /* [batch, beam] */
+  float* alive_score;    /* [batch, beam] */
+  /* finished state, in/out */
+  int32_t* fin_seq;      /* [batch, beam, seq_cap] */
+  float* fin_score;      /* [batch, beam] */
+  int32_t* fin_flag;     /* [batch, beam] 0/1 */
+  /* out: which previous beam each new alive beam came from (for state reordering) */
+  int32_t* parent;       /* [batch, beam] */
+  /* scratch */
+  int32_t* tmp_seq;      /* [batch, 2*beam, seq_cap] */
+  float* ws;             /* workspace, zb_beam_step_ws_bytes() */
+} zb_beam_args;
+int64_t zb_beam_step_ws_bytes(int32_t batch, int32_t beam, int32_t vocab);
+int zb_beam_step(const zb_beam_args* a, zb_stream_t stream);
+
+/* zb_gather_rows: dst[r,:] = src[index[r],:] for bf16/fp32 rows (beam state reordering, search.py:205-209). */
+int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_bytes,
+                   zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K7
+ * zb_prefix_mean_{fwd,bwd}: y[b,t,:] = (sum_{s<=t} x[b,s,:]) / (t+1)   — Average Attention
+ * (models/transformer_aan.py:92-117 with the "aan" bias of func.py:390-398 for an all-ones mask),
+ * O(T d) scan instead of the reference's [T,T] matmul.  bwd: dx[b,s,:] = sum_{t>=s} dy[b,t,:]/(t+1).
+ */
+int zb_prefix_mean_fwd(const void* x, void* y, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream);
+int zb_prefix_mean_bwd(const void* dy, void* dx, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZERO_B200_H_ */

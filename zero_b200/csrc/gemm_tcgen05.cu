@@ -1,0 +1,435 @@
+// gemm_tcgen05.cu — K1: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor cores.
+//
+//   D[m,n] (+)= alpha * sum_k A(m,k) B(n,k)   (+bias[n]) (relu) (* (mask[m,n] > 0))
+//
+// Replaces every tf.matmul on Zero's Transformer path: func.linear (func.py:49,59), the tied-softmax
+// projection (models/transformer.py:194) and, as dgrad/wgrad, their tf.gradients (main.py:28).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer  : cp.async.bulk.tensor -> 128B-swizzled smem ring (A 128x64, B BNx64 bf16)
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma (128 x BN x 16), accumulators in TMEM,
+//                               tcgen05.commit releases smem slots / publishes the accumulator
+//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns) -> alpha/bias/relu/mask -> 16 B stores
+//                               or fp32 red.add (split-K / gradient accumulation)
+// Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
+// Operands may be K-major ([rows][k]) or MN-major ([k][rows]); both map onto SWIZZLE_128B canonical layouts,
+// so forward (x W), dgrad (dy W^T) and wgrad (x^T dy) all read the tensors where they lie — no transposes.
+#include "zb_common.h"
+#include "zb_ptx.cuh"
+
+namespace zb {
+
+struct GemmKParams {
+  int M, N, K;
+  int mt, nt, splits, kb_per_split, kb_total;
+  void* d;
+  long long ldd;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  long long ldmask;
+  float alpha;
+  int flags;
+  int d_f32;
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = kBM * kBK * 2;
+  static constexpr int B_BYTES = BN * kBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 128 / 256 / 512: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.mt * p.nt * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.mt;
+        const int n_blk = (tile / p.mt) % p.nt;
+        const int ks = tile / (p.mt * p.nt);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * kBM, n0 = n_blk * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * kBK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < kBM / 64; ++c)  // box {64 m, 64 k}
+              tma_load_2d(sa + c * 8192, &tma_a, &full_bar[stage], m0 + 64 * c, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)  // box {64 n, 64 k}
+              tma_load_2d(sb + c * 8192, &tma_b, &full_bar[stage], n0 + 64 * c, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // canonical SWIZZLE_128B layouts: K-major  -> 8-row groups every 1024 B (SBO), k-step = 32 B
+      //                                 MN-major -> 64-wide MN atoms every BK*128 B (LBO), 8-k groups every
+      //                                             1024 B (SBO), k-step (16 rows of 128 B) = 2048 B
+      constexpr uint32_t A_LBO = A_MN ? kBK * 128 : 0, A_KSTEP = A_MN ? 2048 : 32;
+      constexpr uint32_t B_LBO = B_MN ? kBK * 128 : 0, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ks = tile / (p.mt * p.nt);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk) {
+            const uint64_t da = umma_smem_desc(sa + kk * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = umma_smem_desc(sb + kk * B_KSTEP, B_LBO, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.mt;
+      const int n_blk = (tile / p.mt) % p.nt;
+      const int m0 = m_blk * kBM, n0 = n_blk * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        const bool full_cols = (col0 + 32 <= p.N);
+        if (p.flags & ZB_EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_cols || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.flags & ZB_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+        if (p.flags & ZB_EPI_RELU_MASK) {
+          const __nv_bfloat16* mrow = p.mask + static_cast<long long>(row) * p.ldmask + col0;
+          if (full_cols) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
+              const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                if (!(f.x > 0.f)) v[q * 8 + e * 2] = 0.f;
+                if (!(f.y > 0.f)) v[q * 8 + e * 2 + 1] = 0.f;
+              }
+            }
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
+          }
+        }
+        if (p.d_f32) {
+          float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+          if (p.flags & ZB_EPI_ACCUM) {
+            if (full_cols) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) red_add_v4(drow + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+              #pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(drow + j, v[j]);
+            }
+          } else {
+            if (full_cols) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(drow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+              #pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) drow[j] = v[j];
+            }
+          }
+        } else {
+          __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+          if (full_cols) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              reinterpret_cast<uint4*>(drow)[q] = o;
+            }
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) drow[j] = __float2bfloat16(v[j]);
+          }
+        }
+        }  // row_ok
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` elements; box {64, box1}; SWIZZLE_128B.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return ZB_ECUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu", (int)r, (unsigned long long)dim0,
+              (unsigned long long)dim1, (unsigned long long)ld);
+    return ZB_ECUDA;
+  }
+  return ZB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int grid, cudaStream_t st) {
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d): %s", GemmCfg<BN>::SMEM_BYTES, cudaGetErrorString(e));
+      return ZB_ECUDA;
+    }
+    attr_done = true;
+  }
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  return check_launch("zb_gemm");
+}
+
+template <int BN>
+static int dispatch_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p,
+                           int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, grid, st);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, grid, st);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, grid, st);
+  return launch<BN, true, true>(ta, tb, p, grid, st);
+}
+
+}  // namespace zb
+
+extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
+  using namespace zb;
+  ZB_REQUIRE(a && a->a && a->b && a->d, "zb_gemm: null pointer");
+  ZB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "zb_gemm: empty problem m=%lld n=%lld k=%lld", (long long)a->m,
+             (long long)a->n, (long long)a->k);
+  ZB_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "zb_gemm: lda/ldb must be multiples of 8 elements (TMA 16 B pitch)");
+  ZB_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->b) & 15) == 0,
+             "zb_gemm: operands must be 16-byte aligned");
+  ZB_REQUIRE(a->d_dtype == ZB_BF16 || a->d_dtype == ZB_F32, "zb_gemm: bad d_dtype");
+  const bool accum = a->flags & ZB_EPI_ACCUM;
+  ZB_REQUIRE(!accum || a->d_dtype == ZB_F32, "zb_gemm: ZB_EPI_ACCUM needs an fp32 destination");
+  ZB_REQUIRE(!(a->flags & ZB_EPI_BIAS) || a->bias, "zb_gemm: ZB_EPI_BIAS without bias");
+  ZB_REQUIRE(!(a->flags & ZB_EPI_RELU_MASK) || (a->mask && a->ldmask % 8 == 0 &&
+                                                (reinterpret_cast<uintptr_t>(a->mask) & 15) == 0),
+             "zb_gemm: ZB_EPI_RELU_MASK needs an aligned mask");
+  const int esz = a->d_dtype == ZB_F32 ? 4 : 2;
+  ZB_REQUIRE((a->ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0,
+             "zb_gemm: destination must be 16-byte aligned with a 16-byte pitch");
+  ZB_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31), "zb_gemm: dimension too large");
+
+  GemmKParams p;
+  p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
+  p.d = a->d; p.ldd = a->ldd; p.bias = a->bias;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
+  p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
+  p.kb_total = (p.K + kBK - 1) / kBK;
+  p.mt = (p.M + kBM - 1) / kBM;
+
+  const int sms = num_sms();
+  // Tile width: the widest BN whose tile count still fills the machine (wave quantisation dominates at the
+  // reference's 4096-token batches); 256 when there is plenty of work.
+  int bn = 256;
+  auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
+  if (p.N <= 64) bn = 64;
+  else if (p.N <= 128) bn = 128;
+  if (bn == 256 && tiles_for(256) < 2ll * sms) bn = 128;
+  if (bn == 128 && tiles_for(128) < sms && p.N > 64) bn = 64;
+  p.nt = (p.N + bn - 1) / bn;
+
+  int splits = a->split_k;
+  const long long tiles = (long long)p.mt * p.nt;
+  if (splits <= 0) {
+    splits = 1;
+    if (accum && tiles < sms) {
+      splits = (int)((sms + tiles - 1) / tiles);
+      // keep at least 4 k-blocks (256 k) per split so the pipeline has something to stream
+      int max_splits = p.kb_total / 4;
+      if (max_splits < 1) max_splits = 1;
+      if (splits > max_splits) splits = max_splits;
+    }
+  }
+  ZB_REQUIRE(splits == 1 || accum, "zb_gemm: split_k > 1 requires ZB_EPI_ACCUM");
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  CUtensorMap ta, tb;
+  int rc;
+  const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
+  if (!a_mn) rc = make_map(&ta, a->a, p.K, p.M, a->lda, kBM);
+  else rc = make_map(&ta, a->a, p.M, p.K, a->lda, kBK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tb, a->b, p.K, p.N, a->ldb, bn);
+  else rc = make_map(&tb, a->b, p.N, p.K, a->ldb, kBK);
+  if (rc) return rc;
+
+  const long long total = tiles * p.splits;
+  const int grid = (int)(total < sms ? total : sms);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return dispatch_layout<64>(a_mn, b_mn, ta, tb, p, grid, st);
+    case 128: return dispatch_layout<128>(a_mn, b_mn, ta, tb, p, grid, st);
+    default: return dispatch_layout<256>(a_mn, b_mn, ta, tb, p, grid, st);
+  }
+}
