@@ -1,0 +1,55 @@
+"""Pin oracle/zero_oracle.py to vectors produced by the reference's own code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import zero_oracle as zo
+from tests.golden_util import MODELS, load_golden
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_train_loss_grads_logits(name):
+    z, hp, variables, grads, vs, vt = load_golden(name)
+    c = zo.Cfg(hp, vs, vt)
+    assert set(zo.param_shapes(c).keys()) == set(variables.keys())
+    for k, shp in zo.param_shapes(c).items():
+        assert tuple(variables[k].shape) == tuple(shp), k
+    P = {k: v.clone().requires_grad_(True) for k, v in variables.items()}
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    loss, logits, per_sample, enc = zo.train_loss(c, P, src, tgt)
+    assert abs(float(loss) - float(z["loss"])) < 2e-5
+    np.testing.assert_allclose(enc["encodes"].detach().numpy(), z["encodes"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(logits.detach().numpy(), z["logits"], atol=1e-4, rtol=1e-5)
+    np.testing.assert_allclose(per_sample.detach().numpy(), z["per_sample_loss"], atol=2e-5, rtol=1e-5)
+    names = sorted(P)
+    gs = torch.autograd.grad(loss, [P[n] for n in names], allow_unused=True)
+    for n, g in zip(names, gs):
+        g = torch.zeros_like(P[n]) if g is None else g
+        np.testing.assert_allclose(g.numpy(), grads[n].numpy(), atol=2e-6, rtol=2e-4, err_msg=n)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_score_and_beam_search(name):
+    z, hp, variables, grads, vs, vt = load_golden(name)
+    c = zo.Cfg(hp, vs, vt)
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    with torch.no_grad():
+        sc = zo.score(c, variables, src, tgt)
+        np.testing.assert_allclose(sc.numpy(), z["score"], atol=2e-5, rtol=1e-5)
+        enc_fn, dec_fn = zo.make_infer_fns(c, variables)
+        steps = {}
+        out = zo.beam_search(c, src, enc_fn, dec_fn, logits_hook=lambda t, lg: steps.setdefault(t, lg.clone()))
+    # golden step_logits_0 is the cache_init dummy call; _1 is t = 0, _2 is t = 1 (search.py:56-77,141)
+    for t in (0, 1, 2):
+        np.testing.assert_allclose(steps[t].numpy(), z["step_logits_%d" % (t + 1)], atol=1e-4, rtol=1e-5)
+    assert out["steps"] + 1 == int(z["n_decode_calls"])
+    np.testing.assert_array_equal(out["seq"].numpy(), z["beam_seq"])  # bit-exact indices
+    np.testing.assert_allclose(out["score"].numpy(), z["beam_score"], atol=1e-5, rtol=1e-5)
+
+
+def test_adam_tf_matches_closed_form():
+    p, m, v, g = [torch.tensor([x]) for x in (1.0, 0.0, 0.0, 0.5)]
+    p1, m1, v1 = zo.adam_tf_step(p, m, v, g, 1, 0.1, 0.9, 0.98, 1e-8)
+    # first step: m = 0.05, v = 0.005, lr_t = 0.1*sqrt(0.02)/0.1
+    want = 1.0 - 0.1 * (0.02 ** 0.5) / 0.1 * 0.05 / (0.005 ** 0.5 + 1e-8)
+    assert abs(float(p1) - want) < 1e-6
