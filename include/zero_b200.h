@@ -104,6 +104,9 @@ typedef struct {
   const void* d_o; void* dq; void* dk; void* dv;
   int64_t lddo, lddq, lddk, lddv, bsdo, bsdq, bsdk, bsdv;
   float* d_rpr_k; float* d_rpr_v;     /* fp32 [2*max_rel+1, dh], accumulated */
+  float* delta;                       /* fp32 [batch, heads, lq] workspace: rowsum(dO * O) */
+  int32_t kv_group;                   /* >= 1: query batch b reads keys/values of batch b / kv_group (beams of one
+                                         sentence share the projected memory instead of tiling it, search.py:36-39) */
 } zb_attention_args;
 int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream);
 int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream);
@@ -111,9 +114,9 @@ int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream);
 /* ------------------------------------------------------------------------------------------------ K4
  * zb_add_ln_{fwd,bwd}: out = scale * (s - mean(s)) * rsqrt(var(s) + eps) + offset with s = x (+ y).
  * Replaces func.residual_fn + func.layer_norm (func.py:321-324, 289-303); biased variance, eps = 1e-8.
- * fwd saves mean / rstd (fp32 [rows]).  bwd returns ds (bf16, the gradient wrt both x and y),
- * optionally ds += extra (gradient arriving through the residual skip), and accumulates
- * dscale / doffset (fp32 [cols]).
+ * fwd saves mean / rstd (fp32 [rows]).  bwd takes the upstream gradient as d_out (+ d_out2: the gradient
+ * arriving through the next residual skip), returns ds (bf16, the gradient wrt both x and y) and
+ * accumulates dscale / doffset (fp32 [cols]).
  */
 typedef struct {
   const void* x; const void* y; /* y may be NULL */
@@ -122,7 +125,7 @@ typedef struct {
   int64_t rows, cols;
   float eps;
   /* backward */
-  const void* d_out; const void* s_hat_src; /* unused, reserved */
+  const void* d_out; const void* d_out2; /* d_out2 (optional) is added to d_out on read */
   void* ds; float* dscale; float* doffset;
 } zb_add_ln_args;
 int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream);
@@ -147,6 +150,7 @@ typedef struct {
   int32_t time;       /* >= 0: every row uses position `time` (cached decode); -1: position = l */
   float mult;
   const void* d_out; float* d_table; float* d_bias;
+  const void* d_out2; /* optional second addend of the upstream gradient */
 } zb_embed_args;
 int zb_embed_fwd(const zb_embed_args* a, zb_stream_t stream);
 int zb_embed_bwd(const zb_embed_args* a, zb_stream_t stream);
@@ -160,13 +164,15 @@ int zb_embed_bwd(const zb_embed_args* a, zb_stream_t stream);
  */
 typedef struct {
   const float* logits; int64_t ld;
-  const int32_t* labels;      /* [rows] */
-  const float* row_weight;    /* [rows] dLoss/dnll per token (mask / len / batch), may be NULL */
-  float* nll;                 /* [rows] */
-  float* lse;                 /* [rows] optional */
-  void* d_logits; int64_t ldd;/* bf16 [rows, ldd] or NULL */
-  int64_t rows; int32_t vocab;
+  const int32_t* labels;      /* [batch, seq_len] target ids; rows = batch * seq_len */
+  int32_t batch, seq_len;
+  float* nll;                 /* [rows] per-token smoothed CE minus the normaliser */
+  void* d_logits; int64_t ldd;/* bf16 [rows, ldd] or NULL.  Scaled by dLoss/dnll = (label != 0) / (len_b * batch) * loss_scale */
+  int32_t vocab;
   float smooth;
+  float loss_scale;
+  float* per_sample;          /* [batch] sum_t nll * mask / sum_t mask       (models/transformer.py:209) */
+  float* loss;                /* [1]     mean_b per_sample                   (models/transformer.py:210) */
 } zb_ce_args;
 int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream);
 
@@ -205,31 +211,35 @@ typedef struct {
   int32_t batch, beam, vocab;
   int32_t time;          /* 0-based step */
   int32_t eos_id, pad_id;
-  float alpha;           /* decode_alpha */
-  float temperature;     /* beam_search_temperature */
-  float inf_value;       /* dtype.inf() used to forbid EOS at t = 0 (search.py:152-155) */
-  const int32_t* max_len;/* [batch] int32: src_len + decode_length */
-  int32_t seq_cap;       /* allocated length of the seq buffers */
+  float temperature;     /* beam_search_temperature (search.py:147) */
+  float inf_value;       /* dtype.inf(): forbids EOS at t = 0 (search.py:152-155) */
+  float length_penalty;  /* ((5 + time + 1) / 6) ^ decode_alpha, computed by the host in fp32 (search.py:169) */
+  const int32_t* max_len;/* [batch] int(src_len + decode_length) (search.py:33,195) */
+  const float* max_penalty; /* [batch] ((5 + max_len) / 6) ^ alpha (search.py:95-96) */
+  int32_t seq_cap;       /* allocated length of every sequence row; needs time + 2 <= seq_cap */
   /* alive state, in/out */
-  int32_t* alive_seq;    /* [batch, beam, seq_cap]; positions [0, time] valid on entry */
+  int32_t* alive_seq;    /* [batch, beam, seq_cap]; positions [0, time] valid on entry ([0] = pad/BOS) */
   float* alive_logp;     /* [batch, beam] */
   float* alive_score;    /* [batch, beam] */
   /* finished state, in/out */
   int32_t* fin_seq;      /* [batch, beam, seq_cap] */
   float* fin_score;      /* [batch, beam] */
   int32_t* fin_flag;     /* [batch, beam] 0/1 */
-  /* out: which previous beam each new alive beam came from (for state reordering) */
-  int32_t* parent;       /* [batch, beam] */
+  /* out: flat row (b * beam + previous beam) each new alive beam continues, for state reordering */
+  int32_t* parent;       /* [batch * beam] */
   /* scratch */
-  int32_t* tmp_seq;      /* [batch, 2*beam, seq_cap] */
-  float* ws;             /* workspace, zb_beam_step_ws_bytes() */
+  int32_t* tmp_seq;      /* [batch, 3 * beam, seq_cap] */
+  /* loop control: zb_beam_cond writes active[0] = search.py:85-113's _not_finished(time); zb_beam_step is a
+   * no-op when active[0] == 0, so the host may poll the flag every few steps without changing the result */
+  int32_t* active;       /* [1] device */
 } zb_beam_args;
-int64_t zb_beam_step_ws_bytes(int32_t batch, int32_t beam, int32_t vocab);
+int zb_beam_cond(const zb_beam_args* a, zb_stream_t stream);
 int zb_beam_step(const zb_beam_args* a, zb_stream_t stream);
 
-/* zb_gather_rows: dst[r,:] = src[index[r],:] for bf16/fp32 rows (beam state reordering, search.py:205-209). */
+/* zb_gather_rows: dst[r, :row_bytes] = src[index[r], :row_bytes], rows `pitch_bytes` apart in both buffers
+ * (beam state reordering, search.py:205-209; only the filled prefix of each cache row is moved). */
 int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_bytes,
-                   zb_stream_t stream);
+                   int64_t pitch_bytes, zb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ K7
  * zb_prefix_mean_{fwd,bwd}: y[b,t,:] = (sum_{s<=t} x[b,s,:]) / (t+1)   — Average Attention

@@ -1,0 +1,342 @@
+"""Per-kernel parity on the GPU, through the C ABI, against plain torch fp32 restatements of the same op
+(inputs rounded to bf16 first so the comparison isolates the kernel's own arithmetic)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def dev():
+    return torch.device("cuda")
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(bf16).to(dev())
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (200, 136, 72), (4096, 1536, 512), (1000, 1000, 520)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+def test_gemm_layouts(m, n, k, a_mn, b_mn):
+    from zero_b200 import ops
+    A = rnd(m, k, seed=1)
+    B = rnd(n, k, seed=2)
+    a_st = A.t().contiguous() if a_mn else A
+    b_st = B.t().contiguous() if b_mn else B
+    # pad pitches to multiples of 8 elements
+    def pad(t):
+        c = (t.shape[1] + 7) // 8 * 8
+        buf = torch.zeros(t.shape[0], c, dtype=t.dtype, device=t.device)
+        buf[:, :t.shape[1]] = t
+        return buf[:, :t.shape[1]]
+    a_st, b_st = pad(a_st), pad(b_st)
+    out = pad(torch.zeros(m, n, dtype=f32, device=dev()))
+    ops.gemm(a_st, b_st, out, a_mn, b_mn, m=m, n=n, k=k)
+    ref = A.float() @ B.float().t()
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
+
+
+def test_gemm_epilogues_and_splitk():
+    from zero_b200 import ops
+    m, n, k = 512, 1536, 4096
+    x, dy = rnd(k, m, seed=3), rnd(k, n, seed=4)
+    acc = torch.randn(m, n, device=dev())
+    want = acc + x.float().t() @ dy.float()
+    ops.linear_wgrad(x, dy, acc)
+    torch.testing.assert_close(acc, want, atol=2e-2, rtol=2e-3)
+    # bias + relu, bf16 out
+    x2, w, b = rnd(300, 512, seed=5), rnd(512, 2048, scale=0.05, seed=6), torch.randn(2048, device=dev())
+    out = torch.empty(300, 2048, dtype=bf16, device=dev())
+    ops.linear_fwd(x2, w, b, out, relu=True)
+    ref = torch.relu(x2.float() @ w.float() + b)
+    torch.testing.assert_close(out.float(), ref, atol=3e-2, rtol=2e-2)
+    # relu-masked dgrad
+    dh = torch.empty(300, 512, dtype=bf16, device=dev())
+    mask = rnd(300, 512, seed=7)
+    ops.linear_dgrad(out, w, dh, relu_mask=mask)  # dh = (dy @ W^T) * (mask > 0), dy := out
+    ref2 = (out.float() @ w.float().t()) * (mask.float() > 0)
+    torch.testing.assert_close(dh.float(), ref2, atol=0.15, rtol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ add + LN
+@pytest.mark.parametrize("rows,cols", [(37, 64), (4096, 512), (100, 1024)])
+def test_add_ln_fwd_bwd(rows, cols):
+    from zero_b200 import ops
+    x, y = rnd(rows, cols, seed=1), rnd(rows, cols, seed=2)
+    scale = (1 + 0.1 * torch.randn(cols)).to(dev())
+    offset = (0.1 * torch.randn(cols)).to(dev())
+    out = torch.empty_like(x)
+    mean = torch.empty(rows, device=dev())
+    rstd = torch.empty(rows, device=dev())
+    ops.add_ln_fwd(x, y, out, scale, offset, mean, rstd, 1e-8)
+    xr = (x.float() + y.float()).requires_grad_(True)
+    sc, of = scale.clone().requires_grad_(True), offset.clone().requires_grad_(True)
+    mu = xr.mean(-1, keepdim=True)
+    var = ((xr - mu) ** 2).mean(-1, keepdim=True)
+    ref = sc * (xr - mu) * torch.rsqrt(var + 1e-8) + of
+    torch.testing.assert_close(out.float(), ref.detach(), atol=2e-2, rtol=2e-2)
+    d1, d2 = rnd(rows, cols, seed=3), rnd(rows, cols, seed=4)
+    ref.backward(d1.float() + d2.float())
+    ds = torch.empty_like(x)
+    dscale = torch.zeros(cols, device=dev())
+    doffset = torch.zeros(cols, device=dev())
+    ops.add_ln_bwd(x, y, d1, d2, mean, rstd, scale, ds, dscale, doffset)
+    torch.testing.assert_close(ds.float(), xr.grad, atol=3e-2, rtol=2e-2)
+    torch.testing.assert_close(dscale, sc.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
+    torch.testing.assert_close(doffset, of.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ embedding
+def test_embed_fwd_bwd():
+    from oracle import zero_oracle as zo
+    from zero_b200 import ops
+    V, d, B, Lq = 96, 64, 3, 7
+    table = rnd(V, d, seed=1)
+    bias = (0.1 * torch.randn(d)).to(dev())
+    ids = torch.randint(0, V, (B, Lq), dtype=torch.int32, device=dev())
+    for shift in (0, 1):
+        out = torch.empty(B, Lq, d, dtype=bf16, device=dev())
+        ops.embed_fwd(ids, table, bias, out, mult=d ** 0.5, shift=shift)
+        x = table.float()[ids.long()] * d ** 0.5 + bias
+        if shift:
+            x = torch.nn.functional.pad(x, (0, 0, 1, 0))[:, :-1]
+        ref = x + zo.timing_signal(Lq, d, torch.float32).to(dev())
+        torch.testing.assert_close(out.float(), ref, atol=3e-2, rtol=2e-2)
+        d_out, d_out2 = rnd(B, Lq, d, seed=5), rnd(B, Lq, d, seed=6)
+        d_table = torch.zeros(V, d, device=dev())
+        d_bias = torch.zeros(d, device=dev())
+        ops.embed_bwd(ids, d_out, d_table, d_bias, mult=d ** 0.5, shift=shift, d_out2=d_out2)
+        g = (d_out.float() + d_out2.float())
+        if shift:
+            g = g[:, 1:]
+            idx = ids[:, :-1]
+        else:
+            idx = ids
+        want_t = torch.zeros(V, d, device=dev()).index_add_(0, idx.reshape(-1).long(), g.reshape(-1, d) * d ** 0.5)
+        torch.testing.assert_close(d_table, want_t, atol=2e-2, rtol=1e-3)
+        torch.testing.assert_close(d_bias, g.reshape(-1, d).sum(0), atol=2e-2, rtol=1e-3)
+    # cached decode: every row at position `time`, zeroed when all ids are pad (models/transformer.py:113-117)
+    ids0 = torch.zeros(4, 1, dtype=torch.int32, device=dev())
+    out = torch.empty(4, 1, d, dtype=bf16, device=dev())
+    ops.embed_fwd(ids0, table, bias, out, mult=d ** 0.5, zero_if_all_pad=True, time=5)
+    ref = zo.timing_signal(1, d, torch.float32, time=5).to(dev()).expand(4, 1, d)
+    torch.testing.assert_close(out.float(), ref, atol=1e-2, rtol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ CE
+@pytest.mark.parametrize("V", [200, 32000])
+def test_softmax_ce(V):
+    from oracle import zero_oracle as zo
+    from zero_b200 import ops
+    B, T = 4, 9
+    logits = (torch.randn(B * T, V) * 2).to(dev())
+    labels = torch.randint(3, V, (B, T), dtype=torch.int32, device=dev())
+    labels[1, 5:] = 0
+    labels[2, 2:] = 0
+    nll = torch.empty(B * T, device=dev())
+    per = torch.empty(B, device=dev())
+    loss = torch.empty(1, device=dev())
+    dl = torch.empty(B * T, V, dtype=bf16, device=dev())
+    ops.softmax_ce(logits, labels, nll, 0.1, d_logits=dl, per_sample=per, loss=loss)
+    lg = logits.clone().requires_grad_(True)
+    ce = zo.smoothed_ce(lg, labels.reshape(-1), 0.1).reshape(B, T)
+    m = (labels != 0).float()
+    ps = (ce * m).sum(-1) / m.sum(-1)
+    ref_loss = ps.mean()
+    ref_loss.backward()
+    torch.testing.assert_close(nll, ce.detach().reshape(-1), atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(per, ps.detach(), atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(loss[0], ref_loss.detach(), atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(dl.float(), lg.grad, atol=2e-4, rtol=1e-2)
+    # score mode: no smoothing, no gradient
+    ops.softmax_ce(logits, labels, nll, 0.0)
+    ce0 = zo.smoothed_ce(logits, labels.reshape(-1), 0.0)
+    torch.testing.assert_close(nll, ce0, atol=2e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, heads, key_len, causal, q_off, inf, ek, ev, max_rel, relu):
+    from oracle import zero_oracle as zo
+    B, Lq, D = q.shape
+    Lk = k.shape[1]
+    dh = D // heads
+    qh, kh, vh = [zo.heads_split(t, heads) for t in (q, k, v)]
+    qh = qh * dh ** -0.5
+    logits = qh @ kh.transpose(-1, -2)
+    if ek is not None:
+        idx = zo.rel_index(Lq, Lk, max_rel, q_off).to(q.device)
+        logits = logits + torch.einsum("bhid,ijd->bhij", qh, ek[idx])
+    bias = torch.zeros(B, 1, Lq, Lk, device=q.device)
+    if key_len is not None:
+        pad = torch.arange(Lk, device=q.device)[None, :] >= key_len[:, None].long()
+        bias = bias + pad[:, None, None, :].float() * -inf
+    if causal:
+        i = torch.arange(Lq, device=q.device)[:, None] + q_off
+        j = torch.arange(Lk, device=q.device)[None, :]
+        bias = bias + (j > i).float()[None, None] * -inf
+    if relu:
+        w = torch.relu(logits * (bias == 0).float())
+    else:
+        w = torch.softmax(logits + bias, -1)
+    o = w @ vh
+    if ev is not None:
+        o = o + torch.einsum("bhij,ijd->bhid", w, ev[idx])
+    return zo.heads_merge(o)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=3, h=2, Lq=11, Lk=11, dh=64, causal=False, klen=True),
+    dict(B=2, h=4, Lq=9, Lk=9, dh=32, causal=True, klen=False),
+    dict(B=2, h=4, Lq=40, Lk=70, dh=16, causal=False, klen=True),
+    dict(B=2, h=2, Lq=33, Lk=33, dh=32, causal=True, klen=False, rpr=4),
+    dict(B=2, h=2, Lq=20, Lk=45, dh=64, causal=False, klen=True, rpr=16),
+    dict(B=2, h=2, Lq=17, Lk=17, dh=32, causal=True, klen=False, relu=True),
+    dict(B=2, h=2, Lq=12, Lk=30, dh=64, causal=False, klen=True, relu=True),
+    dict(B=4, h=8, Lq=64, Lk=64, dh=64, causal=False, klen=True),
+    dict(B=4, h=8, Lq=64, Lk=64, dh=64, causal=True, klen=False),
+    dict(B=2, h=8, Lq=128, Lk=128, dh=64, causal=True, klen=False),
+])
+def test_attention_fwd_bwd(cfg):
+    from zero_b200 import ops
+    B, h, Lq, Lk, dh = cfg["B"], cfg["h"], cfg["Lq"], cfg["Lk"], cfg["dh"]
+    D = h * dh
+    rpr, relu = cfg.get("rpr", 0), cfg.get("relu", False)
+    q, k, v = rnd(B, Lq, D, seed=1), rnd(B, Lk, D, seed=2), rnd(B, Lk, D, seed=3)
+    key_len = None
+    if cfg["klen"]:
+        key_len = torch.randint(1, Lk + 1, (B,), dtype=torch.int32, device=dev())
+        key_len[0] = Lk
+    ek = ev = None
+    if rpr:
+        ek, ev = rnd(2 * rpr + 1, dh, scale=0.5, seed=4), rnd(2 * rpr + 1, dh, scale=0.5, seed=5)
+    o = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+    lse = torch.empty(B, h, Lq, device=dev())
+    a = ops.attention_args(q, k, v, o, h, key_len=key_len, causal=cfg["causal"], lse=lse, rpr_k=ek, rpr_v=ev,
+                           max_rel=rpr, relu_attn=relu)
+    ops.attention_fwd(a)
+    leaves = [t.float().requires_grad_(True) for t in (q, k, v)]
+    ekf = ek.float().requires_grad_(True) if rpr else None
+    evf = ev.float().requires_grad_(True) if rpr else None
+    ref = _attn_ref(leaves[0], leaves[1], leaves[2], h, key_len, cfg["causal"], 0, 1e8, ekf, evf, rpr, relu)
+    torch.testing.assert_close(o.float(), ref.detach(), atol=3e-2, rtol=3e-2)
+    d_o = rnd(B, Lq, D, seed=6)
+    ref.backward(d_o.float())
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(B, h, Lq, device=dev())
+    dek = torch.zeros(2 * rpr + 1, dh, device=dev()) if rpr else None
+    dev_ = torch.zeros(2 * rpr + 1, dh, device=dev()) if rpr else None
+    ops.attention_bwd(a, d_o, dq, dk, dv, delta, dek, dev_)
+    tol = dict(atol=6e-2, rtol=5e-2)
+    torch.testing.assert_close(dq.float(), leaves[0].grad, **tol)
+    torch.testing.assert_close(dk.float(), leaves[1].grad, **tol)
+    torch.testing.assert_close(dv.float(), leaves[2].grad, **tol)
+    if rpr:
+        torch.testing.assert_close(dek, ekf.grad, atol=0.15, rtol=5e-2)
+        torch.testing.assert_close(dev_, evf.grad, atol=0.15, rtol=5e-2)
+
+
+def test_attention_cached_decode_step():
+    """lq = 1 against a growing key cache, kv_group sharing of per-sentence memory."""
+    from zero_b200 import ops
+    B, K, h, dh, S = 3, 4, 2, 32, 13
+    D = h * dh
+    q = rnd(B * K, 1, D, seed=1)
+    mem_k, mem_v = rnd(B, S, D, seed=2), rnd(B, S, D, seed=3)
+    key_len = torch.tensor([13, 7, 2], dtype=torch.int32, device=dev())
+    o = torch.empty(B * K, 1, D, dtype=bf16, device=dev())
+    a = ops.attention_args(q, mem_k, mem_v, o, h, key_len=key_len, kv_group=K)
+    ops.attention_fwd(a)
+    ref = _attn_ref(q.float(), mem_k.float().repeat_interleave(K, 0), mem_v.float().repeat_interleave(K, 0), h,
+                    key_len.repeat_interleave(K), False, 0, 1e8, None, None, 0, False)
+    torch.testing.assert_close(o.float(), ref, atol=3e-2, rtol=3e-2)
+
+
+# ------------------------------------------------------------------------------------------------ optimizer / misc
+def test_adam_tf_and_sumsq_and_colsum():
+    from oracle import zero_oracle as zo
+    from zero_b200 import ops
+    n = 10007
+    p, g = torch.randn(n, device=dev()), torch.randn(n, device=dev())
+    m, v = torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    pb = torch.empty(n, dtype=bf16, device=dev())
+    p_ref, m_ref, v_ref = p.clone(), m.clone(), v.clone()
+    for step in (1, 2, 3):
+        lr_t = 0.01 * math.sqrt(1 - 0.98 ** step) / (1 - 0.9 ** step)
+        sc = torch.tensor([lr_t, 0.5], device=dev())
+        ops.adam_tf(p, m, v, g, pb, 0.9, 0.98, 1e-8, sc)
+        p_ref, m_ref, v_ref = zo.adam_tf_step(p_ref, m_ref, v_ref, g * 0.5, step, 0.01, 0.9, 0.98, 1e-8)
+    torch.testing.assert_close(p, p_ref, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(pb.float(), p_ref, atol=1e-2, rtol=1e-2)
+    out = torch.zeros(1, device=dev())
+    ops.sumsq(g, out)
+    torch.testing.assert_close(out[0], (g * g).sum(), rtol=1e-4, atol=1e-3)
+    x = rnd(777, 130, seed=9)
+    cs = torch.zeros(130, device=dev())
+    ops.colsum(x, cs)
+    torch.testing.assert_close(cs, x.float().sum(0), atol=5e-2, rtol=1e-3)
+
+
+def test_prefix_mean_and_gather_rows():
+    from zero_b200 import ops
+    x = rnd(3, 9, 64, seed=1)
+    y = torch.empty_like(x)
+    ops.prefix_mean_fwd(x, y)
+    ref = torch.cumsum(x.float(), 1) / torch.arange(1, 10, device=dev())[None, :, None]
+    torch.testing.assert_close(y.float(), ref, atol=2e-2, rtol=2e-2)
+    dy = rnd(3, 9, 64, seed=2)
+    dx = torch.empty_like(x)
+    ops.prefix_mean_bwd(dy, dx)
+    w = dy.float() / torch.arange(1, 10, device=dev())[None, :, None]
+    ref_dx = torch.flip(torch.cumsum(torch.flip(w, [1]), 1), [1])
+    torch.testing.assert_close(dx.float(), ref_dx, atol=2e-2, rtol=2e-2)
+    src = rnd(8, 5, 64, seed=3)
+    idx = torch.tensor([3, 3, 0, 7, 1, 1, 2, 6], dtype=torch.int32, device=dev())
+    dst = torch.zeros_like(src)
+    ops.gather_rows(src, idx, dst, row_elems=2 * 64)
+    assert torch.equal(dst[:, :2], src[idx.long()][:, :2]) and float(dst[:, 2:].abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ beam step
+def test_beam_step_matches_oracle_step_for_step():
+    """K8 on the oracle's own logits: indices must be bit-exact (search.py:141-228)."""
+    from oracle import zero_oracle as zo
+    from zero_b200.search import BeamState
+    torch.manual_seed(0)
+    B, K, V, steps = 5, 4, 208, 9
+
+    class C:
+        beam, alpha, decode_length, temperature, inf = K, 0.6, 6, 1.0, 1e8
+    src = torch.randint(3, 50, (B, 7))
+    src[1, 4:] = 0
+    src[3, 2:] = 0
+    logits_seq = [torch.randn(B * K, V) * 3 for _ in range(32)]
+    # make EOS likely sometimes so the finished-merge path is exercised
+    for t, lg in enumerate(logits_seq):
+        lg[:, 2] += 2.0 if t % 3 == 2 else -1.0
+
+    calls = {"n": 0}
+
+    def enc_fn(source):
+        return {"dummy": torch.zeros(source.shape[0], 1)}
+
+    def dec_fn(tok, state, time):
+        lg = logits_seq[calls["n"] - 1] if calls["n"] > 0 else logits_seq[0]
+        calls["n"] += 1
+        return lg, {"dummy": state["dummy"], "decoder": {"state": {}}}
+
+    want = zo.beam_search(C, src, enc_fn, dec_fn)
+    st = BeamState(B, K, V, src.to(dev()), C.decode_length, C.alpha, C.temperature, C.inf, dev())
+    t = 0
+    while st.not_finished(t):
+        st.step(logits_seq[t].to(dev()), t)
+        t += 1
+    got = st.result()
+    assert t == want["steps"]
+    np.testing.assert_array_equal(got["seq"].cpu().numpy(), want["seq"].numpy())
+    np.testing.assert_allclose(got["score"].cpu().numpy(), want["score"].numpy(), rtol=1e-5, atol=1e-5)

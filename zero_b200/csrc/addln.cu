@@ -1,0 +1,249 @@
+// addln.cu — K4: fused residual-add + LayerNorm, forward and backward (HBM-bound).
+// Replaces func.residual_fn + func.layer_norm (func.py:321-324, 289-303): s = x + y,
+// out = scale * (s - mean) * rsqrt(var + eps) + offset, biased variance, eps inside the rsqrt.
+// One warp per row, 16-byte vector loads, the row lives in registers (cols <= 2048, cols % 8 == 0).
+// Algorithmic bytes / row (bf16): fwd 3 * cols * 2 (read x, y; write out); bwd 5 * cols * 2.
+#include "zb_common.h"
+#include "zb_ptx.cuh"
+
+namespace zb {
+
+constexpr int kLnWarps = 8;
+constexpr int kLnMaxVec = 8;  // 8 vectors of 8 bf16 per lane -> cols <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = unpack_bf16x2(w[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                  __nv_bfloat16* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
+                  const float* __restrict__ scale, const float* __restrict__ offset, long long rows, int cols,
+                  float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
+    float s[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        load8(x + row * cols + v * 8, s[i]);
+        if (y) {
+          float t[8];
+          load8(y + row * cols + v * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[i][e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += s[i][e];
+      }
+    }
+    const float mu = warp_sum(sum) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = s[i][e] - mu;
+          sq += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(sq) / cols + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __ldg(scale + v * 8 + e) * (s[i][e] - mu) * rs + __ldg(offset + v * 8 + e);
+        store8(out + row * cols + v * 8, o);
+      }
+    }
+  }
+}
+
+// ds = rstd * (g - mean(g) - s_hat * mean(g * s_hat)), g = d_out * scale;  dscale += sum_rows d_out * s_hat;
+// doffset += sum_rows d_out.  d_out may arrive as two addends (gradient through the next sublayer + the
+// gradient through the residual skip), which fuses the "x + y" gradient fan-in of func.residual_fn.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                  const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                  __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale, float* __restrict__ doffset,
+                  long long rows, int cols) {
+  extern __shared__ float red[];  // [kLnWarps][cols] x 2
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  float acc_s[NV][8], acc_o[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc_s[i][e] = acc_o[i][e] = 0.f;
+
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float sh[NV][8], g[NV][8];
+    float sg = 0.f, sgs = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        load8(x + row * cols + v * 8, sh[i]);
+        if (y) {
+          float t[8];
+          load8(y + row * cols + v * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sh[i][e] += t[e];
+        }
+        float d[8];
+        load8(d_out + row * cols + v * 8, d);
+        if (d_out2) {
+          float t[8];
+          load8(d_out2 + row * cols + v * 8, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] += t[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sh[i][e] = (sh[i][e] - mu) * rs;
+          acc_s[i][e] += d[e] * sh[i][e];
+          acc_o[i][e] += d[e];
+          g[i][e] = d[e] * __ldg(scale + v * 8 + e);
+          sg += g[i][e];
+          sgs += g[i][e] * sh[i][e];
+        }
+      }
+    }
+    sg = warp_sum(sg) / cols;
+    sgs = warp_sum(sgs) / cols;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (g[i][e] - sg - sh[i][e] * sgs);
+        store8(ds + row * cols + v * 8, o);
+      }
+    }
+  }
+  // block-level column reduction, then one atomic per column per block
+  float* rs_ = red;
+  float* ro_ = red + kLnWarps * cols;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        rs_[warp * cols + v * 8 + e] = acc_s[i][e];
+        ro_[warp * cols + v * 8 + e] = acc_o[i][e];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) {
+      a += rs_[w * cols + c];
+      b += ro_[w * cols + c];
+    }
+    atomicAdd(dscale + c, a);
+    atomicAdd(doffset + c, b);
+  }
+}
+
+static int check(const zb_add_ln_args* a, const char* who) {
+  ZB_REQUIRE(a && a->x && a->scale, "%s: null pointer", who);
+  ZB_REQUIRE(a->rows >= 0 && a->cols > 0 && a->cols % 8 == 0 && a->cols <= 8 * 32 * kLnMaxVec,
+             "%s: cols must be a multiple of 8 and <= %d (got %lld)", who, 8 * 32 * kLnMaxVec, (long long)a->cols);
+  return ZB_OK;
+}
+
+}  // namespace zb
+
+#define ZB_LN_DISPATCH(NVEC, CALL)          \
+  do {                                      \
+    if (NVEC <= 1) { CALL(1); }             \
+    else if (NVEC <= 2) { CALL(2); }        \
+    else if (NVEC <= 4) { CALL(4); }        \
+    else { CALL(8); }                       \
+  } while (0)
+
+extern "C" int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream) {
+  using namespace zb;
+  int rc = check(a, "zb_add_ln_fwd");
+  if (rc) return rc;
+  ZB_REQUIRE(a->out && a->offset, "zb_add_ln_fwd: null pointer");
+  if (a->rows == 0) return ZB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nv = (int)((a->cols / 8 + 31) / 32);
+  long long blocks = (a->rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+#define CALL(N)                                                                                              \
+  add_ln_fwd_kernel<N><<<(int)blocks, kLnWarps * 32, 0, st>>>(                                               \
+      (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (__nv_bfloat16*)a->out, a->mean, a->rstd, a->scale, \
+      a->offset, a->rows, (int)a->cols, a->eps)
+  ZB_LN_DISPATCH(nv, CALL);
+#undef CALL
+  return check_launch("zb_add_ln_fwd");
+}
+
+extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
+  using namespace zb;
+  int rc = check(a, "zb_add_ln_bwd");
+  if (rc) return rc;
+  ZB_REQUIRE(a->d_out && a->ds && a->dscale && a->doffset && a->mean && a->rstd, "zb_add_ln_bwd: null pointer");
+  if (a->rows == 0) return ZB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nv = (int)((a->cols / 8 + 31) / 32);
+  long long blocks = (a->rows + kLnWarps - 1) / kLnWarps;
+  const long long cap = (long long)num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (size_t)2 * kLnWarps * a->cols * sizeof(float);
+#define CALL(N)                                                                                              \
+  do {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                    \
+      cudaFuncSetAttribute(add_ln_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    add_ln_bwd_kernel<N><<<(int)blocks, kLnWarps * 32, smem, st>>>(                                          \
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
+        (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
+        a->doffset, a->rows, (int)a->cols);                                                                  \
+  } while (0)
+  ZB_LN_DISPATCH(nv, CALL);
+#undef CALL
+  return check_launch("zb_add_ln_bwd");
+}

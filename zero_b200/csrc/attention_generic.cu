@@ -1,0 +1,465 @@
+// attention_generic.cu — K2/K3 (feature-complete path): fused scaled-dot attention forward / backward with every
+// variant Zero's Transformer family uses, logits never leaving the SM:
+//   * softmax attention with additive -inf masks from key lengths / causal index  (func.py:218-256, 372-388)
+//   * Shaw relative-position terms on keys and values, bucket = clip(i - j, -k, k) + k  (modules/rpr.py:10-75)
+//   * ReLA: relu(logits * keep) instead of softmax                                 (modules/rela.py:52-75)
+//   * cached decode (lq = 1, q_offset = time)                                       (func.py:199-205)
+// CUDA-core (fp32 FMA) implementation: one warp per query row (fwd, dq) or key row (dk/dv), 32-wide key/query
+// tiles staged in shared memory, online softmax.  attention_mma.cu holds the tensor-core fast path for the
+// plain softmax case; this file is the path used when rpr / ReLA / odd head sizes are requested.
+#include <math.h>
+
+#include "zb_common.h"
+#include "zb_ptx.cuh"
+
+namespace zb {
+
+constexpr int kAttnWarps = 8;
+
+struct AttnP {
+  const __nv_bfloat16 *q, *k, *v, *d_o, *rpr_k, *rpr_v;
+  __nv_bfloat16 *o, *dq, *dk, *dv;
+  const __nv_bfloat16* o_in;
+  long long ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso;
+  long long lddo, lddq, lddk, lddv, bsdo, bsdq, bsdk, bsdv;
+  int batch, heads, lq, lk;
+  const int32_t* key_len;
+  int causal, q_offset, max_rel, relu_attn, kv_group;
+  float scale, inf_value;
+  float *lse, *delta, *d_rpr_k, *d_rpr_v;
+};
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int rel_bucket(int i_abs, int j, int R) {
+  int d = i_abs - j;
+  d = d < -R ? -R : (d > R ? R : d);
+  return d + R;
+}
+
+// cooperative load of `rows` x DH bf16 (row pitch ld) into fp32 smem [32][DH+1]; rows beyond `valid` are zeroed
+template <int DH>
+__device__ __forceinline__ void load_tile(float (*dst)[DH + 1], const __nv_bfloat16* src, long long ld, int valid,
+                                          float mul) {
+  for (int idx = threadIdx.x; idx < 32 * DH; idx += kAttnWarps * 32) {
+    const int r = idx / DH, d = idx % DH;
+    dst[r][d] = r < valid ? __bfloat162float(src[(long long)r * ld + d]) * mul : 0.f;
+  }
+}
+
+template <int DH>
+struct Smem {
+  float a[32][DH + 1];
+  float b[32][DH + 1];
+  float aux0[32];
+  float aux1[32];
+};
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int DH>
+__global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_generic(const AttnP p) {
+  constexpr int ND = (DH + 31) / 32;
+  extern __shared__ float smem_f[];
+  Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
+  const int NB = 2 * p.max_rel + 1;
+  float(*ek)[DH + 1] = reinterpret_cast<float(*)[DH + 1]>(smem_f + sizeof(Smem<DH>) / 4);
+  float(*ev)[DH + 1] = ek + NB;
+  const bool rpr = p.rpr_k != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int i = blockIdx.x * kAttnWarps + warp;
+  const bool active = i < p.lq;
+  const int kl = p.key_len ? p.key_len[b / p.kv_group] : p.lk;
+  if (rpr) {
+    for (int idx = threadIdx.x; idx < NB * DH; idx += blockDim.x) {
+      ek[idx / DH][idx % DH] = __bfloat162float(p.rpr_k[idx]);
+      ev[idx / DH][idx % DH] = __bfloat162float(p.rpr_v[idx]);
+    }
+  }
+  float qr[DH];
+  if (active) {
+    const __nv_bfloat16* qp = p.q + (long long)b * p.bsq + (long long)i * p.ldq + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) qr[d] = __bfloat162float(qp[d]) * p.scale;
+  }
+  float m = -INFINITY, l = 0.f, o[ND];
+#pragma unroll
+  for (int dd = 0; dd < ND; ++dd) o[dd] = 0.f;
+  const int i_abs = i + p.q_offset;
+
+  for (int kt = 0; kt < p.lk; kt += 32) {
+    __syncthreads();
+    const int valid_rows = min(32, p.lk - kt);
+    load_tile<DH>(sm.a, p.k + (long long)(b / p.kv_group) * p.bsk + (long long)kt * p.ldk + h * DH, p.ldk, valid_rows, 1.f);
+    load_tile<DH>(sm.b, p.v + (long long)(b / p.kv_group) * p.bsv + (long long)kt * p.ldv + h * DH, p.ldv, valid_rows, 1.f);
+    __syncthreads();
+    if (!active) continue;
+    const int j = kt + lane;
+    const bool inb = j < p.lk;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s += qr[d] * sm.a[lane][d];
+    int bucket = 0;
+    if (rpr) {
+      bucket = rel_bucket(i_abs, j, p.max_rel);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) s += qr[d] * ek[bucket][d];
+    }
+    const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
+    float pj;
+    if (p.relu_attn) {
+      pj = valid ? fmaxf(s, 0.f) : 0.f;
+    } else {
+      s = inb ? (valid ? s : s - p.inf_value) : -INFINITY;
+      const float m_new = fmaxf(m, wmax(s));
+      pj = inb ? __expf(s - m_new) : 0.f;
+      const float corr = __expf(m - m_new);
+      l = l * corr + wsum(pj);
+      m = m_new;
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) o[dd] *= corr;
+    }
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      const float pv = __shfl_sync(0xffffffffu, pj, jj);
+      const int bk = __shfl_sync(0xffffffffu, bucket, jj);
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        const int d = lane + 32 * dd;
+        if (d < DH) {
+          float vv = sm.b[jj][d];
+          if (rpr) vv += ev[bk][d];
+          o[dd] += pv * vv;
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const float inv = p.relu_attn ? 1.f : 1.f / l;
+  __nv_bfloat16* op = p.o + (long long)b * p.bso + (long long)i * p.ldo + h * DH;
+#pragma unroll
+  for (int dd = 0; dd < ND; ++dd) {
+    const int d = lane + 32 * dd;
+    if (d < DH) op[d] = __float2bfloat16(o[dd] * inv);
+  }
+  if (lane == 0 && p.lse) p.lse[((long long)b * p.heads + h) * p.lq + i] = p.relu_attn ? 0.f : m + __logf(l);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dq
+template <int DH>
+__global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const AttnP p) {
+  constexpr int ND = (DH + 31) / 32;
+  extern __shared__ float smem_f[];
+  Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
+  const int NB = 2 * p.max_rel + 1;
+  float(*ek)[DH + 1] = reinterpret_cast<float(*)[DH + 1]>(smem_f + sizeof(Smem<DH>) / 4);
+  float(*ev)[DH + 1] = ek + NB;
+  float(*dek)[DH + 1] = ev + NB;
+  float(*dev)[DH + 1] = dek + NB;
+  const bool rpr = p.rpr_k != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int i = blockIdx.x * kAttnWarps + warp;
+  const bool active = i < p.lq;
+  const int kl = p.key_len ? p.key_len[b / p.kv_group] : p.lk;
+  if (rpr) {
+    for (int idx = threadIdx.x; idx < NB * DH; idx += blockDim.x) {
+      ek[idx / DH][idx % DH] = __bfloat162float(p.rpr_k[idx]);
+      ev[idx / DH][idx % DH] = __bfloat162float(p.rpr_v[idx]);
+      dek[idx / DH][idx % DH] = 0.f;
+      dev[idx / DH][idx % DH] = 0.f;
+    }
+  }
+  float qr[DH], dor[DH], qo[ND], doo[ND], dq[ND];
+  float lse = 0.f, delta = 0.f;
+  if (active) {
+    const __nv_bfloat16* qp = p.q + (long long)b * p.bsq + (long long)i * p.ldq + h * DH;
+    const __nv_bfloat16* dop = p.d_o + (long long)b * p.bsdo + (long long)i * p.lddo + h * DH;
+    const __nv_bfloat16* oin = p.o_in + (long long)b * p.bso + (long long)i * p.ldo + h * DH;
+    float dl = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      qr[d] = __bfloat162float(qp[d]) * p.scale;
+      dor[d] = __bfloat162float(dop[d]);
+    }
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const int d = lane + 32 * dd;
+      qo[dd] = d < DH ? __bfloat162float(qp[d]) * p.scale : 0.f;
+      doo[dd] = d < DH ? __bfloat162float(dop[d]) : 0.f;
+      dl += d < DH ? doo[dd] * __bfloat162float(oin[d]) : 0.f;
+      dq[dd] = 0.f;
+    }
+    delta = wsum(dl);
+    const long long li = ((long long)b * p.heads + h) * p.lq + i;
+    lse = p.lse[li];
+    if (lane == 0) p.delta[li] = delta;
+  }
+  const int i_abs = i + p.q_offset;
+  for (int kt = 0; kt < p.lk; kt += 32) {
+    __syncthreads();
+    const int valid_rows = min(32, p.lk - kt);
+    load_tile<DH>(sm.a, p.k + (long long)(b / p.kv_group) * p.bsk + (long long)kt * p.ldk + h * DH, p.ldk, valid_rows, 1.f);
+    load_tile<DH>(sm.b, p.v + (long long)(b / p.kv_group) * p.bsv + (long long)kt * p.ldv + h * DH, p.ldv, valid_rows, 1.f);
+    __syncthreads();
+    if (!active) continue;
+    const int j = kt + lane;
+    const bool inb = j < p.lk;
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      s += qr[d] * sm.a[lane][d];
+      dp += dor[d] * sm.b[lane][d];
+    }
+    int bucket = 0;
+    if (rpr) {
+      bucket = rel_bucket(i_abs, j, p.max_rel);
+#pragma unroll
+      for (int d = 0; d < DH; ++d) {
+        s += qr[d] * ek[bucket][d];
+        dp += dor[d] * ev[bucket][d];
+      }
+    }
+    const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
+    float pj, ds;
+    if (p.relu_attn) {
+      pj = valid ? fmaxf(s, 0.f) : 0.f;
+      ds = (valid && s > 0.f) ? dp : 0.f;
+    } else {
+      const float sm_ = valid ? s : s - p.inf_value;
+      pj = inb ? __expf(sm_ - lse) : 0.f;
+      ds = pj * (dp - delta);
+    }
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      const float dsv = __shfl_sync(0xffffffffu, ds, jj);
+      const float pv = __shfl_sync(0xffffffffu, pj, jj);
+      const int bk = __shfl_sync(0xffffffffu, bucket, jj);
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        const int d = lane + 32 * dd;
+        if (d < DH) {
+          float kk = sm.a[jj][d];
+          if (rpr) {
+            kk += ek[bk][d];
+            if (dsv != 0.f) atomicAdd(&dek[bk][d], dsv * qo[dd]);
+            if (pv != 0.f) atomicAdd(&dev[bk][d], pv * doo[dd]);
+          }
+          dq[dd] += dsv * kk;
+        }
+      }
+    }
+  }
+  if (active) {
+    __nv_bfloat16* dqp = p.dq + (long long)b * p.bsdq + (long long)i * p.lddq + h * DH;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const int d = lane + 32 * dd;
+      if (d < DH) dqp[d] = __float2bfloat16(dq[dd] * p.scale);
+    }
+  }
+  if (rpr) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NB * DH; idx += blockDim.x) {
+      const float a = dek[idx / DH][idx % DH], c = dev[idx / DH][idx % DH];
+      if (a != 0.f) atomicAdd(p.d_rpr_k + idx, a);
+      if (c != 0.f) atomicAdd(p.d_rpr_v + idx, c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dk, dv
+template <int DH>
+__global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dkv_generic(const AttnP p) {
+  constexpr int ND = (DH + 31) / 32;
+  extern __shared__ float smem_f[];
+  Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
+  const int NB = 2 * p.max_rel + 1;
+  float(*ek)[DH + 1] = reinterpret_cast<float(*)[DH + 1]>(smem_f + sizeof(Smem<DH>) / 4);
+  float(*ev)[DH + 1] = ek + NB;
+  const bool rpr = p.rpr_k != nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int j = blockIdx.x * kAttnWarps + warp;
+  const bool active = j < p.lk;
+  const int kl = p.key_len ? p.key_len[b / p.kv_group] : p.lk;
+  if (rpr) {
+    for (int idx = threadIdx.x; idx < NB * DH; idx += blockDim.x) {
+      ek[idx / DH][idx % DH] = __bfloat162float(p.rpr_k[idx]);
+      ev[idx / DH][idx % DH] = __bfloat162float(p.rpr_v[idx]);
+    }
+  }
+  float kr[DH], vr[DH], dk[ND], dv[ND];
+  if (active) {
+    const __nv_bfloat16* kp = p.k + (long long)b * p.bsk + (long long)j * p.ldk + h * DH;
+    const __nv_bfloat16* vp = p.v + (long long)b * p.bsv + (long long)j * p.ldv + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      kr[d] = __bfloat162float(kp[d]);
+      vr[d] = __bfloat162float(vp[d]);
+    }
+  }
+#pragma unroll
+  for (int dd = 0; dd < ND; ++dd) dk[dd] = dv[dd] = 0.f;
+  const bool key_ok = j < kl;
+  for (int qt = 0; qt < p.lq; qt += 32) {
+    __syncthreads();
+    const int valid_rows = min(32, p.lq - qt);
+    load_tile<DH>(sm.a, p.q + (long long)b * p.bsq + (long long)qt * p.ldq + h * DH, p.ldq, valid_rows, p.scale);
+    load_tile<DH>(sm.b, p.d_o + (long long)b * p.bsdo + (long long)qt * p.lddo + h * DH, p.lddo, valid_rows, 1.f);
+    if (threadIdx.x < 32) {
+      const int i = qt + threadIdx.x;
+      const long long li = ((long long)b * p.heads + h) * p.lq + i;
+      sm.aux0[threadIdx.x] = i < p.lq ? p.lse[li] : 0.f;
+      sm.aux1[threadIdx.x] = i < p.lq ? p.delta[li] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int i = qt + lane;
+    const int i_abs = i + p.q_offset;
+    const bool inb = i < p.lq;
+    float s = 0.f, dp = 0.f;
+    int bucket = 0;
+    if (rpr) bucket = rel_bucket(i_abs, j, p.max_rel);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      float kk = kr[d], vv = vr[d];
+      if (rpr) {
+        kk += ek[bucket][d];
+        vv += ev[bucket][d];
+      }
+      s += sm.a[lane][d] * kk;
+      dp += sm.b[lane][d] * vv;
+    }
+    const bool valid = inb && key_ok && (!p.causal || j <= i_abs);
+    float pj, ds;
+    if (p.relu_attn) {
+      pj = valid ? fmaxf(s, 0.f) : 0.f;
+      ds = (valid && s > 0.f) ? dp : 0.f;
+    } else {
+      const float sm_ = valid ? s : s - p.inf_value;
+      pj = inb ? __expf(sm_ - sm.aux0[lane]) : 0.f;
+      ds = pj * (dp - sm.aux1[lane]);
+    }
+#pragma unroll 4
+    for (int ii = 0; ii < 32; ++ii) {
+      const float pv = __shfl_sync(0xffffffffu, pj, ii);
+      const float dsv = __shfl_sync(0xffffffffu, ds, ii);
+#pragma unroll
+      for (int dd = 0; dd < ND; ++dd) {
+        const int d = lane + 32 * dd;
+        if (d < DH) {
+          dv[dd] += pv * sm.b[ii][d];
+          dk[dd] += dsv * sm.a[ii][d];
+        }
+      }
+    }
+  }
+  if (!active) return;
+  __nv_bfloat16* dkp = p.dk + (long long)b * p.bsdk + (long long)j * p.lddk + h * DH;
+  __nv_bfloat16* dvp = p.dv + (long long)b * p.bsdv + (long long)j * p.lddv + h * DH;
+#pragma unroll
+  for (int dd = 0; dd < ND; ++dd) {
+    const int d = lane + 32 * dd;
+    if (d < DH) {
+      dkp[d] = __float2bfloat16(dk[dd]);
+      dvp[d] = __float2bfloat16(dv[dd]);
+    }
+  }
+}
+
+static AttnP to_params(const zb_attention_args* a) {
+  AttnP p;
+  p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
+  p.o = (__nv_bfloat16*)a->o; p.o_in = (const __nv_bfloat16*)a->o;
+  p.d_o = (const __nv_bfloat16*)a->d_o; p.dq = (__nv_bfloat16*)a->dq; p.dk = (__nv_bfloat16*)a->dk;
+  p.dv = (__nv_bfloat16*)a->dv;
+  p.rpr_k = (const __nv_bfloat16*)a->rpr_k; p.rpr_v = (const __nv_bfloat16*)a->rpr_v;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bso = a->bso;
+  p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.bsdo = a->bsdo; p.bsdq = a->bsdq; p.bsdk = a->bsdk; p.bsdv = a->bsdv;
+  p.batch = a->batch; p.heads = a->heads; p.lq = a->lq; p.lk = a->lk;
+  p.key_len = a->key_len; p.causal = a->causal; p.q_offset = a->q_offset;
+  p.max_rel = a->rpr_k ? a->max_rel : 0; p.relu_attn = a->relu_attn;
+  p.kv_group = a->kv_group > 0 ? a->kv_group : 1;
+  p.scale = a->scale; p.inf_value = a->inf_value;
+  p.lse = a->lse; p.delta = a->delta; p.d_rpr_k = a->d_rpr_k; p.d_rpr_v = a->d_rpr_v;
+  return p;
+}
+
+template <int DH>
+static size_t smem_bytes(const AttnP& p, int tables) {
+  return sizeof(Smem<DH>) + (size_t)tables * (2 * p.max_rel + 1) * (DH + 1) * sizeof(float);
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
+      return ZB_ECUDA;
+    }
+  }
+  return ZB_OK;
+}
+
+int attention_generic_fwd(const zb_attention_args* a, cudaStream_t st) {
+  AttnP p = to_params(a);
+  const dim3 grid((a->lq + kAttnWarps - 1) / kAttnWarps, a->heads, a->batch);
+  const int tables = a->rpr_k ? 2 : 0;
+#define LAUNCH(DH)                                                               \
+  do {                                                                           \
+    const size_t sb = smem_bytes<DH>(p, tables);                                 \
+    int rc = set_smem(attn_fwd_generic<DH>, sb);                                 \
+    if (rc) return rc;                                                           \
+    attn_fwd_generic<DH><<<grid, kAttnWarps * 32, sb, st>>>(p);                  \
+  } while (0)
+  switch (a->dh) {
+    case 16: LAUNCH(16); break;
+    case 32: LAUNCH(32); break;
+    case 64: LAUNCH(64); break;
+    default: set_error("zb_attention: head size %d unsupported (16/32/64)", a->dh); return ZB_EUNSUPPORTED;
+  }
+#undef LAUNCH
+  return check_launch("zb_attention_fwd");
+}
+
+int attention_generic_bwd(const zb_attention_args* a, cudaStream_t st) {
+  AttnP p = to_params(a);
+  const dim3 gq((a->lq + kAttnWarps - 1) / kAttnWarps, a->heads, a->batch);
+  const dim3 gk((a->lk + kAttnWarps - 1) / kAttnWarps, a->heads, a->batch);
+  const bool rpr = a->rpr_k != nullptr;
+#define LAUNCH(DH)                                                               \
+  do {                                                                           \
+    const size_t s1 = smem_bytes<DH>(p, rpr ? 4 : 0);                            \
+    int rc = set_smem(attn_bwd_dq_generic<DH>, s1);                              \
+    if (rc) return rc;                                                           \
+    attn_bwd_dq_generic<DH><<<gq, kAttnWarps * 32, s1, st>>>(p);                 \
+    rc = check_launch("zb_attention_bwd(dq)");                                   \
+    if (rc) return rc;                                                           \
+    const size_t s2 = smem_bytes<DH>(p, rpr ? 2 : 0);                            \
+    rc = set_smem(attn_bwd_dkv_generic<DH>, s2);                                 \
+    if (rc) return rc;                                                           \
+    attn_bwd_dkv_generic<DH><<<gk, kAttnWarps * 32, s2, st>>>(p);                \
+  } while (0)
+  switch (a->dh) {
+    case 16: LAUNCH(16); break;
+    case 32: LAUNCH(32); break;
+    case 64: LAUNCH(64); break;
+    default: set_error("zb_attention: head size %d unsupported (16/32/64)", a->dh); return ZB_EUNSUPPORTED;
+  }
+#undef LAUNCH
+  return check_launch("zb_attention_bwd(dkv)");
+}
+
+}  // namespace zb

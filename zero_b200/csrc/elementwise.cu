@@ -1,0 +1,234 @@
+// elementwise.cu — small HBM-bound helpers around the hot path: dtype casts of the fp32 master weights
+// (utils/dtype.py:55-69), bias-gradient column sums (tf.nn.bias_add grad), global-norm partial sums
+// (utils/cycle.py:94), TF-semantics Adam (main.py:178-181), row gathers for beam reordering
+// (search.py:205-209) and the Average-Attention prefix mean (models/transformer_aan.py:99-108).
+#include "zb_common.h"
+#include "zb_ptx.cuh"
+
+namespace zb {
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+// out[n] += sum_m x[m, n]; grid (col-chunks, row-chunks); each thread owns 2 columns, block reduces over rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long n, long long ld, float* __restrict__ out,
+              long long rows_per_block) {
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long col = ((long long)blockIdx.x * 32 + lane) * 2;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > m) r1 = m;
+  float2 acc = make_float2(0.f, 0.f);
+  if (col + 1 < n) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      const float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + col));
+      acc.x += t.x;
+      acc.y += t.y;
+    }
+  } else if (col < n) {
+    for (long long r = r0 + warp; r < r1; r += 8) acc.x += __bfloat162float(x[r * ld + col]);
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float2 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      t.x += red[w][lane].x;
+      t.y += red[w][lane].y;
+    }
+    if (col < n) atomicAdd(out + col, t.x);
+    if (col + 1 < n) atomicAdd(out + col + 1, t.y);
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    acc += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) (host, passed in scalars[0]);
+// m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2; p <- p - lr_t * m / (sqrt(v) + eps).
+__global__ void __launch_bounds__(256)
+adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+               __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps,
+               const float* __restrict__ scalars) {
+  const float lr_t = scalars[0], gs = scalars[1];
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+           vv = *reinterpret_cast<float4*>(v + i);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i);
+    float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = G[e] * gs;
+      M[e] = b1 * M[e] + (1.f - b1) * gr;
+      V[e] = b2 * V[e] + (1.f - b2) * gr * gr;
+      P[e] -= lr_t * M[e] / (sqrtf(V[e]) + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    if (pb) {
+      uint2 o;
+      o.x = pack_bf16x2(pp.x, pp.y);
+      o.y = pack_bf16x2(pp.z, pp.w);
+      *reinterpret_cast<uint2*>(pb + i) = o;
+    }
+  } else {
+    for (long long j = i; j < n; ++j) {
+      const float gr = g[j] * gs;
+      m[j] = b1 * m[j] + (1.f - b1) * gr;
+      v[j] = b2 * v[j] + (1.f - b2) * gr * gr;
+      p[j] -= lr_t * m[j] / (sqrtf(v[j]) + eps);
+      if (pb) pb[j] = __float2bfloat16(p[j]);
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ index,
+                                   uint4* __restrict__ dst, long long rows, long long vec_per_row,
+                                   long long pitch_vec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * vec_per_row) return;
+  const long long r = i / vec_per_row, c = i % vec_per_row;
+  dst[r * pitch_vec + c] = src[(long long)index[r] * pitch_vec + c];
+}
+
+// y[b,t,:] = (sum_{s<=t} x[b,s,:]) / (t+1); one thread per (b, channel pair), sequential over t (T is short).
+__global__ void prefix_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int batch,
+                                       int len, int dim) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (i >= (long long)batch * half) return;
+  const int b = (int)(i / half), c = (int)(i % half) * 2;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int t = 0; t < len; ++t) {
+    const long long o = ((long long)b * len + t) * dim + c;
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + o));
+    acc.x += v.x;
+    acc.y += v.y;
+    const float inv = 1.f / (float)(t + 1);
+    *reinterpret_cast<uint32_t*>(y + o) = pack_bf16x2(acc.x * inv, acc.y * inv);
+  }
+}
+// dx[b,s,:] = sum_{t>=s} dy[b,t,:] / (t+1)
+__global__ void prefix_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int batch,
+                                       int len, int dim) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (i >= (long long)batch * half) return;
+  const int b = (int)(i / half), c = (int)(i % half) * 2;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int t = len - 1; t >= 0; --t) {
+    const long long o = ((long long)b * len + t) * dim + c;
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + o));
+    const float inv = 1.f / (float)(t + 1);
+    acc.x += v.x * inv;
+    acc.y += v.y * inv;
+    *reinterpret_cast<uint32_t*>(dx + o) = pack_bf16x2(acc.x, acc.y);
+  }
+}
+
+}  // namespace zb
+
+using namespace zb;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int zb_cast_f32_bf16(const float* src, void* dst, int64_t n, zb_stream_t stream) {
+  ZB_REQUIRE(src && dst && n >= 0, "zb_cast_f32_bf16: bad args");
+  if (n == 0) return ZB_OK;
+  const long long blocks = ((n + 3) / 4 + 255) / 256;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  return check_launch("zb_cast_f32_bf16");
+}
+extern "C" int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_stream_t stream) {
+  ZB_REQUIRE(src && dst && n >= 0, "zb_cast_bf16_f32: bad args");
+  if (n == 0) return ZB_OK;
+  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)src, dst, n);
+  return check_launch("zb_cast_bf16_f32");
+}
+extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream) {
+  ZB_REQUIRE(x && out && m >= 0 && n > 0 && ld % 2 == 0, "zb_colsum: bad args");
+  if (m == 0) return ZB_OK;
+  const unsigned gx = (unsigned)((n + 63) / 64);
+  long long gy = (2ll * num_sms() + gx - 1) / gx;
+  if (gy > (m + 63) / 64) gy = (m + 63) / 64;
+  if (gy < 1) gy = 1;
+  const long long rpb = (m + gy - 1) / gy;
+  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, m, n, ld, out, rpb);
+  return check_launch("zb_colsum");
+}
+extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream) {
+  ZB_REQUIRE(x && out && n >= 0, "zb_sumsq: bad args");
+  if (n == 0) return ZB_OK;
+  long long blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 4ll * num_sms()) blocks = 4ll * num_sms();
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(x, n, out);
+  return check_launch("zb_sumsq");
+}
+extern "C" int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream) {
+  ZB_REQUIRE(a && a->param && a->m && a->v && a->grad && a->scalars && a->n >= 0, "zb_adam_tf: bad args");
+  if (a->n == 0) return ZB_OK;
+  const long long blocks = ((a->n + 3) / 4 + 255) / 256;
+  adam_tf_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(a->param, a->m, a->v, a->grad, (__nv_bfloat16*)a->param_bf16,
+                                                          a->n, a->beta1, a->beta2, a->eps, a->scalars);
+  return check_launch("zb_adam_tf");
+}
+extern "C" int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_bytes,
+                              int64_t pitch_bytes, zb_stream_t stream) {
+  ZB_REQUIRE(src && index && dst && rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0 && pitch_bytes % 16 == 0 &&
+                 pitch_bytes >= row_bytes,
+             "zb_gather_rows: row_bytes / pitch_bytes must be multiples of 16");
+  if (rows == 0) return ZB_OK;
+  const long long vec = row_bytes / 16, total = rows * vec;
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const uint4*)src, index, (uint4*)dst, rows,
+                                                                             vec, pitch_bytes / 16);
+  return check_launch("zb_gather_rows");
+}
+extern "C" int zb_prefix_mean_fwd(const void* x, void* y, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream) {
+  ZB_REQUIRE(x && y && batch >= 0 && len > 0 && dim % 2 == 0, "zb_prefix_mean_fwd: bad args");
+  const long long n = (long long)batch * (dim / 2);
+  if (n == 0) return ZB_OK;
+  prefix_mean_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                             batch, len, dim);
+  return check_launch("zb_prefix_mean_fwd");
+}
+extern "C" int zb_prefix_mean_bwd(const void* dy, void* dx, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream) {
+  ZB_REQUIRE(dy && dx && batch >= 0 && len > 0 && dim % 2 == 0, "zb_prefix_mean_bwd: bad args");
+  const long long n = (long long)batch * (dim / 2);
+  if (n == 0) return ZB_OK;
+  prefix_mean_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
+                                                                             batch, len, dim);
+  return check_launch("zb_prefix_mean_bwd");
+}

@@ -1,0 +1,696 @@
+"""Execution engine: Zero's Transformer family (models/transformer*.py) as an explicit forward / backward
+schedule of C-ABI kernel calls over pre-planned device buffers.
+
+The reference builds a TF1 graph and lets `optimizer.compute_gradients` derive the backward pass
+(main.py:22-45).  Here both directions are written out: every activation the backward needs is kept in a
+per-shape workspace (static addresses -> the whole step is CUDA-graph capturable), every parameter lives in
+one flat fp32 master arena with a bf16 compute mirror (utils/dtype.py:55-69), every parameter gradient is
+accumulated in one flat fp32 arena (-> a single NCCL all-reduce, utils/parallel.py:134-208).
+
+Parameter names are the reference's TF variable names; `load_state_dict` /
+`state_dict` speak that vocabulary.  Cross-attention k_map / v_map weights are stored fused ([d, 2d]) so memory
+is projected by one GEMM; their TF names are strided views into the fused tensor.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import lib as L
+from . import ops
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _hp(hp, key, default=None):
+    try:
+        return getattr(hp, key)
+    except AttributeError:
+        return default
+
+
+class ModelConfig(object):
+    """Hot-path hyper-parameters."""
+
+    def __init__(self, hp, src_vocab=None, tgt_vocab=None):
+        self.model = str(_hp(hp, "model_name", "transformer")).lower()
+        self.scope = _hp(hp, "scope_name") or "model"
+        self.d = int(hp.hidden_size)
+        self.e = int(_hp(hp, "embed_size", self.d))
+        self.f = int(hp.filter_size)
+        self.h = int(hp.num_heads)
+        self.nenc = int(hp.num_encoder_layer)
+        self.ndec = int(hp.num_decoder_layer)
+        self.smooth = float(_hp(hp, "label_smooth", 0.1))
+        self.share_st = bool(_hp(hp, "shared_source_target_embedding", False))
+        self.share_ts = bool(_hp(hp, "shared_target_softmax_embedding", True))
+        self.max_rel = int(_hp(hp, "max_relative_position", 16))
+        self.aan_mask = bool(_hp(hp, "aan_mask", True))
+        self.use_ffn = bool(_hp(hp, "use_ffn", False))
+        self.eps = float(_hp(hp, "dtype_epsilon", 1e-8))
+        self.inf = float(_hp(hp, "dtype_inf", 1e8))
+        self.loss_scale = float(_hp(hp, "loss_scale", 1.0))
+        self.deep_init = bool(_hp(hp, "deep_transformer_init", False))
+        self.init = _hp(hp, "initializer", "uniform_unit_scaling")
+        self.init_gain = float(_hp(hp, "initializer_gain", 1.0))
+        sv = src_vocab if src_vocab is not None else _hp(hp, "src_vocab")
+        tv = tgt_vocab if tgt_vocab is not None else _hp(hp, "tgt_vocab")
+        self.vs = int(sv.size() if hasattr(sv, "size") else sv)
+        self.vt = int(tv.size() if hasattr(tv, "size") else tv)
+        if self.e != self.d:
+            raise L.ZeroB200Error("embed_size must equal hidden_size on the Transformer path")
+        if self.d % self.h or (self.d // self.h) not in (16, 32, 64):
+            raise L.ZeroB200Error("head size %d unsupported (16/32/64)" % (self.d // max(self.h, 1)))
+        if self.d % 8 or self.f % 8 or self.vs % 8 or self.vt % 8:
+            raise L.ZeroB200Error("hidden/filter/vocab sizes must be multiples of 8 (16-byte TMA pitch)")
+        known = ("transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse")
+        if self.model not in known:
+            raise L.ZeroB200Error("model %r is outside the hot path (supported: %s)" % (self.model, ", ".join(known)))
+
+    rpr = property(lambda s: s.model == "transformer_rpr")
+    rela = property(lambda s: s.model == "transformer_rela")
+    aan = property(lambda s: s.model == "transformer_aan")
+    fuse = property(lambda s: s.model == "transformer_fuse")
+
+
+# ------------------------------------------------------------------------------------------------ parameters
+class ParamStore(object):
+    """Flat fp32 master / bf16 mirror / fp32 gradient / Adam m,v arenas + TF-named views."""
+
+    ALIGN = 64  # elements; keeps every bf16 view 128-byte aligned
+
+    def __init__(self, cfg: ModelConfig, device):
+        self.cfg = cfg
+        self.device = device
+        self.slots = OrderedDict()     # engine tensor name -> (offset, shape)
+        self.tf_views = OrderedDict()  # TF variable name -> (engine name, slicer)
+        self._plan()
+        n = self.total
+        self.master = torch.zeros(n, dtype=f32, device=device)
+        self.mirror = torch.zeros(n, dtype=bf16, device=device)
+        self.grad = torch.zeros(n, dtype=f32, device=device)
+        self.adam_m = None
+        self.adam_v = None
+
+    # -- layout -------------------------------------------------------------------------------------
+    def _add(self, name, shape, tf_name=None):
+        size = 1
+        for s in shape:
+            size *= s
+        off = getattr(self, "total", 0)
+        self.slots[name] = (off, tuple(shape))
+        self.total = (off + size + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if tf_name is not None:
+            self.tf_views[tf_name] = (name, None)
+
+    def _plan(self):
+        c = self.cfg
+        s = c.scope
+        self.total = 0
+        if c.share_st:
+            self._add("src_emb", (c.vs, c.e), s + "/embedding")
+            self.tf_alias_tgt = "src_emb"
+        else:
+            self._add("src_emb", (c.vs, c.e), s + "/src_embedding")
+            self._add("tgt_emb", (c.vt, c.e), s + "/tgt_embedding")
+            if not c.share_ts:
+                self._add("softmax_emb", (c.vt, c.e), s + "/softmax_embedding")
+        self._add("emb_bias", (c.e,), s + "/bias")
+        dh = c.d // c.h
+        nb = 2 * c.max_rel + 1
+
+        def lin(key, tfp, i, o):
+            self._add(key + ".W", (i, o), tfp + "/W_0_0")
+            self._add(key + ".b", (o,), tfp + "/b_0")
+
+        def ln(key, tfp):
+            self._add(key + ".scale", (c.d,), tfp + "/layer_norm/scale")
+            self._add(key + ".offset", (c.d,), tfp + "/layer_norm/offset")
+
+        def extras(key, tfp):
+            if c.rpr:
+                self._add(key + ".rpr_k", (nb, dh), tfp + "/rpr_keys/embeddings")
+                self._add(key + ".rpr_v", (nb, dh), tfp + "/rpr_values/embeddings")
+            if c.rela:
+                self._add(key + ".post_scale", (c.d,), tfp + "/post/scale")
+                self._add(key + ".post_gate", (c.d,), tfp + "/post/gate")
+
+        def self_attn(key, tfp):
+            lin(key + ".qkv", tfp + "/dot_attention/qkv_map", c.d, 3 * c.d)
+            extras(key, tfp + "/dot_attention")
+            lin(key + ".o", tfp + "/dot_attention/o_map", c.d, c.d)
+            ln(key + ".ln", tfp)
+
+        def cross_attn(key, tfp):
+            lin(key + ".q", tfp + "/dot_attention/q_map", c.d, c.d)
+            # fused k_map | v_map storage; TF names are column slices
+            self._add(key + ".kv.W", (c.d, 2 * c.d))
+            self._add(key + ".kv.b", (2 * c.d,))
+            self.tf_views[tfp + "/dot_attention/k_map/W_0_0"] = (key + ".kv.W", (slice(None), slice(0, c.d)))
+            self.tf_views[tfp + "/dot_attention/k_map/b_0"] = (key + ".kv.b", (slice(0, c.d),))
+            self.tf_views[tfp + "/dot_attention/v_map/W_0_0"] = (key + ".kv.W", (slice(None), slice(c.d, 2 * c.d)))
+            self.tf_views[tfp + "/dot_attention/v_map/b_0"] = (key + ".kv.b", (slice(c.d, 2 * c.d),))
+            extras(key, tfp + "/dot_attention")
+            lin(key + ".o", tfp + "/dot_attention/o_map", c.d, c.d)
+            ln(key + ".ln", tfp)
+
+        def ffn(key, tfp):
+            lin(key + ".w1", tfp + "/ffn_layer/enlarge", c.d, c.f)
+            lin(key + ".w2", tfp + "/ffn_layer/output", c.f, c.d)
+
+        for l in range(c.nenc):
+            key, tfp = "enc%d" % l, "%s/encoder/layer_%d" % (s, l)
+            self_attn(key + ".self", tfp + "/self_attention")
+            ffn(key + ".ffn", tfp + "/feed_forward")
+            ln(key + ".ffn.ln", tfp + "/feed_forward")
+        for l in range(c.ndec):
+            key, tfp = "dec%d" % l, "%s/decoder/layer_%d" % (s, l)
+            if c.aan:
+                a = tfp + "/average_attention"
+                if c.use_ffn:
+                    ffn(key + ".aan.ffn", a)
+                lin(key + ".aan.z", a + "/z_project", 2 * c.d, 2 * c.d)
+                ln(key + ".aan.ln", a)
+                cross_attn(key + ".cross", tfp + "/cross_attention")
+            elif c.fuse:
+                cross_attn(key + ".cross", tfp + "/fuse_attention")
+            else:
+                self_attn(key + ".self", tfp + "/self_attention")
+                cross_attn(key + ".cross", tfp + "/cross_attention")
+            ffn(key + ".ffn", tfp + "/feed_forward")
+            ln(key + ".ffn.ln", tfp + "/feed_forward")
+
+    # -- views ---------------------------------------------------------------------------------------
+    def _view(self, arena, name):
+        off, shape = self.slots[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return arena[off:off + n].view(shape)
+
+    def w(self, name):      # bf16 compute copy
+        return self._view(self.mirror, name)
+
+    def p(self, name):      # fp32 master
+        return self._view(self.master, name)
+
+    def g(self, name):      # fp32 gradient
+        return self._view(self.grad, name)
+
+    def tf_names(self):
+        return list(self.tf_views.keys())
+
+    def tf_view(self, arena, tf_name):
+        eng, sl = self.tf_views[tf_name]
+        v = self._view(arena, eng)
+        return v if sl is None else v[sl]
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self.tf_views if k not in sd]
+        extra = [k for k in sd if k not in self.tf_views]
+        if strict and (missing or extra):
+            raise L.ZeroB200Error("state dict mismatch: missing %s, unexpected %s" % (missing[:4], extra[:4]))
+        for k, (eng, sl) in self.tf_views.items():
+            if k in sd:
+                self.tf_view(self.master, k).copy_(torch.as_tensor(sd[k]).to(self.device, f32))
+        self.refresh_mirror()
+
+    def state_dict(self):
+        return OrderedDict((k, self.tf_view(self.master, k).detach().clone().cpu()) for k in self.tf_views)
+
+    def grad_dict(self):
+        return OrderedDict((k, self.tf_view(self.grad, k).detach().clone().cpu()) for k in self.tf_views)
+
+    def refresh_mirror(self):
+        ops.cast_f32_bf16(self.master, self.mirror)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def init_random(self, seed=1234):
+        """Distribution-equivalent init (modules/initializer.py:11-32; models/transformer.py:18,38-45)."""
+        c = self.cfg
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for k in self.tf_views:
+            v = self.tf_view(self.master, k)
+            shape = tuple(v.shape)
+            leaf = k.rsplit("/", 1)[1]
+            if leaf.endswith("embedding"):
+                t = torch.randn(shape, generator=g) * c.d ** -0.5
+            elif leaf in ("b_0", "offset"):
+                t = torch.zeros(shape)
+            elif leaf == "scale":
+                t = torch.ones(shape)
+            else:
+                scale = c.init_gain
+                layered = "/layer_" in k
+                if c.deep_init and layered:
+                    scale = c.init_gain * (int(k.split("/layer_")[1].split("/")[0]) + 1) ** -0.5
+                if c.init == "uniform" and not (c.deep_init and layered):
+                    t = (torch.rand(shape, generator=g) * 2 - 1) * c.init_gain
+                elif c.init == "normal" and not (c.deep_init and layered):
+                    t = torch.randn(shape, generator=g) * c.init_gain
+                else:
+                    fi, fo = (shape[0], shape[0]) if len(shape) == 1 else (shape[0], shape[1])
+                    lim = math.sqrt(3.0 * scale / ((fi + fo) / 2.0))
+                    t = (torch.rand(shape, generator=g) * 2 - 1) * lim
+            v.copy_(t.to(self.device))
+        self.refresh_mirror()
+
+
+# ------------------------------------------------------------------------------------------------ workspace
+class Workspace(object):
+    """Named device buffers, allocated once per shape signature (static addresses for CUDA graphs)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=bf16, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.device) if zero else \
+                torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+
+def _lens(ids):
+    """Number of leading non-pad tokens per row; the reference's masks are `id != 0` (models/transformer.py:16)."""
+    return (ids != 0).sum(1).to(torch.int32)
+
+
+def compact_columns(ids):
+    """util.remove_invalid_seq (utils/util.py:274-287): drop all-pad columns, always keep column 0."""
+    keep = (ids != 0).any(0)
+    keep[0] = True
+    if bool(keep.all()):
+        return ids
+    return ids[:, keep].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ engine
+class Engine(object):
+    def __init__(self, hp, src_vocab=None, tgt_vocab=None, device="cuda"):
+        if not torch.cuda.is_available():
+            raise L.ZeroB200Error("zero_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        L.load()
+        self.cfg = ModelConfig(hp, src_vocab, tgt_vocab)
+        self.device = torch.device(device)
+        self.ps = ParamStore(self.cfg, self.device)
+        self.ws = Workspace(self.device)
+        self.step_count = 0
+
+    # ================================================================================== forward pieces
+    def _self_attn_fwd(self, key, x, B, Lq, key_len, causal, sv, tag):
+        """func.dot_attention with memory=None (func.py:194-205, 218-256, 277-278)."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        N = B * Lq
+        qkv = ws.get(tag + ".qkv", (N, 3 * c.d))
+        ops.linear_fwd(x, ps.w(key + ".qkv.W"), ps.p(key + ".qkv.b"), qkv)
+        q3 = qkv.view(B, Lq, 3 * c.d)
+        ctx = ws.get(tag + ".ctx", (N, c.d))
+        lse = ws.get(tag + ".lse", (B, c.h, Lq), f32)
+        a = ops.attention_args(q3[:, :, :c.d], q3[:, :, c.d:2 * c.d], q3[:, :, 2 * c.d:], ctx.view(B, Lq, c.d), c.h,
+                               key_len=key_len, causal=causal, inf_value=c.inf, lse=lse,
+                               rpr_k=ps.w(key + ".rpr_k") if c.rpr else None,
+                               rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
+                               relu_attn=c.rela)
+        ops.attention_fwd(a)
+        y = ws.get(tag + ".y", (N, c.d))
+        ops.linear_fwd(ctx, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
+        sv.update(qkv=qkv, ctx=ctx, lse=lse, attn=a, y=y)
+        return y
+
+    def _self_attn_bwd(self, key, x, dy, B, Lq, sv, tag):
+        """Returns dx (gradient wrt the sublayer input through the attention branch)."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        N = B * Lq
+        ops.linear_wgrad(sv["ctx"], dy, ps.g(key + ".o.W"))
+        ops.colsum(dy, ps.g(key + ".o.b"))
+        dctx = ws.get(tag + ".dctx", (N, c.d))
+        ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
+        dqkv = ws.get(tag + ".dqkv", (N, 3 * c.d))
+        d3 = dqkv.view(B, Lq, 3 * c.d)
+        delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
+        ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), d3[:, :, :c.d], d3[:, :, c.d:2 * c.d], d3[:, :, 2 * c.d:],
+                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
+        ops.linear_wgrad(x, dqkv, ps.g(key + ".qkv.W"))
+        ops.colsum(dqkv, ps.g(key + ".qkv.b"))
+        dx = ws.get(tag + ".dx", (N, c.d))
+        ops.linear_dgrad(dqkv, ps.w(key + ".qkv.W"), dx)
+        return dx
+
+    def _cross_attn_fwd(self, key, x, enc, B, Lq, S, src_len, sv, tag):
+        """func.dot_attention with memory (func.py:206-216, 218-256, 277-278)."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        N = B * Lq
+        q = ws.get(tag + ".q", (N, c.d))
+        ops.linear_fwd(x, ps.w(key + ".q.W"), ps.p(key + ".q.b"), q)
+        kv = ws.get(tag + ".kv", (B * S, 2 * c.d))
+        ops.linear_fwd(enc, ps.w(key + ".kv.W"), ps.p(key + ".kv.b"), kv)
+        kv3 = kv.view(B, S, 2 * c.d)
+        ctx = ws.get(tag + ".ctx", (N, c.d))
+        lse = ws.get(tag + ".lse", (B, c.h, Lq), f32)
+        a = ops.attention_args(q.view(B, Lq, c.d), kv3[:, :, :c.d], kv3[:, :, c.d:], ctx.view(B, Lq, c.d), c.h,
+                               key_len=src_len, causal=False, inf_value=c.inf, lse=lse,
+                               rpr_k=ps.w(key + ".rpr_k") if c.rpr else None,
+                               rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
+                               relu_attn=c.rela)
+        ops.attention_fwd(a)
+        y = ws.get(tag + ".y", (N, c.d))
+        ops.linear_fwd(ctx, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
+        sv.update(q=q, kv=kv, ctx=ctx, lse=lse, attn=a, y=y)
+        return y
+
+    def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
+        c, ps, ws = self.cfg, self.ps, self.ws
+        N = B * Lq
+        ops.linear_wgrad(sv["ctx"], dy, ps.g(key + ".o.W"))
+        ops.colsum(dy, ps.g(key + ".o.b"))
+        dctx = ws.get(tag + ".dctx", (N, c.d))
+        ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
+        dq = ws.get(tag + ".dq", (N, c.d))
+        dkv = ws.get(tag + ".dkv", (B * S, 2 * c.d))
+        dkv3 = dkv.view(B, S, 2 * c.d)
+        delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
+        ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), dq.view(B, Lq, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:],
+                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
+        ops.linear_wgrad(x, dq, ps.g(key + ".q.W"))
+        ops.colsum(dq, ps.g(key + ".q.b"))
+        ops.linear_wgrad(enc, dkv, ps.g(key + ".kv.W"))
+        ops.colsum(dkv, ps.g(key + ".kv.b"))
+        # d_enc (fp32, accumulated over decoder layers) += dkv @ Wkv^T
+        ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
+        dx = ws.get(tag + ".dx", (N, c.d))
+        ops.linear_dgrad(dq, ps.w(key + ".q.W"), dx)
+        return dx
+
+    def _ffn_fwd(self, key, x, N, sv, tag):
+        """func.ffn_layer (func.py:327-338): relu fused into the first GEMM's epilogue."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        h = ws.get(tag + ".h", (N, c.f))
+        ops.linear_fwd(x, ps.w(key + ".w1.W"), ps.p(key + ".w1.b"), h, relu=True)
+        y = ws.get(tag + ".y", (N, c.d))
+        ops.linear_fwd(h, ps.w(key + ".w2.W"), ps.p(key + ".w2.b"), y)
+        sv.update(h=h, y=y)
+        return y
+
+    def _ffn_bwd(self, key, x, dy, N, sv, tag):
+        c, ps, ws = self.cfg, self.ps, self.ws
+        ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W"))
+        ops.colsum(dy, ps.g(key + ".w2.b"))
+        dh = ws.get(tag + ".dh", (N, c.f))
+        ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"])
+        ops.linear_wgrad(x, dh, ps.g(key + ".w1.W"))
+        ops.colsum(dh, ps.g(key + ".w1.b"))
+        dx = ws.get(tag + ".dx", (N, c.d))
+        ops.linear_dgrad(dh, ps.w(key + ".w1.W"), dx)
+        return dx
+
+    def _ln_fwd(self, key, x, y, N, sv, tag):
+        c, ps, ws = self.cfg, self.ps, self.ws
+        out = ws.get(tag + ".out", (N, c.d))
+        mean = ws.get(tag + ".mean", (N,), f32)
+        rstd = ws.get(tag + ".rstd", (N,), f32)
+        ops.add_ln_fwd(x, y, out, ps.p(key + ".scale"), ps.p(key + ".offset"), mean, rstd, c.eps)
+        sv.update(x=x, y=y, mean=mean, rstd=rstd)
+        return out
+
+    def _ln_bwd(self, key, d_out, d_out2, N, sv, tag):
+        c, ps, ws = self.cfg, self.ps, self.ws
+        ds = ws.get(tag + ".ds", (N, c.d))
+        ops.add_ln_bwd(sv["x"], sv["y"], d_out, d_out2, sv["mean"], sv["rstd"], ps.p(key + ".scale"), ds,
+                       ps.g(key + ".scale"), ps.g(key + ".offset"))
+        return ds
+
+    # ================================================================================== encoder
+    def encode(self, source, save=None, tag="E"):
+        """models/transformer.py:15-84.  source: int32 [B, S] (pad = 0).  Returns enc [B*S, d] bf16, src_len."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        B, S = source.shape
+        N = B * S
+        src_len = _lens(source)
+        x = ws.get(tag + ".x0", (N, c.d))
+        ops.embed_fwd(source, ps.w("src_emb"), ps.p("emb_bias"), x, mult=c.d ** 0.5)
+        layers = []
+        for l in range(c.nenc):
+            key, t = "enc%d" % l, "%s.L%d" % (tag, l)
+            sv = {"att": {}, "ln1": {}, "ffn": {}, "ln2": {}, "x_in": x}
+            y = self._self_attn_fwd(key + ".self", x, B, S, src_len, False, sv["att"], t + ".att")
+            x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
+            y2 = self._ffn_fwd(key + ".ffn", x1, N, sv["ffn"], t + ".ffn")
+            x = self._ln_fwd(key + ".ffn.ln", x1, y2, N, sv["ln2"], t + ".ln2")
+            sv["x1"] = x1
+            layers.append(sv)
+        if save is not None:
+            save.update(layers=layers, source=source, src_len=src_len, B=B, S=S)
+        return x, src_len
+
+    def encode_bwd(self, d_enc, save, tag="E"):
+        """d_enc: bf16 [B*S, d] gradient wrt the encoder output."""
+        c, ps = self.cfg, self.ps
+        B, S = save["B"], save["S"]
+        N = B * S
+        d1, d2 = d_enc, None
+        for l in reversed(range(c.nenc)):
+            key, t = "enc%d" % l, "%s.L%d" % (tag, l)
+            sv = save["layers"][l]
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], tag + ".bw.ln2")
+            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], ds2, N, sv["ffn"], tag + ".bw.ffn")
+            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], tag + ".bw.ln1")
+            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, S, sv["att"], tag + ".bw.att")
+            d1, d2 = ds1, dx
+        ops.embed_bwd(save["source"], d1, ps.g("src_emb"), ps.g("emb_bias"), mult=c.d ** 0.5, d_out2=d2)
+
+    # ================================================================================== decoder (training)
+    def _tgt_table(self):
+        return "src_emb" if self.cfg.share_st else "tgt_emb"
+
+    def _softmax_table(self):
+        c = self.cfg
+        if c.share_st:
+            return "src_emb"
+        return "tgt_emb" if c.share_ts else "softmax_emb"
+
+    def decode_train(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D"):
+        """models/transformer.py:87-218 in training mode.  Returns (loss[1], per_sample[B], logits fp32 [N,V])."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        if not (c.model == "transformer" or c.rpr):
+            raise L.ZeroB200Error("training path for %s is not built yet" % c.model)
+        B, T = target.shape
+        N = B * T
+        x = ws.get(tag + ".x0", (N, c.d))
+        ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x, mult=c.d ** 0.5, shift=1)
+        layers = []
+        for l in range(c.ndec):
+            key, t = "dec%d" % l, "%s.L%d" % (tag, l)
+            sv = {"att": {}, "ln1": {}, "cross": {}, "lnc": {}, "ffn": {}, "ln2": {}, "x_in": x}
+            # decoder self-attention: causal bias only, no key-padding mask (models/transformer.py:136)
+            y = self._self_attn_fwd(key + ".self", x, B, T, None, True, sv["att"], t + ".att")
+            x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
+            yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross")
+            xc = self._ln_fwd(key + ".cross.ln", x1, yc, N, sv["lnc"], t + ".lnc")
+            y2 = self._ffn_fwd(key + ".ffn", xc, N, sv["ffn"], t + ".ffn")
+            x = self._ln_fwd(key + ".ffn.ln", xc, y2, N, sv["ln2"], t + ".ln2")
+            sv.update(x1=x1, xc=xc)
+            layers.append(sv)
+        feat = x
+        table = ps.w(self._softmax_table())
+        logits = ws.get(tag + ".logits", (N, c.vt), f32)
+        ops.gemm(feat, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)  # feature @ E^T, cast fp32 (transformer.py:194-196)
+        nll = ws.get(tag + ".nll", (N,), f32)
+        per_sample = ws.get(tag + ".per_sample", (B,), f32)
+        loss = ws.get(tag + ".loss", (1,), f32)
+        dlogits = ws.get(tag + ".dlogits", (N, c.vt)) if want_grad else None
+        ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
+                       loss_scale=c.loss_scale)
+        if save is not None:
+            save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc)
+        return loss, per_sample, logits
+
+    def decode_train_bwd(self, save, d_enc_f32, tag="D"):
+        """Backward of decode_train; accumulates the encoder-output gradient into d_enc_f32 (fp32 [B*S, d])."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        B, T, S = save["B"], save["T"], save["S"]
+        N = B * T
+        feat, dlogits, enc = save["feat"], save["dlogits"], save["enc"]
+        table = self._softmax_table()
+        # dE += dlogits^T feat ; dfeat = dlogits E
+        ops.gemm(dlogits, feat, ps.g(table), L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True)
+        dfeat = ws.get(tag + ".dfeat", (N, c.d))
+        ops.gemm(dlogits, ps.w(table), dfeat, L.ZB_K_MAJOR, L.ZB_MN_MAJOR)
+        d1, d2 = dfeat, None
+        for l in reversed(range(c.ndec)):
+            key, t = "dec%d" % l, "%s.L%d" % (tag, l)
+            sv = save["layers"][l]
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], tag + ".bw.ln2")
+            dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], tag + ".bw.ffn")
+            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], tag + ".bw.lnc")
+            dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
+                                       tag + ".bw.cross")
+            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], tag + ".bw.ln1")
+            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], tag + ".bw.att")
+            d1, d2 = ds1, dx
+        ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
+
+    # ================================================================================== public steps
+    @staticmethod
+    def _prep_ids(ids, device, compact=True):
+        ids = torch.as_tensor(ids)
+        if ids.device != device:
+            ids = ids.to(device, non_blocking=True)
+        ids = ids.to(torch.int32)
+        return (compact_columns(ids) if compact else ids).contiguous()
+
+    def forward_backward(self, source, target, zero_grad=True, compact=True):
+        """train_fn + tf.gradients (models/transformer.py:221-232, main.py:22-45) for one tower.
+        Gradients land in self.ps.grad (fp32).  Returns the device loss tensor [1]."""
+        c, ws = self.cfg, self.ws
+        source = self._prep_ids(source, self.device, compact)
+        target = self._prep_ids(target, self.device, compact)
+        if zero_grad:
+            self.ps.zero_grad()
+        B, S = source.shape
+        esave, dsave = {}, {}
+        enc, src_len = self.encode(source, esave)
+        loss, per_sample, _ = self.decode_train(target, enc, src_len, S, c.smooth, True, dsave)
+        d_enc32 = ws.get("d_enc32", (B * S, c.d), f32)
+        d_enc32.zero_()
+        self.decode_train_bwd(dsave, d_enc32)
+        d_enc = ws.get("d_enc", (B * S, c.d))
+        ops.cast_f32_bf16(d_enc32, d_enc)
+        self.encode_bwd(d_enc, esave)
+        return loss
+
+    def train_loss(self, source, target):
+        """train_fn forward only -> (loss, per_sample, logits)."""
+        source = self._prep_ids(source, self.device)
+        target = self._prep_ids(target, self.device)
+        enc, src_len = self.encode(source)
+        return self.decode_train(target, enc, src_len, source.shape[1], self.cfg.smooth, False)
+
+    def score(self, source, target):
+        """score_fn (models/transformer.py:235-249): label smoothing off, returns per-sentence NLL [B]."""
+        source = self._prep_ids(source, self.device)
+        target = self._prep_ids(target, self.device)
+        enc, src_len = self.encode(source)
+        return self.decode_train(target, enc, src_len, source.shape[1], 0.0, False)[1]
+
+
+# ------------------------------------------------------------------------------------------------ cached decode
+class DecodeState(object):
+    """State of infer_fn's (encoding_fn, decoding_fn) pair in 'cache' search mode
+    (models/transformer.py:252-285).  Per-sentence tensors (encoder output, projected
+    memory mk/mv) are kept [B, ...] and shared by the beams of a sentence; only the per-beam self-attention
+    caches are reordered (double-buffered gather of the filled prefix)."""
+
+    def __init__(self, engine, enc, src_len, B, S):
+        self.engine = engine
+        self.device = engine.device
+        self.vocab = engine.cfg.vt
+        self.enc, self.src_len, self.B, self.S = enc, src_len, B, S
+        self.K = 1
+        self.mem = None
+        self.cache = None
+        self.cache_alt = None
+
+    def begin_search(self, beam, cap=None):
+        """search.py:36-39,56-77: tile per-beam state, run the dummy step that creates mk / mv."""
+        eng, c = self.engine, self.engine.cfg
+        self.K = int(beam)
+        R = self.B * self.K
+        if cap is None:
+            cap = int(self.src_len.max().item()) + int(getattr(eng, "decode_length", 50)) + 2
+        self.cap = cap
+        self.mem = []
+        for l in range(c.ndec):
+            key = "dec%d.cross" % l
+            kv = eng.ws.get("dec.mem%d" % l, (self.B * self.S, 2 * c.d))
+            ops.linear_fwd(self.enc, eng.ps.w(key + ".kv.W"), eng.ps.p(key + ".kv.b"), kv)
+            self.mem.append(kv.view(self.B, self.S, 2 * c.d))
+        if not (c.aan or c.fuse):
+            self.cache = [eng.ws.get("dec.cacheA%d" % l, (R, cap, 3 * c.d)) for l in range(c.ndec)]
+            self.cache_alt = [eng.ws.get("dec.cacheB%d" % l, (R, cap, 3 * c.d)) for l in range(c.ndec)]
+
+    def reorder(self, parent, t):
+        """search.py:205-209: new alive beam r continues previous beam parent[r]; moves positions [0, t]."""
+        c = self.engine.cfg
+        if self.cache is None:
+            return
+        for l in range(c.ndec):
+            ops.gather_rows(self.cache[l], parent, self.cache_alt[l], row_elems=(t + 1) * 3 * c.d)
+        self.cache, self.cache_alt = self.cache_alt, self.cache
+
+
+def _engine_encoding_fn(self, source):
+    source = self._prep_ids(source, self.device)
+    enc, src_len = self.encode(source, tag="I")
+    return DecodeState(self, enc, src_len, source.shape[0], source.shape[1])
+
+
+def _engine_decoding_fn(self, target, state, time):
+    """decoding_fn(target [R,1], state, time) -> (logits fp32 [R, V], state)  (models/transformer.py:267-283)."""
+    c, ps, ws = self.cfg, self.ps, self.ws
+    if c.aan or c.fuse:
+        raise L.ZeroB200Error("cached decode for %s is not built yet" % c.model)
+    t = int(time)
+    R = target.shape[0]
+    K = state.K
+    if state.mem is None:
+        state.begin_search(K)
+    x = ws.get("dec.x", (R, c.d))
+    ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x.view(R, 1, c.d), mult=c.d ** 0.5,
+                  zero_if_all_pad=True, time=t)
+    for l in range(c.ndec):
+        key = "dec%d" % l
+        cache = state.cache[l]
+        ops.linear_fwd(x, ps.w(key + ".self.qkv.W"), ps.p(key + ".self.qkv.b"), cache[:, t, :])
+        ctx = ws.get("dec.ctx", (R, c.d))
+        a = ops.attention_args(cache[:, t:t + 1, :c.d], cache[:, :t + 1, c.d:2 * c.d], cache[:, :t + 1, 2 * c.d:],
+                               ctx.view(R, 1, c.d), c.h, q_offset=t, inf_value=c.inf,
+                               rpr_k=ps.w(key + ".self.rpr_k") if c.rpr else None,
+                               rpr_v=ps.w(key + ".self.rpr_v") if c.rpr else None, max_rel=c.max_rel,
+                               relu_attn=c.rela)
+        ops.attention_fwd(a)
+        ctx = self._post_attn(key + ".self", ctx, R)
+        y = ws.get("dec.y", (R, c.d))
+        ops.linear_fwd(ctx, ps.w(key + ".self.o.W"), ps.p(key + ".self.o.b"), y)
+        x1 = ws.get("dec.x1", (R, c.d))
+        ops.add_ln_fwd(x, y, x1, ps.p(key + ".self.ln.scale"), ps.p(key + ".self.ln.offset"), eps=c.eps)
+        q = ws.get("dec.q", (R, c.d))
+        ops.linear_fwd(x1, ps.w(key + ".cross.q.W"), ps.p(key + ".cross.q.b"), q)
+        mem = state.mem[l]
+        a = ops.attention_args(q.view(R, 1, c.d), mem[:, :, :c.d], mem[:, :, c.d:], ctx.view(R, 1, c.d), c.h,
+                               key_len=state.src_len, q_offset=t, inf_value=c.inf, kv_group=K,
+                               rpr_k=ps.w(key + ".cross.rpr_k") if c.rpr else None,
+                               rpr_v=ps.w(key + ".cross.rpr_v") if c.rpr else None, max_rel=c.max_rel,
+                               relu_attn=c.rela)
+        ops.attention_fwd(a)
+        ctx = self._post_attn(key + ".cross", ctx, R)
+        ops.linear_fwd(ctx, ps.w(key + ".cross.o.W"), ps.p(key + ".cross.o.b"), y)
+        xc = ws.get("dec.xc", (R, c.d))
+        ops.add_ln_fwd(x1, y, xc, ps.p(key + ".cross.ln.scale"), ps.p(key + ".cross.ln.offset"), eps=c.eps)
+        h = ws.get("dec.h", (R, c.f))
+        ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
+        ops.linear_fwd(h, ps.w(key + ".ffn.w2.W"), ps.p(key + ".ffn.w2.b"), y)
+        ops.add_ln_fwd(xc, y, x, ps.p(key + ".ffn.ln.scale"), ps.p(key + ".ffn.ln.offset"), eps=c.eps)
+    logits = ws.get("dec.logits", (R, c.vt), f32)
+    ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
+    return logits, state
+
+
+def _engine_post_attn(self, key, ctx, rows):
+    """ReLA's gated RMS norm on the merged heads (modules/rela.py:78-81, 95-109); identity otherwise."""
+    if not self.cfg.rela:
+        return ctx
+    raise L.ZeroB200Error("ReLA gated_rms_norm kernel is not built yet")
+
+
+Engine.encoding_fn = _engine_encoding_fn
+Engine.decoding_fn = _engine_decoding_fn
+Engine._post_attn = _engine_post_attn

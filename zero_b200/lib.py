@@ -1,0 +1,138 @@
+"""ctypes binding of libzero_b200.so (include/zero_b200.h).  PyTorch tensors are only the buffer carrier:
+every wrapper passes raw device pointers + the current CUDA stream through the C ABI.
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzero_b200.so")
+
+ZB_BF16, ZB_F32 = 0, 1
+ZB_K_MAJOR, ZB_MN_MAJOR = 0, 1
+ZB_EPI_BIAS, ZB_EPI_RELU, ZB_EPI_ACCUM, ZB_EPI_RELU_MASK = 1, 2, 4, 8
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("a", vp), ("b", vp), ("d", vp), ("m", i64), ("n", i64), ("k", i64),
+                ("lda", i64), ("ldb", i64), ("ldd", i64), ("a_layout", i32), ("b_layout", i32),
+                ("d_dtype", i32), ("flags", i32), ("bias", vp), ("mask", vp), ("ldmask", i64),
+                ("alpha", f32), ("split_k", i32)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp),
+                ("ldq", i64), ("ldk", i64), ("ldv", i64), ("ldo", i64),
+                ("bsq", i64), ("bsk", i64), ("bsv", i64), ("bso", i64),
+                ("batch", i32), ("heads", i32), ("lq", i32), ("lk", i32), ("dh", i32),
+                ("key_len", vp), ("causal", i32), ("q_offset", i32), ("scale", f32), ("inf_value", f32),
+                ("lse", vp), ("rpr_k", vp), ("rpr_v", vp), ("max_rel", i32), ("relu_attn", i32),
+                ("d_o", vp), ("dq", vp), ("dk", vp), ("dv", vp),
+                ("lddo", i64), ("lddq", i64), ("lddk", i64), ("lddv", i64),
+                ("bsdo", i64), ("bsdq", i64), ("bsdk", i64), ("bsdv", i64),
+                ("d_rpr_k", vp), ("d_rpr_v", vp), ("delta", vp), ("kv_group", i32)]
+
+
+class AddLnArgs(C.Structure):
+    _fields_ = [("x", vp), ("y", vp), ("out", vp), ("mean", vp), ("rstd", vp), ("scale", vp), ("offset", vp),
+                ("rows", i64), ("cols", i64), ("eps", f32),
+                ("d_out", vp), ("d_out2", vp), ("ds", vp), ("dscale", vp), ("doffset", vp)]
+
+
+class EmbedArgs(C.Structure):
+    _fields_ = [("ids", vp), ("table", vp), ("bias", vp), ("out", vp),
+                ("batch", i32), ("len", i32), ("dim", i32), ("vocab", i32),
+                ("shift", i32), ("zero_if_all_pad", i32), ("time", i32), ("mult", f32),
+                ("d_out", vp), ("d_table", vp), ("d_bias", vp), ("d_out2", vp)]
+
+
+class CeArgs(C.Structure):
+    _fields_ = [("logits", vp), ("ld", i64), ("labels", vp), ("batch", i32), ("seq_len", i32), ("nll", vp),
+                ("d_logits", vp), ("ldd", i64), ("vocab", i32), ("smooth", f32), ("loss_scale", f32),
+                ("per_sample", vp), ("loss", vp)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("param", vp), ("m", vp), ("v", vp), ("grad", vp), ("param_bf16", vp), ("n", i64),
+                ("beta1", f32), ("beta2", f32), ("eps", f32), ("scalars", vp)]
+
+
+class BeamArgs(C.Structure):
+    _fields_ = [("logits", vp), ("batch", i32), ("beam", i32), ("vocab", i32), ("time", i32),
+                ("eos_id", i32), ("pad_id", i32), ("temperature", f32), ("inf_value", f32),
+                ("length_penalty", f32), ("max_len", vp), ("max_penalty", vp), ("seq_cap", i32),
+                ("alive_seq", vp), ("alive_logp", vp), ("alive_score", vp),
+                ("fin_seq", vp), ("fin_score", vp), ("fin_flag", vp), ("parent", vp), ("tmp_seq", vp),
+                ("active", vp)]
+
+
+# every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_gemm", "zb_attention_fwd",
+    "zb_attention_bwd", "zb_add_ln_fwd", "zb_add_ln_bwd", "zb_embed_fwd", "zb_embed_bwd", "zb_softmax_ce",
+    "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
+    "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd",
+]
+
+_lib = None
+
+
+class ZeroB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZeroB200Error(
+            "libzero_b200.so not found at %s — build it with `python -m zero_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.zb_abi_version.restype = C.c_int
+    lib.zb_last_error_string.restype = C.c_char_p
+    lib.zb_launch_count.restype = C.c_int64
+    for name, argt in [
+        ("zb_gemm", [C.POINTER(GemmArgs), vp]),
+        ("zb_attention_fwd", [C.POINTER(AttentionArgs), vp]),
+        ("zb_attention_bwd", [C.POINTER(AttentionArgs), vp]),
+        ("zb_add_ln_fwd", [C.POINTER(AddLnArgs), vp]),
+        ("zb_add_ln_bwd", [C.POINTER(AddLnArgs), vp]),
+        ("zb_embed_fwd", [C.POINTER(EmbedArgs), vp]),
+        ("zb_embed_bwd", [C.POINTER(EmbedArgs), vp]),
+        ("zb_softmax_ce", [C.POINTER(CeArgs), vp]),
+        ("zb_colsum", [vp, i64, i64, i64, vp, vp]),
+        ("zb_cast_f32_bf16", [vp, vp, i64, vp]),
+        ("zb_cast_bf16_f32", [vp, vp, i64, vp]),
+        ("zb_adam_tf", [C.POINTER(AdamArgs), vp]),
+        ("zb_sumsq", [vp, i64, vp, vp]),
+        ("zb_beam_cond", [C.POINTER(BeamArgs), vp]),
+        ("zb_beam_step", [C.POINTER(BeamArgs), vp]),
+        ("zb_gather_rows", [vp, vp, vp, i64, i64, i64, vp]),
+        ("zb_prefix_mean_fwd", [vp, vp, i32, i32, i32, vp]),
+        ("zb_prefix_mean_bwd", [vp, vp, i32, i32, i32, vp]),
+    ]:
+        fn = getattr(lib, name)
+        fn.argtypes = argt
+        fn.restype = C.c_int
+    if lib.zb_abi_version() != 1:
+        raise ZeroB200Error("libzero_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().zb_last_error_string()
+        raise ZeroB200Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def launch_count() -> int:
+    return int(load().zb_launch_count())

@@ -1,0 +1,207 @@
+"""Thin Python wrappers: torch.Tensor (buffer carrier) -> raw pointers + current stream -> C ABI.
+
+Each function cites the reference call site it stands in for.  No arithmetic happens in Python/torch here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+bf16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rowmajor2d(t):
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D view"
+    return t.stride(0)
+
+
+def gemm(a, b, out, a_layout=L.ZB_K_MAJOR, b_layout=L.ZB_MN_MAJOR, bias=None, relu=False, accum=False,
+         relu_mask=None, alpha=1.0, split_k=0, m=None, n=None, k=None):
+    """D[m,n] (+)= alpha * sum_k A(m,k) B(n,k) (+bias) (relu) (*mask>0).  a/b/out: 2-D row-major views.
+    Layout semantics as in include/zero_b200.h: K-major operand is stored [rows, k]; MN-major is stored [k, rows].
+    func.linear (func.py:49,59): gemm(x, W, y, b_layout=MN_MAJOR, bias=b)."""
+    lib = L.load()
+    M = m if m is not None else (a.shape[0] if a_layout == L.ZB_K_MAJOR else a.shape[1])
+    Kd = k if k is not None else (a.shape[1] if a_layout == L.ZB_K_MAJOR else a.shape[0])
+    N = n if n is not None else (b.shape[0] if b_layout == L.ZB_K_MAJOR else b.shape[1])
+    flags = 0
+    if bias is not None:
+        flags |= L.ZB_EPI_BIAS
+    if relu:
+        flags |= L.ZB_EPI_RELU
+    if accum:
+        flags |= L.ZB_EPI_ACCUM
+    if relu_mask is not None:
+        flags |= L.ZB_EPI_RELU_MASK
+    args = L.GemmArgs(
+        _p(a), _p(b), _p(out), M, N, Kd, _rowmajor2d(a), _rowmajor2d(b), _rowmajor2d(out),
+        a_layout, b_layout, L.ZB_F32 if out.dtype == torch.float32 else L.ZB_BF16, flags,
+        _p(bias), _p(relu_mask), _rowmajor2d(relu_mask) if relu_mask is not None else 0, float(alpha), int(split_k))
+    L.check(lib.zb_gemm(C.byref(args), _stream()), "zb_gemm")
+    return out
+
+
+def linear_fwd(x, w, bias, out, relu=False):
+    """func.linear: out = x @ W + b (func.py:49,59), optional fused relu (func.py:332)."""
+    return gemm(x, w, out, L.ZB_K_MAJOR, L.ZB_MN_MAJOR, bias=bias, relu=relu)
+
+
+def linear_dgrad(dy, w, dx, relu_mask=None, accum=False):
+    """dx = dy @ W^T (gradient of func.linear wrt its input); optional relu mask of the producer."""
+    return gemm(dy, w, dx, L.ZB_K_MAJOR, L.ZB_K_MAJOR, relu_mask=relu_mask, accum=accum)
+
+
+def linear_wgrad(x, dy, dw):
+    """dW += x^T @ dy into the fp32 gradient arena (split-K, atomic accumulate)."""
+    return gemm(x, dy, dw, L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True)
+
+
+def colsum(x, out):
+    """db += sum_rows x (gradient of tf.nn.bias_add, func.py:59)."""
+    lib = L.load()
+    L.check(lib.zb_colsum(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(out), _stream()), "zb_colsum")
+
+
+def attention_args(q, k, v, o, heads, key_len=None, causal=False, q_offset=0, inf_value=1e8, lse=None,
+                   rpr_k=None, rpr_v=None, max_rel=0, relu_attn=False, kv_group=1):
+    """q/k/v/o: [B, L, heads*dh] views (last dim contiguous)."""
+    B, Lq, D = q.shape
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and o.stride(2) == 1
+    Lk = k.shape[1]
+    dh = D // heads
+    a = L.AttentionArgs()
+    a.q, a.k, a.v, a.o = _p(q), _p(k), _p(v), _p(o)
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(1), k.stride(1), v.stride(1), o.stride(1)
+    a.bsq, a.bsk, a.bsv, a.bso = q.stride(0), k.stride(0), v.stride(0), o.stride(0)
+    a.batch, a.heads, a.lq, a.lk, a.dh = B, heads, Lq, Lk, dh
+    a.key_len = _p(key_len)
+    a.causal, a.q_offset = int(causal), int(q_offset)
+    a.scale, a.inf_value = float(dh) ** -0.5, float(inf_value)
+    a.lse = _p(lse)
+    a.rpr_k, a.rpr_v, a.max_rel = _p(rpr_k), _p(rpr_v), int(max_rel)
+    a.relu_attn = int(relu_attn)
+    a.kv_group = int(kv_group)
+    return a
+
+
+def attention_fwd(a):
+    """func.dot_attention core (func.py:218-256)."""
+    L.check(L.load().zb_attention_fwd(C.byref(a), _stream()), "zb_attention_fwd")
+
+
+def attention_bwd(a, d_o, dq, dk, dv, delta, d_rpr_k=None, d_rpr_v=None):
+    a.d_o, a.dq, a.dk, a.dv = _p(d_o), _p(dq), _p(dk), _p(dv)
+    a.lddo, a.lddq, a.lddk, a.lddv = d_o.stride(1), dq.stride(1), dk.stride(1), dv.stride(1)
+    a.bsdo, a.bsdq, a.bsdk, a.bsdv = d_o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0)
+    a.delta = _p(delta)
+    a.d_rpr_k, a.d_rpr_v = _p(d_rpr_k), _p(d_rpr_v)
+    L.check(L.load().zb_attention_bwd(C.byref(a), _stream()), "zb_attention_bwd")
+
+
+def add_ln_fwd(x, y, out, scale, offset, mean=None, rstd=None, eps=1e-8):
+    """func.residual_fn + func.layer_norm (func.py:321-324, 289-303)."""
+    a = L.AddLnArgs()
+    a.x, a.y, a.out, a.mean, a.rstd = _p(x), _p(y), _p(out), _p(mean), _p(rstd)
+    a.scale, a.offset = _p(scale), _p(offset)
+    a.rows, a.cols, a.eps = x.numel() // x.shape[-1], x.shape[-1], float(eps)
+    L.check(L.load().zb_add_ln_fwd(C.byref(a), _stream()), "zb_add_ln_fwd")
+
+
+def add_ln_bwd(x, y, d_out, d_out2, mean, rstd, scale, ds, dscale, doffset):
+    a = L.AddLnArgs()
+    a.x, a.y, a.mean, a.rstd, a.scale = _p(x), _p(y), _p(mean), _p(rstd), _p(scale)
+    a.rows, a.cols = x.numel() // x.shape[-1], x.shape[-1]
+    a.d_out, a.d_out2, a.ds, a.dscale, a.doffset = _p(d_out), _p(d_out2), _p(ds), _p(dscale), _p(doffset)
+    L.check(L.load().zb_add_ln_bwd(C.byref(a), _stream()), "zb_add_ln_bwd")
+
+
+def embed_fwd(ids, table, bias, out, mult, shift=0, zero_if_all_pad=False, time=-1):
+    """tf.gather * sqrt(d) + bias + timing signal (models/transformer.py:29-31,104-117)."""
+    a = L.EmbedArgs()
+    a.ids, a.table, a.bias, a.out = _p(ids), _p(table), _p(bias), _p(out)
+    a.batch, a.len, a.dim, a.vocab = ids.shape[0], ids.shape[1], table.shape[1], table.shape[0]
+    a.shift, a.zero_if_all_pad, a.time, a.mult = int(shift), int(zero_if_all_pad), int(time), float(mult)
+    L.check(L.load().zb_embed_fwd(C.byref(a), _stream()), "zb_embed_fwd")
+
+
+def embed_bwd(ids, d_out, d_table, d_bias, mult, shift=0, d_out2=None):
+    a = L.EmbedArgs()
+    a.ids, a.d_out, a.d_table, a.d_bias, a.d_out2 = _p(ids), _p(d_out), _p(d_table), _p(d_bias), _p(d_out2)
+    a.batch, a.len, a.dim, a.vocab = ids.shape[0], ids.shape[1], d_table.shape[1], d_table.shape[0]
+    a.shift, a.mult = int(shift), float(mult)
+    L.check(L.load().zb_embed_bwd(C.byref(a), _stream()), "zb_embed_bwd")
+
+
+def softmax_ce(logits, labels, nll, smooth, d_logits=None, per_sample=None, loss=None, loss_scale=1.0):
+    """label-smoothed CE + masked per-sample mean + batch mean (models/transformer.py:198-211)."""
+    a = L.CeArgs()
+    a.logits, a.ld, a.labels = _p(logits), logits.stride(0), _p(labels)
+    a.batch, a.seq_len, a.nll = labels.shape[0], labels.shape[1], _p(nll)
+    a.d_logits, a.ldd = _p(d_logits), (d_logits.stride(0) if d_logits is not None else 0)
+    a.vocab, a.smooth, a.loss_scale = logits.shape[1], float(smooth), float(loss_scale)
+    a.per_sample, a.loss = _p(per_sample), _p(loss)
+    L.check(L.load().zb_softmax_ce(C.byref(a), _stream()), "zb_softmax_ce")
+
+
+def cast_f32_bf16(src, dst):
+    L.check(L.load().zb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "zb_cast_f32_bf16")
+
+
+def cast_bf16_f32(src, dst):
+    L.check(L.load().zb_cast_bf16_f32(_p(src), _p(dst), src.numel(), _stream()), "zb_cast_bf16_f32")
+
+
+def sumsq(x, out):
+    L.check(L.load().zb_sumsq(_p(x), x.numel(), _p(out), _stream()), "zb_sumsq")
+
+
+def adam_tf(param, m, v, grad, param_bf16, beta1, beta2, eps, scalars):
+    """tf.train.AdamOptimizer update on the flat arena (main.py:178-181)."""
+    a = L.AdamArgs(_p(param), _p(m), _p(v), _p(grad), _p(param_bf16), param.numel(), float(beta1), float(beta2),
+                   float(eps), _p(scalars))
+    L.check(L.load().zb_adam_tf(C.byref(a), _stream()), "zb_adam_tf")
+
+
+def gather_rows(src, index, dst, row_elems=None):
+    """dst[r, :row_elems] = src[index[r], :row_elems] over the leading dim (beam state reordering,
+    search.py:205-209).  Rows are dst[0].numel() elements apart; only the first row_elems are moved."""
+    rows = dst.shape[0]
+    pitch = dst[0].numel() * dst.element_size()
+    row_bytes = pitch if row_elems is None else row_elems * dst.element_size()
+    L.check(L.load().zb_gather_rows(_p(src), _p(index), _p(dst), rows, row_bytes, pitch, _stream()), "zb_gather_rows")
+
+
+def prefix_mean_fwd(x, y):
+    L.check(L.load().zb_prefix_mean_fwd(_p(x), _p(y), x.shape[0], x.shape[1], x.shape[2], _stream()),
+            "zb_prefix_mean_fwd")
+
+
+def prefix_mean_bwd(dy, dx):
+    L.check(L.load().zb_prefix_mean_bwd(_p(dy), _p(dx), dy.shape[0], dy.shape[1], dy.shape[2], _stream()),
+            "zb_prefix_mean_bwd")
+
+
+def beam_args(**kw):
+    a = L.BeamArgs()
+    for k, v in kw.items():
+        setattr(a, k, _p(v) if isinstance(v, torch.Tensor) else v)
+    return a
+
+
+def beam_cond(a):
+    L.check(L.load().zb_beam_cond(C.byref(a), _stream()), "zb_beam_cond")
+
+
+def beam_step(a):
+    L.check(L.load().zb_beam_step(C.byref(a), _stream()), "zb_beam_step")
