@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — train tokens/sec of Zero's Transformer-base (BASELINE.json configs[1]) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference's CPU path: oracle port, host cores)
+
+One "step" = one full optimizer step of the reference's hot loop (main.py:312): forward + backward of the 6+6
+d=512 model on this rank's batch of 64 x 64 source / 64 x 64 target tokens (4096 target tokens), one NCCL
+all-reduce of the flat fp32 gradient arena, global norms, TF-semantics Adam, bf16 weight refresh.
+Metric = non-pad target tokens per second (main.py:297 / :335-346), whole job.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, SRC_LEN, TGT_LEN, VOCAB = 64, 64, 64, 32000
+METRIC = "train_tokens_per_sec"
+UNIT = "target tokens/s"
+
+
+def workload_config(n):
+    return {"workload": "Transformer-base 6+6 d_model=512 h=8 f=2048 vocab=32k tied softmax, label_smooth=0.1, "
+                        "dropout=0, batch 64x(src 64, tgt 64)=4096 target tokens per GPU per step, "
+                        "fwd+bwd+allreduce+Adam (BASELINE.json configs[1])",
+            "global_batch_tokens": 4096 * n, "src_len": SRC_LEN, "tgt_len": TGT_LEN,
+            "parallelism": "dp%d" % n, "l2": "working set (1.2 GB of weights/optimizer state + 0.8 GB logits per "
+                                             "step) exceeds the 126 MB L2; no explicit flush"}
+
+
+def make_batch(seed, batch):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(3, VOCAB, (batch, SRC_LEN), generator=g, dtype=torch.int32)
+    tgt = torch.randint(3, VOCAB, (batch, TGT_LEN), generator=g, dtype=torch.int32)
+    src[:, -1] = 2
+    tgt[:, -1] = 2
+    return src, tgt
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU oracle leg
+def cpu_reference_step_fn(sample_batch):
+    """The reference's CPU path = oracle port (TF1.x cannot run here): fwd + bwd (autograd) + TF-Adam, fp32."""
+    import torch
+    from oracle import zero_oracle as zo
+    from zero_b200.params import transformer_base
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = transformer_base()
+    c = zo.Cfg(hp, VOCAB, VOCAB)
+    P = {k: v.requires_grad_(True) for k, v in zo.init_params(c, seed=1).items()}
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    Vv = {k: torch.zeros_like(v) for k, v in P.items()}
+    state = {"t": 0}
+
+    def step(seed):
+        src, tgt = make_batch(seed, sample_batch)
+        loss, _, _, _ = zo.train_loss(c, P, src.long(), tgt.long())
+        grads = torch.autograd.grad(loss, list(P.values()))
+        state["t"] += 1
+        with torch.no_grad():
+            for (k, p), g in zip(P.items(), grads):
+                newp, M[k], Vv[k] = zo.adam_tf_step(p, M[k], Vv[k], g, state["t"], 1e-4, 0.9, 0.98, 1e-8)
+                p.copy_(newp)
+        return float(loss), int((tgt != 0).sum())
+
+    return step, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 4
+    step, cores = cpu_reference_step_fn(sample_batch)
+    for i in range(args.warmup):
+        step(1000 + i)
+    t0 = time.perf_counter()
+    toks = 0
+    for i in range(args.steps):
+        toks += step(i)[1]
+    dt = time.perf_counter() - t0
+    val = toks / dt
+    sample = "%d sentences x (src 64, tgt 64) = %d target tokens per step (1/%d of the per-GPU batch), fp32, " \
+             "torch CPU" % (sample_batch, sample_batch * TGT_LEN, B_PER_GPU // sample_batch)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def gemm_roofline(eng, src, tgt, peaks):
+    """Dominant kernel = zb_gemm (tcgen05).  Re-run one step eagerly with CUDA events around every GEMM launch
+    (on the launching stream) and divide the algorithmic GEMM FLOPs by the summed launch durations."""
+    import torch
+    from zero_b200 import ops
+    records = []
+    real = ops.gemm
+
+    def timed(a, b, out, a_layout=0, b_layout=1, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = real(a, b, out, a_layout, b_layout, **kw)
+        e1.record()
+        M = kw.get("m") or (a.shape[0] if a_layout == 0 else a.shape[1])
+        K = kw.get("k") or (a.shape[1] if a_layout == 0 else a.shape[0])
+        N = kw.get("n") or (b.shape[0] if b_layout == 0 else b.shape[1])
+        records.append((e0, e1, 2.0 * M * N * K))
+        return r
+
+    ops.gemm = timed
+    try:
+        eng.forward_backward(src, tgt, compact=False)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
+    flops = sum(f for _, _, f in records)
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "gemm_bf16_tcgen05", "launches_per_step": len(records),
+            "gemm_ms_per_step": ms, "gemm_flops_per_step": flops,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+            if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from zero_b200 import lib as L
+    from zero_b200.engine import Engine
+    from zero_b200.params import transformer_base
+    from zero_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hp = transformer_base()
+    eng = Engine(hp, VOCAB, VOCAB, device="cuda:%d" % local)
+    eng.ps.init_random(1234)   # identical replicas on every rank (run.py:379-381 seeds)
+    trainer = Trainer(eng, hp, world_size=world, use_graph=not args.no_graph)
+
+    # host-resident (pinned) batches for the e2e leg; device-resident copies for the kernel-side `value`
+    n_batches = max(args.steps, 1)
+    host = [tuple(t.pin_memory() for t in make_batch(rank * 100003 + i, B_PER_GPU)) for i in range(n_batches)]
+    devb = [(s.cuda(non_blocking=True), t.cuda(non_blocking=True)) for s, t in host]
+    tokens_per_step = int(sum(int((t != 0).sum()) for _, t in host) / n_batches)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        trainer.step(*devb[i % n_batches])
+    barrier()
+
+    # ---- leg 1: inputs resident in HBM
+    launches0 = L.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = trainer.step(*devb[i % n_batches])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    eager_launches = L.launch_count() - launches0
+    final_loss = float(loss.item())
+
+    # ---- leg 2: end to end through the public step with HOST buffers (pinned H2D of ids + D2H of the loss)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        loss = trainer.step(*host[i % n_batches])
+        _ = loss.item()
+    t1.record()
+    barrier()
+    ms2 = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # kernel launches per step: graph replays do not pass through the ABI counter, so count one eager step
+    c0 = L.launch_count()
+    roof = gemm_roofline(eng, *devb[0], peaks)
+    per_step_kernels = L.launch_count() - c0 + 3  # + 2 sumsq + adam outside forward_backward
+    value = tokens_per_step * world * args.steps / (ms * 1e-3)
+    e2e = tokens_per_step * world * args.steps / (ms2 * 1e-3)
+    model_flops = 369623040.0 * tokens_per_step  # fwd+bwd FLOPs per (src,tgt) token pair
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_batch = 4
+        stepf, cores = cpu_reference_step_fn(sample_batch)
+        stepf(999)
+        t_0 = time.perf_counter()
+        toks = 0
+        nrep = 0
+        while time.perf_counter() - t_0 < 12.0 and nrep < 6:
+            toks += stepf(nrep)[1]
+            nrep += 1
+        dt = time.perf_counter() - t_0
+        cpu_baseline = {"value": toks / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d optimizer steps of %d sentences x (src 64, tgt 64) through the oracle port "
+                                  "(torch CPU fp32, fwd+bwd+Adam), same model config" % (nrep, sample_batch)}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B_PER_GPU * 64 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps},
+        "gpu_launches": int(per_step_kernels * args.steps),
+        "kernels_per_step": int(per_step_kernels),
+        "abi_calls_in_timed_region": int(eager_launches),
+        "cuda_graph": not args.no_graph,
+        "roofline": roof,
+        "model_tflops_per_gpu": model_flops / (ms / args.steps * 1e-3) / 1e12,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+        "final_loss": final_loss,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else min(args.steps, 50)
+        args.warmup = 1 if args.warmup is None else min(args.warmup, 3)
+        run_reference(args)
+    else:
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 5 if args.warmup is None else args.warmup
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -188,14 +188,15 @@ int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_stream_t stream)
  *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
  *   p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps);  also refreshes the bf16 compute copy.
  * grad_scale carries 1/world_size, 1/loss_scale and the clip_by_global_norm factor (utils/cycle.py:94-101).
- * `scalars` (device, fp32[2]) = {lr_t (already bias-corrected), grad_scale}; read on the device so the
- * step stays CUDA-graph capturable.
+ * lr_t is already bias-corrected by the host; clip_scale (device fp32[1], optional) multiplies grad_scale so
+ * the clip factor can be computed on the device without a host sync.
  */
 typedef struct {
   float* param; float* m; float* v; const float* grad; void* param_bf16;
   int64_t n;
   float beta1, beta2, eps;
-  const float* scalars;
+  float lr_t, grad_scale;
+  const float* clip_scale;
 } zb_adam_args;
 int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream);
 /* zb_sumsq: out[0] += sum x^2 (tf.global_norm, utils/cycle.py:94). */

@@ -268,8 +268,7 @@ def test_adam_tf_and_sumsq_and_colsum():
     p_ref, m_ref, v_ref = p.clone(), m.clone(), v.clone()
     for step in (1, 2, 3):
         lr_t = 0.01 * math.sqrt(1 - 0.98 ** step) / (1 - 0.9 ** step)
-        sc = torch.tensor([lr_t, 0.5], device=dev())
-        ops.adam_tf(p, m, v, g, pb, 0.9, 0.98, 1e-8, sc)
+        ops.adam_tf(p, m, v, g, pb, 0.9, 0.98, 1e-8, lr_t, 0.25, torch.tensor([2.0], device=dev()))
         p_ref, m_ref, v_ref = zo.adam_tf_step(p_ref, m_ref, v_ref, g * 0.5, step, 0.01, 0.9, 0.98, 1e-8)
     torch.testing.assert_close(p, p_ref, atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(pb.float(), p_ref, atol=1e-2, rtol=1e-2)

@@ -44,6 +44,10 @@ def test_train_loss_logits_grads_vs_golden(name):
     got = eng.ps.grad_dict()
     worst = ("", 0.0)
     for k, g in grads.items():
+        if float(g.abs().max()) < 1e-6:
+            # analytically-zero gradients (e.g. k_map/b_0: softmax is invariant to a per-query logit shift)
+            assert float(got[k].abs().max()) < 2e-3, k
+            continue
         r = _rel(got[k], g)
         if r > worst[1]:
             worst = (k, r)

@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 // m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2; p <- p - lr_t * m / (sqrt(v) + eps).
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-               __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps,
-               const float* __restrict__ scalars) {
-  const float lr_t = scalars[0], gs = scalars[1];
+               __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps, float lr_t, float gscale,
+               const float* __restrict__ clip_scale) {
+  const float gs = clip_scale ? gscale * clip_scale[0] : gscale;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
@@ -198,11 +198,12 @@ extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t strea
   return check_launch("zb_sumsq");
 }
 extern "C" int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream) {
-  ZB_REQUIRE(a && a->param && a->m && a->v && a->grad && a->scalars && a->n >= 0, "zb_adam_tf: bad args");
+  ZB_REQUIRE(a && a->param && a->m && a->v && a->grad && a->n >= 0, "zb_adam_tf: bad args");
   if (a->n == 0) return ZB_OK;
   const long long blocks = ((a->n + 3) / 4 + 255) / 256;
   adam_tf_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(a->param, a->m, a->v, a->grad, (__nv_bfloat16*)a->param_bf16,
-                                                          a->n, a->beta1, a->beta2, a->eps, a->scalars);
+                                                          a->n, a->beta1, a->beta2, a->eps, a->lr_t, a->grad_scale,
+                                                          a->clip_scale);
   return check_launch("zb_adam_tf");
 }
 extern "C" int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_bytes,

@@ -1,0 +1,75 @@
+"""The Transformer-family plugins of the hot path, registered under the reference's names
+(models/transformer.py:289, transformer_aan.py:331, transformer_rpr.py:297, transformer_rela.py:290,
+transformer_fuse.py:269).
+
+Callable contract, tensors being torch tensors instead of TF ones:
+  train_fn(features, params, initializer=None) -> {"loss": fp32[1]}      (also leaves d loss / d params in the
+        engine's gradient arena: the reference gets them from optimizer.compute_gradients, main.py:28)
+  score_fn(features, params, initializer=None) -> {"score": fp32[B]}
+  infer_fn(params) -> (encoding_fn(source) -> state, decoding_fn(target, state, time) -> (logits, state))
+The TF variable store is replaced by one Engine per (scope_name, model_name), created on first use and kept in
+`_engines` (the analogue of tf.AUTO_REUSE variable scopes).
+"""
+import copy
+
+from . import model
+from ..engine import Engine
+
+_engines = {}
+
+
+def get_engine(params, initializer=None):
+    key = (params.scope_name or "model", str(params.model_name).lower())
+    eng = _engines.get(key)
+    if eng is None:
+        eng = Engine(params)
+        eng.ps.init_random(int(getattr(params, "random_seed", 1234)))
+        _engines[key] = eng
+    return eng
+
+
+def reset_engines():
+    _engines.clear()
+
+
+def _closing_dropout(params):
+    """utils/util.py:106-114."""
+    for k in list(params.values()):
+        if "dropout" in k or "label_smoothing" in k:
+            setattr(params, k, 0.0)
+    return params
+
+
+def _check_dropout(params):
+    for k, v in params.values().items():
+        if "dropout" in k and v:
+            raise NotImplementedError(
+                "dropout > 0 is not implemented on the CUDA path yet (parity runs use dropout = 0, "
+                "like util.closing_dropout does for score/infer); got %s=%r" % (k, v))
+
+
+def _make(name):
+    def train_fn(features, params, initializer=None):
+        _check_dropout(params)
+        eng = get_engine(params, initializer)
+        loss = eng.forward_backward(features["source"], features["target"])
+        return {"loss": loss}
+
+    def score_fn(features, params, initializer=None):
+        params = _closing_dropout(copy.copy(params))
+        eng = get_engine(params, initializer)
+        return {"score": eng.score(features["source"], features["target"])}
+
+    def infer_fn(params):
+        params = _closing_dropout(copy.copy(params))
+        if getattr(params, "search_mode", "cache") != "cache":
+            raise NotImplementedError("search_mode='dev' (re-run the decoder on the prefix) is not on the hot path")
+        eng = get_engine(params)
+        eng.decode_length = int(params.decode_length)
+        return eng.encoding_fn, eng.decoding_fn
+
+    model.model_register(name, train_fn, score_fn, infer_fn)
+
+
+for _name in ("transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse"):
+    _make(_name)
