@@ -246,9 +246,32 @@ int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t row
  * zb_prefix_mean_{fwd,bwd}: y[b,t,:] = (sum_{s<=t} x[b,s,:]) / (t+1)   — Average Attention
  * (models/transformer_aan.py:92-117 with the "aan" bias of func.py:390-398 for an all-ones mask),
  * O(T d) scan instead of the reference's [T,T] matmul.  bwd: dx[b,s,:] = sum_{t>=s} dy[b,t,:]/(t+1).
+ * `lens` [batch] (or NULL = all valid) carries the target mask; mode 0 = the masked "aan" bias (pad rows -> 0),
+ * mode 1 = cumsum / count (aan_mask=False, transformer_aan.py:103-108).
  */
-int zb_prefix_mean_fwd(const void* x, void* y, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream);
-int zb_prefix_mean_bwd(const void* dy, void* dx, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream);
+int zb_prefix_mean_fwd(const void* x, void* y, const int32_t* lens, int32_t batch, int32_t len, int32_t dim,
+                       int32_t mode, zb_stream_t stream);
+int zb_prefix_mean_bwd(const void* dy, void* dx, const int32_t* lens, int32_t batch, int32_t len, int32_t dim,
+                       int32_t mode, zb_stream_t stream);
+/* zb_aan_step: cached decode of the average layer, y = (x + sum) / (time + 1); sum += x (fp32 running sum)
+ * (models/transformer_aan.py:110-112, func.py:262-272). */
+int zb_aan_step(const void* x, float* sum, void* y, int64_t n, int32_t time, zb_stream_t stream);
+/* zb_aan_gate_{fwd,bwd}: out = sigmoid(i) * x + sigmoid(f) * y with z = [i | f] (transformer_aan.py:185-189). */
+int zb_aan_gate_fwd(const void* x, const void* y, const void* z, void* out, int64_t rows, int32_t dim,
+                    zb_stream_t stream);
+int zb_aan_gate_bwd(const void* x, const void* y, const void* z, const void* dout, void* dx, void* dy, void* dz,
+                    int64_t rows, int32_t dim, zb_stream_t stream);
+/* zb_gated_rms_{fwd,bwd}: ReLA's post-attention norm scale * x * rsqrt(mean(x^2) + eps) * sigmoid(gate * x)
+ * (modules/rela.py:95-109).  rstd [rows] fp32 saved by fwd; bwd accumulates dscale / dgate (fp32 [cols]). */
+int zb_gated_rms_fwd(const void* x, void* out, float* rstd, const float* scale, const float* gate, int64_t rows,
+                     int64_t cols, float eps, zb_stream_t stream);
+int zb_gated_rms_bwd(const void* x, const void* dy, const float* rstd, const float* scale, const float* gate,
+                     void* dx, float* dscale, float* dgate, int64_t rows, int64_t cols, zb_stream_t stream);
+/* zb_add2d: out[r, :cols] = a[r, :cols] (+ b[r, :cols]) over strided 2-D bf16 views, b optional (plain copy).
+ * Merged attention o_cross + aan_o (func.py:274-275); tf.concat([x, y], -1) of the AAN gate input
+ * (models/transformer_aan.py:185) as two strided copies. */
+int zb_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows,
+             int64_t cols, zb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,92 @@
+"""world_size-2 check of the data-parallel host logic on CPU (gloo): per-rank gradients packed into the flat
+gradient arena (ParamStore layout, fused k|v views included), ONE all-reduce(sum), 1/N scale == gradient of the
+mean of the per-tower losses (main.py:42-43, utils/parallel.py:184-196; SURVEY.md section 4, identity 4)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import zero_oracle as zo
+from zero_b200.engine import ModelConfig, ParamStore
+from zero_b200.params import transformer_base
+
+
+def _hp():
+    return transformer_base(hidden_size=64, embed_size=64, filter_size=128, num_heads=2, num_encoder_layer=1,
+                            num_decoder_layer=1)
+
+
+def _batch(rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    src = torch.randint(3, 96, (3, 7), generator=g)
+    tgt = torch.randint(3, 96, (3, 6), generator=g)
+    src[0, 4:] = 0
+    tgt[1, 3:] = 0
+    return src, tgt
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    hp = _hp()
+    cfg = ModelConfig(hp, 96, 96)
+    c = zo.Cfg(hp, 96, 96)
+    ps = ParamStore(cfg, torch.device("cpu"))
+    P = {k: v.requires_grad_(True) for k, v in zo.init_params(c, seed=5).items()}
+    assert set(P) == set(ps.tf_names())
+    src, tgt = _batch(rank)
+    loss = zo.train_loss(c, P, src, tgt)[0]
+    grads = torch.autograd.grad(loss, [P[k] for k in ps.tf_names()])
+    for k, g in zip(ps.tf_names(), grads):
+        ps.tf_view(ps.grad, k).copy_(g)
+    dist.all_reduce(ps.grad, op=dist.ReduceOp.SUM)      # the single collective of the training step
+    ps.grad.mul_(1.0 / world)                           # folded into zb_adam_tf's grad_scale on the GPU
+    if rank == 0:
+        torch.save({k: ps.tf_view(ps.grad, k).clone() for k in ps.tf_names()}, out_path)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(180)
+def test_flat_arena_allreduce_equals_gradient_of_mean_loss(tmp_path):
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    hp = _hp()
+    c = zo.Cfg(hp, 96, 96)
+    P = {k: v.requires_grad_(True) for k, v in zo.init_params(c, seed=5).items()}
+    losses = [zo.train_loss(c, P, *_batch(r))[0] for r in range(2)]
+    mean_loss = (losses[0] + losses[1]) / 2
+    names = sorted(P)
+    ref = torch.autograd.grad(mean_loss, [P[k] for k in names])
+    for k, g in zip(names, ref):
+        torch.testing.assert_close(got[k], g, atol=1e-6, rtol=1e-5, msg=k)
+
+
+def test_param_store_layout_is_tma_legal_and_name_complete():
+    hp = transformer_base()
+    cfg = ModelConfig(hp, 32000, 32000)
+    ps = ParamStore.__new__(ParamStore)
+    ps.cfg, ps.slots, ps.tf_views = cfg, {}, {}
+    from collections import OrderedDict
+    ps.slots, ps.tf_views = OrderedDict(), OrderedDict()
+    ps._plan()
+    c = zo.Cfg(hp, 32000, 32000)
+    shapes = zo.param_shapes(c)
+    assert set(ps.tf_views) == set(shapes)
+    assert len(shapes) == 207                      # 207 variables at config 2
+    assert sum(int(torch.tensor(s).prod()) for s in shapes.values()) == 76907008
+    for name, (off, shape) in ps.slots.items():
+        assert off % 64 == 0, name                 # 128-byte aligned bf16 views

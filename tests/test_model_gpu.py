@@ -10,8 +10,9 @@ from tests.golden_util import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TRAIN_MODELS = ["transformer", "transformer_h4", "transformer_rpr"]
-DECODE_MODELS = ["transformer", "transformer_h4", "transformer_rpr"]
+TRAIN_MODELS = ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela"]
+SCORE_MODELS = TRAIN_MODELS + ["transformer_aan", "transformer_aan_cumsum", "transformer_fuse"]
+DECODE_MODELS = SCORE_MODELS
 
 
 def _engine(name):
@@ -56,11 +57,17 @@ def test_train_loss_logits_grads_vs_golden(name):
     assert worst[1] < 0.12, "worst gradient %s rel err %.4f" % worst
 
 
-@pytest.mark.parametrize("name", TRAIN_MODELS)
-def test_score_fn_vs_golden(name):
+@pytest.mark.parametrize("name", SCORE_MODELS)
+def test_score_fn_and_teacher_forced_logits_vs_golden(name):
     eng, z, hp, variables, grads = _engine(name)
-    sc = eng.score(torch.from_numpy(z["source"]), torch.from_numpy(z["target"]))
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    sc = eng.score(src, tgt)
     np.testing.assert_allclose(sc.cpu().numpy(), z["score"], atol=5e-2, rtol=1e-2)
+    loss, per_sample, logits = eng.train_loss(src, tgt)
+    want = torch.from_numpy(z["logits"])
+    mask = (tgt.reshape(-1) != 0)  # pad rows of the aan variants are don't-care for every consumer of logits
+    assert _rel(logits.cpu()[mask], want[mask]) < 2e-2
+    assert abs(float(loss[0]) - float(z["loss"])) < 2e-2
 
 
 @pytest.mark.parametrize("name", DECODE_MODELS)

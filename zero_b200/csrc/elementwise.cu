@@ -125,41 +125,6 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t*
   dst[r * pitch_vec + c] = src[(long long)index[r] * pitch_vec + c];
 }
 
-// y[b,t,:] = (sum_{s<=t} x[b,s,:]) / (t+1); one thread per (b, channel pair), sequential over t (T is short).
-__global__ void prefix_mean_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int batch,
-                                       int len, int dim) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int half = dim >> 1;
-  if (i >= (long long)batch * half) return;
-  const int b = (int)(i / half), c = (int)(i % half) * 2;
-  float2 acc = make_float2(0.f, 0.f);
-  for (int t = 0; t < len; ++t) {
-    const long long o = ((long long)b * len + t) * dim + c;
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + o));
-    acc.x += v.x;
-    acc.y += v.y;
-    const float inv = 1.f / (float)(t + 1);
-    *reinterpret_cast<uint32_t*>(y + o) = pack_bf16x2(acc.x * inv, acc.y * inv);
-  }
-}
-// dx[b,s,:] = sum_{t>=s} dy[b,t,:] / (t+1)
-__global__ void prefix_mean_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int batch,
-                                       int len, int dim) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int half = dim >> 1;
-  if (i >= (long long)batch * half) return;
-  const int b = (int)(i / half), c = (int)(i % half) * 2;
-  float2 acc = make_float2(0.f, 0.f);
-  for (int t = len - 1; t >= 0; --t) {
-    const long long o = ((long long)b * len + t) * dim + c;
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + o));
-    const float inv = 1.f / (float)(t + 1);
-    acc.x += v.x * inv;
-    acc.y += v.y * inv;
-    *reinterpret_cast<uint32_t*>(dx + o) = pack_bf16x2(acc.x, acc.y);
-  }
-}
-
 }  // namespace zb
 
 using namespace zb;
@@ -216,20 +181,4 @@ extern "C" int zb_gather_rows(const void* src, const int32_t* index, void* dst, 
   gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const uint4*)src, index, (uint4*)dst, rows,
                                                                              vec, pitch_bytes / 16);
   return check_launch("zb_gather_rows");
-}
-extern "C" int zb_prefix_mean_fwd(const void* x, void* y, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream) {
-  ZB_REQUIRE(x && y && batch >= 0 && len > 0 && dim % 2 == 0, "zb_prefix_mean_fwd: bad args");
-  const long long n = (long long)batch * (dim / 2);
-  if (n == 0) return ZB_OK;
-  prefix_mean_fwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
-                                                                             batch, len, dim);
-  return check_launch("zb_prefix_mean_fwd");
-}
-extern "C" int zb_prefix_mean_bwd(const void* dy, void* dx, int32_t batch, int32_t len, int32_t dim, zb_stream_t stream) {
-  ZB_REQUIRE(dy && dx && batch >= 0 && len > 0 && dim % 2 == 0, "zb_prefix_mean_bwd: bad args");
-  const long long n = (long long)batch * (dim / 2);
-  if (n == 0) return ZB_OK;
-  prefix_mean_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
-                                                                             batch, len, dim);
-  return check_launch("zb_prefix_mean_bwd");
 }

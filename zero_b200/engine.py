@@ -321,19 +321,21 @@ class Engine(object):
                                rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
                                relu_attn=c.rela)
         ops.attention_fwd(a)
+        feed = self._post_fwd(key, ctx, N, sv, tag)
         y = ws.get(tag + ".y", (N, c.d))
-        ops.linear_fwd(ctx, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
-        sv.update(qkv=qkv, ctx=ctx, lse=lse, attn=a, y=y)
+        ops.linear_fwd(feed, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
+        sv.update(qkv=qkv, ctx=ctx, feed=feed, lse=lse, attn=a, y=y)
         return y
 
     def _self_attn_bwd(self, key, x, dy, B, Lq, sv, tag):
         """Returns dx (gradient wrt the sublayer input through the attention branch)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        ops.linear_wgrad(sv["ctx"], dy, ps.g(key + ".o.W"))
+        ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W"))
         ops.colsum(dy, ps.g(key + ".o.b"))
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
+        dctx = self._post_bwd(key, dctx, N, sv, tag)
         dqkv = ws.get(tag + ".dqkv", (N, 3 * c.d))
         d3 = dqkv.view(B, Lq, 3 * c.d)
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
@@ -362,18 +364,20 @@ class Engine(object):
                                rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
                                relu_attn=c.rela)
         ops.attention_fwd(a)
+        feed = self._post_fwd(key, ctx, N, sv, tag)
         y = ws.get(tag + ".y", (N, c.d))
-        ops.linear_fwd(ctx, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
-        sv.update(q=q, kv=kv, ctx=ctx, lse=lse, attn=a, y=y)
+        ops.linear_fwd(feed, ps.w(key + ".o.W"), ps.p(key + ".o.b"), y)
+        sv.update(q=q, kv=kv, ctx=ctx, feed=feed, lse=lse, attn=a, y=y)
         return y
 
     def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        ops.linear_wgrad(sv["ctx"], dy, ps.g(key + ".o.W"))
+        ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W"))
         ops.colsum(dy, ps.g(key + ".o.b"))
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
+        dctx = self._post_bwd(key, dctx, N, sv, tag)
         dq = ws.get(tag + ".dq", (N, c.d))
         dkv = ws.get(tag + ".dkv", (B * S, 2 * c.d))
         dkv3 = dkv.view(B, S, 2 * c.d)
@@ -388,6 +392,26 @@ class Engine(object):
         ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dq, ps.w(key + ".q.W"), dx)
+        return dx
+
+    def _post_fwd(self, key, ctx, N, sv, tag):
+        """ReLA's gated RMS norm between the merged heads and o_map (modules/rela.py:78-81); identity otherwise."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        if not c.rela:
+            return ctx
+        out = ws.get(tag + ".ctxn", (N, c.d))
+        rstd = ws.get(tag + ".rrstd", (N,), f32)
+        ops.gated_rms_fwd(ctx, out, rstd, ps.p(key + ".post_scale"), ps.p(key + ".post_gate"), c.eps)
+        sv["rrstd"] = rstd
+        return out
+
+    def _post_bwd(self, key, dctx, N, sv, tag):
+        c, ps, ws = self.cfg, self.ps, self.ws
+        if not c.rela:
+            return dctx
+        dx = ws.get(tag + ".dctx2", (N, c.d))
+        ops.gated_rms_bwd(sv["ctx"], dctx, sv["rrstd"], ps.p(key + ".post_scale"), ps.p(key + ".post_gate"), dx,
+                          ps.g(key + ".post_scale"), ps.g(key + ".post_gate"))
         return dx
 
     def _ffn_fwd(self, key, x, N, sv, tag):
@@ -480,8 +504,8 @@ class Engine(object):
     def decode_train(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D"):
         """models/transformer.py:87-218 in training mode.  Returns (loss[1], per_sample[B], logits fp32 [N,V])."""
         c, ps, ws = self.cfg, self.ps, self.ws
-        if not (c.model == "transformer" or c.rpr):
-            raise L.ZeroB200Error("training path for %s is not built yet" % c.model)
+        if c.aan or c.fuse:
+            return self._decode_train_avg(target, enc, src_len, S, smooth, want_grad, save, tag)
         B, T = target.shape
         N = B * T
         x = ws.get(tag + ".x0", (N, c.d))
@@ -636,13 +660,13 @@ def _engine_encoding_fn(self, source):
 def _engine_decoding_fn(self, target, state, time):
     """decoding_fn(target [R,1], state, time) -> (logits fp32 [R, V], state)  (models/transformer.py:267-283)."""
     c, ps, ws = self.cfg, self.ps, self.ws
+    if state.mem is None:
+        state.begin_search(state.K)
     if c.aan or c.fuse:
-        raise L.ZeroB200Error("cached decode for %s is not built yet" % c.model)
+        return self._decoding_fn_avg(target, state, time)
     t = int(time)
     R = target.shape[0]
     K = state.K
-    if state.mem is None:
-        state.begin_search(K)
     x = ws.get("dec.x", (R, c.d))
     ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x.view(R, 1, c.d), mult=c.d ** 0.5,
                   zero_if_all_pad=True, time=t)
@@ -686,11 +710,16 @@ def _engine_decoding_fn(self, target, state, time):
 
 def _engine_post_attn(self, key, ctx, rows):
     """ReLA's gated RMS norm on the merged heads (modules/rela.py:78-81, 95-109); identity otherwise."""
-    if not self.cfg.rela:
+    c, ps = self.cfg, self.ps
+    if not c.rela:
         return ctx
-    raise L.ZeroB200Error("ReLA gated_rms_norm kernel is not built yet")
+    out = self.ws.get("dec.ctxn", (rows, c.d))
+    ops.gated_rms_fwd(ctx, out, None, ps.p(key + ".post_scale"), ps.p(key + ".post_gate"), c.eps)
+    return out
 
 
 Engine.encoding_fn = _engine_encoding_fn
 Engine.decoding_fn = _engine_decoding_fn
 Engine._post_attn = _engine_post_attn
+
+from . import engine_avg  # noqa: E402,F401  (registers the average-attention family on Engine / DecodeState)

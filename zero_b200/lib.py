@@ -77,7 +77,8 @@ EXPORTS = [
     "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_gemm", "zb_attention_fwd",
     "zb_attention_bwd", "zb_add_ln_fwd", "zb_add_ln_bwd", "zb_embed_fwd", "zb_embed_bwd", "zb_softmax_ce",
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
-    "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd",
+    "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
+    "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
 ]
 
 _lib = None
@@ -117,8 +118,14 @@ def load():
         ("zb_beam_cond", [C.POINTER(BeamArgs), vp]),
         ("zb_beam_step", [C.POINTER(BeamArgs), vp]),
         ("zb_gather_rows", [vp, vp, vp, i64, i64, i64, vp]),
-        ("zb_prefix_mean_fwd", [vp, vp, i32, i32, i32, vp]),
-        ("zb_prefix_mean_bwd", [vp, vp, i32, i32, i32, vp]),
+        ("zb_prefix_mean_fwd", [vp, vp, vp, i32, i32, i32, i32, vp]),
+        ("zb_prefix_mean_bwd", [vp, vp, vp, i32, i32, i32, i32, vp]),
+        ("zb_aan_step", [vp, vp, vp, i64, i32, vp]),
+        ("zb_aan_gate_fwd", [vp, vp, vp, vp, i64, i32, vp]),
+        ("zb_aan_gate_bwd", [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
+        ("zb_gated_rms_fwd", [vp, vp, vp, vp, vp, i64, i64, f32, vp]),
+        ("zb_gated_rms_bwd", [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
+        ("zb_add2d", [vp, i64, vp, i64, vp, i64, i64, i64, vp]),
     ]:
         fn = getattr(lib, name)
         fn.argtypes = argt

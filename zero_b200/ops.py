@@ -182,14 +182,48 @@ def gather_rows(src, index, dst, row_elems=None):
     L.check(L.load().zb_gather_rows(_p(src), _p(index), _p(dst), rows, row_bytes, pitch, _stream()), "zb_gather_rows")
 
 
-def prefix_mean_fwd(x, y):
-    L.check(L.load().zb_prefix_mean_fwd(_p(x), _p(y), x.shape[0], x.shape[1], x.shape[2], _stream()),
-            "zb_prefix_mean_fwd")
+def prefix_mean_fwd(x, y, lens=None, mode=0):
+    """Average Attention prefix mean (models/transformer_aan.py:99-108; func.py:389-398)."""
+    L.check(L.load().zb_prefix_mean_fwd(_p(x), _p(y), _p(lens), x.shape[0], x.shape[1], x.shape[2], int(mode),
+                                        _stream()), "zb_prefix_mean_fwd")
 
 
-def prefix_mean_bwd(dy, dx):
-    L.check(L.load().zb_prefix_mean_bwd(_p(dy), _p(dx), dy.shape[0], dy.shape[1], dy.shape[2], _stream()),
-            "zb_prefix_mean_bwd")
+def prefix_mean_bwd(dy, dx, lens=None, mode=0):
+    L.check(L.load().zb_prefix_mean_bwd(_p(dy), _p(dx), _p(lens), dy.shape[0], dy.shape[1], dy.shape[2], int(mode),
+                                        _stream()), "zb_prefix_mean_bwd")
+
+
+def aan_step(x, running_sum, y, time):
+    """cached decode of the average layer (models/transformer_aan.py:110-112)."""
+    L.check(L.load().zb_aan_step(_p(x), _p(running_sum), _p(y), x.numel(), int(time), _stream()), "zb_aan_step")
+
+
+def aan_gate_fwd(x, y, z, out):
+    """y' = sigmoid(i) x + sigmoid(f) y (models/transformer_aan.py:185-189)."""
+    L.check(L.load().zb_aan_gate_fwd(_p(x), _p(y), _p(z), _p(out), x.numel() // x.shape[-1], x.shape[-1], _stream()),
+            "zb_aan_gate_fwd")
+
+
+def aan_gate_bwd(x, y, z, dout, dx, dy, dz):
+    L.check(L.load().zb_aan_gate_bwd(_p(x), _p(y), _p(z), _p(dout), _p(dx), _p(dy), _p(dz),
+                                     x.numel() // x.shape[-1], x.shape[-1], _stream()), "zb_aan_gate_bwd")
+
+
+def gated_rms_fwd(x, out, rstd, scale, gate, eps):
+    """ReLA gated RMS norm (modules/rela.py:95-109)."""
+    L.check(L.load().zb_gated_rms_fwd(_p(x), _p(out), _p(rstd), _p(scale), _p(gate), x.numel() // x.shape[-1],
+                                      x.shape[-1], float(eps), _stream()), "zb_gated_rms_fwd")
+
+
+def gated_rms_bwd(x, dy, rstd, scale, gate, dx, dscale, dgate):
+    L.check(L.load().zb_gated_rms_bwd(_p(x), _p(dy), _p(rstd), _p(scale), _p(gate), _p(dx), _p(dscale), _p(dgate),
+                                      x.numel() // x.shape[-1], x.shape[-1], _stream()), "zb_gated_rms_bwd")
+
+
+def add2d(a, b, out):
+    """out = a (+ b) over row-major 2-D bf16 views (strided allowed); b=None is a strided copy."""
+    L.check(L.load().zb_add2d(_p(a), a.stride(0), _p(b), b.stride(0) if b is not None else 0, _p(out), out.stride(0),
+                              a.shape[0], a.shape[1], _stream()), "zb_add2d")
 
 
 def beam_args(**kw):
