@@ -201,6 +201,9 @@ def _attn_ref(q, k, v, heads, key_len, causal, q_off, inf, ek, ev, max_rel, relu
     dict(B=4, h=8, Lq=64, Lk=64, dh=64, causal=False, klen=True),
     dict(B=4, h=8, Lq=64, Lk=64, dh=64, causal=True, klen=False),
     dict(B=2, h=8, Lq=128, Lk=128, dh=64, causal=True, klen=False),
+    dict(B=3, h=2, Lq=40, Lk=70, dh=64, causal=False, klen=True),
+    dict(B=2, h=4, Lq=100, Lk=100, dh=64, causal=True, klen=False),
+    dict(B=2, h=2, Lq=17, Lk=200, dh=64, causal=False, klen=True),
 ])
 def test_attention_fwd_bwd(cfg):
     from zero_b200 import ops

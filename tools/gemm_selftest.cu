@@ -152,6 +152,14 @@ static void time_case(int M, int N, int K, int a_mn, int b_mn, int flags, int d_
   g.a = dA; g.b = dB; g.d = dD; g.m = M; g.n = N; g.k = K;
   g.lda = a_mn ? M : K; g.ldb = b_mn ? N : K; g.ldd = N;
   g.a_layout = a_mn; g.b_layout = b_mn; g.d_dtype = d_f32 ? ZB_F32 : ZB_BF16; g.flags = flags; g.alpha = 1.f;
+  float* dBias;
+  CK(cudaMalloc(&dBias, (size_t)N * 4));
+  CK(cudaMemset(dBias, 0, (size_t)N * 4));
+  g.bias = dBias;
+  if (zb_gemm(&g, 0) != 0) {
+    printf("time_case: %s\n", zb_last_error_string());
+    return;
+  }
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -180,6 +188,10 @@ static int run_case_f(const Case& c, bool verbose) {
 int main(int argc, char** argv) {
   int fails = 0;
   printf("abi %d\n", zb_abi_version());
+  if (argc > 8 && !strcmp(argv[1], "--one")) {  // --one m n k a_mn b_mn flags f32 : time (or profile) one shape
+    time_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
+    return 0;
+  }
   if (argc > 3 && !strcmp(argv[1], "--layout")) {
     only_a = atoi(argv[2]);
     only_b = atoi(argv[3]);

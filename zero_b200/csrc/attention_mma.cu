@@ -1,8 +1,424 @@
-// attention_mma.cu — tensor-core fast path for plain softmax attention (placeholder until enabled).
+// attention_mma.cu — K2/K3 fast path: flash-style fused attention on the warp-level tensor cores (mma.sync
+// m16n8k16 bf16 -> fp32) for the plain softmax case with dh = 64 (every attention of Transformer-base: encoder
+// self, decoder causal self, decoder cross; func.py:218-256).  Logits / probabilities live only in registers;
+// the backward recomputes them from q, k and the saved log-sum-exp.
+//   fwd : CTA = 64 query rows of one (batch, head), 4 warps x 16 rows, 64-key tiles, online softmax
+//   bwd : dq kernel (CTA per 64 queries, loops over key tiles) + dk/dv kernel (CTA per 64 keys, loops over
+//         query tiles); no atomics, deterministic
+// Shared-memory tiles are [64][64] bf16 with a 16-byte-chunk XOR swizzle (chunk ^= row & 7) so ldmatrix is
+// bank-conflict free.  Masks come from key lengths / causal index (func.attention_bias, func.py:372-388) with the
+// reference's additive -inf_value.  (A tcgen05/TMEM version is future work: at S = 64 the QK^T / PV tiles are
+// 64x64x64 and attention is ~2% of the layer FLOPs; the dense contractions run on tcgen05 in gemm_tcgen05.cu.)
+#include <math.h>
+
 #include "zb_common.h"
+#include "zb_ptx.cuh"
 
 namespace zb {
-bool attention_mma_supported(const zb_attention_args* a, bool bwd) { return false; }
-int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) { return ZB_EUNSUPPORTED; }
-int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) { return ZB_EUNSUPPORTED; }
+
+namespace fa {
+
+constexpr int BQ = 64, BK = 64, DH = 64, NT = 128;
+
+struct Params {
+  const __nv_bfloat16 *q, *k, *v, *o, *d_o;
+  __nv_bfloat16 *out, *dq, *dk, *dv;
+  long long ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso;
+  long long lddo, lddq, lddk, lddv, bsdo, bsdq, bsdk, bsdv;
+  int heads, lq, lk, causal, q_offset, kv_group;
+  const int32_t* key_len;
+  float scale, inf_value;
+  float *lse, *delta;
+};
+
+__device__ __forceinline__ int swz(int r, int c) { return r * 64 + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  const uint32_t s = smem_u32(smem);
+  const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// 64 x 64 bf16 tile, rows [r0, r0 + 64) of a [rows, ld] view starting at column 0 of `src`
+__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int chunk = threadIdx.x + i * NT;  // 512 chunks of 16 B
+    const int r = chunk >> 3, ch = chunk & 7;
+    const bool ok = r < rows_valid;
+    cp_async16(dst + r * 64 + ((ch ^ (r & 7)) << 3), src + (long long)(ok ? r : 0) * ld + ch * 8, ok);
+  }
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragments (16 rows x 64 k) of the warp's row block from a row-major tile
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* tile, int row0) {
+  const int lane = threadIdx.x & 31;
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], tile + swz(r, ks * 16 + (lane >> 4) * 8));
+}
+
+// acc[nt] += A(16 x 64) * B^T where B tile is stored [n][k] (k contiguous): acc is 16 x 64 (8 n-tiles)
+__device__ __forceinline__ void gemm_nk(float (&acc)[8][4], const uint32_t (&a)[4][4], const __nv_bfloat16* tile) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      const int n = np * 16 + (lane & 7) + (lane >> 4) * 8;
+      const int kc = ks * 16 + ((lane >> 3) & 1) * 8;
+      ldsm_x4(b, tile + swz(n, kc));
+      mma16816(acc[2 * np], a[ks], b[0], b[1]);
+      mma16816(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+// acc[nt] += P(16 x 64, A fragments) * B where B tile is stored [k][n] (n contiguous): acc is 16 x 64
+__device__ __forceinline__ void gemm_kn(float (&acc)[8][4], const uint32_t (&a)[4][4], const __nv_bfloat16* tile) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      const int kr = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int nc = np * 16 + (lane >> 4) * 8;
+      ldsm_x4_t(b, tile + swz(kr, nc));
+      mma16816(acc[2 * np], a[ks], b[0], b[1]);
+      mma16816(acc[2 * np + 1], a[ks], b[2], b[3]);
+    }
+  }
+}
+// C-layout fp32 (16 x 64) -> A-layout bf16 fragments for the next GEMM's k dimension
+__device__ __forceinline__ void c_to_a(uint32_t (&a)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = pack_bf16x2(c[2 * ks][0], c[2 * ks][1]);
+    a[ks][1] = pack_bf16x2(c[2 * ks][2], c[2 * ks][3]);
+    a[ks][2] = pack_bf16x2(c[2 * ks + 1][0], c[2 * ks + 1][1]);
+    a[ks][3] = pack_bf16x2(c[2 * ks + 1][2], c[2 * ks + 1][3]);
+  }
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ void store_c_bf16(__nv_bfloat16* base, long long ld, int row0, int rows_valid,
+                                             const float (&c)[8][4], float mul0, float mul1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * t;
+    if (row0 + g < rows_valid)
+      *reinterpret_cast<uint32_t*>(base + (long long)(row0 + g) * ld + col) = pack_bf16x2(c[nt][0] * mul0, c[nt][1] * mul0);
+    if (row0 + g + 8 < rows_valid)
+      *reinterpret_cast<uint32_t*>(base + (long long)(row0 + g + 8) * ld + col) =
+          pack_bf16x2(c[nt][2] * mul1, c[nt][3] * mul1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int kb = b / p.kv_group;
+  const int kl = p.key_len ? p.key_len[kb] : p.lk;
+  const __nv_bfloat16* qb = p.q + (long long)b * p.bsq + (long long)q0 * p.ldq + h * DH;
+  load_tile(sQ, qb, p.ldq, p.lq - q0);
+  cp_async_wait_all();
+  __syncthreads();
+  uint32_t qa[4][4];
+  load_a_frags(qa, sQ, warp * 16);
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  const int row_abs0 = q0 + warp * 16 + g + p.q_offset;
+  int k_end = p.lk;
+  if (p.causal) k_end = min(p.lk, q0 + BQ + p.q_offset);  // keys beyond the last query row contribute exp(-inf) = 0
+  for (int kt = 0; kt < k_end; kt += BK) {
+    __syncthreads();
+    load_tile(sK, p.k + (long long)kb * p.bsk + (long long)kt * p.ldk + h * DH, p.ldk, p.lk - kt);
+    load_tile(sV, p.v + (long long)kb * p.bsv + (long long)kt * p.ldv + h * DH, p.ldv, p.lk - kt);
+    cp_async_wait_all();
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+    gemm_nk(s, qa, sK);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kt + nt * 8 + 2 * t + (j & 1);
+        const int ra = row_abs0 + (j >> 1) * 8;
+        const bool inb = col < p.lk;
+        const bool valid = inb && col < kl && (!p.causal || col <= ra);
+        float v = s[nt][j] * p.scale;
+        v = inb ? (valid ? v : v - p.inf_value) : -INFINITY;
+        s[nt][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float mn = fmaxf(m[r], quad_max(mx[r]));
+      corr[r] = __expf(m[r] - mn);
+      m[r] = mn;
+      l[r] *= corr[r];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = __expf(s[nt][j] - m[j >> 1]);
+        s[nt][j] = pv;
+        l[j >> 1] += pv;
+        o[nt][j] *= corr[j >> 1];
+      }
+    uint32_t pa[4][4];
+    c_to_a(pa, s);
+    gemm_kn(o, pa, sV);
+  }
+  const float l0 = quad_sum(l[0]), l1 = quad_sum(l[1]);
+  __nv_bfloat16* ob = p.out + (long long)b * p.bso + (long long)q0 * p.ldo + h * DH;
+  store_c_bf16(ob, p.ldo, warp * 16, p.lq - q0, o, 1.f / l0, 1.f / l1);
+  if (t == 0 && p.lse) {
+    const int r0 = q0 + warp * 16 + g;
+    float* lp = p.lse + ((long long)b * p.heads + h) * p.lq;
+    if (r0 < p.lq) lp[r0] = m[0] + __logf(l0);
+    if (r0 + 8 < p.lq) lp[r0 + 8] = m[1] + __logf(l1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dq
+__global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int kl = p.key_len ? p.key_len[b] : p.lk;
+  const int rows = p.lq - q0;
+  uint32_t qa[4][4], doa[4][4];
+  // dO and O tiles -> delta = rowsum(dO * O); dO fragments stay in registers
+  load_tile(sK, p.d_o + (long long)b * p.bsdo + (long long)q0 * p.lddo + h * DH, p.lddo, rows);
+  load_tile(sV, p.o + (long long)b * p.bso + (long long)q0 * p.ldo + h * DH, p.ldo, rows);
+  load_tile(sQ, p.q + (long long)b * p.bsq + (long long)q0 * p.ldq + h * DH, p.ldq, rows);
+  cp_async_wait_all();
+  __syncthreads();
+  load_a_frags(qa, sQ, warp * 16);
+  load_a_frags(doa, sK, warp * 16);
+  float delta[2] = {0.f, 0.f};
+  {
+    uint32_t oa[4][4];
+    load_a_frags(oa, sV, warp * 16);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float2 x = unpack_bf16x2(doa[ks][r]), y = unpack_bf16x2(oa[ks][r]);
+        delta[r & 1] += x.x * y.x + x.y * y.y;  // regs 0,2 -> row g ; regs 1,3 -> row g + 8
+      }
+    delta[0] = quad_sum(delta[0]);
+    delta[1] = quad_sum(delta[1]);
+  }
+  const int r0 = q0 + warp * 16 + g;
+  const long long lbase = ((long long)b * p.heads + h) * p.lq;
+  float lse[2] = {r0 < p.lq ? p.lse[lbase + r0] : 0.f, r0 + 8 < p.lq ? p.lse[lbase + r0 + 8] : 0.f};
+  if (t == 0) {
+    if (r0 < p.lq) p.delta[lbase + r0] = delta[0];
+    if (r0 + 8 < p.lq) p.delta[lbase + r0 + 8] = delta[1];
+  }
+  float dq[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+  const int row_abs0 = r0 + p.q_offset;
+  int k_end = p.lk;
+  if (p.causal) k_end = min(p.lk, q0 + BQ + p.q_offset);
+  for (int kt = 0; kt < k_end; kt += BK) {
+    __syncthreads();
+    load_tile(sK, p.k + (long long)b * p.bsk + (long long)kt * p.ldk + h * DH, p.ldk, p.lk - kt);
+    load_tile(sV, p.v + (long long)b * p.bsv + (long long)kt * p.ldv + h * DH, p.ldv, p.lk - kt);
+    cp_async_wait_all();
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = 0.f;
+    gemm_nk(s, qa, sK);
+    gemm_nk(dp, doa, sV);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = kt + nt * 8 + 2 * t + (j & 1);
+        const int ra = row_abs0 + (j >> 1) * 8;
+        const bool inb = col < p.lk;
+        const bool valid = inb && col < kl && (!p.causal || col <= ra);
+        float v = s[nt][j] * p.scale;
+        v = valid ? v : v - p.inf_value;
+        const float pv = inb ? __expf(v - lse[j >> 1]) : 0.f;
+        s[nt][j] = pv * (dp[nt][j] - delta[j >> 1]);
+      }
+    uint32_t dsa[4][4];
+    c_to_a(dsa, s);
+    gemm_kn(dq, dsa, sK);
+  }
+  store_c_bf16(p.dq + (long long)b * p.bsdq + (long long)q0 * p.lddq + h * DH, p.lddq, warp * 16, rows, dq, p.scale,
+               p.scale);
+}
+
+// ------------------------------------------------------------------------------------------------ backward: dk, dv
+__global__ void __launch_bounds__(NT) bwd_dkv_kernel(const Params p) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sDO[64 * 64];
+  __shared__ float sLse[64], sDelta[64];
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int kl = p.key_len ? p.key_len[b] : p.lk;
+  const int krows = p.lk - k0;
+  uint32_t ka[4][4], va[4][4];
+  load_tile(sQ, p.k + (long long)b * p.bsk + (long long)k0 * p.ldk + h * DH, p.ldk, krows);
+  load_tile(sDO, p.v + (long long)b * p.bsv + (long long)k0 * p.ldv + h * DH, p.ldv, krows);
+  cp_async_wait_all();
+  __syncthreads();
+  load_a_frags(ka, sQ, warp * 16);
+  load_a_frags(va, sDO, warp * 16);
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+  const int key0 = k0 + warp * 16 + g;
+  const long long lbase = ((long long)b * p.heads + h) * p.lq;
+  int q_begin = 0;
+  if (p.causal) q_begin = max(0, (k0 - p.q_offset) / BQ * BQ);  // queries before the first key of the block see none of it
+  for (int qt = q_begin; qt < p.lq; qt += BQ) {
+    __syncthreads();
+    load_tile(sQ, p.q + (long long)b * p.bsq + (long long)qt * p.ldq + h * DH, p.ldq, p.lq - qt);
+    load_tile(sDO, p.d_o + (long long)b * p.bsdo + (long long)qt * p.lddo + h * DH, p.lddo, p.lq - qt);
+    if (threadIdx.x < 64) {
+      const int i = qt + threadIdx.x;
+      sLse[threadIdx.x] = i < p.lq ? p.lse[lbase + i] : 0.f;
+      sDelta[threadIdx.x] = i < p.lq ? p.delta[lbase + i] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[i][j] = dpt[i][j] = 0.f;
+    gemm_nk(st, ka, sQ);     // S^T[key, query] = K Q^T
+    gemm_nk(dpt, va, sDO);   // dP^T[key, query] = V dO^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int qi = nt * 8 + 2 * t + (j & 1);
+        const int key = key0 + (j >> 1) * 8;
+        const bool inb = qt + qi < p.lq && key < p.lk;
+        const bool valid = key < kl && (!p.causal || key <= qt + qi + p.q_offset);
+        float v = st[nt][j] * p.scale;
+        v = valid ? v : v - p.inf_value;
+        const float pv = inb ? __expf(v - sLse[qi]) : 0.f;
+        st[nt][j] = pv;
+        dpt[nt][j] = pv * (dpt[nt][j] - sDelta[qi]);
+      }
+    uint32_t pa[4][4], dsa[4][4];
+    c_to_a(pa, st);
+    c_to_a(dsa, dpt);
+    gemm_kn(dv, pa, sDO);   // dV += P^T dO
+    gemm_kn(dk, dsa, sQ);   // dK += dS^T Q
+  }
+  store_c_bf16(p.dk + (long long)b * p.bsdk + (long long)k0 * p.lddk + h * DH, p.lddk, warp * 16, krows, dk, p.scale,
+               p.scale);
+  store_c_bf16(p.dv + (long long)b * p.bsdv + (long long)k0 * p.lddv + h * DH, p.lddv, warp * 16, krows, dv, 1.f, 1.f);
+}
+
+static Params to_params(const zb_attention_args* a) {
+  Params p;
+  p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
+  p.o = (const __nv_bfloat16*)a->o; p.out = (__nv_bfloat16*)a->o; p.d_o = (const __nv_bfloat16*)a->d_o;
+  p.dq = (__nv_bfloat16*)a->dq; p.dk = (__nv_bfloat16*)a->dk; p.dv = (__nv_bfloat16*)a->dv;
+  p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv; p.ldo = a->ldo;
+  p.bsq = a->bsq; p.bsk = a->bsk; p.bsv = a->bsv; p.bso = a->bso;
+  p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.bsdo = a->bsdo; p.bsdq = a->bsdq; p.bsdk = a->bsdk; p.bsdv = a->bsdv;
+  p.heads = a->heads; p.lq = a->lq; p.lk = a->lk; p.causal = a->causal; p.q_offset = a->q_offset;
+  p.kv_group = a->kv_group > 0 ? a->kv_group : 1;
+  p.key_len = a->key_len; p.scale = a->scale; p.inf_value = a->inf_value; p.lse = a->lse; p.delta = a->delta;
+  return p;
+}
+
+}  // namespace fa
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool attention_mma_supported(const zb_attention_args* a, bool bwd) {
+  if (a->dh != 64 || a->rpr_k || a->relu_attn) return false;
+  if (a->lq < 16 && !bwd) return false;  // decode steps (lq = 1) are better served by the warp-per-row kernel
+  if (a->ldq % 8 || a->ldk % 8 || a->ldv % 8 || a->ldo % 8 || a->bsq % 8 || a->bsk % 8 || a->bsv % 8 || a->bso % 8)
+    return false;
+  if (!aligned16(a->q) || !aligned16(a->k) || !aligned16(a->v) || !aligned16(a->o)) return false;
+  if (bwd) {
+    if (a->lddo % 8 || a->lddq % 8 || a->lddk % 8 || a->lddv % 8 || a->bsdo % 8 || a->bsdq % 8 || a->bsdk % 8 ||
+        a->bsdv % 8)
+      return false;
+    if (!aligned16(a->d_o) || !aligned16(a->dq) || !aligned16(a->dk) || !aligned16(a->dv)) return false;
+    if (a->lq < 16) return false;
+  }
+  return true;
+}
+
+int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
+  const fa::Params p = fa::to_params(a);
+  const dim3 grid((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
+  fa::fwd_kernel<<<grid, fa::NT, 0, st>>>(p);
+  return check_launch("zb_attention_fwd(mma)");
+}
+
+int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
+  const fa::Params p = fa::to_params(a);
+  const dim3 gq((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
+  const dim3 gk((a->lk + fa::BK - 1) / fa::BK, a->heads, a->batch);
+  fa::bwd_dq_kernel<<<gq, fa::NT, 0, st>>>(p);
+  int rc = check_launch("zb_attention_bwd(mma dq)");
+  if (rc) return rc;
+  fa::bwd_dkv_kernel<<<gk, fa::NT, 0, st>>>(p);
+  return check_launch("zb_attention_bwd(mma dkv)");
+}
+
 }  // namespace zb
