@@ -197,6 +197,7 @@ typedef struct {
   float beta1, beta2, eps;
   float lr_t, grad_scale;
   const float* clip_scale;
+  float* norms; /* optional fp32[2], accumulated: {sum (grad*grad_scale)^2, sum param^2} (utils/cycle.py:94-95) */
 } zb_adam_args;
 int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream);
 /* zb_sumsq: out[0] += sum x^2 (tf.global_norm, utils/cycle.py:94). */

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_sizes_match_header_layout():
     # spot-check: natural C alignment of the mirrored structs (pointers 8, int64 8, int32/float 4)
     assert ctypes.sizeof(L.GemmArgs) == 3 * 8 + 6 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4
-    assert ctypes.sizeof(L.AdamArgs) == 5 * 8 + 8 + 5 * 4 + 4 + 8
+    assert ctypes.sizeof(L.AdamArgs) == 5 * 8 + 8 + 5 * 4 + 4 + 8 + 8
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

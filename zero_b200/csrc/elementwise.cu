@@ -81,9 +81,39 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
                __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps, float lr_t, float gscale,
-               const float* __restrict__ clip_scale) {
+               const float* __restrict__ clip_scale, float* __restrict__ norms) {
   const float gs = clip_scale ? gscale * clip_scale[0] : gscale;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (norms) {
+    // tf.global_norm of the (averaged, unclipped) gradients and of the pre-update parameters
+    // (utils/cycle.py:94-95), fused into the pass that reads both anyway
+    float sg = 0.f, sp = 0.f;
+    for (long long j = i; j < n && j < i + 4; ++j) {
+      const float gr = g[j] * gscale;
+      sg += gr * gr;
+      sp += p[j] * p[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    __shared__ float rg[8], rp[8];
+    if ((threadIdx.x & 31) == 0) {
+      rg[threadIdx.x >> 5] = sg;
+      rp[threadIdx.x >> 5] = sp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        a += rg[w];
+        b += rp[w];
+      }
+      atomicAdd(norms, a);
+      atomicAdd(norms + 1, b);
+    }
+  }
   if (i + 3 < n) {
     float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
            vv = *reinterpret_cast<float4*>(v + i);
@@ -168,7 +198,7 @@ extern "C" int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream) {
   const long long blocks = ((a->n + 3) / 4 + 255) / 256;
   adam_tf_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(a->param, a->m, a->v, a->grad, (__nv_bfloat16*)a->param_bf16,
                                                           a->n, a->beta1, a->beta2, a->eps, a->lr_t, a->grad_scale,
-                                                          a->clip_scale);
+                                                          a->clip_scale, a->norms);
   return check_launch("zb_adam_tf");
 }
 extern "C" int zb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int64_t row_bytes,

@@ -305,6 +305,46 @@ class Engine(object):
         self.ws = Workspace(self.device)
         self.step_count = 0
 
+    # ================================================================================== side stream
+    # Weight-gradient work (wgrad GEMMs + bias column sums) only writes the gradient arena, so it runs on a
+    # second stream next to the dgrad critical path (captured as parallel branches of the step's CUDA graph).
+    # Backward temporaries exist in two sets (layer parity); layer l waits for the side work of layer l + 2.
+    def enable_side_stream(self, on=True):
+        self.side = torch.cuda.Stream(device=self.device) if on else None
+        self._side_ev = {}
+
+    def _side(self, fn):
+        side = getattr(self, "side", None)
+        if side is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            fn()
+
+    def _side_layer_begin(self, tag, l):
+        if getattr(self, "side", None) is None:
+            return
+        ev = self._side_ev.get((tag, l + 2))
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _side_layer_end(self, tag, l):
+        side = getattr(self, "side", None)
+        if side is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(side)
+        self._side_ev[(tag, l)] = ev
+
+    def _side_join(self):
+        side = getattr(self, "side", None)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            self._side_ev = {}
+
     # ================================================================================== forward pieces
     def _self_attn_fwd(self, key, x, B, Lq, key_len, causal, sv, tag):
         """func.dot_attention with memory=None (func.py:194-205, 218-256, 277-278)."""
@@ -331,8 +371,7 @@ class Engine(object):
         """Returns dx (gradient wrt the sublayer input through the attention branch)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W"))
-        ops.colsum(dy, ps.g(key + ".o.b"))
+        self._side(lambda: (ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")), ops.colsum(dy, ps.g(key + ".o.b"))))
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -341,8 +380,7 @@ class Engine(object):
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), d3[:, :, :c.d], d3[:, :, c.d:2 * c.d], d3[:, :, 2 * c.d:],
                           delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
-        ops.linear_wgrad(x, dqkv, ps.g(key + ".qkv.W"))
-        ops.colsum(dqkv, ps.g(key + ".qkv.b"))
+        self._side(lambda: (ops.linear_wgrad(x, dqkv, ps.g(key + ".qkv.W")), ops.colsum(dqkv, ps.g(key + ".qkv.b"))))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dqkv, ps.w(key + ".qkv.W"), dx)
         return dx
@@ -373,8 +411,7 @@ class Engine(object):
     def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W"))
-        ops.colsum(dy, ps.g(key + ".o.b"))
+        self._side(lambda: (ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")), ops.colsum(dy, ps.g(key + ".o.b"))))
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -384,10 +421,8 @@ class Engine(object):
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), dq.view(B, Lq, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:],
                           delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
-        ops.linear_wgrad(x, dq, ps.g(key + ".q.W"))
-        ops.colsum(dq, ps.g(key + ".q.b"))
-        ops.linear_wgrad(enc, dkv, ps.g(key + ".kv.W"))
-        ops.colsum(dkv, ps.g(key + ".kv.b"))
+        self._side(lambda: (ops.linear_wgrad(x, dq, ps.g(key + ".q.W")), ops.colsum(dq, ps.g(key + ".q.b")),
+                            ops.linear_wgrad(enc, dkv, ps.g(key + ".kv.W")), ops.colsum(dkv, ps.g(key + ".kv.b"))))
         # d_enc (fp32, accumulated over decoder layers) += dkv @ Wkv^T
         ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
         dx = ws.get(tag + ".dx", (N, c.d))
@@ -426,12 +461,10 @@ class Engine(object):
 
     def _ffn_bwd(self, key, x, dy, N, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
-        ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W"))
-        ops.colsum(dy, ps.g(key + ".w2.b"))
+        self._side(lambda: (ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W")), ops.colsum(dy, ps.g(key + ".w2.b"))))
         dh = ws.get(tag + ".dh", (N, c.f))
         ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"])
-        ops.linear_wgrad(x, dh, ps.g(key + ".w1.W"))
-        ops.colsum(dh, ps.g(key + ".w1.b"))
+        self._side(lambda: (ops.linear_wgrad(x, dh, ps.g(key + ".w1.W")), ops.colsum(dh, ps.g(key + ".w1.b"))))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dh, ps.w(key + ".w1.W"), dx)
         return dx
@@ -482,12 +515,14 @@ class Engine(object):
         N = B * S
         d1, d2 = d_enc, None
         for l in reversed(range(c.nenc)):
-            key, t = "enc%d" % l, "%s.L%d" % (tag, l)
+            key, bw = "enc%d" % l, "%s.bw%d" % (tag, l & 1)   # backward temporaries: two sets, by layer parity
             sv = save["layers"][l]
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], tag + ".bw.ln2")
-            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], ds2, N, sv["ffn"], tag + ".bw.ffn")
-            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], tag + ".bw.ln1")
-            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, S, sv["att"], tag + ".bw.att")
+            self._side_layer_begin(tag, l)
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2")
+            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], ds2, N, sv["ffn"], bw + ".ffn")
+            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1")
+            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, S, sv["att"], bw + ".att")
+            self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
         ops.embed_bwd(save["source"], d1, ps.g("src_emb"), ps.g("emb_bias"), mult=c.d ** 0.5, d_out2=d2)
 
@@ -545,20 +580,22 @@ class Engine(object):
         feat, dlogits, enc = save["feat"], save["dlogits"], save["enc"]
         table = self._softmax_table()
         # dE += dlogits^T feat ; dfeat = dlogits E
-        ops.gemm(dlogits, feat, ps.g(table), L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True)
+        self._side(lambda: ops.gemm(dlogits, feat, ps.g(table), L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True))
         dfeat = ws.get(tag + ".dfeat", (N, c.d))
         ops.gemm(dlogits, ps.w(table), dfeat, L.ZB_K_MAJOR, L.ZB_MN_MAJOR)
         d1, d2 = dfeat, None
         for l in reversed(range(c.ndec)):
-            key, t = "dec%d" % l, "%s.L%d" % (tag, l)
+            key, bw = "dec%d" % l, "%s.bw%d" % (tag, l & 1)
             sv = save["layers"][l]
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], tag + ".bw.ln2")
-            dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], tag + ".bw.ffn")
-            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], tag + ".bw.lnc")
+            self._side_layer_begin(tag, l)
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2")
+            dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], bw + ".ffn")
+            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc")
             dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
-                                       tag + ".bw.cross")
-            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], tag + ".bw.ln1")
-            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], tag + ".bw.att")
+                                       bw + ".cross")
+            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1")
+            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], bw + ".att")
+            self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
         ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
 
@@ -589,6 +626,7 @@ class Engine(object):
         d_enc = ws.get("d_enc", (B * S, c.d))
         ops.cast_f32_bf16(d_enc32, d_enc)
         self.encode_bwd(d_enc, esave)
+        self._side_join()
         return loss
 
     def train_loss(self, source, target):

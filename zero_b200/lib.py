@@ -60,7 +60,7 @@ class CeArgs(C.Structure):
 class AdamArgs(C.Structure):
     _fields_ = [("param", vp), ("m", vp), ("v", vp), ("grad", vp), ("param_bf16", vp), ("n", i64),
                 ("beta1", f32), ("beta2", f32), ("eps", f32), ("lr_t", f32), ("grad_scale", f32),
-                ("clip_scale", vp)]
+                ("clip_scale", vp), ("norms", vp)]
 
 
 class BeamArgs(C.Structure):

@@ -166,10 +166,10 @@ def sumsq(x, out):
     L.check(L.load().zb_sumsq(_p(x), x.numel(), _p(out), _stream()), "zb_sumsq")
 
 
-def adam_tf(param, m, v, grad, param_bf16, beta1, beta2, eps, lr_t, grad_scale, clip_scale=None):
+def adam_tf(param, m, v, grad, param_bf16, beta1, beta2, eps, lr_t, grad_scale, clip_scale=None, norms=None):
     """tf.train.AdamOptimizer update on the flat arena (main.py:178-181)."""
     a = L.AdamArgs(_p(param), _p(m), _p(v), _p(grad), _p(param_bf16), param.numel(), float(beta1), float(beta2),
-                   float(eps), float(lr_t), float(grad_scale), _p(clip_scale))
+                   float(eps), float(lr_t), float(grad_scale), _p(clip_scale), _p(norms))
     L.check(L.load().zb_adam_tf(C.byref(a), _stream()), "zb_adam_tf")
 
 

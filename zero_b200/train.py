@@ -27,8 +27,10 @@ def noam_lr(step, init_lr, warmup_steps, hidden_size, min_lr=0.0, max_lr=1.0):
 
 
 class Trainer(object):
-    def __init__(self, engine: Engine, hp, world_size=1, use_graph=False):
+    def __init__(self, engine: Engine, hp, world_size=1, use_graph=False, side_stream=True):
         self.eng = engine
+        if side_stream:
+            engine.enable_side_stream(True)
         self.hp = hp
         self.world = int(world_size)
         n = engine.ps.total
@@ -87,10 +89,11 @@ class Trainer(object):
         loss = self._fwd_bwd(source, target)
         if self.world > 1:
             dist.all_reduce(ps.grad, op=dist.ReduceOp.SUM)
-        # tf.global_norm of gradients and parameters (utils/cycle.py:94-95)
+        # tf.global_norm of gradients and parameters (utils/cycle.py:94-95): a separate pass only when the clip
+        # factor needs the gradient norm before the update; otherwise fused into the Adam kernel
         self.norms.zero_()
-        ops.sumsq(ps.grad, self.norms[0:1])
-        ops.sumsq(ps.master, self.norms[1:2])
+        if self.clip is not None:
+            ops.sumsq(ps.grad, self.norms[0:1])
         self.global_step += 1
         t = self.global_step
         lr_t = self.lr() * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
@@ -101,9 +104,14 @@ class Trainer(object):
             gn = torch.sqrt(self.norms[0]) * gscale
             torch.div(self.clip, torch.clamp(gn, min=self.clip), out=self.clip_scale[0])
             clip_scale = self.clip_scale
+            self.norms.zero_()
         ops.adam_tf(ps.master, ps.adam_m, ps.adam_v, ps.grad, ps.mirror, self.beta1, self.beta2, self.eps,
-                    lr_t, gscale, clip_scale)
+                    lr_t, gscale, clip_scale, self.norms)
         return loss
 
     def gradient_norm(self):
-        return float(torch.sqrt(self.norms[0]).item()) / (self.world * self.loss_scale)
+        """GNorm of main.py:336-346 (already averaged over towers and un-scaled)."""
+        return float(torch.sqrt(self.norms[0]).item())
+
+    def parameter_norm(self):
+        return float(torch.sqrt(self.norms[1]).item())
