@@ -136,6 +136,55 @@ def run_reference(args):
     }))
 
 
+def decode_bench(device, batches=3):
+    """Secondary metric of BASELINE.json: beam-4 decode tok/s on configs[2] (transformer_aan 6+6, B=64, len 64,
+    cached decode).  Tokens = top-1 hypothesis lengths incl. EOS (evalu.py:25-46) / time of beam_search per batch
+    (evalu.py:106-120); also reported as decoder row-steps per second (rows = batch * beam)."""
+    import torch
+    from zero_b200 import search
+    from zero_b200.engine import Engine
+    from zero_b200.params import SimpleVocab, transformer_base
+    hp = transformer_base(model_name="transformer_aan", scope_name="transformer_aan", use_ffn=False, aan_mask=True,
+                          beam_size=4, decode_length=0, decode_alpha=0.6)
+    hp.add_hparam("src_vocab", SimpleVocab(VOCAB))
+    hp.add_hparam("tgt_vocab", SimpleVocab(VOCAB))
+    eng = Engine(hp, VOCAB, VOCAB, device=device)
+    eng.ps.init_random(7)
+    eng.decode_length = 0
+    tot_tok, tot_steps, tot_ms = 0, 0, 0.0
+    for i in range(batches + 1):
+        src, _ = make_batch(500 + i, 64)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        steps = {"n": 0}
+
+        def dec(tok, state, t):
+            steps["n"] += 1
+            return eng.decoding_fn(tok, state, t)
+
+        out = search.beam_search({"source": src}, eng.encoding_fn, dec, hp)
+        e1.record()
+        torch.cuda.synchronize()
+        if i == 0:
+            continue  # warm-up batch (allocations)
+        top1 = out["seq"][:, 0, :].cpu()
+        lens = []
+        for row in top1.tolist():
+            n = 0
+            for tok in row:
+                n += 1
+                if tok == 2 or tok == 0:
+                    break
+            lens.append(n)
+        tot_tok += sum(lens)
+        tot_steps += steps["n"]
+        tot_ms += e0.elapsed_time(e1)
+    return {"metric": "beam4_decode_tokens_per_sec", "value": tot_tok / (tot_ms * 1e-3), "unit": "top-1 tokens/s",
+            "row_steps_per_sec": tot_steps * 256 / (tot_ms * 1e-3), "steps": tot_steps, "ms_per_step": tot_ms / max(tot_steps, 1),
+            "config": "transformer_aan 6+6 d=512, beam 4, batch 64, src len 64, max target len 64 (BASELINE configs[2])"}
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def gemm_roofline(eng, src, tgt, peaks):
     """Dominant kernel = zb_gemm (tcgen05).  Re-run one step eagerly with CUDA events around every GEMM launch
@@ -286,6 +335,7 @@ def run_ours(args):
         "roofline": roof,
         "model_tflops_per_gpu": model_flops / (ms / args.steps * 1e-3) / 1e12,
         "cpu_baseline": cpu_baseline,
+        "decode": decode_bench("cuda:%d" % local) if (world == 1 and not args.no_decode) else None,
         "clocks": clocks,
         "final_loss": final_loss,
     }
@@ -302,6 +352,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else min(args.steps, 50)

@@ -22,6 +22,8 @@ namespace zb {
 struct GemmKParams {
   int M, N, K;
   int mt, nt, splits, kb_per_split, kb_total;
+  int gn;  // rasterisation: tiles are walked in column panels of `gn` n-blocks, n fastest inside a panel, so the
+           // CTAs running at the same time share A row-panels and B column-panels in L2 instead of re-reading them
   void* d;
   long long ldd;
   const float* bias;
@@ -47,6 +49,19 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 128 / 256 / 512: powers of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// linear tile index -> (m block, n block, k split)
+__device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int& m_blk, int& n_blk, int& ks) {
+  const int per_split = p.mt * p.nt;
+  ks = tile / per_split;
+  const int t = tile - ks * per_split;
+  const int panel_tiles = p.mt * p.gn;
+  const int pn = t / panel_tiles;
+  const int r = t - pn * panel_tiles;
+  const int w = min(p.gn, p.nt - pn * p.gn);
+  m_blk = r / w;
+  n_blk = pn * p.gn + (r - m_blk * w);
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -98,9 +113,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.mt;
-        const int n_blk = (tile / p.mt) % p.nt;
-        const int ks = tile / (p.mt * p.nt);
+        int m_blk, n_blk, ks;
+        tile_coords(p, tile, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * kBM, n0 = n_blk * BN;
@@ -145,7 +159,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int ks = tile / (p.mt * p.nt);
+        int m_blk, n_blk, ks;
+        tile_coords(p, tile, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -177,103 +192,134 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // Per tile each warp owns 32 accumulator rows (its TMEM lane quadrant) and walks the BN columns in chunks of
+    // 32.  Two register sets ping-pong so the tcgen05.ld of chunk c+1 is in flight while chunk c is converted
+    // and stored; the per-column bias is fetched once per chunk by one coalesced load (lane j <- bias[col0+j]),
+    // issued before the TMEM wait, and broadcast with shuffles.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int flags = p.flags;
+    const float alpha = p.alpha;
+    const bool d_f32 = p.d_f32 != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.mt;
-      const int n_blk = (tile / p.mt) % p.nt;
-      const int m0 = m_blk * kBM, n0 = n_blk * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
+
+    auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4]) {
+      if (col0 >= p.N) return;
+      const bool full_cols = (col0 + 32 <= p.N);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
+      if (flags & ZB_EPI_BIAS) {
         __syncwarp();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c * 32;
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) continue;
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        const bool full_cols = (col0 + 32 <= p.N);
-        if (p.flags & ZB_EPI_BIAS) {
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+      }
+      if (flags & ZB_EPI_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full_cols || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-        }
-        if (p.flags & ZB_EPI_RELU) {
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (!row_ok) return;
+      if (flags & ZB_EPI_RELU_MASK) {
+        if (full_cols) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (row_ok) {
-        if (p.flags & ZB_EPI_RELU_MASK) {
-          const __nv_bfloat16* mrow = p.mask + static_cast<long long>(row) * p.ldmask + col0;
-          if (full_cols) {
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mrow) + q);
-              const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(w[e]);
-                if (!(f.x > 0.f)) v[q * 8 + e * 2] = 0.f;
-                if (!(f.y > 0.f)) v[q * 8 + e * 2 + 1] = 0.f;
-              }
-            }
-          } else {
-            #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
-          }
-        }
-        if (p.d_f32) {
-          float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
-          if (p.flags & ZB_EPI_ACCUM) {
-            if (full_cols) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) red_add_v4(drow + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
-              #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(drow + j, v[j]);
-            }
-          } else {
-            if (full_cols) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(drow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
-              #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) drow[j] = v[j];
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w[e]);
+              if (!(f.x > 0.f)) v[q * 8 + e * 2] = 0.f;
+              if (!(f.y > 0.f)) v[q * 8 + e * 2 + 1] = 0.f;
             }
           }
         } else {
-          __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+          const __nv_bfloat16* mrow = p.mask + static_cast<long long>(row) * p.ldmask + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
+        }
+      }
+      if (d_f32) {
+        float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+        if (flags & ZB_EPI_ACCUM) {
           if (full_cols) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              reinterpret_cast<uint4*>(drow)[q] = o;
-            }
+            for (int q = 0; q < 8; ++q) red_add_v4(drow + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           } else {
-            #pragma unroll
+#pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) drow[j] = __float2bfloat16(v[j]);
+              if (col0 + j < p.N) atomicAdd(drow + j, v[j]);
+          }
+        } else {
+          if (full_cols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(drow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) drow[j] = v[j];
           }
         }
-        }  // row_ok
+      } else {
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+        if (full_cols) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            reinterpret_cast<uint4*>(drow)[q] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) drow[j] = __float2bfloat16(v[j]);
+        }
       }
-      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+    };
+    // operands of a chunk that come from global memory: issued early so their latency hides behind tcgen05.ld
+    auto prefetch_chunk = [&](int row, bool row_ok, int col0, float& bias_lane, uint4 (&mk)[4]) {
+      bias_lane = 0.f;
+      if ((flags & ZB_EPI_BIAS) && col0 + lane < p.N) bias_lane = __ldg(p.bias + col0 + lane);
+      if ((flags & ZB_EPI_RELU_MASK) && row_ok && col0 + 32 <= p.N) {
+        const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + static_cast<long long>(row) * p.ldmask + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk[q] = __ldg(mrow + q);
+      }
+    };
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk, ks;
+      tile_coords(p, tile, m_blk, n_blk, ks);
+      const int m0 = m_blk * kBM, n0 = n_blk * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      float bias_a, bias_b;
+      uint4 mk_a[4], mk_b[4];
+      prefetch_chunk(row, row_ok, n0, bias_a, mk_a);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tbase, ra);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c += 2) {
+        __syncwarp();
+        tmem_ld_wait();  // ra (chunk c) has landed
+        tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
+        prefetch_chunk(row, row_ok, n0 + (c + 1) * 32, bias_b, mk_b);
+        finish_chunk(ra, row, row_ok, n0 + c * 32, bias_a, mk_a);
+        __syncwarp();
+        tmem_ld_wait();  // rb (chunk c + 1) has landed
+        if (c + 2 < BN / 32) {
+          tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
+          prefetch_chunk(row, row_ok, n0 + (c + 2) * 32, bias_a, mk_a);
+        }
+        finish_chunk(rb, row, row_ok, n0 + (c + 1) * 32, bias_b, mk_b);
+      }
+      // all TMEM reads of this accumulator stage are complete (every tcgen05.ld was waited on)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -396,6 +442,10 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   if (bn == 256 && tiles_for(256) < 2ll * sms) bn = 128;
   if (bn == 128 && tiles_for(128) < sms && p.N > 64) bn = 64;
   p.nt = (p.N + bn - 1) / bn;
+  // panel width minimising the bytes the ~#SM concurrently running tiles pull through L2:
+  // (sms / gn) A row-blocks of 128 rows + gn B column-blocks of bn rows  ->  gn ~ sqrt(sms * 128 / bn)
+  p.gn = bn == 256 ? 8 : (bn == 128 ? 12 : 16);
+  if (p.gn > p.nt) p.gn = p.nt;
 
   int splits = a->split_k;
   const long long tiles = (long long)p.mt * p.nt;
