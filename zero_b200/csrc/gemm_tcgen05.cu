@@ -5,15 +5,17 @@
 // Replaces every tf.matmul on Zero's Transformer path: func.linear (func.py:49,59), the tied-softmax
 // projection (models/transformer.py:194) and, as dgrad/wgrad, their tf.gradients (main.py:28).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor -> 128B-swizzled smem ring (A 128x64, B BNx64 bf16)
 //   warp 1      MMA issuer    : one elected lane issues tcgen05.mma (128 x BN x 16), accumulators in TMEM,
 //                               tcgen05.commit releases smem slots / publishes the accumulator
-//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns) -> alpha/bias/relu/mask -> 16 B stores
+//   warps 2..9  epilogue      : tcgen05.ld (32 lanes x 32 columns) -> alpha/bias/relu/mask -> 16 B stores
 //                               or fp32 red.add (split-K / gradient accumulation)
 // Two TMEM accumulator stages (2 x BN columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
 // Operands may be K-major ([rows][k]) or MN-major ([k][rows]); both map onto SWIZZLE_128B canonical layouts,
 // so forward (x W), dgrad (dy W^T) and wgrad (x^T dy) all read the tensors where they lie — no transposes.
+#include <stdlib.h>
+
 #include "zb_common.h"
 #include "zb_ptx.cuh"
 
@@ -36,7 +38,7 @@ struct GemmKParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 
 template <int BN>
@@ -95,7 +97,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -106,6 +108,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous
+  // kernel when launched with programmatic stream serialisation; from here on we touch its results.
+  grid_dep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -191,12 +196,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     // Per tile each warp owns 32 accumulator rows (its TMEM lane quadrant) and walks the BN columns in chunks of
     // 32.  Two register sets ping-pong so the tcgen05.ld of chunk c+1 is in flight while chunk c is converted
     // and stored; the per-column bias is fetched once per chunk by one coalesced load (lane j <- bias[col0+j]),
     // issued before the TMEM wait, and broadcast with shuffles.
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the tile's columns (two warps per quadrant)
     const int flags = p.flags;
     const float alpha = p.alpha;
     const bool d_f32 = p.d_f32 != 0;
@@ -298,26 +304,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const bool row_ok = row < p.M;
       float bias_a, bias_b;
       uint4 mk_a[4], mk_b[4];
-      prefetch_chunk(row, row_ok, n0, bias_a, mk_a);
+      // this warp's column range: the two warps of a lane quadrant split the BN columns in halves
+      constexpr int NCH = BN / 64;  // 32-column chunks per warp
+      const int c0 = half * NCH;
+      prefetch_chunk(row, row_ok, n0 + c0 * 32, bias_a, mk_a);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c0 * 32;
       uint32_t ra[32], rb[32];
       tmem_ld_32x32b_x32(tbase, ra);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c += 2) {
+      for (int c = 0; c < NCH; c += 2) {
         __syncwarp();
         tmem_ld_wait();  // ra (chunk c) has landed
-        tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
-        prefetch_chunk(row, row_ok, n0 + (c + 1) * 32, bias_b, mk_b);
-        finish_chunk(ra, row, row_ok, n0 + c * 32, bias_a, mk_a);
-        __syncwarp();
-        tmem_ld_wait();  // rb (chunk c + 1) has landed
-        if (c + 2 < BN / 32) {
-          tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
-          prefetch_chunk(row, row_ok, n0 + (c + 2) * 32, bias_a, mk_a);
+        if (c + 1 < NCH) {
+          tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
+          prefetch_chunk(row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
         }
-        finish_chunk(rb, row, row_ok, n0 + (c + 1) * 32, bias_b, mk_b);
+        finish_chunk(ra, row, row_ok, n0 + (c0 + c) * 32, bias_a, mk_a);
+        if (c + 1 < NCH) {
+          __syncwarp();
+          tmem_ld_wait();  // rb (chunk c + 1) has landed
+          if (c + 2 < NCH) {
+            tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
+            prefetch_chunk(row, row_ok, n0 + (c0 + c + 2) * 32, bias_a, mk_a);
+          }
+          finish_chunk(rb, row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
+        }
       }
       // all TMEM reads of this accumulator stage are complete (every tcgen05.ld was waited on)
       tc_fence_before();
@@ -389,7 +402,22 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
     }
     attr_done = true;
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  static const bool use_pdl = getenv("ZB_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (le != cudaSuccess) {
+    set_error("zb_gemm launch: %s", cudaGetErrorString(le));
+    return ZB_ECUDA;
+  }
   return check_launch("zb_gemm");
 }
 
@@ -439,8 +467,10 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
   if (p.N <= 64) bn = 64;
   else if (p.N <= 128) bn = 128;
-  if (bn == 256 && tiles_for(256) < 2ll * sms) bn = 128;
-  if (bn == 128 && tiles_for(128) < sms && p.N > 64) bn = 64;
+  if (!accum) {  // with an accumulating epilogue split-K fills the machine, so keep the widest (most L2-frugal) tile
+    if (bn == 256 && tiles_for(256) < 2ll * sms) bn = 128;
+    if (bn == 128 && tiles_for(128) < sms && p.N > 64) bn = 64;
+  }
   p.nt = (p.N + bn - 1) / bn;
   // panel width minimising the bytes the ~#SM concurrently running tiles pull through L2:
   // (sms / gn) A row-blocks of 128 rows + gn B column-blocks of bn rows  ->  gn ~ sqrt(sms * 128 / bn)
@@ -452,11 +482,21 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   if (splits <= 0) {
     splits = 1;
     if (accum && tiles < sms) {
-      splits = (int)((sms + tiles - 1) / tiles);
-      // keep at least 4 k-blocks (256 k) per split so the pipeline has something to stream
+      // pick the split count whose tiles * splits fills whole waves of SMs best (ties -> fewer splits), keeping
+      // at least 4 k-blocks (256 k) per split so the pipeline has something to stream
       int max_splits = p.kb_total / 4;
       if (max_splits < 1) max_splits = 1;
-      if (splits > max_splits) splits = max_splits;
+      if (max_splits > 64) max_splits = 64;
+      double best = 0.0;
+      for (int s = 1; s <= max_splits; ++s) {
+        const long long work = tiles * s;
+        const long long waves = (work + sms - 1) / sms;
+        const double eff = (double)work / (double)(waves * sms);
+        if (eff > best + 0.02) {
+          best = eff;
+          splits = s;
+        }
+      }
     }
   }
   ZB_REQUIRE(splits == 1 || accum, "zb_gemm: split_k > 1 requires ZB_EPI_ACCUM");

@@ -581,8 +581,13 @@ class Engine(object):
         table = self._softmax_table()
         # dE += dlogits^T feat ; dfeat = dlogits E
         self._side(lambda: ops.gemm(dlogits, feat, ps.g(table), L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True))
+        # dfeat = dlogits @ E is a K = V contraction with few output tiles: split-K into an fp32 scratch
+        # (wide 128x256 tiles, every SM busy), then one cast
+        dfeat32 = ws.get(tag + ".dfeat32", (N, c.d), f32)
+        dfeat32.zero_()
+        ops.gemm(dlogits, ps.w(table), dfeat32, L.ZB_K_MAJOR, L.ZB_MN_MAJOR, accum=True)
         dfeat = ws.get(tag + ".dfeat", (N, c.d))
-        ops.gemm(dlogits, ps.w(table), dfeat, L.ZB_K_MAJOR, L.ZB_MN_MAJOR)
+        ops.cast_f32_bf16(dfeat32, dfeat)
         d1, d2 = dfeat, None
         for l in reversed(range(c.ndec)):
             key, bw = "dec%d" % l, "%s.bw%d" % (tag, l & 1)
