@@ -127,6 +127,8 @@ typedef struct {
   /* backward */
   const void* d_out; const void* d_out2; /* d_out2 (optional) is added to d_out on read */
   void* ds; float* dscale; float* doffset;
+  float* dbias; /* optional fp32 [cols], accumulated: column sums of ds = the bias gradient of the linear layer
+                   that produced y (tf.nn.bias_add grad, func.py:59) */
 } zb_add_ln_args;
 int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream);
 int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream);

@@ -86,8 +86,10 @@ def test_add_ln_fwd_bwd(rows, cols):
     ds = torch.empty_like(x)
     dscale = torch.zeros(cols, device=dev())
     doffset = torch.zeros(cols, device=dev())
-    ops.add_ln_bwd(x, y, d1, d2, mean, rstd, scale, ds, dscale, doffset)
+    dbias = torch.zeros(cols, device=dev())
+    ops.add_ln_bwd(x, y, d1, d2, mean, rstd, scale, ds, dscale, doffset, dbias)
     torch.testing.assert_close(ds.float(), xr.grad, atol=3e-2, rtol=2e-2)
+    torch.testing.assert_close(dbias, xr.grad.sum(0), atol=2e-2 * math.sqrt(rows), rtol=1e-2)
     torch.testing.assert_close(dscale, sc.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
     torch.testing.assert_close(doffset, of.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
 
@@ -282,6 +284,11 @@ def test_adam_tf_and_sumsq_and_colsum():
     cs = torch.zeros(130, device=dev())
     ops.colsum(x, cs)
     torch.testing.assert_close(cs, x.float().sum(0), atol=5e-2, rtol=1e-3)
+    for m_, n_ in ((1000, 512), (4096, 1536), (77, 2048)):   # 16-byte vectorised path, incl. a strided view
+        xb = rnd(m_, n_ + 64, seed=10)[:, :n_]
+        cs2 = torch.zeros(n_, device=dev())
+        ops.colsum(xb, cs2)
+        torch.testing.assert_close(cs2, xb.float().sum(0), atol=8e-2, rtol=1e-3)
 
 
 def test_prefix_mean_and_gather_rows():

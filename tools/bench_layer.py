@@ -43,9 +43,9 @@ def main():
         x1 = eng._ln_fwd("enc0.self.ln", x, y, N, sv["ln1"], "L.ln1")
         y2 = eng._ffn_fwd("enc0.ffn", x1, N, sv["ffn"], "L.ffn")
         eng._ln_fwd("enc0.ffn.ln", x1, y2, N, sv["ln2"], "L.ln2")
-        ds2 = eng._ln_bwd("enc0.ffn.ln", d_out, None, N, sv["ln2"], "L.bw.ln2")
+        ds2 = eng._ln_bwd("enc0.ffn.ln", d_out, None, N, sv["ln2"], "L.bw.ln2", eng.ps.g("enc0.ffn.w2.b"))
         dx1 = eng._ffn_bwd("enc0.ffn", x1, ds2, N, sv["ffn"], "L.bw.ffn")
-        ds1 = eng._ln_bwd("enc0.self.ln", ds2, dx1, N, sv["ln1"], "L.bw.ln1")
+        ds1 = eng._ln_bwd("enc0.self.ln", ds2, dx1, N, sv["ln1"], "L.bw.ln1", eng.ps.g("enc0.self.o.b"))
         eng._self_attn_bwd("enc0.self", x, ds1, B, S, sv["att"], "L.bw.att")
         eng._side_join()
 

@@ -101,15 +101,15 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
                   __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale, float* __restrict__ doffset,
-                  long long rows, int cols) {
+                  float* __restrict__ dbias, long long rows, int cols) {
   extern __shared__ float red[];  // [kLnWarps][cols] x 2
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
-  float acc_s[NV][8], acc_o[NV][8];
+  float acc_s[NV][8], acc_o[NV][8], acc_b[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc_s[i][e] = acc_o[i][e] = 0.f;
+    for (int e = 0; e < 8; ++e) acc_s[i][e] = acc_o[i][e] = acc_b[i][e] = 0.f;
 
   for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
     const float mu = mean[row], rs = rstd[row];
@@ -153,7 +153,10 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       if (v < nvec) {
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (g[i][e] - sg - sh[i][e] * sgs);
+        for (int e = 0; e < 8; ++e) {
+          o[e] = rs * (g[i][e] - sg - sh[i][e] * sgs);
+          acc_b[i][e] += o[e];  // column sum of ds = bias gradient of the linear layer that produced y
+        }
         store8(ds + row * cols + v * 8, o);
       }
     }
@@ -161,6 +164,7 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   // block-level column reduction, then one atomic per column per block
   float* rs_ = red;
   float* ro_ = red + kLnWarps * cols;
+  float* rb_ = red + 2 * kLnWarps * cols;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
@@ -169,19 +173,22 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       for (int e = 0; e < 8; ++e) {
         rs_[warp * cols + v * 8 + e] = acc_s[i][e];
         ro_[warp * cols + v * 8 + e] = acc_o[i][e];
+        if (dbias) rb_[warp * cols + v * 8 + e] = acc_b[i][e];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
     for (int w = 0; w < kLnWarps; ++w) {
       a += rs_[w * cols + c];
       b += ro_[w * cols + c];
+      if (dbias) d += rb_[w * cols + c];
     }
     atomicAdd(dscale + c, a);
     atomicAdd(doffset + c, b);
+    if (dbias) atomicAdd(dbias + c, d);
   }
 }
 
@@ -233,7 +240,7 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   long long blocks = (a->rows + kLnWarps - 1) / kLnWarps;
   const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  const size_t smem = (size_t)2 * kLnWarps * a->cols * sizeof(float);
+  const size_t smem = (size_t)3 * kLnWarps * a->cols * sizeof(float);
 #define CALL(N)                                                                                              \
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
@@ -241,7 +248,7 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
     add_ln_bwd_kernel<N><<<(int)blocks, kLnWarps * 32, smem, st>>>(                                          \
         (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
         (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
-        a->doffset, a->rows, (int)a->cols);                                                                  \
+        a->doffset, a->dbias, a->rows, (int)a->cols);                                                                  \
   } while (0)
   ZB_LN_DISPATCH(nv, CALL);
 #undef CALL

@@ -371,7 +371,7 @@ class Engine(object):
         """Returns dx (gradient wrt the sublayer input through the attention branch)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        self._side(lambda: (ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")), ops.colsum(dy, ps.g(key + ".o.b"))))
+        self._side(lambda: ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")))  # o.b: summed by the LN backward
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -411,7 +411,7 @@ class Engine(object):
     def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        self._side(lambda: (ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")), ops.colsum(dy, ps.g(key + ".o.b"))))
+        self._side(lambda: ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")))  # o.b: summed by the LN backward
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -461,7 +461,7 @@ class Engine(object):
 
     def _ffn_bwd(self, key, x, dy, N, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
-        self._side(lambda: (ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W")), ops.colsum(dy, ps.g(key + ".w2.b"))))
+        self._side(lambda: ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W")))  # w2.b: summed by the LN backward
         dh = ws.get(tag + ".dh", (N, c.f))
         ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"])
         self._side(lambda: (ops.linear_wgrad(x, dh, ps.g(key + ".w1.W")), ops.colsum(dh, ps.g(key + ".w1.b"))))
@@ -478,11 +478,12 @@ class Engine(object):
         sv.update(x=x, y=y, mean=mean, rstd=rstd)
         return out
 
-    def _ln_bwd(self, key, d_out, d_out2, N, sv, tag):
+    def _ln_bwd(self, key, d_out, d_out2, N, sv, tag, dbias=None):
+        """dbias: gradient slot of the bias of the linear layer that produced y (its column sum rides along)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         ds = ws.get(tag + ".ds", (N, c.d))
         ops.add_ln_bwd(sv["x"], sv["y"], d_out, d_out2, sv["mean"], sv["rstd"], ps.p(key + ".scale"), ds,
-                       ps.g(key + ".scale"), ps.g(key + ".offset"))
+                       ps.g(key + ".scale"), ps.g(key + ".offset"), dbias)
         return ds
 
     # ================================================================================== encoder
@@ -518,9 +519,9 @@ class Engine(object):
             key, bw = "enc%d" % l, "%s.bw%d" % (tag, l & 1)   # backward temporaries: two sets, by layer parity
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2")
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
             dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], ds2, N, sv["ffn"], bw + ".ffn")
-            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1")
+            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
             dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, S, sv["att"], bw + ".att")
             self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
@@ -593,12 +594,12 @@ class Engine(object):
             key, bw = "dec%d" % l, "%s.bw%d" % (tag, l & 1)
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2")
+            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
             dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], bw + ".ffn")
-            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc")
+            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
             dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
                                        bw + ".cross")
-            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1")
+            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
             dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], bw + ".att")
             self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
@@ -691,13 +692,22 @@ class DecodeState(object):
             return
         for l in range(c.ndec):
             ops.gather_rows(self.cache[l], parent, self.cache_alt[l], row_elems=(t + 1) * 3 * c.d)
-        self.cache, self.cache_alt = self.cache_alt, self.cache
+        self.swap_buffers()
+
+    def swap_buffers(self):
+        """Host-side half of reorder(): the double-buffered caches trade places (also called after a CUDA-graph
+        replay of a step, which runs the kernels but not this bookkeeping)."""
+        if self.cache is not None:
+            self.cache, self.cache_alt = self.cache_alt, self.cache
 
 
 def _engine_encoding_fn(self, source):
     source = self._prep_ids(source, self.device)
     enc, src_len = self.encode(source, tag="I")
-    return DecodeState(self, enc, src_len, source.shape[0], source.shape[1])
+    # fixed address across batches of the same shape: decode steps are replayed from CUDA graphs
+    src_len_static = self.ws.get("I.src_len", (source.shape[0],), torch.int32)
+    src_len_static.copy_(src_len)
+    return DecodeState(self, enc, src_len_static, source.shape[0], source.shape[1])
 
 
 def _engine_decoding_fn(self, target, state, time):

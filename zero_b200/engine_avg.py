@@ -162,17 +162,29 @@ def _begin_search(self, beam, cap=None):
             s.zero_()
 
 
+_orig_swap = DecodeState.swap_buffers
+
+
+def _swap_buffers(self):
+    c = self.engine.cfg
+    if c.aan or c.fuse:
+        self.sums, self.sums_alt = self.sums_alt, self.sums
+        return
+    _orig_swap(self)
+
+
 def _reorder(self, parent, t):
     c = self.engine.cfg
     if c.aan or c.fuse:
         for l in range(c.ndec):
             ops.gather_rows(self.sums[l], parent, self.sums_alt[l])
-        self.sums, self.sums_alt = self.sums_alt, self.sums
+        self.swap_buffers()
         return
     _orig_reorder(self, parent, t)
 
 
 DecodeState.begin_search = _begin_search
+DecodeState.swap_buffers = _swap_buffers
 DecodeState.reorder = _reorder
 Engine._decode_train_avg = _decode_train_avg
 Engine._decoding_fn_avg = _decoding_fn_avg

@@ -41,7 +41,7 @@ class AttentionArgs(C.Structure):
 class AddLnArgs(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("out", vp), ("mean", vp), ("rstd", vp), ("scale", vp), ("offset", vp),
                 ("rows", i64), ("cols", i64), ("eps", f32),
-                ("d_out", vp), ("d_out2", vp), ("ds", vp), ("dscale", vp), ("doffset", vp)]
+                ("d_out", vp), ("d_out2", vp), ("ds", vp), ("dscale", vp), ("doffset", vp), ("dbias", vp)]
 
 
 class EmbedArgs(C.Structure):

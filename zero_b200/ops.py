@@ -118,11 +118,12 @@ def add_ln_fwd(x, y, out, scale, offset, mean=None, rstd=None, eps=1e-8):
     L.check(L.load().zb_add_ln_fwd(C.byref(a), _stream()), "zb_add_ln_fwd")
 
 
-def add_ln_bwd(x, y, d_out, d_out2, mean, rstd, scale, ds, dscale, doffset):
+def add_ln_bwd(x, y, d_out, d_out2, mean, rstd, scale, ds, dscale, doffset, dbias=None):
     a = L.AddLnArgs()
     a.x, a.y, a.mean, a.rstd, a.scale = _p(x), _p(y), _p(mean), _p(rstd), _p(scale)
     a.rows, a.cols = x.numel() // x.shape[-1], x.shape[-1]
     a.d_out, a.d_out2, a.ds, a.dscale, a.doffset = _p(d_out), _p(d_out2), _p(ds), _p(dscale), _p(doffset)
+    a.dbias = _p(dbias)
     L.check(L.load().zb_add_ln_bwd(C.byref(a), _stream()), "zb_add_ln_bwd")
 
 

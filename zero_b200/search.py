@@ -6,6 +6,10 @@ t = 0, GNMT length penalty, top-2k over beam*V, alive / finished bookkeeping) is
 (zb_beam_step, csrc/beam.cu); the loop condition of search.py:85-113 is zb_beam_cond.  Model state is not
 tiled per beam the way search.py:36-39 does: per-sentence tensors (encoder output, projected memory) stay
 [B, ...] and only per-beam caches are reordered, by the `parent` rows the step kernel returns.
+
+The reference wraps the step in a tf.while_loop (search.py:251); here every step index t owns a CUDA graph
+(decoder step + beam step + cache reorder, ~100 kernels) captured the second time that (shape, t) is seen and
+replayed afterwards, so the host only evaluates the loop condition.
 """
 from __future__ import annotations
 
@@ -21,28 +25,48 @@ class BeamState(object):
     """Device-side alive / finished buffers of search.py:46-54 plus the step / condition kernels."""
 
     def __init__(self, batch, beam, vocab, source, decode_length, alpha, temperature, inf_value, device,
-                 eos_id=2, pad_id=0):
+                 eos_id=2, pad_id=0, cap=None):
         self.B, self.K, self.V = batch, beam, vocab
         self.alpha, self.temperature, self.inf_value = float(alpha), float(temperature), float(inf_value)
         self.eos_id, self.pad_id = eos_id, pad_id
-        src_len = (source != 0).sum(1)
-        self.max_len = (src_len + int(decode_length)).to(torch.int32).contiguous()
-        self.cap = int(self.max_len.max().item()) + 2
-        # ((5 + max_len) / 6) ^ alpha in fp32 on the host, like the reference's tf.pow on a float tensor
-        ml = (src_len.float().cpu() + float(decode_length))
-        self.max_penalty = torch.pow((5.0 + ml) / 6.0, self.alpha).to(device)
+        self.decode_length = int(decode_length)
+        self.device = device
+        source = torch.as_tensor(source)
+        self.cap = int(cap) if cap is not None else int(source.shape[1]) + self.decode_length + 2
         i32, f32 = torch.int32, torch.float32
-        self.alive_seq = torch.full((batch, beam, self.cap), pad_id, dtype=i32, device=device)
-        logp = torch.full((batch, beam), F32_MIN, dtype=f32)
-        logp[:, 0] = 0.0
-        self.alive_logp = logp.to(device)
+        self.max_len = torch.zeros(batch, dtype=i32, device=device)
+        self.max_penalty = torch.ones(batch, dtype=f32, device=device)
+        self.alive_seq = torch.zeros(batch, beam, self.cap, dtype=i32, device=device)
+        self.alive_logp = torch.zeros(batch, beam, dtype=f32, device=device)
         self.alive_score = torch.zeros(batch, beam, dtype=f32, device=device)
         self.fin_seq = torch.zeros(batch, beam, self.cap, dtype=i32, device=device)
-        self.fin_score = torch.full((batch, beam), F32_MIN, dtype=f32, device=device)
+        self.fin_score = torch.zeros(batch, beam, dtype=f32, device=device)
         self.fin_flag = torch.zeros(batch, beam, dtype=i32, device=device)
         self.parent = torch.arange(batch * beam, dtype=i32, device=device)
         self.tmp_seq = torch.zeros(batch, 3 * beam, self.cap, dtype=i32, device=device)
         self.active = torch.ones(1, dtype=i32, device=device)
+        self.tok_buf = torch.zeros(batch * beam, 1, dtype=i32, device=device)
+        init_logp = torch.full((batch, beam), F32_MIN, dtype=f32)
+        init_logp[:, 0] = 0.0
+        self._init_logp = init_logp.to(device)
+        self.time = 0
+        self.reset(source)
+
+    def reset(self, source):
+        """search.py:46-54 initial state for a new batch (buffers are reused, addresses stay fixed)."""
+        src = torch.as_tensor(source)
+        src_len = (src != 0).sum(1).cpu()
+        assert int(src_len.max()) + self.decode_length + 2 <= self.cap, "BeamState capacity too small"
+        self.max_len.copy_((src_len + self.decode_length).to(torch.int32))
+        # ((5 + max_len) / 6) ^ alpha in fp32 on the host, like the reference's tf.pow on a float tensor
+        ml = src_len.float() + float(self.decode_length)
+        self.max_penalty.copy_(torch.pow((5.0 + ml) / 6.0, self.alpha))
+        self.alive_seq.fill_(self.pad_id)
+        self.alive_logp.copy_(self._init_logp)
+        self.alive_score.zero_()
+        self.fin_seq.zero_()
+        self.fin_score.fill_(F32_MIN)
+        self.fin_flag.zero_()
         self.time = 0
 
     def _args(self, logits, t):
@@ -63,8 +87,9 @@ class BeamState(object):
         return bool(self.active.item())
 
     def last_tokens(self, t):
-        """[B*beam, 1] int32: the token fed to decoding_fn at step t (search.py:130)."""
-        return self.alive_seq[:, :, t].reshape(self.B * self.K, 1).contiguous()
+        """[B*beam, 1] int32: the token fed to decoding_fn at step t (search.py:130); static buffer."""
+        self.tok_buf.copy_(self.alive_seq[:, :, t].reshape(self.B * self.K, 1))
+        return self.tok_buf
 
     def step(self, logits, t):
         ops.beam_step(self._args(logits, t))
@@ -77,7 +102,7 @@ class BeamState(object):
         any_fin = (self.fin_flag != 0).any(1)
         seq = torch.where(any_fin[:, None, None], self.fin_seq[:, :, :t + 1], self.alive_seq[:, :, :t + 1])
         score = torch.where(any_fin[:, None], self.fin_score, self.alive_score)
-        return {"seq": seq[:, :, 1:], "score": score}
+        return {"seq": seq[:, :, 1:].clone(), "score": score.clone()}
 
 
 def beam_search(features, encoding_fn, decoding_fn, params):
@@ -86,18 +111,53 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     zero_b200's infer_fn; `state.reorder(parent)` replaces the gather_nd over the tiled state."""
     source = features["source"]
     state = encoding_fn(source)
+    eng = state.engine
     dev = state.device
     src = torch.as_tensor(source).to(dev)
     B = src.shape[0]
     K = int(params.beam_size)
-    state.begin_search(K)
-    st = BeamState(B, K, state.vocab, src, params.decode_length, params.decode_alpha,
-                   getattr(params, "beam_search_temperature", 1.0), getattr(params, "dtype_inf", 1e8), dev,
-                   eos_id=params.tgt_vocab.eos(), pad_id=params.tgt_vocab.pad())
-    t = 0
-    while st.not_finished(t):
+    cap = int(src.shape[1]) + int(params.decode_length) + 2
+    key = (B, K, state.vocab, cap, float(params.decode_alpha), int(params.decode_length))
+    cache = eng.__dict__.setdefault("_beam_states", {})
+    st = cache.get(key)
+    if st is None:
+        st = BeamState(B, K, state.vocab, src, params.decode_length, params.decode_alpha,
+                       getattr(params, "beam_search_temperature", 1.0), getattr(params, "dtype_inf", 1e8), dev,
+                       eos_id=params.tgt_vocab.eos(), pad_id=params.tgt_vocab.pad(), cap=cap)
+        cache[key] = st
+    else:
+        st.reset(src)
+    state.begin_search(K, cap)
+    # CUDA-graph replay is only valid for the engine's own decoding_fn (a wrapped one may have side effects)
+    own = getattr(decoding_fn, "__self__", None) is eng and getattr(decoding_fn, "__func__", None) is type(eng).decoding_fn
+    use_graph = own and bool(getattr(params, "decode_graph", True))
+    graphs = eng.__dict__.setdefault("_decode_graphs", {})
+    seen = eng.__dict__.setdefault("_decode_seen", {})
+
+    def run_step(t):
+        nonlocal state
         logits, state = decoding_fn(st.last_tokens(t), state, t)
         parent = st.step(logits, t)
         state.reorder(parent, t)
+
+    t = 0
+    while st.not_finished(t):
+        gkey = key + (int(src.shape[1]), t)
+        g = graphs.get(gkey) if use_graph else None
+        if g is not None:
+            g.replay()
+            st.time = t + 1
+            state.swap_buffers()
+        elif use_graph and seen.get(gkey):
+            # second visit: every workspace buffer exists, capture this step (capture does not execute it)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run_step(t)      # records the kernels; the host-side buffer swap / time bookkeeping happens now
+            graphs[gkey] = g
+            g.replay()
+        else:
+            seen[gkey] = True
+            run_step(t)
         t += 1
     return st.result()
