@@ -152,22 +152,18 @@ def decode_bench(device, batches=3):
     eng.ps.init_random(7)
     eng.decode_length = 0
     tot_tok, tot_steps, tot_ms = 0, 0, 0.0
-    for i in range(batches + 1):
+    for i in range(batches + 2):
         src, _ = make_batch(500 + i, 64)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        steps = {"n": 0}
-
-        def dec(tok, state, t):
-            steps["n"] += 1
-            return eng.decoding_fn(tok, state, t)
-
-        out = search.beam_search({"source": src}, eng.encoding_fn, dec, hp)
+        # the engine's own decoding_fn: beam_search replays one CUDA graph per step index
+        out = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+        steps = {"n": int(out["seq"].shape[-1])}
         e1.record()
         torch.cuda.synchronize()
-        if i == 0:
-            continue  # warm-up batch (allocations)
+        if i < 2:
+            continue  # batch 0 allocates the workspace, batch 1 captures the per-step CUDA graphs
         top1 = out["seq"][:, 0, :].cpu()
         lens = []
         for row in top1.tolist():
@@ -187,37 +183,52 @@ def decode_bench(device, batches=3):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 def gemm_roofline(eng, src, tgt, peaks):
-    """Dominant kernel = zb_gemm (tcgen05).  Re-run one step eagerly with CUDA events around every GEMM launch
-    (on the launching stream) and divide the algorithmic GEMM FLOPs by the summed launch durations."""
+    """Dominant kernel = zb_gemm (tcgen05, 201 launches per step).  The GEMM launches of one real step are recorded
+    (same operands, same order), re-issued back to back from a CUDA graph — so no host launch gaps pollute the
+    number — and timed with CUDA events on the launching stream: achieved = algorithmic GEMM FLOPs / that time."""
     import torch
     from zero_b200 import ops
-    records = []
+    calls, flops = [], [0.0]
     real = ops.gemm
 
-    def timed(a, b, out, a_layout=0, b_layout=1, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = real(a, b, out, a_layout, b_layout, **kw)
-        e1.record()
+    def recording(a, b, out, a_layout=0, b_layout=1, **kw):
         M = kw.get("m") or (a.shape[0] if a_layout == 0 else a.shape[1])
         K = kw.get("k") or (a.shape[1] if a_layout == 0 else a.shape[0])
         N = kw.get("n") or (b.shape[0] if b_layout == 0 else b.shape[1])
-        records.append((e0, e1, 2.0 * M * N * K))
-        return r
+        flops[0] += 2.0 * M * N * K
+        calls.append(lambda: real(a, b, out, a_layout, b_layout, **kw))
+        return real(a, b, out, a_layout, b_layout, **kw)
 
-    ops.gemm = timed
+    side = getattr(eng, "side", None)
+    eng.side = None  # record the launches in program order on one stream
+    ops.gemm = recording
     try:
         eng.forward_backward(src, tgt, compact=False)
         torch.cuda.synchronize()
     finally:
         ops.gemm = real
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-    flops = sum(f for _, _, f in records)
-    achieved = flops / (ms * 1e-3) / 1e12
+        eng.side = side
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for c in calls:
+            c()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    achieved = flops[0] / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gemm_bf16_tcgen05", "launches_per_step": len(records),
-            "gemm_ms_per_step": ms, "gemm_flops_per_step": flops,
+            "traffic": None, "kernel": "gemm_bf16_tcgen05", "launches_per_step": len(calls),
+            "gemm_ms_per_step": ms, "avg_launch_us": 1000.0 * ms / max(len(calls), 1),
+            "gemm_flops_per_step": flops[0],
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
             if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"}
 

@@ -37,7 +37,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, NV <= 2 ? 6 : 2)
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                   __nv_bfloat16* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
                   const float* __restrict__ scale, const float* __restrict__ offset, long long rows, int cols,
@@ -84,8 +84,14 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
       const int v = lane + 32 * i;
       if (v < nvec) {
         float o[8];
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + v * 8)),
+                     sc1 = __ldg(reinterpret_cast<const float4*>(scale + v * 8) + 1),
+                     of0 = __ldg(reinterpret_cast<const float4*>(offset + v * 8)),
+                     of1 = __ldg(reinterpret_cast<const float4*>(offset + v * 8) + 1);
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float of[8] = {of0.x, of0.y, of0.z, of0.w, of1.x, of1.y, of1.z, of1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __ldg(scale + v * 8 + e) * (s[i][e] - mu) * rs + __ldg(offset + v * 8 + e);
+        for (int e = 0; e < 8; ++e) o[e] = sc[e] * (s[i][e] - mu) * rs + of[e];
         store8(out + row * cols + v * 8, o);
       }
     }

@@ -34,6 +34,7 @@ struct GemmKParams {
   float alpha;
   int flags;
   int d_f32;
+  unsigned long long* trace;  // debug (ZB_GEMM_TRACE=1): CTA 0 records globaltimer at 7 points of its life
 };
 
 constexpr int kBM = 128;
@@ -87,6 +88,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.mt * p.nt * p.splits;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  if (tracing && threadIdx.x == 0) p.trace[0] = globaltimer_ns();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -111,6 +114,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of the previous
   // kernel when launched with programmatic stream serialisation; from here on we touch its results.
   grid_dep_wait();
+  if (tracing && threadIdx.x == 0) p.trace[1] = globaltimer_ns();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -173,6 +177,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (tracing && tile == blockIdx.x && kb == kb0) p.trace[2] = globaltimer_ns();
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -189,6 +194,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (tracing && tile == blockIdx.x) p.trace[3] = globaltimer_ns();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -309,6 +315,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int c0 = half * NCH;
       prefetch_chunk(row, row_ok, n0 + c0 * 32, bias_a, mk_a);
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (tracing && tile == blockIdx.x && warp == 2 && lane == 0) p.trace[4] = globaltimer_ns();
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c0 * 32;
       uint32_t ra[32], rb[32];
@@ -336,6 +343,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (tracing && tile == blockIdx.x && warp == 2 && lane == 0) p.trace[5] = globaltimer_ns();
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -345,6 +353,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (tracing && threadIdx.x == 0) p.trace[6] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -457,6 +466,13 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   p.d = a->d; p.ldd = a->ldd; p.bias = a->bias;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
   p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
+  p.trace = nullptr;
+  static const bool trace_on = getenv("ZB_GEMM_TRACE") != nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 8 * sizeof(unsigned long long));
+    p.trace = trace_buf;
+  }
   p.kb_total = (p.K + kBK - 1) / kBK;
   p.mt = (p.M + kBM - 1) / kBM;
 
@@ -517,9 +533,20 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   const long long total = tiles * p.splits;
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int lrc;
   switch (bn) {
-    case 64: return dispatch_layout<64>(a_mn, b_mn, ta, tb, p, grid, st);
-    case 128: return dispatch_layout<128>(a_mn, b_mn, ta, tb, p, grid, st);
-    default: return dispatch_layout<256>(a_mn, b_mn, ta, tb, p, grid, st);
+    case 64: lrc = dispatch_layout<64>(a_mn, b_mn, ta, tb, p, grid, st); break;
+    case 128: lrc = dispatch_layout<128>(a_mn, b_mn, ta, tb, p, grid, st); break;
+    default: lrc = dispatch_layout<256>(a_mn, b_mn, ta, tb, p, grid, st); break;
   }
+  if (trace_on && lrc == ZB_OK) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "[zb_gemm trace] m=%d n=%d k=%d bn=%d splits=%d grid=%d | ns since entry: dep_wait %llu, first data %llu, "
+            "tile0 mma issued %llu, tile0 acc ready %llu, tile0 epilogue done %llu, exit %llu\n",
+            p.M, p.N, p.K, bn, p.splits, grid, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0]);
+  }
+  return lrc;
 }
