@@ -1,5 +1,6 @@
 // abi.cu — process-wide pieces of the C ABI: version, thread-local error string, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "zb_common.h"
@@ -14,6 +15,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("ZB_NO_PDL") == nullptr;
+  return on;
 }
 
 int num_sms() {

@@ -42,6 +42,7 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   __nv_bfloat16* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
                   const float* __restrict__ scale, const float* __restrict__ offset, long long rows, int cols,
                   float eps) {
+  grid_dep_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
   for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
@@ -108,6 +109,7 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
                   __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale, float* __restrict__ doffset,
                   float* __restrict__ dbias, long long rows, int cols) {
+  grid_dep_wait();
   extern __shared__ float red[];  // [kLnWarps][cols] x 2
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
@@ -227,7 +229,7 @@ extern "C" int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream) {
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
 #define CALL(N)                                                                                              \
-  add_ln_fwd_kernel<N><<<(int)blocks, kLnWarps * 32, 0, st>>>(                                               \
+  ZB_LAUNCH(add_ln_fwd_kernel<N>, (int)blocks, kLnWarps * 32, 0, st,                                                \
       (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (__nv_bfloat16*)a->out, a->mean, a->rstd, a->scale, \
       a->offset, a->rows, (int)a->cols, a->eps)
   ZB_LN_DISPATCH(nv, CALL);
@@ -251,7 +253,7 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   do {                                                                                                       \
     if (smem > 48 * 1024)                                                                                    \
       cudaFuncSetAttribute(add_ln_bwd_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    add_ln_bwd_kernel<N><<<(int)blocks, kLnWarps * 32, smem, st>>>(                                          \
+    ZB_LAUNCH(add_ln_bwd_kernel<N>, (int)blocks, kLnWarps * 32, smem, st,                                           \
         (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
         (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
         a->doffset, a->dbias, a->rows, (int)a->cols);                                                                  \

@@ -66,6 +66,7 @@ struct Smem {
 // ------------------------------------------------------------------------------------------------ forward
 template <int DH>
 __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_generic(const AttnP p) {
+  grid_dep_wait();
   constexpr int ND = (DH + 31) / 32;
   extern __shared__ float smem_f[];
   Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_generic(const Att
 // ------------------------------------------------------------------------------------------------ backward: dq
 template <int DH>
 __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const AttnP p) {
+  grid_dep_wait();
   constexpr int ND = (DH + 31) / 32;
   extern __shared__ float smem_f[];
   Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
 template <int DH>
 __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dkv_generic(const AttnP p) {
+  grid_dep_wait();
   constexpr int ND = (DH + 31) / 32;
   extern __shared__ float smem_f[];
   Smem<DH>& sm = *reinterpret_cast<Smem<DH>*>(smem_f);
@@ -422,7 +425,7 @@ int attention_generic_fwd(const zb_attention_args* a, cudaStream_t st) {
     const size_t sb = smem_bytes<DH>(p, tables);                                 \
     int rc = set_smem(attn_fwd_generic<DH>, sb);                                 \
     if (rc) return rc;                                                           \
-    attn_fwd_generic<DH><<<grid, kAttnWarps * 32, sb, st>>>(p);                  \
+    ZB_LAUNCH(attn_fwd_generic<DH>, grid, kAttnWarps * 32, sb, st, p);                  \
   } while (0)
   switch (a->dh) {
     case 16: LAUNCH(16); break;
@@ -444,13 +447,13 @@ int attention_generic_bwd(const zb_attention_args* a, cudaStream_t st) {
     const size_t s1 = smem_bytes<DH>(p, rpr ? 4 : 0);                            \
     int rc = set_smem(attn_bwd_dq_generic<DH>, s1);                              \
     if (rc) return rc;                                                           \
-    attn_bwd_dq_generic<DH><<<gq, kAttnWarps * 32, s1, st>>>(p);                 \
+    ZB_LAUNCH(attn_bwd_dq_generic<DH>, gq, kAttnWarps * 32, s1, st, p);                 \
     rc = check_launch("zb_attention_bwd(dq)");                                   \
     if (rc) return rc;                                                           \
     const size_t s2 = smem_bytes<DH>(p, rpr ? 2 : 0);                            \
     rc = set_smem(attn_bwd_dkv_generic<DH>, s2);                                 \
     if (rc) return rc;                                                           \
-    attn_bwd_dkv_generic<DH><<<gk, kAttnWarps * 32, s2, st>>>(p);                \
+    ZB_LAUNCH(attn_bwd_dkv_generic<DH>, gk, kAttnWarps * 32, s2, st, p);                \
   } while (0)
   switch (a->dh) {
     case 16: LAUNCH(16); break;

@@ -144,6 +144,7 @@ __device__ __forceinline__ void store_c_bf16(__nv_bfloat16* base, long long ld, 
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
+  grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
 
 // ------------------------------------------------------------------------------------------------ backward: dq
 __global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
+  grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
 __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const Params p) {
+  grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sDO[64 * 64];
   __shared__ float sLse[64], sDelta[64];
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BK;
@@ -406,7 +409,7 @@ bool attention_mma_supported(const zb_attention_args* a, bool bwd) {
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   const dim3 grid((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
-  fa::fwd_kernel<<<grid, fa::NT, 0, st>>>(p);
+  ZB_LAUNCH(fa::fwd_kernel, grid, fa::NT, 0, st, p);
   return check_launch("zb_attention_fwd(mma)");
 }
 
@@ -414,10 +417,10 @@ int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   const dim3 gq((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
   const dim3 gk((a->lk + fa::BK - 1) / fa::BK, a->heads, a->batch);
-  fa::bwd_dq_kernel<<<gq, fa::NT, 0, st>>>(p);
+  ZB_LAUNCH(fa::bwd_dq_kernel, gq, fa::NT, 0, st, p);
   int rc = check_launch("zb_attention_bwd(mma dq)");
   if (rc) return rc;
-  fa::bwd_dkv_kernel<<<gk, fa::NT, 0, st>>>(p);
+  ZB_LAUNCH(fa::bwd_dkv_kernel, gk, fa::NT, 0, st, p);
   return check_launch("zb_attention_bwd(mma dkv)");
 }
 

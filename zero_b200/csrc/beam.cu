@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "zb_common.h"
+#include "zb_ptx.cuh"
 
 namespace zb {
 
@@ -55,6 +56,7 @@ __device__ void small_topk(const float* v, int n, int k, float* out_v, int* out_
 
 template <int N2>
 __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const zb_beam_args a) {
+  grid_dep_wait();
   if (a.active && a.active[0] == 0) return;
   const int b = blockIdx.x, K = a.beam, V = a.vocab, t = a.time, cap = a.seq_cap;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const zb_beam_a
 
 // search.py:85-113 _not_finished(time): not(all_b(worst finished > best alive bound)) and any_b(time < max_len)
 __global__ void beam_cond_kernel(const zb_beam_args a) {
+  grid_dep_wait();
   __shared__ int s_all, s_any;
   if (threadIdx.x == 0) {
     s_all = 1;
@@ -271,8 +274,8 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   ZB_REQUIRE((long long)a->beam * a->vocab < (1ll << 31), "zb_beam_step: beam * vocab overflows int32");
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (2 * a->beam <= 8) beam_step_kernel<8><<<a->batch, kBeamThreads, 0, st>>>(*a);
-  else beam_step_kernel<16><<<a->batch, kBeamThreads, 0, st>>>(*a);
+  if (2 * a->beam <= 8) ZB_LAUNCH(beam_step_kernel<8>, a->batch, kBeamThreads, 0, st, *a);
+  else ZB_LAUNCH(beam_step_kernel<16>, a->batch, kBeamThreads, 0, st, *a);
   return check_launch("zb_beam_step");
 }
 
@@ -280,6 +283,6 @@ extern "C" int zb_beam_cond(const zb_beam_args* a, zb_stream_t stream) {
   using namespace zb;
   ZB_REQUIRE(a && a->active && a->max_len && a->max_penalty && a->alive_logp && a->fin_score && a->fin_flag,
              "zb_beam_cond: null pointer");
-  beam_cond_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
+  ZB_LAUNCH(beam_cond_kernel, 1, 256, 0, reinterpret_cast<cudaStream_t>(stream), *a);
   return check_launch("zb_beam_cond");
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kCeThreads)
 softmax_ce_kernel(const float* __restrict__ logits, long long ld, const int32_t* __restrict__ labels, int batch,
                   int seq_len, float* __restrict__ nll, __nv_bfloat16* __restrict__ d_logits, long long ldd, int vocab,
                   float smooth, float loss_scale) {
+  grid_dep_wait();
   __shared__ float sm_m[kCeThreads / 32], sm_s[kCeThreads / 32], sm_t[kCeThreads / 32];
   __shared__ float sh_lse, sh_sumlogit, sh_w;
   const long long row = blockIdx.x;
@@ -139,6 +140,7 @@ softmax_ce_kernel(const float* __restrict__ logits, long long ld, const int32_t*
 // per_sample[b] = sum_t nll * mask / sum_t mask ; loss = mean_b per_sample  (models/transformer.py:208-216)
 __global__ void ce_reduce_kernel(const float* __restrict__ nll, const int32_t* __restrict__ labels, int batch,
                                  int seq_len, float* __restrict__ per_sample, float* __restrict__ loss) {
+  grid_dep_wait();
   __shared__ float acc[32];
   float local = 0.f;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
@@ -174,14 +176,14 @@ extern "C" int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream) {
   const long long rows = (long long)a->batch * a->seq_len;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (rows > 0) {
-    softmax_ce_kernel<<<(unsigned)rows, kCeThreads, 0, st>>>(a->logits, a->ld, a->labels, a->batch, a->seq_len, a->nll,
+    ZB_LAUNCH(softmax_ce_kernel, (unsigned)rows, kCeThreads, 0, st, a->logits, a->ld, a->labels, a->batch, a->seq_len, a->nll,
                                                             (__nv_bfloat16*)a->d_logits, a->ldd, a->vocab, a->smooth,
                                                             a->loss_scale);
     int rc = check_launch("zb_softmax_ce");
     if (rc) return rc;
   }
   if (a->per_sample || a->loss) {
-    ce_reduce_kernel<<<1, 256, 0, st>>>(a->nll, a->labels, a->batch, a->seq_len, a->per_sample, a->loss);
+    ZB_LAUNCH(ce_reduce_kernel, 1, 256, 0, st, a->nll, a->labels, a->batch, a->seq_len, a->per_sample, a->loss);
     return check_launch("zb_ce_reduce");
   }
   return ZB_OK;

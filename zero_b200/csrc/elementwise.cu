@@ -8,6 +8,7 @@
 namespace zb {
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  grid_dep_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
@@ -20,6 +21,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
@@ -28,6 +30,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long n, long long ld, float* __restrict__ out,
               long long rows_per_block) {
+  grid_dep_wait();
   __shared__ float2 red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long col = ((long long)blockIdx.x * 32 + lane) * 2;
@@ -63,6 +66,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long n, lon
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long nvec, long long ld,
                   float* __restrict__ out, long long rows_per_block) {
+  grid_dep_wait();
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const long long vc = (long long)blockIdx.x * 32 + lane;
@@ -113,6 +117,7 @@ colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long nv
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  grid_dep_wait();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(256)
 adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
                __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps, float lr_t, float gscale,
                const float* __restrict__ clip_scale, float* __restrict__ norms) {
+  grid_dep_wait();
   const float gs = clip_scale ? gscale * clip_scale[0] : gscale;
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (norms) {
@@ -200,9 +206,83 @@ adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__
   }
 }
 
+// Same update, kIt float4 groups per thread: 8x fewer blocks, so the two norm atomics per block stop mattering.
+constexpr int kAdamIt = 8;
+__global__ void __launch_bounds__(256)
+adam_tf_kernel_v2(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                  __nv_bfloat16* __restrict__ pb, long long n, float b1, float b2, float eps, float lr_t, float gscale,
+                  const float* __restrict__ clip_scale, float* __restrict__ norms) {
+  grid_dep_wait();
+  __shared__ float rg[8], rp[8];
+  const float gs = clip_scale ? gscale * clip_scale[0] : gscale;
+  float sg = 0.f, sp = 0.f;
+#pragma unroll 2
+  for (int it = 0; it < kAdamIt; ++it) {
+    const long long i = (((long long)blockIdx.x * kAdamIt + it) * 256 + threadIdx.x) * 4;
+    if (i + 3 < n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+             vv = *reinterpret_cast<float4*>(v + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gu = G[e] * gscale;
+        sg += gu * gu;
+        sp += P[e] * P[e];
+        const float gr = G[e] * gs;
+        M[e] = b1 * M[e] + (1.f - b1) * gr;
+        V[e] = b2 * V[e] + (1.f - b2) * gr * gr;
+        P[e] -= lr_t * M[e] / (sqrtf(V[e]) + eps);
+      }
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+      if (pb) {
+        uint2 o;
+        o.x = pack_bf16x2(pp.x, pp.y);
+        o.y = pack_bf16x2(pp.z, pp.w);
+        *reinterpret_cast<uint2*>(pb + i) = o;
+      }
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const float gu = g[j] * gscale;
+        sg += gu * gu;
+        sp += p[j] * p[j];
+        const float gr = g[j] * gs;
+        m[j] = b1 * m[j] + (1.f - b1) * gr;
+        v[j] = b2 * v[j] + (1.f - b2) * gr * gr;
+        p[j] -= lr_t * m[j] / (sqrtf(v[j]) + eps);
+        if (pb) pb[j] = __float2bfloat16(p[j]);
+      }
+    }
+  }
+  if (norms) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      rg[threadIdx.x >> 5] = sg;
+      rp[threadIdx.x >> 5] = sp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        a += rg[w];
+        b += rp[w];
+      }
+      atomicAdd(norms, a);
+      atomicAdd(norms + 1, b);
+    }
+  }
+}
+
 __global__ void gather_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ index,
                                    uint4* __restrict__ dst, long long rows, long long vec_per_row,
                                    long long pitch_vec) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * vec_per_row) return;
   const long long r = i / vec_per_row, c = i % vec_per_row;
@@ -218,13 +298,13 @@ extern "C" int zb_cast_f32_bf16(const float* src, void* dst, int64_t n, zb_strea
   ZB_REQUIRE(src && dst && n >= 0, "zb_cast_f32_bf16: bad args");
   if (n == 0) return ZB_OK;
   const long long blocks = ((n + 3) / 4 + 255) / 256;
-  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  ZB_LAUNCH(cast_f32_bf16_kernel, (unsigned)blocks, 256, 0, ST(stream), src, (__nv_bfloat16*)dst, n);
   return check_launch("zb_cast_f32_bf16");
 }
 extern "C" int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_stream_t stream) {
   ZB_REQUIRE(src && dst && n >= 0, "zb_cast_bf16_f32: bad args");
   if (n == 0) return ZB_OK;
-  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)src, dst, n);
+  ZB_LAUNCH(cast_bf16_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)src, dst, n);
   return check_launch("zb_cast_bf16_f32");
 }
 extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream) {
@@ -237,7 +317,7 @@ extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float*
     if (by < 1) by = 1;
     const long long rows_pb = ((m + by - 1) / by + 7) / 8 * 8;
     by = (m + rows_pb - 1) / rows_pb;
-    colsum_vec_kernel<<<dim3(bx, (unsigned)by), 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, m, n / 8, ld, out, rows_pb);
+    ZB_LAUNCH(colsum_vec_kernel, dim3(bx, (unsigned)by), 256, 0, ST(stream), (const __nv_bfloat16*)x, m, n / 8, ld, out, rows_pb);
     return check_launch("zb_colsum");
   }
   const unsigned gx = (unsigned)((n + 63) / 64);
@@ -245,7 +325,7 @@ extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float*
   if (gy > (m + 63) / 64) gy = (m + 63) / 64;
   if (gy < 1) gy = 1;
   const long long rpb = (m + gy - 1) / gy;
-  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, m, n, ld, out, rpb);
+  ZB_LAUNCH(colsum_kernel, dim3(gx, (unsigned)gy), 256, 0, ST(stream), (const __nv_bfloat16*)x, m, n, ld, out, rpb);
   return check_launch("zb_colsum");
 }
 extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream) {
@@ -253,14 +333,15 @@ extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t strea
   if (n == 0) return ZB_OK;
   long long blocks = (n + 256 * 16 - 1) / (256 * 16);
   if (blocks > 4ll * num_sms()) blocks = 4ll * num_sms();
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(x, n, out);
+  ZB_LAUNCH(sumsq_kernel, (unsigned)blocks, 256, 0, ST(stream), x, n, out);
   return check_launch("zb_sumsq");
 }
 extern "C" int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream) {
   ZB_REQUIRE(a && a->param && a->m && a->v && a->grad && a->n >= 0, "zb_adam_tf: bad args");
   if (a->n == 0) return ZB_OK;
-  const long long blocks = ((a->n + 3) / 4 + 255) / 256;
-  adam_tf_kernel<<<(unsigned)blocks, 256, 0, ST(stream)>>>(a->param, a->m, a->v, a->grad, (__nv_bfloat16*)a->param_bf16,
+  const long long per_block = 256ll * 4 * kAdamIt;
+  const long long blocks = (a->n + per_block - 1) / per_block;
+  ZB_LAUNCH(adam_tf_kernel_v2, (unsigned)blocks, 256, 0, ST(stream), a->param, a->m, a->v, a->grad, (__nv_bfloat16*)a->param_bf16,
                                                           a->n, a->beta1, a->beta2, a->eps, a->lr_t, a->grad_scale,
                                                           a->clip_scale, a->norms);
   return check_launch("zb_adam_tf");
@@ -272,7 +353,7 @@ extern "C" int zb_gather_rows(const void* src, const int32_t* index, void* dst, 
              "zb_gather_rows: row_bytes / pitch_bytes must be multiples of 16");
   if (rows == 0) return ZB_OK;
   const long long vec = row_bytes / 16, total = rows * vec;
-  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>((const uint4*)src, index, (uint4*)dst, rows,
+  ZB_LAUNCH(gather_rows_kernel, (unsigned)((total + 255) / 256), 256, 0, ST(stream), (const uint4*)src, index, (uint4*)dst, rows,
                                                                              vec, pitch_bytes / 16);
   return check_launch("zb_gather_rows");
 }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kEmbWarps * 32)
 embed_fwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int batch, int len, int dim,
                  int vocab, int shift, int zero_if_all_pad, int time, float mult) {
+  grid_dep_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool all_pad = false;
   if (zero_if_all_pad) {
@@ -74,6 +75,7 @@ embed_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restric
                  const __nv_bfloat16* __restrict__ d_out2,
                  float* __restrict__ d_table, float* __restrict__ d_bias, int batch, int len, int dim, int vocab,
                  int shift, float mult) {
+  grid_dep_wait();
   extern __shared__ float red[];  // [kEmbWarps][dim]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long rows = (long long)batch * len;
@@ -137,7 +139,7 @@ extern "C" int zb_embed_fwd(const zb_embed_args* a, zb_stream_t stream) {
   long long blocks = (rows + kEmbWarps - 1) / kEmbWarps;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  embed_fwd_kernel<<<(int)blocks, kEmbWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  ZB_LAUNCH(embed_fwd_kernel, (int)blocks, kEmbWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream), 
       a->ids, (const __nv_bfloat16*)a->table, a->bias, (__nv_bfloat16*)a->out, a->batch, a->len, a->dim, a->vocab,
       a->shift, a->zero_if_all_pad, a->time, a->mult);
   return check_launch("zb_embed_fwd");
@@ -153,7 +155,7 @@ extern "C" int zb_embed_bwd(const zb_embed_args* a, zb_stream_t stream) {
   const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)kEmbWarps * a->dim * sizeof(float);
-  embed_bwd_kernel<<<(int)blocks, kEmbWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  ZB_LAUNCH(embed_bwd_kernel, (int)blocks, kEmbWarps * 32, smem, reinterpret_cast<cudaStream_t>(stream), 
       a->ids, (const __nv_bfloat16*)a->d_out, (const __nv_bfloat16*)a->d_out2, a->d_table, a->d_bias, a->batch, a->len, a->dim, a->vocab, a->shift,
       a->mult);
   return check_launch("zb_embed_bwd");

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kVWarps * 32)
 gated_rms_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, float* __restrict__ rstd,
                      const float* __restrict__ scale, const float* __restrict__ gate, long long rows, int cols,
                      float eps) {
+  grid_dep_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nvec = cols >> 3;
   for (long long row = (long long)blockIdx.x * kVWarps + warp; row < rows; row += (long long)gridDim.x * kVWarps) {
     float xs[8][8];
@@ -80,6 +81,7 @@ gated_rms_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      const float* __restrict__ rstd, const float* __restrict__ scale,
                      const float* __restrict__ gate, __nv_bfloat16* __restrict__ dx, float* __restrict__ dscale,
                      float* __restrict__ dgate, long long rows, int cols) {
+  grid_dep_wait();
   extern __shared__ float red[];  // 2 x [kVWarps][cols]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nvec = cols >> 3;
   for (int c = threadIdx.x; c < 2 * kVWarps * cols; c += blockDim.x) red[c] = 0.f;
@@ -142,6 +144,7 @@ gated_rms_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 __global__ void aan_gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                                     const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ out,
                                     long long rows, int d) {
+  grid_dep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nvec = d >> 3;
   if (idx >= rows * nvec) return;
@@ -160,6 +163,7 @@ __global__ void aan_gate_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dout,
                                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dy,
                                     __nv_bfloat16* __restrict__ dz, long long rows, int d) {
+  grid_dep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nvec = d >> 3;
   if (idx >= rows * nvec) return;
@@ -190,6 +194,7 @@ __global__ void aan_gate_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
 // mode 1 (cumsum / count, transformer_aan.py:103-108): y[t] = cumsum(x)[t] / max(count_valid(<=t), 1)
 __global__ void prefix_mean_fwd_kernel2(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                         const int32_t* __restrict__ lens, int batch, int len, int dim, int mode) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim >> 1;
   if (i >= (long long)batch * half) return;
@@ -221,6 +226,7 @@ __global__ void prefix_mean_fwd_kernel2(const __nv_bfloat16* __restrict__ x, __n
 }
 __global__ void prefix_mean_bwd_kernel2(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
                                         const int32_t* __restrict__ lens, int batch, int len, int dim, int mode) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim >> 1;
   if (i >= (long long)batch * half) return;
@@ -254,6 +260,7 @@ __global__ void prefix_mean_bwd_kernel2(const __nv_bfloat16* __restrict__ dy, __
 // cached decode: y = (x + sum) / (t + 1); sum += x   (transformer_aan.py:110-112), fp32 running sum
 __global__ void aan_step_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sum,
                                 __nv_bfloat16* __restrict__ y, long long n, float inv) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float s = sum[i] + __bfloat162float(x[i]);
@@ -264,6 +271,7 @@ __global__ void aan_step_kernel(const __nv_bfloat16* __restrict__ x, float* __re
 // out[r, :cols] = a[r, :cols] (+ b[r, :cols]); every operand a strided 2-D bf16 view (pitches in elements)
 __global__ void add2d_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
                              long long ldb, __nv_bfloat16* __restrict__ out, long long ldo, long long rows, int cols) {
+  grid_dep_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nvec = cols >> 3;
   if (i >= rows * nvec) return;
@@ -291,7 +299,7 @@ extern "C" int zb_gated_rms_fwd(const void* x, void* out, float* rstd, const flo
   if (rows == 0) return ZB_OK;
   long long blocks = (rows + kVWarps - 1) / kVWarps;
   if (blocks > 16ll * num_sms()) blocks = 16ll * num_sms();
-  gated_rms_fwd_kernel<<<(int)blocks, kVWarps * 32, 0, ST(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rstd,
+  ZB_LAUNCH(gated_rms_fwd_kernel, (int)blocks, kVWarps * 32, 0, ST(stream), (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rstd,
                                                                     scale, gate, rows, (int)cols, eps);
   return check_launch("zb_gated_rms_fwd");
 }
@@ -305,7 +313,7 @@ extern "C" int zb_gated_rms_bwd(const void* x, const void* dy, const float* rstd
   if (blocks > 2ll * num_sms()) blocks = 2ll * num_sms();
   const size_t smem = (size_t)2 * kVWarps * cols * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(gated_rms_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gated_rms_bwd_kernel<<<(int)blocks, kVWarps * 32, smem, ST(stream)>>>(
+  ZB_LAUNCH(gated_rms_bwd_kernel, (int)blocks, kVWarps * 32, smem, ST(stream), 
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, rstd, scale, gate, (__nv_bfloat16*)dx, dscale, dgate, rows,
       (int)cols);
   return check_launch("zb_gated_rms_bwd");
@@ -315,7 +323,7 @@ extern "C" int zb_aan_gate_fwd(const void* x, const void* y, const void* z, void
   ZB_REQUIRE(x && y && z && out && dim > 0 && dim % 8 == 0, "zb_aan_gate_fwd: bad args");
   const long long n = rows * (dim / 8);
   if (n == 0) return ZB_OK;
-  aan_gate_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
+  ZB_LAUNCH(aan_gate_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), 
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (__nv_bfloat16*)out, rows, dim);
   return check_launch("zb_aan_gate_fwd");
 }
@@ -324,7 +332,7 @@ extern "C" int zb_aan_gate_bwd(const void* x, const void* y, const void* z, cons
   ZB_REQUIRE(x && y && z && dout && dx && dy && dz && dim > 0 && dim % 8 == 0, "zb_aan_gate_bwd: bad args");
   const long long n = rows * (dim / 8);
   if (n == 0) return ZB_OK;
-  aan_gate_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(
+  ZB_LAUNCH(aan_gate_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), 
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, (const __nv_bfloat16*)dout,
       (__nv_bfloat16*)dx, (__nv_bfloat16*)dy, (__nv_bfloat16*)dz, rows, dim);
   return check_launch("zb_aan_gate_bwd");
@@ -334,7 +342,7 @@ extern "C" int zb_prefix_mean_fwd(const void* x, void* y, const int32_t* lens, i
   ZB_REQUIRE(x && y && batch >= 0 && len > 0 && dim % 2 == 0 && (mode == 0 || mode == 1), "zb_prefix_mean_fwd: bad args");
   const long long n = (long long)batch * (dim / 2);
   if (n == 0) return ZB_OK;
-  prefix_mean_fwd_kernel2<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+  ZB_LAUNCH(prefix_mean_fwd_kernel2, (unsigned)((n + 127) / 128), 128, 0, ST(stream), (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
                                                                               lens, batch, len, dim, mode);
   return check_launch("zb_prefix_mean_fwd");
 }
@@ -343,14 +351,14 @@ extern "C" int zb_prefix_mean_bwd(const void* dy, void* dx, const int32_t* lens,
   ZB_REQUIRE(dy && dx && batch >= 0 && len > 0 && dim % 2 == 0 && (mode == 0 || mode == 1), "zb_prefix_mean_bwd: bad args");
   const long long n = (long long)batch * (dim / 2);
   if (n == 0) return ZB_OK;
-  prefix_mean_bwd_kernel2<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
+  ZB_LAUNCH(prefix_mean_bwd_kernel2, (unsigned)((n + 127) / 128), 128, 0, ST(stream), (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx,
                                                                               lens, batch, len, dim, mode);
   return check_launch("zb_prefix_mean_bwd");
 }
 extern "C" int zb_aan_step(const void* x, float* sum, void* y, int64_t n, int32_t time, zb_stream_t stream) {
   ZB_REQUIRE(x && sum && y && n >= 0 && time >= 0, "zb_aan_step: bad args");
   if (n == 0) return ZB_OK;
-  aan_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, sum, (__nv_bfloat16*)y, n,
+  ZB_LAUNCH(aan_step_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)x, sum, (__nv_bfloat16*)y, n,
                                                                       1.f / (float)(time + 1));
   return check_launch("zb_aan_step");
 }
@@ -360,7 +368,7 @@ extern "C" int zb_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, 
              "zb_add2d: cols and pitches must be multiples of 8");
   const long long n = rows * (cols / 8);
   if (n == 0) return ZB_OK;
-  add2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb,
+  ZB_LAUNCH(add2d_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb,
                                                                    (__nv_bfloat16*)out, ldo, rows, (int)cols);
   return check_launch("zb_add2d");
 }

@@ -25,7 +25,30 @@ inline int check_launch(const char* what) {
 
 int num_sms();
 
+// Every kernel of the library starts with griddepcontrol.wait and is launched with programmatic stream
+// serialisation, so its launch latency and prologue overlap the tail of its predecessor in the stream (or in the
+// captured CUDA graph).  ZB_NO_PDL=1 turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface in check_launch()
+}
+
 }  // namespace zb
+
+#define ZB_LAUNCH(kern, grid, block, smem, stream, ...) \
+  ::zb::launch_kernel(kern, dim3(grid), dim3(block), static_cast<size_t>(smem), stream, __VA_ARGS__)
 
 #define ZB_REQUIRE(cond, ...)        \
   do {                               \

@@ -115,9 +115,6 @@ class ParamStore(object):
             self.tf_alias_tgt = "src_emb"
         else:
             self._add("src_emb", (c.vs, c.e), s + "/src_embedding")
-            self._add("tgt_emb", (c.vt, c.e), s + "/tgt_embedding")
-            if not c.share_ts:
-                self._add("softmax_emb", (c.vt, c.e), s + "/softmax_embedding")
         self._add("emb_bias", (c.e,), s + "/bias")
         dh = c.d // c.h
         nb = 2 * c.max_rel + 1
@@ -166,6 +163,14 @@ class ParamStore(object):
             self_attn(key + ".self", tfp + "/self_attention")
             ffn(key + ".ffn", tfp + "/feed_forward")
             ln(key + ".ffn.ln", tfp + "/feed_forward")
+        # Everything from here on receives its last gradient contribution during the DECODER backward, which
+        # finishes before the encoder backward starts: [dec_offset, total) is the first all-reduce bucket and
+        # overlaps with the encoder backward (train.py).
+        self.dec_offset = self.total
+        if not c.share_st:
+            self._add("tgt_emb", (c.vt, c.e), s + "/tgt_embedding")
+            if not c.share_ts:
+                self._add("softmax_emb", (c.vt, c.e), s + "/softmax_embedding")
         for l in range(c.ndec):
             key, tfp = "dec%d" % l, "%s/decoder/layer_%d" % (s, l)
             if c.aan:
@@ -617,6 +622,14 @@ class Engine(object):
     def forward_backward(self, source, target, zero_grad=True, compact=True):
         """train_fn + tf.gradients (models/transformer.py:221-232, main.py:22-45) for one tower.
         Gradients land in self.ps.grad (fp32).  Returns the device loss tensor [1]."""
+        loss = self.forward_backward_decoder(source, target, zero_grad, compact)
+        self.backward_encoder()
+        return loss
+
+    def forward_backward_decoder(self, source, target, zero_grad=True, compact=True):
+        """Phase 1 of a training step: forward of the whole model + backward of the decoder.  When it returns
+        (stream order), every gradient in ps.grad[ps.dec_offset:] is final — the trainer starts all-reducing that
+        bucket while phase 2 runs."""
         c, ws = self.cfg, self.ws
         source = self._prep_ids(source, self.device, compact)
         target = self._prep_ids(target, self.device, compact)
@@ -631,9 +644,16 @@ class Engine(object):
         self.decode_train_bwd(dsave, d_enc32)
         d_enc = ws.get("d_enc", (B * S, c.d))
         ops.cast_f32_bf16(d_enc32, d_enc)
+        self._side_join()
+        self._pending = (d_enc, esave)
+        return loss
+
+    def backward_encoder(self):
+        """Phase 2: backward of the encoder (finalises ps.grad[:ps.dec_offset])."""
+        d_enc, esave = self._pending
+        self._pending = None
         self.encode_bwd(d_enc, esave)
         self._side_join()
-        return loss
 
     def train_loss(self, source, target):
         """train_fn forward only -> (loss, per_sample, logits)."""

@@ -57,38 +57,51 @@ class Trainer(object):
         return float(hp.lrate)
 
     # ------------------------------------------------------------------------------------------ step
-    def _fwd_bwd(self, source, target):
+    def _phases(self, source, target):
+        """Runs phase 1 (forward + decoder backward), calls `between()` hooks via the caller, then phase 2."""
+        eng = self.eng
         if not self.use_graph:
-            return self.eng.forward_backward(source, target)
+            loss = eng.forward_backward_decoder(source, target)
+            return loss, eng.backward_encoder
         key = (tuple(source.shape), tuple(target.shape))
         if self._graph is None or self._static[0] != key:
-            s_src = torch.empty(source.shape, dtype=torch.int32, device=self.eng.device)
-            s_tgt = torch.empty(target.shape, dtype=torch.int32, device=self.eng.device)
+            s_src = torch.empty(source.shape, dtype=torch.int32, device=eng.device)
+            s_tgt = torch.empty(target.shape, dtype=torch.int32, device=eng.device)
             s_src.copy_(source)
             s_tgt.copy_(target)
-            # warm-up on a side stream (allocates every workspace buffer), then capture
+            # warm-up on a side stream (allocates every workspace buffer), then capture the two phases
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.eng.forward_backward(s_src, s_tgt, compact=False)
+                eng.forward_backward(s_src, s_tgt, compact=False)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss = self.eng.forward_backward(s_src, s_tgt, compact=False)
-            self._graph, self._static = g, (key, s_src, s_tgt, loss)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                loss = eng.forward_backward_decoder(s_src, s_tgt, compact=False)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                eng.backward_encoder()
+            self._graph, self._static = (g1, g2), (key, s_src, s_tgt, loss)
         _, s_src, s_tgt, loss = self._static
         s_src.copy_(source, non_blocking=True)
         s_tgt.copy_(target, non_blocking=True)
-        self._graph.replay()
-        return loss
+        self._graph[0].replay()
+        return loss, self._graph[1].replay
 
     def step(self, source, target):
-        """One optimizer step on this rank's batch.  Returns the device loss tensor (no host sync)."""
+        """One optimizer step on this rank's batch.  Returns the device loss tensor (no host sync).
+        Data parallel: the decoder-side bucket of the flat gradient arena is all-reduced (NCCL, async) while the
+        encoder backward is still running; the encoder-side bucket follows; both complete before Adam."""
         eng, ps = self.eng, self.eng.ps
-        loss = self._fwd_bwd(source, target)
+        loss, phase2 = self._phases(source, target)
+        works = []
         if self.world > 1:
-            dist.all_reduce(ps.grad, op=dist.ReduceOp.SUM)
+            works.append(dist.all_reduce(ps.grad[ps.dec_offset:], op=dist.ReduceOp.SUM, async_op=True))
+        phase2()
+        if self.world > 1:
+            works.append(dist.all_reduce(ps.grad[:ps.dec_offset], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()
         # tf.global_norm of gradients and parameters (utils/cycle.py:94-95): a separate pass only when the clip
         # factor needs the gradient norm before the update; otherwise fused into the Adam kernel
         self.norms.zero_()
