@@ -1,0 +1,528 @@
+// gemm2_tcgen05.cu — K1, CTA-pair variant: tcgen05.mma.cta_group::2 (UMMA 256 x BN x 16) over a 2-CTA cluster.
+//
+// Why: timeline traces of the 1-CTA kernel (profiles/r01_gemm_trace.log) show every GEMM of the training step
+// waiting on operand delivery — a 128 x BN tile needs (128 + BN) * 128 B per k-block per SM, more than the
+// ~50-60 B/cycle an SM ingests from L2.  With a CTA pair the B tile is split across the two SMs (each loads
+// BN/2 rows) and the tensor cores of both read it in place, so a 256 x BN pair-tile costs each SM only
+// (128 + BN/2) * 128 B per k-block: 1.5x (BN = 256) to 1.33x (BN = 128) fewer bytes per FLOP.
+//
+// Roles per CTA (320 threads): warp 0 TMA producer (both CTAs; the .cta_group::2 form of cp.async.bulk.tensor
+// signals the LEADER's full barrier), warp 1 MMA issuer (leader CTA only) / TMEM allocator (both),
+// warps 2..9 epilogue (each CTA drains its own 128 accumulator rows from its own TMEM).
+// tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs; the peer's epilogue warps hand the
+// accumulator stage back with a remote mbarrier arrive on the leader's barrier.
+#include <stdlib.h>
+
+#include "zb_common.h"
+#include "zb_ptx.cuh"
+
+namespace zb {
+
+int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);
+
+struct Gemm2Params {
+  int M, N, K;
+  int mt, nt, splits, kb_per_split, kb_total;  // mt counts 256-row pair tiles
+  int gn;
+  void* d;
+  long long ldd;
+  const float* bias;
+  const __nv_bfloat16* mask;
+  long long ldmask;
+  float alpha;
+  int flags;
+  int d_f32;
+};
+
+constexpr int k2BK = 64;
+constexpr int k2Threads = 320;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = 128 * k2BK * 2;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * k2BK * 2;   // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  // acquire at cluster scope: the arrivals come from the peer CTA
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3FF) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) asm volatile("trap;");
+    }
+  }
+}
+// 2-CTA TMA load: data lands in THIS CTA's shared memory, completion bytes are credited to the barrier at the
+// same offset in the LEADER CTA (peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                int32_t c1) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void tile2_coords(const Gemm2Params& p, int tile, int& m_blk, int& n_blk, int& ks) {
+  const int per_split = p.mt * p.nt;
+  ks = tile / per_split;
+  const int t = tile - ks * per_split;
+  const int panel_tiles = p.mt * p.gn;
+  const int pn = t / panel_tiles;
+  const int r = t - pn * panel_tiles;
+  const int w = min(p.gn, p.nt - pn * p.gn);
+  m_blk = r / w;
+  n_blk = pn * p.gn + (r - m_blk * w);
+}
+
+__device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(k2Threads, 1)
+gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const Gemm2Params p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const bool leader = rank == 0;
+  const int num_tiles = p.mt * p.nt * p.splits;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's producer arms it; both CTAs' TMA bytes are credited to the leader's
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps of each CTA (used in the leader only)
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  grid_dep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk, ks;
+        tile2_coords(p, tile, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = m_blk * 256 + (int)rank * 128;       // this CTA's rows of A
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);   // this CTA's rows of B
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * k2BK;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * 8192, &tma_a, &full_bar[stage], m0 + 64 * c, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN/2 n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c)
+              tma_load_2d_2sm(sb + c * 8192, &tma_b, &full_bar[stage], n0 + 64 * c, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      constexpr uint32_t A_LBO = A_MN ? k2BK * 128 : 0, A_KSTEP = A_MN ? 2048 : 32;
+      constexpr uint32_t B_LBO = B_MN ? k2BK * 128 : 0, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk, ks;
+        tile2_coords(p, tile, m_blk, n_blk, ks);
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < k2BK / 16; ++kk) {
+            const uint64_t da = umma_smem_desc(sa + kk * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = umma_smem_desc(sb + kk * B_KSTEP, B_LBO, 1024);
+            umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int flags = p.flags;
+    const float alpha = p.alpha;
+    const bool d_f32 = p.d_f32 != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4]) {
+      if (col0 >= p.N) return;
+      const bool full_cols = (col0 + 32 <= p.N);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
+      if (flags & ZB_EPI_BIAS) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
+      }
+      if (flags & ZB_EPI_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (!row_ok) return;
+      if (flags & ZB_EPI_RELU_MASK) {
+        if (full_cols) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(w[e]);
+              if (!(f.x > 0.f)) v[q * 8 + e * 2] = 0.f;
+              if (!(f.y > 0.f)) v[q * 8 + e * 2 + 1] = 0.f;
+            }
+          }
+        } else {
+          const __nv_bfloat16* mrow = p.mask + static_cast<long long>(row) * p.ldmask + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
+        }
+      }
+      if (d_f32) {
+        float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+        if (flags & ZB_EPI_ACCUM) {
+          if (full_cols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red_add_v4_(drow + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(drow + j, v[j]);
+          }
+        } else {
+          if (full_cols) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(drow)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) drow[j] = v[j];
+          }
+        }
+      } else {
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+        if (full_cols) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            reinterpret_cast<uint4*>(drow)[q] = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) drow[j] = __float2bfloat16(v[j]);
+        }
+      }
+    };
+    auto prefetch_chunk = [&](int row, bool row_ok, int col0, float& bias_lane, uint4 (&mk)[4]) {
+      bias_lane = 0.f;
+      if ((flags & ZB_EPI_BIAS) && col0 + lane < p.N) bias_lane = __ldg(p.bias + col0 + lane);
+      if ((flags & ZB_EPI_RELU_MASK) && row_ok && col0 + 32 <= p.N) {
+        const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + static_cast<long long>(row) * p.ldmask + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk[q] = __ldg(mrow + q);
+      }
+    };
+    const uint32_t leader_tempty0 = mapa_u32(&tempty_bar[0], 0), leader_tempty1 = mapa_u32(&tempty_bar[1], 0);
+
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk, ks;
+      tile2_coords(p, tile, m_blk, n_blk, ks);
+      const int m0 = m_blk * 256 + (int)rank * 128, n0 = n_blk * BN;
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      float bias_a, bias_b;
+      uint4 mk_a[4], mk_b[4];
+      constexpr int NCH = BN / 64;
+      const int c0 = half * NCH;
+      prefetch_chunk(row, row_ok, n0 + c0 * 32, bias_a, mk_a);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c0 * 32;
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tbase, ra);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        __syncwarp();
+        tmem_ld_wait();
+        if (c + 1 < NCH) {
+          tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
+          prefetch_chunk(row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
+        }
+        finish_chunk(ra, row, row_ok, n0 + (c0 + c) * 32, bias_a, mk_a);
+        if (c + 1 < NCH) {
+          __syncwarp();
+          tmem_ld_wait();
+          if (c + 2 < NCH) {
+            tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
+            prefetch_chunk(row, row_ok, n0 + (c0 + c + 2) * 32, bias_a, mk_a);
+          }
+          finish_chunk(rb, row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(acc == 0 ? leader_tempty0 : leader_tempty1);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still signal this CTA's barriers / read its shared memory until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, int grid, cudaStream_t st) {
+  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm2 cudaFuncSetAttribute(smem=%d): %s", Gemm2Cfg<BN>::SMEM_BYTES, cudaGetErrorString(e));
+      return ZB_ECUDA;
+    }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(k2Threads);
+  cfg.dynamicSmemBytes = Gemm2Cfg<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (le != cudaSuccess) {
+    set_error("zb_gemm (cta pair) launch: %s", cudaGetErrorString(le));
+    return ZB_ECUDA;
+  }
+  return check_launch("zb_gemm(2cta)");
+}
+
+template <int BN>
+static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, int grid,
+                     cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, p, grid, st);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, p, grid, st);
+  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, p, grid, st);
+  return launch2<BN, true, true>(ta, tb, p, grid, st);
+}
+
+// Whether the CTA-pair kernel should take this problem.  ZB_GEMM2=0 disables it, ZB_GEMM2=1 forces it whenever legal.
+bool gemm2_wanted(const zb_gemm_args* a) {
+  static const char* env = getenv("ZB_GEMM2");
+  if (env && env[0] == '0') return false;
+  if (a->n < 128 || a->m < 256) return false;
+  if (env && env[0] == '1') return true;
+  return true;
+}
+
+int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
+  Gemm2Params p;
+  p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
+  p.d = a->d; p.ldd = a->ldd; p.bias = a->bias;
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
+  p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
+  p.kb_total = (p.K + k2BK - 1) / k2BK;
+  p.mt = (p.M + 255) / 256;
+  const bool accum = a->flags & ZB_EPI_ACCUM;
+  const int pairs_hw = num_sms() / 2;
+  int bn = 256;
+  auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
+  if (p.N <= 128) bn = 128;
+  if (!accum && bn == 256 && tiles_for(256) < pairs_hw) bn = 128;  // keep every CTA pair busy
+  p.nt = (p.N + bn - 1) / bn;
+  p.gn = bn == 256 ? 6 : 8;
+  if (p.gn > p.nt) p.gn = p.nt;
+  const long long tiles = (long long)p.mt * p.nt;
+  int splits = a->split_k;
+  if (splits <= 0) {
+    splits = 1;
+    if (accum && tiles < pairs_hw) {
+      int max_splits = p.kb_total / 4;
+      if (max_splits < 1) max_splits = 1;
+      if (max_splits > 64) max_splits = 64;
+      double best = 0.0;
+      for (int s = 1; s <= max_splits; ++s) {
+        const long long work = tiles * s;
+        const long long waves = (work + pairs_hw - 1) / pairs_hw;
+        const double eff = (double)work / (double)(waves * pairs_hw);
+        if (eff > best + 0.02) {
+          best = eff;
+          splits = s;
+        }
+      }
+    }
+  }
+  if (splits > 1 && !accum) {
+    set_error("zb_gemm: split_k > 1 requires ZB_EPI_ACCUM");
+    return ZB_EINVAL;
+  }
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  CUtensorMap ta, tb;
+  int rc;
+  const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
+  if (!a_mn) rc = make_map(&ta, a->a, p.K, p.M, a->lda, 128);
+  else rc = make_map(&ta, a->a, p.M, p.K, a->lda, k2BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tb, a->b, p.K, p.N, a->ldb, bn / 2);
+  else rc = make_map(&tb, a->b, p.N, p.K, a->ldb, k2BK);
+  if (rc) return rc;
+  const long long total = tiles * p.splits;
+  const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
+  if (bn == 128) return dispatch2<128>(a_mn, b_mn, ta, tb, p, grid, st);
+  return dispatch2<256>(a_mn, b_mn, ta, tb, p, grid, st);
+}
+
+}  // namespace zb

@@ -21,6 +21,9 @@
 
 namespace zb {
 
+bool gemm2_wanted(const zb_gemm_args* a);
+int gemm2_launch(const zb_gemm_args* a, cudaStream_t st);
+
 struct GemmKParams {
   int M, N, K;
   int mt, nt, splits, kb_per_split, kb_total;
@@ -378,7 +381,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` elements; box {64, box1}; SWIZZLE_128B.
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
+int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable");
@@ -460,6 +463,8 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   ZB_REQUIRE((a->ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0,
              "zb_gemm: destination must be 16-byte aligned with a 16-byte pitch");
   ZB_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31), "zb_gemm: dimension too large");
+  // CTA-pair kernel (tcgen05 cta_group::2, gemm2_tcgen05.cu) for everything with at least one 256 x 128 pair tile
+  if (gemm2_wanted(a)) return gemm2_launch(a, reinterpret_cast<cudaStream_t>(stream));
 
   GemmKParams p;
   p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
