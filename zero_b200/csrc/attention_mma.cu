@@ -10,6 +10,7 @@
 // reference's additive -inf_value.  (A tcgen05/TMEM version is future work: at S = 64 the QK^T / PV tiles are
 // 64x64x64 and attention is ~2% of the layer FLOPs; the dense contractions run on tcgen05 in gemm_tcgen05.cu.)
 #include <math.h>
+#include <stdlib.h>
 
 #include "zb_common.h"
 #include "zb_ptx.cuh"
@@ -371,6 +372,236 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const Params p) {
   store_c_bf16(p.dv + (long long)b * p.bsdv + (long long)k0 * p.lddv + h * DH, p.lddv, warp * 16, krows, dv, 1.f, 1.f);
 }
 
+// ================================================================================================ single-tile path
+// lq <= 64 and lk <= 64 (every attention of the reference's 64-token training batches): one (batch, head) problem is
+// one 64 x 64 tile, so a CTA is handed a stream of (batch, head) items and double-buffers them through shared memory
+// with cp.async — the loads of item i+1 overlap the math of item i and the kernel runs at HBM speed instead of
+// load -> wait -> compute per CTA.  The backward is fused: dQ, dK and dV of an item come from ONE load of
+// Q, K, V, dO, O (the two-kernel general path loads them twice).
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct Tile64Fwd {
+  __nv_bfloat16 q[64 * 64], k[64 * 64], v[64 * 64];
+};
+struct Tile64Bwd {
+  __nv_bfloat16 q[64 * 64], k[64 * 64], v[64 * 64], d_o[64 * 64], o[64 * 64];
+  float lse[64];
+};
+
+__global__ void __launch_bounds__(NT) fwd64_kernel(const Params p, const int items) {
+  grid_dep_wait();
+  extern __shared__ __align__(128) uint8_t smem64[];
+  Tile64Fwd* bufs = reinterpret_cast<Tile64Fwd*>(smem64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  auto issue = [&](int item, int buf) {
+    const int b = item / p.heads, h = item % p.heads;
+    load_tile(bufs[buf].q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
+    load_tile(bufs[buf].k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
+    load_tile(bufs[buf].v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
+    cp_async_commit();
+  };
+  int item = blockIdx.x;
+  if (item < items) issue(item, 0);
+  for (int buf = 0; item < items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < items) {
+      issue(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const Tile64Fwd& T = bufs[buf];
+    const int b = item / p.heads, h = item % p.heads;
+    const int kl = p.key_len ? p.key_len[b] : p.lk;
+    uint32_t qa[4][4];
+    load_a_frags(qa, T.q, warp * 16);
+    float s[8][4], o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = o[i][j] = 0.f;
+    gemm_nk(s, qa, T.k);
+    const int row_abs0 = warp * 16 + g + p.q_offset;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = nt * 8 + 2 * t + (j & 1);
+        const int ra = row_abs0 + (j >> 1) * 8;
+        const bool inb = col < p.lk;
+        const bool valid = inb && col < kl && (!p.causal || col <= ra);
+        float v = s[nt][j] * p.scale;
+        v = inb ? (valid ? v : v - p.inf_value) : -INFINITY;
+        s[nt][j] = v;
+        mx[j >> 1] = fmaxf(mx[j >> 1], v);
+      }
+    const float m0 = quad_max(mx[0]), m1 = quad_max(mx[1]);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pv = __expf(s[nt][j] - ((j >> 1) ? m1 : m0));
+        s[nt][j] = pv;
+        if (j >> 1) l1 += pv; else l0 += pv;
+      }
+    uint32_t pa[4][4];
+    c_to_a(pa, s);
+    gemm_kn(o, pa, T.v);
+    l0 = quad_sum(l0);
+    l1 = quad_sum(l1);
+    store_c_bf16(p.out + (long long)b * p.bso + h * DH, p.ldo, warp * 16, p.lq, o, 1.f / l0, 1.f / l1);
+    if (t == 0 && p.lse) {
+      const int r0 = warp * 16 + g;
+      float* lp = p.lse + ((long long)b * p.heads + h) * p.lq;
+      if (r0 < p.lq) lp[r0] = m0 + __logf(l0);
+      if (r0 + 8 < p.lq) lp[r0 + 8] = m1 + __logf(l1);
+    }
+    __syncthreads();  // everyone is done with bufs[buf] before the next iteration's prefetch overwrites it
+  }
+}
+
+__global__ void __launch_bounds__(NT) bwd64_kernel(const Params p, const int items) {
+  grid_dep_wait();
+  extern __shared__ __align__(128) uint8_t smem64[];
+  Tile64Bwd* bufs = reinterpret_cast<Tile64Bwd*>(smem64);
+  __shared__ float sDelta[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  auto issue = [&](int item, int buf) {
+    const int b = item / p.heads, h = item % p.heads;
+    load_tile(bufs[buf].q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
+    load_tile(bufs[buf].k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
+    load_tile(bufs[buf].v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
+    load_tile(bufs[buf].d_o, p.d_o + (long long)b * p.bsdo + h * DH, p.lddo, p.lq);
+    load_tile(bufs[buf].o, p.o + (long long)b * p.bso + h * DH, p.ldo, p.lq);
+    if (threadIdx.x < 16) {  // 64 fp32 log-sum-exps (lq may be < 64: rows beyond lq read as 0 through the predicate)
+      const int r = threadIdx.x * 4;
+      const float* src = p.lse + ((long long)b * p.heads + h) * p.lq + r;
+      if (r + 3 < p.lq && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        cp_async16(&bufs[buf].lse[r], src, true);
+      } else {
+        for (int e = 0; e < 4; ++e) bufs[buf].lse[r + e] = (r + e < p.lq) ? src[e] : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+  int item = blockIdx.x;
+  if (item < items) issue(item, 0);
+  for (int buf = 0; item < items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < items) {
+      issue(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const Tile64Bwd& T = bufs[buf];
+    const int b = item / p.heads, h = item % p.heads;
+    const int kl = p.key_len ? p.key_len[b] : p.lk;
+    // ---- delta = rowsum(dO * O) for this warp's 16 query rows -> shared (every warp needs all 64 below)
+    uint32_t doa[4][4];
+    load_a_frags(doa, T.d_o, warp * 16);
+    float delta[2] = {0.f, 0.f};
+    {
+      uint32_t oa[4][4];
+      load_a_frags(oa, T.o, warp * 16);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 x = unpack_bf16x2(doa[ks][r]), y = unpack_bf16x2(oa[ks][r]);
+          delta[r & 1] += x.x * y.x + x.y * y.y;
+        }
+      delta[0] = quad_sum(delta[0]);
+      delta[1] = quad_sum(delta[1]);
+      if (t == 0) {
+        sDelta[warp * 16 + g] = delta[0];
+        sDelta[warp * 16 + g + 8] = delta[1];
+      }
+    }
+    __syncthreads();
+    // ---- dQ for query rows [16w, 16w + 16)
+    {
+      uint32_t qa[4][4];
+      load_a_frags(qa, T.q, warp * 16);
+      float s[8][4], dp[8][4], dq[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = dp[i][j] = dq[i][j] = 0.f;
+      gemm_nk(s, qa, T.k);
+      gemm_nk(dp, doa, T.v);
+      const int r0 = warp * 16 + g;
+      const float lse0 = T.lse[r0], lse1 = T.lse[r0 + 8];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = nt * 8 + 2 * t + (j & 1);
+          const int ra = r0 + p.q_offset + (j >> 1) * 8;
+          const bool inb = col < p.lk;
+          const bool valid = inb && col < kl && (!p.causal || col <= ra);
+          float v = s[nt][j] * p.scale;
+          v = valid ? v : v - p.inf_value;
+          const float pv = inb ? __expf(v - ((j >> 1) ? lse1 : lse0)) : 0.f;
+          s[nt][j] = pv * (dp[nt][j] - delta[j >> 1]);
+        }
+      uint32_t dsa[4][4];
+      c_to_a(dsa, s);
+      gemm_kn(dq, dsa, T.k);
+      store_c_bf16(p.dq + (long long)b * p.bsdq + h * DH, p.lddq, warp * 16, p.lq, dq, p.scale, p.scale);
+    }
+    // ---- dK, dV for key rows [16w, 16w + 16)
+    {
+      uint32_t ka[4][4], va[4][4];
+      load_a_frags(ka, T.k, warp * 16);
+      load_a_frags(va, T.v, warp * 16);
+      float st[8][4], dpt[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st[i][j] = dpt[i][j] = 0.f;
+      gemm_nk(st, ka, T.q);
+      gemm_nk(dpt, va, T.d_o);
+      const int key0 = warp * 16 + g;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qi = nt * 8 + 2 * t + (j & 1);
+          const int key = key0 + (j >> 1) * 8;
+          const bool inb = qi < p.lq && key < p.lk;
+          const bool valid = key < kl && (!p.causal || key <= qi + p.q_offset);
+          float v = st[nt][j] * p.scale;
+          v = valid ? v : v - p.inf_value;
+          const float pv = inb ? __expf(v - T.lse[qi]) : 0.f;
+          st[nt][j] = pv;
+          dpt[nt][j] = pv * (dpt[nt][j] - sDelta[qi]);
+        }
+      uint32_t pa[4][4], dsa[4][4];
+      c_to_a(pa, st);
+      c_to_a(dsa, dpt);
+      float dk[8][4], dv[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dk[i][j] = dv[i][j] = 0.f;
+      gemm_kn(dv, pa, T.d_o);
+      gemm_kn(dk, dsa, T.q);
+      store_c_bf16(p.dk + (long long)b * p.bsdk + h * DH, p.lddk, warp * 16, p.lk, dk, p.scale, p.scale);
+      store_c_bf16(p.dv + (long long)b * p.bsdv + h * DH, p.lddv, warp * 16, p.lk, dv, 1.f, 1.f);
+    }
+    __syncthreads();  // bufs[buf] and sDelta are free again
+  }
+}
+
 static Params to_params(const zb_attention_args* a) {
   Params p;
   p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
@@ -406,8 +637,25 @@ bool attention_mma_supported(const zb_attention_args* a, bool bwd) {
   return true;
 }
 
+static bool tile64_ok(const zb_attention_args* a) {
+  static const bool off = getenv("ZB_NO_TILE64") != nullptr;
+  return !off && a->lq <= 64 && a->lk <= 64 && a->kv_group <= 1;
+}
+
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
+  if (tile64_ok(a)) {
+    const int items = a->batch * a->heads;
+    const int smem = 2 * (int)sizeof(fa::Tile64Fwd);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(fa::fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr = true;
+    }
+    const int grid = items < 3 * num_sms() ? items : 3 * num_sms();
+    ZB_LAUNCH(fa::fwd64_kernel, grid, fa::NT, smem, st, p, items);
+    return check_launch("zb_attention_fwd(tile64)");
+  }
   const dim3 grid((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
   ZB_LAUNCH(fa::fwd_kernel, grid, fa::NT, 0, st, p);
   return check_launch("zb_attention_fwd(mma)");
@@ -415,6 +663,18 @@ int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
 
 int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
+  if (tile64_ok(a)) {
+    const int items = a->batch * a->heads;
+    const int smem = 2 * (int)sizeof(fa::Tile64Bwd);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(fa::bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr = true;
+    }
+    const int grid = items < 2 * num_sms() ? items : 2 * num_sms();
+    ZB_LAUNCH(fa::bwd64_kernel, grid, fa::NT, smem, st, p, items);
+    return check_launch("zb_attention_bwd(tile64)");
+  }
   const dim3 gq((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
   const dim3 gk((a->lk + fa::BK - 1) / fa::BK, a->heads, a->batch);
   ZB_LAUNCH(fa::bwd_dq_kernel, gq, fa::NT, 0, st, p);

@@ -478,7 +478,13 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   int bn = 256;
   auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
   if (p.N <= 128) bn = 128;
-  if (!accum && bn == 256 && tiles_for(256) < pairs_hw) bn = 128;  // keep every CTA pair busy
+  if (!accum && bn == 256) {
+    // wave quantisation: cost ~ (#waves of pair tiles) x (tile width); e.g. N = 1536 at M = 4096 is 96 tiles of 256
+    // (2 waves of 74 pairs) but 192 tiles of 128 (3 waves of half the work each)
+    const long long w256 = (tiles_for(256) + pairs_hw - 1) / pairs_hw * 256;
+    const long long w128 = (tiles_for(128) + pairs_hw - 1) / pairs_hw * 128;
+    if (w128 < w256) bn = 128;
+  }
   p.nt = (p.N + bn - 1) / bn;
   p.gn = bn == 256 ? 6 : 8;
   if (p.gn > p.nt) p.gn = p.nt;
