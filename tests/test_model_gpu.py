@@ -10,8 +10,9 @@ from tests.golden_util import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TRAIN_MODELS = ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela"]
-SCORE_MODELS = TRAIN_MODELS + ["transformer_aan", "transformer_aan_cumsum", "transformer_fuse"]
+TRAIN_MODELS = ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela", "transformer_aan",
+                "transformer_aan_cumsum", "transformer_fuse"]
+SCORE_MODELS = TRAIN_MODELS
 DECODE_MODELS = SCORE_MODELS
 
 

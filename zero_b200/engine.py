@@ -601,13 +601,16 @@ class Engine(object):
             self._side_layer_begin(tag, l)
             ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
             dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], bw + ".ffn")
-            dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
-            dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
-                                       bw + ".cross")
-            ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
-            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], bw + ".att")
+            if c.aan or c.fuse:
+                d1, d2 = self._avg_layer_bwd(key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save)
+            else:
+                dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
+                dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
+                                           bw + ".cross")
+                ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
+                dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], bw + ".att")
+                d1, d2 = ds1, dx
             self._side_layer_end(tag, l)
-            d1, d2 = ds1, dx
         ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
 
     # ================================================================================== public steps

@@ -1,8 +1,6 @@
 """Average-attention family on the engine: transformer_aan (models/transformer_aan.py:120-260) and the merged
-attention of transformer_fuse (models/transformer_fuse.py:120-165, func.py:258-275).
-
-Teacher-forced forward (train_fn forward / score_fn) and cached decode are built; the backward pass of these two
-variants is the next row to build ("what comes next").
+attention of transformer_fuse (models/transformer_fuse.py:120-165, func.py:258-275): teacher-forced forward,
+backward, and cached decode (one fp32 running sum per layer instead of a growing K/V cache).
 """
 from __future__ import annotations
 
@@ -15,18 +13,20 @@ from .engine import DecodeState, Engine, _lens
 bf16, f32 = torch.bfloat16, torch.float32
 
 
-def _aan_layer_fwd(eng, key, x, B, T, tgt_len, tag):
-    """average_attention sublayer in training mode (transformer_aan.py:165-192): returns LN(x + gate(...))."""
+# ------------------------------------------------------------------------------------------------ training forward
+def _aan_sublayer_fwd(eng, key, x, B, T, tgt_len, sv, tag):
+    """average_attention sublayer (transformer_aan.py:165-192): LN(x + sigmoid(i) x + sigmoid(f) y)."""
     c, ps, ws = eng.cfg, eng.ps, eng.ws
     N = B * T
     xf = ws.get(tag + ".xf", (N, c.d))
     ops.prefix_mean_fwd(x.view(B, T, c.d), xf.view(B, T, c.d), tgt_len, mode=0 if c.aan_mask else 1)
-    cat = ws.get(tag + ".cat", (N, 2 * c.d))
+    cat = ws.get(tag + ".cat", (N, 2 * c.d))  # tf.concat([x, y], -1) (transformer_aan.py:185)
     ops.add2d(x, None, cat[:, :c.d])
     if c.use_ffn:
         h = ws.get(tag + ".h", (N, c.f))
         ops.linear_fwd(xf, ps.w(key + ".aan.ffn.w1.W"), ps.p(key + ".aan.ffn.w1.b"), h, relu=True)
         ops.linear_fwd(h, ps.w(key + ".aan.ffn.w2.W"), ps.p(key + ".aan.ffn.w2.b"), cat[:, c.d:])
+        sv["h"] = h
     else:
         ops.add2d(xf, None, cat[:, c.d:])
     y0 = ws.get(tag + ".y0", (N, c.d))
@@ -35,58 +35,146 @@ def _aan_layer_fwd(eng, key, x, B, T, tgt_len, tag):
     ops.linear_fwd(cat, ps.w(key + ".aan.z.W"), ps.p(key + ".aan.z.b"), z)
     yg = ws.get(tag + ".yg", (N, c.d))
     ops.aan_gate_fwd(x, y0, z, yg)
-    x1 = ws.get(tag + ".x1", (N, c.d))
-    ops.add_ln_fwd(x, yg, x1, ps.p(key + ".aan.ln.scale"), ps.p(key + ".aan.ln.offset"), eps=c.eps)
-    return x1
+    sv.update(xf=xf, cat=cat, y0=y0, z=z, yg=yg, ln={})
+    return eng._ln_fwd(key + ".aan.ln", x, yg, N, sv["ln"], tag + ".ln")
+
+
+def _fuse_sublayer_fwd(eng, key, x, enc, B, T, S, src_len, tgt_len, sv, tag):
+    """merged attention (func.py:206-278 with fuse_mask): o_map(cross_attention(x) + prefix_mean(v_map(x)))."""
+    c, ps, ws = eng.cfg, eng.ps, eng.ws
+    N = B * T
+    kc = key + ".cross"
+    q = ws.get(tag + ".q", (N, c.d))
+    ops.linear_fwd(x, ps.w(kc + ".q.W"), ps.p(kc + ".q.b"), q)
+    kv = ws.get(tag + ".kv", (B * S, 2 * c.d))
+    ops.linear_fwd(enc, ps.w(kc + ".kv.W"), ps.p(kc + ".kv.b"), kv)
+    kv3 = kv.view(B, S, 2 * c.d)
+    ctx = ws.get(tag + ".ctx", (N, c.d))
+    lse = ws.get(tag + ".lse", (B, c.h, T), f32)
+    a = ops.attention_args(q.view(B, T, c.d), kv3[:, :, :c.d], kv3[:, :, c.d:], ctx.view(B, T, c.d), c.h,
+                           key_len=src_len, inf_value=c.inf, lse=lse)
+    ops.attention_fwd(a)
+    vq = ws.get(tag + ".vq", (N, c.d))
+    ops.linear_fwd(x, ps.w(kc + ".kv.W")[:, c.d:], ps.p(kc + ".kv.b")[c.d:], vq)  # v_map applied to the query
+    av = ws.get(tag + ".av", (N, c.d))
+    ops.prefix_mean_fwd(vq.view(B, T, c.d), av.view(B, T, c.d), tgt_len, mode=0)
+    osum = ws.get(tag + ".osum", (N, c.d))
+    ops.add2d(ctx, av, osum)
+    yc = ws.get(tag + ".y", (N, c.d))
+    ops.linear_fwd(osum, ps.w(kc + ".o.W"), ps.p(kc + ".o.b"), yc)
+    sv.update(q=q, kv=kv, ctx=ctx, lse=lse, attn=a, osum=osum, ln={})
+    return eng._ln_fwd(kc + ".ln", x, yc, N, sv["ln"], tag + ".ln")
 
 
 def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D"):
     c, ps, ws = self.cfg, self.ps, self.ws
-    if want_grad:
-        raise L.ZeroB200Error("backward pass of %s is not built yet (forward / score / decode are)" % c.model)
     B, T = target.shape
     N = B * T
-    tgt_len = _lens(target)
+    tgt_len = ws.get(tag + ".tgt_len", (B,), torch.int32)
+    tgt_len.copy_(_lens(target))
     x = ws.get(tag + ".x0", (N, c.d))
     ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x, mult=c.d ** 0.5, shift=1)
+    layers = []
     for l in range(c.ndec):
         key, t = "dec%d" % l, "%s.A%d" % (tag, l)
-        sv = {"cross": {}, "ffn": {}, "lnc": {}, "ln2": {}}
+        sv = {"sub": {}, "cross": {}, "ffn": {}, "lnc": {}, "ln2": {}, "x_in": x}
         if c.aan:
-            x1 = _aan_layer_fwd(self, key, x, B, T, tgt_len, t)
+            x1 = _aan_sublayer_fwd(self, key, x, B, T, tgt_len, sv["sub"], t + ".aan")
             yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross")
             xc = self._ln_fwd(key + ".cross.ln", x1, yc, N, sv["lnc"], t + ".lnc")
+            sv["x1"] = x1
         else:
-            # merged attention: o = cross_attention(x) + prefix_mean(v_map(x)), then o_map (func.py:258-278)
-            kc = key + ".cross"
-            q = ws.get(t + ".q", (N, c.d))
-            ops.linear_fwd(x, ps.w(kc + ".q.W"), ps.p(kc + ".q.b"), q)
-            kv = ws.get(t + ".kv", (B * S, 2 * c.d))
-            ops.linear_fwd(enc, ps.w(kc + ".kv.W"), ps.p(kc + ".kv.b"), kv)
-            kv3 = kv.view(B, S, 2 * c.d)
-            ctx = ws.get(t + ".ctx", (N, c.d))
-            a = ops.attention_args(q.view(B, T, c.d), kv3[:, :, :c.d], kv3[:, :, c.d:], ctx.view(B, T, c.d), c.h,
-                                   key_len=src_len, inf_value=c.inf)
-            ops.attention_fwd(a)
-            vq = ws.get(t + ".vq", (N, c.d))
-            ops.linear_fwd(x, ps.w(kc + ".kv.W")[:, c.d:], ps.p(kc + ".kv.b")[c.d:], vq)
-            av = ws.get(t + ".av", (N, c.d))
-            ops.prefix_mean_fwd(vq.view(B, T, c.d), av.view(B, T, c.d), tgt_len, mode=0)
-            ops.add2d(ctx, av, ctx)
-            yc = ws.get(t + ".y", (N, c.d))
-            ops.linear_fwd(ctx, ps.w(kc + ".o.W"), ps.p(kc + ".o.b"), yc)
-            xc = self._ln_fwd(kc + ".ln", x, yc, N, sv["lnc"], t + ".lnc")
+            xc = _fuse_sublayer_fwd(self, key, x, enc, B, T, S, src_len, tgt_len, sv["sub"], t + ".fuse")
         y2 = self._ffn_fwd(key + ".ffn", xc, N, sv["ffn"], t + ".ffn")
         x = self._ln_fwd(key + ".ffn.ln", xc, y2, N, sv["ln2"], t + ".ln2")
+        sv["xc"] = xc
+        layers.append(sv)
+    feat = x
     logits = ws.get(tag + ".logits", (N, c.vt), f32)
-    ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
+    ops.gemm(feat, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
     nll = ws.get(tag + ".nll", (N,), f32)
     per_sample = ws.get(tag + ".per_sample", (B,), f32)
     loss = ws.get(tag + ".loss", (1,), f32)
-    ops.softmax_ce(logits, target, nll, smooth, per_sample=per_sample, loss=loss, loss_scale=c.loss_scale)
+    dlogits = ws.get(tag + ".dlogits", (N, c.vt)) if want_grad else None
+    ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
+                   loss_scale=c.loss_scale)
+    if save is not None:
+        save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
+                    tgt_len=tgt_len)
     return loss, per_sample, logits
 
 
+# ------------------------------------------------------------------------------------------------ training backward
+def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
+    """Backward of the attention part of one aan / fuse decoder layer.  (ds2, dxc) are the two addends of the
+    gradient wrt xc (the input of the feed-forward sublayer).  Returns the two addends of d loss / d x_in."""
+    c, ps, ws = self.cfg, self.ps, self.ws
+    N = B * T
+    tgt_len = save["tgt_len"]
+    sub = sv["sub"]
+    x = sv["x_in"]
+    if c.aan:
+        dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
+        dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"], bw + ".cross")
+        # LN(x + gate): ds is the gradient wrt x (skip) and wrt the gate output
+        ds = self._ln_bwd(key + ".aan.ln", dsc, dx1, N, sub["ln"], bw + ".aln")
+        dxg = ws.get(bw + ".dxg", (N, c.d))
+        dy0 = ws.get(bw + ".dy0", (N, c.d))
+        dz = ws.get(bw + ".dz", (N, 2 * c.d))
+        ops.aan_gate_bwd(x, sub["y0"], sub["z"], ds, dxg, dy0, dz)
+        cat = sub["cat"]
+        self._side(lambda: (ops.linear_wgrad(cat, dz, ps.g(key + ".aan.z.W")), ops.colsum(dz, ps.g(key + ".aan.z.b"))))
+        dcat = ws.get(bw + ".dcat", (N, 2 * c.d))
+        ops.linear_dgrad(dz, ps.w(key + ".aan.z.W"), dcat)
+        ops.add2d(dy0, dcat[:, c.d:], dy0)          # y enters through the gate and through concat([x, y])
+        if c.use_ffn:
+            xf, h = sub["xf"], sub["h"]
+            self._side(lambda: (ops.linear_wgrad(h, dy0, ps.g(key + ".aan.ffn.w2.W")),
+                                ops.colsum(dy0, ps.g(key + ".aan.ffn.w2.b"))))
+            dh = ws.get(bw + ".adh", (N, c.f))
+            ops.linear_dgrad(dy0, ps.w(key + ".aan.ffn.w2.W"), dh, relu_mask=h)
+            self._side(lambda: (ops.linear_wgrad(xf, dh, ps.g(key + ".aan.ffn.w1.W")),
+                                ops.colsum(dh, ps.g(key + ".aan.ffn.w1.b"))))
+            dxf = ws.get(bw + ".dxf", (N, c.d))
+            ops.linear_dgrad(dh, ps.w(key + ".aan.ffn.w1.W"), dxf)
+        else:
+            dxf = dy0
+        dxpm = ws.get(bw + ".dxpm", (N, c.d))
+        ops.prefix_mean_bwd(dxf.view(B, T, c.d), dxpm.view(B, T, c.d), tgt_len, mode=0 if c.aan_mask else 1)
+        t1 = ws.get(bw + ".t1", (N, c.d))
+        ops.add2d(ds, dxg, t1)
+        t2 = ws.get(bw + ".t2", (N, c.d))
+        ops.add2d(dcat[:, :c.d], dxpm, t2)
+        return t1, t2
+    # ---- merged attention
+    kc = key + ".cross"
+    dsc = self._ln_bwd(kc + ".ln", ds2, dxc, N, sub["ln"], bw + ".lnc", ps.g(kc + ".o.b"))
+    osum = sub["osum"]
+    self._side(lambda: ops.linear_wgrad(osum, dsc, ps.g(kc + ".o.W")))
+    do = ws.get(bw + ".do", (N, c.d))
+    ops.linear_dgrad(dsc, ps.w(kc + ".o.W"), do)
+    dq = ws.get(bw + ".dq", (N, c.d))
+    dkv = ws.get(bw + ".dkv", (B * S, 2 * c.d))
+    dkv3 = dkv.view(B, S, 2 * c.d)
+    delta = ws.get(bw + ".delta", (B, c.h, T), f32)
+    ops.attention_bwd(sub["attn"], do.view(B, T, c.d), dq.view(B, T, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:], delta)
+    self._side(lambda: (ops.linear_wgrad(x, dq, ps.g(kc + ".q.W")), ops.colsum(dq, ps.g(kc + ".q.b")),
+                        ops.linear_wgrad(enc, dkv, ps.g(kc + ".kv.W")), ops.colsum(dkv, ps.g(kc + ".kv.b"))))
+    ops.linear_dgrad(dkv, ps.w(kc + ".kv.W"), d_enc_f32, accum=True)
+    dxq = ws.get(bw + ".dxq", (N, c.d))
+    ops.linear_dgrad(dq, ps.w(kc + ".q.W"), dxq)
+    # the averaged branch: aan_o = prefix_mean(v_map(x)); v_map is the second half of the fused kv weights
+    dvq = ws.get(bw + ".dvq", (N, c.d))
+    ops.prefix_mean_bwd(do.view(B, T, c.d), dvq.view(B, T, c.d), tgt_len, mode=0)
+    self._side(lambda: (ops.linear_wgrad(x, dvq, ps.g(kc + ".kv.W")[:, c.d:]),
+                        ops.colsum(dvq, ps.g(kc + ".kv.b")[c.d:])))
+    dxv = ws.get(bw + ".dxv", (N, c.d))
+    ops.linear_dgrad(dvq, ps.w(kc + ".kv.W")[:, c.d:], dxv)
+    ops.add2d(dxq, dxv, dxq)
+    return dsc, dxq
+
+
+# ------------------------------------------------------------------------------------------------ cached decode
 def _decoding_fn_avg(self, target, state, time):
     """Cached decode step of transformer_aan / transformer_fuse: the growing K/V cache of self-attention is
     replaced by one fp32 running sum per layer (transformer_aan.py:110-112; func.py:262-272)."""
@@ -149,6 +237,7 @@ def _decoding_fn_avg(self, target, state, time):
 # ---- DecodeState: running sums instead of K/V caches
 _orig_begin = DecodeState.begin_search
 _orig_reorder = DecodeState.reorder
+_orig_swap = DecodeState.swap_buffers
 
 
 def _begin_search(self, beam, cap=None):
@@ -160,9 +249,6 @@ def _begin_search(self, beam, cap=None):
         self.sums_alt = [eng.ws.get("dec.sumB%d" % l, (R, c.d), f32) for l in range(c.ndec)]
         for s in self.sums:
             s.zero_()
-
-
-_orig_swap = DecodeState.swap_buffers
 
 
 def _swap_buffers(self):
@@ -187,4 +273,5 @@ DecodeState.begin_search = _begin_search
 DecodeState.swap_buffers = _swap_buffers
 DecodeState.reorder = _reorder
 Engine._decode_train_avg = _decode_train_avg
+Engine._avg_layer_bwd = _avg_layer_bwd
 Engine._decoding_fn_avg = _decoding_fn_avg
