@@ -199,13 +199,16 @@ def gemm_roofline(eng, src, tgt, peaks):
         calls.append(lambda: real(a, b, out, a_layout, b_layout, **kw))
         return real(a, b, out, a_layout, b_layout, **kw)
 
+    from zero_b200 import lib as L
     side = getattr(eng, "side", None)
     eng.side = None  # record the launches in program order on one stream
     ops.gemm = recording
+    c0 = L.launch_count()
     try:
         eng.forward_backward(src, tgt, compact=False)
         torch.cuda.synchronize()
     finally:
+        step_launches = L.launch_count() - c0  # every kernel of one eager fwd+bwd (graph replays bypass the counter)
         ops.gemm = real
         eng.side = side
     g = torch.cuda.CUDAGraph()
@@ -227,6 +230,7 @@ def gemm_roofline(eng, src, tgt, peaks):
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": None, "kernel": "gemm_bf16_tcgen05", "launches_per_step": len(calls),
+            "step_launches": step_launches,
             "gemm_ms_per_step": ms, "avg_launch_us": 1000.0 * ms / max(len(calls), 1),
             "gemm_flops_per_step": flops[0],
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
@@ -312,9 +316,8 @@ def run_ours(args):
     except Exception:
         pass
     # kernel launches per step: graph replays do not pass through the ABI counter, so count one eager step
-    c0 = L.launch_count()
     roof = gemm_roofline(eng, *devb[0], peaks)
-    per_step_kernels = L.launch_count() - c0 + 3  # + 2 sumsq + adam outside forward_backward
+    per_step_kernels = roof.pop("step_launches") + 1  # + the fused Adam/norm kernel outside forward_backward
     value = tokens_per_step * world * args.steps / (ms * 1e-3)
     e2e = tokens_per_step * world * args.steps / (ms2 * 1e-3)
     model_flops = 369623040.0 * tokens_per_step  # fwd+bwd FLOPs per (src,tgt) token pair
