@@ -19,6 +19,7 @@
 namespace zb {
 
 int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);
+int make_map_f32(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);
 
 struct Gemm2Params {
   int M, N, K;
@@ -32,6 +33,7 @@ struct Gemm2Params {
   float alpha;
   int flags;
   int d_f32;
+  int d_tma;  // output written through shared memory + TMA tile stores (full 128 B lines): 1 = bf16, 2 = fp32
 };
 
 constexpr int k2BK = 64;
@@ -42,10 +44,11 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = 128 * k2BK * 2;        // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * k2BK * 2;   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = 8 * 4096;  // one 32-row x 128 B (64 bf16) staging tile per epilogue warp
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -145,12 +148,13 @@ __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                   const Gemm2Params p) {
+                   const __grid_constant__ CUtensorMap tma_d, const Gemm2Params p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -166,6 +170,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.d_tma) tma_prefetch_desc(&tma_d);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's producer arms it; both CTAs' TMA bytes are credited to the leader's
       mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
@@ -270,11 +275,28 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const int flags = p.flags;
     const float alpha = p.alpha;
     const bool d_f32 = p.d_f32 != 0;
+    const bool d_tma = p.d_tma != 0;
+    const bool tma_f32 = p.d_tma == 2;  // fp32: one 32-column chunk (128 B per row) per tile store
+    uint8_t* stg = epi_smem + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
 
-    auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4]) {
-      if (col0 >= p.N) return;
+    // TMA mode: chunk pairs (64 columns) are staged as a 32-row x 128 B tile in the 128B-swizzle layout (16 B unit u
+    // of row r lives at unit u ^ (r & 7): conflict-free for row-per-lane writes) and written with one bulk tile store
+    auto issue_store = [&](int row0, int col_even) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tma_d, stg, col_even, row0);
+        bulk_commit_group();
+      }
+    };
+    auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4],
+                            int cpar) {
+      if (col0 >= p.N) {
+        if (d_tma && !tma_f32 && cpar == 1 && col0 - 32 < p.N) issue_store(row - lane, col0 - 32);
+        return;
+      }
       const bool full_cols = (col0 + 32 <= p.N);
       float v[32];
 #pragma unroll
@@ -288,8 +310,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (!row_ok) return;
-      if (flags & ZB_EPI_RELU_MASK) {
+      if (!row_ok && !d_tma) return;
+      if ((flags & ZB_EPI_RELU_MASK) && row_ok) {
         if (full_cols) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -308,7 +330,32 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) v[j] = 0.f;
         }
       }
-      if (d_f32) {
+      if (tma_f32) {
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+        uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
+              make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        issue_store(row - lane, col0);
+      } else if (d_tma) {
+        if (cpar == 0) {  // the previous tile store must have drained the staging buffer
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
+        }
+        uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+          o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+          o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+          o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(rowp + (((cpar * 4 + q) ^ (lane & 7)) << 4)) = o;
+        }
+        if (cpar == 1) issue_store(row - lane, col0 - 32);
+      } else if (d_f32) {
         float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
         if (flags & ZB_EPI_ACCUM) {
           if (full_cols) {
@@ -384,7 +431,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
           prefetch_chunk(row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
         }
-        finish_chunk(ra, row, row_ok, n0 + (c0 + c) * 32, bias_a, mk_a);
+        finish_chunk(ra, row, row_ok, n0 + (c0 + c) * 32, bias_a, mk_a, 0);
         if (c + 1 < NCH) {
           __syncwarp();
           tmem_ld_wait();
@@ -392,7 +439,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
             prefetch_chunk(row, row_ok, n0 + (c0 + c + 2) * 32, bias_a, mk_a);
           }
-          finish_chunk(rb, row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
+          finish_chunk(rb, row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b, 1);
         }
       }
       tc_fence_before();
@@ -403,6 +450,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         acc_phase ^= 1;
       }
     }
+    if (d_tma && lane == 0) bulk_wait_all();  // the tile stores of this warp have landed before the CTA exits
   }
 
   tc_fence_before();
@@ -414,7 +462,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, int grid, cudaStream_t st) {
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const Gemm2Params& p, int grid,
+                   cudaStream_t st) {
   auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -439,7 +488,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Para
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p);
   if (le != cudaSuccess) {
     set_error("zb_gemm (cta pair) launch: %s", cudaGetErrorString(le));
     return ZB_ECUDA;
@@ -448,12 +497,12 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Para
 }
 
 template <int BN>
-static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, int grid,
-                     cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, p, grid, st);
-  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, p, grid, st);
-  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, p, grid, st);
-  return launch2<BN, true, true>(ta, tb, p, grid, st);
+static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
+                     const Gemm2Params& p, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, td, p, grid, st);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, td, p, grid, st);
+  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, td, p, grid, st);
+  return launch2<BN, true, true>(ta, tb, td, p, grid, st);
 }
 
 // Whether the CTA-pair kernel should take this problem.  ZB_GEMM2=0 disables it, ZB_GEMM2=1 forces it whenever legal.
@@ -525,10 +574,25 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   if (!b_mn) rc = make_map(&tb, a->b, p.K, p.N, a->ldb, bn / 2);
   else rc = make_map(&tb, a->b, p.N, p.K, a->ldb, k2BK);
   if (rc) return rc;
+  // bf16 overwrite outputs with 16 B-aligned rows go through shared memory + TMA tile stores
+  static const char* no_tma_d = getenv("ZB_GEMM_NO_TMA_STORE");
+  CUtensorMap td = ta;
+  p.d_tma = 0;
+  if (!accum && !no_tma_d && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0) {
+    if (!p.d_f32 && (a->ldd * 2) % 16 == 0) {
+      rc = make_map(&td, a->d, p.N, p.M, a->ldd, 32);
+      if (rc) return rc;
+      p.d_tma = 1;
+    } else if (p.d_f32 && (a->ldd * 4) % 16 == 0) {
+      rc = make_map_f32(&td, a->d, p.N, p.M, a->ldd, 32);
+      if (rc) return rc;
+      p.d_tma = 2;
+    }
+  }
   const long long total = tiles * p.splits;
   const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
-  if (bn == 128) return dispatch2<128>(a_mn, b_mn, ta, tb, p, grid, st);
-  return dispatch2<256>(a_mn, b_mn, ta, tb, p, grid, st);
+  if (bn == 128) return dispatch2<128>(a_mn, b_mn, ta, tb, td, p, grid, st);
+  return dispatch2<256>(a_mn, b_mn, ta, tb, td, p, grid, st);
 }
 
 }  // namespace zb

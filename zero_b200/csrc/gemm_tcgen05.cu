@@ -402,6 +402,28 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint
   return ZB_OK;
 }
 
+// fp32 output tiles for the epilogue's TMA stores: box {32 floats = 128 B, box1 rows}, 128B swizzle
+int make_map_f32(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return ZB_ECUDA;
+  }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32) failed (%d): dims %llu x %llu ld %llu", (int)r, (unsigned long long)dim0,
+              (unsigned long long)dim1, (unsigned long long)ld);
+    return ZB_ECUDA;
+  }
+  return ZB_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int grid, cudaStream_t st) {
   auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzero_b200.so")
+# ZB_LIB_PATH: load a differently-built copy of the same library (A/B experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("ZB_LIB_PATH") or os.path.join(_HERE, "libzero_b200.so")
 
 ZB_BF16, ZB_F32 = 0, 1
 ZB_K_MAJOR, ZB_MN_MAJOR = 0, 1
