@@ -392,31 +392,22 @@ struct Tile64Bwd {
   float lse[64];
 };
 
-__global__ void __launch_bounds__(NT) fwd64_kernel(const Params p, const int items) {
+// These kernels are latency-bound per warp (ncu: 2 warps / scheduler, 26 % issue slots used), so they are sized for
+// residency rather than prefetch: one tile set per CTA (24 / 41 KB), <= 128 registers, 4 CTAs per SM; at batch 64 x 8
+// heads every (batch, head) item of the step is resident at once.
+__global__ void __launch_bounds__(NT, 4) fwd64_kernel(const Params p, const int items) {
   grid_dep_wait();
   extern __shared__ __align__(128) uint8_t smem64[];
-  Tile64Fwd* bufs = reinterpret_cast<Tile64Fwd*>(smem64);
+  Tile64Fwd& T = *reinterpret_cast<Tile64Fwd*>(smem64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  auto issue = [&](int item, int buf) {
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / p.heads, h = item % p.heads;
-    load_tile(bufs[buf].q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
-    load_tile(bufs[buf].k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
-    load_tile(bufs[buf].v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
+    load_tile(T.q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
+    load_tile(T.k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
+    load_tile(T.v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
     cp_async_commit();
-  };
-  int item = blockIdx.x;
-  if (item < items) issue(item, 0);
-  for (int buf = 0; item < items; item += gridDim.x, buf ^= 1) {
-    const int next = item + gridDim.x;
-    if (next < items) {
-      issue(next, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    cp_async_wait<0>();
     __syncthreads();
-    const Tile64Fwd& T = bufs[buf];
-    const int b = item / p.heads, h = item % p.heads;
     const int kl = p.key_len ? p.key_len[b] : p.lk;
     uint32_t qa[4][4];
     load_a_frags(qa, T.q, warp * 16);
@@ -463,47 +454,35 @@ __global__ void __launch_bounds__(NT) fwd64_kernel(const Params p, const int ite
       if (r0 < p.lq) lp[r0] = m0 + __logf(l0);
       if (r0 + 8 < p.lq) lp[r0 + 8] = m1 + __logf(l1);
     }
-    __syncthreads();  // everyone is done with bufs[buf] before the next iteration's prefetch overwrites it
+    __syncthreads();  // everyone is done with the tiles before the next item's loads overwrite them
   }
 }
 
-__global__ void __launch_bounds__(NT) bwd64_kernel(const Params p, const int items) {
+__global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int items) {
   grid_dep_wait();
   extern __shared__ __align__(128) uint8_t smem64[];
-  Tile64Bwd* bufs = reinterpret_cast<Tile64Bwd*>(smem64);
+  Tile64Bwd& T = *reinterpret_cast<Tile64Bwd*>(smem64);
   __shared__ float sDelta[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  auto issue = [&](int item, int buf) {
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / p.heads, h = item % p.heads;
-    load_tile(bufs[buf].q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
-    load_tile(bufs[buf].k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
-    load_tile(bufs[buf].v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
-    load_tile(bufs[buf].d_o, p.d_o + (long long)b * p.bsdo + h * DH, p.lddo, p.lq);
-    load_tile(bufs[buf].o, p.o + (long long)b * p.bso + h * DH, p.ldo, p.lq);
+    load_tile(T.q, p.q + (long long)b * p.bsq + h * DH, p.ldq, p.lq);
+    load_tile(T.k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
+    load_tile(T.v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
+    load_tile(T.d_o, p.d_o + (long long)b * p.bsdo + h * DH, p.lddo, p.lq);
+    load_tile(T.o, p.o + (long long)b * p.bso + h * DH, p.ldo, p.lq);
     if (threadIdx.x < 16) {  // 64 fp32 log-sum-exps (lq may be < 64: rows beyond lq read as 0 through the predicate)
       const int r = threadIdx.x * 4;
       const float* src = p.lse + ((long long)b * p.heads + h) * p.lq + r;
       if (r + 3 < p.lq && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        cp_async16(&bufs[buf].lse[r], src, true);
+        cp_async16(&T.lse[r], src, true);
       } else {
-        for (int e = 0; e < 4; ++e) bufs[buf].lse[r + e] = (r + e < p.lq) ? src[e] : 0.f;
+        for (int e = 0; e < 4; ++e) T.lse[r + e] = (r + e < p.lq) ? src[e] : 0.f;
       }
     }
     cp_async_commit();
-  };
-  int item = blockIdx.x;
-  if (item < items) issue(item, 0);
-  for (int buf = 0; item < items; item += gridDim.x, buf ^= 1) {
-    const int next = item + gridDim.x;
-    if (next < items) {
-      issue(next, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    cp_async_wait<0>();
     __syncthreads();
-    const Tile64Bwd& T = bufs[buf];
-    const int b = item / p.heads, h = item % p.heads;
     const int kl = p.key_len ? p.key_len[b] : p.lk;
     // ---- delta = rowsum(dO * O) for this warp's 16 query rows -> shared (every warp needs all 64 below)
     uint32_t doa[4][4];
@@ -598,7 +577,7 @@ __global__ void __launch_bounds__(NT) bwd64_kernel(const Params p, const int ite
       store_c_bf16(p.dk + (long long)b * p.bsdk + h * DH, p.lddk, warp * 16, p.lk, dk, p.scale, p.scale);
       store_c_bf16(p.dv + (long long)b * p.bsdv + h * DH, p.lddv, warp * 16, p.lk, dv, 1.f, 1.f);
     }
-    __syncthreads();  // bufs[buf] and sDelta are free again
+    __syncthreads();  // the tiles and sDelta are free again
   }
 }
 
@@ -646,13 +625,13 @@ int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
-    const int smem = 2 * (int)sizeof(fa::Tile64Fwd);
+    const int smem = (int)sizeof(fa::Tile64Fwd);
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(fa::fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       attr = true;
     }
-    const int grid = items < 3 * num_sms() ? items : 3 * num_sms();
+    const int grid = items < 8 * num_sms() ? items : 8 * num_sms();
     ZB_LAUNCH(fa::fwd64_kernel, grid, fa::NT, smem, st, p, items);
     return check_launch("zb_attention_fwd(tile64)");
   }
@@ -665,13 +644,13 @@ int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
-    const int smem = 2 * (int)sizeof(fa::Tile64Bwd);
+    const int smem = (int)sizeof(fa::Tile64Bwd);
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(fa::bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       attr = true;
     }
-    const int grid = items < 2 * num_sms() ? items : 2 * num_sms();
+    const int grid = items < 4 * num_sms() ? items : 4 * num_sms();
     ZB_LAUNCH(fa::bwd64_kernel, grid, fa::NT, smem, st, p, items);
     return check_launch("zb_attention_bwd(tile64)");
   }

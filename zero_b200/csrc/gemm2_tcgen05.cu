@@ -33,7 +33,8 @@ struct Gemm2Params {
   float alpha;
   int flags;
   int d_f32;
-  int d_tma;  // output written through shared memory + TMA tile stores (full 128 B lines): 1 = bf16, 2 = fp32
+  int d_tma;  // output written through shared memory + TMA tile stores (full 128 B lines): 1 = bf16, 2 = fp32,
+              // 3 = fp32 bulk reduce-add
 };
 
 constexpr int k2BK = 64;
@@ -276,7 +277,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     const float alpha = p.alpha;
     const bool d_f32 = p.d_f32 != 0;
     const bool d_tma = p.d_tma != 0;
-    const bool tma_f32 = p.d_tma == 2;  // fp32: one 32-column chunk (128 B per row) per tile store
+    const bool tma_f32 = p.d_tma >= 2;  // fp32: one 32-column chunk (128 B per row) per tile store
+    const bool tma_red = p.d_tma == 3;  // ... as a bulk reduce-add (split-K / gradient accumulation)
     uint8_t* stg = epi_smem + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -287,7 +289,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&tma_d, stg, col_even, row0);
+        if (tma_red) tma_reduce_add_2d(&tma_d, stg, col_even, row0);
+        else tma_store_2d(&tma_d, stg, col_even, row0);
         bulk_commit_group();
       }
     };
@@ -578,6 +581,13 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   static const char* no_tma_d = getenv("ZB_GEMM_NO_TMA_STORE");
   CUtensorMap td = ta;
   p.d_tma = 0;
+  static const char* no_tma_red = getenv("ZB_GEMM_NO_TMA_REDUCE");
+  if (accum && p.d_f32 && !no_tma_d && !no_tma_red && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
+      (a->ldd * 4) % 16 == 0) {
+    rc = make_map_f32(&td, a->d, p.N, p.M, a->ldd, 32);
+    if (rc) return rc;
+    p.d_tma = 3;
+  }
   if (!accum && !no_tma_d && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0) {
     if (!p.d_f32 && (a->ldd * 2) % 16 == 0) {
       rc = make_map(&td, a->d, p.N, p.M, a->ldd, 32);
