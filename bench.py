@@ -188,7 +188,7 @@ def gemm_roofline(eng, src, tgt, peaks):
     number — and timed with CUDA events on the launching stream: achieved = algorithmic GEMM FLOPs / that time."""
     import torch
     from zero_b200 import ops
-    calls, flops = [], [0.0]
+    calls, flops, nsingle = [], [0.0], [0]
     real = ops.gemm
 
     def recording(a, b, out, a_layout=0, b_layout=1, **kw):
@@ -196,13 +196,25 @@ def gemm_roofline(eng, src, tgt, peaks):
         K = kw.get("k") or (a.shape[1] if a_layout == 0 else a.shape[0])
         N = kw.get("n") or (b.shape[0] if b_layout == 0 else b.shape[1])
         flops[0] += 2.0 * M * N * K
+        nsingle[0] += 1
         calls.append(lambda: real(a, b, out, a_layout, b_layout, **kw))
         return real(a, b, out, a_layout, b_layout, **kw)
 
+    real_grouped = ops.gemm_grouped
+
+    def recording_grouped(problems):
+        for g in problems:
+            flops[0] += 2.0 * g.m * g.n * g.k
+        calls.append(lambda: real_grouped(problems))
+        nprob[0] += len(problems)
+        return real_grouped(problems)
+
+    nprob = [0]
     from zero_b200 import lib as L
     side = getattr(eng, "side", None)
     eng.side = None  # record the launches in program order on one stream
     ops.gemm = recording
+    ops.gemm_grouped = recording_grouped
     c0 = L.launch_count()
     try:
         eng.forward_backward(src, tgt, compact=False)
@@ -210,6 +222,7 @@ def gemm_roofline(eng, src, tgt, peaks):
     finally:
         step_launches = L.launch_count() - c0  # every kernel of one eager fwd+bwd (graph replays bypass the counter)
         ops.gemm = real
+        ops.gemm_grouped = real_grouped
         eng.side = side
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -229,7 +242,8 @@ def gemm_roofline(eng, src, tgt, peaks):
     achieved = flops[0] / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gemm_bf16_tcgen05", "launches_per_step": len(calls),
+            "traffic": None, "kernel": "gemm2_bf16_tcgen05", "launches_per_step": len(calls),
+            "gemm_problems_per_step": nsingle[0] + nprob[0],
             "step_launches": step_launches,
             "gemm_ms_per_step": ms, "avg_launch_us": 1000.0 * ms / max(len(calls), 1),
             "gemm_flops_per_step": flops[0],

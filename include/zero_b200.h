@@ -75,6 +75,11 @@ typedef struct {
   int32_t split_k;     /* 0 = choose; >1 requires ZB_EPI_ACCUM */
 } zb_gemm_args;
 int zb_gemm(const zb_gemm_args* a, zb_stream_t stream);
+/* zb_gemm_grouped: `count` independent zb_gemm problems (non-overlapping outputs), same results as `count` zb_gemm
+ * calls.  The weight gradients of one layer (dW += x^T dy for every func.linear of the layer, i.e. what
+ * optimizer.compute_gradients emits per variable, main.py:33-37) are all MN-major / accumulate-into-fp32 and share
+ * ONE persistent launch; anything else falls back to per-problem launches. */
+int zb_gemm_grouped(const zb_gemm_args* problems, int32_t count, zb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ K2/K3
  * zb_attention_{fwd,bwd}: fused scaled-dot attention softmax(q k^T * scale + mask) v per (batch, head).
@@ -181,6 +186,13 @@ int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream);
 /* ------------------------------------------------------------------------------------------------ misc
  * zb_colsum: out[n] += sum_m x[m,n] (bias gradients; tf.nn.bias_add grad).  x bf16, out fp32. */
 int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream);
+/* zb_colsum_grouped: up to 8 column sums (the bias gradients of one layer) in one launch. */
+typedef struct {
+  const void* x;       /* bf16 [m, ld] */
+  int64_t m, n, ld;
+  float* out;          /* [n] fp32, accumulated into */
+} zb_colsum_args;
+int zb_colsum_grouped(const zb_colsum_args* problems, int32_t count, zb_stream_t stream);
 /* zb_cast_f32_bf16: bf16 compute copies of the fp32 master weights (utils/dtype.py:55-69). */
 int zb_cast_f32_bf16(const float* src, void* dst, int64_t n, zb_stream_t stream);
 int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_stream_t stream);

@@ -64,6 +64,38 @@ def test_gemm_epilogues_and_splitk():
     torch.testing.assert_close(dh.float(), ref2, atol=0.15, rtol=2e-2)
 
 
+@pytest.mark.parametrize("tokens", [4096, 1000])
+def test_gemm_grouped_and_colsum_grouped(tokens):
+    """The weight gradients + bias gradients of one decoder layer through the grouped entry points (one launch
+    each) equal the fp32 reference and the per-problem launches; a group that does not qualify (small / bf16
+    problems mixed in) falls back to per-problem launches with the same results."""
+    from zero_b200 import ops
+    shapes = [(512, 1536), (512, 512), (512, 512), (512, 1024), (512, 512), (512, 2048), (2048, 512)]
+    xs = [rnd(tokens, i, seed=10 + j) for j, (i, o) in enumerate(shapes)]
+    dys = [rnd(tokens, o, seed=30 + j) for j, (i, o) in enumerate(shapes)]
+    accs = [torch.randn(i, o, device=dev()) for i, o in shapes]
+    want = [a + x.float().t() @ dy.float() for a, x, dy in zip(accs, xs, dys)]
+    single = [a.clone() for a in accs]
+    for s, x, dy in zip(single, xs, dys):
+        ops.linear_wgrad(x, dy, s)
+    ops.gemm_grouped([ops.wgrad_args(x, dy, a) for x, dy, a in zip(xs, dys, accs)])
+    for got, one, ref in zip(accs, single, want):
+        torch.testing.assert_close(got, ref, atol=3e-2, rtol=3e-3)
+        torch.testing.assert_close(got, one, atol=3e-2, rtol=3e-3)
+    # bias gradients
+    dbs = [torch.randn(o, device=dev()) for _, o in shapes]
+    want_b = [b + dy.float().sum(0) for b, dy in zip(dbs, dys)]
+    ops.colsum_grouped(list(zip(dys, dbs)))
+    for got, ref in zip(dbs, want_b):
+        torch.testing.assert_close(got, ref, atol=5e-2, rtol=3e-3)
+    # non-qualifying group (a 64-wide problem): per-problem fallback, same numbers
+    x2, dy2 = rnd(tokens, 64, seed=77), rnd(tokens, 72, seed=78)
+    a2, a3 = torch.zeros(64, 72, device=dev()), torch.zeros(512, 1536, device=dev())
+    ops.gemm_grouped([ops.wgrad_args(x2, dy2, a2), ops.wgrad_args(xs[0], dys[0], a3)])
+    torch.testing.assert_close(a2, x2.float().t() @ dy2.float(), atol=3e-2, rtol=3e-3)
+    torch.testing.assert_close(a3, xs[0].float().t() @ dys[0].float(), atol=3e-2, rtol=3e-3)
+
+
 # ------------------------------------------------------------------------------------------------ add + LN
 @pytest.mark.parametrize("rows,cols", [(37, 64), (4096, 512), (100, 1024)])
 def test_add_ln_fwd_bwd(rows, cols):

@@ -63,14 +63,13 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long n, lon
 
 // Vectorised variant for n % 8 == 0: a warp reads 512 contiguous bytes of one row (32 x 16 B), 8 row lanes per
 // block, 4 rows in flight per thread; block-level reduction, one atomic per column per block.
-__global__ void __launch_bounds__(256)
-colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long nvec, long long ld,
-                  float* __restrict__ out, long long rows_per_block) {
-  grid_dep_wait();
+__device__ __forceinline__ void colsum_vec_body(const __nv_bfloat16* __restrict__ x, long long m, long long nvec,
+                                                long long ld, float* __restrict__ out, long long rows_per_block,
+                                                unsigned bx, unsigned by) {
   __shared__ float red[8][32][9];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const long long vc = (long long)blockIdx.x * 32 + lane;
-  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long vc = (long long)bx * 32 + lane;
+  const long long r0 = (long long)by * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > m) r1 = m;
   float acc[8];
@@ -114,6 +113,27 @@ colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long nv
   for (int w = 0; w < 8; ++w) t += red[w][c >> 3][c & 7];
   const long long col = (long long)blockIdx.x * 256 + c;
   if (col < nvec * 8) atomicAdd(out + col, t);
+}
+
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const __nv_bfloat16* __restrict__ x, long long m, long long nvec, long long ld,
+                  float* __restrict__ out, long long rows_per_block) {
+  grid_dep_wait();
+  colsum_vec_body(x, m, nvec, ld, out, rows_per_block, blockIdx.x, blockIdx.y);
+}
+
+// Several column sums in one launch (blockIdx.z = problem; blocks outside a problem's own grid exit at once).
+struct ColsumGroup {
+  const __nv_bfloat16* x[8];
+  float* out[8];
+  long long m[8], nvec[8], ld[8], rows_pb[8];
+  unsigned bx[8], by[8];
+};
+__global__ void __launch_bounds__(256) colsum_vec_group_kernel(const ColsumGroup g) {
+  grid_dep_wait();
+  const int z = blockIdx.z;
+  if (blockIdx.x >= g.bx[z] || blockIdx.y >= g.by[z]) return;
+  colsum_vec_body(g.x[z], g.m[z], g.nvec[z], g.ld[z], g.out[z], g.rows_pb[z], blockIdx.x, blockIdx.y);
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
@@ -327,6 +347,51 @@ extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float*
   const long long rpb = (m + gy - 1) / gy;
   ZB_LAUNCH(colsum_kernel, dim3(gx, (unsigned)gy), 256, 0, ST(stream), (const __nv_bfloat16*)x, m, n, ld, out, rpb);
   return check_launch("zb_colsum");
+}
+extern "C" int zb_colsum_grouped(const zb_colsum_args* problems, int32_t count, zb_stream_t stream) {
+  ZB_REQUIRE(count >= 0 && (count == 0 || problems), "zb_colsum_grouped: null pointer");
+  int done = 0;
+  while (done < count) {
+    int n = count - done < 8 ? count - done : 8;
+    bool vec = n > 1;
+    for (int i = 0; i < n && vec; ++i) {
+      const zb_colsum_args& a = problems[done + i];
+      vec = a.x && a.out && a.m > 0 && a.n > 0 && a.n % 8 == 0 && a.ld % 8 == 0 &&
+            (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    }
+    if (!vec) {
+      for (int i = 0; i < n; ++i) {
+        const zb_colsum_args& a = problems[done + i];
+        int rc = zb_colsum(a.x, a.m, a.n, a.ld, a.out, stream);
+        if (rc) return rc;
+      }
+    } else {
+      ColsumGroup g;
+      unsigned gx = 1, gy = 1;
+      for (int i = 0; i < n; ++i) {
+        const zb_colsum_args& a = problems[done + i];
+        const unsigned bx = (unsigned)((a.n / 8 + 31) / 32);
+        long long by = (4ll * num_sms() / n + bx - 1) / bx;  // the group shares the machine
+        if (by > (a.m + 31) / 32) by = (a.m + 31) / 32;
+        if (by < 1) by = 1;
+        const long long rows_pb = ((a.m + by - 1) / by + 7) / 8 * 8;
+        by = (a.m + rows_pb - 1) / rows_pb;
+        g.x[i] = (const __nv_bfloat16*)a.x; g.out[i] = a.out; g.m[i] = a.m; g.nvec[i] = a.n / 8; g.ld[i] = a.ld;
+        g.rows_pb[i] = rows_pb; g.bx[i] = bx; g.by[i] = (unsigned)by;
+        gx = bx > gx ? bx : gx;
+        gy = (unsigned)by > gy ? (unsigned)by : gy;
+      }
+      for (int i = n; i < 8; ++i) {
+        g.x[i] = g.x[0]; g.out[i] = g.out[0]; g.m[i] = 0; g.nvec[i] = 0; g.ld[i] = 0; g.rows_pb[i] = 8;
+        g.bx[i] = 0; g.by[i] = 0;
+      }
+      ZB_LAUNCH(colsum_vec_group_kernel, dim3(gx, gy, (unsigned)n), 256, 0, ST(stream), g);
+      int rc = check_launch("zb_colsum_grouped");
+      if (rc) return rc;
+    }
+    done += n;
+  }
+  return ZB_OK;
 }
 extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream) {
   ZB_REQUIRE(x && out && n >= 0, "zb_sumsq: bad args");

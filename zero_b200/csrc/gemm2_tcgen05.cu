@@ -33,9 +33,20 @@ struct Gemm2Params {
   float alpha;
   int flags;
   int d_f32;
+  int tile_begin;  // first work unit of this problem in the launch (grouped launches)
   int d_tma;  // output written through shared memory + TMA tile stores (full 128 B lines): 1 = bf16, 2 = fp32,
               // 3 = fp32 bulk reduce-add
 };
+
+// One launch may carry several independent problems of the same operand layouts (the weight-gradient GEMMs of a
+// layer): work units are numbered across the problems and dealt round-robin to the CTA pairs.
+template <int NP>
+struct Gemm2Group {
+  CUtensorMap maps[3 * NP];  // a, b, d of each problem
+  Gemm2Params prob[NP];
+  int count, total_tiles;
+};
+constexpr int k2MaxGroup = 8;
 
 constexpr int k2BK = 64;
 constexpr int k2Threads = 320;
@@ -146,10 +157,18 @@ __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float
                : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int NP>
+__device__ __forceinline__ int find_problem(const Gemm2Group<NP>& G, int tile) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < NP; ++i)
+    if (i < G.count && tile >= G.prob[i].tile_begin) pi = i;
+  return pi;
+}
+
+template <int BN, bool A_MN, bool B_MN, int NP>
 __global__ void __launch_bounds__(k2Threads, 1)
-gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                   const __grid_constant__ CUtensorMap tma_d, const Gemm2Params p) {
+gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -165,13 +184,11 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader
   const bool leader = rank == 0;
-  const int num_tiles = p.mt * p.nt * p.splits;
+  const int num_tiles = G.total_tiles;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
+  if (warp == 0 && lane < 3 * NP && lane < 3 * G.count) tma_prefetch_desc(&G.maps[lane]);
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    if (p.d_tma) tma_prefetch_desc(&tma_d);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's producer arms it; both CTAs' TMA bytes are credited to the leader's
       mbar_init(&empty_bar[s], 1);  // one multicast commit per phase
@@ -195,8 +212,12 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int pi = find_problem<NP>(G, tile);
+        const Gemm2Params& p = G.prob[pi];
+        const CUtensorMap* tma_a = &G.maps[3 * pi];
+        const CUtensorMap* tma_b = &G.maps[3 * pi + 1];
         int m_blk, n_blk, ks;
-        tile2_coords(p, tile, m_blk, n_blk, ks);
+        tile2_coords(p, tile - p.tile_begin, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * 256 + (int)rank * 128;       // this CTA's rows of A
@@ -208,17 +229,17 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const int k0 = kb * k2BK;
           if constexpr (!A_MN) {
-            tma_load_2d_2sm(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+            tma_load_2d_2sm(sa, tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
           } else {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * 8192, &tma_a, &full_bar[stage], m0 + 64 * c, k0);
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * 8192, tma_a, &full_bar[stage], m0 + 64 * c, k0);
           }
           if constexpr (!B_MN) {
-            tma_load_2d_2sm(sb, &tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN/2 n}
+            tma_load_2d_2sm(sb, tma_b, &full_bar[stage], k0, n0);  // box {64 k, BN/2 n}
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 128; ++c)
-              tma_load_2d_2sm(sb + c * 8192, &tma_b, &full_bar[stage], n0 + 64 * c, k0);
+              tma_load_2d_2sm(sb + c * 8192, tma_b, &full_bar[stage], n0 + 64 * c, k0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -238,8 +259,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const Gemm2Params& p = G.prob[find_problem<NP>(G, tile)];
         int m_blk, n_blk, ks;
-        tile2_coords(p, tile, m_blk, n_blk, ks);
+        tile2_coords(p, tile - p.tile_begin, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait_cluster(&tempty_bar[acc], acc_phase ^ 1);
@@ -273,24 +295,30 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
+    uint8_t* stg = epi_smem + (warp - 2) * 4096;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    const uint32_t leader_tempty0 = mapa_u32(&tempty_bar[0], 0), leader_tempty1 = mapa_u32(&tempty_bar[1], 0);
+
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int pi = find_problem<NP>(G, tile);
+      const Gemm2Params& p = G.prob[pi];
+      const CUtensorMap* tma_d = &G.maps[3 * pi + 2];
     const int flags = p.flags;
     const float alpha = p.alpha;
     const bool d_f32 = p.d_f32 != 0;
     const bool d_tma = p.d_tma != 0;
     const bool tma_f32 = p.d_tma >= 2;  // fp32: one 32-column chunk (128 B per row) per tile store
     const bool tma_red = p.d_tma == 3;  // ... as a bulk reduce-add (split-K / gradient accumulation)
-    uint8_t* stg = epi_smem + (warp - 2) * 4096;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-
     // TMA mode: chunk pairs (64 columns) are staged as a 32-row x 128 B tile in the 128B-swizzle layout (16 B unit u
     // of row r lives at unit u ^ (r & 7): conflict-free for row-per-lane writes) and written with one bulk tile store
     auto issue_store = [&](int row0, int col_even) {
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        if (tma_red) tma_reduce_add_2d(&tma_d, stg, col_even, row0);
-        else tma_store_2d(&tma_d, stg, col_even, row0);
+        if (tma_red) tma_reduce_add_2d(tma_d, stg, col_even, row0);
+        else tma_store_2d(tma_d, stg, col_even, row0);
         bulk_commit_group();
       }
     };
@@ -408,11 +436,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int q = 0; q < 4; ++q) mk[q] = __ldg(mrow + q);
       }
     };
-    const uint32_t leader_tempty0 = mapa_u32(&tempty_bar[0], 0), leader_tempty1 = mapa_u32(&tempty_bar[1], 0);
-
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk, ks;
-      tile2_coords(p, tile, m_blk, n_blk, ks);
+      tile2_coords(p, tile - p.tile_begin, m_blk, n_blk, ks);
       const int m0 = m_blk * 256 + (int)rank * 128, n0 = n_blk * BN;
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
@@ -453,7 +478,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         acc_phase ^= 1;
       }
     }
-    if (d_tma && lane == 0) bulk_wait_all();  // the tile stores of this warp have landed before the CTA exits
+    if (lane == 0) bulk_wait_all();  // the tile stores of this warp have landed before the CTA exits
   }
 
   tc_fence_before();
@@ -464,10 +489,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const Gemm2Params& p, int grid,
-                   cudaStream_t st) {
-  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN>;
+template <int BN, bool A_MN, bool B_MN, int NP>
+static int launch2(const Gemm2Group<NP>& G, int grid, cudaStream_t st) {
+  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, NP>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
@@ -491,7 +515,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, G);
   if (le != cudaSuccess) {
     set_error("zb_gemm (cta pair) launch: %s", cudaGetErrorString(le));
     return ZB_ECUDA;
@@ -500,12 +524,11 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 }
 
 template <int BN>
-static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
-                     const Gemm2Params& p, int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, td, p, grid, st);
-  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, td, p, grid, st);
-  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, td, p, grid, st);
-  return launch2<BN, true, true>(ta, tb, td, p, grid, st);
+static int dispatch2(int a_mn, int b_mn, const Gemm2Group<1>& G, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false, 1>(G, grid, st);
+  if (!a_mn && b_mn) return launch2<BN, false, true, 1>(G, grid, st);
+  if (a_mn && !b_mn) return launch2<BN, true, false, 1>(G, grid, st);
+  return launch2<BN, true, true, 1>(G, grid, st);
 }
 
 // Whether the CTA-pair kernel should take this problem.  ZB_GEMM2=0 disables it, ZB_GEMM2=1 forces it whenever legal.
@@ -513,23 +536,92 @@ bool gemm2_wanted(const zb_gemm_args* a) {
   static const char* env = getenv("ZB_GEMM2");
   if (env && env[0] == '0') return false;
   if (a->n < 128 || a->m < 256) return false;
-  if (env && env[0] == '1') return true;
   return true;
 }
 
-int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
-  Gemm2Params p;
+// Split-K choice for `tiles` output tiles of `kb_total` k-blocks each.  Cost model fitted to measurements on the
+// weight-gradient shapes (tools/gemm_selftest --one ... with ZB_FORCE_SPLITS): a wave of CTA pairs costs
+// ~0.27 us per k-block plus ~1.5 us of fill / drain, so e.g. 16 tiles take 4 splits (one wave of 64) rather than
+// 9 (two waves of 72).
+static int choose_splits(long long tiles, int kb_total, int pairs_hw) {
+  static const char* force_splits = getenv("ZB_FORCE_SPLITS");  // calibration
+  if (force_splits) return atoi(force_splits);
+  int max_splits = kb_total / 4;
+  if (max_splits < 1) max_splits = 1;
+  if (max_splits > 64) max_splits = 64;
+  int best_s = 1;
+  double best = 1e30;
+  for (int s = 1; s <= max_splits; ++s) {
+    const long long waves = (tiles * s + pairs_hw - 1) / pairs_hw;
+    const double cost = (double)waves * (((kb_total + s - 1) / s) * 0.27 + 1.5);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_s = s;
+    }
+  }
+  return best_s;
+}
+
+// Fills the tile geometry (everything but the split fields) and the three tensor maps of one problem.
+static int setup_problem(const zb_gemm_args* a, int bn, Gemm2Params& p, CUtensorMap* maps) {
   p.M = (int)a->m; p.N = (int)a->n; p.K = (int)a->k;
   p.d = a->d; p.ldd = a->ldd; p.bias = a->bias;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
   p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
   p.kb_total = (p.K + k2BK - 1) / k2BK;
   p.mt = (p.M + 255) / 256;
+  p.nt = (p.N + bn - 1) / bn;
+  p.gn = bn == 256 ? 6 : 8;
+  if (p.gn > p.nt) p.gn = p.nt;
+  p.tile_begin = 0;
+  const bool accum = a->flags & ZB_EPI_ACCUM;
+  int rc;
+  const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
+  if (!a_mn) rc = make_map(&maps[0], a->a, p.K, p.M, a->lda, 128);
+  else rc = make_map(&maps[0], a->a, p.M, p.K, a->lda, k2BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&maps[1], a->b, p.K, p.N, a->ldb, bn / 2);
+  else rc = make_map(&maps[1], a->b, p.N, p.K, a->ldb, k2BK);
+  if (rc) return rc;
+  // outputs with 16 B-aligned rows go through shared memory + TMA tile stores / bulk reduce-adds
+  static const char* no_tma_d = getenv("ZB_GEMM_NO_TMA_STORE");
+  static const char* no_tma_red = getenv("ZB_GEMM_NO_TMA_REDUCE");
+  maps[2] = maps[0];
+  p.d_tma = 0;
+  const bool d_al = (reinterpret_cast<uintptr_t>(a->d) & 15) == 0;
+  if (accum && p.d_f32 && !no_tma_d && !no_tma_red && d_al && (a->ldd * 4) % 16 == 0) {
+    rc = make_map_f32(&maps[2], a->d, p.N, p.M, a->ldd, 32);
+    if (rc) return rc;
+    p.d_tma = 3;
+  }
+  if (!accum && !no_tma_d && d_al) {
+    if (!p.d_f32 && (a->ldd * 2) % 16 == 0) {
+      rc = make_map(&maps[2], a->d, p.N, p.M, a->ldd, 32);
+      if (rc) return rc;
+      p.d_tma = 1;
+    } else if (p.d_f32 && (a->ldd * 4) % 16 == 0) {
+      rc = make_map_f32(&maps[2], a->d, p.N, p.M, a->ldd, 32);
+      if (rc) return rc;
+      p.d_tma = 2;
+    }
+  }
+  return ZB_OK;
+}
+
+static void set_splits(Gemm2Params& p, int splits) {
+  if (splits > p.kb_total) splits = p.kb_total;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+}
+
+int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   const bool accum = a->flags & ZB_EPI_ACCUM;
   const int pairs_hw = num_sms() / 2;
+  const int mt = (int)((a->m + 255) / 256);
   int bn = 256;
-  auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
-  if (p.N <= 128) bn = 128;
+  auto tiles_for = [&](int b) { return (long long)mt * ((a->n + b - 1) / b); };
+  if (a->n <= 128) bn = 128;
   if (!accum && bn == 256) {
     // wave quantisation: cost ~ (#waves of pair tiles) x (tile width); e.g. N = 1536 at M = 4096 is 96 tiles of 256
     // (2 waves of 74 pairs) but 192 tiles of 128 (3 waves of half the work each)
@@ -537,72 +629,66 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
     const long long w128 = (tiles_for(128) + pairs_hw - 1) / pairs_hw * 128;
     if (w128 < w256) bn = 128;
   }
-  p.nt = (p.N + bn - 1) / bn;
-  p.gn = bn == 256 ? 6 : 8;
-  if (p.gn > p.nt) p.gn = p.nt;
+  Gemm2Group<1> G;
+  Gemm2Params& p = G.prob[0];
+  int rc = setup_problem(a, bn, p, G.maps);
+  if (rc) return rc;
   const long long tiles = (long long)p.mt * p.nt;
   int splits = a->split_k;
-  if (splits <= 0) {
-    splits = 1;
-    if (accum && tiles < pairs_hw) {
-      int max_splits = p.kb_total / 4;
-      if (max_splits < 1) max_splits = 1;
-      if (max_splits > 64) max_splits = 64;
-      double best = 0.0;
-      for (int s = 1; s <= max_splits; ++s) {
-        const long long work = tiles * s;
-        const long long waves = (work + pairs_hw - 1) / pairs_hw;
-        const double eff = (double)work / (double)(waves * pairs_hw);
-        if (eff > best + 0.02) {
-          best = eff;
-          splits = s;
-        }
-      }
-    }
-  }
+  if (splits <= 0) splits = (accum && tiles < pairs_hw) ? choose_splits(tiles, p.kb_total, pairs_hw) : 1;
   if (splits > 1 && !accum) {
     set_error("zb_gemm: split_k > 1 requires ZB_EPI_ACCUM");
     return ZB_EINVAL;
   }
-  if (splits > p.kb_total) splits = p.kb_total;
-  p.kb_per_split = (p.kb_total + splits - 1) / splits;
-  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-
-  CUtensorMap ta, tb;
-  int rc;
-  const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
-  if (!a_mn) rc = make_map(&ta, a->a, p.K, p.M, a->lda, 128);
-  else rc = make_map(&ta, a->a, p.M, p.K, a->lda, k2BK);
-  if (rc) return rc;
-  if (!b_mn) rc = make_map(&tb, a->b, p.K, p.N, a->ldb, bn / 2);
-  else rc = make_map(&tb, a->b, p.N, p.K, a->ldb, k2BK);
-  if (rc) return rc;
-  // bf16 overwrite outputs with 16 B-aligned rows go through shared memory + TMA tile stores
-  static const char* no_tma_d = getenv("ZB_GEMM_NO_TMA_STORE");
-  CUtensorMap td = ta;
-  p.d_tma = 0;
-  static const char* no_tma_red = getenv("ZB_GEMM_NO_TMA_REDUCE");
-  if (accum && p.d_f32 && !no_tma_d && !no_tma_red && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0 &&
-      (a->ldd * 4) % 16 == 0) {
-    rc = make_map_f32(&td, a->d, p.N, p.M, a->ldd, 32);
-    if (rc) return rc;
-    p.d_tma = 3;
-  }
-  if (!accum && !no_tma_d && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0) {
-    if (!p.d_f32 && (a->ldd * 2) % 16 == 0) {
-      rc = make_map(&td, a->d, p.N, p.M, a->ldd, 32);
-      if (rc) return rc;
-      p.d_tma = 1;
-    } else if (p.d_f32 && (a->ldd * 4) % 16 == 0) {
-      rc = make_map_f32(&td, a->d, p.N, p.M, a->ldd, 32);
-      if (rc) return rc;
-      p.d_tma = 2;
-    }
-  }
+  set_splits(p, splits);
   const long long total = tiles * p.splits;
+  G.count = 1;
+  G.total_tiles = (int)total;
   const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
-  if (bn == 128) return dispatch2<128>(a_mn, b_mn, ta, tb, td, p, grid, st);
-  return dispatch2<256>(a_mn, b_mn, ta, tb, td, p, grid, st);
+  const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
+  if (bn == 128) return dispatch2<128>(a_mn, b_mn, G, grid, st);
+  return dispatch2<256>(a_mn, b_mn, G, grid, st);
+}
+
+// One launch for several accumulate-into-fp32 problems with MN-major operands (the weight gradients of a layer).
+// Returns ZB_OK after launching, a negative status on error, or +1 when the set does not qualify (the caller then
+// launches the problems one by one).
+int gemm2_launch_group(const zb_gemm_args* args, int count, cudaStream_t st) {
+  static const char* off = getenv("ZB_NO_GEMM_GROUP");
+  if (off || count < 2 || count > k2MaxGroup) return 1;
+  for (int i = 0; i < count; ++i) {
+    const zb_gemm_args* a = &args[i];
+    if (a->a_layout != ZB_MN_MAJOR || a->b_layout != ZB_MN_MAJOR || !(a->flags & ZB_EPI_ACCUM) ||
+        a->d_dtype != ZB_F32 || a->split_k > 0 || a->n < 256 || a->m < 256 || !gemm2_wanted(a))
+      return 1;
+  }
+  const int pairs_hw = num_sms() / 2;
+  Gemm2Group<k2MaxGroup> G;
+  long long tiles = 0;
+  int kb_min = 1 << 30, kb_max = 0;
+  for (int i = 0; i < count; ++i) {
+    int rc = setup_problem(&args[i], 256, G.prob[i], &G.maps[3 * i]);
+    if (rc) return rc;
+    tiles += (long long)G.prob[i].mt * G.prob[i].nt;
+    kb_min = G.prob[i].kb_total < kb_min ? G.prob[i].kb_total : kb_min;
+    kb_max = G.prob[i].kb_total > kb_max ? G.prob[i].kb_total : kb_max;
+  }
+  int splits = choose_splits(tiles, kb_max, pairs_hw);
+  if (splits > kb_min / 4) splits = kb_min / 4 > 0 ? kb_min / 4 : 1;
+  long long total = 0;
+  for (int i = 0; i < count; ++i) {
+    set_splits(G.prob[i], splits);
+    G.prob[i].tile_begin = (int)total;
+    total += (long long)G.prob[i].mt * G.prob[i].nt * G.prob[i].splits;
+  }
+  for (int i = count; i < k2MaxGroup; ++i) {
+    G.prob[i] = G.prob[0];
+    G.prob[i].tile_begin = 1 << 30;
+  }
+  G.count = count;
+  G.total_tiles = (int)total;
+  const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
+  return launch2<256, true, true, k2MaxGroup>(G, grid, st);
 }
 
 }  // namespace zb

@@ -23,6 +23,7 @@ namespace zb {
 
 bool gemm2_wanted(const zb_gemm_args* a);
 int gemm2_launch(const zb_gemm_args* a, cudaStream_t st);
+int gemm2_launch_group(const zb_gemm_args* args, int count, cudaStream_t st);
 
 struct GemmKParams {
   int M, N, K;
@@ -466,7 +467,7 @@ static int dispatch_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUte
 
 }  // namespace zb
 
-extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
+static int validate_gemm(const zb_gemm_args* a) {
   using namespace zb;
   ZB_REQUIRE(a && a->a && a->b && a->d, "zb_gemm: null pointer");
   ZB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "zb_gemm: empty problem m=%lld n=%lld k=%lld", (long long)a->m,
@@ -485,6 +486,39 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   ZB_REQUIRE((a->ldd * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0,
              "zb_gemm: destination must be 16-byte aligned with a 16-byte pitch");
   ZB_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31), "zb_gemm: dimension too large");
+  return ZB_OK;
+}
+
+// Same result as zb_gemm on every problem (outputs must not overlap); accumulate-into-fp32 problems with MN-major
+// operands (the weight gradients of one layer) share ONE persistent launch.
+extern "C" int zb_gemm_grouped(const zb_gemm_args* problems, int32_t count, zb_stream_t stream) {
+  using namespace zb;
+  ZB_REQUIRE(count >= 0 && (count == 0 || problems), "zb_gemm_grouped: null pointer");
+  for (int i = 0; i < count; ++i) {
+    int rc = validate_gemm(&problems[i]);
+    if (rc) return rc;
+  }
+  int done = 0;
+  while (done < count) {
+    int n = count - done < 8 ? count - done : 8;
+    int rc = gemm2_launch_group(problems + done, n, reinterpret_cast<cudaStream_t>(stream));
+    if (rc < 0) return rc;
+    if (rc > 0) {  // not groupable: one by one
+      for (int i = 0; i < n; ++i) {
+        rc = zb_gemm(&problems[done + i], stream);
+        if (rc) return rc;
+      }
+    }
+    done += n;
+  }
+  return ZB_OK;
+}
+
+extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
+  using namespace zb;
+  int vrc = validate_gemm(a);
+  if (vrc) return vrc;
+  const bool accum = a->flags & ZB_EPI_ACCUM;
   // CTA-pair kernel (tcgen05 cta_group::2, gemm2_tcgen05.cu) for everything with at least one 256 x 128 pair tile
   if (gemm2_wanted(a)) return gemm2_launch(a, reinterpret_cast<cudaStream_t>(stream));
 

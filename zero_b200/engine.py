@@ -336,7 +336,24 @@ class Engine(object):
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 
+    def _wgrad(self, x, dy, dw, db=None):
+        """Queue dW += x^T dy (and db += column sums of dy) of one func.linear; the queue is flushed once per layer
+        as ONE grouped GEMM launch + ONE grouped column-sum launch on the side stream (_side_layer_end)."""
+        if not hasattr(self, "_wg"):
+            self._wg, self._cs = [], []
+        self._wg.append((x, dy, dw))
+        if db is not None:
+            self._cs.append((dy, db))
+
+    def _flush_wgrads(self):
+        wg, cs = getattr(self, "_wg", []), getattr(self, "_cs", [])
+        if not wg and not cs:
+            return
+        self._wg, self._cs = [], []
+        self._side(lambda: (ops.gemm_grouped([ops.wgrad_args(*t) for t in wg]), ops.colsum_grouped(cs)))
+
     def _side_layer_end(self, tag, l):
+        self._flush_wgrads()
         side = getattr(self, "side", None)
         if side is None:
             return
@@ -345,6 +362,7 @@ class Engine(object):
         self._side_ev[(tag, l)] = ev
 
     def _side_join(self):
+        self._flush_wgrads()
         side = getattr(self, "side", None)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
@@ -376,7 +394,7 @@ class Engine(object):
         """Returns dx (gradient wrt the sublayer input through the attention branch)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        self._side(lambda: ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")))  # o.b: summed by the LN backward
+        self._wgrad(sv["feed"], dy, ps.g(key + ".o.W"))  # o.b: summed by the LN backward
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -385,7 +403,7 @@ class Engine(object):
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), d3[:, :, :c.d], d3[:, :, c.d:2 * c.d], d3[:, :, 2 * c.d:],
                           delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
-        self._side(lambda: (ops.linear_wgrad(x, dqkv, ps.g(key + ".qkv.W")), ops.colsum(dqkv, ps.g(key + ".qkv.b"))))
+        self._wgrad(x, dqkv, ps.g(key + ".qkv.W"), ps.g(key + ".qkv.b"))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dqkv, ps.w(key + ".qkv.W"), dx)
         return dx
@@ -416,7 +434,7 @@ class Engine(object):
     def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
-        self._side(lambda: ops.linear_wgrad(sv["feed"], dy, ps.g(key + ".o.W")))  # o.b: summed by the LN backward
+        self._wgrad(sv["feed"], dy, ps.g(key + ".o.W"))  # o.b: summed by the LN backward
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
@@ -426,8 +444,8 @@ class Engine(object):
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), dq.view(B, Lq, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:],
                           delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
-        self._side(lambda: (ops.linear_wgrad(x, dq, ps.g(key + ".q.W")), ops.colsum(dq, ps.g(key + ".q.b")),
-                            ops.linear_wgrad(enc, dkv, ps.g(key + ".kv.W")), ops.colsum(dkv, ps.g(key + ".kv.b"))))
+        self._wgrad(x, dq, ps.g(key + ".q.W"), ps.g(key + ".q.b"))
+        self._wgrad(enc, dkv, ps.g(key + ".kv.W"), ps.g(key + ".kv.b"))
         # d_enc (fp32, accumulated over decoder layers) += dkv @ Wkv^T
         ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
         dx = ws.get(tag + ".dx", (N, c.d))
@@ -466,10 +484,10 @@ class Engine(object):
 
     def _ffn_bwd(self, key, x, dy, N, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
-        self._side(lambda: ops.linear_wgrad(sv["h"], dy, ps.g(key + ".w2.W")))  # w2.b: summed by the LN backward
+        self._wgrad(sv["h"], dy, ps.g(key + ".w2.W"))  # w2.b: summed by the LN backward
         dh = ws.get(tag + ".dh", (N, c.f))
         ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"])
-        self._side(lambda: (ops.linear_wgrad(x, dh, ps.g(key + ".w1.W")), ops.colsum(dh, ps.g(key + ".w1.b"))))
+        self._wgrad(x, dh, ps.g(key + ".w1.W"), ps.g(key + ".w1.b"))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dh, ps.w(key + ".w1.W"), dx)
         return dx

@@ -26,6 +26,10 @@ class GemmArgs(C.Structure):
                 ("alpha", f32), ("split_k", i32)]
 
 
+class ColsumArgs(C.Structure):
+    _fields_ = [("x", vp), ("m", i64), ("n", i64), ("ld", i64), ("out", vp)]
+
+
 class AttentionArgs(C.Structure):
     _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp),
                 ("ldq", i64), ("ldk", i64), ("ldv", i64), ("ldo", i64),
@@ -80,6 +84,7 @@ EXPORTS = [
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
+    "zb_gemm_grouped", "zb_colsum_grouped",
 ]
 
 _lib = None
@@ -104,6 +109,8 @@ def load():
     lib.zb_launch_count.restype = C.c_int64
     for name, argt in [
         ("zb_gemm", [C.POINTER(GemmArgs), vp]),
+        ("zb_gemm_grouped", [C.POINTER(GemmArgs), i32, vp]),
+        ("zb_colsum_grouped", [C.POINTER(ColsumArgs), i32, vp]),
         ("zb_attention_fwd", [C.POINTER(AttentionArgs), vp]),
         ("zb_attention_bwd", [C.POINTER(AttentionArgs), vp]),
         ("zb_add_ln_fwd", [C.POINTER(AddLnArgs), vp]),

@@ -31,7 +31,14 @@ def gemm(a, b, out, a_layout=L.ZB_K_MAJOR, b_layout=L.ZB_MN_MAJOR, bias=None, re
     """D[m,n] (+)= alpha * sum_k A(m,k) B(n,k) (+bias) (relu) (*mask>0).  a/b/out: 2-D row-major views.
     Layout semantics as in include/zero_b200.h: K-major operand is stored [rows, k]; MN-major is stored [k, rows].
     func.linear (func.py:49,59): gemm(x, W, y, b_layout=MN_MAJOR, bias=b)."""
-    lib = L.load()
+    args = gemm_args(a, b, out, a_layout, b_layout, bias, relu, accum, relu_mask, alpha, split_k, m, n, k)
+    L.check(L.load().zb_gemm(C.byref(args), _stream()), "zb_gemm")
+    return out
+
+
+def gemm_args(a, b, out, a_layout=L.ZB_K_MAJOR, b_layout=L.ZB_MN_MAJOR, bias=None, relu=False, accum=False,
+              relu_mask=None, alpha=1.0, split_k=0, m=None, n=None, k=None):
+    """The zb_gemm_args record of one problem (see gemm)."""
     M = m if m is not None else (a.shape[0] if a_layout == L.ZB_K_MAJOR else a.shape[1])
     Kd = k if k is not None else (a.shape[1] if a_layout == L.ZB_K_MAJOR else a.shape[0])
     N = n if n is not None else (b.shape[0] if b_layout == L.ZB_K_MAJOR else b.shape[1])
@@ -44,12 +51,32 @@ def gemm(a, b, out, a_layout=L.ZB_K_MAJOR, b_layout=L.ZB_MN_MAJOR, bias=None, re
         flags |= L.ZB_EPI_ACCUM
     if relu_mask is not None:
         flags |= L.ZB_EPI_RELU_MASK
-    args = L.GemmArgs(
+    return L.GemmArgs(
         _p(a), _p(b), _p(out), M, N, Kd, _rowmajor2d(a), _rowmajor2d(b), _rowmajor2d(out),
         a_layout, b_layout, L.ZB_F32 if out.dtype == torch.float32 else L.ZB_BF16, flags,
         _p(bias), _p(relu_mask), _rowmajor2d(relu_mask) if relu_mask is not None else 0, float(alpha), int(split_k))
-    L.check(lib.zb_gemm(C.byref(args), _stream()), "zb_gemm")
-    return out
+
+
+def gemm_grouped(problems):
+    """zb_gemm_grouped over a list of gemm_args records (one persistent launch for a layer's weight gradients)."""
+    if not problems:
+        return
+    arr = (L.GemmArgs * len(problems))(*problems)
+    L.check(L.load().zb_gemm_grouped(arr, len(problems), _stream()), "zb_gemm_grouped")
+
+
+def wgrad_args(x, dy, dw):
+    """Problem record of linear_wgrad (dW += x^T dy)."""
+    return gemm_args(x, dy, dw, L.ZB_MN_MAJOR, L.ZB_MN_MAJOR, accum=True)
+
+
+def colsum_grouped(pairs):
+    """db_i += sum_rows x_i for every (x_i, db_i): the bias gradients of one layer in one launch."""
+    if not pairs:
+        return
+    arr = (L.ColsumArgs * len(pairs))(*[L.ColsumArgs(_p(x), x.shape[0], x.shape[1], x.stride(0), _p(o))
+                                       for x, o in pairs])
+    L.check(L.load().zb_colsum_grouped(arr, len(pairs), _stream()), "zb_colsum_grouped")
 
 
 def linear_fwd(x, w, bias, out, relu=False):
