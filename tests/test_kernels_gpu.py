@@ -97,7 +97,7 @@ def test_gemm_grouped_and_colsum_grouped(tokens):
 
 
 # ------------------------------------------------------------------------------------------------ add + LN
-@pytest.mark.parametrize("rows,cols", [(37, 64), (4096, 512), (100, 1024)])
+@pytest.mark.parametrize("rows,cols", [(37, 64), (4096, 512), (100, 1024), (5000, 512), (300, 128)])
 def test_add_ln_fwd_bwd(rows, cols):
     from zero_b200 import ops
     x, y = rnd(rows, cols, seed=1), rnd(rows, cols, seed=2)
@@ -124,6 +124,13 @@ def test_add_ln_fwd_bwd(rows, cols):
     torch.testing.assert_close(dbias, xr.grad.sum(0), atol=2e-2 * math.sqrt(rows), rtol=1e-2)
     torch.testing.assert_close(dscale, sc.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
     torch.testing.assert_close(doffset, of.grad, atol=2e-2 * math.sqrt(rows), rtol=1e-2)
+    # without the bias-gradient rider and with a single gradient addend
+    ds2 = torch.empty_like(x)
+    dscale2, doffset2 = torch.zeros(cols, device=dev()), torch.zeros(cols, device=dev())
+    d12 = (d1.float() + d2.float()).to(torch.bfloat16)
+    ops.add_ln_bwd(x, y, d12, None, mean, rstd, scale, ds2, dscale2, doffset2, None)
+    torch.testing.assert_close(ds2.float(), xr.grad, atol=6e-2, rtol=3e-2)
+    torch.testing.assert_close(doffset2, d12.float().sum(0), atol=2e-2 * math.sqrt(rows), rtol=1e-2)
 
 
 # ------------------------------------------------------------------------------------------------ embedding
@@ -164,7 +171,7 @@ def test_embed_fwd_bwd():
 
 
 # ------------------------------------------------------------------------------------------------ CE
-@pytest.mark.parametrize("V", [200, 32000])
+@pytest.mark.parametrize("V", [200, 1002, 32000, 40000])
 def test_softmax_ce(V):
     from oracle import zero_oracle as zo
     from zero_b200 import ops

@@ -5,6 +5,7 @@
 // Algorithmic bytes / row (bf16): fwd 3 * cols * 2 (read x, y; write out); bwd 5 * cols * 2.
 #include "zb_common.h"
 #include "zb_ptx.cuh"
+#include <stdlib.h>
 
 namespace zb {
 
@@ -200,6 +201,123 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   }
 }
 
+// Single-pass variant for cols <= 512 and rows <= 32 * gridDim.x (every add+LN backward of a 4096-token training
+// batch): one CTA of 32 warps per 32 rows, ONE row per warp, so every row of the batch is in flight at once (the
+// looping kernel above needs two latency-bound passes at 4096 rows).  The column sums (dscale, doffset, dbias) of
+// the CTA's 32 rows are combined through shared memory and leave as 16-byte vector reductions: the per-address
+// serialisation of the L2 atomic unit made the 296-CTA x 1536 scalar atomics of the looping kernel cost ~6 us.
+constexpr int kLn1pWarps = 32;
+
+__device__ __forceinline__ void red_add_f32x4(float* addr, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kLn1pWarps * 32, 1)
+add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                        const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ scale, __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale,
+                        float* __restrict__ doffset, float* __restrict__ dbias, long long rows, int cols) {
+  grid_dep_wait();
+  extern __shared__ __align__(16) float red[];  // [3][kLn1pWarps][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  const long long row = (long long)blockIdx.x * kLn1pWarps + warp;
+  const bool live = row < rows;
+  float* r_s = red + (size_t)warp * cols;
+  float* r_o = red + (size_t)(kLn1pWarps + warp) * cols;
+  float* r_b = red + (size_t)(2 * kLn1pWarps + warp) * cols;
+  float sh[NV][8], d[NV][8];
+  float sg = 0.f, sgs = 0.f;
+  float mu = 0.f, rs = 0.f;
+  if (live) {
+    mu = mean[row];
+    rs = rstd[row];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sh[i][e] = d[i][e] = 0.f;
+    if (live && v < nvec) {
+      load8(x + row * cols + v * 8, sh[i]);
+      if (y) {
+        float t[8];
+        load8(y + row * cols + v * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sh[i][e] += t[e];
+      }
+      load8(d_out + row * cols + v * 8, d[i]);
+      if (d_out2) {
+        float t[8];
+        load8(d_out2 + row * cols + v * 8, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[i][e] += t[e];
+      }
+      const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + v * 8)),
+                   sc1 = __ldg(reinterpret_cast<const float4*>(scale + v * 8) + 1);
+      const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sh[i][e] = (sh[i][e] - mu) * rs;
+        const float g = d[i][e] * sc[e];
+        sg += g;
+        sgs += g * sh[i][e];
+      }
+    }
+  }
+  sg = warp_sum(sg) / cols;
+  sgs = warp_sum(sgs) / cols;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float o[8], ps[8];
+      if (live) {
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + v * 8)),
+                     sc1 = __ldg(reinterpret_cast<const float4*>(scale + v * 8) + 1);
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rs * (d[i][e] * sc[e] - sg - sh[i][e] * sgs);
+        store8(ds + row * cols + v * 8, o);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ps[e] = d[i][e] * sh[i][e];
+      float4* ws = reinterpret_cast<float4*>(r_s + v * 8);
+      float4* wo = reinterpret_cast<float4*>(r_o + v * 8);
+      ws[0] = make_float4(ps[0], ps[1], ps[2], ps[3]);
+      ws[1] = make_float4(ps[4], ps[5], ps[6], ps[7]);
+      wo[0] = make_float4(d[i][0], d[i][1], d[i][2], d[i][3]);
+      wo[1] = make_float4(d[i][4], d[i][5], d[i][6], d[i][7]);
+      if (dbias) {
+        float4* wb = reinterpret_cast<float4*>(r_b + v * 8);
+        wb[0] = make_float4(o[0], o[1], o[2], o[3]);   // bf16-rounded ds is what the GEMMs see; the sum uses fp32
+        wb[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+  __syncthreads();
+  // thread (q, c4): quantity q in {dscale, doffset, dbias}, 4 columns; sums the CTA's 32 row partials
+  const int c4n = cols >> 2;
+  const int q = threadIdx.x / c4n, c4 = threadIdx.x % c4n;
+  if (q < (dbias ? 3 : 2)) {
+    const float* src = red + (size_t)q * kLn1pWarps * cols + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int w = 0; w < kLn1pWarps; ++w) {
+      const float4 t = *reinterpret_cast<const float4*>(src + (size_t)w * cols);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float* dst = (q == 0 ? dscale : (q == 1 ? doffset : dbias)) + c4 * 4;
+    red_add_f32x4(dst, acc);
+  }
+}
+
 static int check(const zb_add_ln_args* a, const char* who) {
   ZB_REQUIRE(a && a->x && a->scale, "%s: null pointer", who);
   ZB_REQUIRE(a->rows >= 0 && a->cols > 0 && a->cols % 8 == 0 && a->cols <= 8 * 32 * kLnMaxVec,
@@ -245,6 +363,30 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   if (a->rows == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (int)((a->cols / 8 + 31) / 32);
+  static const bool no_1pass = getenv("ZB_LN_BWD_LOOP") != nullptr;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(a->dscale) | reinterpret_cast<uintptr_t>(a->doffset) |
+                        reinterpret_cast<uintptr_t>(a->dbias)) & 15) == 0;
+  if (!no_1pass && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= kLn1pWarps * 32 &&
+      a->rows <= (long long)num_sms() * kLn1pWarps) {
+    const int grid = (int)((a->rows + kLn1pWarps - 1) / kLn1pWarps);
+    const size_t smem1 = (size_t)3 * kLn1pWarps * a->cols * sizeof(float);
+#define CALL1(N)                                                                                             \
+  do {                                                                                                       \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      cudaFuncSetAttribute(add_ln_bwd_1pass_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                           3 * kLn1pWarps * 512 * (int)sizeof(float));                                       \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    ZB_LAUNCH(add_ln_bwd_1pass_kernel<N>, grid, kLn1pWarps * 32, smem1, st,                                  \
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
+        (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
+        a->doffset, a->dbias, a->rows, (int)a->cols);                                                        \
+  } while (0)
+    if (nv <= 1) CALL1(1); else CALL1(2);
+#undef CALL1
+    return check_launch("zb_add_ln_bwd(1pass)");
+  }
   long long blocks = (a->rows + kLnWarps - 1) / kLnWarps;
   const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;

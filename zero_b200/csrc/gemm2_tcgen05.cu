@@ -45,6 +45,7 @@ struct Gemm2Group {
   CUtensorMap maps[3 * NP];  // a, b, d of each problem
   Gemm2Params prob[NP];
   int count, total_tiles;
+  unsigned long long* trace;  // debug (ZB_GEMM_TRACE=1): CTA 0 stamps globaltimer at 10 points of its life
 };
 constexpr int k2MaxGroup = 8;
 
@@ -68,8 +69,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Cluster barrier with a RELAXED arrive: ptxas lowers the release form to MEMBAR.ALL.GPU + ERRBAR before the
+// UCGABAR_ARV (SASS), a GPU-scope fence the kernel does not need — what crosses the pair is ordered by
+// fence.mbarrier_init / the tcgen05 fences, and the CTA-local part by the __syncthreads in front of it.
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
@@ -77,8 +82,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Default semantics (.release.cta), like CUTLASS' ClusterBarrier::arrive(cta_id): the cluster-scope release form
+// costs a MEMBAR.ALL.GPU per accumulator hand-back (~1.2 us between "store issued" and "arrived" in the trace);
+// the hand-back only has to order the TMEM reads, which tcgen05.fence::before_thread_sync does.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   // acquire at cluster scope: the arrivals come from the peer CTA
@@ -140,6 +148,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
+// explicit shared-space 16 B store (the staging pointer arithmetic otherwise compiles to generic ST.E.128)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __device__ __forceinline__ void tile2_coords(const Gemm2Params& p, int tile, int& m_blk, int& n_blk, int& ks) {
   const int per_split = p.mt * p.nt;
   ks = tile / per_split;
@@ -186,6 +199,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
   const bool leader = rank == 0;
   const int num_tiles = G.total_tiles;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const bool tracing = G.trace != nullptr && blockIdx.x == 0;
+  if (tracing && threadIdx.x == 0) G.trace[0] = globaltimer_ns();
 
   if (warp == 0 && lane < 3 * NP && lane < 3 * G.count) tma_prefetch_desc(&G.maps[lane]);
   if (warp == 0 && lane == 0) {
@@ -200,30 +215,49 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  {
+    // The problem descriptors live in the kernel-parameter constant bank; their first read after the dependency wait
+    // cost the producer ~0.5 us (trace: dep_wait -> first TMA).  Reading them here, in the shadow of the TMEM
+    // allocation and of the predecessor's tail, pulls them into the constant cache.
+    int warm = G.prob[0].M + G.prob[0].tile_begin + G.prob[0].d_tma;
+    if (NP > 1) warm += G.prob[NP - 1].M + G.prob[NP - 1].d_tma + G.prob[NP / 2].M;
+    asm volatile("" ::"r"(warm));
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  grid_dep_wait();
+  if (tracing && threadIdx.x == 0) G.trace[1] = globaltimer_ns();
+  // griddepcontrol.wait is executed only by the threads that touch global memory (the producer and the epilogue
+  // warps), each AFTER the parameter-only part of its prologue: the producer's tile coordinates (three integer
+  // divisions + constant-bank reads, ~0.3 us) are computed in the shadow of the predecessor's tail.
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pi = 0, m0 = 0, n0 = 0, kb0 = 0, kb1 = 0;
+      auto locate = [&](int tile) {
+        pi = find_problem<NP>(G, tile);
+        const Gemm2Params& q = G.prob[pi];
+        int m_blk, n_blk, ks;
+        tile2_coords(q, tile - q.tile_begin, m_blk, n_blk, ks);
+        kb0 = ks * q.kb_per_split;
+        kb1 = min(q.kb_total, kb0 + q.kb_per_split);
+        m0 = m_blk * 256 + (int)rank * 128;       // this CTA's rows of A
+        n0 = n_blk * BN + (int)rank * (BN / 2);   // this CTA's rows of B
+      };
+      if (pair < num_tiles) locate(pair);
+      grid_dep_wait();
+      if (tracing) G.trace[2] = globaltimer_ns();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int pi = find_problem<NP>(G, tile);
-        const Gemm2Params& p = G.prob[pi];
+        if (tile != pair) locate(tile);
         const CUtensorMap* tma_a = &G.maps[3 * pi];
         const CUtensorMap* tma_b = &G.maps[3 * pi + 1];
-        int m_blk, n_blk, ks;
-        tile2_coords(p, tile - p.tile_begin, m_blk, n_blk, ks);
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = m_blk * 256 + (int)rank * 128;       // this CTA's rows of A
-        const int n0 = n_blk * BN + (int)rank * (BN / 2);   // this CTA's rows of B
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (tracing && tile == pair && kb == kb0) G.trace[3] = globaltimer_ns();
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -270,6 +304,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (tracing && tile == pair && kb == kb0) G.trace[4] = globaltimer_ns();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
@@ -285,6 +320,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
           }
         }
         umma_commit_2sm(&tfull_bar[acc]);
+        if (tracing && tile == pair) G.trace[5] = globaltimer_ns();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -296,10 +332,13 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stg = epi_smem + (warp - 2) * 4096;
+    const uint32_t stg_s = smem_u32(stg);
+    bool store_pending = false;  // warp-uniform: a bulk tile store of this warp may still be reading `stg`
     int acc = 0;
     uint32_t acc_phase = 0;
 
     const uint32_t leader_tempty0 = mapa_u32(&tempty_bar[0], 0), leader_tempty1 = mapa_u32(&tempty_bar[1], 0);
+    grid_dep_wait();  // bias / mask reads and the output writes below; hidden behind the first tile's main loop
 
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int pi = find_problem<NP>(G, tile);
@@ -321,6 +360,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
         else tma_store_2d(tma_d, stg, col_even, row0);
         bulk_commit_group();
       }
+      store_pending = true;
     };
     auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4],
                             int cpar) {
@@ -362,29 +402,27 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
         }
       }
       if (tma_f32) {
-        if (lane == 0) bulk_wait_read_all();
-        __syncwarp();
-        uint8_t* rowp = stg + lane * 128;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) =
-              make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-        issue_store(row - lane, col0);
-      } else if (d_tma) {
-        if (cpar == 0) {  // the previous tile store must have drained the staging buffer
+        if (store_pending) {
           if (lane == 0) bulk_wait_read_all();
           __syncwarp();
         }
-        uint8_t* rowp = stg + lane * 128;
+        const uint32_t rowp = stg_s + lane * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-          o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-          o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-          o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(rowp + (((cpar * 4 + q) ^ (lane & 7)) << 4)) = o;
+        for (int q = 0; q < 8; ++q)
+          sts128(rowp + ((q ^ (lane & 7)) << 4), __float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]),
+                 __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+        issue_store(row - lane, col0);
+      } else if (d_tma) {
+        if (cpar == 0 && store_pending) {  // the previous tile store must have drained the staging buffer
+          if (lane == 0) bulk_wait_read_all();
+          __syncwarp();
         }
+        const uint32_t rowp = stg_s + lane * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(rowp + (((cpar * 4 + q) ^ (lane & 7)) << 4), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
+                 pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                 pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
         if (cpar == 1) issue_store(row - lane, col0 - 32);
       } else if (d_f32) {
         float* drow = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
@@ -450,35 +488,45 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + c0 * 32;
       uint32_t ra[32], rb[32];
+      if (tracing && tile == pair && warp == 2 && lane == 0) G.trace[6] = globaltimer_ns();
       tmem_ld_32x32b_x32(tbase, ra);
 #pragma unroll 1
+      const bool tr = tracing && tile == pair && warp == 2 && lane == 0;
       for (int c = 0; c < NCH; c += 2) {
         __syncwarp();
         tmem_ld_wait();
+        if (tr && c == 0) G.trace[10] = globaltimer_ns();
         if (c + 1 < NCH) {
           tmem_ld_32x32b_x32(tbase + (c + 1) * 32, rb);
           prefetch_chunk(row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b);
         }
         finish_chunk(ra, row, row_ok, n0 + (c0 + c) * 32, bias_a, mk_a, 0);
+        if (tr && c == 0) G.trace[11] = globaltimer_ns();
         if (c + 1 < NCH) {
           __syncwarp();
           tmem_ld_wait();
+          if (tr && c == 0) G.trace[12] = globaltimer_ns();
           if (c + 2 < NCH) {
             tmem_ld_32x32b_x32(tbase + (c + 2) * 32, ra);
             prefetch_chunk(row, row_ok, n0 + (c0 + c + 2) * 32, bias_a, mk_a);
           }
           finish_chunk(rb, row, row_ok, n0 + (c0 + c + 1) * 32, bias_b, mk_b, 1);
+          if (tr && c == 0) G.trace[13] = globaltimer_ns();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(acc == 0 ? leader_tempty0 : leader_tempty1);
+      if (tracing && tile == pair && warp == 2 && lane == 0) G.trace[7] = globaltimer_ns();
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
-    if (lane == 0) bulk_wait_all();  // the tile stores of this warp have landed before the CTA exits
+    // the tile stores of this warp have finished reading the staging buffer before the CTA exits (their global
+    // writes complete with the grid, like CUTLASS' tma_store_wait<0>)
+    if (lane == 0) bulk_wait_read_all();
+    if (tracing && warp == 2 && lane == 0) G.trace[8] = globaltimer_ns();
   }
 
   tc_fence_before();
@@ -487,6 +535,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
+  if (tracing && threadIdx.x == 0) G.trace[9] = globaltimer_ns();
 }
 
 template <int BN, bool A_MN, bool B_MN, int NP>
@@ -644,10 +693,31 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   const long long total = tiles * p.splits;
   G.count = 1;
   G.total_tiles = (int)total;
+  G.trace = nullptr;
+  static const bool trace_on = getenv("ZB_GEMM_TRACE") != nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(trace_buf, 0, 16 * sizeof(unsigned long long), st);
+    G.trace = trace_buf;
+  }
   const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
   const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
-  if (bn == 128) return dispatch2<128>(a_mn, b_mn, G, grid, st);
-  return dispatch2<256>(a_mn, b_mn, G, grid, st);
+  const int lrc = bn == 128 ? dispatch2<128>(a_mn, b_mn, G, grid, st) : dispatch2<256>(a_mn, b_mn, G, grid, st);
+  if (trace_on && lrc == ZB_OK) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    auto d = [&](int i) { return h[i] ? (long long)(h[i] - h[0]) : -1ll; };
+    fprintf(stderr,
+            "[zb_gemm2 trace] m=%d n=%d k=%d bn=%d splits=%d grid=%d tiles=%lld | ns since entry: setup %lld, dep_wait %lld, "
+            "first tma %lld, first data %lld, tile0 mma issued %lld, tile0 acc ready %lld, tile0 epilogue done %lld, "
+            "stores drained %lld, exit %lld | epilogue warp 2: ld0 done %lld, chunk0 staged %lld, ld1 done %lld, "
+            "chunk1 staged + store issued %lld\n",
+            p.M, p.N, p.K, bn, p.splits, grid, total, d(1), d(2), d(3), d(4), d(5), d(6), d(7), d(8), d(9), d(10), d(11),
+            d(12), d(13));
+  }
+  return lrc;
 }
 
 // One launch for several accumulate-into-fp32 problems with MN-major operands (the weight gradients of a layer).
@@ -687,6 +757,7 @@ int gemm2_launch_group(const zb_gemm_args* args, int count, cudaStream_t st) {
   }
   G.count = count;
   G.total_tiles = (int)total;
+  G.trace = nullptr;
   const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
   return launch2<256, true, true, k2MaxGroup>(G, grid, st);
 }
