@@ -39,6 +39,9 @@ int zb_abi_version(void);
 const char* zb_last_error_string(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 int64_t zb_launch_count(void);
+/* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,
+ * 7 colsum; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
+int64_t zb_abi_struct_size(int32_t which);
 
 /* ------------------------------------------------------------------------------------------------ K1
  * zb_gemm: D[m,n] (+)= alpha * sum_k A(m,k) * B(n,k)  (+ bias[n]) (relu) (* (mask[m,n] > 0))
@@ -112,6 +115,12 @@ typedef struct {
   float* delta;                       /* fp32 [batch, heads, lq] workspace: rowsum(dO * O) */
   int32_t kv_group;                   /* >= 1: query batch b reads keys/values of batch b / kv_group (beams of one
                                          sentence share the projected memory instead of tiling it, search.py:36-39) */
+  /* attention dropout (func.py:245, modules/rela.py:74): the softmax / relu weights are multiplied by
+     mask / (1 - rate) before the value product; mask = zb_dropout's function of (*seed, site, flat index into
+     [batch, heads, lq, lk]).  rate = 0 or seed = NULL: off. */
+  float dropout_rate;
+  uint32_t dropout_site;
+  const uint64_t* dropout_seed;       /* device pointer */
 } zb_attention_args;
 int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream);
 int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream);
@@ -287,6 +296,13 @@ int zb_gated_rms_bwd(const void* x, const void* dy, const float* rstd, const flo
  * (models/transformer_aan.py:185) as two strided copies. */
 int zb_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows,
              int64_t cols, zb_stream_t stream);
+/* zb_dropout: out[i] = x[i] (+ x2[i]) kept with probability 1 - rate and scaled by 1 / (1 - rate), else 0
+ * (tf.nn.dropout via util.valid_apply_dropout, utils/util.py:75-79).  bf16 [n]; out may alias x; x2 optional second
+ * addend (gradient fan-in).  The mask is a pure function of (*seed, site, i): the backward pass applies the SAME call
+ * to the upstream gradient.  Sites: embedding dropout (models/transformer.py:33,119), relu dropout
+ * (func.py:334), residual dropout (func.py:323).  seed: device pointer to one uint64. */
+int zb_dropout(const void* x, const void* x2, void* out, int64_t n, float rate, const uint64_t* seed, uint32_t site,
+               zb_stream_t stream);
 
 #ifdef __cplusplus
 }

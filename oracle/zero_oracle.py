@@ -28,6 +28,47 @@ import torch
 F32_MIN = float(np.finfo(np.float32).min)
 
 
+# ---- dropout hook (test infrastructure).  `DROP` is None (all dropout closed, like util.closing_dropout) or a
+# callable drop(site_name, x) -> tf.nn.dropout(x) with an externally supplied mask; site names are the CUDA engine's
+# ("enc0.self.att", "enc0.self.ln.res", "enc0.ffn.relu", "enc.emb", ...), so a test can hand the oracle exactly the
+# masks the kernels generate (dropout_mask below restates the kernels' counter-based keep function).
+DROP = None
+
+
+def _drop(site, x):
+    return x if DROP is None else DROP(site, x)
+
+
+def dropout_keep(seed, site_name, numel, rate):
+    """The CUDA path's keep mask (csrc/zb_ptx.cuh dropout_hash4 / dropout_mul) for flat indices [0, numel):
+    one splitmix64 hash per 4 consecutive elements, 16 bits each, keep iff bits >= round(rate * 65536)."""
+    import zlib
+    site = np.uint64(zlib.crc32(site_name.encode("ascii")) & 0xFFFFFFFF)
+    idx = np.arange(numel, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + site * np.uint64(0x9E3779B97F4A7C15) + (idx >> np.uint64(2)) * np.uint64(0xD1B54A32D192ED03)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        bits = (z >> (np.uint64(16) * (idx & np.uint64(3)))) & np.uint64(0xFFFF)
+    thr = min(max(int(np.float32(rate) * np.float32(65536.0) + np.float32(0.5)), 0), 65536)
+    return bits >= np.uint64(thr)
+
+
+def make_drop(seed, rates):
+    """drop(site, x) for DROP: rates = {"emb", "att", "relu", "res"} -> rate; the kind is the site's suffix."""
+    def drop(site, x):
+        kind = site.rsplit(".", 1)[1]
+        rate = float(rates.get(kind, 0.0))
+        if rate <= 0.0:
+            return x
+        keep = torch.from_numpy(dropout_keep(seed, site, x.numel(), rate)).reshape(x.shape)
+        return x * keep.to(x.dtype) / (1.0 - rate)
+    return drop
+
+
 def _ident(x):
     return x
 
@@ -230,7 +271,7 @@ def rel_index(lq, lk, k, q_offset=0):
     return torch.clamp(i - j, -k, k) + k
 
 
-def attention_core(c, P, prefix, qh, kh, vh, bias, q_offset=0, q=_ident):
+def attention_core(c, P, prefix, qh, kh, vh, bias, q_offset=0, q=_ident, site=None):
     """func.dot_attention core (func.py:218-256) / rela variant (modules/rela.py:52-75).
     qh,kh,vh: [B,h,L,dh]; bias: additive, broadcastable to [B,h,Lq,Lk] (or None)."""
     dh = qh.shape[-1]
@@ -249,6 +290,8 @@ def attention_core(c, P, prefix, qh, kh, vh, bias, q_offset=0, q=_ident):
         if bias is not None:
             logits = logits + bias
         w = torch.softmax(logits, -1)
+    if site is not None:
+        w = _drop(site + ".att", w)   # func.py:245 / modules/rela.py:74: the dropped weights feed both value terms
     o = w @ vh
     if c.rpr:
         ev = P[prefix + "/rpr_values/embeddings"][idx]
@@ -280,7 +323,7 @@ def aan_matrix(mask, inf):
     return w * m
 
 
-def self_attention(c, P, p, x, bias, cache=None, q_offset=0, q=_ident):
+def self_attention(c, P, p, x, bias, cache=None, q_offset=0, q=_ident, site=None):
     a = p + "/dot_attention"
     qkv = linear(P, a + "/qkv_map", x, q)
     qq, kk, vv = torch.split(qkv, c.d, -1)
@@ -289,11 +332,11 @@ def self_attention(c, P, p, x, bias, cache=None, q_offset=0, q=_ident):
         vv = torch.cat([cache["v"], vv], 1)
         cache = dict(cache, k=kk, v=vv)
     o, _ = attention_core(c, P, a, heads_split(qq, c.h), heads_split(kk, c.h), heads_split(vv, c.h), bias,
-                          q_offset, q)
+                          q_offset, q, site)
     return linear(P, a + "/o_map", o, q), cache
 
 
-def cross_attention(c, P, p, x, memory, bias, cache=None, q_offset=0, fuse=None, q=_ident):
+def cross_attention(c, P, p, x, memory, bias, cache=None, q_offset=0, fuse=None, q=_ident, site=None):
     """func.dot_attention with memory (func.py:206-216) and the merged-attention branch (func.py:258-275)."""
     a = p + "/dot_attention"
     qq = linear(P, a + "/q_map", x, q)
@@ -305,7 +348,7 @@ def cross_attention(c, P, p, x, memory, bias, cache=None, q_offset=0, fuse=None,
     if cache is not None:
         cache = dict(cache, mk=kk, mv=vv)
     o, _ = attention_core(c, P, a, heads_split(qq, c.h), heads_split(kk, c.h), heads_split(vv, c.h), bias,
-                          q_offset, q)
+                          q_offset, q, site)
     if fuse is not None:
         vq = linear(P, a + "/v_map", x, q)  # query projected with the cross-attention v_map (func.py:260)
         if cache is not None and "aan" in cache:
@@ -319,9 +362,11 @@ def cross_attention(c, P, p, x, memory, bias, cache=None, q_offset=0, fuse=None,
     return linear(P, a + "/o_map", o, q), cache
 
 
-def ffn(c, P, p, x, q=_ident):
+def ffn(c, P, p, x, q=_ident, site=None):
     """func.ffn_layer (func.py:327-338)."""
     hdn = q(torch.relu(x @ P[p + "/ffn_layer/enlarge/W_0_0"] + P[p + "/ffn_layer/enlarge/b_0"]))
+    if site is not None:
+        hdn = _drop(site + ".relu", hdn)
     return linear(P, p + "/ffn_layer/output", hdn, q)
 
 
@@ -342,13 +387,15 @@ def encoder(c, P, source, dtype=torch.float32, q=_ident):
     emb = P[s + ("/embedding" if c.share_st else "/src_embedding")]
     x = emb[source] * c.d ** 0.5 + P[s + "/bias"]
     x = q(x + timing_signal(x.shape[1], x.shape[2], dtype))
+    x = _drop("enc.emb", x)
     bias = mask_bias(mask, c.inf)
     for l in range(c.nenc):
         p = "%s/encoder/layer_%d" % (s, l)
-        y, _ = self_attention(c, P, p + "/self_attention", x, bias, q=q)
-        x = layer_norm(P, p + "/self_attention/layer_norm", x + y, c.eps, q)
-        y = ffn(c, P, p + "/feed_forward", x, q)
-        x = layer_norm(P, p + "/feed_forward/layer_norm", x + y, c.eps, q)
+        k = "enc%d" % l
+        y, _ = self_attention(c, P, p + "/self_attention", x, bias, q=q, site=k + ".self")
+        x = layer_norm(P, p + "/self_attention/layer_norm", x + _drop(k + ".self.ln.res", y), c.eps, q)
+        y = ffn(c, P, p + "/feed_forward", x, q, site=k + ".ffn")
+        x = layer_norm(P, p + "/feed_forward/layer_norm", x + _drop(k + ".ffn.ln.res", y), c.eps, q)
     return {"encodes": x, "mask": mask}
 
 
@@ -376,6 +423,7 @@ def decoder(c, P, target, state, time=None, smooth=None, dtype=torch.float32, q=
     if training:
         x = torch.nn.functional.pad(x, (0, 0, 1, 0))[:, :-1]
         x = q(x + timing_signal(x.shape[1], x.shape[2], dtype))
+        x = _drop("dec.emb", x)
     else:
         if bool((target == 0).all()):
             x = torch.zeros_like(x)
@@ -389,6 +437,7 @@ def decoder(c, P, target, state, time=None, smooth=None, dtype=torch.float32, q=
     for l in range(c.ndec):
         p = "%s/decoder/layer_%d" % (s, l)
         cache = None if training else dict(state["decoder"]["state"]["layer_%d" % l])
+        k = "dec%d" % l
         if c.aan:
             a = p + "/average_attention"
             if training:
@@ -402,26 +451,28 @@ def decoder(c, P, target, state, time=None, smooth=None, dtype=torch.float32, q=
                 xf = (x + cache["aan"]) / float(time + 1)
                 cache["aan"] = x + cache["aan"]
             xf = q(xf)
-            y = ffn(c, P, a, xf, q) if c.use_ffn else xf
+            y = ffn(c, P, a, xf, q, site=k + ".aan") if c.use_ffn else xf
             z = linear(P, a + "/z_project", torch.cat([x, y], -1), q)
             gi, gf = torch.split(z, c.d, -1)
             y = q(torch.sigmoid(gi) * x + torch.sigmoid(gf) * y)
-            x = layer_norm(P, a + "/layer_norm", x + y, c.eps, q)
-            y, cache = cross_attention(c, P, p + "/cross_attention", x, state["encodes"], mbias, cache, q_off, q=q)
-            x = layer_norm(P, p + "/cross_attention/layer_norm", x + y, c.eps, q)
+            x = layer_norm(P, a + "/layer_norm", x + _drop(k + ".aan.ln.res", y), c.eps, q)
+            y, cache = cross_attention(c, P, p + "/cross_attention", x, state["encodes"], mbias, cache, q_off, q=q,
+                                       site=k + ".cross")
+            x = layer_norm(P, p + "/cross_attention/layer_norm", x + _drop(k + ".cross.ln.res", y), c.eps, q)
         elif c.fuse:
             fuse = aan_matrix(mask, c.inf) if training else time
             y, cache = cross_attention(c, P, p + "/fuse_attention", x, state["encodes"], mbias, cache, q_off,
-                                       fuse=fuse, q=q)
-            x = layer_norm(P, p + "/fuse_attention/layer_norm", x + y, c.eps, q)
+                                       fuse=fuse, q=q, site=k + ".cross")
+            x = layer_norm(P, p + "/fuse_attention/layer_norm", x + _drop(k + ".cross.ln.res", y), c.eps, q)
         else:
             # decoder self-attention: causal bias only, no key-padding mask (models/transformer.py:136)
-            y, cache = self_attention(c, P, p + "/self_attention", x, cbias, cache, q_off, q)
-            x = layer_norm(P, p + "/self_attention/layer_norm", x + y, c.eps, q)
-            y, cache = cross_attention(c, P, p + "/cross_attention", x, state["encodes"], mbias, cache, q_off, q=q)
-            x = layer_norm(P, p + "/cross_attention/layer_norm", x + y, c.eps, q)
-        y = ffn(c, P, p + "/feed_forward", x, q)
-        x = layer_norm(P, p + "/feed_forward/layer_norm", x + y, c.eps, q)
+            y, cache = self_attention(c, P, p + "/self_attention", x, cbias, cache, q_off, q, site=k + ".self")
+            x = layer_norm(P, p + "/self_attention/layer_norm", x + _drop(k + ".self.ln.res", y), c.eps, q)
+            y, cache = cross_attention(c, P, p + "/cross_attention", x, state["encodes"], mbias, cache, q_off, q=q,
+                                       site=k + ".cross")
+            x = layer_norm(P, p + "/cross_attention/layer_norm", x + _drop(k + ".cross.ln.res", y), c.eps, q)
+        y = ffn(c, P, p + "/feed_forward", x, q, site=k + ".ffn")
+        x = layer_norm(P, p + "/feed_forward/layer_norm", x + _drop(k + ".ffn.ln.res", y), c.eps, q)
         if not training:
             new_layers["layer_%d" % l] = cache
     feat = x.reshape(-1, c.e)

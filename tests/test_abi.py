@@ -36,6 +36,15 @@ def test_ctypes_struct_sizes_match_header_layout():
     assert ctypes.sizeof(L.AdamArgs) == 5 * 8 + 8 + 5 * 4 + 4 + 8 + 8
 
 
+def test_mirrored_struct_layouts_match_the_library():
+    lib = ctypes.CDLL(L.LIB_PATH)
+    lib.zb_abi_struct_size.argtypes = [ctypes.c_int32]
+    lib.zb_abi_struct_size.restype = ctypes.c_int64
+    for which, cls in enumerate(L.STRUCTS):
+        assert lib.zb_abi_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.zb_abi_struct_size(99) == -1
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "_lib", None)
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))

@@ -1,0 +1,86 @@
+"""Host-side pieces (BLEU, batch indexers, Dataset batcher + leak buffer, vocab, LR schedules) against vectors
+produced by the reference's own modules (tests/golden/make_host_golden.py -> host_golden.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "host_golden.json")))
+
+
+def test_bleu_matches_reference_metric():
+    from zero_b200.evalu import bleu
+    for c in G["bleu"]:
+        got = bleu(c["cand"], c["refs"], bp=c["bp"], smooth=c["smooth"])
+        assert got == pytest.approx(c["bleu"], rel=1e-12, abs=1e-15), c
+    assert G["bleu"][-1]["bleu"] == pytest.approx(1.0)
+
+
+def test_indexers_match_reference():
+    from zero_b200.data import batch_indexer, token_indexer
+    for c in G["indexers"]:
+        assert token_indexer([tuple(l) for l in c["lens"]], c["token_size"]) == c["token_indexer"]
+        assert batch_indexer(len(c["lens"]), c["batch_size"]) == c["batch_indexer"]
+    assert token_indexer([], 10) == []
+
+
+def test_dataset_batcher_and_vocab_match_reference():
+    from zero_b200.data import Dataset, synthetic_corpus
+    from zero_b200.vocab import Vocab
+    b = G["batcher"]
+    corp = synthetic_corpus(n_train=b["n_train"], n_heldout=8, seed=b["corpus_seed"])
+    v = Vocab(tokens=corp["symbols"])
+    assert v.size() == b["vocab_size"]
+    assert v.to_id(["w3", "nope", "w10"]) == b["ids_w3"]
+    assert v.to_tokens([0, 1, 2, 3, 10 ** 6]) == ["<pad>", "<unk>", "<eos>", "w0", "<unk>"]
+    for run in b["runs"]:
+        ds = Dataset(corp["train_src"], corp["train_tgt"], v, v, max_len=b["max_len"], batch_or_token=run["mode"],
+                     data_leak_ratio=0.5)
+        np.random.seed(11)
+        for want in run["epochs"]:
+            got = list(ds.batcher(run["size"], buffer_size=run["buffer_size"], shuffle=run["shuffle"],
+                                  train=run["train"]))
+            assert len(got) == len(want), run["mode"]
+            for g, w in zip(got, want):
+                assert [int(i) for i in g["index"]] == w["index"]
+                assert g["src"].dtype == np.int32 and g["src"].tolist() == w["src"]
+                assert g["tgt"].tolist() == w["tgt"]
+
+
+def test_lr_schedules_match_reference():
+    from zero_b200 import lrs
+    from zero_b200.params import global_params
+    steps = (0, 1, 10, 399, 400, 401, 650, 900, 1199, 1500, 2500)
+    for key, want in G["lrs"].items():
+        name = key.replace("_tmult2", "")
+        p = global_params()
+        p.override_from_dict(dict(lrate_strategy=name, lrate=1.0, min_lrate=0.0, max_lrate=10.0, warmup_steps=400,
+                                  hidden_size=128, nstable=4, lrdecay_start=600, lrdecay_end=1200, lrate_decay=0.5,
+                                  lrate_patience=1, cosine_factor=2 if key.endswith("_tmult2") else 1,
+                                  cosine_period=500))
+        s = lrs.get_lr(p)
+        got = []
+        if name == "epoch":
+            for e in range(1, 5):
+                s.after_epoch(eidx=e)
+                got.append(s.get_lr())
+        elif name == "score":
+            for sc in (0.1, 0.2, 0.15, 0.18, 0.3, 0.3):
+                s.after_eval(sc)
+                got.append(s.get_lr())
+        else:
+            for t in steps:
+                s.step(t)
+                got.append(float(s.get_lr()))
+        assert got == pytest.approx(want, rel=1e-12), key
+    with pytest.raises(NotImplementedError):
+        p.lrate_strategy = "nope"
+        lrs.get_lr(p)
+
+
+def test_shard_for_rank_takes_every_nth_batch():
+    from zero_b200.data import shard_for_rank
+    assert list(shard_for_rank(range(7), 2, 0)) == [0, 2, 4]
+    assert list(shard_for_rank(range(7), 2, 1)) == [1, 3, 5]

@@ -53,3 +53,26 @@ def test_adam_tf_matches_closed_form():
     # first step: m = 0.05, v = 0.005, lr_t = 0.1*sqrt(0.02)/0.1
     want = 1.0 - 0.1 * (0.02 ** 0.5) / 0.1 * 0.05 / (0.005 ** 0.5 + 1e-8)
     assert abs(float(p1) - want) < 1e-6
+
+
+def test_dropout_hook_and_restated_keep_mask():
+    """DROP = None is the dropout-free model; with masks the loss moves; the restated keep function is a pure
+    function of (seed, site, index) with the requested rate."""
+    import numpy as np
+    keep = zo.dropout_keep(123, "enc0.ffn.relu", 200000, 0.25)
+    assert abs(float(keep.mean()) - 0.75) < 5e-3
+    assert (keep == zo.dropout_keep(123, "enc0.ffn.relu", 200000, 0.25)).all()
+    assert (keep[:1000] == zo.dropout_keep(123, "enc0.ffn.relu", 1000, 0.25)).all()
+    assert (keep != zo.dropout_keep(124, "enc0.ffn.relu", 200000, 0.25)).mean() > 0.2
+    assert (keep != zo.dropout_keep(123, "enc1.ffn.relu", 200000, 0.25)).mean() > 0.2
+    assert zo.dropout_keep(5, "x.res", 64, 0.0).all()
+    z, hp, variables, grads, vs, vt = load_golden("transformer")
+    c = zo.Cfg(hp, vs, vt)
+    src, tgt = torch.from_numpy(z["source"]).long(), torch.from_numpy(z["target"]).long()
+    base = float(zo.train_loss(c, variables, src, tgt)[0])
+    zo.DROP = zo.make_drop(77, {"emb": 0.1, "att": 0.1, "relu": 0.1, "res": 0.1})
+    try:
+        dropped = float(zo.train_loss(c, variables, src, tgt)[0])
+    finally:
+        zo.DROP = None
+    assert abs(base - float(z["loss"])) < 2e-5 and abs(dropped - base) > 1e-3

@@ -38,3 +38,16 @@ int num_sms() {
 extern "C" int zb_abi_version(void) { return ZB_ABI_VERSION; }
 extern "C" const char* zb_last_error_string(void) { return zb::g_err; }
 extern "C" int64_t zb_launch_count(void) { return zb::g_launches.load(); }
+extern "C" int64_t zb_abi_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(zb_gemm_args);
+    case 1: return sizeof(zb_attention_args);
+    case 2: return sizeof(zb_add_ln_args);
+    case 3: return sizeof(zb_embed_args);
+    case 4: return sizeof(zb_ce_args);
+    case 5: return sizeof(zb_adam_args);
+    case 6: return sizeof(zb_beam_args);
+    case 7: return sizeof(zb_colsum_args);
+    default: return -1;
+  }
+}

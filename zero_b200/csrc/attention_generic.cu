@@ -27,6 +27,29 @@ struct AttnP {
   int causal, q_offset, max_rel, relu_attn, kv_group;
   float scale, inf_value;
   float *lse, *delta, *d_rpr_k, *d_rpr_v;
+  float drop_rate;                        // attention dropout (func.py:245): 0 = off
+  uint32_t drop_site;
+  const unsigned long long* drop_seed;
+};
+
+// multiplier of attention weight (b, h, i, j) under dropout: 0 or 1 / keep
+struct DropCtx {
+  bool on;
+  uint64_t seed;
+  uint32_t site, thr;
+  float inv_keep;
+  __device__ __forceinline__ explicit DropCtx(const AttnP& p) {
+    on = p.drop_seed != nullptr && p.drop_rate > 0.f;
+    seed = on ? *p.drop_seed : 0ull;
+    site = p.drop_site;
+    thr = dropout_threshold(p.drop_rate);
+    inv_keep = on ? 1.f / (1.f - p.drop_rate) : 1.f;
+  }
+  __device__ __forceinline__ float mul(const AttnP& p, int b, int h, int i, int j) const {
+    if (!on) return 1.f;
+    const uint64_t idx = (((uint64_t)b * p.heads + h) * p.lq + i) * (uint64_t)p.lk + j;
+    return dropout_mul(seed, site, idx, thr, inv_keep);
+  }
 };
 
 __device__ __forceinline__ float wsum(float v) {
@@ -95,6 +118,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_generic(const Att
 #pragma unroll
   for (int dd = 0; dd < ND; ++dd) o[dd] = 0.f;
   const int i_abs = i + p.q_offset;
+  const DropCtx drop(p);
 
   for (int kt = 0; kt < p.lk; kt += 32) {
     __syncthreads();
@@ -128,6 +152,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_fwd_generic(const Att
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) o[dd] *= corr;
     }
+    // dropout acts on the normalised weights (the 1 / l is applied at the end), not on the normaliser
+    if (inb) pj *= drop.mul(p, b, h, i, j);
 #pragma unroll 4
     for (int jj = 0; jj < 32; ++jj) {
       const float pv = __shfl_sync(0xffffffffu, pj, jj);
@@ -206,6 +232,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const 
     if (lane == 0) p.delta[li] = delta;
   }
   const int i_abs = i + p.q_offset;
+  const DropCtx drop(p);
   for (int kt = 0; kt < p.lk; kt += 32) {
     __syncthreads();
     const int valid_rows = min(32, p.lk - kt);
@@ -231,6 +258,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const 
       }
     }
     const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
+    const float dm = inb ? drop.mul(p, b, h, i, j) : 0.f;
+    dp *= dm;  // gradient wrt the undropped weight
     float pj, ds;
     if (p.relu_attn) {
       pj = valid ? fmaxf(s, 0.f) : 0.f;
@@ -240,6 +269,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dq_generic(const 
       pj = inb ? __expf(sm_ - lse) : 0.f;
       ds = pj * (dp - delta);
     }
+    pj *= dm;  // the dropped weight is what multiplied the values
 #pragma unroll 4
     for (int jj = 0; jj < 32; ++jj) {
       const float dsv = __shfl_sync(0xffffffffu, ds, jj);
@@ -313,6 +343,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dkv_generic(const
 #pragma unroll
   for (int dd = 0; dd < ND; ++dd) dk[dd] = dv[dd] = 0.f;
   const bool key_ok = j < kl;
+  const DropCtx drop(p);
   for (int qt = 0; qt < p.lq; qt += 32) {
     __syncthreads();
     const int valid_rows = min(32, p.lq - qt);
@@ -343,6 +374,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dkv_generic(const
       dp += sm.b[lane][d] * vv;
     }
     const bool valid = inb && key_ok && (!p.causal || j <= i_abs);
+    const float dm = inb ? drop.mul(p, b, h, i, j) : 0.f;
+    dp *= dm;
     float pj, ds;
     if (p.relu_attn) {
       pj = valid ? fmaxf(s, 0.f) : 0.f;
@@ -352,6 +385,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1) attn_bwd_dkv_generic(const
       pj = inb ? __expf(sm_ - sm.aux0[lane]) : 0.f;
       ds = pj * (dp - sm.aux1[lane]);
     }
+    pj *= dm;
 #pragma unroll 4
     for (int ii = 0; ii < 32; ++ii) {
       const float pv = __shfl_sync(0xffffffffu, pj, ii);
@@ -396,6 +430,8 @@ static AttnP to_params(const zb_attention_args* a) {
   p.kv_group = a->kv_group > 0 ? a->kv_group : 1;
   p.scale = a->scale; p.inf_value = a->inf_value;
   p.lse = a->lse; p.delta = a->delta; p.d_rpr_k = a->d_rpr_k; p.d_rpr_v = a->d_rpr_v;
+  p.drop_rate = a->dropout_seed ? a->dropout_rate : 0.f; p.drop_site = a->dropout_site;
+  p.drop_seed = reinterpret_cast<const unsigned long long*>(a->dropout_seed);
   return p;
 }
 

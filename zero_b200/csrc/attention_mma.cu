@@ -30,6 +30,33 @@ struct Params {
   const int32_t* key_len;
   float scale, inf_value;
   float *lse, *delta;
+  float drop_rate;  // attention dropout (func.py:245); the kernels are instantiated with DROP = true when > 0
+  uint32_t drop_site;
+  const unsigned long long* drop_seed;
+};
+
+// Dropout multiplier (0 or 1 / keep) of attention weight (query row i, key j) of one (batch, head): the same pure
+// function of (*seed, site, flat index into [batch, heads, lq, lk]) in every forward / backward kernel.
+template <bool DROP>
+struct Drop {
+  uint64_t seed, base;
+  uint32_t site, thr;
+  float inv_keep;
+  int lk;
+  __device__ __forceinline__ Drop(const Params& p, int b, int h) {
+    if (DROP) {
+      seed = *p.drop_seed;
+      base = ((uint64_t)b * p.heads + h) * (uint64_t)p.lq;
+      site = p.drop_site;
+      thr = dropout_threshold(p.drop_rate);
+      inv_keep = 1.f / (1.f - p.drop_rate);
+      lk = p.lk;
+    }
+  }
+  __device__ __forceinline__ float mul(int i, int j) const {
+    if (!DROP) return 1.f;
+    return dropout_mul(seed, site, (base + i) * (uint64_t)lk + j, thr, inv_keep);
+  }
 };
 
 __device__ __forceinline__ int swz(int r, int c) { return r * 64 + ((((c >> 3) ^ (r & 7)) << 3) | (c & 7)); }
@@ -144,11 +171,13 @@ __device__ __forceinline__ void store_c_bf16(__nv_bfloat16* base, long long ld, 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+template <bool DROP>
 __global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
   grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const Drop<DROP> drop(p, b, h);
   const int kb = b / p.kv_group;
   const int kl = p.key_len ? p.key_len[kb] : p.lk;
   const __nv_bfloat16* qb = p.q + (long long)b * p.bsq + (long long)q0 * p.ldq + h * DH;
@@ -205,8 +234,8 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float pv = __expf(s[nt][j] - m[j >> 1]);
-        s[nt][j] = pv;
-        l[j >> 1] += pv;
+        l[j >> 1] += pv;  // the normaliser sums the undropped weights
+        s[nt][j] = pv * drop.mul(q0 + warp * 16 + g + (j >> 1) * 8, kt + nt * 8 + 2 * t + (j & 1));
         o[nt][j] *= corr[j >> 1];
       }
     uint32_t pa[4][4];
@@ -225,11 +254,13 @@ __global__ void __launch_bounds__(NT) fwd_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dq
+template <bool DROP>
 __global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
   grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sK[64 * 64], sV[64 * 64];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const Drop<DROP> drop(p, b, h);
   const int kl = p.key_len ? p.key_len[b] : p.lk;
   const int rows = p.lq - q0;
   uint32_t qa[4][4], doa[4][4];
@@ -294,7 +325,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
         float v = s[nt][j] * p.scale;
         v = valid ? v : v - p.inf_value;
         const float pv = inb ? __expf(v - lse[j >> 1]) : 0.f;
-        s[nt][j] = pv * (dp[nt][j] - delta[j >> 1]);
+        s[nt][j] = pv * (dp[nt][j] * drop.mul(r0 + (j >> 1) * 8, col) - delta[j >> 1]);
       }
     uint32_t dsa[4][4];
     c_to_a(dsa, s);
@@ -305,12 +336,14 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ backward: dk, dv
+template <bool DROP>
 __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const Params p) {
   grid_dep_wait();
   __shared__ __align__(128) __nv_bfloat16 sQ[64 * 64], sDO[64 * 64];
   __shared__ float sLse[64], sDelta[64];
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BK;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const Drop<DROP> drop(p, b, h);
   const int kl = p.key_len ? p.key_len[b] : p.lk;
   const int krows = p.lk - k0;
   uint32_t ka[4][4], va[4][4];
@@ -358,8 +391,9 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(const Params p) {
         float v = st[nt][j] * p.scale;
         v = valid ? v : v - p.inf_value;
         const float pv = inb ? __expf(v - sLse[qi]) : 0.f;
-        st[nt][j] = pv;
-        dpt[nt][j] = pv * (dpt[nt][j] - sDelta[qi]);
+        const float dm = drop.mul(qt + qi, key);
+        st[nt][j] = pv * dm;
+        dpt[nt][j] = pv * (dpt[nt][j] * dm - sDelta[qi]);
       }
     uint32_t pa[4][4], dsa[4][4];
     c_to_a(pa, st);
@@ -395,6 +429,7 @@ struct Tile64Bwd {
 // These kernels are latency-bound per warp (ncu: 2 warps / scheduler, 26 % issue slots used), so they are sized for
 // residency rather than prefetch: one tile set per CTA (24 / 41 KB), <= 128 registers, 4 CTAs per SM; at batch 64 x 8
 // heads every (batch, head) item of the step is resident at once.
+template <bool DROP>
 __global__ void __launch_bounds__(NT, 4) fwd64_kernel(const Params p, const int items) {
   grid_dep_wait();
   extern __shared__ __align__(128) uint8_t smem64[];
@@ -406,6 +441,7 @@ __global__ void __launch_bounds__(NT, 4) fwd64_kernel(const Params p, const int 
     load_tile(T.k, p.k + (long long)b * p.bsk + h * DH, p.ldk, p.lk);
     load_tile(T.v, p.v + (long long)b * p.bsv + h * DH, p.ldv, p.lk);
     cp_async_commit();
+    const Drop<DROP> drop(p, b, h);
     cp_async_wait<0>();
     __syncthreads();
     const int kl = p.key_len ? p.key_len[b] : p.lk;
@@ -439,8 +475,8 @@ __global__ void __launch_bounds__(NT, 4) fwd64_kernel(const Params p, const int 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float pv = __expf(s[nt][j] - ((j >> 1) ? m1 : m0));
-        s[nt][j] = pv;
         if (j >> 1) l1 += pv; else l0 += pv;
+        s[nt][j] = pv * drop.mul(warp * 16 + g + (j >> 1) * 8, nt * 8 + 2 * t + (j & 1));
       }
     uint32_t pa[4][4];
     c_to_a(pa, s);
@@ -458,6 +494,7 @@ __global__ void __launch_bounds__(NT, 4) fwd64_kernel(const Params p, const int 
   }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int items) {
   grid_dep_wait();
   extern __shared__ __align__(128) uint8_t smem64[];
@@ -481,6 +518,7 @@ __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int 
       }
     }
     cp_async_commit();
+    const Drop<DROP> drop(p, b, h);
     cp_async_wait<0>();
     __syncthreads();
     const int kl = p.key_len ? p.key_len[b] : p.lk;
@@ -530,7 +568,7 @@ __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int 
           float v = s[nt][j] * p.scale;
           v = valid ? v : v - p.inf_value;
           const float pv = inb ? __expf(v - ((j >> 1) ? lse1 : lse0)) : 0.f;
-          s[nt][j] = pv * (dp[nt][j] - delta[j >> 1]);
+          s[nt][j] = pv * (dp[nt][j] * drop.mul(r0 + (j >> 1) * 8, col) - delta[j >> 1]);
         }
       uint32_t dsa[4][4];
       c_to_a(dsa, s);
@@ -561,8 +599,9 @@ __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int 
           float v = st[nt][j] * p.scale;
           v = valid ? v : v - p.inf_value;
           const float pv = inb ? __expf(v - T.lse[qi]) : 0.f;
-          st[nt][j] = pv;
-          dpt[nt][j] = pv * (dpt[nt][j] - sDelta[qi]);
+          const float dm = drop.mul(qi, key);
+          st[nt][j] = pv * dm;
+          dpt[nt][j] = pv * (dpt[nt][j] * dm - sDelta[qi]);
         }
       uint32_t pa[4][4], dsa[4][4];
       c_to_a(pa, st);
@@ -593,6 +632,9 @@ static Params to_params(const zb_attention_args* a) {
   p.heads = a->heads; p.lq = a->lq; p.lk = a->lk; p.causal = a->causal; p.q_offset = a->q_offset;
   p.kv_group = a->kv_group > 0 ? a->kv_group : 1;
   p.key_len = a->key_len; p.scale = a->scale; p.inf_value = a->inf_value; p.lse = a->lse; p.delta = a->delta;
+  p.drop_rate = (a->dropout_seed && a->dropout_rate > 0.f) ? a->dropout_rate : 0.f;
+  p.drop_site = a->dropout_site;
+  p.drop_seed = reinterpret_cast<const unsigned long long*>(a->dropout_seed);
   return p;
 }
 
@@ -623,43 +665,52 @@ static bool tile64_ok(const zb_attention_args* a) {
 
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
+  const bool drop = p.drop_rate > 0.f;
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
     const int smem = (int)sizeof(fa::Tile64Fwd);
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(fa::fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(fa::fwd64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(fa::fwd64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       attr = true;
     }
     const int grid = items < 8 * num_sms() ? items : 8 * num_sms();
-    ZB_LAUNCH(fa::fwd64_kernel, grid, fa::NT, smem, st, p, items);
+    if (drop) ZB_LAUNCH(fa::fwd64_kernel<true>, grid, fa::NT, smem, st, p, items);
+    else ZB_LAUNCH(fa::fwd64_kernel<false>, grid, fa::NT, smem, st, p, items);
     return check_launch("zb_attention_fwd(tile64)");
   }
   const dim3 grid((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
-  ZB_LAUNCH(fa::fwd_kernel, grid, fa::NT, 0, st, p);
+  if (drop) ZB_LAUNCH(fa::fwd_kernel<true>, grid, fa::NT, 0, st, p);
+  else ZB_LAUNCH(fa::fwd_kernel<false>, grid, fa::NT, 0, st, p);
   return check_launch("zb_attention_fwd(mma)");
 }
 
 int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
+  const bool drop = p.drop_rate > 0.f;
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
     const int smem = (int)sizeof(fa::Tile64Bwd);
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(fa::bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(fa::bwd64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(fa::bwd64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       attr = true;
     }
     const int grid = items < 4 * num_sms() ? items : 4 * num_sms();
-    ZB_LAUNCH(fa::bwd64_kernel, grid, fa::NT, smem, st, p, items);
+    if (drop) ZB_LAUNCH(fa::bwd64_kernel<true>, grid, fa::NT, smem, st, p, items);
+    else ZB_LAUNCH(fa::bwd64_kernel<false>, grid, fa::NT, smem, st, p, items);
     return check_launch("zb_attention_bwd(tile64)");
   }
   const dim3 gq((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
   const dim3 gk((a->lk + fa::BK - 1) / fa::BK, a->heads, a->batch);
-  ZB_LAUNCH(fa::bwd_dq_kernel, gq, fa::NT, 0, st, p);
+  if (drop) ZB_LAUNCH(fa::bwd_dq_kernel<true>, gq, fa::NT, 0, st, p);
+  else ZB_LAUNCH(fa::bwd_dq_kernel<false>, gq, fa::NT, 0, st, p);
   int rc = check_launch("zb_attention_bwd(mma dq)");
   if (rc) return rc;
-  ZB_LAUNCH(fa::bwd_dkv_kernel, gk, fa::NT, 0, st, p);
+  if (drop) ZB_LAUNCH(fa::bwd_dkv_kernel<true>, gk, fa::NT, 0, st, p);
+  else ZB_LAUNCH(fa::bwd_dkv_kernel<false>, gk, fa::NT, 0, st, p);
   return check_launch("zb_attention_bwd(mma dkv)");
 }
 

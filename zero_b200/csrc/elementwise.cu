@@ -136,6 +136,61 @@ __global__ void __launch_bounds__(256) colsum_vec_group_kernel(const ColsumGroup
   colsum_vec_body(g.x[z], g.m[z], g.nvec[z], g.ld[z], g.out[z], g.rows_pb[z], blockIdx.x, blockIdx.y);
 }
 
+// out = dropout(x (+ x2)): 8 elements per thread (two mask hashes), 16-byte accesses when aligned.
+__global__ void __launch_bounds__(256)
+dropout_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x2, __nv_bfloat16* out, long long n,
+               float rate, const unsigned long long* __restrict__ seed_p, uint32_t site) {
+  grid_dep_wait();
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i0 >= n) return;
+  const uint64_t seed = *seed_p;
+  const uint32_t thr = dropout_threshold(rate);
+  const float inv_keep = 1.f / (1.f - rate);
+  const bool vec = i0 + 8 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                                    reinterpret_cast<uintptr_t>(x2)) & 15) == 0;
+  float f[8];
+  if (vec) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + i0);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16x2(w[e]);
+      f[2 * e] = t.x;
+      f[2 * e + 1] = t.y;
+    }
+    if (x2) {
+      const uint4 u2 = *reinterpret_cast<const uint4*>(x2 + i0);
+      const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_bf16x2(w2[e]);
+        f[2 * e] += t.x;
+        f[2 * e + 1] += t.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      f[e] = i0 + e < n ? __bfloat162float(x[i0 + e]) : 0.f;
+      if (x2 && i0 + e < n) f[e] += __bfloat162float(x2[i0 + e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] *= dropout_mul(seed, site, (uint64_t)(i0 + e), thr, inv_keep);
+  if (vec) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + i0) = o;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (i0 + e < n) out[i0 + e] = __float2bfloat16(f[e]);
+  }
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   grid_dep_wait();
   __shared__ float red[8];
@@ -326,6 +381,17 @@ extern "C" int zb_cast_bf16_f32(const void* src, float* dst, int64_t n, zb_strea
   if (n == 0) return ZB_OK;
   ZB_LAUNCH(cast_bf16_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)src, dst, n);
   return check_launch("zb_cast_bf16_f32");
+}
+extern "C" int zb_dropout(const void* x, const void* x2, void* out, int64_t n, float rate, const uint64_t* seed,
+                          uint32_t site, zb_stream_t stream) {
+  ZB_REQUIRE(x && out && seed && n >= 0, "zb_dropout: null pointer");
+  ZB_REQUIRE(rate >= 0.f && rate < 1.f, "zb_dropout: rate must be in [0, 1) (got %g)", (double)rate);
+  if (n == 0) return ZB_OK;
+  const long long threads = (n + 7) / 8;
+  ZB_LAUNCH(dropout_kernel, (unsigned)((threads + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)x,
+            (const __nv_bfloat16*)x2, (__nv_bfloat16*)out, (long long)n, rate,
+            reinterpret_cast<const unsigned long long*>(seed), site);
+  return check_launch("zb_dropout");
 }
 extern "C" int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream) {
   ZB_REQUIRE(x && out && m >= 0 && n > 0 && ld % 2 == 0, "zb_colsum: bad args");

@@ -41,6 +41,31 @@ __device__ __forceinline__ void grid_dep_wait() {
 #endif
 }
 
+// ---------------------------------------------------------------- dropout (counter-based mask)
+// tf.nn.dropout (utils/util.py:75-79) keeps an element with probability 1 - rate and scales it by 1 / (1 - rate).
+// The keep decision is a pure function of (seed, site, flat element index), so forward and backward kernels
+// regenerate the same mask and nothing is stored: one splitmix64 hash per 4 consecutive elements, 16 bits each,
+// keep iff bits >= round(rate * 65536).  `seed` lives in device memory (one value per optimizer step, so CUDA-graph
+// replays see a fresh mask); `site` distinguishes the dropout call sites of the model.
+__device__ __forceinline__ uint64_t dropout_hash4(uint64_t seed, uint32_t site, uint64_t idx4) {
+  uint64_t z = seed + (uint64_t)site * 0x9E3779B97F4A7C15ull + idx4 * 0xD1B54A32D192ED03ull;
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float rate) {
+  const float t = rate * 65536.f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : (uint32_t)t);
+}
+// multiplier of element `idx`: 0 (dropped) or inv_keep
+__device__ __forceinline__ float dropout_mul(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thr, float inv_keep) {
+  const uint32_t bits = (uint32_t)(dropout_hash4(seed, site, idx >> 2) >> (16 * (idx & 3))) & 0xFFFFu;
+  return bits >= thr ? inv_keep : 0.f;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

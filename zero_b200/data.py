@@ -7,7 +7,7 @@
 * `shard_for_rank` — the reference feeds `len(gpus)` consecutive batches to the towers of one step
   (main.py:268-273); with one process per GPU, rank r of N takes batch N * step + r.
 * `synthetic_corpus` — BASELINE.json configs[0] / SURVEY.md 8(d) C1: a learnable token transduction over a 1k
-  vocabulary (256 training pairs + 64 held-out).
+  vocabulary (256 training pairs + 64 held-out, none of which is a training sentence).
 
 Batches are numpy int32 matrices; `pin()` turns one into pinned torch tensors for the H2D copy of a step.
 """
@@ -151,30 +151,39 @@ def pin(data):
     return s, t
 
 
-def synthetic_corpus(n_train=256, n_heldout=64, n_symbols=997, min_len=4, max_len=24, zipf=1.1, seed=1234):
-    """C1 of SURVEY.md 8(d): symbols w0..w{n-1}; source length ~U[min_len, max_len], tokens ~Zipf(zipf); the target
-    is a fixed token substitution (a permutation of the symbol set) of the reversed second half followed by the
-    first half, so there is something to attend to; held-out sources only use symbols seen in training."""
+def synthetic_corpus(n_train=256, n_heldout=64, n_symbols=997, min_len=4, max_len=24, zipf=1.1, seed=1234,
+                     active_symbols=40, swap_pairs=False):
+    """C1 of SURVEY.md 8(d): a 1k vocabulary (3 specials + symbols w0..w{n-1}); source length ~U[min_len, max_len],
+    tokens ~Zipf(zipf) over the `active_symbols` most frequent symbols (so 256 sentences cover every symbol many
+    times and the held-out set measures generalisation, not vocabulary coverage); the target is a fixed token
+    substitution (a permutation of the whole symbol set) of the source, optionally with every adjacent pair swapped
+    (local reordering) — a lexical mapping plus positional alignment that a 2-layer model learns, and generalises,
+    within about a thousand updates."""
     rng = np.random.RandomState(seed)
     symbols = ["w%d" % i for i in range(n_symbols)]
     perm = rng.permutation(n_symbols)
-    p = 1.0 / np.arange(1, n_symbols + 1) ** zipf
+    k = min(active_symbols, n_symbols)
+    p = 1.0 / np.arange(1, k + 1) ** zipf
     p /= p.sum()
 
     def transduce(ids):
-        h = len(ids) // 2
-        return [int(perm[i]) for i in (list(reversed(ids[h:])) + ids[:h])]
+        out = list(ids)
+        if swap_pairs:
+            for i in range(0, len(out) - 1, 2):
+                out[i], out[i + 1] = out[i + 1], out[i]
+        return [int(perm[i]) for i in out]
 
-    def draw(allowed=None):
+    def draw():
         n = int(rng.randint(min_len, max_len + 1))
-        while True:
-            ids = [int(i) for i in rng.choice(n_symbols, size=n, p=p)]
-            if allowed is None or all(i in allowed for i in ids):
-                return ids
+        return [int(i) for i in rng.choice(k, size=n, p=p)]
 
     train = [draw() for _ in range(n_train)]
-    seen = set(i for s in train for i in s)
-    held = [draw(seen) for _ in range(n_heldout)]
+    seen = set(tuple(s) for s in train)
+    held = []
+    while len(held) < n_heldout:
+        s = draw()
+        if tuple(s) not in seen:
+            held.append(s)
 
     def text(rows):
         return [[symbols[i] for i in r] for r in rows]

@@ -14,6 +14,7 @@ is projected by one GEMM; their TF names are strided views into the fused tensor
 from __future__ import annotations
 
 import math
+import zlib
 from collections import OrderedDict
 
 import torch
@@ -284,6 +285,12 @@ class Workspace(object):
         return t
 
 
+def dropout_site(name):
+    """32-bit id of a dropout call site (the `site` argument of zb_dropout / zb_attention): crc32 of its name,
+    e.g. "enc0.self.att", "enc0.self.ln.res", "enc0.ffn.relu", "enc.emb"."""
+    return zlib.crc32(name.encode("ascii")) & 0xFFFFFFFF
+
+
 def _lens(ids):
     """Number of leading non-pad tokens per row; the reference's masks are `id != 0` (models/transformer.py:16)."""
     return (ids != 0).sum(1).to(torch.int32)
@@ -309,6 +316,36 @@ class Engine(object):
         self.ps = ParamStore(self.cfg, self.device)
         self.ws = Workspace(self.device)
         self.step_count = 0
+        # dropout (utils/util.py:75-79), applied only inside the training step; score / infer close it
+        # (util.closing_dropout, utils/util.py:106-114).  The seed lives on the device so that CUDA-graph replays of
+        # the step see a new mask each time; the trainer advances it once per micro-batch.
+        self.rates = {"emb": float(_hp(hp, "dropout", 0.0) or 0.0),
+                      "att": float(_hp(hp, "attention_dropout", 0.0) or 0.0),
+                      "relu": float(_hp(hp, "relu_dropout", 0.0) or 0.0),
+                      "res": float(_hp(hp, "residual_dropout", 0.0) or 0.0)}
+        for k, r in self.rates.items():
+            if not 0.0 <= r < 1.0:
+                raise L.ZeroB200Error("%s dropout rate %r outside [0, 1)" % (k, r))
+        self._training = False
+        seed0 = (int(_hp(hp, "random_seed", 1234)) * 0x9E3779B97F4A7C15 + 0x1234567) % (1 << 62)
+        self.drop_seed = torch.tensor([seed0], dtype=torch.int64, device=self.device)
+
+    # ================================================================================== dropout state
+    def _rate(self, kind):
+        return self.rates[kind] if self._training else 0.0
+
+    def set_dropout_seed(self, value):
+        self.drop_seed.fill_(int(value) % (1 << 62))
+
+    def advance_dropout_seed(self):
+        """New masks for the next micro-batch (a device-side increment: legal between CUDA-graph replays)."""
+        if any(self.rates.values()):
+            self.drop_seed.add_(1)
+
+    def _queue_colsum(self, dy, db):
+        if not hasattr(self, "_wg"):
+            self._wg, self._cs = [], []
+        self._cs.append((dy, db))
 
     # ================================================================================== side stream
     # Weight-gradient work (wgrad GEMMs + bias column sums) only writes the gradient arena, so it runs on a
@@ -382,7 +419,8 @@ class Engine(object):
                                key_len=key_len, causal=causal, inf_value=c.inf, lse=lse,
                                rpr_k=ps.w(key + ".rpr_k") if c.rpr else None,
                                rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
-                               relu_attn=c.rela)
+                               relu_attn=c.rela,
+                               dropout=(self._rate("att"), dropout_site(key + ".att"), self.drop_seed))
         ops.attention_fwd(a)
         feed = self._post_fwd(key, ctx, N, sv, tag)
         y = ws.get(tag + ".y", (N, c.d))
@@ -423,7 +461,8 @@ class Engine(object):
                                key_len=src_len, causal=False, inf_value=c.inf, lse=lse,
                                rpr_k=ps.w(key + ".rpr_k") if c.rpr else None,
                                rpr_v=ps.w(key + ".rpr_v") if c.rpr else None, max_rel=c.max_rel,
-                               relu_attn=c.rela)
+                               relu_attn=c.rela,
+                               dropout=(self._rate("att"), dropout_site(key + ".att"), self.drop_seed))
         ops.attention_fwd(a)
         feed = self._post_fwd(key, ctx, N, sv, tag)
         y = ws.get(tag + ".y", (N, c.d))
@@ -477,16 +516,20 @@ class Engine(object):
         c, ps, ws = self.cfg, self.ps, self.ws
         h = ws.get(tag + ".h", (N, c.f))
         ops.linear_fwd(x, ps.w(key + ".w1.W"), ps.p(key + ".w1.b"), h, relu=True)
+        r = self._rate("relu")
+        if r > 0.0:   # func.py:334; dropped and relu-inactive units are both exact zeros of h afterwards
+            ops.dropout(h, h, r, self.drop_seed, dropout_site(key + ".relu"))
         y = ws.get(tag + ".y", (N, c.d))
         ops.linear_fwd(h, ps.w(key + ".w2.W"), ps.p(key + ".w2.b"), y)
-        sv.update(h=h, y=y)
+        sv.update(h=h, y=y, relu_rate=r)
         return y
 
     def _ffn_bwd(self, key, x, dy, N, sv, tag):
         c, ps, ws = self.cfg, self.ps, self.ws
         self._wgrad(sv["h"], dy, ps.g(key + ".w2.W"))  # w2.b: summed by the LN backward
         dh = ws.get(tag + ".dh", (N, c.f))
-        ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"])
+        # h > 0 is the relu AND the dropout mask; the kept units carry the 1 / keep scale
+        ops.linear_dgrad(dy, ps.w(key + ".w2.W"), dh, relu_mask=sv["h"], alpha=1.0 / (1.0 - sv.get("relu_rate", 0.0)))
         self._wgrad(x, dh, ps.g(key + ".w1.W"), ps.g(key + ".w1.b"))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dh, ps.w(key + ".w1.W"), dx)
@@ -497,17 +540,29 @@ class Engine(object):
         out = ws.get(tag + ".out", (N, c.d))
         mean = ws.get(tag + ".mean", (N,), f32)
         rstd = ws.get(tag + ".rstd", (N,), f32)
+        r = self._rate("res")
+        if r > 0.0:   # func.residual_fn: x + dropout(y) (func.py:321-324); y is replaced by its dropped version
+            ops.dropout(y, y, r, self.drop_seed, dropout_site(key + ".res"))
         ops.add_ln_fwd(x, y, out, ps.p(key + ".scale"), ps.p(key + ".offset"), mean, rstd, c.eps)
-        sv.update(x=x, y=y, mean=mean, rstd=rstd)
+        sv.update(x=x, y=y, mean=mean, rstd=rstd, res_rate=r, res_site=dropout_site(key + ".res"))
         return out
 
     def _ln_bwd(self, key, d_out, d_out2, N, sv, tag, dbias=None):
-        """dbias: gradient slot of the bias of the linear layer that produced y (its column sum rides along)."""
+        """Returns (ds, dy): ds = gradient wrt the sum x + y, i.e. wrt the skip input x; dy = gradient wrt the branch
+        output y (the same tensor unless residual dropout is on, then its masked / rescaled copy).
+        dbias: gradient slot of the bias of the linear layer that produced y (the column sum of dy)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         ds = ws.get(tag + ".ds", (N, c.d))
+        r = sv.get("res_rate", 0.0)
         ops.add_ln_bwd(sv["x"], sv["y"], d_out, d_out2, sv["mean"], sv["rstd"], ps.p(key + ".scale"), ds,
-                       ps.g(key + ".scale"), ps.g(key + ".offset"), dbias)
-        return ds
+                       ps.g(key + ".scale"), ps.g(key + ".offset"), dbias if r == 0.0 else None)
+        if r == 0.0:
+            return ds, ds
+        dy = ws.get(tag + ".dyb", (N, c.d))
+        ops.dropout(ds, dy, r, self.drop_seed, sv["res_site"])
+        if dbias is not None:
+            self._queue_colsum(dy, dbias)
+        return ds, dy
 
     # ================================================================================== encoder
     def encode(self, source, save=None, tag="E"):
@@ -518,6 +573,9 @@ class Engine(object):
         src_len = _lens(source)
         x = ws.get(tag + ".x0", (N, c.d))
         ops.embed_fwd(source, ps.w("src_emb"), ps.p("emb_bias"), x, mult=c.d ** 0.5)
+        r_emb = self._rate("emb")
+        if r_emb > 0.0:   # models/transformer.py:33
+            ops.dropout(x, x, r_emb, self.drop_seed, dropout_site("enc.emb"))
         layers = []
         for l in range(c.nenc):
             key, t = "enc%d" % l, "%s.L%d" % (tag, l)
@@ -529,7 +587,7 @@ class Engine(object):
             sv["x1"] = x1
             layers.append(sv)
         if save is not None:
-            save.update(layers=layers, source=source, src_len=src_len, B=B, S=S)
+            save.update(layers=layers, source=source, src_len=src_len, B=B, S=S, emb_rate=r_emb)
         return x, src_len
 
     def encode_bwd(self, d_enc, save, tag="E"):
@@ -542,13 +600,22 @@ class Engine(object):
             key, bw = "enc%d" % l, "%s.bw%d" % (tag, l & 1)   # backward temporaries: two sets, by layer parity
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
-            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], ds2, N, sv["ffn"], bw + ".ffn")
-            ds1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
-            dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, S, sv["att"], bw + ".att")
+            ds2, dy2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
+            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], dy2, N, sv["ffn"], bw + ".ffn")
+            ds1, dy1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
+            dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, S, sv["att"], bw + ".att")
             self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
+        d1, d2 = self._embed_dropout_bwd(d1, d2, save.get("emb_rate", 0.0), "enc.emb", tag)
         ops.embed_bwd(save["source"], d1, ps.g("src_emb"), ps.g("emb_bias"), mult=c.d ** 0.5, d_out2=d2)
+
+    def _embed_dropout_bwd(self, d1, d2, rate, site, tag):
+        """Gradient through the embedding dropout: the two addends are summed, masked and rescaled in one pass."""
+        if rate == 0.0:
+            return d1, d2
+        d = self.ws.get(tag + ".demb", tuple(d1.shape))
+        ops.dropout(d1, d, rate, self.drop_seed, dropout_site(site), x2=d2)
+        return d, None
 
     # ================================================================================== decoder (training)
     def _tgt_table(self):
@@ -569,6 +636,9 @@ class Engine(object):
         N = B * T
         x = ws.get(tag + ".x0", (N, c.d))
         ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x, mult=c.d ** 0.5, shift=1)
+        r_emb = self._rate("emb")
+        if r_emb > 0.0:   # models/transformer.py:119
+            ops.dropout(x, x, r_emb, self.drop_seed, dropout_site("dec.emb"))
         layers = []
         for l in range(c.ndec):
             key, t = "dec%d" % l, "%s.L%d" % (tag, l)
@@ -593,7 +663,8 @@ class Engine(object):
         ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
                        loss_scale=c.loss_scale)
         if save is not None:
-            save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc)
+            save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
+                        emb_rate=r_emb)
         return loss, per_sample, logits
 
     def decode_train_bwd(self, save, d_enc_f32, tag="D"):
@@ -617,18 +688,21 @@ class Engine(object):
             key, bw = "dec%d" % l, "%s.bw%d" % (tag, l & 1)
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
-            ds2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
-            dxc = self._ffn_bwd(key + ".ffn", sv["xc"], ds2, N, sv["ffn"], bw + ".ffn")
+            ds2, dy2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
+            dxc = self._ffn_bwd(key + ".ffn", sv["xc"], dy2, N, sv["ffn"], bw + ".ffn")
             if c.aan or c.fuse:
                 d1, d2 = self._avg_layer_bwd(key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save)
             else:
-                dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
-                dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"],
+                dsc, dyc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc",
+                                        ps.g(key + ".cross.o.b"))
+                dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dyc, d_enc_f32, B, T, S, sv["cross"],
                                            bw + ".cross")
-                ds1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
-                dx = self._self_attn_bwd(key + ".self", sv["x_in"], ds1, B, T, sv["att"], bw + ".att")
+                ds1, dy1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1",
+                                        ps.g(key + ".self.o.b"))
+                dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, T, sv["att"], bw + ".att")
                 d1, d2 = ds1, dx
             self._side_layer_end(tag, l)
+        d1, d2 = self._embed_dropout_bwd(d1, d2, save.get("emb_rate", 0.0), "dec.emb", tag)
         ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
 
     # ================================================================================== public steps
@@ -658,8 +732,12 @@ class Engine(object):
             self.ps.zero_grad()
         B, S = source.shape
         esave, dsave = {}, {}
-        enc, src_len = self.encode(source, esave)
-        loss, per_sample, _ = self.decode_train(target, enc, src_len, S, c.smooth, True, dsave)
+        self._training = True     # dropout is part of train_fn only (score_fn / infer_fn close it)
+        try:
+            enc, src_len = self.encode(source, esave)
+            loss, per_sample, _ = self.decode_train(target, enc, src_len, S, c.smooth, True, dsave)
+        finally:
+            self._training = False
         d_enc32 = ws.get("d_enc32", (B * S, c.d), f32)
         d_enc32.zero_()
         self.decode_train_bwd(dsave, d_enc32)

@@ -8,7 +8,7 @@ import torch
 
 from . import lib as L
 from . import ops
-from .engine import DecodeState, Engine, _lens
+from .engine import DecodeState, Engine, _lens, dropout_site
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -25,8 +25,12 @@ def _aan_sublayer_fwd(eng, key, x, B, T, tgt_len, sv, tag):
     if c.use_ffn:
         h = ws.get(tag + ".h", (N, c.f))
         ops.linear_fwd(xf, ps.w(key + ".aan.ffn.w1.W"), ps.p(key + ".aan.ffn.w1.b"), h, relu=True)
+        r = eng._rate("relu")
+        if r > 0.0:   # transformer_aan.py:180
+            ops.dropout(h, h, r, eng.drop_seed, dropout_site(key + ".aan.relu"))
         ops.linear_fwd(h, ps.w(key + ".aan.ffn.w2.W"), ps.p(key + ".aan.ffn.w2.b"), cat[:, c.d:])
         sv["h"] = h
+        sv["relu_rate"] = r
     else:
         ops.add2d(xf, None, cat[:, c.d:])
     y0 = ws.get(tag + ".y0", (N, c.d))
@@ -52,7 +56,8 @@ def _fuse_sublayer_fwd(eng, key, x, enc, B, T, S, src_len, tgt_len, sv, tag):
     ctx = ws.get(tag + ".ctx", (N, c.d))
     lse = ws.get(tag + ".lse", (B, c.h, T), f32)
     a = ops.attention_args(q.view(B, T, c.d), kv3[:, :, :c.d], kv3[:, :, c.d:], ctx.view(B, T, c.d), c.h,
-                           key_len=src_len, inf_value=c.inf, lse=lse)
+                           key_len=src_len, inf_value=c.inf, lse=lse,
+                           dropout=(eng._rate("att"), dropout_site(kc + ".att"), eng.drop_seed))
     ops.attention_fwd(a)
     vq = ws.get(tag + ".vq", (N, c.d))
     ops.linear_fwd(x, ps.w(kc + ".kv.W")[:, c.d:], ps.p(kc + ".kv.b")[c.d:], vq)  # v_map applied to the query
@@ -74,6 +79,9 @@ def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=Non
     tgt_len.copy_(_lens(target))
     x = ws.get(tag + ".x0", (N, c.d))
     ops.embed_fwd(target, ps.w(self._tgt_table()), ps.p("emb_bias"), x, mult=c.d ** 0.5, shift=1)
+    r_emb = self._rate("emb")
+    if r_emb > 0.0:   # transformer_aan.py:152 / transformer_fuse.py:118
+        ops.dropout(x, x, r_emb, self.drop_seed, dropout_site("dec.emb"))
     layers = []
     for l in range(c.ndec):
         key, t = "dec%d" % l, "%s.A%d" % (tag, l)
@@ -100,7 +108,7 @@ def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=Non
                    loss_scale=c.loss_scale)
     if save is not None:
         save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
-                    tgt_len=tgt_len)
+                    tgt_len=tgt_len, emb_rate=r_emb)
     return loss, per_sample, logits
 
 
@@ -114,14 +122,14 @@ def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
     sub = sv["sub"]
     x = sv["x_in"]
     if c.aan:
-        dsc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
-        dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dsc, d_enc_f32, B, T, S, sv["cross"], bw + ".cross")
-        # LN(x + gate): ds is the gradient wrt x (skip) and wrt the gate output
-        ds = self._ln_bwd(key + ".aan.ln", dsc, dx1, N, sub["ln"], bw + ".aln")
+        dsc, dyc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc", ps.g(key + ".cross.o.b"))
+        dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dyc, d_enc_f32, B, T, S, sv["cross"], bw + ".cross")
+        # LN(x + gate): ds is the gradient wrt x (skip), dyg the gradient wrt the gate output
+        ds, dyg = self._ln_bwd(key + ".aan.ln", dsc, dx1, N, sub["ln"], bw + ".aln")
         dxg = ws.get(bw + ".dxg", (N, c.d))
         dy0 = ws.get(bw + ".dy0", (N, c.d))
         dz = ws.get(bw + ".dz", (N, 2 * c.d))
-        ops.aan_gate_bwd(x, sub["y0"], sub["z"], ds, dxg, dy0, dz)
+        ops.aan_gate_bwd(x, sub["y0"], sub["z"], dyg, dxg, dy0, dz)
         cat = sub["cat"]
         self._side(lambda: (ops.linear_wgrad(cat, dz, ps.g(key + ".aan.z.W")), ops.colsum(dz, ps.g(key + ".aan.z.b"))))
         dcat = ws.get(bw + ".dcat", (N, 2 * c.d))
@@ -132,7 +140,8 @@ def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
             self._side(lambda: (ops.linear_wgrad(h, dy0, ps.g(key + ".aan.ffn.w2.W")),
                                 ops.colsum(dy0, ps.g(key + ".aan.ffn.w2.b"))))
             dh = ws.get(bw + ".adh", (N, c.f))
-            ops.linear_dgrad(dy0, ps.w(key + ".aan.ffn.w2.W"), dh, relu_mask=h)
+            ops.linear_dgrad(dy0, ps.w(key + ".aan.ffn.w2.W"), dh, relu_mask=h,
+                             alpha=1.0 / (1.0 - sub.get("relu_rate", 0.0)))
             self._side(lambda: (ops.linear_wgrad(xf, dh, ps.g(key + ".aan.ffn.w1.W")),
                                 ops.colsum(dh, ps.g(key + ".aan.ffn.w1.b"))))
             dxf = ws.get(bw + ".dxf", (N, c.d))
@@ -148,11 +157,11 @@ def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
         return t1, t2
     # ---- merged attention
     kc = key + ".cross"
-    dsc = self._ln_bwd(kc + ".ln", ds2, dxc, N, sub["ln"], bw + ".lnc", ps.g(kc + ".o.b"))
+    dsc, dyc = self._ln_bwd(kc + ".ln", ds2, dxc, N, sub["ln"], bw + ".lnc", ps.g(kc + ".o.b"))
     osum = sub["osum"]
-    self._side(lambda: ops.linear_wgrad(osum, dsc, ps.g(kc + ".o.W")))
+    self._side(lambda: ops.linear_wgrad(osum, dyc, ps.g(kc + ".o.W")))
     do = ws.get(bw + ".do", (N, c.d))
-    ops.linear_dgrad(dsc, ps.w(kc + ".o.W"), do)
+    ops.linear_dgrad(dyc, ps.w(kc + ".o.W"), do)
     dq = ws.get(bw + ".dq", (N, c.d))
     dkv = ws.get(bw + ".dkv", (B * S, 2 * c.d))
     dkv3 = dkv.view(B, S, 2 * c.d)

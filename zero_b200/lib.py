@@ -40,7 +40,8 @@ class AttentionArgs(C.Structure):
                 ("d_o", vp), ("dq", vp), ("dk", vp), ("dv", vp),
                 ("lddo", i64), ("lddq", i64), ("lddk", i64), ("lddv", i64),
                 ("bsdo", i64), ("bsdq", i64), ("bsdk", i64), ("bsdv", i64),
-                ("d_rpr_k", vp), ("d_rpr_v", vp), ("delta", vp), ("kv_group", i32)]
+                ("d_rpr_k", vp), ("d_rpr_v", vp), ("delta", vp), ("kv_group", i32),
+                ("dropout_rate", f32), ("dropout_site", C.c_uint32), ("dropout_seed", vp)]
 
 
 class AddLnArgs(C.Structure):
@@ -78,8 +79,11 @@ class BeamArgs(C.Structure):
 
 
 # every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
+# order = the index zb_abi_struct_size() understands
+STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs]
+
 EXPORTS = [
-    "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_gemm", "zb_attention_fwd",
+    "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
     "zb_attention_bwd", "zb_add_ln_fwd", "zb_add_ln_bwd", "zb_embed_fwd", "zb_embed_bwd", "zb_softmax_ce",
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
@@ -134,12 +138,19 @@ def load():
         ("zb_gated_rms_fwd", [vp, vp, vp, vp, vp, i64, i64, f32, vp]),
         ("zb_gated_rms_bwd", [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
         ("zb_add2d", [vp, i64, vp, i64, vp, i64, i64, i64, vp]),
+        ("zb_dropout", [vp, vp, vp, i64, f32, vp, C.c_uint32, vp]),
     ]:
         fn = getattr(lib, name)
         fn.argtypes = argt
         fn.restype = C.c_int
     if lib.zb_abi_version() != 1:
         raise ZeroB200Error("libzero_b200.so ABI version mismatch")
+    lib.zb_abi_struct_size.argtypes = [i32]
+    lib.zb_abi_struct_size.restype = C.c_int64
+    for which, cls in enumerate(STRUCTS):
+        if lib.zb_abi_struct_size(which) != C.sizeof(cls):
+            raise ZeroB200Error("libzero_b200.so: %s is %d bytes in the library, %d in the binding (stale build?)" % (
+                cls.__name__, lib.zb_abi_struct_size(which), C.sizeof(cls)))
     _lib = lib
     return lib
 

@@ -1,0 +1,125 @@
+"""Training / evaluation loops around the hot path (reference main.py:133-470 `train`, :473-545 `evaluate`).
+
+What the reference does with a TF session, placeholders and `sess.run(train_op, feed_dict)` is here a `Trainer`
+(zero_b200/train.py) stepping the engine; everything else keeps the reference's behaviour and knobs:
+epochs over a length-bucketed batcher, `len(gpus)` consecutive batches per step (one per rank here),
+`update_cycle` accumulation, the host-side LR schedule, the NaN / Inf guard and `safe_nan` skip
+(main.py:316-332), the display line every `disp_freq` updates (Loss, GNorm, PNorm, Lr, Tokens, UD — main.py:335-346,
+the reference's own tokens/sec definition), evaluation every `eval_freq` updates (beam search -> BLEU, with the
+EMA weights swapped in when ema_decay > 0), early stopping on `estop_patience`, `max_training_steps`.
+Checkpoint files (utils/saver.py) are out of scope; `state` carries what record.json would (run.py:276-296).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import evalu, lrs
+from .data import pin, shard_for_rank
+from .models import model as model_registry
+from .models.transformer import get_engine
+from .train import Trainer
+
+
+def _log(msg):
+    print(msg, flush=True)
+
+
+def evaluate(params, dataset, references=None, log=_log):
+    """main.evaluate (main.py:473-545): beam-search `dataset`, BLEU against `references` (list of corpora)."""
+    graph = model_registry.get_model(params.model_name)
+    trans, scores, indices, timing = evalu.decoding(graph.infer_fn(params), dataset, params, log=None)
+    bleu = evalu.eval_metric(trans, references, indices=indices) if references else 0.0
+    log("Scores %.4f, BLEU %.4f, %d sentences, %d tokens in %.3f s (%.0f tok/s)" % (
+        float(np.mean(scores)) if scores else 0.0, bleu, timing["sentences"], timing["tokens"], timing["seconds"],
+        timing["tokens"] / max(timing["seconds"], 1e-9)))
+    return {"bleu": bleu, "translations": evalu.in_corpus_order(trans, indices), "scores": scores, "timing": timing}
+
+
+def train(params, train_dataset, dev_dataset=None, dev_references=None, world_size=1, rank=0, use_graph=False,
+          log=_log, on_step=None):
+    """main.train (main.py:133-470).  Returns the training record: {"step", "epoch", "losses": [(gstep, loss)],
+    "valid_script_scores": [(gstep, bleu)], "estop", "tokens_per_sec": [...] }."""
+    np.random.seed(int(params.random_seed))            # run.py:379-381 (batch shuffling uses the numpy RNG)
+    eng = get_engine(params)
+    schedule = lrs.get_lr(params)
+    trainer = Trainer(eng, params, world_size=world_size, use_graph=use_graph, lr_schedule=schedule)
+    state = {"step": 0, "epoch": 0, "losses": [], "valid_script_scores": [], "history_scores": [], "estop": False,
+             "bad_counter": 0, "tokens_per_sec": []}
+    size = params.batch_size if params.batch_or_token == "batch" else params.token_size
+    cum_tokens, start_time = 0, time.time()
+    for epoch in range(1, int(params.epoches) + 1):
+        state["epoch"] = epoch
+        log("Training the model for epoch %d" % epoch)
+        schedule.before_epoch(eidx=epoch)
+        batches = train_dataset.batcher(size, buffer_size=params.buffer_size, shuffle=params.shuffle_batch,
+                                        train=True)
+        lidx = -1
+        for lidx, data in enumerate(shard_for_rank(batches, world_size, rank)):
+            src, tgt = pin(data)
+            cum_tokens += int(np.sum(data["tgt"] > 0))          # main.py:297
+            loss_t = trainer.compute(src, tgt)
+            if not trainer.cycle_ready():
+                continue                                        # collect_op: accumulate, no update (main.py:300-302)
+            loss_t = trainer.cycle_loss() if trainer.cycle > 1 else loss_t
+            if params.safe_nan:
+                loss, gnorm = float(loss_t.item()), trainer.gradient_norm(before_apply=True)
+                if not (math.isfinite(loss) and math.isfinite(gnorm)) or gnorm > params.gnorm_upper_bound:
+                    log("Nan or Inf raised, GStep %d is passed! Loss %s GNorm %s." % (trainer.global_step, loss, gnorm))
+                    trainer.skip()
+                    continue
+                trainer.apply()
+            else:
+                trainer.apply()
+                loss, gnorm = float(loss_t.item()), trainer.gradient_norm()
+                if not (math.isfinite(loss) and math.isfinite(gnorm)):
+                    log("Nan or Inf raised! Loss %s GNorm %s." % (loss, gnorm))
+                    state["estop"] = True
+                    break
+            gstep = trainer.global_step
+            state["step"] = gstep
+            state["losses"].append((gstep, loss))
+            if on_step is not None:
+                on_step(gstep, loss)
+            if gstep % params.disp_freq == 0:
+                now = time.time()
+                ud = now - start_time
+                log("Epoch %d, GStep %d~%d, LStep %d~%d, Loss %.3f, GNorm %.3f, PNorm %.3f, Lr %.5f, Src %s, Tgt %s, "
+                    "Tokens %d, UD %.3f s" % (epoch, gstep - params.disp_freq + 1, gstep, lidx - params.disp_freq + 1,
+                                              lidx, loss, gnorm, trainer.parameter_norm(), schedule.get_lr(),
+                                              data["src"].shape, data["tgt"].shape, cum_tokens, ud))
+                state["tokens_per_sec"].append(cum_tokens / max(ud, 1e-9))
+                cum_tokens, start_time = 0, time.time()
+            if dev_dataset is not None and gstep > 0 and gstep % params.eval_freq == 0:
+                trainer.ema_assign()
+                t0 = time.time()
+                res = evaluate(params, dev_dataset, dev_references, log=lambda m: None)
+                trainer.ema_restore()
+                bleu = res["bleu"]
+                log("GStep %d, Scores %.4f, BLEU %.4f, Duration %.3f s" % (
+                    gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0, bleu, time.time() - t0))
+                prev = [v[1] for v in state["valid_script_scores"]]
+                if not prev or bleu > max(prev):
+                    state["bad_counter"] = 0
+                else:
+                    state["bad_counter"] += 1
+                    if state["bad_counter"] > params.estop_patience:
+                        state["estop"] = True
+                state["history_scores"].append((gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0))
+                state["valid_script_scores"].append((gstep, float(bleu)))
+                schedule.after_eval(float(bleu))
+                if state["estop"]:
+                    break
+            if gstep >= params.max_training_steps:
+                state["estop"] = True
+                break
+        if state["estop"]:
+            log("Early Stopped!")
+            break
+        schedule.after_epoch(eidx=epoch)
+    torch.cuda.synchronize()
+    state["trainer"] = trainer
+    return state

@@ -40,18 +40,10 @@ def _closing_dropout(params):
     return params
 
 
-def _check_dropout(params):
-    for k, v in params.values().items():
-        if "dropout" in k and v:
-            raise NotImplementedError(
-                "dropout > 0 is not implemented on the CUDA path yet (parity runs use dropout = 0, "
-                "like util.closing_dropout does for score/infer); got %s=%r" % (k, v))
-
-
 def _make(name):
     def train_fn(features, params, initializer=None):
-        _check_dropout(params)
         eng = get_engine(params, initializer)
+        eng.advance_dropout_seed()   # dropout rates come from params at engine creation (utils/util.py:75-79)
         loss = eng.forward_backward(features["source"], features["target"])
         return {"loss": loss}
 

@@ -84,9 +84,9 @@ def linear_fwd(x, w, bias, out, relu=False):
     return gemm(x, w, out, L.ZB_K_MAJOR, L.ZB_MN_MAJOR, bias=bias, relu=relu)
 
 
-def linear_dgrad(dy, w, dx, relu_mask=None, accum=False):
-    """dx = dy @ W^T (gradient of func.linear wrt its input); optional relu mask of the producer."""
-    return gemm(dy, w, dx, L.ZB_K_MAJOR, L.ZB_K_MAJOR, relu_mask=relu_mask, accum=accum)
+def linear_dgrad(dy, w, dx, relu_mask=None, accum=False, alpha=1.0):
+    """dx = alpha * dy @ W^T (gradient of func.linear wrt its input); optional relu mask of the producer."""
+    return gemm(dy, w, dx, L.ZB_K_MAJOR, L.ZB_K_MAJOR, relu_mask=relu_mask, accum=accum, alpha=alpha)
 
 
 def linear_wgrad(x, dy, dw):
@@ -101,8 +101,9 @@ def colsum(x, out):
 
 
 def attention_args(q, k, v, o, heads, key_len=None, causal=False, q_offset=0, inf_value=1e8, lse=None,
-                   rpr_k=None, rpr_v=None, max_rel=0, relu_attn=False, kv_group=1):
-    """q/k/v/o: [B, L, heads*dh] views (last dim contiguous)."""
+                   rpr_k=None, rpr_v=None, max_rel=0, relu_attn=False, kv_group=1, dropout=None):
+    """q/k/v/o: [B, L, heads*dh] views (last dim contiguous).
+    dropout: None or (rate, site, seed_tensor) — attention dropout of func.py:245."""
     B, Lq, D = q.shape
     assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and o.stride(2) == 1
     Lk = k.shape[1]
@@ -119,7 +120,18 @@ def attention_args(q, k, v, o, heads, key_len=None, causal=False, q_offset=0, in
     a.rpr_k, a.rpr_v, a.max_rel = _p(rpr_k), _p(rpr_v), int(max_rel)
     a.relu_attn = int(relu_attn)
     a.kv_group = int(kv_group)
+    if dropout is not None and dropout[0] > 0.0:
+        a.dropout_rate, a.dropout_site, a.dropout_seed = float(dropout[0]), int(dropout[1]), _p(dropout[2])
     return a
+
+
+def dropout(x, out, rate, seed, site, x2=None):
+    """out = tf.nn.dropout(x (+ x2), keep_prob = 1 - rate) with the counter-based mask of (seed, site)
+    (utils/util.py:75-79).  bf16, contiguous; out may be x.  seed: device uint64/int64 tensor [1]."""
+    assert x.is_contiguous() and out.is_contiguous() and (x2 is None or x2.is_contiguous())
+    L.check(L.load().zb_dropout(_p(x), _p(x2), _p(out), x.numel(), float(rate), _p(seed), int(site), _stream()),
+            "zb_dropout")
+    return out
 
 
 def attention_fwd(a):

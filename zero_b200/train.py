@@ -27,7 +27,13 @@ def noam_lr(step, init_lr, warmup_steps, hidden_size, min_lr=0.0, max_lr=1.0):
 
 
 class Trainer(object):
-    def __init__(self, engine: Engine, hp, world_size=1, use_graph=False, side_stream=True):
+    """One optimizer step = `update_cycle` micro-batches per rank (utils/cycle.py:53-92: gradients and the loss are
+    averaged over the cycle), one all-reduce, one fused Adam.  `lr_schedule` is a zero_b200.lrs schedule object
+    (or None: Noam from the hyper-parameters, as the Transformer recipes use)."""
+
+    MAX_GRAPHS = 24   # captured (shape, zero_grad) variants kept; further shapes run eagerly
+
+    def __init__(self, engine: Engine, hp, world_size=1, use_graph=False, side_stream=True, lr_schedule=None):
         self.eng = engine
         if side_stream:
             engine.enable_side_stream(True)
@@ -39,78 +45,134 @@ class Trainer(object):
         engine.ps.adam_v = torch.zeros(n, dtype=f32, device=dev)
         self.clip_scale = torch.ones(1, dtype=f32, device=dev)    # clip_by_global_norm factor, device side
         self.norms = torch.zeros(2, dtype=f32, device=dev)        # {sum g^2, sum p^2}
+        self.loss_acc = torch.zeros(1, dtype=f32, device=dev)     # sum of the cycle's micro-batch losses
         self.global_step = 0
         self.beta1, self.beta2, self.eps = float(hp.beta1), float(hp.beta2), float(hp.epsilon)
         clip = getattr(hp, "clip_grad_norm", 0.0)
         self.clip = float(clip) if isinstance(clip or None, float) else None   # utils/cycle.py:98
         self.loss_scale = float(getattr(hp, "loss_scale", 1.0))
+        self.cycle = max(1, int(getattr(hp, "update_cycle", 1)))
+        self.lr_schedule = lr_schedule
         self.use_graph = use_graph
-        self._graph = None
-        self._static = None
+        self._graphs = {}
+        self._micro = 0
+        self._pending = None
+        # exponential moving average of the parameters (utils/cycle.py:114-127), off unless ema_decay > 0
+        self.ema_decay = float(getattr(hp, "ema_decay", -1.0))
+        self.ema = engine.ps.master.clone() if self.ema_decay > 0.0 else None
+        self._ema_backup = None
 
     # ------------------------------------------------------------------------------------------ lr
     def lr(self):
         hp = self.hp
+        if self.lr_schedule is not None:
+            self.lr_schedule.step(self.global_step)
+            return float(self.lr_schedule.get_lr())
         if getattr(hp, "lrate_strategy", "noam") == "noam":
             return noam_lr(self.global_step, hp.lrate, hp.warmup_steps, hp.hidden_size,
                            getattr(hp, "min_lrate", 0.0), getattr(hp, "max_lrate", 1.0))
         return float(hp.lrate)
 
     # ------------------------------------------------------------------------------------------ step
-    def _phases(self, source, target):
-        """Runs phase 1 (forward + decoder backward), calls `between()` hooks via the caller, then phase 2."""
+    def _phases(self, source, target, zero_grad=True):
+        """Runs phase 1 (forward + decoder backward) and returns (loss, phase-2 callable)."""
         eng = self.eng
-        if not self.use_graph:
-            loss = eng.forward_backward_decoder(source, target)
-            return loss, eng.backward_encoder
-        key = (tuple(source.shape), tuple(target.shape))
-        if self._graph is None or self._static[0] != key:
+        eng.advance_dropout_seed()
+        key = (tuple(source.shape), tuple(target.shape), bool(zero_grad))
+        entry = self._graphs.get(key) if self.use_graph else None
+        if self.use_graph and entry is None and len(self._graphs) < self.MAX_GRAPHS:
             s_src = torch.empty(source.shape, dtype=torch.int32, device=eng.device)
             s_tgt = torch.empty(target.shape, dtype=torch.int32, device=eng.device)
             s_src.copy_(source)
             s_tgt.copy_(target)
-            # warm-up on a side stream (allocates every workspace buffer), then capture the two phases
+            # warm-up on a side stream (allocates every workspace buffer), then capture the two phases; the warm-up
+            # must not disturb gradients that a running accumulation cycle has already collected
+            keep = eng.ps.grad.clone() if not zero_grad else None
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 eng.forward_backward(s_src, s_tgt, compact=False)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            if keep is not None:
+                eng.ps.grad.copy_(keep)
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
-                loss = eng.forward_backward_decoder(s_src, s_tgt, compact=False)
+                loss = eng.forward_backward_decoder(s_src, s_tgt, zero_grad=zero_grad, compact=False)
             with torch.cuda.graph(g2, pool=g1.pool()):
                 eng.backward_encoder()
-            self._graph, self._static = (g1, g2), (key, s_src, s_tgt, loss)
-        _, s_src, s_tgt, loss = self._static
+            if keep is not None:
+                eng.ps.grad.copy_(keep)   # capture does not execute, but stay safe against future changes
+            entry = self._graphs[key] = (g1, g2, s_src, s_tgt, loss)
+        if entry is None:
+            loss = eng.forward_backward_decoder(source, target, zero_grad=zero_grad,
+                                                compact=not self.use_graph)
+            return loss, eng.backward_encoder
+        g1, g2, s_src, s_tgt, loss = entry
         s_src.copy_(source, non_blocking=True)
         s_tgt.copy_(target, non_blocking=True)
-        self._graph[0].replay()
-        return loss, self._graph[1].replay
+        g1.replay()
+        return loss, g2.replay
 
     def step(self, source, target):
-        """One optimizer step on this rank's batch.  Returns the device loss tensor (no host sync).
+        """One micro-batch.  Returns the device loss tensor [1] of this micro-batch (no host sync).  The parameters
+        are updated when the call completes an `update_cycle` (every call for update_cycle = 1).
         Data parallel: the decoder-side bucket of the flat gradient arena is all-reduced (NCCL, async) while the
         encoder backward is still running; the encoder-side bucket follows; both complete before Adam."""
+        loss = self.compute(source, target)
+        if self._pending:
+            self.apply()
+        return loss
+
+    def compute(self, source, target):
+        """Forward + backward (+ all-reduce on the last micro-batch of the cycle); no parameter change.
+        `self.cycle_ready()` tells whether `apply()` is due; `gradient_norm(ready=False)` reads GNorm first
+        (safe_nan mode, main.py:320-332)."""
         eng, ps = self.eng, self.eng.ps
-        loss, phase2 = self._phases(source, target)
+        first = self._micro == 0
+        last = self._micro == self.cycle - 1
+        loss, phase2 = self._phases(source, target, zero_grad=first)
+        if self.cycle > 1:
+            if first:
+                self.loss_acc.zero_()
+            self.loss_acc += loss
         works = []
-        if self.world > 1:
+        if last and self.world > 1:
             works.append(dist.all_reduce(ps.grad[ps.dec_offset:], op=dist.ReduceOp.SUM, async_op=True))
         phase2()
-        if self.world > 1:
+        if last and self.world > 1:
             works.append(dist.all_reduce(ps.grad[:ps.dec_offset], op=dist.ReduceOp.SUM, async_op=True))
             for w in works:
                 w.wait()
+        self._micro = 0 if last else self._micro + 1
+        self._pending = last
+        return loss
+
+    def cycle_ready(self):
+        return bool(self._pending)
+
+    def cycle_loss(self):
+        """Mean loss of the finished cycle (utils/cycle.py:90-92), device tensor."""
+        return self.loss_acc / float(self.cycle)
+
+    def skip(self):
+        """Drop the collected gradients without updating (safe_nan, main.py:326-330: the step is 'passed')."""
+        self._pending = False
+
+    def apply(self):
+        """clip_by_global_norm + TF Adam on the averaged gradients (utils/cycle.py:94-105) + EMA."""
+        ps = self.eng.ps
+        self._pending = False
         # tf.global_norm of gradients and parameters (utils/cycle.py:94-95): a separate pass only when the clip
         # factor needs the gradient norm before the update; otherwise fused into the Adam kernel
         self.norms.zero_()
         if self.clip is not None:
             ops.sumsq(ps.grad, self.norms[0:1])
+        lr = self.lr()
         self.global_step += 1
         t = self.global_step
-        lr_t = self.lr() * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
-        gscale = 1.0 / (self.world * self.loss_scale)
+        lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        gscale = 1.0 / (self.world * self.cycle * self.loss_scale)
         clip_scale = None
         if self.clip is not None:
             # clip_by_global_norm: g * clip / max(norm, clip)   (device-side scalar ops, no host sync)
@@ -120,10 +182,37 @@ class Trainer(object):
             self.norms.zero_()
         ops.adam_tf(ps.master, ps.adam_m, ps.adam_v, ps.grad, ps.mirror, self.beta1, self.beta2, self.eps,
                     lr_t, gscale, clip_scale, self.norms)
-        return loss
+        if self.ema is not None:
+            # tf.train.ExponentialMovingAverage(decay, num_updates=global_step): decay' = min(decay, (1+n)/(10+n))
+            n = float(self.global_step)
+            d = min(self.ema_decay, (1.0 + n) / (10.0 + n))
+            self.ema.lerp_(ps.master, 1.0 - d)
 
-    def gradient_norm(self):
-        """GNorm of main.py:336-346 (already averaged over towers and un-scaled)."""
+    # ------------------------------------------------------------------------------------------ EMA swap (eval)
+    def ema_assign(self):
+        """ema_backup_op + ema_assign_op (main.py:368-370): evaluate with the averaged parameters."""
+        if self.ema is None:
+            return
+        ps = self.eng.ps
+        self._ema_backup = ps.master.clone()
+        ps.master.copy_(self.ema)
+        ps.refresh_mirror()
+
+    def ema_restore(self):
+        if self.ema is None or self._ema_backup is None:
+            return
+        ps = self.eng.ps
+        ps.master.copy_(self._ema_backup)
+        self._ema_backup = None
+        ps.refresh_mirror()
+
+    def gradient_norm(self, before_apply=False):
+        """GNorm of main.py:336-346 (averaged over towers / cycle, un-scaled).  With before_apply=True the norm of
+        the collected, not yet applied gradients is computed by a separate pass (safe_nan mode)."""
+        if before_apply:
+            tmp = torch.zeros(1, dtype=f32, device=self.eng.device)
+            ops.sumsq(self.eng.ps.grad, tmp)
+            return float(torch.sqrt(tmp[0]).item()) / (self.world * self.cycle * self.loss_scale)
         return float(torch.sqrt(self.norms[0]).item())
 
     def parameter_norm(self):
