@@ -63,7 +63,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -241,8 +241,15 @@ def gemm_roofline(eng, src, tgt, peaks):
     ms = e0.elapsed_time(e1) / reps
     achieved = flops[0] / (ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    traffic, traffic_src = None, None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic.json")))
+        traffic, traffic_src = float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        pass
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gemm2_bf16_tcgen05", "launches_per_step": len(calls),
+            "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "gemm2_bf16_tcgen05", "launches_per_step": len(calls),
             "gemm_problems_per_step": nsingle[0] + nprob[0],
             "step_launches": step_launches,
             "gemm_ms_per_step": ms, "avg_launch_us": 1000.0 * ms / max(len(calls), 1),
@@ -301,7 +308,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    clocks = sampler.stop() if sampler else None
     eager_launches = L.launch_count() - launches0
     final_loss = float(loss.item())
 
@@ -319,6 +325,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms2 = float(ms2.item())
+    clocks = sampler.stop() if sampler else None   # sampled across both timed regions
 
     if rank != 0:
         if world > 1:
@@ -387,7 +394,7 @@ def main():
         args.warmup = 1 if args.warmup is None else min(args.warmup, 3)
         run_reference(args)
     else:
-        args.steps = 20 if args.steps is None else args.steps
+        args.steps = 100 if args.steps is None else args.steps
         args.warmup = 5 if args.warmup is None else args.warmup
         run_ours(args)
 

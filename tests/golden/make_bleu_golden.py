@@ -55,10 +55,14 @@ def c1_data(hp):
 
 
 def main(steps):
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(int(os.environ.get('C1_THREADS', os.cpu_count() or 1)))
     corp = synthetic_corpus()
     v = Vocab(tokens=corp["symbols"])
     hp = c1_params(v, max_training_steps=steps)
+    if os.environ.get("C1_LRATE"):
+        hp.lrate = float(os.environ["C1_LRATE"])
+    if os.environ.get("C1_WARMUP"):
+        hp.warmup_steps = int(os.environ["C1_WARMUP"])
     _, train, dev = c1_data(hp)
     c = zo.Cfg(hp, v.size(), v.size())
     P = {k: t.requires_grad_(True) for k, t in zo.init_params(c, seed=INIT_SEED).items()}
@@ -96,7 +100,7 @@ def main(steps):
     bleu = evalu.bleu(hyps, [[r] for r in corp["dev_tgt"]])
     exact = sum(int(h == r) for h, r in zip(hyps, corp["dev_tgt"]))
     print("held-out BLEU %.4f, %d / %d exact" % (bleu, exact, len(hyps)))
-    with open(os.path.join(HERE, "c1_bleu.json"), "w") as f:
+    with open(os.environ.get("C1_OUT", os.path.join(HERE, "c1_bleu.json")), "w") as f:
         json.dump({"steps": steps, "init_seed": INIT_SEED, "losses": losses, "bleu": bleu, "exact": exact,
                    "hyps": hyps, "what": "oracle (CPU fp32) trained on C1; see make_bleu_golden.py"}, f)
 

@@ -169,3 +169,67 @@ def test_full_size_properties_c2_shapes():
     pad = torch.zeros(32, 5, dtype=src2.dtype)
     _, ps2, _ = eng.train_loss(torch.cat([src2, pad], 1), torch.cat([tgt2, pad], 1))
     torch.testing.assert_close(ps2, ps, atol=1e-5, rtol=1e-5)
+
+
+def test_full_size_properties_c4_relative_positions_len128():
+    """BASELINE configs[3]: transformer_rpr 6+6 d=512, src / tgt length 128, max_relative_position 16 (a reduced
+    batch keeps the test short).  Size-independent properties: finite loss near ln(V) at init, every relative-
+    position table receives gradient, batch independence, and translation invariance of the relative-position
+    model's logits when the timing signal is the only absolute-position input (pad columns do not change them)."""
+    from zero_b200.engine import Engine
+    from zero_b200.params import transformer_base
+    hp = transformer_base(model_name="transformer_rpr", scope_name="transformer_rpr", max_relative_position=16)
+    eng = Engine(hp, 32000, 32000)
+    eng.ps.init_random(2)
+    g = torch.Generator().manual_seed(1)
+    src = torch.randint(3, 32000, (4, 128), generator=g)
+    tgt = torch.randint(3, 32000, (4, 128), generator=g)
+    src[:, -1] = 2
+    tgt[:, -1] = 2
+    src[1, 90:] = 0
+    tgt[2, 77:] = 0
+    src2, tgt2 = torch.cat([src, src]), torch.cat([tgt, tgt])
+    loss = eng.forward_backward(src2, tgt2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and 8.0 < float(loss[0]) < 14.0
+    assert torch.isfinite(eng.ps.grad).all()
+    for l in range(6):
+        for key in ("enc%d.self" % l, "dec%d.self" % l, "dec%d.cross" % l):
+            assert float(eng.ps.g(key + ".rpr_k").abs().sum()) > 0, key
+            assert float(eng.ps.g(key + ".rpr_v").abs().sum()) > 0, key
+    _, ps, _ = eng.train_loss(src2, tgt2)
+    ps = ps.clone()
+    torch.testing.assert_close(ps[:4], ps[4:], atol=1e-5, rtol=1e-5)
+    pad = torch.zeros(8, 3, dtype=src2.dtype)
+    _, ps2, _ = eng.train_loss(torch.cat([src2, pad], 1), torch.cat([tgt2, pad], 1))
+    torch.testing.assert_close(ps2, ps, atol=1e-5, rtol=1e-5)
+
+
+def test_full_size_properties_c5_deep_encoder_len1024():
+    """BASELINE configs[4]: 24-layer encoder with depth-scaled initialisation (models/transformer.py:38-45),
+    source length 1024 (multi-tile attention, looping add+LN backward), 6 decoder layers, target length 64.
+    The speech front-end is not part of the reference checkout: the encoder is fed token ids."""
+    from zero_b200.engine import Engine
+    from zero_b200.params import transformer_base
+    hp = transformer_base(num_encoder_layer=24, num_decoder_layer=6, deep_transformer_init=True,
+                          initializer="uniform_unit_scaling", initializer_gain=1.0)
+    eng = Engine(hp, 32000, 32000)
+    eng.ps.init_random(3)
+    # DS-Init: layer l weights ~ U(+-sqrt(3 * gain / (l + 1)^0.5 / fan_avg)) -> deeper layers are smaller
+    w0 = float(eng.ps.p("enc0.ffn.w1.W").std())
+    w23 = float(eng.ps.p("enc23.ffn.w1.W").std())
+    assert abs(w23 / w0 - 24 ** -0.25) < 0.02, (w0, w23)
+    g = torch.Generator().manual_seed(2)
+    src = torch.randint(3, 32000, (4, 1024), generator=g)
+    tgt = torch.randint(3, 32000, (4, 64), generator=g)
+    src[:, -1] = 2
+    tgt[:, -1] = 2
+    src[1, 700:] = 0
+    src2, tgt2 = torch.cat([src, src]), torch.cat([tgt, tgt])
+    loss = eng.forward_backward(src2, tgt2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and 8.0 < float(loss[0]) < 14.0
+    assert torch.isfinite(eng.ps.grad).all()
+    assert float(eng.ps.g("enc0.self.qkv.W").abs().sum()) > 0 and float(eng.ps.g("enc23.ffn.w2.W").abs().sum()) > 0
+    _, ps, _ = eng.train_loss(src2, tgt2)
+    torch.testing.assert_close(ps[:4].clone(), ps[4:].clone(), atol=1e-5, rtol=1e-5)

@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "zb_common.h"
 
 namespace zb {
@@ -20,6 +23,19 @@ void set_error(const char* fmt, ...) {
 bool pdl_enabled() {
   static const bool on = getenv("ZB_NO_PDL") == nullptr;
   return on;
+}
+
+bool carveout_enabled() {
+  static const bool on = getenv("ZB_CARVEOUT") != nullptr && getenv("ZB_CARVEOUT")[0] == '1';
+  return on;
+}
+
+void note_kernel_for_carveout(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert(kern).second)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 int num_sms() {

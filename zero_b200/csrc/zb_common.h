@@ -30,8 +30,14 @@ int num_sms();
 // captured CUDA graph).  ZB_NO_PDL=1 turns the attribute off.
 bool pdl_enabled();
 
+// Every kernel of the library asks for the SAME shared-memory carveout (the maximum): consecutive kernels with
+// different L1 / shared splits make the SM reconfigure between them.  ZB_CARVEOUT=0 leaves the driver's default.
+bool carveout_enabled();
+void note_kernel_for_carveout(const void* kern);
+
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (carveout_enabled()) note_kernel_for_carveout(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -151,8 +151,8 @@ def pin(data):
     return s, t
 
 
-def synthetic_corpus(n_train=256, n_heldout=64, n_symbols=997, min_len=4, max_len=24, zipf=1.1, seed=1234,
-                     active_symbols=40, swap_pairs=False):
+def synthetic_corpus(n_train=256, n_heldout=64, n_symbols=997, min_len=12, max_len=24, zipf=0.6, seed=1234,
+                     active_symbols=16, swap_pairs=False):
     """C1 of SURVEY.md 8(d): a 1k vocabulary (3 specials + symbols w0..w{n-1}); source length ~U[min_len, max_len],
     tokens ~Zipf(zipf) over the `active_symbols` most frequent symbols (so 256 sentences cover every symbol many
     times and the held-out set measures generalisation, not vocabulary coverage); the target is a fixed token

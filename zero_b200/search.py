@@ -109,6 +109,10 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     """Drop-in for reference search.beam_search (search.py:19).  `encoding_fn(source) -> state`,
     `decoding_fn(target [B*beam,1], state, time) -> (logits fp32 [B*beam,V], state)` as returned by
     zero_b200's infer_fn; `state.reorder(parent)` replaces the gather_nd over the tiled state."""
+    if bool(getattr(params, "enable_noise_beam_search", False)):
+        # search.py:144-145 adds tf.random_uniform Gumbel noise to the logits: a sampling mode, not reproducible
+        # across frameworks and outside the parity-checked path
+        raise NotImplementedError("enable_noise_beam_search (Gumbel top-k sampling) is not on the CUDA path")
     source = features["source"]
     state = encoding_fn(source)
     eng = state.engine
