@@ -84,3 +84,23 @@ def test_shard_for_rank_takes_every_nth_batch():
     from zero_b200.data import shard_for_rank
     assert list(shard_for_rank(range(7), 2, 0)) == [0, 2, 4]
     assert list(shard_for_rank(range(7), 2, 1)) == [1, 3, 5]
+
+
+def test_run_parameter_precedence_and_param_json(tmp_path):
+    """run.py:367-376: command line > saved param.json > --config file > defaults; param.json round trip."""
+    from zero_b200 import run, saver
+    from zero_b200.params import global_params
+    out = tmp_path / "model"
+    cfg = tmp_path / "cfg.py"
+    cfg.write_text("dict(hidden_size=256, num_heads=4, output_dir=%r, beam_size=8)" % str(out))
+    p = run.build_params(str(cfg), "beam_size=2,model_name=transformer")
+    assert (p.hidden_size, p.num_heads, p.beam_size, p.model_name) == (256, 4, 2, "transformer")
+    saver.save_parameters(p, str(out))
+    # a later run with other defaults picks the saved values up, the command line still wins
+    p2 = run.build_params(str(cfg), "beam_size=5", defaults=global_params())
+    assert (p2.hidden_size, p2.beam_size, p2.model_name) == (256, 5, "transformer")
+    p3 = saver.setup_recorder(p2)
+    assert p3.recorder.step == 0 and p3.recorder.epoch == 1
+    p3.recorder.step = 7
+    p3.recorder.save_to_json(str(out / "record.json"))
+    assert saver.setup_recorder(run.build_params(str(cfg), "")).recorder.step == 7

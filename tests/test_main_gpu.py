@@ -139,3 +139,37 @@ def test_c1_train_loop_reaches_oracle_bleu():
     # the display line carries the reference's fields (main.py:336-346)
     assert any("GNorm" in m and "Tokens" in m and "UD" in m for m in logs)
     plugins.reset_engines()
+
+
+def test_checkpoint_round_trip_with_tf_variable_names(tmp_path):
+    """utils/saver.py: keep-N rotation, best/ directory, restore of weights + Adam slots + global step; tensors are
+    stored under the reference's TF variable names."""
+    from zero_b200.engine import Engine
+    from zero_b200.saver import Saver
+    from zero_b200.train import Trainer
+    z, hp, variables, grads, vs, vt = load_golden("transformer")
+    hp.override_from_dict(dict(lrate=1.0, warmup_steps=10, beta1=0.9, beta2=0.98, epsilon=1e-8, clip_grad_norm=0.0,
+                               lrate_strategy="noam"))
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    eng = Engine(hp, vs, vt)
+    eng.ps.load_state_dict(variables)
+    tr = Trainer(eng, hp)
+    sv = Saver(checkpoints=2, output_dir=str(tmp_path), best_checkpoints=1)
+    for step in range(1, 4):
+        tr.step(src, tgt)
+        sv.save(eng, step, metric_score=[0.2, 0.5, 0.3][step - 1], trainer=tr)
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("model-"))
+    assert files == ["model-2.npz", "model-3.npz"]                       # keep the newest two
+    assert os.listdir(tmp_path / "best") == ["model-2.npz"] and sv.best_score == 0.5
+    with np.load(tmp_path / "model-3.npz") as ck:
+        assert set(variables) <= set(ck.files) and int(ck["global_step"]) == 3
+        k = sorted(variables)[0]
+        assert ck[k].shape == tuple(variables[k].shape) and (k + "/Adam") in ck.files
+    want_p, want_m = eng.ps.master.clone(), eng.ps.adam_m.clone()
+    loss3 = float(tr.step(src, tgt)[0])                                   # step 4 from the step-3 state
+    eng2 = Engine(hp, vs, vt)
+    eng2.ps.init_random(99)
+    tr2 = Trainer(eng2, hp)
+    assert Saver(checkpoints=2, output_dir=str(tmp_path)).restore(eng2, trainer=tr2)
+    assert tr2.global_step == 3 and torch.equal(eng2.ps.master, want_p) and torch.equal(eng2.ps.adam_m, want_m)
+    assert abs(float(tr2.step(src, tgt)[0]) - loss3) < 1e-4

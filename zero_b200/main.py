@@ -7,7 +7,8 @@ epochs over a length-bucketed batcher, `len(gpus)` consecutive batches per step 
 (main.py:316-332), the display line every `disp_freq` updates (Loss, GNorm, PNorm, Lr, Tokens, UD — main.py:335-346,
 the reference's own tokens/sec definition), evaluation every `eval_freq` updates (beam search -> BLEU, with the
 EMA weights swapped in when ema_decay > 0), early stopping on `estop_patience`, `max_training_steps`.
-Checkpoint files (utils/saver.py) are out of scope; `state` carries what record.json would (run.py:276-296).
+Checkpoints go through zero_b200/saver.py when `output_dir` is set (utils/saver.py: keep-N + best/); `state` carries
+what record.json would (run.py:276-296).
 """
 from __future__ import annotations
 
@@ -18,6 +19,7 @@ import numpy as np
 import torch
 
 from . import evalu, lrs
+from . import saver as ckpt
 from .data import pin, shard_for_rank
 from .models import model as model_registry
 from .models.transformer import get_engine
@@ -47,6 +49,13 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
     eng = get_engine(params)
     schedule = lrs.get_lr(params)
     trainer = Trainer(eng, params, world_size=world_size, use_graph=use_graph, lr_schedule=schedule)
+    # checkpoints (utils/saver.py) only when an output directory is configured; rank 0 writes
+    saver = None
+    if getattr(params, "output_dir", ""):
+        saver = ckpt.Saver(checkpoints=params.checkpoints, output_dir=params.output_dir,
+                           best_checkpoints=params.best_checkpoints)
+        if getattr(params, "train_continue", True) and saver.restore(eng, trainer=trainer):
+            log("Restored parameters from %s (global step %d)" % (saver.latest(), trainer.global_step))
     state = {"step": 0, "epoch": 0, "losses": [], "valid_script_scores": [], "history_scores": [], "estop": False,
              "bad_counter": 0, "tokens_per_sec": []}
     size = params.batch_size if params.batch_or_token == "batch" else params.token_size
@@ -93,6 +102,8 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                                               data["src"].shape, data["tgt"].shape, cum_tokens, ud))
                 state["tokens_per_sec"].append(cum_tokens / max(ud, 1e-9))
                 cum_tokens, start_time = 0, time.time()
+            if saver is not None and rank == 0 and gstep > 0 and gstep % params.save_freq == 0:
+                saver.save(eng, gstep, trainer=trainer)
             if dev_dataset is not None and gstep > 0 and gstep % params.eval_freq == 0:
                 trainer.ema_assign()
                 t0 = time.time()
@@ -110,6 +121,8 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                         state["estop"] = True
                 state["history_scores"].append((gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0))
                 state["valid_script_scores"].append((gstep, float(bleu)))
+                if saver is not None and rank == 0:
+                    saver.save(eng, gstep, metric_score=bleu, trainer=trainer)
                 schedule.after_eval(float(bleu))
                 if state["estop"]:
                     break

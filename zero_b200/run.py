@@ -1,0 +1,113 @@
+"""Command-line entry with the reference's flag surface (run.py:241-246, 307-420):
+
+    python -m zero_b200.run --mode train|test|score [--config FILE] [--parameters "k=v,..."]
+
+Precedence: command line > saved param.json > --config file > defaults (run.py:367-376).  --config is a Python dict
+file like the reference's (`dict(...)` or `{...}`, read without executing it).  `ensemble` mode
+(main.py:623-747) is outside the hot path.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import os
+import random
+import time
+
+import numpy as np
+
+from . import main as graph
+from . import models  # noqa: F401  (registers the model plugins, run.py:320)
+from . import saver
+from .data import Dataset
+from .params import global_params
+from .vocab import Vocab
+
+
+def _config_dict(path):
+    """The reference eval()s the file (run.py:370); its configs are `dict(key=value, ...)` calls or `{...}` literals
+    (docs/usage).  Both forms are read here without executing code."""
+    if not path or not os.path.exists(path):
+        return {}
+    node = ast.parse(open(path).read().strip(), mode="eval").body
+    if isinstance(node, ast.Call) and getattr(node.func, "id", None) == "dict" and not node.args:
+        return {kw.arg: ast.literal_eval(kw.value) for kw in node.keywords}
+    return ast.literal_eval(node)
+
+
+def build_params(config="", parameters="", defaults=None):
+    """run.py:367-376."""
+    params = defaults if defaults is not None else global_params()
+    cfg = _config_dict(config)
+    params.parse(parameters)
+    params.override_from_dict({k: v for k, v in cfg.items() if k in params})
+    params = saver.load_parameters(params, params.output_dir)
+    params.override_from_dict({k: v for k, v in cfg.items() if k in params})
+    params.parse(parameters)
+    return params
+
+
+def _refs(path):
+    """Reference files: `path` itself, else path0, path1, ... (utils/util.py fetch_valid_ref_files)."""
+    files = []
+    if os.path.exists(path):
+        files.append(path)
+    else:
+        while os.path.exists("%s%d" % (path, len(files))):
+            files.append("%s%d" % (path, len(files)))
+    return [[line.strip().split() for line in open(f)] for f in files]
+
+
+def run(mode, params, log=print):
+    random.seed(params.random_seed)
+    np.random.seed(params.random_seed)
+    t0 = time.time()
+    for key, f in (("src_vocab", params.src_vocab_file), ("tgt_vocab", params.tgt_vocab_file)):
+        if key in params:
+            setattr(params, key, Vocab(f))
+        else:
+            params.add_hparam(key, Vocab(f))
+    log("End Loading Vocabulary, Source Vocab Size %d, Target Vocab Size %d, within %.3f seconds" % (
+        params.src_vocab.size(), params.tgt_vocab.size(), time.time() - t0))
+
+    def dataset(src, tgt, max_len):
+        return Dataset(src, tgt, params.src_vocab, params.tgt_vocab, max_len, params.batch_or_token,
+                       params.data_leak_ratio)
+
+    if mode == "train":
+        saver.save_parameters(params, params.output_dir)
+        params = saver.setup_recorder(params)
+        dev = dataset(params.src_dev_file, params.src_dev_file, params.eval_max_len) if params.src_dev_file else None
+        refs = _refs(params.tgt_dev_file) if params.tgt_dev_file else None
+        return graph.train(params, dataset(params.src_train_file, params.tgt_train_file, params.max_len), dev, refs,
+                           log=log)
+    if mode == "test":
+        test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len)
+        res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log)
+        if params.test_output:
+            with open(params.test_output, "w") as f:
+                for hyp in res["translations"]:
+                    f.write(" ".join(hyp) + "\n")
+        return res
+    if mode == "score":
+        from . import evalu
+        from .models import model as registry
+        ds = dataset(params.src_test_file, params.tgt_test_file, params.eval_max_len)
+        scores, ppl = evalu.scoring(registry.get_model(params.model_name).score_fn, ds, params)
+        log("Scores %.4f, PPL %.4f" % (float(np.mean(scores)), ppl))
+        return {"scores": scores, "ppl": ppl}
+    raise ValueError("Invalid mode: {}".format(mode))
+
+
+def cli(argv=None):
+    ap = argparse.ArgumentParser(description="zero_b200: Zero's run.py surface on the B200 path")
+    ap.add_argument("--config", default="")
+    ap.add_argument("--parameters", default="")
+    ap.add_argument("--name", default="model")
+    ap.add_argument("--mode", default="train")
+    a = ap.parse_args(argv)
+    return run(a.mode, build_params(a.config, a.parameters))
+
+
+if __name__ == "__main__":
+    cli()

@@ -1,0 +1,159 @@
+"""Checkpoints and the training record (reference utils/saver.py:11-171, utils/recorder.py:10-23, run.py:250-296).
+
+The reference wraps tf.train.Saver: numbered checkpoints with keep-N rotation, a "best/" directory of the top-k
+checkpoints by dev score, restore of the latest, and a name-matched fallback for partially compatible models
+(utils/saver.py:150-171).  TF's file format is not reproducible without TF; what IS kept is the contract that
+matters for interchange: every tensor is stored under its TF variable name, so a dump of a
+Zero checkpoint into {name: array} loads with `restore_state_dict`.  Files are .npz; optimizer slots are stored as
+"<name>/Adam" and "<name>/Adam_1" like TF names its Adam slots; `global_step` rides along.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+
+import numpy as np
+import torch
+
+
+class Recorder(object):
+    """utils/recorder.py: attribute bag <-> record.json (the fields of run.py:276-296)."""
+
+    def load_from_json(self, file_name):
+        with open(file_name, "r") as f:
+            self.__dict__.update(json.load(f))
+
+    def save_to_json(self, file_name):
+        with open(file_name, "w") as f:
+            json.dump({k: v for k, v in self.__dict__.items() if _jsonable(v)}, f, indent=2)
+
+
+def _jsonable(v):
+    try:
+        json.dumps(v)
+        return True
+    except TypeError:
+        return False
+
+
+def setup_recorder(params):
+    """run.py:276-301."""
+    r = Recorder()
+    r.bad_counter, r.estop, r.lidx, r.step, r.epoch = 0, False, -1, 0, 1
+    r.lrate, r.history_scores, r.valid_script_scores = params.lrate, [], []
+    path = os.path.abspath(os.path.join(params.output_dir, "record.json"))
+    if os.path.exists(path):
+        r.load_from_json(path)
+    if "recorder" in params:
+        params.recorder = r
+    else:
+        params.add_hparam("recorder", r)
+    return params
+
+
+def save_parameters(params, output_dir):
+    """run.py:250-259."""
+    os.makedirs(output_dir, exist_ok=True)
+    with open(os.path.join(output_dir, "param.json"), "w") as f:
+        f.write(params.to_json())
+
+
+def load_parameters(params, output_dir):
+    """run.py:262-273."""
+    path = os.path.abspath(os.path.join(output_dir, "param.json"))
+    if os.path.exists(path):
+        with open(path, "r") as f:
+            params.parse_json(f.readline())
+    return params
+
+
+class Saver(object):
+    def __init__(self, checkpoints=5, output_dir=None, best_score=-1, best_checkpoints=1):
+        self.output_dir = output_dir or "./output"
+        self.best_dir = os.path.join(self.output_dir, "best")
+        self.checkpoints, self.best_checkpoints = int(checkpoints), int(best_checkpoints)
+        self.best_score = best_score
+        os.makedirs(self.best_dir, exist_ok=True)
+        self._index = os.path.join(self.output_dir, "checkpoint.json")
+        self._meta = {"all": [], "best": []}
+        if os.path.exists(self._index):
+            self._meta = json.load(open(self._index))
+
+    # -- state <-> arrays --------------------------------------------------------------------------------
+    @staticmethod
+    def state_of(engine, trainer=None):
+        """{TF variable name: fp32 array} (+ Adam slots and global_step when a trainer is given)."""
+        ps = engine.ps
+        out = {k: ps.tf_view(ps.master, k).detach().float().cpu().numpy() for k in ps.tf_names()}
+        if trainer is not None and ps.adam_m is not None:
+            for k in ps.tf_names():
+                out[k + "/Adam"] = ps.tf_view(ps.adam_m, k).detach().cpu().numpy()
+                out[k + "/Adam_1"] = ps.tf_view(ps.adam_v, k).detach().cpu().numpy()
+            out["global_step"] = np.asarray(trainer.global_step, dtype=np.int64)
+        return out
+
+    @staticmethod
+    def restore_state_dict(engine, arrays, trainer=None, strict=False):
+        """Name-matched restore (utils/saver.py:150-171): variables present under the same name and shape are
+        loaded, the rest keep their values; returns (loaded, skipped) name lists."""
+        ps = engine.ps
+        loaded, skipped = [], []
+        for k in ps.tf_names():
+            if k in arrays and tuple(arrays[k].shape) == tuple(ps.tf_view(ps.master, k).shape):
+                ps.tf_view(ps.master, k).copy_(torch.as_tensor(np.asarray(arrays[k])).to(ps.device, torch.float32))
+                loaded.append(k)
+                if trainer is not None and k + "/Adam" in arrays and ps.adam_m is not None:
+                    ps.tf_view(ps.adam_m, k).copy_(torch.as_tensor(np.asarray(arrays[k + "/Adam"])).to(ps.device))
+                    ps.tf_view(ps.adam_v, k).copy_(torch.as_tensor(np.asarray(arrays[k + "/Adam_1"])).to(ps.device))
+            else:
+                skipped.append(k)
+        if strict and skipped:
+            raise KeyError("checkpoint misses or mismatches %s" % skipped[:4])
+        if trainer is not None and "global_step" in arrays:
+            trainer.global_step = int(arrays["global_step"])
+        ps.refresh_mirror()
+        return loaded, skipped
+
+    # -- files -------------------------------------------------------------------------------------------
+    def save(self, engine, step, metric_score=None, trainer=None):
+        """utils/saver.py:42-103: write model-<step>, rotate to keep the newest `checkpoints`; with a score, keep
+        the `best_checkpoints` highest-scoring copies under best/."""
+        arrays = self.state_of(engine, trainer)
+        name = "model-%d.npz" % int(step)
+        path = os.path.join(self.output_dir, name)
+        np.savez(path, **arrays)
+        if name not in self._meta["all"]:
+            self._meta["all"].append(name)
+        while len(self._meta["all"]) > self.checkpoints:
+            old = self._meta["all"].pop(0)
+            if os.path.exists(os.path.join(self.output_dir, old)):
+                os.remove(os.path.join(self.output_dir, old))
+        if metric_score is not None and self.best_checkpoints > 0:
+            best = self._meta["best"]
+            if len(best) < self.best_checkpoints or metric_score > min(s for _, s in best):
+                shutil.copy(path, os.path.join(self.best_dir, name))
+                best.append([name, float(metric_score)])
+                best.sort(key=lambda p: -p[1])
+                for old, _ in best[self.best_checkpoints:]:
+                    if os.path.exists(os.path.join(self.best_dir, old)):
+                        os.remove(os.path.join(self.best_dir, old))
+                del best[self.best_checkpoints:]
+                self.best_score = best[0][1]
+        json.dump(self._meta, open(self._index, "w"))
+        return path
+
+    def latest(self, directory=None):
+        directory = directory or self.output_dir
+        if directory == self.best_dir:
+            return os.path.join(directory, self._meta["best"][0][0]) if self._meta["best"] else None
+        return os.path.join(directory, self._meta["all"][-1]) if self._meta["all"] else None
+
+    def restore(self, engine, path=None, trainer=None):
+        """utils/saver.py:105-148: load `path`, else the latest checkpoint; False when there is none."""
+        path = path or self.latest()
+        if path is None or not os.path.exists(path):
+            return False
+        with np.load(path) as z:
+            self.restore_state_dict(engine, {k: z[k] for k in z.files}, trainer)
+        return True
