@@ -55,15 +55,46 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _nvml(self):
+        """NVML in-process (sub-millisecond per sample); None when the binding or the driver call is unavailable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "Active"),
+                    (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "Active"),
+                    (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "Active"),
+                    (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "Active")]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def sample():
+                r = int(get_reasons(h))
+                return [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                        "%.1f" % (nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] + \
+                       ["Active" if r & b else "Not Active" for b, _ in bits]
+            sample()
+            return sample
+        except Exception:
+            return None
+
     def run(self):
+        sample = self._nvml()
+        self.source = "nvml" if sample else "nvidia-smi"
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+                if sample:
+                    self.rows.append(sample())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.01 if sample else 0.05)
 
     def stop(self):
         self._halt.set()
@@ -77,7 +108,7 @@ class ClockSampler(threading.Thread):
                 if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": getattr(self, "source", None)}
 
 
 # ---------------------------------------------------------------------------------------------- CPU oracle leg
@@ -395,7 +426,7 @@ def main():
         run_reference(args)
     else:
         args.steps = 100 if args.steps is None else args.steps
-        args.warmup = 5 if args.warmup is None else args.warmup
+        args.warmup = 10 if args.warmup is None else args.warmup
         run_ours(args)
 
 

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--csv", default=None)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--decode", action="store_true",
+                    help="trace the beam-4 cached decode of BASELINE configs[2] (one batch) instead of the training step")
     args = ap.parse_args()
     import torch
     from torch.profiler import ProfilerActivity, profile
@@ -29,18 +31,37 @@ def main():
     from zero_b200.params import transformer_base
     from zero_b200.train import Trainer
 
-    hp = transformer_base()
-    eng = Engine(hp, bench.VOCAB, bench.VOCAB, device="cuda:0")
-    eng.ps.init_random(1234)
-    trainer = Trainer(eng, hp, world_size=1, use_graph=not args.no_graph)
-    batches = [tuple(t.cuda() for t in bench.make_batch(i, bench.B_PER_GPU)) for i in range(4)]
-    for i in range(6):
-        trainer.step(*batches[i % 4])
-    torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(args.steps):
+    if args.decode:
+        from zero_b200 import search
+        from zero_b200.params import SimpleVocab
+        hp = transformer_base(model_name="transformer_aan", scope_name="transformer_aan", use_ffn=False, aan_mask=True,
+                              beam_size=4, decode_length=0, decode_alpha=0.6)
+        hp.add_hparam("decode_graph", not args.no_graph)
+        hp.add_hparam("src_vocab", SimpleVocab(bench.VOCAB))
+        hp.add_hparam("tgt_vocab", SimpleVocab(bench.VOCAB))
+        eng = Engine(hp, bench.VOCAB, bench.VOCAB, device="cuda:0")
+        eng.ps.init_random(7)
+        eng.decode_length = 0
+        for i in range(3):
+            search.beam_search({"source": bench.make_batch(500 + i, 64)[0]}, eng.encoding_fn, eng.decoding_fn, hp)
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            out = search.beam_search({"source": bench.make_batch(503, 64)[0]}, eng.encoding_fn, eng.decoding_fn, hp)
+            torch.cuda.synchronize()
+        args.steps = int(out["seq"].shape[-1])     # per-"step" figures below are per decode step
+    else:
+        hp = transformer_base()
+        eng = Engine(hp, bench.VOCAB, bench.VOCAB, device="cuda:0")
+        eng.ps.init_random(1234)
+        trainer = Trainer(eng, hp, world_size=1, use_graph=not args.no_graph)
+        batches = [tuple(t.cuda() for t in bench.make_batch(i, bench.B_PER_GPU)) for i in range(4)]
+        for i in range(6):
             trainer.step(*batches[i % 4])
         torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(args.steps):
+                trainer.step(*batches[i % 4])
+            torch.cuda.synchronize()
     evs = []
     for e in prof.events():
         if str(e.device_type).endswith("CUDA"):
@@ -74,7 +95,7 @@ def main():
     gaps.sort(reverse=True)
     print("idle gaps: n=%d total %.1f us / step, largest %s" % (
         len(gaps), sum(gaps) / args.steps, ["%.1f" % g for g in gaps[:8]]))
-    for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:28]:
+    for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:
         print("%-60s n/step=%6.1f avg %7.2f us  total/step %8.1f us  %5.1f%%" % (
             n, c / args.steps, t / c, t / args.steps, 100.0 * t / span))
     if args.csv:
