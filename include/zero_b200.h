@@ -24,7 +24,7 @@ extern "C" {
 
 typedef struct CUstream_st* zb_stream_t; /* == cudaStream_t */
 
-#define ZB_ABI_VERSION 1
+#define ZB_ABI_VERSION 2
 
 typedef enum {
   ZB_OK = 0,
@@ -257,6 +257,9 @@ typedef struct {
   /* loop control: zb_beam_cond writes active[0] = search.py:85-113's _not_finished(time); zb_beam_step is a
    * no-op when active[0] == 0, so the host may poll the flag every few steps without changing the result */
   int32_t* active;       /* [1] device */
+  /* optional scratch of the row-parallel kernel (one CTA per (sentence, beam) row): batch * (4 * beam^2 + 1) 4-byte
+   * words, zeroed ONCE by the caller (the kernel leaves it zeroed); NULL = one CTA per sentence */
+  float* row_ws;
 } zb_beam_args;
 int zb_beam_cond(const zb_beam_args* a, zb_stream_t stream);
 int zb_beam_step(const zb_beam_args* a, zb_stream_t stream);

@@ -42,6 +42,31 @@ def test_gemm_layouts(m, n, k, a_mn, b_mn):
     torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
 
 
+@pytest.mark.parametrize("m,n,k", [(256, 512, 512), (256, 2048, 512), (256, 512, 2048), (256, 1024, 1024),
+                                   (100, 128, 64), (1, 64, 192), (384, 1536, 512), (37, 384, 128)])
+@pytest.mark.parametrize("b_mn", [1, 0])
+def test_gemm_skinny_rows(m, n, k, b_mn):
+    """The decode-step GEMM (gemm_skinny.cu: m <= 384 rows, 64 x 64 tiles, mma.sync) on the projections of one
+    cached decode step at configs[2] (256 rows) and on ragged row counts: plain fp32 output, then the
+    bias + relu epilogue into a strided bf16 destination (func.linear writing into the [rows, cap, 3d] cache)."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    x = rnd(m, k, seed=11)
+    w = rnd(k, n, scale=0.05, seed=12)            # [in, out] like func.linear's W
+    b_st = w if b_mn else w.t().contiguous()      # MN-major = [k][n]; K-major = [n][k]
+    out = torch.zeros(m, n, dtype=f32, device=dev())
+    ops.gemm(x, b_st, out, L.ZB_K_MAJOR, L.ZB_MN_MAJOR if b_mn else L.ZB_K_MAJOR)
+    ref = x.float() @ w.float()
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
+    if b_mn:
+        bias = torch.randn(n, device=dev())
+        buf = torch.full((m, 3, n + 64), 7.0, dtype=bf16, device=dev())
+        ops.linear_fwd(x, w, bias, buf[:, 1, :n], relu=True)
+        torch.testing.assert_close(buf[:, 1, :n].float(), torch.relu(ref + bias), atol=3e-2, rtol=2e-2)
+        assert float((buf[:, 0] - 7).abs().max()) == 0 and float((buf[:, 2] - 7).abs().max()) == 0
+        assert float((buf[:, 1, n:] - 7).abs().max()) == 0
+
+
 def test_gemm_epilogues_and_splitk():
     from zero_b200 import ops
     m, n, k = 512, 1536, 4096
@@ -302,6 +327,48 @@ def test_attention_cached_decode_step():
 
 
 # ------------------------------------------------------------------------------------------------ optimizer / misc
+@pytest.mark.parametrize("cfg", [
+    dict(B=64, K=4, h=8, dh=64, S=64, relu=False),     # BASELINE configs[2] cross-attention shape
+    dict(B=5, K=3, h=2, dh=16, S=70, relu=False),      # ragged key tile, odd group size
+    dict(B=2, K=12, h=2, dh=32, S=33, relu=False),     # more rows per memory than warps in the CTA
+    dict(B=3, K=1, h=4, dh=64, S=100, relu=True),      # ReLA decode (modules/rela.py:52-75)
+])
+def test_attention_decode_kernel(cfg):
+    """The lq = 1 kernel (one warp per (row, head)): per-sentence memories shared by the beams, key-length masks,
+    self-attention against a strided, partly filled cache with the causal offset, and the log-sum-exp output."""
+    from zero_b200 import ops
+    B, K, h, dh, S = cfg["B"], cfg["K"], cfg["h"], cfg["dh"], cfg["S"]
+    D = h * dh
+    q = rnd(B * K, 1, D, seed=1)
+    mem = rnd(B, S, 2 * D, seed=2)                      # fused [k | v] memory like the engine's
+    key_len = torch.randint(1, S + 1, (B,), dtype=torch.int32, device=dev())
+    key_len[0] = S
+    o = torch.empty(B * K, 1, D, dtype=bf16, device=dev())
+    lse = torch.empty(B * K, h, 1, device=dev())
+    a = ops.attention_args(q, mem[:, :, :D], mem[:, :, D:], o, h, key_len=key_len, kv_group=K, lse=lse,
+                           relu_attn=cfg["relu"])
+    ops.attention_fwd(a)
+    kf, vf = mem[:, :, :D].float().repeat_interleave(K, 0), mem[:, :, D:].float().repeat_interleave(K, 0)
+    ref = _attn_ref(q.float(), kf, vf, h, key_len.repeat_interleave(K), False, 0, 1e8, None, None, 0, cfg["relu"])
+    torch.testing.assert_close(o.float(), ref, atol=3e-2, rtol=3e-2)
+    if not cfg["relu"]:
+        from oracle import zero_oracle as zo
+        qh, kh = zo.heads_split(q.float(), h) * dh ** -0.5, zo.heads_split(kf, h)
+        pad = torch.arange(S, device=dev())[None, :] >= key_len.repeat_interleave(K)[:, None].long()
+        want = torch.logsumexp(qh @ kh.transpose(-1, -2) + pad[:, None, None, :].float() * -1e8, -1)
+        torch.testing.assert_close(lse, want, atol=2e-2, rtol=2e-2)
+    # self-attention step t against a [rows, cap, 3D] cache: keys 0..t valid, q_offset = t
+    R, cap, t = B * K, S + 3, S - 1
+    cache = rnd(R, cap, 3 * D, seed=5)
+    o2 = torch.empty(R, 1, D, dtype=bf16, device=dev())
+    a = ops.attention_args(cache[:, t:t + 1, :D], cache[:, :t + 1, D:2 * D], cache[:, :t + 1, 2 * D:], o2, h,
+                           q_offset=t, causal=True, relu_attn=cfg["relu"])
+    ops.attention_fwd(a)
+    ref2 = _attn_ref(cache[:, t:t + 1, :D].float(), cache[:, :t + 1, D:2 * D].float(), cache[:, :t + 1, 2 * D:].float(),
+                     h, None, True, t, 1e8, None, None, 0, cfg["relu"])
+    torch.testing.assert_close(o2.float(), ref2, atol=3e-2, rtol=3e-2)
+
+
 def test_adam_tf_and_sumsq_and_colsum():
     from oracle import zero_oracle as zo
     from zero_b200 import ops
@@ -388,3 +455,40 @@ def test_beam_step_matches_oracle_step_for_step():
     assert t == want["steps"]
     np.testing.assert_array_equal(got["seq"].cpu().numpy(), want["seq"].numpy())
     np.testing.assert_allclose(got["score"].cpu().numpy(), want["score"].numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,K,V", [(3, 1, 64), (4, 3, 207), (2, 5, 1000), (64, 4, 32000), (2, 8, 60001), (2, 2, 50000)])
+def test_beam_row_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
+    """The row-parallel step kernel (one CTA per (sentence, beam) row, last-arriver merge) against the
+    one-CTA-per-sentence kernel on the same logits, step for step: sequences, parents and flags bit-exact, scores
+    to fp32 round-off (the two kernels sum the soft-max normaliser in different orders).  Covers vocabularies that
+    are / are not a multiple of 4 (vector vs scalar staging), beyond the shared-memory staging limit, beams 1..8."""
+    from zero_b200.search import BeamState
+    g = torch.Generator().manual_seed(V + K)
+    S = 6
+    src = torch.randint(3, 50, (B, S), generator=g)
+    src[0, 3:] = 0
+    states = []
+    for rows in ("0", "1"):
+        monkeypatch.setenv("ZB_BEAM_ROWS", rows)
+        states.append(BeamState(B, K, V, src.to(dev()), 4, 0.6, 1.0 if V != 1000 else 0.7, 1e8, dev()))
+    assert states[0].row_ws is None and states[1].row_ws is not None
+    t = 0
+    while True:
+        nf = [st.not_finished(t) for st in states]
+        assert nf[0] == nf[1]
+        if not nf[0]:
+            break
+        lg = (torch.randn(B * K, V, generator=g) * 3)
+        lg[:, 2] += 3.0 if t % 3 == 2 else -1.0
+        lg = lg.to(dev())
+        for st in states:
+            st.step(lg, t)
+        for name in ("alive_seq", "fin_seq", "fin_flag", "parent"):
+            assert torch.equal(getattr(states[0], name), getattr(states[1], name)), (name, t)
+        for name in ("alive_logp", "alive_score", "fin_score"):
+            torch.testing.assert_close(getattr(states[0], name), getattr(states[1], name), rtol=1e-5, atol=1e-5)
+        t += 1
+    assert t >= 3
+    # the arrival tickets (last word of each sentence's scratch) are back to zero after every step
+    assert int(states[1].row_ws.view(torch.int32).view(B, -1)[:, -1].abs().sum()) == 0

@@ -5,6 +5,8 @@
 namespace zb {
 int attention_generic_fwd(const zb_attention_args* a, cudaStream_t st);
 int attention_generic_bwd(const zb_attention_args* a, cudaStream_t st);
+bool attention_decode_supported(const zb_attention_args* a);
+int attention_decode_fwd(const zb_attention_args* a, cudaStream_t st);
 bool attention_mma_supported(const zb_attention_args* a, bool bwd);
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st);
 int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st);
@@ -30,6 +32,7 @@ extern "C" int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream) 
   if (rc) return rc;
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (attention_decode_supported(a)) return attention_decode_fwd(a, st);
   if (attention_mma_supported(a, false)) return attention_mma_fwd(a, st);
   return attention_generic_fwd(a, st);
 }

@@ -8,6 +8,7 @@
 // tiles staged in shared memory, online softmax.  attention_mma.cu holds the tensor-core fast path for the
 // plain softmax case; this file is the path used when rpr / ReLA / odd head sizes are requested.
 #include <math.h>
+#include <stdlib.h>
 
 #include "zb_common.h"
 #include "zb_ptx.cuh"
@@ -450,6 +451,130 @@ static int set_smem(K kern, size_t bytes) {
     }
   }
   return ZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cached decode
+// lq = 1 (one new target position per row, func.py:199-216 with the cache): the tiled kernel above would leave seven
+// of its eight warps idle and run one CTA per (row, head).  Here one warp owns one (row, head): lanes split the keys
+// for q.k (16-byte loads of a key's head slice), the softmax runs on shuffles, and for p.v each lane owns head
+// channels lane, lane+32 so a value row is one coalesced read.  The rows that share a memory (the beams of a sentence,
+// kv_group) sit in the same CTA, so their K / V reads hit L1 after the first warp.  No shared memory.
+template <int DH>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnP p) {
+  grid_dep_wait();
+  constexpr int ND = (DH + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int kl = p.key_len ? p.key_len[g] : p.lk;
+  const __nv_bfloat16* kbase = p.k + (long long)g * p.bsk + h * DH;
+  const __nv_bfloat16* vbase = p.v + (long long)g * p.bsv + h * DH;
+  const int i_abs = p.q_offset;
+  for (int r = warp; r < p.kv_group; r += nwarp) {
+    const int b = g * p.kv_group + r;
+    float qr[DH];
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.bsq + h * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 8; ++c) {
+        const uint4 u = qp[c];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          qr[8 * c + 2 * e] = f.x * p.scale;
+          qr[8 * c + 2 * e + 1] = f.y * p.scale;
+        }
+      }
+    }
+    float m = -INFINITY, l = 0.f, o[ND];
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) o[dd] = 0.f;
+    for (int kt = 0; kt < p.lk; kt += 32) {
+      const int j = kt + lane;
+      const bool inb = j < p.lk;
+      float s = 0.f;
+      if (inb) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * p.ldk);
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          const uint4 u = kp[c];
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h2[e]);
+            s += qr[8 * c + 2 * e] * f.x;
+            s += qr[8 * c + 2 * e + 1] * f.y;
+          }
+        }
+      }
+      const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
+      float pj;
+      if (p.relu_attn) {
+        pj = valid ? fmaxf(s, 0.f) : 0.f;
+      } else {
+        s = inb ? (valid ? s : s - p.inf_value) : -INFINITY;
+        const float m_new = fmaxf(m, wmax(s));
+        pj = inb ? __expf(s - m_new) : 0.f;
+        const float corr = __expf(m - m_new);
+        l = l * corr + wsum(pj);
+        m = m_new;
+#pragma unroll
+        for (int dd = 0; dd < ND; ++dd) o[dd] *= corr;
+      }
+      const int nv = min(32, p.lk - kt);
+#pragma unroll 8
+      for (int jj = 0; jj < nv; ++jj) {
+        const float pv = __shfl_sync(0xffffffffu, pj, jj);
+        const __nv_bfloat16* vp = vbase + (long long)(kt + jj) * p.ldv;
+#pragma unroll
+        for (int dd = 0; dd < ND; ++dd) {
+          const int d = lane + 32 * dd;
+          if (d < DH) o[dd] += pv * __bfloat162float(vp[d]);
+        }
+      }
+    }
+    const float inv = p.relu_attn ? 1.f : 1.f / l;
+    __nv_bfloat16* op = p.o + (long long)b * p.bso + h * DH;
+#pragma unroll
+    for (int dd = 0; dd < ND; ++dd) {
+      const int d = lane + 32 * dd;
+      if (d < DH) op[d] = __float2bfloat16(o[dd] * inv);
+    }
+    if (lane == 0 && p.lse) p.lse[(long long)b * p.heads + h] = p.relu_attn ? 0.f : m + __logf(l);
+  }
+}
+
+static bool decode_path_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ZB_DECODE_ATTN");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// lq = 1, plain or ReLU attention without relative positions or dropout, 16-byte aligned head slices
+bool attention_decode_supported(const zb_attention_args* a) {
+  if (!decode_path_enabled()) return false;
+  if (a->lq != 1 || a->rpr_k || (a->dropout_seed && a->dropout_rate > 0.f)) return false;
+  if (a->dh != 16 && a->dh != 32 && a->dh != 64) return false;
+  const int grp = a->kv_group > 0 ? a->kv_group : 1;
+  if (a->batch % grp) return false;
+  auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  if (!al16(a->q) || !al16(a->k)) return false;
+  if ((a->bsq % 8) || (a->bsk % 8) || (a->ldk % 8)) return false;
+  return true;
+}
+
+int attention_decode_fwd(const zb_attention_args* a, cudaStream_t st) {
+  AttnP p = to_params(a);
+  const int warps = p.kv_group < 8 ? p.kv_group : 8;
+  const dim3 grid(a->batch / p.kv_group, a->heads);
+  switch (a->dh) {
+    case 16: ZB_LAUNCH(attn_decode_kernel<16>, grid, warps * 32, 0, st, p); break;
+    case 32: ZB_LAUNCH(attn_decode_kernel<32>, grid, warps * 32, 0, st, p); break;
+    default: ZB_LAUNCH(attn_decode_kernel<64>, grid, warps * 32, 0, st, p); break;
+  }
+  return check_launch("zb_attention_fwd(decode)");
 }
 
 int attention_generic_fwd(const zb_attention_args* a, cudaStream_t st) {

@@ -236,6 +236,241 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const zb_beam_a
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row-parallel step
+// One CTA per (sentence, beam) row instead of one per sentence: batch * beam CTAs fill the machine where `batch` CTAs
+// left most SMs idle, and each CTA reads its row of logits from HBM / L2 exactly once (staged in shared memory, then
+// max, sum-exp and candidate scan run out of shared memory).  A row's top-2k candidates are exact (same score
+// arithmetic and (score, flat index) order as the reference's top_k over beam*V), so the top-2k of the sentence is
+// the top-2k of the union of its rows' lists.  The last CTA of a sentence to publish its list (atomic ticket in
+// row_ws, the classic fence + counter hand-off) merges the lists and does the bookkeeping of search.py:179-228.
+
+// Pop the n best entries of the lanes' sorted lists (head-of-list arg-max over the warp, n rounds); every lane
+// returns with the r-th winner in (ws[r], wi[r]) if `keep`, else lane 0 stores it to out_s / out_i.
+template <int N>
+__device__ __forceinline__ void warp_pop(const float (&ls)[N], const int (&li)[N], int n, float* out_s, int* out_i) {
+  const int lane = threadIdx.x & 31;
+  int head = 0;
+  for (int r = 0; r < n; ++r) {
+    float hs = -INFINITY;
+    int hi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (k == head) {
+        hs = ls[k];
+        hi = li[k];
+      }
+    float bs = hs;
+    int bidx = hi, bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bidx, o);
+      const int l2 = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (better(s2, i2, bs, bidx)) {
+        bs = s2;
+        bidx = i2;
+        bl = l2;
+      }
+    }
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    bidx = __shfl_sync(0xffffffffu, bidx, 0);
+    bl = __shfl_sync(0xffffffffu, bl, 0);
+    if (lane == bl) ++head;
+    if (lane == 0) {
+      out_s[r] = bs;
+      out_i[r] = bidx;
+    }
+  }
+}
+
+constexpr int kRowThreads = 512;
+
+template <int N2>
+__global__ void __launch_bounds__(kRowThreads) beam_row_kernel(const zb_beam_args a, const int stage) {
+  grid_dep_wait();
+  if (a.active && a.active[0] == 0) return;
+  const int K = a.beam, V = a.vocab, t = a.time, cap = a.seq_cap;
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kRowThreads / 32;
+  const int n2 = 2 * K;
+  extern __shared__ __align__(16) float row_smem[];
+  __shared__ float red[NW];
+  __shared__ float bcast;
+  __shared__ float wl_s[NW * N2];   // per-warp winners, later the row's / the sentence's winners
+  __shared__ int wl_i[NW * N2];
+  __shared__ int is_last;
+  __shared__ float top_s[2 * kMaxBeam];
+  __shared__ int top_i[2 * kMaxBeam];
+  __shared__ int bi[2 * kMaxBeam], wi[2 * kMaxBeam], done[2 * kMaxBeam];
+  __shared__ float tmpv[3 * kMaxBeam], a_s[kMaxBeam], f_s[kMaxBeam];
+  __shared__ int a_i[kMaxBeam], f_i[kMaxBeam], new_flag[kMaxBeam];
+
+  const float* grow = a.logits + ((long long)b * K + k) * V;
+  const bool t_one = a.temperature == 1.f;
+  // ---- pass 1: stage x = logits / T in shared memory (when it fits), row max
+  float m = -INFINITY;
+  const float* src = grow;
+  if (stage) {
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(grow) & 15u) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(grow);
+      float4* s4 = reinterpret_cast<float4*>(row_smem);
+      for (int w = tid; w < V / 4; w += kRowThreads) {
+        float4 x = g4[w];
+        if (!t_one) {
+          x.x = x.x / a.temperature; x.y = x.y / a.temperature; x.z = x.z / a.temperature; x.w = x.w / a.temperature;
+        }
+        s4[w] = x;
+        m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+      }
+    } else {
+      for (int w = tid; w < V; w += kRowThreads) {
+        const float x = t_one ? grow[w] : grow[w] / a.temperature;
+        row_smem[w] = x;
+        m = fmaxf(m, x);
+      }
+    }
+    src = row_smem;
+  } else {
+    for (int w = tid; w < V; w += kRowThreads) m = fmaxf(m, t_one ? grow[w] : grow[w] / a.temperature);
+  }
+  const bool scaled = stage || t_one;   // src already holds logits / T
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float M = red[0];
+    for (int w = 1; w < NW; ++w) M = fmaxf(M, red[w]);
+    bcast = M;
+  }
+  __syncthreads();
+  const float M = bcast;
+  // ---- pass 2: sum exp(x - max)
+  float sum = 0.f;
+  for (int w = tid; w < V; w += kRowThreads) {
+    const float x = scaled ? src[w] : src[w] / a.temperature;
+    sum += __expf(x - M);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();   // red / bcast reuse
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float S = 0.f;
+    for (int w = 0; w < NW; ++w) S += red[w];
+    bcast = M + logf(S);
+  }
+  __syncthreads();
+  const float l = bcast;
+  // ---- pass 3: candidate scores of the row (search.py:148-170), per-thread sorted top-2k lists
+  float ls[N2];
+  int li[N2];
+#pragma unroll
+  for (int c = 0; c < N2; ++c) {
+    ls[c] = -INFINITY;
+    li[c] = 0x7fffffff;
+  }
+  const float pen = a.length_penalty;
+  const float lp_prev = a.alive_logp[b * K + k];
+  for (int w = tid; w < V; w += kRowThreads) {
+    const float x = scaled ? src[w] : src[w] / a.temperature;
+    float lp = x - l;
+    if (t < 1 && w == a.eos_id) lp = lp + (-a.inf_value);
+    const float sc = (lp_prev + lp) / pen;
+    list_insert<N2>(ls, li, sc, k * V + w);
+  }
+  // warp winners -> shared, then warp 0 reduces the NW * n2 warp winners to the row's n2
+  warp_pop<N2>(ls, li, n2, wl_s + warp * N2, wl_i + warp * N2);
+  __syncthreads();
+  float* ws_s = a.row_ws + (long long)b * (4 * K * K + 1);
+  int* ws_i = reinterpret_cast<int*>(ws_s) + 2 * K * K;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws_s) + 4 * K * K;
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < NW * n2; c += 32) {
+      const int w = c / n2, r = c % n2;
+      list_insert<N2>(ls, li, wl_s[w * N2 + r], wl_i[w * N2 + r]);
+    }
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, top_s, top_i);
+    __syncwarp();
+    if (lane < n2) {
+      ws_s[k * n2 + lane] = top_s[lane];
+      ws_i[k * n2 + lane] = top_i[lane];
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned prev = atomicAdd(ticket, 1u);
+      is_last = prev == (unsigned)(K - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // ---- the sentence's last row: merge the K lists (K * 2K <= 128 candidates), then search.py:179-228
+  __threadfence();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < K * n2; c += 32) list_insert<N2>(ls, li, __ldcg(ws_s + c), __ldcg(ws_i + c));
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, top_s, top_i);
+    if (lane == 0) *ticket = 0u;   // ready for the next step
+  }
+  __syncthreads();
+  const int max_len = a.max_len[b];
+  if (tid < n2) {
+    bi[tid] = top_i[tid] / V;
+    wi[tid] = top_i[tid] % V;
+    done[tid] = (wi[tid] == a.eos_id) || (t >= max_len);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = 0; c < n2; ++c) tmpv[c] = top_s[c] + (float)done[c] * F32_MIN;
+    small_topk(tmpv, n2, K, a_s, a_i);
+    for (int c = 0; c < K; ++c) tmpv[c] = a.fin_score[b * K + c];
+    for (int c = 0; c < n2; ++c) tmpv[K + c] = top_s[c] + (1.0f - (float)done[c]) * F32_MIN;
+    small_topk(tmpv, 3 * K, K, f_s, f_i);
+    for (int c = 0; c < K; ++c) new_flag[c] = f_i[c] < K ? a.fin_flag[b * K + f_i[c]] : done[f_i[c] - K];
+  }
+  __syncthreads();
+  int* tmp = a.tmp_seq + (long long)b * 3 * K * cap;
+  const int newlen = t + 2;
+  for (int idx = tid; idx < 3 * K * newlen; idx += kRowThreads) {
+    const int r = idx / newlen, pos = idx % newlen;
+    int val;
+    if (r < K) {
+      val = pos <= t ? a.fin_seq[((long long)b * K + r) * cap + pos] : a.pad_id;
+    } else {
+      const int c = r - K;
+      val = pos <= t ? a.alive_seq[((long long)b * K + bi[c]) * cap + pos] : wi[c];
+    }
+    tmp[r * cap + pos] = val;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < K * newlen; idx += kRowThreads) {
+    const int c = idx / newlen, pos = idx % newlen;
+    a.alive_seq[((long long)b * K + c) * cap + pos] = tmp[(K + a_i[c]) * cap + pos];
+    a.fin_seq[((long long)b * K + c) * cap + pos] = tmp[f_i[c] * cap + pos];
+  }
+  if (tid < K) {
+    a.alive_logp[b * K + tid] = a_s[tid] * pen;
+    a.alive_score[b * K + tid] = a_s[tid];
+    a.fin_score[b * K + tid] = f_s[tid];
+    a.fin_flag[b * K + tid] = new_flag[tid];
+    a.parent[b * K + tid] = b * K + bi[a_i[tid]];
+  }
+}
+
 // search.py:85-113 _not_finished(time): not(all_b(worst finished > best alive bound)) and any_b(time < max_len)
 __global__ void beam_cond_kernel(const zb_beam_args a) {
   grid_dep_wait();
@@ -274,6 +509,21 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   ZB_REQUIRE((long long)a->beam * a->vocab < (1ll << 31), "zb_beam_step: beam * vocab overflows int32");
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->row_ws) {
+    // row-parallel kernel: stage the row in shared memory when it fits beside the static buffers
+    const size_t row_bytes = (size_t)a->vocab * sizeof(float);
+    const int stage = row_bytes <= 200 * 1024 ? 1 : 0;
+    const size_t smem = stage ? row_bytes : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(beam_row_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(beam_row_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    if (2 * a->beam <= 8) ZB_LAUNCH(beam_row_kernel<8>, a->batch * a->beam, kRowThreads, smem, st, *a, stage);
+    else ZB_LAUNCH(beam_row_kernel<16>, a->batch * a->beam, kRowThreads, smem, st, *a, stage);
+    return check_launch("zb_beam_step(rows)");
+  }
   if (2 * a->beam <= 8) ZB_LAUNCH(beam_step_kernel<8>, a->batch, kBeamThreads, 0, st, *a);
   else ZB_LAUNCH(beam_step_kernel<16>, a->batch, kBeamThreads, 0, st, *a);
   return check_launch("zb_beam_step");

@@ -21,6 +21,8 @@
 
 namespace zb {
 
+bool gemm_skinny_wanted(const zb_gemm_args* a);
+int gemm_skinny_launch(const zb_gemm_args* a, cudaStream_t st);
 bool gemm2_wanted(const zb_gemm_args* a);
 int gemm2_launch(const zb_gemm_args* a, cudaStream_t st);
 int gemm2_launch_group(const zb_gemm_args* args, int count, cudaStream_t st);
@@ -519,6 +521,8 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   int vrc = validate_gemm(a);
   if (vrc) return vrc;
   const bool accum = a->flags & ZB_EPI_ACCUM;
+  // a few hundred rows (the cached decode step): latency-bound, small-tile kernel of gemm_skinny.cu
+  if (gemm_skinny_wanted(a)) return gemm_skinny_launch(a, reinterpret_cast<cudaStream_t>(stream));
   // CTA-pair kernel (tcgen05 cta_group::2, gemm2_tcgen05.cu) for everything with at least one 256 x 128 pair tile
   if (gemm2_wanted(a)) return gemm2_launch(a, reinterpret_cast<cudaStream_t>(stream));
 

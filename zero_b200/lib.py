@@ -75,7 +75,7 @@ class BeamArgs(C.Structure):
                 ("length_penalty", f32), ("max_len", vp), ("max_penalty", vp), ("seq_cap", i32),
                 ("alive_seq", vp), ("alive_logp", vp), ("alive_score", vp),
                 ("fin_seq", vp), ("fin_score", vp), ("fin_flag", vp), ("parent", vp), ("tmp_seq", vp),
-                ("active", vp)]
+                ("active", vp), ("row_ws", vp)]
 
 
 # every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
@@ -143,7 +143,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argt
         fn.restype = C.c_int
-    if lib.zb_abi_version() != 1:
+    if lib.zb_abi_version() != 2:
         raise ZeroB200Error("libzero_b200.so ABI version mismatch")
     lib.zb_abi_struct_size.argtypes = [i32]
     lib.zb_abi_struct_size.restype = C.c_int64

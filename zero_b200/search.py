@@ -9,9 +9,11 @@ tiled per beam the way search.py:36-39 does: per-sentence tensors (encoder outpu
 
 The reference wraps the step in a tf.while_loop (search.py:251); here every step index t owns a CUDA graph
 (decoder step + beam step + cache reorder, ~100 kernels) captured the second time that (shape, t) is seen and
-replayed afterwards, so the host only evaluates the loop condition.
+replayed afterwards, so the host only evaluates the loop condition - one step behind the device, see beam_search.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -45,7 +47,12 @@ class BeamState(object):
         self.parent = torch.arange(batch * beam, dtype=i32, device=device)
         self.tmp_seq = torch.zeros(batch, 3 * beam, self.cap, dtype=i32, device=device)
         self.active = torch.ones(1, dtype=i32, device=device)
+        # scratch of the row-parallel step kernel (one CTA per (sentence, beam) row); ZB_BEAM_ROWS=0 keeps the
+        # one-CTA-per-sentence kernel
+        self.row_ws = None if os.environ.get("ZB_BEAM_ROWS", "1") == "0" else \
+            torch.zeros(batch * (4 * beam * beam + 1), dtype=f32, device=device)
         self.tok_buf = torch.zeros(batch * beam, 1, dtype=i32, device=device)
+        self._host_flag, self._flag_events = None, None
         init_logp = torch.full((batch, beam), F32_MIN, dtype=f32)
         init_logp[:, 0] = 0.0
         self._init_logp = init_logp.to(device)
@@ -67,6 +74,8 @@ class BeamState(object):
         self.fin_seq.zero_()
         self.fin_score.fill_(F32_MIN)
         self.fin_flag.zero_()
+        if self.row_ws is not None:
+            self.row_ws.zero_()
         self.time = 0
 
     def _args(self, logits, t):
@@ -77,7 +86,7 @@ class BeamState(object):
             max_len=self.max_len, max_penalty=self.max_penalty, seq_cap=self.cap, alive_seq=self.alive_seq,
             alive_logp=self.alive_logp, alive_score=self.alive_score, fin_seq=self.fin_seq,
             fin_score=self.fin_score, fin_flag=self.fin_flag, parent=self.parent, tmp_seq=self.tmp_seq,
-            active=self.active)
+            active=self.active, row_ws=self.row_ws)
 
     def not_finished(self, t):
         """search.py:85-113, evaluated on the device; one 4-byte read-back."""
@@ -85,6 +94,24 @@ class BeamState(object):
             return False
         ops.beam_cond(self._args(None, t))
         return bool(self.active.item())
+
+    def cond_async(self, t):
+        """Enqueue search.py:85-113 for step t and an asynchronous copy of the flag to pinned host memory.
+        Returns the slot to pass to cond_wait, or None when the sequence buffers are full."""
+        if t + 2 > self.cap:
+            return None
+        if self._host_flag is None:
+            self._host_flag = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._flag_events = [torch.cuda.Event(), torch.cuda.Event()]
+        slot = t & 1
+        ops.beam_cond(self._args(None, t))
+        self._host_flag[slot:slot + 1].copy_(self.active, non_blocking=True)
+        self._flag_events[slot].record()
+        return slot
+
+    def cond_wait(self, slot):
+        self._flag_events[slot].synchronize()
+        return bool(int(self._host_flag[slot]))
 
     def last_tokens(self, t):
         """[B*beam, 1] int32: the token fed to decoding_fn at step t (search.py:130); static buffer."""
@@ -144,24 +171,45 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         parent = st.step(logits, t)
         state.reorder(parent, t)
 
-    t = 0
-    while st.not_finished(t):
+    # The loop condition of step t is one kernel + a 4-byte read-back.  Waiting for it before launching step t
+    # leaves the GPU idle for a launch + sync round trip every step, so with the engine's own decoding_fn the host
+    # runs one step ahead: step t (and the condition of t + 1) are enqueued before the flag of t is read.  A step
+    # enqueued past the end is harmless: zb_beam_step is a no-op once active[0] == 0 and the per-beam state it
+    # would reorder is discarded with the search.  ZB_DECODE_SPEC=0 restores the lock-step loop.
+    speculate = own and os.environ.get("ZB_DECODE_SPEC", "1") != "0"
+
+    def enqueue_step(t):
         gkey = key + (int(src.shape[1]), t)
         g = graphs.get(gkey) if use_graph else None
         if g is not None:
             g.replay()
-            st.time = t + 1
             state.swap_buffers()
         elif use_graph and seen.get(gkey):
             # second visit: every workspace buffer exists, capture this step (capture does not execute it)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                run_step(t)      # records the kernels; the host-side buffer swap / time bookkeeping happens now
+                run_step(t)      # records the kernels; the host-side buffer swap happens now
             graphs[gkey] = g
             g.replay()
         else:
             seen[gkey] = True
             run_step(t)
+
+    t = 0
+    slot = st.cond_async(0)
+    while slot is not None:
+        if speculate:
+            enqueue_step(t)
+            nxt = st.cond_async(t + 1)
+            if not st.cond_wait(slot):
+                break
+        else:
+            if not st.cond_wait(slot):
+                break
+            enqueue_step(t)
+            nxt = st.cond_async(t + 1)
         t += 1
+        slot = nxt
+    st.time = t
     return st.result()
