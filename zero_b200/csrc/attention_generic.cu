@@ -455,27 +455,40 @@ static int set_smem(K kern, size_t bytes) {
 
 // ------------------------------------------------------------------------------------------------ cached decode
 // lq = 1 (one new target position per row, func.py:199-216 with the cache): the tiled kernel above would leave seven
-// of its eight warps idle and run one CTA per (row, head).  Here one warp owns one (row, head): lanes split the keys
-// for q.k (16-byte loads of a key's head slice), the softmax runs on shuffles, and for p.v each lane owns head
-// channels lane, lane+32 so a value row is one coalesced read.  The rows that share a memory (the beams of a sentence,
-// kv_group) sit in the same CTA, so their K / V reads hit L1 after the first warp.  No shared memory.
+// of its eight warps idle and run one CTA per (row, head).  Here a CTA owns one (memory, head): the rows that share
+// the memory (the beams of a sentence, kv_group) are its warps, and the 64-key tiles of K and V are staged ONCE in
+// shared memory by all threads with 16-byte cp.async (every load of the tile in flight at once).  Per warp: lanes
+// split the keys for q.k (padded rows, conflict-free 16-byte reads), the softmax runs on shuffles, and for p.v each
+// lane owns two head channels so a value row is one 128-byte shared-memory read.
+__device__ __forceinline__ void dec_cp16(void* smem, const void* gmem, bool pred) {
+  const uint32_t s = smem_u32(smem);
+  const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+
 template <int DH>
 __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnP p) {
   grid_dep_wait();
-  constexpr int ND = (DH + 31) / 32;
+  constexpr int KT = 64;        // keys per tile
+  constexpr int PK = DH + 8;    // K row pitch: 16-byte reads of 8 consecutive rows fall in distinct banks
+  constexpr int CH = DH / 8;    // 16-byte chunks per row
+  __shared__ __align__(16) __nv_bfloat16 sK[KT * PK];
+  __shared__ __align__(16) __nv_bfloat16 sV[KT * DH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int g = blockIdx.x, h = blockIdx.y;
   const int kl = p.key_len ? p.key_len[g] : p.lk;
   const __nv_bfloat16* kbase = p.k + (long long)g * p.bsk + h * DH;
   const __nv_bfloat16* vbase = p.v + (long long)g * p.bsv + h * DH;
   const int i_abs = p.q_offset;
-  for (int r = warp; r < p.kv_group; r += nwarp) {
-    const int b = g * p.kv_group + r;
+  for (int r0 = 0; r0 < p.kv_group; r0 += nwarp) {
+    const int r = r0 + warp;
+    const bool row_on = r < p.kv_group;          // warp-uniform
+    const int b = g * p.kv_group + (row_on ? r : 0);
     float qr[DH];
     {
       const uint4* qp = reinterpret_cast<const uint4*>(p.q + (long long)b * p.bsq + h * DH);
 #pragma unroll
-      for (int c = 0; c < DH / 8; ++c) {
+      for (int c = 0; c < CH; ++c) {
         const uint4 u = qp[c];
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -486,17 +499,29 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnP p) {
         }
       }
     }
-    float m = -INFINITY, l = 0.f, o[ND];
+    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int kt = 0; kt < p.lk; kt += KT) {
+      __syncthreads();                           // the previous tile has been consumed by every warp
+      const int nvalid = min(KT, p.lk - kt);
+      for (int c = threadIdx.x; c < 2 * KT * CH; c += blockDim.x) {
+        const int which = c / (KT * CH), cc = c % (KT * CH), row = cc / CH, ch = cc % CH;
+        const bool ok = row < nvalid;
+        const long long grow = kt + (ok ? row : 0);
+        if (which == 0) dec_cp16(sK + row * PK + ch * 8, kbase + grow * p.ldk + ch * 8, ok);
+        else dec_cp16(sV + row * DH + ch * 8, vbase + grow * p.ldv + ch * 8, ok);
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (!row_on) continue;
+      float sc[2], pj[2];
 #pragma unroll
-    for (int dd = 0; dd < ND; ++dd) o[dd] = 0.f;
-    for (int kt = 0; kt < p.lk; kt += 32) {
-      const int j = kt + lane;
-      const bool inb = j < p.lk;
-      float s = 0.f;
-      if (inb) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * p.ldk);
+      for (int half = 0; half < 2; ++half) {
+        const int jl = half * 32 + lane, j = kt + jl;
+        const bool inb = j < p.lk;
+        float s = 0.f;
+        const uint4* kp = reinterpret_cast<const uint4*>(sK + jl * PK);
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
+        for (int c = 0; c < CH; ++c) {
           const uint4 u = kp[c];
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -506,39 +531,56 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnP p) {
             s += qr[8 * c + 2 * e + 1] * f.y;
           }
         }
+        const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
+        if (p.relu_attn) {
+          pj[half] = valid ? fmaxf(s, 0.f) : 0.f;
+          sc[half] = 0.f;
+        } else {
+          sc[half] = inb ? (valid ? s : s - p.inf_value) : -INFINITY;
+        }
       }
-      const bool valid = inb && j < kl && (!p.causal || j <= i_abs);
-      float pj;
-      if (p.relu_attn) {
-        pj = valid ? fmaxf(s, 0.f) : 0.f;
-      } else {
-        s = inb ? (valid ? s : s - p.inf_value) : -INFINITY;
-        const float m_new = fmaxf(m, wmax(s));
-        pj = inb ? __expf(s - m_new) : 0.f;
+      if (!p.relu_attn) {
+        const float m_new = fmaxf(m, wmax(fmaxf(sc[0], sc[1])));
+        pj[0] = sc[0] == -INFINITY ? 0.f : __expf(sc[0] - m_new);
+        pj[1] = sc[1] == -INFINITY ? 0.f : __expf(sc[1] - m_new);
         const float corr = __expf(m - m_new);
-        l = l * corr + wsum(pj);
+        l = l * corr + wsum(pj[0] + pj[1]);
         m = m_new;
-#pragma unroll
-        for (int dd = 0; dd < ND; ++dd) o[dd] *= corr;
+        o0 *= corr;
+        o1 *= corr;
       }
-      const int nv = min(32, p.lk - kt);
+      // p.v: lane owns channels 2 * lane, 2 * lane + 1 (dh = 64) or channel lane (dh <= 32)
+      const int n0 = min(32, nvalid), n1 = nvalid - n0;
 #pragma unroll 8
-      for (int jj = 0; jj < nv; ++jj) {
-        const float pv = __shfl_sync(0xffffffffu, pj, jj);
-        const __nv_bfloat16* vp = vbase + (long long)(kt + jj) * p.ldv;
-#pragma unroll
-        for (int dd = 0; dd < ND; ++dd) {
-          const int d = lane + 32 * dd;
-          if (d < DH) o[dd] += pv * __bfloat162float(vp[d]);
+      for (int jj = 0; jj < n0; ++jj) {
+        const float pv = __shfl_sync(0xffffffffu, pj[0], jj);
+        if (DH == 64) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + jj * DH + 2 * lane));
+          o0 += pv * f.x;
+          o1 += pv * f.y;
+        } else if (lane < DH) {
+          o0 += pv * __bfloat162float(sV[jj * DH + lane]);
+        }
+      }
+#pragma unroll 8
+      for (int jj = 0; jj < n1; ++jj) {
+        const float pv = __shfl_sync(0xffffffffu, pj[1], jj);
+        if (DH == 64) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + (32 + jj) * DH + 2 * lane));
+          o0 += pv * f.x;
+          o1 += pv * f.y;
+        } else if (lane < DH) {
+          o0 += pv * __bfloat162float(sV[(32 + jj) * DH + lane]);
         }
       }
     }
+    if (!row_on) continue;
     const float inv = p.relu_attn ? 1.f : 1.f / l;
     __nv_bfloat16* op = p.o + (long long)b * p.bso + h * DH;
-#pragma unroll
-    for (int dd = 0; dd < ND; ++dd) {
-      const int d = lane + 32 * dd;
-      if (d < DH) op[d] = __float2bfloat16(o[dd] * inv);
+    if (DH == 64) {
+      *reinterpret_cast<__nv_bfloat162*>(op + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+    } else if (lane < DH) {
+      op[lane] = __float2bfloat16(o0 * inv);
     }
     if (lane == 0 && p.lse) p.lse[(long long)b * p.heads + h] = p.relu_attn ? 0.f : m + __logf(l);
   }
@@ -560,14 +602,16 @@ bool attention_decode_supported(const zb_attention_args* a) {
   const int grp = a->kv_group > 0 ? a->kv_group : 1;
   if (a->batch % grp) return false;
   auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
-  if (!al16(a->q) || !al16(a->k)) return false;
-  if ((a->bsq % 8) || (a->bsk % 8) || (a->ldk % 8)) return false;
+  if (!al16(a->q) || !al16(a->k) || !al16(a->v)) return false;
+  if ((a->bsq % 8) || (a->bsk % 8) || (a->ldk % 8) || (a->bsv % 8) || (a->ldv % 8)) return false;
+  if ((a->bso % 2) || (reinterpret_cast<uintptr_t>(a->o) & 3u)) return false;
   return true;
 }
 
 int attention_decode_fwd(const zb_attention_args* a, cudaStream_t st) {
   AttnP p = to_params(a);
-  const int warps = p.kv_group < 8 ? p.kv_group : 8;
+  // one warp per row of the group; at least four so the cooperative tile loads have enough threads in flight
+  const int warps = p.kv_group < 4 ? 4 : (p.kv_group < 8 ? p.kv_group : 8);
   const dim3 grid(a->batch / p.kv_group, a->heads);
   switch (a->dh) {
     case 16: ZB_LAUNCH(attn_decode_kernel<16>, grid, warps * 32, 0, st, p); break;

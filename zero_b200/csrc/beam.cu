@@ -315,13 +315,27 @@ __global__ void __launch_bounds__(kRowThreads) beam_row_kernel(const zb_beam_arg
     if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(grow) & 15u) == 0) {
       const float4* g4 = reinterpret_cast<const float4*>(grow);
       float4* s4 = reinterpret_cast<float4*>(row_smem);
-      for (int w = tid; w < V / 4; w += kRowThreads) {
-        float4 x = g4[w];
-        if (!t_one) {
-          x.x = x.x / a.temperature; x.y = x.y / a.temperature; x.z = x.z / a.temperature; x.w = x.w / a.temperature;
+      const int V4 = V / 4;
+      constexpr int U = 4;   // loads in flight per thread: issue U independent 16-byte loads, then consume them
+      for (int w0 = tid; w0 < V4; w0 += U * kRowThreads) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * kRowThreads;
+          x[u] = w < V4 ? __ldg(g4 + w) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
-        s4[w] = x;
-        m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * kRowThreads;
+          if (w < V4) {
+            if (!t_one) {
+              x[u].x = x[u].x / a.temperature; x[u].y = x[u].y / a.temperature;
+              x[u].z = x[u].z / a.temperature; x[u].w = x[u].w / a.temperature;
+            }
+            s4[w] = x[u];
+            m = fmaxf(m, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+          }
+        }
       }
     } else {
       for (int w = tid; w < V; w += kRowThreads) {

@@ -7,7 +7,12 @@
 // projection, 30 projections per decode step).  This kernel is the small-problem complement: 64 x 64 output tiles so
 // that even a 256 x 512 projection spreads over 32 SMs, operands streamed through a 4-stage cp.async ring of
 // XOR-swizzled 64 x 64 bf16 tiles, warp-level mma.sync m16n8k16 (fp32 accumulation) — no set-up beyond the first
-// cp.async.  zb_gemm routes a problem here only when m <= kSkinnyMaxM; everything token-sized stays on tcgen05.
+// cp.async.  A 256 x 512 x 512 projection is still only 32 tiles with a serial chain of 8 k-chunks each (measured:
+// no faster than the tcgen05 kernel), so the k dimension is additionally split over a thread-block cluster of up to
+// 8 CTAs (grid z): every CTA streams 1 - 4 chunks, all in flight at once, and the partial accumulators are summed by
+// the cluster's rank 0 through distributed shared memory in a fixed order (deterministic), which then applies the
+// epilogue.  zb_gemm routes a problem here only when m <= kSkinnyMaxM; everything token-sized stays on tcgen05.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "zb_common.h"
@@ -27,6 +32,7 @@ struct Params {
   long long lda, ldb, ldd;
   float alpha;
   int relu, d_f32;
+  int split;   // cluster size along grid z = number of k slices
 };
 
 // [64][64] bf16 tile, 16-byte chunks XOR-swizzled by (row & 7): conflict-free for ldmatrix
@@ -81,9 +87,13 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(const Params p) {
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int rows_valid = min(BM, p.M - m0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nk = p.K / BK;
-  const __nv_bfloat16* ag = p.a + (long long)m0 * p.lda;
-  const __nv_bfloat16* bg = B_MN ? p.b + n0 : p.b + (long long)n0 * p.ldb;
+  namespace cg = cooperative_groups;
+  const int S = p.split;
+  const int z = S > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const int nk = p.K / BK / S;                           // chunks of this CTA's k slice
+  const __nv_bfloat16* ag = p.a + (long long)m0 * p.lda + (long long)z * nk * BK;
+  const __nv_bfloat16* bg = B_MN ? p.b + n0 + (long long)z * nk * BK * p.ldb
+                                 : p.b + (long long)n0 * p.ldb + (long long)z * nk * BK;
 
   auto issue = [&](int kc) {
     const int s = kc % STAGES;
@@ -133,6 +143,30 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(const Params p) {
         mma16816(acc[2 * np + 1], a[ks], b[2], b[3]);
       }
     }
+  }
+  if (S > 1) {
+    // k slices -> rank 0: [32 values][128 threads] fp32 in the (now idle) operand ring, read over DSMEM
+    cg::cluster_group cluster = cg::this_cluster();
+    float* red = reinterpret_cast<float*>(sk_smem);
+    __syncthreads();
+    if (z != 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[(i * 4 + j) * NT + threadIdx.x] = acc[i][j];
+    }
+    cluster.sync();
+    if (z == 0) {
+      for (int r = 1; r < S; ++r) {
+        const float* rr = cluster.map_shared_rank(red, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += rr[(i * 4 + j) * NT + threadIdx.x];
+      }
+    }
+    cluster.sync();   // the other ranks' shared memory must outlive rank 0's reads
+    if (z != 0) return;
   }
   // epilogue: alpha, bias, relu; the thread holds rows g and g + 8 of its warp's 16, columns nt * 8 + 2t, +1
   const int g = lane >> 2, t = lane & 3;
@@ -198,9 +232,42 @@ int gemm_skinny_launch(const zb_gemm_args* a, cudaStream_t st) {
     cudaFuncSetAttribute(sk::gemm_skinny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  const dim3 grid(p.N / sk::BN, (p.M + sk::BM - 1) / sk::BM);
-  if (a->b_layout == ZB_MN_MAJOR) ZB_LAUNCH(sk::gemm_skinny_kernel<true>, grid, sk::NT, smem, st, p);
-  else ZB_LAUNCH(sk::gemm_skinny_kernel<false>, grid, sk::NT, smem, st, p);
+  // k slices: double while the grid does not fill the machine or a CTA would still chain more than 4 chunks
+  const int tiles = (p.N / sk::BN) * ((p.M + sk::BM - 1) / sk::BM), nk = p.K / sk::BK;
+  static const bool split_on = [] {
+    const char* e = getenv("ZB_SKINNY_SPLIT");
+    return !(e && e[0] == '0');
+  }();
+  int S = 1;
+  while (split_on && S < 8 && nk % (2 * S) == 0 && (tiles * S < num_sms() || nk / S > 4)) S *= 2;
+  p.split = S;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.N / sk::BN, (p.M + sk::BM - 1) / sk::BM, S);
+  cfg.blockDim = dim3(sk::NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (S > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = S;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t le = a->b_layout == ZB_MN_MAJOR ? cudaLaunchKernelEx(&cfg, sk::gemm_skinny_kernel<true>, p)
+                                              : cudaLaunchKernelEx(&cfg, sk::gemm_skinny_kernel<false>, p);
+  if (le != cudaSuccess) {
+    set_error("zb_gemm (skinny, %d k slices) launch: %s", S, cudaGetErrorString(le));
+    return ZB_ECUDA;
+  }
   return check_launch("zb_gemm(skinny)");
 }
 
