@@ -179,6 +179,7 @@ def decode_bench(device, batches=3):
                           beam_size=4, decode_length=0, decode_alpha=0.6)
     hp.add_hparam("src_vocab", SimpleVocab(VOCAB))
     hp.add_hparam("tgt_vocab", SimpleVocab(VOCAB))
+    hp.add_hparam("decode_graph", os.environ.get("ZB_DECODE_GRAPH", "1") != "0")   # 0: eager steps (for ncu)
     eng = Engine(hp, VOCAB, VOCAB, device=device)
     eng.ps.init_random(7)
     eng.decode_length = 0

@@ -39,6 +39,20 @@ int zb_abi_version(void);
 const char* zb_last_error_string(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 int64_t zb_launch_count(void);
+/* Launches per dispatch path, for callers (and parity tests) that need to know WHICH kernel served a call:
+ * the entry points choose between several implementations of the same op by shape / alignment / switches. */
+typedef enum {
+  ZB_PATH_GEMM_TCGEN05 = 0,   /* single-CTA tcgen05 GEMM (gemm_tcgen05.cu) */
+  ZB_PATH_GEMM_PAIR = 1,      /* CTA-pair tcgen05 GEMM (gemm2_tcgen05.cu), grouped launches count once */
+  ZB_PATH_GEMM_SKINNY = 2,    /* <= 384-row mma.sync GEMM (gemm_skinny.cu), opt-in */
+  ZB_PATH_ATTN_MMA = 3,       /* attention_mma.cu */
+  ZB_PATH_ATTN_GENERIC = 4,   /* attention_generic.cu tiled kernels */
+  ZB_PATH_ATTN_DECODE = 5,    /* attention_generic.cu lq = 1 kernel */
+  ZB_PATH_BEAM_SENTENCE = 6,  /* beam.cu one CTA per sentence */
+  ZB_PATH_BEAM_ROWS = 7,      /* beam.cu one CTA per (sentence, beam) row */
+  ZB_PATH_COUNT_ = 8
+} zb_path;
+int64_t zb_path_launch_count(int32_t which);
 /* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,
  * 7 colsum; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
 int64_t zb_abi_struct_size(int32_t which);

@@ -45,12 +45,17 @@ def test_gemm_layouts(m, n, k, a_mn, b_mn):
 @pytest.mark.parametrize("m,n,k", [(256, 512, 512), (256, 2048, 512), (256, 512, 2048), (256, 1024, 1024),
                                    (100, 128, 64), (1, 64, 192), (384, 1536, 512), (37, 384, 128)])
 @pytest.mark.parametrize("b_mn", [1, 0])
-def test_gemm_skinny_rows(m, n, k, b_mn):
-    """The decode-step GEMM (gemm_skinny.cu: m <= 384 rows, 64 x 64 tiles, mma.sync) on the projections of one
-    cached decode step at configs[2] (256 rows) and on ragged row counts: plain fp32 output, then the
-    bias + relu epilogue into a strided bf16 destination (func.linear writing into the [rows, cap, 3d] cache)."""
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_gemm_skinny_rows(m, n, k, b_mn, split, monkeypatch):
+    """The opt-in decode-step GEMM (gemm_skinny.cu: m <= 384 rows, 64 x 64 tiles, mma.sync, k split over a
+    thread-block cluster with a DSMEM reduction) on the projections of one cached decode step at configs[2]
+    (256 rows) and on ragged row counts: plain fp32 output, then the bias + relu epilogue into a strided bf16
+    destination (func.linear writing into the [rows, cap, 3d] cache)."""
     from zero_b200 import ops
     import zero_b200.lib as L
+    monkeypatch.setenv("ZB_SKINNY_GEMM", "1")
+    monkeypatch.setenv("ZB_SKINNY_SPLIT", split)
+    before = L.path_launch_count("gemm_skinny")
     x = rnd(m, k, seed=11)
     w = rnd(k, n, scale=0.05, seed=12)            # [in, out] like func.linear's W
     b_st = w if b_mn else w.t().contiguous()      # MN-major = [k][n]; K-major = [n][k]
@@ -65,6 +70,7 @@ def test_gemm_skinny_rows(m, n, k, b_mn):
         torch.testing.assert_close(buf[:, 1, :n].float(), torch.relu(ref + bias), atol=3e-2, rtol=2e-2)
         assert float((buf[:, 0] - 7).abs().max()) == 0 and float((buf[:, 2] - 7).abs().max()) == 0
         assert float((buf[:, 1, n:] - 7).abs().max()) == 0
+    assert L.path_launch_count("gemm_skinny") > before      # the switch really routed the problem to this kernel
 
 
 def test_gemm_epilogues_and_splitk():
@@ -337,8 +343,10 @@ def test_attention_decode_kernel(cfg):
     """The lq = 1 kernel (one warp per (row, head)): per-sentence memories shared by the beams, key-length masks,
     self-attention against a strided, partly filled cache with the causal offset, and the log-sum-exp output."""
     from zero_b200 import ops
+    import zero_b200.lib as L
     B, K, h, dh, S = cfg["B"], cfg["K"], cfg["h"], cfg["dh"], cfg["S"]
     D = h * dh
+    before = L.path_launch_count("attn_decode")
     q = rnd(B * K, 1, D, seed=1)
     mem = rnd(B, S, 2 * D, seed=2)                      # fused [k | v] memory like the engine's
     key_len = torch.randint(1, S + 1, (B,), dtype=torch.int32, device=dev())
@@ -367,6 +375,7 @@ def test_attention_decode_kernel(cfg):
     ref2 = _attn_ref(cache[:, t:t + 1, :D].float(), cache[:, :t + 1, D:2 * D].float(), cache[:, :t + 1, 2 * D:].float(),
                      h, None, True, t, 1e8, None, None, 0, cfg["relu"])
     torch.testing.assert_close(o2.float(), ref2, atol=3e-2, rtol=3e-2)
+    assert L.path_launch_count("attn_decode") == before + 2
 
 
 def test_adam_tf_and_sumsq_and_colsum():
@@ -473,6 +482,8 @@ def test_beam_row_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
         monkeypatch.setenv("ZB_BEAM_ROWS", rows)
         states.append(BeamState(B, K, V, src.to(dev()), 4, 0.6, 1.0 if V != 1000 else 0.7, 1e8, dev()))
     assert states[0].row_ws is None and states[1].row_ws is not None
+    import zero_b200.lib as L
+    n_rows, n_sent = L.path_launch_count("beam_rows"), L.path_launch_count("beam_sentence")
     t = 0
     while True:
         nf = [st.not_finished(t) for st in states]
@@ -490,5 +501,6 @@ def test_beam_row_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
             torch.testing.assert_close(getattr(states[0], name), getattr(states[1], name), rtol=1e-5, atol=1e-5)
         t += 1
     assert t >= 3
+    assert L.path_launch_count("beam_rows") == n_rows + t and L.path_launch_count("beam_sentence") == n_sent + t
     # the arrival tickets (last word of each sentence's scratch) are back to zero after every step
     assert int(states[1].row_ws.view(torch.int32).view(B, -1)[:, -1].abs().sum()) == 0

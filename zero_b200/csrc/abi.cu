@@ -12,6 +12,7 @@ namespace zb {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_path_launches[ZB_PATH_COUNT_] = {};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -54,6 +55,9 @@ int num_sms() {
 extern "C" int zb_abi_version(void) { return ZB_ABI_VERSION; }
 extern "C" const char* zb_last_error_string(void) { return zb::g_err; }
 extern "C" int64_t zb_launch_count(void) { return zb::g_launches.load(); }
+extern "C" int64_t zb_path_launch_count(int32_t which) {
+  return which >= 0 && which < ZB_PATH_COUNT_ ? zb::g_path_launches[which].load() : -1;
+}
 extern "C" int64_t zb_abi_struct_size(int32_t which) {
   switch (which) {
     case 0: return sizeof(zb_gemm_args);

@@ -618,6 +618,7 @@ int attention_decode_fwd(const zb_attention_args* a, cudaStream_t st) {
     case 32: ZB_LAUNCH(attn_decode_kernel<32>, grid, warps * 32, 0, st, p); break;
     default: ZB_LAUNCH(attn_decode_kernel<64>, grid, warps * 32, 0, st, p); break;
   }
+  note_path(ZB_PATH_ATTN_DECODE);
   return check_launch("zb_attention_fwd(decode)");
 }
 
@@ -639,6 +640,7 @@ int attention_generic_fwd(const zb_attention_args* a, cudaStream_t st) {
     default: set_error("zb_attention: head size %d unsupported (16/32/64)", a->dh); return ZB_EUNSUPPORTED;
   }
 #undef LAUNCH
+  note_path(ZB_PATH_ATTN_GENERIC);
   return check_launch("zb_attention_fwd");
 }
 

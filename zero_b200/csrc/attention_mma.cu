@@ -678,11 +678,13 @@ int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
     const int grid = items < 8 * num_sms() ? items : 8 * num_sms();
     if (drop) ZB_LAUNCH(fa::fwd64_kernel<true>, grid, fa::NT, smem, st, p, items);
     else ZB_LAUNCH(fa::fwd64_kernel<false>, grid, fa::NT, smem, st, p, items);
+    note_path(ZB_PATH_ATTN_MMA);
     return check_launch("zb_attention_fwd(tile64)");
   }
   const dim3 grid((a->lq + fa::BQ - 1) / fa::BQ, a->heads, a->batch);
   if (drop) ZB_LAUNCH(fa::fwd_kernel<true>, grid, fa::NT, 0, st, p);
   else ZB_LAUNCH(fa::fwd_kernel<false>, grid, fa::NT, 0, st, p);
+  note_path(ZB_PATH_ATTN_MMA);
   return check_launch("zb_attention_fwd(mma)");
 }
 

@@ -536,10 +536,12 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
     }
     if (2 * a->beam <= 8) ZB_LAUNCH(beam_row_kernel<8>, a->batch * a->beam, kRowThreads, smem, st, *a, stage);
     else ZB_LAUNCH(beam_row_kernel<16>, a->batch * a->beam, kRowThreads, smem, st, *a, stage);
+    note_path(ZB_PATH_BEAM_ROWS);
     return check_launch("zb_beam_step(rows)");
   }
   if (2 * a->beam <= 8) ZB_LAUNCH(beam_step_kernel<8>, a->batch, kBeamThreads, 0, st, *a);
   else ZB_LAUNCH(beam_step_kernel<16>, a->batch, kBeamThreads, 0, st, *a);
+  note_path(ZB_PATH_BEAM_SENTENCE);
   return check_launch("zb_beam_step");
 }
 

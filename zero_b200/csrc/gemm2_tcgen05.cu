@@ -569,6 +569,7 @@ static int launch2(const Gemm2Group<NP>& G, int grid, cudaStream_t st) {
     set_error("zb_gemm (cta pair) launch: %s", cudaGetErrorString(le));
     return ZB_ECUDA;
   }
+  note_path(ZB_PATH_GEMM_PAIR);
   return check_launch("zb_gemm(2cta)");
 }
 

@@ -196,12 +196,13 @@ __global__ void __launch_bounds__(NT) gemm_skinny_kernel(const Params p) {
 
 }  // namespace sk
 
+// Opt-in (ZB_SKINNY_GEMM=1): in the decode step of BASELINE configs[2] this kernel measured 10.2 us per projection
+// (10.9 us with the cluster k split) against 9.1 us for the tcgen05 kernel it was meant to undercut — all three sit on
+// the same floor, so the k-loop is not what bounds a 256-row projection (profiles/r01_decode_ab_v2.jsonl).  Kept,
+// parity-tested (tests/test_kernels_gpu.py::test_gemm_skinny_rows sets the switch), for the follow-up that finds the floor.
 static bool skinny_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("ZB_SKINNY_GEMM");
-    return !(e && e[0] == '0');
-  }();
-  return on;
+  const char* e = getenv("ZB_SKINNY_GEMM");   // read per call: the parity test flips it inside one process
+  return e && e[0] == '1';
 }
 
 // K-major A, whole 64-wide tiles in n and k, plain / bias / relu epilogue, a few hundred rows at most
@@ -234,10 +235,8 @@ int gemm_skinny_launch(const zb_gemm_args* a, cudaStream_t st) {
   }
   // k slices: double while the grid does not fill the machine or a CTA would still chain more than 4 chunks
   const int tiles = (p.N / sk::BN) * ((p.M + sk::BM - 1) / sk::BM), nk = p.K / sk::BK;
-  static const bool split_on = [] {
-    const char* e = getenv("ZB_SKINNY_SPLIT");
-    return !(e && e[0] == '0');
-  }();
+  const char* split_env = getenv("ZB_SKINNY_SPLIT");
+  const bool split_on = !(split_env && split_env[0] == '0');
   int S = 1;
   while (split_on && S < 8 && nk % (2 * S) == 0 && (tiles * S < num_sms() || nk / S > 4)) S *= 2;
   p.split = S;
@@ -268,6 +267,7 @@ int gemm_skinny_launch(const zb_gemm_args* a, cudaStream_t st) {
     set_error("zb_gemm (skinny, %d k slices) launch: %s", S, cudaGetErrorString(le));
     return ZB_ECUDA;
   }
+  note_path(ZB_PATH_GEMM_SKINNY);
   return check_launch("zb_gemm(skinny)");
 }
 

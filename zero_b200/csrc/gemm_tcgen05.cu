@@ -455,6 +455,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
     set_error("zb_gemm launch: %s", cudaGetErrorString(le));
     return ZB_ECUDA;
   }
+  note_path(ZB_PATH_GEMM_TCGEN05);
   return check_launch("zb_gemm");
 }
 

@@ -12,6 +12,8 @@ namespace zb {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_path_launches[ZB_PATH_COUNT_];
+inline void note_path(int which) { g_path_launches[which].fetch_add(1, std::memory_order_relaxed); }
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

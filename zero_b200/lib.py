@@ -83,7 +83,7 @@ class BeamArgs(C.Structure):
 STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs]
 
 EXPORTS = [
-    "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
+    "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_path_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
     "zb_attention_bwd", "zb_add_ln_fwd", "zb_add_ln_bwd", "zb_embed_fwd", "zb_embed_bwd", "zb_softmax_ce",
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
@@ -111,6 +111,8 @@ def load():
     lib.zb_abi_version.restype = C.c_int
     lib.zb_last_error_string.restype = C.c_char_p
     lib.zb_launch_count.restype = C.c_int64
+    lib.zb_path_launch_count.argtypes = [i32]
+    lib.zb_path_launch_count.restype = C.c_int64
     for name, argt in [
         ("zb_gemm", [C.POINTER(GemmArgs), vp]),
         ("zb_gemm_grouped", [C.POINTER(GemmArgs), i32, vp]),
@@ -159,6 +161,15 @@ def check(rc, what):
     if rc != 0:
         msg = load().zb_last_error_string()
         raise ZeroB200Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+PATHS = {"gemm_tcgen05": 0, "gemm_pair": 1, "gemm_skinny": 2, "attn_mma": 3, "attn_generic": 4, "attn_decode": 5,
+         "beam_sentence": 6, "beam_rows": 7}
+
+
+def path_launch_count(name) -> int:
+    """Launches served by one dispatch path (include/zero_b200.h zb_path)."""
+    return int(load().zb_path_launch_count(PATHS[name]))
 
 
 def launch_count() -> int:
