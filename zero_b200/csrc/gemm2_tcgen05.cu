@@ -585,7 +585,13 @@ static int dispatch2(int a_mn, int b_mn, const Gemm2Group<1>& G, int grid, cudaS
 bool gemm2_wanted(const zb_gemm_args* a) {
   static const char* env = getenv("ZB_GEMM2");
   if (env && env[0] == '0') return false;
-  if (a->n < 128 || a->m < 256) return false;
+  // ZB_GEMM2_MIN_M: smallest m the pair kernel takes (default 512).  A few hundred rows make only n / 128 pair
+  // tiles (8 CTAs for the 256 x 512 projections of a decode step), each bound by its own SM's L2 ingest (~0.27 us per
+  // k-block); the single-CTA kernel's 128 x 64 tiles spread the same problem over 2 - 4x as many SMs: decode step
+  // 0.646 -> 0.604 ms at BASELINE configs[2] (profiles/r01_decode_ab_v3.jsonl).
+  static const char* min_m_env = getenv("ZB_GEMM2_MIN_M");
+  const long long min_m = min_m_env ? atoll(min_m_env) : 512;
+  if (a->n < 128 || a->m < min_m) return false;
   return true;
 }
 
