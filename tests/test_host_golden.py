@@ -104,3 +104,37 @@ def test_run_parameter_precedence_and_param_json(tmp_path):
     p3.recorder.step = 7
     p3.recorder.save_to_json(str(out / "record.json"))
     assert saver.setup_recorder(run.build_params(str(cfg), "")).recorder.step == 7
+
+
+def test_checkpoint_averaging_follows_the_reference_script(tmp_path):
+    """scripts/checkpoint_averaging.py: mean of the newest N checkpoints (by step), global_step excluded and reset,
+    json side files copied; missing files skipped; errors like the script's."""
+    import json as _json
+    import numpy as np
+    import pytest
+    from zero_b200 import saver
+    src, out = tmp_path / "train", tmp_path / "avg"
+    src.mkdir()
+    rng = np.random.RandomState(0)
+    steps = [100, 300, 200, 400]
+    vals = {}
+    for s in steps:
+        vals[s] = {"transformer/bias": rng.randn(8).astype(np.float32),
+                   "transformer/encoder/layer_0/feed_forward/ffn_layer/enlarge/W_0_0": rng.randn(4, 6).astype(np.float32)}
+        np.savez(src / ("model-%d.npz" % s), global_step=np.asarray(s, dtype=np.int64), **vals[s])
+    _json.dump({"all": ["model-%d.npz" % s for s in steps], "best": []}, open(src / "checkpoint.json", "w"))
+    (src / "param.json").write_text("{}")
+    path = saver.average_checkpoints(str(src), 3, str(out))
+    with np.load(path) as z:
+        assert int(z["global_step"]) == 0
+        for k in vals[100]:
+            want = (vals[400][k].astype(np.float64) + vals[300][k] + vals[200][k]) / 3      # newest three by step
+            np.testing.assert_allclose(z[k], want.astype(np.float32), rtol=0, atol=0)
+            assert z[k].dtype == np.float32
+    assert (out / "param.json").exists() and _json.load(open(out / "checkpoint.json"))["all"] == ["average-0.npz"]
+    # a checkpoint listed in the index but deleted from disk is skipped (checkpoint_averaging.py:66)
+    (src / "model-400.npz").unlink()
+    with np.load(saver.average_checkpoints(str(src), 2, str(out))) as z:
+        np.testing.assert_array_equal(z["transformer/bias"], vals[300]["transformer/bias"])
+    with pytest.raises(ValueError):
+        saver.average_checkpoints(str(tmp_path / "nowhere"), 2, str(out))

@@ -157,3 +157,53 @@ class Saver(object):
         with np.load(path) as z:
             self.restore_state_dict(engine, {k: z[k] for k in z.files}, trainer)
         return True
+
+
+def average_checkpoints(path, checkpoints, output):
+    """scripts/checkpoint_averaging.py:31-125: arithmetic mean of the newest `checkpoints` checkpoints under `path`
+    (every variable except global_step, which restarts at 0; accumulated in float64 like the script's np.zeros),
+    written to `output`/average-0.npz with its own index, and the *.json files (param.json, record.json) copied
+    along.  Returns the output file."""
+    index = os.path.join(path, "checkpoint.json")
+    if not os.path.exists(index):
+        raise ValueError("Cannot find checkpoints in %s" % path)
+    names = json.load(open(index))["all"]
+    # newest first by the step in the name (checkpoint_averaging.py:41-48)
+    names = sorted(names, key=lambda n: int(n.rsplit("-", 1)[-1].split(".")[0]), reverse=True)[:int(checkpoints)]
+    if not names:
+        raise ValueError("No checkpoints provided for averaging.")
+    names = [n for n in names if os.path.exists(os.path.join(path, n))]
+    if not names:
+        raise ValueError("None of the provided checkpoints exist. %s" % checkpoints)
+    total, dtypes = {}, {}
+    for n in names:
+        with np.load(os.path.join(path, n)) as z:
+            for k in z.files:
+                if k.startswith("global_step"):
+                    continue
+                if k not in total:
+                    if n != names[0]:
+                        continue     # the variable list comes from the first (newest) checkpoint
+                    total[k] = np.zeros(z[k].shape)
+                dtypes[k] = z[k].dtype
+                total[k] += z[k]
+    out = {k: (v / len(names)).astype(dtypes[k]) for k, v in total.items()}
+    out["global_step"] = np.asarray(0, dtype=np.int64)
+    os.makedirs(output, exist_ok=True)
+    name = "average-0.npz"
+    np.savez(os.path.join(output, name), **out)
+    json.dump({"all": [name], "best": []}, open(os.path.join(output, "checkpoint.json"), "w"))
+    for f in os.listdir(path):
+        if f.endswith(".json") and f != "checkpoint.json":
+            shutil.copy(os.path.join(path, f), os.path.join(output, f))
+    return os.path.join(output, name)
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="Average checkpoints", usage="python -m zero_b200.saver [<args>]")
+    ap.add_argument("--path", type=str, required=True, help="checkpoint dir")
+    ap.add_argument("--checkpoints", type=int, required=True, help="number of checkpoints to use")
+    ap.add_argument("--output", type=str, required=True, help="output path")
+    a = ap.parse_args()
+    print("Averaged checkpoints saved in %s" % average_checkpoints(a.path, a.checkpoints, a.output))
