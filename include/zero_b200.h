@@ -50,7 +50,8 @@ typedef enum {
   ZB_PATH_ATTN_DECODE = 5,    /* attention_generic.cu lq = 1 kernel */
   ZB_PATH_BEAM_SENTENCE = 6,  /* beam.cu one CTA per sentence */
   ZB_PATH_BEAM_ROWS = 7,      /* beam.cu one CTA per (sentence, beam) row */
-  ZB_PATH_COUNT_ = 8
+  ZB_PATH_BEAM_PARTS = 8,     /* beam.cu a 4-CTA cluster per row with a threshold pass, opt-in */
+  ZB_PATH_COUNT_ = 9
 } zb_path;
 int64_t zb_path_launch_count(int32_t which);
 /* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,

@@ -504,3 +504,46 @@ def test_beam_row_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
     assert L.path_launch_count("beam_rows") == n_rows + t and L.path_launch_count("beam_sentence") == n_sent + t
     # the arrival tickets (last word of each sentence's scratch) are back to zero after every step
     assert int(states[1].row_ws.view(torch.int32).view(B, -1)[:, -1].abs().sum()) == 0
+
+
+# Kernels written after the round's last GPU visit: compiled and reviewed, never run.  Their parity tests are opt-in
+# (ZB_TEST_UNVALIDATED=1) until a GPU run has seen them pass; the product path does not use them by default either.
+unvalidated = pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
+                                 reason="kernel not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
+
+
+@unvalidated
+@pytest.mark.parametrize("B,K,V", [(3, 1, 64), (4, 3, 207), (2, 5, 1000), (64, 4, 32000), (2, 8, 60000), (3, 2, 7)])
+def test_beam_part_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
+    """ZB_BEAM_PARTS=1 (a 4-CTA cluster per row, DSMEM exchange of the soft-max statistics, threshold pass before
+    the sorted lists) against the one-CTA-per-sentence kernel, step for step: sequences / parents / flags bit-exact,
+    scores to fp32 round-off.  V = 7 leaves parts empty; 207 / 1000 exercise the scalar staging path."""
+    import zero_b200.lib as L
+    from zero_b200.search import BeamState
+    g = torch.Generator().manual_seed(V + K)
+    src = torch.randint(3, 50, (B, 6), generator=g)
+    src[0, 3:] = 0
+    monkeypatch.setenv("ZB_BEAM_ROWS", "0")
+    ref = BeamState(B, K, V, src.to(dev()), 4, 0.6, 1.0 if V != 1000 else 0.7, 1e8, dev())
+    monkeypatch.setenv("ZB_BEAM_ROWS", "1")
+    new = BeamState(B, K, V, src.to(dev()), 4, 0.6, 1.0 if V != 1000 else 0.7, 1e8, dev())
+    before = L.path_launch_count("beam_parts")
+    t = 0
+    while True:
+        nf = [ref.not_finished(t), new.not_finished(t)]
+        assert nf[0] == nf[1]
+        if not nf[0]:
+            break
+        lg = torch.randn(B * K, V, generator=g) * 3
+        lg[:, 2] += 3.0 if t % 3 == 2 else -1.0
+        lg = lg.to(dev())
+        ref.step(lg, t)
+        monkeypatch.setenv("ZB_BEAM_PARTS", "1")
+        new.step(lg, t)
+        monkeypatch.delenv("ZB_BEAM_PARTS")
+        for name in ("alive_seq", "fin_seq", "fin_flag", "parent"):
+            assert torch.equal(getattr(ref, name), getattr(new, name)), (name, t)
+        for name in ("alive_logp", "alive_score", "fin_score"):
+            torch.testing.assert_close(getattr(ref, name), getattr(new, name), rtol=1e-5, atol=1e-5)
+        t += 1
+    assert t >= 3 and L.path_launch_count("beam_parts") == before + t

@@ -5,8 +5,10 @@
 // here a CTA streams its beam*V logits twice (log-sum-exp, then candidate scan with per-thread top-2k lists)
 // and finishes the bookkeeping in shared memory.  All index arithmetic is int32; all scores fp32 with the
 // reference's constants (float32.min masking, additive -inf on EOS), ties -> lower flat index like tf.nn.top_k.
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "zb_common.h"
 #include "zb_ptx.cuh"
@@ -485,6 +487,297 @@ __global__ void __launch_bounds__(kRowThreads) beam_row_kernel(const zb_beam_arg
   }
 }
 
+// ------------------------------------------------------------------------------------------------ part-parallel step
+// (opt-in, ZB_BEAM_PARTS=1 — written after the round's last GPU visit, parity-tested but not yet timed.)
+// What the timeline says about beam_row_kernel (96 us at batch 64, beam 4, V = 32000): a 128 KB row in shared memory
+// means one CTA per SM and two waves of 148 + 108 CTAs, and inside a CTA the per-thread sorted lists dominate — with
+// 62 elements per thread almost every warp iteration has some lane inserting, so the whole warp pays the ~130-instruction
+// insertion path 62 times (the same divergence model reproduces the 152 us of the one-CTA-per-sentence kernel).
+// This kernel attacks both:
+//  * a row is split over a cluster of kParts CTAs (a quarter row = 32 KB of shared memory, 256 threads: seven CTAs per
+//    SM, all batch * beam * kParts CTAs resident in one wave); the parts exchange (max, sum-exp) through distributed
+//    shared memory, so every part scores with the same log-sum-exp, and rank 0 merges the parts' candidate lists;
+//  * a threshold pass first: T = the 2k-th largest of the threads' maximum scores.  At least 2k elements score >= T,
+//    so the part's exact top-2k all pass `score >= T` (ties included) while on average only a handful of the
+//    8000 elements do — the sorted-list insertion runs for those only.
+// The hand-off to the sentence's last arriver and the bookkeeping of search.py:179-228 are those of beam_row_kernel.
+constexpr int kParts = 4;
+constexpr int kPartThreads = 256;
+
+// The last arriver of sentence b: merge the K rows' lists from row_ws, then search.py:179-228.  NT = blockDim.x.
+template <int N2, int NT>
+__device__ void beam_sentence_tail(const zb_beam_args& a, int b, float* ws_s, int* ws_i, unsigned* ticket) {
+  const int K = a.beam, V = a.vocab, t = a.time, cap = a.seq_cap;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n2 = 2 * K;
+  const float pen = a.length_penalty;
+  __shared__ float top_s[2 * kMaxBeam];
+  __shared__ int top_i[2 * kMaxBeam];
+  __shared__ int bi[2 * kMaxBeam], wi[2 * kMaxBeam], done[2 * kMaxBeam];
+  __shared__ float tmpv[3 * kMaxBeam], a_s[kMaxBeam], f_s[kMaxBeam];
+  __shared__ int a_i[kMaxBeam], f_i[kMaxBeam], new_flag[kMaxBeam];
+  __threadfence();
+  if (warp == 0) {
+    float ls[N2];
+    int li[N2];
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < K * n2; c += 32) list_insert<N2>(ls, li, __ldcg(ws_s + c), __ldcg(ws_i + c));
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, top_s, top_i);
+    if (lane == 0) *ticket = 0u;   // ready for the next step
+  }
+  __syncthreads();
+  const int max_len = a.max_len[b];
+  if (tid < n2) {
+    bi[tid] = top_i[tid] / V;
+    wi[tid] = top_i[tid] % V;
+    done[tid] = (wi[tid] == a.eos_id) || (t >= max_len);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = 0; c < n2; ++c) tmpv[c] = top_s[c] + (float)done[c] * F32_MIN;
+    small_topk(tmpv, n2, K, a_s, a_i);
+    for (int c = 0; c < K; ++c) tmpv[c] = a.fin_score[b * K + c];
+    for (int c = 0; c < n2; ++c) tmpv[K + c] = top_s[c] + (1.0f - (float)done[c]) * F32_MIN;
+    small_topk(tmpv, 3 * K, K, f_s, f_i);
+    for (int c = 0; c < K; ++c) new_flag[c] = f_i[c] < K ? a.fin_flag[b * K + f_i[c]] : done[f_i[c] - K];
+  }
+  __syncthreads();
+  int* tmp = a.tmp_seq + (long long)b * 3 * K * cap;
+  const int newlen = t + 2;
+  for (int idx = tid; idx < 3 * K * newlen; idx += NT) {
+    const int r = idx / newlen, pos = idx % newlen;
+    int val;
+    if (r < K) {
+      val = pos <= t ? a.fin_seq[((long long)b * K + r) * cap + pos] : a.pad_id;
+    } else {
+      const int c = r - K;
+      val = pos <= t ? a.alive_seq[((long long)b * K + bi[c]) * cap + pos] : wi[c];
+    }
+    tmp[r * cap + pos] = val;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < K * newlen; idx += NT) {
+    const int c = idx / newlen, pos = idx % newlen;
+    a.alive_seq[((long long)b * K + c) * cap + pos] = tmp[(K + a_i[c]) * cap + pos];
+    a.fin_seq[((long long)b * K + c) * cap + pos] = tmp[f_i[c] * cap + pos];
+  }
+  if (tid < K) {
+    a.alive_logp[b * K + tid] = a_s[tid] * pen;
+    a.alive_score[b * K + tid] = a_s[tid];
+    a.fin_score[b * K + tid] = f_s[tid];
+    a.fin_flag[b * K + tid] = new_flag[tid];
+    a.parent[b * K + tid] = b * K + bi[a_i[tid]];
+  }
+}
+
+template <int N2>
+__global__ void __launch_bounds__(kPartThreads) beam_part_kernel(const zb_beam_args a, const int vp) {
+  namespace cg = cooperative_groups;
+  grid_dep_wait();
+  if (a.active && a.active[0] == 0) return;    // uniform over the grid: no cluster barrier is left waiting
+  cg::cluster_group cluster = cg::this_cluster();
+  const int part = (int)cluster.block_rank();
+  const int K = a.beam, V = a.vocab, t = a.time;
+  const int row = blockIdx.x / kParts;          // b * K + k
+  const int b = row / K, k = row % K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kPartThreads / 32;
+  const int n2 = 2 * K;
+  extern __shared__ __align__(16) float part_smem[];   // this part's logits / T
+  __shared__ float red[NW];
+  __shared__ float bcast;
+  __shared__ float stat[2];                            // (max, sum exp(x - max)) of this part, read by the cluster
+  __shared__ float wl_s[NW * N2];
+  __shared__ int wl_i[NW * N2];
+  __shared__ float part_s[2 * kMaxBeam];               // this part's top-2k, read by rank 0
+  __shared__ int part_i[2 * kMaxBeam];
+  __shared__ float row_s[2 * kMaxBeam];
+  __shared__ int row_i[2 * kMaxBeam];
+  __shared__ int is_last;
+
+  const int w_lo = part * vp, w_hi = min(V, w_lo + vp), n = max(0, w_hi - w_lo);
+  const float* grow = a.logits + (long long)row * V + w_lo;
+  const bool t_one = a.temperature == 1.f;
+  // ---- pass 1: stage the part, part max
+  float m = -INFINITY;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(grow) & 15u) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(grow);
+    float4* s4 = reinterpret_cast<float4*>(part_smem);
+    const int n4 = n / 4;
+    constexpr int U = 4;
+    for (int w0 = tid; w0 < n4; w0 += U * kPartThreads) {
+      float4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kPartThreads;
+        x[u] = w < n4 ? __ldg(g4 + w) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * kPartThreads;
+        if (w < n4) {
+          if (!t_one) {
+            x[u].x = x[u].x / a.temperature; x[u].y = x[u].y / a.temperature;
+            x[u].z = x[u].z / a.temperature; x[u].w = x[u].w / a.temperature;
+          }
+          s4[w] = x[u];
+          m = fmaxf(m, fmaxf(fmaxf(x[u].x, x[u].y), fmaxf(x[u].z, x[u].w)));
+        }
+      }
+    }
+  } else {
+    for (int w = tid; w < n; w += kPartThreads) {
+      const float x = t_one ? grow[w] : grow[w] / a.temperature;
+      part_smem[w] = x;
+      m = fmaxf(m, x);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float M = red[0];
+    for (int w = 1; w < NW; ++w) M = fmaxf(M, red[w]);
+    bcast = M;
+  }
+  __syncthreads();
+  const float mp = bcast;
+  // ---- pass 2: part sum of exp(x - part max)
+  float sum = 0.f;
+  for (int w = tid; w < n; w += kPartThreads) sum += __expf(part_smem[w] - mp);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float S = 0.f;
+    for (int w = 0; w < NW; ++w) S += red[w];
+    stat[0] = mp;
+    stat[1] = S;
+  }
+  cluster.sync();
+  // every part combines the kParts statistics in the same order -> bit-identical log-sum-exp in the whole row
+  float l;
+  {
+    float pm[kParts], psum[kParts];
+    float M = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < kParts; ++p) {
+      const float* st = cluster.map_shared_rank(stat, p);
+      pm[p] = st[0];
+      psum[p] = st[1];
+      M = fmaxf(M, pm[p]);
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int p = 0; p < kParts; ++p)
+      if (pm[p] != -INFINITY) S += psum[p] * expf(pm[p] - M);
+    l = M + logf(S);
+  }
+  // ---- pass 3a: thread maxima of the candidate scores (search.py:148-170), T = their 2k-th largest
+  const float pen = a.length_penalty;
+  const float lp_prev = a.alive_logp[row];
+  float tm = -INFINITY;
+  for (int w = tid; w < n; w += kPartThreads) {
+    float lp = part_smem[w] - l;
+    if (t < 1 && w_lo + w == a.eos_id) lp = lp + (-a.inf_value);
+    tm = fmaxf(tm, (lp_prev + lp) / pen);
+  }
+  {
+    float l1[1] = {tm};
+    int i1[1] = {tid};
+    warp_pop<1>(l1, i1, n2, wl_s + warp * N2, wl_i + warp * N2);
+  }
+  __syncthreads();
+  float ls[N2];
+  int li[N2];
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < NW * n2; c += 32) {
+      const int w = c / n2, r = c % n2;
+      list_insert<N2>(ls, li, wl_s[w * N2 + r], wl_i[w * N2 + r]);
+    }
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, part_s, part_i);   // part_s is scratch here; its last entry is the threshold
+    __syncwarp();
+    if (lane == 0) bcast = part_s[n2 - 1];
+  }
+  __syncthreads();
+  const float T = bcast;
+  // ---- pass 3b: exact top-2k of the part among the few elements scoring >= T
+#pragma unroll
+  for (int c = 0; c < N2; ++c) {
+    ls[c] = -INFINITY;
+    li[c] = 0x7fffffff;
+  }
+  for (int w = tid; w < n; w += kPartThreads) {
+    float lp = part_smem[w] - l;
+    if (t < 1 && w_lo + w == a.eos_id) lp = lp + (-a.inf_value);
+    const float sc = (lp_prev + lp) / pen;
+    if (sc >= T) list_insert<N2>(ls, li, sc, k * V + w_lo + w);
+  }
+  __syncthreads();   // wl_* (threshold scratch) is rewritten below
+  warp_pop<N2>(ls, li, n2, wl_s + warp * N2, wl_i + warp * N2);
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < NW * n2; c += 32) {
+      const int w = c / n2, r = c % n2;
+      list_insert<N2>(ls, li, wl_s[w * N2 + r], wl_i[w * N2 + r]);
+    }
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, part_s, part_i);
+  }
+  cluster.sync();     // every part's top-2k is in its shared memory
+  float* ws_s = a.row_ws + (long long)b * (4 * K * K + 1);
+  int* ws_i = reinterpret_cast<int*>(ws_s) + 2 * K * K;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws_s) + 4 * K * K;
+  if (part == 0 && warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < kParts * n2; c += 32) {
+      const int p = c / n2, r = c % n2;
+      const float* ps = cluster.map_shared_rank(part_s, p);
+      const int* pi = cluster.map_shared_rank(part_i, p);
+      list_insert<N2>(ls, li, ps[r], pi[r]);
+    }
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, row_s, row_i);
+    __syncwarp();
+    if (lane < n2) {
+      ws_s[k * n2 + lane] = row_s[lane];
+      ws_i[k * n2 + lane] = row_i[lane];
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned prev = atomicAdd(ticket, 1u);
+      is_last = prev == (unsigned)(K - 1);
+    }
+  }
+  cluster.sync();     // the parts' shared memory outlives rank 0's reads; also orders is_last for rank 0's threads
+  if (part != 0 || !is_last) return;
+  beam_sentence_tail<N2, kPartThreads>(a, b, ws_s, ws_i, ticket);
+}
+
 // search.py:85-113 _not_finished(time): not(all_b(worst finished > best alive bound)) and any_b(time < max_len)
 __global__ void beam_cond_kernel(const zb_beam_args a) {
   grid_dep_wait();
@@ -523,6 +816,38 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   ZB_REQUIRE((long long)a->beam * a->vocab < (1ll << 31), "zb_beam_step: beam * vocab overflows int32");
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const char* parts_env = getenv("ZB_BEAM_PARTS");   // per call: the parity test flips it inside one process
+  const int vp = (((a->vocab + kParts - 1) / kParts) + 3) & ~3;   // elements per part, 16-byte granular
+  if (a->row_ws && parts_env && parts_env[0] == '1' && (size_t)vp * sizeof(float) <= 64 * 1024) {
+    static bool part_attr = false;
+    if (!part_attr) {
+      cudaFuncSetAttribute(beam_part_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(beam_part_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      part_attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a->batch * a->beam * kParts);
+    cfg.blockDim = dim3(kPartThreads);
+    cfg.dynamicSmemBytes = (size_t)vp * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kParts;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t le = 2 * a->beam <= 8 ? cudaLaunchKernelEx(&cfg, beam_part_kernel<8>, *a, vp)
+                                      : cudaLaunchKernelEx(&cfg, beam_part_kernel<16>, *a, vp);
+    if (le != cudaSuccess) {
+      set_error("zb_beam_step (parts) launch: %s", cudaGetErrorString(le));
+      return ZB_ECUDA;
+    }
+    note_path(ZB_PATH_BEAM_PARTS);
+    return check_launch("zb_beam_step(parts)");
+  }
   if (a->row_ws) {
     // row-parallel kernel: stage the row in shared memory when it fits beside the static buffers
     const size_t row_bytes = (size_t)a->vocab * sizeof(float);

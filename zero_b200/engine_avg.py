@@ -209,10 +209,11 @@ def _decoding_fn_avg(self, target, state, time):
                 h = ws.get("dec.h", (R, c.f))
                 ops.linear_fwd(xf, ps.w(key + ".aan.ffn.w1.W"), ps.p(key + ".aan.ffn.w1.b"), h, relu=True)
                 ops.linear_fwd(h, ps.w(key + ".aan.ffn.w2.W"), ps.p(key + ".aan.ffn.w2.b"), cat[:, c.d:])
+                y0 = ws.get("dec.y0", (R, c.d))
+                ops.add2d(cat[:, c.d:], None, y0)      # contiguous copy of the FFN output for the gate kernel
             else:
                 ops.add2d(xf, None, cat[:, c.d:])
-            y0 = ws.get("dec.y0", (R, c.d))
-            ops.add2d(cat[:, c.d:], None, y0)
+                y0 = xf                                # without the FFN the averaged input IS y: no second copy
             z = ws.get("dec.z", (R, 2 * c.d))
             ops.linear_fwd(cat, ps.w(key + ".aan.z.W"), ps.p(key + ".aan.z.b"), z)
             ops.aan_gate_fwd(x, y0, z, y)
