@@ -547,3 +547,42 @@ def test_beam_part_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
             torch.testing.assert_close(getattr(ref, name), getattr(new, name), rtol=1e-5, atol=1e-5)
         t += 1
     assert t >= 3 and L.path_launch_count("beam_parts") == before + t
+
+
+@unvalidated
+@pytest.mark.parametrize("m,n,k", [(256, 512, 512), (256, 2048, 512), (256, 512, 2048), (256, 1024, 1024),
+                                   (1, 64, 64), (37, 136, 72), (100, 1000, 520), (300, 2048, 512), (511, 384, 128)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (0, 0), (1, 1), (1, 0)])
+def test_gemm_bm64_tiles(m, n, k, a_mn, b_mn, monkeypatch):
+    """ZB_GEMM_BM64=1: the single-CTA tcgen05 kernel with 64-row tiles (accumulator in the lower 16 lanes of each TMEM
+    quadrant) for problems of <= 512 rows: every operand layout, ragged m / n / k, fp32 output; then bias + relu into
+    a strided bf16 destination and the relu-masked dgrad epilogue."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    monkeypatch.setenv("ZB_GEMM_BM64", "1")
+    before = L.path_launch_count("gemm_bm64")
+    A, B = rnd(m, k, seed=21), rnd(n, k, scale=0.1, seed=22)
+
+    def pad(t):
+        c = (t.shape[1] + 7) // 8 * 8
+        buf = torch.zeros(t.shape[0], c, dtype=t.dtype, device=t.device)
+        buf[:, :t.shape[1]] = t
+        return buf[:, :t.shape[1]]
+    a_st, b_st = pad(A.t().contiguous() if a_mn else A), pad(B.t().contiguous() if b_mn else B)
+    out = pad(torch.zeros(m, n, dtype=f32, device=dev()))
+    ops.gemm(a_st, b_st, out, a_mn, b_mn, m=m, n=n, k=k)
+    ref = A.float() @ B.float().t()
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
+    assert L.path_launch_count("gemm_bm64") == before + 1
+    if (a_mn, b_mn) == (0, 1) and n % 8 == 0:
+        bias = torch.randn(n, device=dev())
+        buf = torch.full((m, 3, n + 64), 7.0, dtype=bf16, device=dev())
+        ops.linear_fwd(pad(A), pad(B.t().contiguous()), bias, buf[:, 1, :n], relu=True)
+        torch.testing.assert_close(buf[:, 1, :n].float(), torch.relu(ref + bias), atol=3e-2, rtol=2e-2)
+        assert float((buf[:, 0] - 7).abs().max()) == 0 and float((buf[:, 2] - 7).abs().max()) == 0
+        assert float((buf[:, 1, n:] - 7).abs().max()) == 0
+    if (a_mn, b_mn) == (0, 0) and n % 8 == 0:
+        mask = rnd(m, n, seed=23)
+        dx = torch.empty(m, n, dtype=bf16, device=dev())
+        ops.linear_dgrad(pad(A), pad(B), dx, relu_mask=mask)   # dx = (A @ B^T) * (mask > 0), B stored [n][k]
+        torch.testing.assert_close(dx.float(), ref * (mask.float() > 0), atol=3e-2, rtol=2e-2)

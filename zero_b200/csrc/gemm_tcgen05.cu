@@ -48,9 +48,9 @@ constexpr int kBK = 64;
 constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int BN>
+template <int BN, int BM = kBM>
 struct GemmCfg {
-  static constexpr int A_BYTES = kBM * kBK * 2;
+  static constexpr int A_BYTES = BM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
@@ -77,11 +77,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// BM = 128 is the production tile.  BM = 64 (opt-in, ZB_GEMM_BM64=1, for problems of a few hundred rows) halves the
+// A bytes a CTA pulls per k-block and doubles the number of CTAs a skinny problem spreads over; tcgen05.mma with M = 64
+// leaves the accumulator in the lower 16 lanes of each 32-lane TMEM quadrant (row r -> lane 32 * (r / 16) + r % 16),
+// so an epilogue warp of quadrant q owns rows 16 q .. 16 q + 15 in its lanes 0..15.
+template <int BN, bool A_MN, bool B_MN, int BM = kBM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  static_assert(BM == 64 || BM == 128, "tcgen05.mma cta_group::1: M is 64 or 128");
+  using Cfg = GemmCfg<BN, BM>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,7 +137,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         tile_coords(p, tile, m_blk, n_blk, ks);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = m_blk * kBM, n0 = n_blk * BN;
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -140,10 +145,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * kBK;
           if constexpr (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, 128 m}
+            tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);  // box {64 k, BM m}
           } else {
 #pragma unroll
-            for (int c = 0; c < kBM / 64; ++c)  // box {64 m, 64 k}
+            for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k}
               tma_load_2d(sa + c * 8192, &tma_a, &full_bar[stage], m0 + 64 * c, k0);
           }
           if constexpr (!B_MN) {
@@ -163,7 +168,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       // canonical SWIZZLE_128B layouts: K-major  -> 8-row groups every 1024 B (SBO), k-step = 32 B
       //                                 MN-major -> 64-wide MN atoms every BK*128 B (LBO), 8-k groups every
       //                                             1024 B (SBO), k-step (16 rows of 128 B) = 2048 B
@@ -311,9 +316,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk, ks;
       tile_coords(p, tile, m_blk, n_blk, ks);
-      const int m0 = m_blk * kBM, n0 = n_blk * BN;
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int row = BM == 128 ? m0 + quad * 32 + lane : m0 + quad * 16 + lane;
+      const bool row_ok = BM == 128 ? row < p.M : (lane < 16 && row < p.M);
       float bias_a, bias_b;
       uint4 mk_a[4], mk_b[4];
       // this warp's column range: the two warps of a lane quadrant split the BN columns in halves
@@ -427,14 +432,14 @@ int make_map_f32(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, 
   return ZB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int BM = kBM>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, int grid, cudaStream_t st) {
-  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, BM>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, BM>::SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(smem=%d): %s", GemmCfg<BN>::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(smem=%d): %s", GemmCfg<BN, BM>::SMEM_BYTES, cudaGetErrorString(e));
       return ZB_ECUDA;
     }
     attr_done = true;
@@ -443,7 +448,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = GemmCfg<BN>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = GemmCfg<BN, BM>::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -459,13 +464,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParam
   return check_launch("zb_gemm");
 }
 
-template <int BN>
+template <int BN, int BM = kBM>
 static int dispatch_layout(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p,
                            int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, grid, st);
-  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, grid, st);
-  if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, grid, st);
-  return launch<BN, true, true>(ta, tb, p, grid, st);
+  if (!a_mn && !b_mn) return launch<BN, false, false, BM>(ta, tb, p, grid, st);
+  if (!a_mn && b_mn) return launch<BN, false, true, BM>(ta, tb, p, grid, st);
+  if (a_mn && !b_mn) return launch<BN, true, false, BM>(ta, tb, p, grid, st);
+  return launch<BN, true, true, BM>(ta, tb, p, grid, st);
 }
 
 }  // namespace zb
@@ -540,14 +545,18 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
     p.trace = trace_buf;
   }
   p.kb_total = (p.K + kBK - 1) / kBK;
-  p.mt = (p.M + kBM - 1) / kBM;
+  // 64-row tiles (opt-in): a problem of a few hundred rows spreads over twice the CTAs, each pulling half the A bytes
+  const char* bm64_env = getenv("ZB_GEMM_BM64");   // per call: the parity test flips it inside one process
+  const bool bm64 = bm64_env && bm64_env[0] == '1' && !accum && p.M <= 512;
+  const int bm = bm64 ? 64 : kBM;
+  p.mt = (p.M + bm - 1) / bm;
 
   const int sms = num_sms();
   // Tile width: the widest BN whose tile count still fills the machine (wave quantisation dominates at the
   // reference's 4096-token batches); 256 when there is plenty of work.
   int bn = 256;
   auto tiles_for = [&](int b) { return (long long)p.mt * ((p.N + b - 1) / b); };
-  if (p.N <= 64) bn = 64;
+  if (p.N <= 64 || bm64) bn = 64;
   else if (p.N <= 128) bn = 128;
   if (!accum) {  // with an accumulating epilogue split-K fills the machine, so keep the widest (most L2-frugal) tile
     if (bn == 256 && tiles_for(256) < 2ll * sms) bn = 128;
@@ -589,7 +598,7 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   CUtensorMap ta, tb;
   int rc;
   const bool a_mn = a->a_layout == ZB_MN_MAJOR, b_mn = a->b_layout == ZB_MN_MAJOR;
-  if (!a_mn) rc = make_map(&ta, a->a, p.K, p.M, a->lda, kBM);
+  if (!a_mn) rc = make_map(&ta, a->a, p.K, p.M, a->lda, bm);
   else rc = make_map(&ta, a->a, p.M, p.K, a->lda, kBK);
   if (rc) return rc;
   if (!b_mn) rc = make_map(&tb, a->b, p.K, p.N, a->ldb, bn);
@@ -600,6 +609,10 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   const int grid = (int)(total < sms ? total : sms);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int lrc;
+  if (bm64) {
+    note_path(ZB_PATH_GEMM_BM64);
+    return dispatch_layout<64, 64>(a_mn, b_mn, ta, tb, p, grid, st);
+  }
   switch (bn) {
     case 64: lrc = dispatch_layout<64>(a_mn, b_mn, ta, tb, p, grid, st); break;
     case 128: lrc = dispatch_layout<128>(a_mn, b_mn, ta, tb, p, grid, st); break;
