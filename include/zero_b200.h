@@ -299,6 +299,14 @@ int zb_prefix_mean_bwd(const void* dy, void* dx, const int32_t* lens, int32_t ba
 /* zb_aan_step: cached decode of the average layer, y = (x + sum) / (time + 1); sum += x (fp32 running sum)
  * (models/transformer_aan.py:110-112, func.py:262-272). */
 int zb_aan_step(const void* x, float* sum, void* y, int64_t n, int32_t time, zb_stream_t stream);
+/* zb_aan_cat_step: zb_aan_step plus the two copies around it in one launch: sum += x, y = sum / (time + 1),
+ * cat[r] = [x[r] | y[r]] (row pitch ldcat >= 2 * dim; the tf.concat of transformer_aan.py:185). */
+int zb_aan_cat_step(const void* x, float* sum, void* cat, int64_t ldcat, void* y, int64_t rows, int32_t dim,
+                    int32_t time, zb_stream_t stream);
+/* zb_aan_gate_ln: out = LayerNorm(x + (sigmoid(i) * x + sigmoid(f) * y)), z = [i | f]: zb_aan_gate_fwd followed by
+ * zb_add_ln_fwd in one pass, bit-identical to the pair (transformer_aan.py:185-192). */
+int zb_aan_gate_ln(const void* x, const void* y, const void* z, void* out, const float* scale, const float* offset,
+                   int64_t rows, int32_t dim, float eps, zb_stream_t stream);
 /* zb_aan_gate_{fwd,bwd}: out = sigmoid(i) * x + sigmoid(f) * y with z = [i | f] (transformer_aan.py:185-189). */
 int zb_aan_gate_fwd(const void* x, const void* y, const void* z, void* out, int64_t rows, int32_t dim,
                     zb_stream_t stream);

@@ -586,3 +586,35 @@ def test_gemm_bm64_tiles(m, n, k, a_mn, b_mn, monkeypatch):
         dx = torch.empty(m, n, dtype=bf16, device=dev())
         ops.linear_dgrad(pad(A), pad(B), dx, relu_mask=mask)   # dx = (A @ B^T) * (mask > 0), B stored [n][k]
         torch.testing.assert_close(dx.float(), ref * (mask.float() > 0), atol=3e-2, rtol=2e-2)
+
+
+@unvalidated
+@pytest.mark.parametrize("rows,d", [(256, 512), (5, 64), (33, 1024)])
+def test_fused_small_decode_kernels_equal_the_unfused_pairs(rows, d):
+    """zb_aan_cat_step == zb_aan_step + two zb_add2d copies (bit-exact); zb_aan_gate_ln == zb_aan_gate_fwd +
+    zb_add_ln_fwd (same rounding points and reduction order; compared to 1 bf16 ulp)."""
+    from zero_b200 import ops
+    x, z = rnd(rows, d, seed=31), rnd(rows, 2 * d, seed=32)
+    sums_a = torch.randn(rows, d, device=dev())
+    sums_b = sums_a.clone()
+    t = 5
+    # unfused
+    xf = torch.empty_like(x)
+    cat = torch.zeros(rows, 2 * d, dtype=bf16, device=dev())
+    ops.aan_step(x, sums_a, xf, t)
+    ops.add2d(x, None, cat[:, :d])
+    ops.add2d(xf, None, cat[:, d:])
+    # fused
+    xf2 = torch.empty_like(x)
+    cat2 = torch.zeros(rows, 2 * d, dtype=bf16, device=dev())
+    ops.aan_cat_step(x, sums_b, cat2, xf2, t)
+    assert torch.equal(xf, xf2) and torch.equal(cat, cat2) and torch.equal(sums_a, sums_b)
+    scale, offset = torch.randn(d, device=dev()), torch.randn(d, device=dev())
+    y = torch.empty_like(x)
+    out = torch.empty_like(x)
+    ops.aan_gate_fwd(x, xf, z, y)
+    ops.add_ln_fwd(x, y, out, scale, offset, eps=1e-8)
+    out2 = torch.empty_like(x)
+    ops.aan_gate_ln(x, xf, z, out2, scale, offset, 1e-8)
+    torch.testing.assert_close(out2.float(), out.float(), atol=2e-2, rtol=1e-2)
+    assert float((out2.float() - out.float()).abs().max()) <= 0.0625   # at most an ulp of bf16 at |v| < 8

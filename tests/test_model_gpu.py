@@ -233,3 +233,24 @@ def test_full_size_properties_c5_deep_encoder_len1024():
     assert float(eng.ps.g("enc0.self.qkv.W").abs().sum()) > 0 and float(eng.ps.g("enc23.ffn.w2.W").abs().sum()) > 0
     _, ps, _ = eng.train_loss(src2, tgt2)
     torch.testing.assert_close(ps[:4].clone(), ps[4:].clone(), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
+                    reason="switches not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("switch", ["ZB_DECODE_FUSED_SMALL", "ZB_BEAM_PARTS", "ZB_GEMM_BM64"])
+def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
+    """transformer_aan golden model: beam search with an opt-in decode-path switch returns the same sequences as
+    the default path (and as the reference-executed golden beams checked in test_cached_decode_and_beam_search)."""
+    from zero_b200 import search
+    from zero_b200.params import SimpleVocab
+    eng, z, hp, variables, grads = _engine("transformer_aan")
+    hp.add_hparam("src_vocab", SimpleVocab(eng.cfg.vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(eng.cfg.vt))
+    hp.add_hparam("decode_graph", False)
+    eng.decode_length = hp.decode_length
+    src = torch.from_numpy(z["source"])
+    ref = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+    monkeypatch.setenv(switch, "1")
+    got = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+    np.testing.assert_array_equal(got["seq"].cpu().numpy(), ref["seq"].cpu().numpy())
+    np.testing.assert_allclose(got["score"].cpu().numpy(), ref["score"].cpu().numpy(), rtol=1e-3, atol=1e-3)

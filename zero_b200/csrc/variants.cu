@@ -268,6 +268,101 @@ __global__ void aan_step_kernel(const __nv_bfloat16* __restrict__ x, float* __re
   y[i] = __float2bfloat16(s * inv);
 }
 
+// The three launches at the head of the cached average-attention sublayer in one: sum += x; y = sum / (t + 1);
+// cat = [x | y] (tf.concat of transformer_aan.py:185) and a contiguous copy of y for the gate.  Same arithmetic and
+// rounding as aan_step_kernel + two add2d copies.
+__global__ void aan_cat_step_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ sum,
+                                    __nv_bfloat16* __restrict__ cat, long long ldcat, __nv_bfloat16* __restrict__ y,
+                                    long long rows, int d, float inv) {
+  grid_dep_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nvec = d >> 3;
+  if (i >= rows * nvec) return;
+  const long long r = i / nvec;
+  const int v = (int)(i % nvec);
+  const uint4 xr = __ldg(reinterpret_cast<const uint4*>(x + r * d + v * 8));
+  const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
+  float4* sp = reinterpret_cast<float4*>(sum + r * d + v * 8);
+  float4 s0 = sp[0], s1 = sp[1];
+  float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = unpack_bf16x2(w[e]);
+    s[2 * e] += t.x;
+    s[2 * e + 1] += t.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = s[e] * inv;
+  sp[0] = make_float4(s[0], s[1], s[2], s[3]);
+  sp[1] = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<uint4*>(cat + r * ldcat + v * 8) = xr;
+  st8(cat + r * ldcat + d + v * 8, o);
+  st8(y + r * d + v * 8, o);
+}
+
+// Gate + residual + LayerNorm of the average-attention sublayer in one pass over the row (one warp per row):
+// g = sigmoid(i) x + sigmoid(f) y with z = [i | f] (transformer_aan.py:185-189), out = LN(x + g) (func.py:289-324).
+// g is rounded to bf16 before the residual add, exactly what aan_gate_fwd_kernel hands to add_ln_fwd_kernel, and the
+// reductions run in the same order, so the fused and the two-kernel paths agree bit for bit.
+template <int NV>
+__global__ void __launch_bounds__(kVWarps * 32)
+aan_gate_ln_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                   const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ out,
+                   const float* __restrict__ scale, const float* __restrict__ offset, long long rows, int d, float eps) {
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = d >> 3;
+  const long long row = (long long)blockIdx.x * kVWarps + warp;
+  if (row >= rows) return;
+  float s[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float xv[8], yv[8], iv[8], fv[8];
+      ld8(x + row * d + v * 8, xv);
+      ld8(y + row * d + v * 8, yv);
+      ld8(z + row * 2 * d + v * 8, iv);
+      ld8(z + row * 2 * d + d + v * 8, fv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float g = sigm(iv[e]) * xv[e] + sigm(fv[e]) * yv[e];
+        s[i][e] = xv[e] + __bfloat162float(__float2bfloat16(g));
+        sum += s[i][e];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mu = sum / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dd = s[i][e] - mu;
+        sq += dd * dd;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rs = rsqrtf(sq / d + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = __ldg(scale + v * 8 + e) * (s[i][e] - mu) * rs + __ldg(offset + v * 8 + e);
+      st8(out + row * d + v * 8, o);
+    }
+  }
+}
+
 // out[r, :cols] = a[r, :cols] (+ b[r, :cols]); every operand a strided 2-D bf16 view (pitches in elements)
 __global__ void add2d_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b,
                              long long ldb, __nv_bfloat16* __restrict__ out, long long ldo, long long rows, int cols) {
@@ -361,6 +456,38 @@ extern "C" int zb_aan_step(const void* x, float* sum, void* y, int64_t n, int32_
   ZB_LAUNCH(aan_step_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)x, sum, (__nv_bfloat16*)y, n,
                                                                       1.f / (float)(time + 1));
   return check_launch("zb_aan_step");
+}
+extern "C" int zb_aan_cat_step(const void* x, float* sum, void* cat, int64_t ldcat, void* y, int64_t rows, int32_t dim,
+                               int32_t time, zb_stream_t stream) {
+  ZB_REQUIRE(x && sum && cat && y && rows >= 0 && dim > 0 && dim % 8 == 0 && ldcat % 8 == 0 && ldcat >= 2 * dim &&
+                 time >= 0,
+             "zb_aan_cat_step: bad args");
+  ZB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(sum) | reinterpret_cast<uintptr_t>(cat) |
+               reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+             "zb_aan_cat_step: operands must be 16-byte aligned");
+  const long long n = rows * (dim / 8);
+  if (n == 0) return ZB_OK;
+  ZB_LAUNCH(aan_cat_step_kernel, (unsigned)((n + 255) / 256), 256, 0, ST(stream), (const __nv_bfloat16*)x, sum,
+            (__nv_bfloat16*)cat, (long long)ldcat, (__nv_bfloat16*)y, (long long)rows, (int)dim,
+            1.f / (float)(time + 1));
+  return check_launch("zb_aan_cat_step");
+}
+extern "C" int zb_aan_gate_ln(const void* x, const void* y, const void* z, void* out, const float* scale,
+                              const float* offset, int64_t rows, int32_t dim, float eps, zb_stream_t stream) {
+  ZB_REQUIRE(x && y && z && out && scale && offset && rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= 8 * 32 * 8,
+             "zb_aan_gate_ln: bad args (dim must be a multiple of 8, <= 2048)");
+  if (rows == 0) return ZB_OK;
+  const unsigned grid = (unsigned)((rows + kVWarps - 1) / kVWarps);
+  const int nv = (dim / 8 + 31) / 32;
+#define ZB_GLN(N)                                                                                                   \
+  ZB_LAUNCH(aan_gate_ln_kernel<N>, grid, kVWarps * 32, 0, ST(stream), (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, \
+            (const __nv_bfloat16*)z, (__nv_bfloat16*)out, scale, offset, (long long)rows, (int)dim, eps)
+  if (nv <= 1) ZB_GLN(1);
+  else if (nv <= 2) ZB_GLN(2);
+  else if (nv <= 4) ZB_GLN(4);
+  else ZB_GLN(8);
+#undef ZB_GLN
+  return check_launch("zb_aan_gate_ln");
 }
 extern "C" int zb_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows,
                         int64_t cols, zb_stream_t stream) {

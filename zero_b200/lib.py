@@ -88,7 +88,7 @@ EXPORTS = [
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
-    "zb_gemm_grouped", "zb_colsum_grouped",
+    "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln",
 ]
 
 _lib = None
@@ -135,6 +135,8 @@ def load():
         ("zb_prefix_mean_fwd", [vp, vp, vp, i32, i32, i32, i32, vp]),
         ("zb_prefix_mean_bwd", [vp, vp, vp, i32, i32, i32, i32, vp]),
         ("zb_aan_step", [vp, vp, vp, i64, i32, vp]),
+        ("zb_aan_cat_step", [vp, vp, vp, i64, vp, i64, i32, i32, vp]),
+        ("zb_aan_gate_ln", [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]),
         ("zb_aan_gate_fwd", [vp, vp, vp, vp, i64, i32, vp]),
         ("zb_aan_gate_bwd", [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
         ("zb_gated_rms_fwd", [vp, vp, vp, vp, vp, i64, i64, f32, vp]),

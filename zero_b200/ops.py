@@ -238,6 +238,20 @@ def aan_step(x, running_sum, y, time):
     L.check(L.load().zb_aan_step(_p(x), _p(running_sum), _p(y), x.numel(), int(time), _stream()), "zb_aan_step")
 
 
+def aan_cat_step(x, running_sum, cat, y, time):
+    """aan_step + the concat of transformer_aan.py:185 in one launch: cat = [x | y], y = (sum += x) / (time + 1)."""
+    assert x.is_contiguous() and y.is_contiguous() and running_sum.is_contiguous() and cat.stride(1) == 1
+    L.check(L.load().zb_aan_cat_step(_p(x), _p(running_sum), _p(cat), cat.stride(0), _p(y), x.shape[0], x.shape[1],
+                                     int(time), _stream()), "zb_aan_cat_step")
+
+
+def aan_gate_ln(x, y, z, out, scale, offset, eps):
+    """out = LN(x + sigmoid(i) x + sigmoid(f) y), z = [i | f] (transformer_aan.py:185-192) in one launch."""
+    assert x.is_contiguous() and y.is_contiguous() and z.is_contiguous() and out.is_contiguous()
+    L.check(L.load().zb_aan_gate_ln(_p(x), _p(y), _p(z), _p(out), _p(scale), _p(offset), x.shape[0], x.shape[1],
+                                    float(eps), _stream()), "zb_aan_gate_ln")
+
+
 def aan_gate_fwd(x, y, z, out):
     """y' = sigmoid(i) x + sigmoid(f) y (models/transformer_aan.py:185-189)."""
     L.check(L.load().zb_aan_gate_fwd(_p(x), _p(y), _p(z), _p(out), x.numel() // x.shape[-1], x.shape[-1], _stream()),
