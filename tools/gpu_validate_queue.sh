@@ -1,0 +1,36 @@
+#!/bin/bash
+# First GPU-box visit after a stretch of CPU-only work: (1) the default parity suite, (2) the opt-in parity tests of
+# every kernel / switch written without a GPU, (3) the decode A/B over those switches,
+# (4) ncu --set full of the two kernels whose time is not explained yet.  Outputs under gpurun_out/TAG_*.
+tag=${1:-queue}
+mkdir -p gpurun_out
+t0=$SECONDS
+timeout 120 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests.log
+t0=$SECONDS
+ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode" \
+  > gpurun_out/${tag}_tests_unvalidated.log 2>&1; echo "unvalidated rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests_unvalidated.log
+{
+  timeout 60 python tools/decode_ab.py
+  ZB_BEAM_PARTS=1 timeout 60 python tools/decode_ab.py
+  ZB_GEMM_BM64=1 timeout 60 python tools/decode_ab.py
+  ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
+  ZB_BEAM_PARTS=1 ZB_GEMM_BM64=1 ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
+} > gpurun_out/${tag}_decode_ab.jsonl 2> gpurun_out/${tag}_decode_ab.err
+if [ -z "$SKIP_NCU" ]; then
+ZB_DECODE_GRAPH=0 timeout 90 ncu --set full --clock-control none --import-source on -k regex:"beam_row|beam_part" \
+  --launch-skip 70 -c 2 -f -o gpurun_out/${tag}_beam_full python tools/decode_ab.py 1 > gpurun_out/${tag}_ncu_beam.log 2>&1
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:"add_ln_bwd_1pass" --launch-skip 40 -c 2 -f \
+  -o gpurun_out/${tag}_lnbwd_full python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-decode \
+  > gpurun_out/${tag}_ncu_lnbwd.log 2>&1
+fi
+grep -E "passed|failed|error" gpurun_out/${tag}_tests.log | tail -2
+grep -E "passed|failed|error" gpurun_out/${tag}_tests_unvalidated.log | tail -2; grep -E "^FAILED|^ERROR" gpurun_out/${tag}_tests_unvalidated.log | head -30
+python - <<PY
+import json
+for l in open("gpurun_out/${tag}_decode_ab.jsonl"):
+    try:
+        d = json.loads(l); print("%-100s %8.0f tok/s  %.3f ms/step" % (d["switches"], d["value"], d["ms_per_step"]))
+    except Exception:
+        print("bad line", l[:100])
+PY
+tail -3 gpurun_out/${tag}_decode_ab.err
