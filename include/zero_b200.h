@@ -52,7 +52,8 @@ typedef enum {
   ZB_PATH_BEAM_ROWS = 7,      /* beam.cu one CTA per (sentence, beam) row */
   ZB_PATH_BEAM_PARTS = 8,     /* beam.cu a 4-CTA cluster per row with a threshold pass, opt-in */
   ZB_PATH_GEMM_BM64 = 9,      /* single-CTA tcgen05 GEMM with 64-row tiles, opt-in (also counted as GEMM_TCGEN05) */
-  ZB_PATH_COUNT_ = 10
+  ZB_PATH_ATTN_TC = 10,       /* attention_mma.cu tcgen05 forward for 64-token head pairs, opt-in */
+  ZB_PATH_COUNT_ = 11
 } zb_path;
 int64_t zb_path_launch_count(int32_t which);
 /* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,

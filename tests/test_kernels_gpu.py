@@ -618,3 +618,38 @@ def test_fused_small_decode_kernels_equal_the_unfused_pairs(rows, d):
     ops.aan_gate_ln(x, xf, z, out2, scale, offset, 1e-8)
     torch.testing.assert_close(out2.float(), out.float(), atol=2e-2, rtol=1e-2)
     assert float((out2.float() - out.float()).abs().max()) <= 0.0625   # at most an ulp of bf16 at |v| < 8
+
+
+@unvalidated
+@pytest.mark.parametrize("B,h,causal,klen,fused", [(4, 8, False, True, True), (4, 8, True, False, True),
+                                                     (64, 8, False, True, True), (3, 2, True, True, False)])
+def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
+    """ZB_ATTN_TC=1: the tcgen05 forward for 64-token head pairs (S and O in TMEM, P through shared memory) against
+    the torch restatement and against the mma.sync tile kernel it replaces, reading q / k / v in place from a fused
+    [tokens, 3d] buffer (fused=True) or from separate tensors."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    D, Lq = h * 64, 64
+    if fused:
+        qkv = rnd(B, Lq, 3 * D, seed=41)
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    else:
+        q, k, v = rnd(B, Lq, D, seed=42), rnd(B, Lq, D, seed=43), rnd(B, Lq, D, seed=44)
+    key_len = None
+    if klen:
+        key_len = torch.randint(1, Lq + 1, (B,), dtype=torch.int32, device=dev())
+        key_len[0] = Lq
+    outs, lses = [], []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("ZB_ATTN_TC", tc)
+        before = L.path_launch_count("attn_tc")
+        o = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+        lse = torch.empty(B, h, Lq, device=dev())
+        ops.attention_fwd(ops.attention_args(q, k, v, o, h, key_len=key_len, causal=causal, lse=lse))
+        assert L.path_launch_count("attn_tc") == before + int(tc)
+        outs.append(o)
+        lses.append(lse)
+    ref = _attn_ref(q.float(), k.float(), v.float(), h, key_len, causal, 0, 1e8, None, None, 0, False)
+    torch.testing.assert_close(outs[1].float(), ref, atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(outs[1].float(), outs[0].float(), atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lses[1], lses[0], atol=1e-3, rtol=1e-3)

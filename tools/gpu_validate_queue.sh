@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 t0=$SECONDS
 timeout 120 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests.log
 t0=$SECONDS
-ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode" \
+ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode or attention_tcgen05" \
   > gpurun_out/${tag}_tests_unvalidated.log 2>&1; echo "unvalidated rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests_unvalidated.log
 {
   timeout 60 python tools/decode_ab.py
@@ -16,6 +16,12 @@ ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part
   ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
   ZB_BEAM_PARTS=1 ZB_GEMM_BM64=1 ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
 } > gpurun_out/${tag}_decode_ab.jsonl 2> gpurun_out/${tag}_decode_ab.err
+# training step with / without the tcgen05 attention forward (only if its parity test passed)
+if grep -q "attention_tcgen05.*PASSED\|passed" gpurun_out/${tag}_tests_unvalidated.log && ! grep -q "FAILED.*attention_tcgen05" gpurun_out/${tag}_tests_unvalidated.log; then
+  timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_default.json 2>/dev/null
+  ZB_ATTN_TC=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_attn_tc.json 2>/dev/null
+  cut -c1-200 gpurun_out/${tag}_bench_default.json gpurun_out/${tag}_bench_attn_tc.json
+fi
 if [ -z "$SKIP_NCU" ]; then
 ZB_DECODE_GRAPH=0 timeout 90 ncu --set full --clock-control none --import-source on -k regex:"beam_row|beam_part" \
   --launch-skip 70 -c 2 -f -o gpurun_out/${tag}_beam_full python tools/decode_ab.py 1 > gpurun_out/${tag}_ncu_beam.log 2>&1

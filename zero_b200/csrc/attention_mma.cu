@@ -620,6 +620,168 @@ __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int 
   }
 }
 
+// ================================================================================================ tcgen05 path
+// (opt-in, ZB_ATTN_TC=1 — written after the round's last GPU visit; parity test opt-in, not yet timed.)
+// Forward attention of the 64-token training batches on the 5th-generation tensor cores: one CTA per PAIR of heads
+// (h, h + 1) of one batch element, so the two 64 x 64 problems fill one 128-row tcgen05.mma:
+//   S[128 x 128] = [Q_h ; Q_h+1] [K_h ; K_h+1]^T       (fp32 in TMEM; only the two diagonal 64 x 64 blocks are used)
+//   P[128 x 128] = softmax rows of the diagonal blocks, zero elsewhere (bf16, written to shared memory in the
+//                  canonical K-major SWIZZLE_128B layout a TMA load would produce)
+//   O[128 x 64]  = P [V_h ; V_h+1]                     (the zero blocks cancel the other head's values)
+// Q / K / V tiles arrive by TMA (two 64 x 64 boxes each, read in place from the fused [tokens, 3d] buffer), one
+// elected thread issues both MMAs, four warps own one S / O row per thread (tcgen05.ld), logits and probabilities
+// never touch HBM.  Everything is single-shot per CTA (every mbarrier is used once, phase 0): 80 KB of shared memory
+// and 256 TMEM columns let two CTAs share an SM, which is where the overlap of one pair's softmax with another pair's
+// loads and MMAs comes from.  Requires lq = lk = 64, an even head count, no dropout, batch-contiguous q / k / v views.
+constexpr int TC_THREADS = 160;  // warp 0: TMEM allocation, TMA, MMA issue; warps 1-4: one S / O row per thread
+struct TcSmem {
+  __nv_bfloat16 q[128 * 64], k[128 * 64], v[128 * 64];   // two 64-row boxes each (head h, head h + 1)
+  __nv_bfloat16 p[2][128 * 64];                            // A operand of the second MMA: two 64-wide k atoms
+  uint64_t bar_full, bar_s, bar_p, bar_o;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+fwd_tc64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                const __grid_constant__ CUtensorMap tma_v, const Params p) {
+  extern __shared__ uint8_t tc_raw[];
+  TcSmem& T = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairs = p.heads >> 1;
+  const int b = blockIdx.x / pairs, h0 = (blockIdx.x % pairs) * 2;
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tma_q);
+      tma_prefetch_desc(&tma_k);
+      tma_prefetch_desc(&tma_v);
+      mbar_init(&T.bar_full, 1);
+      mbar_init(&T.bar_s, 1);
+      mbar_init(&T.bar_p, 4);   // one arrival per softmax warp
+      mbar_init(&T.bar_o, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(&T.tmem_slot, 256);   // S: columns [0, 128), O: columns [128, 192)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = T.tmem_slot;
+  grid_dep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&T.bar_full, 3 * 128 * 64 * 2);
+      const int qrow = b * 64, krow = b * 64;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {   // box {64 channels of head h0 + i, 64 rows}
+        tma_load_2d(T.q + i * 64 * 64, &tma_q, &T.bar_full, (h0 + i) * 64, qrow);
+        tma_load_2d(T.k + i * 64 * 64, &tma_k, &T.bar_full, (h0 + i) * 64, krow);
+        tma_load_2d(T.v + i * 64 * 64, &tma_v, &T.bar_full, (h0 + i) * 64, krow);
+      }
+      mbar_wait(&T.bar_full, 0);
+      tc_fence_after();
+      {  // S = Q K^T : A = Q [128 m][64 k] K-major, B = K [128 n][64 k] K-major
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0u, 0u);
+        const uint32_t sa = smem_u32(T.q), sb = smem_u32(T.k);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem_base, umma_smem_desc(sa + kk * 32, 0, 1024), umma_smem_desc(sb + kk * 32, 0, 1024), idesc,
+                       kk > 0 ? 1u : 0u);
+        umma_commit(&T.bar_s);
+      }
+      mbar_wait(&T.bar_p, 0);
+      tc_fence_after();
+      {  // O = P V : A = P [128 m][128 k] K-major (two 64-wide k atoms), B = V [128 k][64 n] MN-major
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0u, 1u);
+        const uint32_t sb = smem_u32(T.v);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t sa = smem_u32(T.p[kk >> 2]) + (kk & 3) * 32;
+          umma_bf16_ss(tmem_base + 128, umma_smem_desc(sa, 0, 1024), umma_smem_desc(sb + kk * 2048, 64 * 128, 1024), idesc,
+                       kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&T.bar_o);
+      }
+    }
+  } else {
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;             // row of the stacked problem
+    const int item = row >> 6, r = row & 63;      // which head of the pair, query position
+    const int h = h0 + item;
+    const int kl = p.key_len ? p.key_len[b] : p.lk;
+    mbar_wait(&T.bar_s, 0);
+    tc_fence_after();
+    uint32_t ra[32], rb[32];
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + item * 64;
+    tmem_ld_32x32b_x32(t_s, ra);
+    tmem_ld_32x32b_x32(t_s + 32, rb);
+    tmem_ld_wait();
+    float sv[64];
+    const int i_abs = r + p.q_offset;
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      float v = __uint_as_float(j < 32 ? ra[j] : rb[j - 32]) * p.scale;
+      const bool valid = j < kl && (!p.causal || j <= i_abs);
+      v = valid ? v : v - p.inf_value;
+      sv[j] = v;
+      m = fmaxf(m, v);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      sv[j] = __expf(sv[j] - m);
+      l += sv[j];
+    }
+    // P row: 16 chunks of 8 bf16; chunk c of atom a lives at row * 128 B + ((c ^ (row & 7)) * 16 B) of T.p[a]
+    uint8_t* prow0 = reinterpret_cast<uint8_t*>(T.p[0]) + row * 128;
+    uint8_t* prow1 = reinterpret_cast<uint8_t*>(T.p[1]) + row * 128;
+    uint8_t* mine = item ? prow1 : prow0;
+    uint8_t* other = item ? prow0 : prow1;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u;
+      u.x = pack_bf16x2(sv[8 * c + 0], sv[8 * c + 1]);
+      u.y = pack_bf16x2(sv[8 * c + 2], sv[8 * c + 3]);
+      u.z = pack_bf16x2(sv[8 * c + 4], sv[8 * c + 5]);
+      u.w = pack_bf16x2(sv[8 * c + 6], sv[8 * c + 7]);
+      const int pc = (c ^ (row & 7)) * 16;
+      *reinterpret_cast<uint4*>(mine + pc) = u;
+      *reinterpret_cast<uint4*>(other + pc) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();    // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    tc_fence_before();           // this thread's tcgen05.ld of S are complete (waited) before the MMA warp proceeds
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&T.bar_p);
+    mbar_wait(&T.bar_o, 0);
+    tc_fence_after();
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 128;
+    tmem_ld_32x32b_x32(t_o, ra);
+    tmem_ld_32x32b_x32(t_o + 32, rb);
+    tmem_ld_wait();
+    const float inv = 1.f / l;
+    __nv_bfloat16* op = p.out + (long long)b * p.bso + (long long)r * p.ldo + h * DH;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u;
+      const uint32_t* src = c < 4 ? ra + 8 * c : rb + 8 * (c - 4);
+      u.x = pack_bf16x2(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+      u.y = pack_bf16x2(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+      u.z = pack_bf16x2(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+      u.w = pack_bf16x2(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+      reinterpret_cast<uint4*>(op)[c] = u;
+    }
+    if (p.lse) p.lse[((long long)b * p.heads + h) * p.lq + r] = m + __logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 static Params to_params(const zb_attention_args* a) {
   Params p;
   p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
@@ -663,9 +825,40 @@ static bool tile64_ok(const zb_attention_args* a) {
   return !off && a->lq <= 64 && a->lk <= 64 && a->kv_group <= 1;
 }
 
+int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);  // gemm_tcgen05.cu
+
+// lq = lk = 64, head pairs, batch-contiguous 2-D views (row pitch ld, batch pitch 64 * ld), no dropout
+static bool tc64_ok(const zb_attention_args* a, const fa::Params& p) {
+  const char* e = getenv("ZB_ATTN_TC");   // per call: the parity test flips it inside one process
+  if (!(e && e[0] == '1')) return false;
+  if (a->lq != 64 || a->lk != 64 || (a->heads & 1) || p.drop_rate > 0.f || a->kv_group > 1) return false;
+  if (a->bsq != 64 * a->ldq || a->bsk != 64 * a->ldk || a->bsv != 64 * a->ldv) return false;
+  if (a->ldo % 8 || a->bso % 8) return false;
+  return true;
+}
+
+static int attention_tc_fwd(const zb_attention_args* a, const fa::Params& p, cudaStream_t st) {
+  CUtensorMap mq, mk, mv;
+  const uint64_t width = (uint64_t)a->heads * 64, rows = (uint64_t)a->batch * 64;
+  int rc = make_map(&mq, a->q, width, rows, a->ldq, 64);
+  if (!rc) rc = make_map(&mk, a->k, width, rows, a->ldk, 64);
+  if (!rc) rc = make_map(&mv, a->v, width, rows, a->ldv, 64);
+  if (rc) return rc;
+  const int smem = (int)sizeof(fa::TcSmem) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fa::fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  ZB_LAUNCH(fa::fwd_tc64_kernel, a->batch * (a->heads / 2), fa::TC_THREADS, smem, st, mq, mk, mv, p);
+  note_path(ZB_PATH_ATTN_TC);
+  return check_launch("zb_attention_fwd(tcgen05)");
+}
+
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   const bool drop = p.drop_rate > 0.f;
+  if (tile64_ok(a) && tc64_ok(a, p)) return attention_tc_fwd(a, p, st);
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
     const int smem = (int)sizeof(fa::Tile64Fwd);

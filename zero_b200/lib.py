@@ -166,7 +166,7 @@ def check(rc, what):
 
 
 PATHS = {"gemm_tcgen05": 0, "gemm_pair": 1, "gemm_skinny": 2, "attn_mma": 3, "attn_generic": 4, "attn_decode": 5,
-         "beam_sentence": 6, "beam_rows": 7, "beam_parts": 8, "gemm_bm64": 9}
+         "beam_sentence": 6, "beam_rows": 7, "beam_parts": 8, "gemm_bm64": 9, "attn_tc": 10}
 
 
 def path_launch_count(name) -> int:
