@@ -22,6 +22,12 @@ if grep -q "attention_tcgen05.*PASSED\|passed" gpurun_out/${tag}_tests_unvalidat
   ZB_ATTN_TC=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_attn_tc.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_default.json gpurun_out/${tag}_bench_attn_tc.json
 fi
+# add+LN backward with 16 rows per CTA: parity test under the switch, then the training bench
+ZB_LN1P_WARPS=16 timeout 60 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "add_ln" > gpurun_out/${tag}_tests_ln16.log 2>&1
+if tail -1 gpurun_out/${tag}_tests_ln16.log | grep -q passed && ! grep -q failed gpurun_out/${tag}_tests_ln16.log; then
+  ZB_LN1P_WARPS=16 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_ln16.json 2>/dev/null
+  cut -c1-200 gpurun_out/${tag}_bench_ln16.json
+fi
 if [ -z "$SKIP_NCU" ]; then
 ZB_DECODE_GRAPH=0 timeout 90 ncu --set full --clock-control none --import-source on -k regex:"beam_row|beam_part" \
   --launch-skip 70 -c 2 -f -o gpurun_out/${tag}_beam_full python tools/decode_ab.py 1 > gpurun_out/${tag}_ncu_beam.log 2>&1

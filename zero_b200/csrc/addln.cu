@@ -213,22 +213,24 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, const float4 v) {
                : "memory");
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kLn1pWarps * 32, 1)
+// W = warps (= rows) per CTA: 32 is the measured default; 16 (ZB_LN1P_WARPS=16, opt-in, untimed) halves the shared
+// memory per CTA (two CTAs per SM, twice the CTAs) at the price of twice the vector reductions per column.
+template <int NV, int W = kLn1pWarps>
+__global__ void __launch_bounds__(W * 32, 1)
 add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                         const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ scale, __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale,
                         float* __restrict__ doffset, float* __restrict__ dbias, long long rows, int cols) {
   grid_dep_wait();
-  extern __shared__ __align__(16) float red[];  // [3][kLn1pWarps][cols]
+  extern __shared__ __align__(16) float red[];  // [3][W][cols]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = cols >> 3;
-  const long long row = (long long)blockIdx.x * kLn1pWarps + warp;
+  const long long row = (long long)blockIdx.x * W + warp;
   const bool live = row < rows;
   float* r_s = red + (size_t)warp * cols;
-  float* r_o = red + (size_t)(kLn1pWarps + warp) * cols;
-  float* r_b = red + (size_t)(2 * kLn1pWarps + warp) * cols;
+  float* r_o = red + (size_t)(W + warp) * cols;
+  float* r_b = red + (size_t)(2 * W + warp) * cols;
   float sh[NV][8], d[NV][8];
   float sg = 0.f, sgs = 0.f;
   float mu = 0.f, rs = 0.f;
@@ -306,10 +308,10 @@ add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
   const int c4n = cols >> 2;
   const int q = threadIdx.x / c4n, c4 = threadIdx.x % c4n;
   if (q < (dbias ? 3 : 2)) {
-    const float* src = red + (size_t)q * kLn1pWarps * cols + c4 * 4;
+    const float* src = red + (size_t)q * W * cols + c4 * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-    for (int w = 0; w < kLn1pWarps; ++w) {
+    for (int w = 0; w < W; ++w) {
       const float4 t = *reinterpret_cast<const float4*>(src + (size_t)w * cols);
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
@@ -366,6 +368,27 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   static const bool no_1pass = getenv("ZB_LN_BWD_LOOP") != nullptr;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(a->dscale) | reinterpret_cast<uintptr_t>(a->doffset) |
                         reinterpret_cast<uintptr_t>(a->dbias)) & 15) == 0;
+  static const bool w16 = getenv("ZB_LN1P_WARPS") != nullptr && atoi(getenv("ZB_LN1P_WARPS")) == 16;
+  if (!no_1pass && w16 && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= 16 * 32 && a->rows <= (long long)num_sms() * 32) {
+    const int grid = (int)((a->rows + 15) / 16);
+    const size_t smem1 = (size_t)3 * 16 * a->cols * sizeof(float);
+#define CALL16(N)                                                                                            \
+  do {                                                                                                       \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      cudaFuncSetAttribute(add_ln_bwd_1pass_kernel<N, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           3 * 16 * 512 * (int)sizeof(float));                                               \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    ZB_LAUNCH((add_ln_bwd_1pass_kernel<N, 16>), grid, 16 * 32, smem1, st,                                    \
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
+        (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
+        a->doffset, a->dbias, a->rows, (int)a->cols);                                                        \
+  } while (0)
+    if (nv <= 1) CALL16(1); else CALL16(2);
+#undef CALL16
+    return check_launch("zb_add_ln_bwd(1pass, 16 rows)");
+  }
   if (!no_1pass && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= kLn1pWarps * 32 &&
       a->rows <= (long long)num_sms() * kLn1pWarps) {
     const int grid = (int)((a->rows + kLn1pWarps - 1) / kLn1pWarps);
