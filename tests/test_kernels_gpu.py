@@ -649,7 +649,28 @@ def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
         assert L.path_launch_count("attn_tc") == before + int(tc)
         outs.append(o)
         lses.append(lse)
-    ref = _attn_ref(q.float(), k.float(), v.float(), h, key_len, causal, 0, 1e8, None, None, 0, False)
-    torch.testing.assert_close(outs[1].float(), ref, atol=3e-2, rtol=3e-2)
+    leaves = [t.float().detach().clone().requires_grad_(True) for t in (q, k, v)]
+    ref = _attn_ref(leaves[0], leaves[1], leaves[2], h, key_len, causal, 0, 1e8, None, None, 0, False)
+    torch.testing.assert_close(outs[1].float(), ref.detach(), atol=3e-2, rtol=3e-2)
     torch.testing.assert_close(outs[1].float(), outs[0].float(), atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lses[1], lses[0], atol=1e-3, rtol=1e-3)
+    # backward: five tcgen05 MMAs per head pair against autograd and against the mma.sync tile kernel
+    d_o = rnd(B, Lq, D, seed=45)
+    ref.backward(d_o.float())
+    grads = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("ZB_ATTN_TC", tc)
+        before = L.path_launch_count("attn_tc")
+        if fused:
+            dqkv = torch.zeros(B, Lq, 3 * D, dtype=bf16, device=dev())
+            dq, dk, dv = dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:]
+        else:
+            dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        a = ops.attention_args(q, k, v, outs[0], h, key_len=key_len, causal=causal, lse=lses[0])
+        delta = torch.empty(B, h, Lq, device=dev())
+        ops.attention_bwd(a, d_o, dq, dk, dv, delta, None, None)
+        assert L.path_launch_count("attn_tc") == before + int(tc)
+        grads.append((dq, dk, dv))
+    for got, old_, want in zip(grads[1], grads[0], [t.grad for t in leaves]):
+        torch.testing.assert_close(got.float(), want, atol=6e-2, rtol=5e-2)
+        torch.testing.assert_close(got.float(), old_.float(), atol=4e-2, rtol=4e-2)
