@@ -90,3 +90,38 @@ def test_param_store_layout_is_tma_legal_and_name_complete():
     assert sum(int(torch.tensor(s).prod()) for s in shapes.values()) == 76907008
     for name, (off, shape) in ps.slots.items():
         assert off % 64 == 0, name                 # 128-byte aligned bf16 views
+
+
+def test_batched_memory_projection_layout(monkeypatch):
+    """ZB_BATCH_MEM_PROJ=1: the k_map | v_map weights of all decoder layers are windows of ONE [d, ndec * 2d] matrix.
+    Same TF names, same shapes, every parameter element owned by exactly one TF variable, per-layer windows strided
+    with a 16-byte-granular pitch (TMA-legal), and the TF-name order (hence the seeded initialisation) unchanged."""
+    from collections import OrderedDict
+    hp = transformer_base()
+
+    def plan():
+        cfg = ModelConfig(hp, 32000, 32000)
+        ps = ParamStore.__new__(ParamStore)
+        ps.cfg, ps.slots, ps.alias, ps.tf_views = cfg, OrderedDict(), {}, OrderedDict()
+        ps._plan()
+        return cfg, ps
+    cfg0, ps0 = plan()
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "1")
+    cfg1, ps1 = plan()
+    assert not cfg0.batch_mem and cfg1.batch_mem
+    assert list(ps1.tf_views) == list(ps0.tf_views)
+    d, nd = cfg1.d, cfg1.ndec
+    arena = torch.zeros(ps1.total, dtype=torch.int32)
+    for k in ps1.tf_views:
+        v0, v1 = ps0.tf_view(torch.zeros(ps0.total), k), ps1.tf_view(arena, k)
+        assert tuple(v0.shape) == tuple(v1.shape), k
+        v1 += 1
+    assert int(arena.sum()) == 76907008 and int(arena.max()) == 1      # disjoint windows, nothing counted twice
+    for l in range(nd):
+        w = ps1._view(arena, "dec%d.cross.kv.W" % l)
+        assert tuple(w.shape) == (d, 2 * d) and w.stride() == (nd * 2 * d, 1)
+        assert w.data_ptr() == ps1._view(arena, "dec.kvall.W").data_ptr() + l * 2 * d * arena.element_size()
+        k_map = ps1.tf_view(arena, "transformer/decoder/layer_%d/cross_attention/dot_attention/k_map/W_0_0" % l)
+        assert k_map.data_ptr() == w.data_ptr() and tuple(k_map.shape) == (d, d)
+    assert ps1.slots["dec.kvall.W"][0] % 64 == 0 and (nd * 2 * d) % 8 == 0
+    assert ps1.slots["dec.kvall.W"][0] >= ps1.dec_offset               # stays in the decoder-side all-reduce bucket

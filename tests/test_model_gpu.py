@@ -254,3 +254,38 @@ def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     got = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
     np.testing.assert_array_equal(got["seq"].cpu().numpy(), ref["seq"].cpu().numpy())
     np.testing.assert_allclose(got["score"].cpu().numpy(), ref["score"].cpu().numpy(), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
+                    reason="switch not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("name", ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela"])
+def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch):
+    """ZB_BATCH_MEM_PROJ=1 (one GEMM for every decoder layer's k_map | v_map, one dgrad / wgrad pair backward):
+    loss, every gradient and the beams against the reference-executed golden vectors, and the gradients against
+    the default layout's to bf16 round-off."""
+    from zero_b200 import search
+    from zero_b200.params import SimpleVocab
+    eng0, z, hp, variables, grads = _engine(name)
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    loss0 = float(eng0.forward_backward(src, tgt)[0])
+    got0 = eng0.ps.grad_dict()
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "1")
+    eng1, _, _, _, _ = _engine(name)
+    assert eng1.cfg.batch_mem and "dec.kvall.W" in eng1.ps.slots
+    loss1 = float(eng1.forward_backward(src, tgt)[0])
+    torch.cuda.synchronize()
+    assert abs(loss1 - float(z["loss"])) < 2e-2 and abs(loss1 - loss0) < 2e-3
+    got1 = eng1.ps.grad_dict()
+    for k, g in grads.items():
+        if float(g.abs().max()) < 1e-6:
+            assert float(got1[k].abs().max()) < 2e-3, k
+            continue
+        cos = torch.nn.functional.cosine_similarity(got1[k].double().flatten(), got0[k].double().flatten(), dim=0)
+        assert cos > 0.999, "%s: cosine to the default layout %.5f" % (k, float(cos))
+    hp.add_hparam("src_vocab", SimpleVocab(eng1.cfg.vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(eng1.cfg.vt))
+    hp.add_hparam("decode_graph", False)
+    eng0.decode_length = eng1.decode_length = hp.decode_length
+    a = search.beam_search({"source": src}, eng0.encoding_fn, eng0.decoding_fn, hp)
+    b = search.beam_search({"source": src}, eng1.encoding_fn, eng1.decoding_fn, hp)
+    np.testing.assert_array_equal(a["seq"].cpu().numpy(), b["seq"].cpu().numpy())

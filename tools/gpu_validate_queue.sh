@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 t0=$SECONDS
 timeout 120 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests.log
 t0=$SECONDS
-ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode or attention_tcgen05" \
+ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode or attention_tcgen05 or batched_memory" \
   > gpurun_out/${tag}_tests_unvalidated.log 2>&1; echo "unvalidated rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests_unvalidated.log
 {
   timeout 60 python tools/decode_ab.py
@@ -21,6 +21,11 @@ if grep -q "attention_tcgen05.*PASSED\|passed" gpurun_out/${tag}_tests_unvalidat
   timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_default.json 2>/dev/null
   ZB_ATTN_TC=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_attn_tc.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_default.json gpurun_out/${tag}_bench_attn_tc.json
+fi
+# batched memory projection: training bench under the switch (its parity test ran above)
+if ! grep -q "FAILED.*batched_memory" gpurun_out/${tag}_tests_unvalidated.log; then
+  ZB_BATCH_MEM_PROJ=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_batchmem.json 2>/dev/null
+  cut -c1-200 gpurun_out/${tag}_bench_batchmem.json
 fi
 # add+LN backward with 16 rows per CTA: parity test under the switch, then the training bench
 ZB_LN1P_WARPS=16 timeout 60 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "add_ln" > gpurun_out/${tag}_tests_ln16.log 2>&1

@@ -14,6 +14,7 @@ is projected by one GEMM; their TF names are strided views into the fused tensor
 from __future__ import annotations
 
 import math
+import os
 import zlib
 from collections import OrderedDict
 
@@ -70,6 +71,11 @@ class ModelConfig(object):
         known = ("transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse")
         if self.model not in known:
             raise L.ZeroB200Error("model %r is outside the hot path (supported: %s)" % (self.model, ", ".join(known)))
+        # opt-in (ZB_BATCH_MEM_PROJ=1, untimed): the k_map | v_map weights of ALL decoder layers live side by side in
+        # one [d, ndec * 2d] matrix, so the memory projections of a training step are ONE GEMM forward (n = ndec * 2d)
+        # and ONE dgrad / wgrad pair backward (k = ndec * 2d) instead of ndec small ones each
+        self.batch_mem = os.environ.get("ZB_BATCH_MEM_PROJ") == "1" and self.model not in (
+            "transformer_aan", "transformer_fuse")
 
     rpr = property(lambda s: s.model == "transformer_rpr")
     rela = property(lambda s: s.model == "transformer_rela")
@@ -87,6 +93,7 @@ class ParamStore(object):
         self.cfg = cfg
         self.device = device
         self.slots = OrderedDict()     # engine tensor name -> (offset, shape)
+        self.alias = {}                # engine tensor name -> (parent slot, slicer): a strided window of another slot
         self.tf_views = OrderedDict()  # TF variable name -> (engine name, slicer)
         self._plan()
         n = self.total
@@ -142,11 +149,15 @@ class ParamStore(object):
             lin(key + ".o", tfp + "/dot_attention/o_map", c.d, c.d)
             ln(key + ".ln", tfp)
 
-        def cross_attn(key, tfp):
+        def cross_attn(key, tfp, l=0):
             lin(key + ".q", tfp + "/dot_attention/q_map", c.d, c.d)
             # fused k_map | v_map storage; TF names are column slices
-            self._add(key + ".kv.W", (c.d, 2 * c.d))
-            self._add(key + ".kv.b", (2 * c.d,))
+            if c.batch_mem:
+                self.alias[key + ".kv.W"] = ("dec.kvall.W", (slice(None), slice(l * 2 * c.d, (l + 1) * 2 * c.d)))
+                self.alias[key + ".kv.b"] = ("dec.kvall.b", (slice(l * 2 * c.d, (l + 1) * 2 * c.d),))
+            else:
+                self._add(key + ".kv.W", (c.d, 2 * c.d))
+                self._add(key + ".kv.b", (2 * c.d,))
             self.tf_views[tfp + "/dot_attention/k_map/W_0_0"] = (key + ".kv.W", (slice(None), slice(0, c.d)))
             self.tf_views[tfp + "/dot_attention/k_map/b_0"] = (key + ".kv.b", (slice(0, c.d),))
             self.tf_views[tfp + "/dot_attention/v_map/W_0_0"] = (key + ".kv.W", (slice(None), slice(c.d, 2 * c.d)))
@@ -172,6 +183,9 @@ class ParamStore(object):
             self._add("tgt_emb", (c.vt, c.e), s + "/tgt_embedding")
             if not c.share_ts:
                 self._add("softmax_emb", (c.vt, c.e), s + "/softmax_embedding")
+        if c.batch_mem:
+            self._add("dec.kvall.W", (c.d, c.ndec * 2 * c.d))
+            self._add("dec.kvall.b", (c.ndec * 2 * c.d,))
         for l in range(c.ndec):
             key, tfp = "dec%d" % l, "%s/decoder/layer_%d" % (s, l)
             if c.aan:
@@ -185,12 +199,15 @@ class ParamStore(object):
                 cross_attn(key + ".cross", tfp + "/fuse_attention")
             else:
                 self_attn(key + ".self", tfp + "/self_attention")
-                cross_attn(key + ".cross", tfp + "/cross_attention")
+                cross_attn(key + ".cross", tfp + "/cross_attention", l)
             ffn(key + ".ffn", tfp + "/feed_forward")
             ln(key + ".ffn.ln", tfp + "/feed_forward")
 
     # -- views ---------------------------------------------------------------------------------------
     def _view(self, arena, name):
+        if name in self.alias:
+            parent, sl = self.alias[name]
+            return self._view(arena, parent)[sl]
         off, shape = self.slots[name]
         n = 1
         for s in shape:
@@ -446,14 +463,16 @@ class Engine(object):
         ops.linear_dgrad(dqkv, ps.w(key + ".qkv.W"), dx)
         return dx
 
-    def _cross_attn_fwd(self, key, x, enc, B, Lq, S, src_len, sv, tag):
-        """func.dot_attention with memory (func.py:206-216, 218-256, 277-278)."""
+    def _cross_attn_fwd(self, key, x, enc, B, Lq, S, src_len, sv, tag, kv=None):
+        """func.dot_attention with memory (func.py:206-216, 218-256, 277-278).  `kv`: this layer's window of the
+        batched memory projection (cfg.batch_mem), else the projection runs here."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
         q = ws.get(tag + ".q", (N, c.d))
         ops.linear_fwd(x, ps.w(key + ".q.W"), ps.p(key + ".q.b"), q)
-        kv = ws.get(tag + ".kv", (B * S, 2 * c.d))
-        ops.linear_fwd(enc, ps.w(key + ".kv.W"), ps.p(key + ".kv.b"), kv)
+        if kv is None:
+            kv = ws.get(tag + ".kv", (B * S, 2 * c.d))
+            ops.linear_fwd(enc, ps.w(key + ".kv.W"), ps.p(key + ".kv.b"), kv)
         kv3 = kv.view(B, S, 2 * c.d)
         ctx = ws.get(tag + ".ctx", (N, c.d))
         lse = ws.get(tag + ".lse", (B, c.h, Lq), f32)
@@ -470,23 +489,28 @@ class Engine(object):
         sv.update(q=q, kv=kv, ctx=ctx, feed=feed, lse=lse, attn=a, y=y)
         return y
 
-    def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag):
+    def _cross_attn_bwd(self, key, x, enc, dy, d_enc, B, Lq, S, sv, tag, dkv=None):
+        """`dkv`: this layer's window of the batched d(memory projection) (cfg.batch_mem): its weight / input
+        gradients are then taken once for all layers by decode_train_bwd."""
         c, ps, ws = self.cfg, self.ps, self.ws
         N = B * Lq
+        batched = dkv is not None
         self._wgrad(sv["feed"], dy, ps.g(key + ".o.W"))  # o.b: summed by the LN backward
         dctx = ws.get(tag + ".dctx", (N, c.d))
         ops.linear_dgrad(dy, ps.w(key + ".o.W"), dctx)
         dctx = self._post_bwd(key, dctx, N, sv, tag)
         dq = ws.get(tag + ".dq", (N, c.d))
-        dkv = ws.get(tag + ".dkv", (B * S, 2 * c.d))
+        if not batched:
+            dkv = ws.get(tag + ".dkv", (B * S, 2 * c.d))
         dkv3 = dkv.view(B, S, 2 * c.d)
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), dq.view(B, Lq, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:],
                           delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
         self._wgrad(x, dq, ps.g(key + ".q.W"), ps.g(key + ".q.b"))
-        self._wgrad(enc, dkv, ps.g(key + ".kv.W"), ps.g(key + ".kv.b"))
-        # d_enc (fp32, accumulated over decoder layers) += dkv @ Wkv^T
-        ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
+        if not batched:
+            self._wgrad(enc, dkv, ps.g(key + ".kv.W"), ps.g(key + ".kv.b"))
+            # d_enc (fp32, accumulated over decoder layers) += dkv @ Wkv^T
+            ops.linear_dgrad(dkv, ps.w(key + ".kv.W"), d_enc, accum=True)
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dq, ps.w(key + ".q.W"), dx)
         return dx
@@ -640,13 +664,18 @@ class Engine(object):
         if r_emb > 0.0:   # models/transformer.py:119
             ops.dropout(x, x, r_emb, self.drop_seed, dropout_site("dec.emb"))
         layers = []
+        kv_all = None
+        if c.batch_mem:   # every layer's k_map | v_map of the encoder output in one GEMM (n = ndec * 2d)
+            kv_all = ws.get(tag + ".kv_all", (B * S, c.ndec * 2 * c.d))
+            ops.linear_fwd(enc, ps.w("dec.kvall.W"), ps.p("dec.kvall.b"), kv_all)
         for l in range(c.ndec):
             key, t = "dec%d" % l, "%s.L%d" % (tag, l)
             sv = {"att": {}, "ln1": {}, "cross": {}, "lnc": {}, "ffn": {}, "ln2": {}, "x_in": x}
             # decoder self-attention: causal bias only, no key-padding mask (models/transformer.py:136)
             y = self._self_attn_fwd(key + ".self", x, B, T, None, True, sv["att"], t + ".att")
             x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
-            yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross")
+            yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross",
+                                      kv=None if kv_all is None else kv_all[:, l * 2 * c.d:(l + 1) * 2 * c.d])
             xc = self._ln_fwd(key + ".cross.ln", x1, yc, N, sv["lnc"], t + ".lnc")
             y2 = self._ffn_fwd(key + ".ffn", xc, N, sv["ffn"], t + ".ffn")
             x = self._ln_fwd(key + ".ffn.ln", xc, y2, N, sv["ln2"], t + ".ln2")
@@ -684,6 +713,8 @@ class Engine(object):
         dfeat = ws.get(tag + ".dfeat", (N, c.d))
         ops.cast_f32_bf16(dfeat32, dfeat)
         d1, d2 = dfeat, None
+        batched = c.batch_mem and not (c.aan or c.fuse)
+        dkv_all = ws.get(tag + ".dkv_all", (B * S, c.ndec * 2 * c.d)) if batched else None
         for l in reversed(range(c.ndec)):
             key, bw = "dec%d" % l, "%s.bw%d" % (tag, l & 1)
             sv = save["layers"][l]
@@ -696,12 +727,18 @@ class Engine(object):
                 dsc, dyc = self._ln_bwd(key + ".cross.ln", ds2, dxc, N, sv["lnc"], bw + ".lnc",
                                         ps.g(key + ".cross.o.b"))
                 dx1 = self._cross_attn_bwd(key + ".cross", sv["x1"], enc, dyc, d_enc_f32, B, T, S, sv["cross"],
-                                           bw + ".cross")
+                                           bw + ".cross",
+                                           dkv=None if dkv_all is None else dkv_all[:, l * 2 * c.d:(l + 1) * 2 * c.d])
                 ds1, dy1 = self._ln_bwd(key + ".self.ln", dsc, dx1, N, sv["ln1"], bw + ".ln1",
                                         ps.g(key + ".self.o.b"))
                 dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, T, sv["att"], bw + ".att")
                 d1, d2 = ds1, dx
             self._side_layer_end(tag, l)
+        if batched:
+            # all layers at once: dWkv += enc^T dkv_all (+ bias sums), d_enc += dkv_all Wkv_all^T (k = ndec * 2d)
+            self._wgrad(enc, dkv_all, ps.g("dec.kvall.W"), ps.g("dec.kvall.b"))
+            self._flush_wgrads()
+            ops.linear_dgrad(dkv_all, ps.w("dec.kvall.W"), d_enc_f32, accum=True)
         d1, d2 = self._embed_dropout_bwd(d1, d2, save.get("emb_rate", 0.0), "dec.emb", tag)
         ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
 
