@@ -1,0 +1,110 @@
+"""Dry run of the engine's host-side schedule on the CPU: every kernel entry point of zero_b200.ops is replaced by a
+recorder, buffers live on the CPU, and forward_backward / score / one cached decode step are driven through the
+real Python control flow.  Nothing is computed — what is checked is that the schedule itself is sound for every
+model family and every host-level switch: names resolve, views of the planned buffers have the shapes and strides
+the argument builders (ops.attention_args, ops.gemm_args: the real ones) accept, and the launch sequence is the
+expected one.  The numerics of the same paths are the GPU tests' job (tests/test_model_gpu.py)."""
+import collections
+
+import pytest
+import torch
+
+from zero_b200.params import transformer_base
+
+BUILDERS = ("attention_args", "gemm_args", "wgrad_args", "beam_args")
+
+
+def _mock_ops(monkeypatch):
+    """Replace every launching function of zero_b200.ops by a recorder; returns the list of recorded names."""
+    import zero_b200.ops as ops
+    calls = []
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if callable(fn) and not name.startswith("_") and getattr(fn, "__module__", "") == ops.__name__ \
+                and name not in BUILDERS:
+            monkeypatch.setattr(ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
+    return calls
+
+
+def _engine(**over):
+    import zero_b200.engine as E
+    hp = transformer_base(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=2,
+                          num_decoder_layer=3, **over)
+    eng = E.Engine(hp, 208, 208, device="cpu")
+    eng.ps.init_random(3)
+    return eng
+
+
+def _dry_engine(monkeypatch, **over):
+    calls = _mock_ops(monkeypatch)
+    return _engine(**over), calls
+
+
+def _batch():
+    g = torch.Generator().manual_seed(0)
+    src = torch.randint(3, 208, (4, 9), generator=g)
+    tgt = torch.randint(3, 208, (4, 7), generator=g)
+    src[1, 5:] = 0
+    tgt[2, 4:] = 0
+    return src, tgt
+
+
+FAMILIES = [dict(model_name="transformer", scope_name="transformer"),
+            dict(model_name="transformer_rpr", scope_name="transformer_rpr", max_relative_position=4),
+            dict(model_name="transformer_rela", scope_name="transformer_rela"),
+            dict(model_name="transformer_aan", scope_name="transformer_aan"),
+            dict(model_name="transformer_aan", scope_name="transformer_aan", use_ffn=True, aan_mask=False),
+            dict(model_name="transformer_fuse", scope_name="transformer_fuse")]
+
+
+@pytest.mark.parametrize("family", FAMILIES, ids=lambda f: f["model_name"] + ("+ffn" if f.get("use_ffn") else ""))
+@pytest.mark.parametrize("switch", [None, "ZB_BATCH_MEM_PROJ", "ZB_DECODE_FUSED_SMALL"])
+def test_schedule_runs_for_every_family_and_switch(family, switch, monkeypatch):
+    if switch:
+        monkeypatch.setenv(switch, "1")
+    eng, calls = _dry_engine(monkeypatch, **family)
+    src, tgt = _batch()
+    loss = eng.forward_backward(src, tgt)
+    assert tuple(loss.shape) == (1,)
+    n = collections.Counter(calls)
+    assert n["softmax_ce"] == 1 and n["embed_fwd"] == 2 and n["embed_bwd"] == 2
+    assert n["attention_fwd"] == n["attention_bwd"] > 0
+    score = eng.score(src, tgt)
+    assert tuple(score.shape) == (4,)
+    # one cached decode step per family (beam 2): the per-sentence memories, the per-beam caches / running sums
+    del calls[:]
+    state = eng.encoding_fn(src)
+    state.begin_search(2, cap=12)
+    tok = torch.zeros(8, 1, dtype=torch.int32)
+    for t in range(2):
+        logits, state = eng.decoding_fn(tok, state, t)
+        state.reorder(torch.arange(8, dtype=torch.int32), t)
+    assert tuple(logits.shape) == (8, 208)
+    n = collections.Counter(calls)
+    if switch == "ZB_DECODE_FUSED_SMALL" and family["model_name"] == "transformer_aan" and not family.get("use_ffn"):
+        assert n["aan_cat_step"] == 2 * 3 and n["aan_gate_ln"] == 2 * 3 and n["aan_step"] == 0
+    elif family["model_name"] == "transformer_aan":
+        assert n["aan_step"] == 2 * 3 and n["aan_gate_fwd"] == 2 * 3
+    if switch == "ZB_BATCH_MEM_PROJ":
+        batched = family["model_name"] not in ("transformer_aan", "transformer_fuse")
+        assert eng.cfg.batch_mem == batched and ("dec.kvall.W" in eng.ps.slots) == batched
+
+
+def test_batched_memory_projection_changes_the_launch_count(monkeypatch):
+    """One memory-projection GEMM forward and one dgrad backward for all decoder layers instead of one per layer."""
+    src, tgt = _batch()
+    calls = _mock_ops(monkeypatch)
+    eng0 = _engine()
+    del calls[:]
+    eng0.forward_backward(src, tgt)
+    n0 = collections.Counter(calls)
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "1")
+    eng1 = _engine()
+    del calls[:]
+    eng1.forward_backward(src, tgt)
+    n1 = collections.Counter(calls)
+    ndec = eng1.cfg.ndec
+    assert n0["linear_fwd"] - n1["linear_fwd"] == ndec - 1
+    assert n0["linear_dgrad"] - n1["linear_dgrad"] == ndec - 1
+    assert n0["attention_fwd"] == n1["attention_fwd"]
