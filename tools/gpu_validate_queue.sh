@@ -6,9 +6,14 @@ tag=${1:-queue}
 mkdir -p gpurun_out
 t0=$SECONDS
 timeout 120 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests.log
-t0=$SECONDS
-ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part or gemm_bm64 or fused_small or opt_in_decode or attention_tcgen05 or batched_memory" \
-  > gpurun_out/${tag}_tests_unvalidated.log 2>&1; echo "unvalidated rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests_unvalidated.log
+# one process per group: a kernel that traps (every mbarrier wait is bounded) poisons its CUDA context, not the others
+: > gpurun_out/${tag}_tests_unvalidated.log
+for grp in beam_part gemm_bm64 fused_small opt_in_decode attention_tcgen05 batched_memory; do
+  t0=$SECONDS
+  echo "=== $grp" >> gpurun_out/${tag}_tests_unvalidated.log
+  ZB_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests -m gpu -q -k "$grp" >> gpurun_out/${tag}_tests_unvalidated.log 2>&1
+  echo "=== $grp rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests_unvalidated.log
+done
 {
   timeout 60 python tools/decode_ab.py
   ZB_BEAM_PARTS=1 timeout 60 python tools/decode_ab.py
@@ -17,13 +22,13 @@ ZB_TEST_UNVALIDATED=1 timeout 200 python -m pytest tests -m gpu -q -k "beam_part
   ZB_BEAM_PARTS=1 ZB_GEMM_BM64=1 ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
 } > gpurun_out/${tag}_decode_ab.jsonl 2> gpurun_out/${tag}_decode_ab.err
 # training step with / without the tcgen05 attention forward (only if its parity test passed)
-if grep -q "attention_tcgen05.*PASSED\|passed" gpurun_out/${tag}_tests_unvalidated.log && ! grep -q "FAILED.*attention_tcgen05" gpurun_out/${tag}_tests_unvalidated.log; then
+if grep -q "=== attention_tcgen05 rc=0" gpurun_out/${tag}_tests_unvalidated.log; then
   timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_default.json 2>/dev/null
   ZB_ATTN_TC=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_attn_tc.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_default.json gpurun_out/${tag}_bench_attn_tc.json
 fi
 # batched memory projection: training bench under the switch (its parity test ran above)
-if ! grep -q "FAILED.*batched_memory" gpurun_out/${tag}_tests_unvalidated.log; then
+if grep -q "=== batched_memory rc=0" gpurun_out/${tag}_tests_unvalidated.log; then
   ZB_BATCH_MEM_PROJ=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_batchmem.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_batchmem.json
 fi
@@ -41,7 +46,7 @@ timeout 120 ncu --set full --clock-control none --import-source on -k regex:"add
   > gpurun_out/${tag}_ncu_lnbwd.log 2>&1
 fi
 grep -E "passed|failed|error" gpurun_out/${tag}_tests.log | tail -2
-grep -E "passed|failed|error" gpurun_out/${tag}_tests_unvalidated.log | tail -2; grep -E "^FAILED|^ERROR" gpurun_out/${tag}_tests_unvalidated.log | head -30
+grep -E "^=== .* rc=|passed|failed" gpurun_out/${tag}_tests_unvalidated.log; grep -E "^FAILED|^ERROR" gpurun_out/${tag}_tests_unvalidated.log | head -30
 python - <<PY
 import json
 for l in open("gpurun_out/${tag}_decode_ab.jsonl"):
