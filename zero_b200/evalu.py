@@ -161,5 +161,15 @@ def bleu(cand, refs, bp="closest", smooth=False, n=4, weights=None):
     return lp * math.exp(logsum)
 
 
+def dump_tanslation(tranes, output, indices=None):
+    """evalu.dump_tanslation (evalu.py:269-280, the reference's spelling): one hypothesis (token list) or score per
+    line, restored to corpus order when `indices` are given."""
+    if indices is not None:
+        tranes = [d[1] for d in sorted(zip(indices, tranes), key=lambda x: x[0])]
+    with open(output, "w") as writer:
+        for hypo in tranes:
+            writer.write((" ".join(hypo) if isinstance(hypo, list) else str(hypo)) + "\n")
+
+
 def timer():
     return time.time()

@@ -58,6 +58,22 @@ def _refs(path):
     return [[line.strip().split() for line in open(f)] for f in files]
 
 
+def restore_for_eval(params, log=print):
+    """evaluate / scorer (main.py:503-529, 578-606): restore the latest checkpoint of output_dir into the model's
+    variables, then assign the moving averages when ema_decay > 0.  Without a checkpoint the variables keep their
+    initial values, as tf.global_variables_initializer leaves them in the reference."""
+    from .models.transformer import get_engine
+    eng = get_engine(params)
+    if not getattr(params, "output_dir", ""):
+        return False
+    log("Trying restore existing parameters")
+    ok = saver.Saver(checkpoints=params.checkpoints, output_dir=params.output_dir).restore(
+        eng, use_ema=float(getattr(params, "ema_decay", -1.0)) > 0.0)
+    if ok:
+        log("Restored parameters from %s" % params.output_dir)
+    return ok
+
+
 def run(mode, params, log=print):
     random.seed(params.random_seed)
     np.random.seed(params.random_seed)
@@ -81,13 +97,14 @@ def run(mode, params, log=print):
         refs = _refs(params.tgt_dev_file) if params.tgt_dev_file else None
         return graph.train(params, dataset(params.src_train_file, params.tgt_train_file, params.max_len), dev, refs,
                            log=log)
+    if mode in ("test", "score"):
+        restore_for_eval(params, log)
     if mode == "test":
+        from . import evalu
         test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len)
         res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log)
         if params.test_output:
-            with open(params.test_output, "w") as f:
-                for hyp in res["translations"]:
-                    f.write(" ".join(hyp) + "\n")
+            evalu.dump_tanslation(res["translations"], params.test_output)      # main.py:543
         return res
     if mode == "score":
         from . import evalu
@@ -95,6 +112,8 @@ def run(mode, params, log=print):
         ds = dataset(params.src_test_file, params.tgt_test_file, params.eval_max_len)
         scores, ppl = evalu.scoring(registry.get_model(params.model_name).score_fn, ds, params)
         log("Scores %.4f, PPL %.4f" % (float(np.mean(scores)), ppl))
+        if params.test_output:
+            evalu.dump_tanslation(scores, params.test_output)                   # main.py:619
         return {"scores": scores, "ppl": ppl}
     raise ValueError("Invalid mode: {}".format(mode))
 

@@ -17,6 +17,9 @@ import numpy as np
 import torch
 
 
+EMA_SUFFIX = "/ExponentialMovingAverage"
+
+
 class Recorder(object):
     """utils/recorder.py: attribute bag <-> record.json (the fields of run.py:276-296)."""
 
@@ -91,18 +94,28 @@ class Saver(object):
                 out[k + "/Adam"] = ps.tf_view(ps.adam_m, k).detach().cpu().numpy()
                 out[k + "/Adam_1"] = ps.tf_view(ps.adam_v, k).detach().cpu().numpy()
             out["global_step"] = np.asarray(trainer.global_step, dtype=np.int64)
+        if trainer is not None and getattr(trainer, "ema", None) is not None:
+            # tf.train.ExponentialMovingAverage keeps its shadow variables under this suffix (main.py:214-221)
+            for k in ps.tf_names():
+                out[k + EMA_SUFFIX] = ps.tf_view(trainer.ema, k).detach().float().cpu().numpy()
         return out
 
     @staticmethod
-    def restore_state_dict(engine, arrays, trainer=None, strict=False):
+    def restore_state_dict(engine, arrays, trainer=None, strict=False, use_ema=False):
         """Name-matched restore (utils/saver.py:150-171): variables present under the same name and shape are
-        loaded, the rest keep their values; returns (loaded, skipped) name lists."""
+        loaded, the rest keep their values; returns (loaded, skipped) name lists.  `use_ema`: load the moving
+        averages INTO the parameters where the checkpoint has them — what evaluate / scorer do with ema_assign_op
+        after restoring (main.py:503-529, 578-606)."""
         ps = engine.ps
         loaded, skipped = [], []
         for k in ps.tf_names():
             if k in arrays and tuple(arrays[k].shape) == tuple(ps.tf_view(ps.master, k).shape):
-                ps.tf_view(ps.master, k).copy_(torch.as_tensor(np.asarray(arrays[k])).to(ps.device, torch.float32))
+                src = arrays[k + EMA_SUFFIX] if (use_ema and k + EMA_SUFFIX in arrays) else arrays[k]
+                ps.tf_view(ps.master, k).copy_(torch.as_tensor(np.asarray(src)).to(ps.device, torch.float32))
                 loaded.append(k)
+                if trainer is not None and getattr(trainer, "ema", None) is not None and k + EMA_SUFFIX in arrays:
+                    ps.tf_view(trainer.ema, k).copy_(
+                        torch.as_tensor(np.asarray(arrays[k + EMA_SUFFIX])).to(ps.device, torch.float32))
                 if trainer is not None and k + "/Adam" in arrays and ps.adam_m is not None:
                     ps.tf_view(ps.adam_m, k).copy_(torch.as_tensor(np.asarray(arrays[k + "/Adam"])).to(ps.device))
                     ps.tf_view(ps.adam_v, k).copy_(torch.as_tensor(np.asarray(arrays[k + "/Adam_1"])).to(ps.device))
@@ -149,13 +162,13 @@ class Saver(object):
             return os.path.join(directory, self._meta["best"][0][0]) if self._meta["best"] else None
         return os.path.join(directory, self._meta["all"][-1]) if self._meta["all"] else None
 
-    def restore(self, engine, path=None, trainer=None):
+    def restore(self, engine, path=None, trainer=None, use_ema=False):
         """utils/saver.py:105-148: load `path`, else the latest checkpoint; False when there is none."""
         path = path or self.latest()
         if path is None or not os.path.exists(path):
             return False
         with np.load(path) as z:
-            self.restore_state_dict(engine, {k: z[k] for k in z.files}, trainer)
+            self.restore_state_dict(engine, {k: z[k] for k in z.files}, trainer, use_ema=use_ema)
         return True
 
 
