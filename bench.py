@@ -407,7 +407,11 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "dtype": "bf16", "data": "synthetic",
+        "config": dict(workload_config(world), gradient_step=(
+            "NCCL all-reduce of the fp32 gradient arena (two buckets) + replicated Adam" if trainer.shard is None else
+            "fused reduce-scatter + sharded Adam + bf16 all-gather in one kernel per rank over %s (ZB_SHARD_OPT)" % (
+                "NVSwitch multicast" if trainer.shard.grad_mc else "NVLink peer memory")) if world > 1 else "Adam"),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * B_PER_GPU * 64 * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps},
         "gpu_launches": int(per_step_kernels * args.steps),

@@ -57,7 +57,7 @@ typedef enum {
 } zb_path;
 int64_t zb_path_launch_count(int32_t which);
 /* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,
- * 7 colsum; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
+ * 7 colsum, 8 shard_adam; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
 int64_t zb_abi_struct_size(int32_t which);
 
 /* ------------------------------------------------------------------------------------------------ K1
@@ -242,6 +242,55 @@ typedef struct {
 int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream);
 /* zb_sumsq: out[0] += sum x^2 (tf.global_norm, utils/cycle.py:94). */
 int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ K10
+ * zb_shard_adam: gradient aggregation + optimizer step of ONE rank's shard of the flat arenas in ONE kernel, over
+ * NVLink / NVSwitch peer memory (opt-in; replaces utils/parallel.py:134-208 average_gradients + main.py:42-43 +
+ * the TF Adam of main.py:178-181 when the batch is sharded over the GPUs of one box):
+ *     g[i]  = sum over ranks of grad_r[i]           i in [lo, lo + n)   (reduce-scatter step)
+ *     Adam on param / m / v [lo, lo + n)            (zb_adam_tf semantics, this rank owns the shard)
+ *     mirror_r[i] = bf16(param[i]) on EVERY rank    (all-gather step, bf16: half the bytes of the fp32 gradients)
+ * The sum is taken either inside the NVSwitch (grad_mc != NULL: the multicast address of the symmetric gradient
+ * arena, multimem.ld_reduce — each element crosses this GPU's link once) or in registers from the ranks' unicast
+ * addresses (grad_peer[r], rank order).  The bf16 copy goes out through multimem.st (mirror_mc) or one store per rank.
+ * Every rank runs the call on its own shard; the shards tile the arena.  The caller brackets the call with a
+ * cross-rank barrier on both sides (all gradients final before / all copies landed after); the kernel itself only
+ * ends with a system-scope fence.  Optimizer state outside the shard is not touched (and goes stale on this rank),
+ * except where the forward pass reads the fp32 master directly (biases, LayerNorm scale / offset — every 1-D
+ * variable): wide_mask (optional, one byte per 64-element slot of the arena, non-zero = broadcast) marks the slots
+ * whose refreshed fp32 values are ALSO stored into every rank's master arena (param_mc / param_peer[r]).
+ * flags: ZB_SHARD_UPDATE       Adam + bf16 broadcast (without it nothing but the outputs below is written)
+ *        ZB_SHARD_STORE_GRAD   grad_out[i] = g[i] (local fp32 arena; the two-pass clip_by_global_norm flow)
+ *        ZB_SHARD_NORM_G / _P  norms[0] += sum (g * grad_scale)^2 / norms[1] += sum param^2 (pre-update)
+ * norm_parts_peer (optional): fp32 [world][2] tables, one per rank; the last CTA to finish copies this rank's
+ * norms[0..1] into row `rank` of every table, so after the closing barrier each rank can form tf.global_norm
+ * (utils/cycle.py:94-95) without another collective.  done_counter: device uint32, zero on entry, zero on exit.
+ * lo and n are multiples of 8 elements. */
+#define ZB_SHARD_MAX_WORLD 16
+enum { ZB_SHARD_UPDATE = 1, ZB_SHARD_STORE_GRAD = 2, ZB_SHARD_NORM_G = 4, ZB_SHARD_NORM_P = 8 };
+typedef struct {
+  int64_t lo, n;
+  int32_t world, rank;   /* ranks the bf16 / fp32 copies go to; this rank's index (row of the norm tables) */
+  int32_t grad_sources;  /* gradient copies summed from grad_peer[0 .. grad_sources): `world` for the reduce step,
+                            1 when grad_peer[0] already holds the summed gradients (second pass of the clip flow) */
+  int32_t flags;
+  const float* grad_mc;
+  const float* grad_peer[ZB_SHARD_MAX_WORLD];
+  float* param; float* m; float* v; /* arena bases (element 0), local */
+  const uint8_t* wide_mask;
+  float* param_mc;
+  float* param_peer[ZB_SHARD_MAX_WORLD];
+  void* mirror_mc;
+  void* mirror_peer[ZB_SHARD_MAX_WORLD];
+  float* grad_out;
+  float beta1, beta2, eps;
+  float lr_t, grad_scale;
+  const float* clip_scale;
+  float* norms;
+  float* norm_parts_peer[ZB_SHARD_MAX_WORLD];
+  uint32_t* done_counter;
+} zb_shard_adam_args;
+int zb_shard_adam(const zb_shard_adam_args* a, zb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ K8
  * zb_beam_step: one expansion step of search.beam_search (search.py:115-238) for a whole batch.

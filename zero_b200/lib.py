@@ -78,9 +78,23 @@ class BeamArgs(C.Structure):
                 ("active", vp), ("row_ws", vp)]
 
 
+SHARD_MAX_WORLD = 16
+ZB_SHARD_UPDATE, ZB_SHARD_STORE_GRAD, ZB_SHARD_NORM_G, ZB_SHARD_NORM_P = 1, 2, 4, 8
+
+
+class ShardAdamArgs(C.Structure):
+    _fields_ = [("lo", i64), ("n", i64), ("world", i32), ("rank", i32), ("grad_sources", i32), ("flags", i32),
+                ("grad_mc", vp), ("grad_peer", vp * SHARD_MAX_WORLD),
+                ("param", vp), ("m", vp), ("v", vp),
+                ("wide_mask", vp), ("param_mc", vp), ("param_peer", vp * SHARD_MAX_WORLD),
+                ("mirror_mc", vp), ("mirror_peer", vp * SHARD_MAX_WORLD), ("grad_out", vp),
+                ("beta1", f32), ("beta2", f32), ("eps", f32), ("lr_t", f32), ("grad_scale", f32),
+                ("clip_scale", vp), ("norms", vp), ("norm_parts_peer", vp * SHARD_MAX_WORLD), ("done_counter", vp)]
+
+
 # every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
 # order = the index zb_abi_struct_size() understands
-STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs]
+STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs, ShardAdamArgs]
 
 EXPORTS = [
     "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_path_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
@@ -88,7 +102,7 @@ EXPORTS = [
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
-    "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln",
+    "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam",
 ]
 
 _lib = None
@@ -128,6 +142,7 @@ def load():
         ("zb_cast_f32_bf16", [vp, vp, i64, vp]),
         ("zb_cast_bf16_f32", [vp, vp, i64, vp]),
         ("zb_adam_tf", [C.POINTER(AdamArgs), vp]),
+        ("zb_shard_adam", [C.POINTER(ShardAdamArgs), vp]),
         ("zb_sumsq", [vp, i64, vp, vp]),
         ("zb_beam_cond", [C.POINTER(BeamArgs), vp]),
         ("zb_beam_step", [C.POINTER(BeamArgs), vp]),

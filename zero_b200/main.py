@@ -102,8 +102,10 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                                               data["src"].shape, data["tgt"].shape, cum_tokens, ud))
                 state["tokens_per_sec"].append(cum_tokens / max(ud, 1e-9))
                 cum_tokens, start_time = 0, time.time()
-            if saver is not None and rank == 0 and gstep > 0 and gstep % params.save_freq == 0:
-                saver.save(eng, gstep, trainer=trainer)
+            if saver is not None and gstep > 0 and gstep % params.save_freq == 0:
+                trainer.sync_full_state()                       # every rank (collective when the step is sharded)
+                if rank == 0:
+                    saver.save(eng, gstep, trainer=trainer)
             if dev_dataset is not None and gstep > 0 and gstep % params.eval_freq == 0:
                 trainer.ema_assign()
                 t0 = time.time()
@@ -121,8 +123,10 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                         state["estop"] = True
                 state["history_scores"].append((gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0))
                 state["valid_script_scores"].append((gstep, float(bleu)))
-                if saver is not None and rank == 0:
-                    saver.save(eng, gstep, metric_score=bleu, trainer=trainer)
+                if saver is not None:
+                    trainer.sync_full_state()
+                    if rank == 0:
+                        saver.save(eng, gstep, metric_score=bleu, trainer=trainer)
                 schedule.after_eval(float(bleu))
                 if state["estop"]:
                     break

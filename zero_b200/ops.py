@@ -213,6 +213,37 @@ def adam_tf(param, m, v, grad, param_bf16, beta1, beta2, eps, lr_t, grad_scale, 
     L.check(L.load().zb_adam_tf(C.byref(a), _stream()), "zb_adam_tf")
 
 
+def shard_adam(lo, n, world, rank, grad_ptrs, mirror_ptrs, param, m, v, beta1, beta2, eps, lr_t, grad_scale,
+               flags=L.ZB_SHARD_UPDATE | L.ZB_SHARD_NORM_G | L.ZB_SHARD_NORM_P, grad_mc=0, mirror_mc=0, grad_out=None,
+               clip_scale=None, norms=None, norm_parts_ptrs=None, done_counter=None, wide_mask=None, param_ptrs=None,
+               param_mc=0, grad_sources=None):
+    """Gradient aggregation (utils/parallel.py:134-208, main.py:42-43) + TF Adam (main.py:178-181) + refresh of every
+    rank's bf16 compute copy for the shard [lo, lo + n) of the flat arenas, in one kernel over peer memory.
+    `grad_ptrs` / `mirror_ptrs` / `norm_parts_ptrs`: per-rank device addresses (ints) of the symmetric arenas as
+    mapped in THIS process; `grad_mc` / `mirror_mc`: their multicast addresses (0: use the per-rank addresses).
+    param / m / v: the local fp32 arenas (whole tensors; the kernel indexes them from element 0).  `wide_mask`
+    (uint8 per 64-element slot) marks the 1-D variables whose fp32 values also go to every rank's master arena
+    (`param_ptrs` / `param_mc`): the forward pass reads biases and LayerNorm parameters from the master.
+    `grad_sources` (default: world) entries of `grad_ptrs` are summed; `grad_out` is a tensor or a raw address."""
+    a = L.ShardAdamArgs()
+    a.lo, a.n, a.world, a.rank = int(lo), int(n), int(world), int(rank)
+    a.grad_sources = int(world if grad_sources is None else grad_sources)
+    a.grad_mc = grad_mc or None
+    a.mirror_mc = mirror_mc or None
+    for r in range(world):
+        a.grad_peer[r] = grad_ptrs[r] if grad_ptrs and r < len(grad_ptrs) else None
+        a.mirror_peer[r] = mirror_ptrs[r] if mirror_ptrs else None
+        a.norm_parts_peer[r] = norm_parts_ptrs[r] if norm_parts_ptrs else None
+        a.param_peer[r] = param_ptrs[r] if param_ptrs else None
+    a.wide_mask, a.param_mc = _p(wide_mask), (param_mc or None)
+    a.param, a.m, a.v = _p(param), _p(m), _p(v)
+    a.grad_out = grad_out if isinstance(grad_out, int) else _p(grad_out)
+    a.beta1, a.beta2, a.eps, a.lr_t, a.grad_scale = float(beta1), float(beta2), float(eps), float(lr_t), float(grad_scale)
+    a.flags = int(flags)
+    a.clip_scale, a.norms, a.done_counter = _p(clip_scale), _p(norms), _p(done_counter)
+    L.check(L.load().zb_shard_adam(C.byref(a), _stream()), "zb_shard_adam")
+
+
 def gather_rows(src, index, dst, row_elems=None):
     """dst[r, :row_elems] = src[index[r], :row_elems] over the leading dim (beam state reordering,
     search.py:205-209).  Rows are dst[0].numel() elements apart; only the first row_elems are moved."""

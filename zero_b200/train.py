@@ -13,6 +13,7 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import lib as L
 from . import ops
 from .engine import Engine
 
@@ -34,7 +35,7 @@ class Trainer(object):
     MAX_GRAPHS = 24   # captured (shape, zero_grad) variants kept; further shapes run eagerly
 
     def __init__(self, engine: Engine, hp, world_size=1, use_graph=False, side_stream=True, lr_schedule=None,
-                 early_adam=False):
+                 early_adam=False, shard_transport=None):
         self.eng = engine
         if side_stream:
             engine.enable_side_stream(True)
@@ -58,13 +59,23 @@ class Trainer(object):
         self._graphs = {}
         self._micro = 0
         self._pending = None
+        # opt-in (ZB_SHARD_OPT=1; =p2p: without the multicast mappings): gradient aggregation + Adam + refresh of every
+        # rank's compute copy as ONE kernel per rank over NVLink peer memory (zero_b200/shard_opt.py) instead of the
+        # NCCL all-reduce + replicated Adam below.  safe_nan needs the summed gradients on the host BEFORE the update
+        # (main.py:320-332), which the fused step never materialises: that mode keeps the all-reduce.
+        import os
+        self.shard = None
+        mode = os.environ.get("ZB_SHARD_OPT", "0")
+        if shard_transport is not None or (self.world > 1 and mode in ("1", "p2p")
+                                           and not bool(getattr(hp, "safe_nan", False))):
+            from .shard_opt import ShardedStep, SymmMemTransport
+            self.shard = ShardedStep(engine, shard_transport or SymmMemTransport(), use_multicast=mode != "p2p")
         # exponential moving average of the parameters (utils/cycle.py:114-127), off unless ema_decay > 0
         self.ema_decay = float(getattr(hp, "ema_decay", -1.0))
         self.ema = engine.ps.master.clone() if self.ema_decay > 0.0 else None
         self._ema_backup = None
         # split optimizer step (see _step_split); ZB_EARLY_ADAM=0 keeps the single fused pass after the backward
-        import os
-        self.early_adam = early_adam or os.environ.get("ZB_EARLY_ADAM", "0") == "1"
+        self.early_adam = (early_adam or os.environ.get("ZB_EARLY_ADAM", "0") == "1") and self.shard is None
         self._opt_stream = None
 
     # ------------------------------------------------------------------------------------------ lr
@@ -186,10 +197,11 @@ class Trainer(object):
                 self.loss_acc.zero_()
             self.loss_acc += loss
         works = []
-        if last and self.world > 1:
+        reduce_now = last and self.world > 1 and self.shard is None   # sharded step: the sum is taken in apply()
+        if reduce_now:
             works.append(dist.all_reduce(ps.grad[ps.dec_offset:], op=dist.ReduceOp.SUM, async_op=True))
         phase2()
-        if last and self.world > 1:
+        if reduce_now:
             works.append(dist.all_reduce(ps.grad[:ps.dec_offset], op=dist.ReduceOp.SUM, async_op=True))
             for w in works:
                 w.wait()
@@ -212,6 +224,14 @@ class Trainer(object):
         """clip_by_global_norm + TF Adam on the averaged gradients (utils/cycle.py:94-105) + EMA."""
         ps = self.eng.ps
         self._pending = False
+        if self.shard is not None:
+            lr = self.lr()
+            self.global_step += 1
+            t = self.global_step
+            lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+            self.shard.step(self, lr_t, 1.0 / (self.world * self.cycle * self.loss_scale))
+            self._ema_update()
+            return
         # tf.global_norm of gradients and parameters (utils/cycle.py:94-95): a separate pass only when the clip
         # factor needs the gradient norm before the update; otherwise fused into the Adam kernel
         self.norms.zero_()
@@ -238,13 +258,24 @@ class Trainer(object):
             # tf.train.ExponentialMovingAverage(decay, num_updates=global_step): decay' = min(decay, (1+n)/(10+n))
             n = float(self.global_step)
             d = min(self.ema_decay, (1.0 + n) / (10.0 + n))
-            self.ema.lerp_(self.eng.ps.master, 1.0 - d)
+            if self.shard is not None:   # only the own shard of the master is current
+                lo, hi = self.shard.lo, self.shard.lo + self.shard.n
+                self.ema[lo:hi].lerp_(self.eng.ps.master[lo:hi], 1.0 - d)
+            else:
+                self.ema.lerp_(self.eng.ps.master, 1.0 - d)
+
+    def sync_full_state(self):
+        """Collective, no-op unless the optimizer step is sharded: every rank's fp32 master, Adam slots and EMA shadow
+        become whole again (before a checkpoint is written or the averaged parameters are swapped in)."""
+        if self.shard is not None:
+            self.shard.sync_full_state(extra=() if self.ema is None else (self.ema,))
 
     # ------------------------------------------------------------------------------------------ EMA swap (eval)
     def ema_assign(self):
         """ema_backup_op + ema_assign_op (main.py:368-370): evaluate with the averaged parameters."""
         if self.ema is None:
             return
+        self.sync_full_state()
         ps = self.eng.ps
         self._ema_backup = ps.master.clone()
         ps.master.copy_(self.ema)
@@ -262,10 +293,15 @@ class Trainer(object):
         """GNorm of main.py:336-346 (averaged over towers / cycle, un-scaled).  With before_apply=True the norm of
         the collected, not yet applied gradients is computed by a separate pass (safe_nan mode)."""
         if before_apply:
+            if self.shard is not None:
+                raise L.ZeroB200Error("the sharded optimizer step never materialises the summed gradients")
             tmp = torch.zeros(1, dtype=f32, device=self.eng.device)
             ops.sumsq(self.eng.ps.grad, tmp)
             return float(torch.sqrt(tmp[0]).item()) / (self.world * self.cycle * self.loss_scale)
-        return float(torch.sqrt(self.norms[0]).item())
+        return float(torch.sqrt(self._norms()[0]).item())
 
     def parameter_norm(self):
-        return float(torch.sqrt(self.norms[1]).item())
+        return float(torch.sqrt(self._norms()[1]).item())
+
+    def _norms(self):
+        return self.norms if self.shard is None else self.shard.norms()
