@@ -64,6 +64,12 @@ class SymmMemTransport(object):
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self._handles = []
+        enable = getattr(symm, "enable_symm_mem_for_group", None)
+        if enable is not None:          # a no-op where rendezvous() registers the group itself
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                enable(self.group.group_name)
 
     def alloc(self, n, dtype, device):
         t = self.symm.empty(n, dtype=dtype, device=device)
