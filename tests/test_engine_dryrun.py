@@ -108,3 +108,19 @@ def test_batched_memory_projection_changes_the_launch_count(monkeypatch):
     assert n0["linear_fwd"] - n1["linear_fwd"] == ndec - 1
     assert n0["linear_dgrad"] - n1["linear_dgrad"] == ndec - 1
     assert n0["attention_fwd"] == n1["attention_fwd"]
+
+
+def test_empty_tower_contributes_zero_loss_and_no_launches(monkeypatch):
+    """The reference's zero-shape guard (models/transformer.py:213-216): a tower that receives no sentence returns
+    loss 0; here it also launches nothing and leaves the (zeroed) gradient arena alone."""
+    eng, calls = _dry_engine(monkeypatch, model_name="transformer", scope_name="transformer")
+    eng.ps.grad.fill_(1.0)
+    del calls[:]
+    loss = eng.forward_backward(torch.zeros(0, 5, dtype=torch.int64), torch.zeros(0, 4, dtype=torch.int64))
+    assert tuple(loss.shape) == (1,) and float(loss) == 0.0
+    assert calls == [] and float(eng.ps.grad.abs().sum()) == 0.0
+    assert tuple(eng.score(torch.zeros(0, 5, dtype=torch.int64), torch.zeros(0, 4, dtype=torch.int64)).shape) == (0,)
+    # the next real batch runs the normal schedule again
+    src, tgt = _batch()
+    eng.forward_backward(src, tgt)
+    assert collections.Counter(calls)["softmax_ce"] == 1

@@ -768,6 +768,10 @@ class Engine(object):
         if zero_grad:
             self.ps.zero_grad()
         B, S = source.shape
+        if B == 0 or target.shape[0] == 0:
+            # zero-shape guard (models/transformer.py:213-216): an empty tower contributes loss 0 and no gradients
+            self._pending = None
+            return torch.zeros(1, dtype=f32, device=self.device)
         esave, dsave = {}, {}
         self._training = True     # dropout is part of train_fn only (score_fn / infer_fn close it)
         try:
@@ -786,6 +790,8 @@ class Engine(object):
 
     def backward_encoder(self):
         """Phase 2: backward of the encoder (finalises ps.grad[:ps.dec_offset])."""
+        if self._pending is None:      # empty tower (see forward_backward_decoder)
+            return
         d_enc, esave = self._pending
         self._pending = None
         self.encode_bwd(d_enc, esave)
@@ -802,6 +808,8 @@ class Engine(object):
         """score_fn (models/transformer.py:235-249): label smoothing off, returns per-sentence NLL [B]."""
         source = self._prep_ids(source, self.device)
         target = self._prep_ids(target, self.device)
+        if source.shape[0] == 0:
+            return torch.zeros(0, dtype=f32, device=self.device)
         enc, src_len = self.encode(source)
         return self.decode_train(target, enc, src_len, source.shape[1], 0.0, False)[1]
 

@@ -95,8 +95,9 @@ class Trainer(object):
         eng = self.eng
         eng.advance_dropout_seed()
         key = (tuple(source.shape), tuple(target.shape), bool(zero_grad))
-        entry = self._graphs.get(key) if self.use_graph else None
-        if self.use_graph and entry is None and len(self._graphs) < self.MAX_GRAPHS:
+        graphable = self.use_graph and source.shape[0] > 0      # an empty tower launches nothing (engine guard)
+        entry = self._graphs.get(key) if graphable else None
+        if graphable and entry is None and len(self._graphs) < self.MAX_GRAPHS:
             s_src = torch.empty(source.shape, dtype=torch.int32, device=eng.device)
             s_tgt = torch.empty(target.shape, dtype=torch.int32, device=eng.device)
             s_src.copy_(source)
