@@ -251,7 +251,7 @@ int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t stream);
  *     Adam on param / m / v [lo, lo + n)            (zb_adam_tf semantics, this rank owns the shard)
  *     mirror_r[i] = bf16(param[i]) on EVERY rank    (all-gather step, bf16: half the bytes of the fp32 gradients)
  * The sum is taken either inside the NVSwitch (grad_mc != NULL: the multicast address of the symmetric gradient
- * arena, multimem.ld_reduce — each element crosses this GPU's link once) or in registers from the ranks' unicast
+ * arena, multimem.ld_reduce — the reduced element arrives over this GPU's link once) or in registers from the ranks' unicast
  * addresses (grad_peer[r], rank order).  The bf16 copy goes out through multimem.st (mirror_mc) or one store per rank.
  * Every rank runs the call on its own shard; the shards tile the arena.  The caller brackets the call with a
  * cross-rank barrier on both sides (all gradients final before / all copies landed after); the kernel itself only

@@ -11,8 +11,9 @@ This module replaces both by ONE kernel per rank (`zb_shard_adam`, csrc/shard_op
     shard's master / m / v, and stores the refreshed bf16 compute copy into every rank's mirror arena (multimem.st or
     one store per rank); the 1-D variables, which the forward pass reads in fp32, also go to every rank's master;
   * a cross-rank barrier before (all backwards finished) and after (all copies landed) is the only other
-    communication of the step.  Per rank and step: 4 B/param/N in, 2 B/param/N out on its link, and the Adam pass
-    touches 1/N of the optimizer state (config 2 at N = 8: 2.3 GB -> 0.29 GB of HBM traffic).
+    communication of the step.  Per rank and step the Adam pass touches 1/N of the optimizer state (config 2 at
+    N = 8: 2.3 GB -> 0.29 GB of HBM traffic) and the broadcast leg carries bf16; the gradient arena itself still
+    crosses each GPU's link once on its way to the switch, as in any reduce-scatter.
 
 fp32 master / Adam slots outside the own shard go stale; `sync_full_state()` (a collective: one broadcast per rank
 and arena) makes them whole again before a checkpoint or an EMA swap.
