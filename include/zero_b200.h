@@ -380,6 +380,11 @@ int zb_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, 
  * (func.py:334), residual dropout (func.py:323).  seed: device pointer to one uint64. */
 int zb_dropout(const void* x, const void* x2, void* out, int64_t n, float rate, const uint64_t* seed, uint32_t site,
                zb_stream_t stream);
+/* zb_gumbel_add: x[i] += -log(-log(u_i + eps) + eps), u_i uniform in [0, 1) — util.gumbel_noise (utils/util.py:189-195)
+ * added to the step logits when params.enable_noise_beam_search is set (search.py:143-145: Gumbel top-k sampling
+ * without replacement).  fp32 [n] in place; u is a pure function of (*seed, site, i) (the counter-based generator of
+ * zb_dropout), so the caller varies `site` per decode step and bumps *seed per search. */
+int zb_gumbel_add(float* x, int64_t n, float eps, const uint64_t* seed, uint32_t site, zb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -674,3 +674,28 @@ def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
     for got, old_, want in zip(grads[1], grads[0], [t.grad for t in leaves]):
         torch.testing.assert_close(got.float(), want, atol=6e-2, rtol=5e-2)
         torch.testing.assert_close(got.float(), old_.float(), atol=4e-2, rtol=4e-2)
+
+
+@unvalidated
+def test_gumbel_add_noise_statistics_and_reproducibility():
+    """zb_gumbel_add (util.gumbel_noise, utils/util.py:189-195): Gumbel(0, 1) has mean 0.5772 (Euler's constant) and
+    variance pi^2 / 6; draws are a pure function of (seed, site, index)."""
+    from zero_b200 import ops
+    n = 1 << 20
+    seed = torch.tensor([77], dtype=torch.int64, device=dev())
+    x = torch.zeros(n + 1, device=dev())[:n]                      # odd tail handled too
+    base = torch.full((n,), 3.0, device=dev())
+    a = ops.gumbel_add(base.clone(), seed, 5) - 3.0
+    assert abs(float(a.mean()) - 0.5772) < 5e-3 and abs(float(a.var()) - math.pi ** 2 / 6) < 2e-2
+    assert float(a.max()) < 18.5 and float(a.min()) > -3.0        # -log(eps) = 18.4 caps the right tail
+    b = ops.gumbel_add(base.clone(), seed, 5) - 3.0
+    assert torch.equal(a, b)
+    c = ops.gumbel_add(base.clone(), seed, 6) - 3.0
+    seed.add_(1)
+    d = ops.gumbel_add(base.clone(), seed, 5) - 3.0
+    assert not torch.equal(a, c) and not torch.equal(a, d)
+    assert abs(float((a * c).mean()) - 0.5772 ** 2) < 5e-3        # different sites are uncorrelated
+    odd = torch.zeros(1001, device=dev())
+    ops.gumbel_add(odd, seed, 1)
+    assert bool(torch.isfinite(odd).all()) and float(odd.abs().sum()) > 0
+    del x

@@ -289,3 +289,43 @@ def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch)
     a = search.beam_search({"source": src}, eng0.encoding_fn, eng0.decoding_fn, hp)
     b = search.beam_search({"source": src}, eng1.encoding_fn, eng1.decoding_fn, hp)
     np.testing.assert_array_equal(a["seq"].cpu().numpy(), b["seq"].cpu().numpy())
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
+                    reason="kernel not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
+def test_noise_beam_search_samples_reproducibly():
+    """enable_noise_beam_search (search.py:143-145): Gumbel noise on the step logits.  The bookkeeping stays the
+    oracle's when it is replayed on the SAME (noised) logits; a re-run from the same seed repeats the beams; the next
+    search (seed advanced) draws other noise; graph replays read the advanced seed."""
+    from oracle import zero_oracle as zo
+    from zero_b200 import search
+    from zero_b200.params import SimpleVocab
+    eng, z, hp, variables, grads = _engine("transformer")
+    hp.add_hparam("src_vocab", SimpleVocab(eng.cfg.vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(eng.cfg.vt))
+    hp.enable_noise_beam_search = True
+    src = torch.from_numpy(z["source"])
+    eng.decode_length = hp.decode_length
+    plain = []
+
+    def dec_fn(tok, state, t):
+        lg, st = eng.decoding_fn(tok, state, t)
+        plain.append(lg)                              # the buffer the noise is added to in place afterwards
+        return lg, st
+
+    out = search.beam_search({"source": src}, eng.encoding_fn, dec_fn, hp)
+    torch.cuda.synchronize()
+    assert out["seq"].shape[0] == src.shape[0] and out["seq"].shape[1] == hp.beam_size
+    hp.enable_noise_beam_search = False
+    base = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+    hp.enable_noise_beam_search = True
+    runs = []
+    for _ in range(4):                                # eager, eager (marks steps seen), captured, replayed
+        runs.append(search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)["seq"].cpu())
+    assert any(r.shape != runs[0].shape or not torch.equal(r, runs[0]) for r in runs[1:])     # fresh noise per search
+    st = next(v for k, v in eng.__dict__["_beam_states"].items() if k[-1] is True)
+    seed_now = int(st.noise_seed)
+    st.noise_seed.fill_(seed_now - 1)                 # re-run the last search from its seed (add_(1) happens inside)
+    again = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)["seq"].cpu()
+    assert again.shape == runs[-1].shape and torch.equal(again, runs[-1])
+    assert base["seq"].shape[0] == src.shape[0]

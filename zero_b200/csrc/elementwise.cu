@@ -210,6 +210,25 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   }
 }
 
+// util.gumbel_noise (utils/util.py:189-195) added to the step logits (search.py:143-145): x += -log(-log(u + eps) + eps),
+// u uniform in [0, 1) with 24 random bits per element, a pure function of (*seed, site, element index) like the dropout
+// masks (one splitmix64 hash per two elements), so a replayed decode graph draws fresh noise when the host bumps *seed.
+__global__ void __launch_bounds__(256)
+gumbel_add_kernel(float* __restrict__ x, long long n, float eps, const unsigned long long* __restrict__ seed_p,
+                  uint32_t site) {
+  grid_dep_wait();
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i0 >= n) return;
+  const uint64_t h = dropout_hash4(*seed_p, site ^ 0x6A09E667u, (uint64_t)(i0 >> 1));
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (i0 + e < n) {
+      const float u = (float)((uint32_t)(h >> (32 * e)) >> 8) * (1.f / 16777216.f);
+      x[i0 + e] += -logf(-logf(u + eps) + eps);
+    }
+  }
+}
+
 // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) (host, passed in scalars[0]);
 // m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2; p <- p - lr_t * m / (sqrt(v) + eps).
 __global__ void __launch_bounds__(256)
@@ -466,6 +485,13 @@ extern "C" int zb_sumsq(const float* x, int64_t n, float* out, zb_stream_t strea
   if (blocks > 4ll * num_sms()) blocks = 4ll * num_sms();
   ZB_LAUNCH(sumsq_kernel, (unsigned)blocks, 256, 0, ST(stream), x, n, out);
   return check_launch("zb_sumsq");
+}
+extern "C" int zb_gumbel_add(float* x, int64_t n, float eps, const uint64_t* seed, uint32_t site, zb_stream_t stream) {
+  ZB_REQUIRE(x && seed && n >= 0 && eps > 0.f, "zb_gumbel_add: bad args");
+  if (n == 0) return ZB_OK;
+  ZB_LAUNCH(gumbel_add_kernel, (unsigned)((n + 511) / 512), 256, 0, ST(stream), x, (long long)n, eps,
+            reinterpret_cast<const unsigned long long*>(seed), site);
+  return check_launch("zb_gumbel_add");
 }
 extern "C" int zb_adam_tf(const zb_adam_args* a, zb_stream_t stream) {
   ZB_REQUIRE(a && a->param && a->m && a->v && a->grad && a->n >= 0, "zb_adam_tf: bad args");

@@ -102,7 +102,7 @@ EXPORTS = [
     "zb_colsum", "zb_cast_f32_bf16", "zb_cast_bf16_f32", "zb_adam_tf", "zb_sumsq", "zb_beam_cond",
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
-    "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam",
+    "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam", "zb_gumbel_add",
 ]
 
 _lib = None
@@ -158,6 +158,7 @@ def load():
         ("zb_gated_rms_bwd", [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]),
         ("zb_add2d", [vp, i64, vp, i64, vp, i64, i64, i64, vp]),
         ("zb_dropout", [vp, vp, vp, i64, f32, vp, C.c_uint32, vp]),
+        ("zb_gumbel_add", [vp, i64, f32, vp, C.c_uint32, vp]),
     ]:
         fn = getattr(lib, name)
         fn.argtypes = argt

@@ -134,6 +134,14 @@ def dropout(x, out, rate, seed, site, x2=None):
     return out
 
 
+def gumbel_add(logits, seed, site, eps=1e-8):
+    """logits += util.gumbel_noise(shape) (utils/util.py:189-195; search.py:143-145).  fp32, contiguous, in place."""
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    L.check(L.load().zb_gumbel_add(_p(logits), logits.numel(), float(eps), _p(seed), int(site), _stream()),
+            "zb_gumbel_add")
+    return logits
+
+
 def attention_fwd(a):
     """func.dot_attention core (func.py:218-256)."""
     L.check(L.load().zb_attention_fwd(C.byref(a), _stream()), "zb_attention_fwd")

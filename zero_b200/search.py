@@ -52,6 +52,7 @@ class BeamState(object):
         self.row_ws = None if os.environ.get("ZB_BEAM_ROWS", "1") == "0" else \
             torch.zeros(batch * (4 * beam * beam + 1), dtype=f32, device=device)
         self.tok_buf = torch.zeros(batch * beam, 1, dtype=i32, device=device)
+        self.noise_seed = torch.zeros(1, dtype=torch.int64, device=device)   # zb_gumbel_add (noise beam search)
         self._host_flag, self._flag_events = None, None
         init_logp = torch.full((batch, beam), F32_MIN, dtype=f32)
         init_logp[:, 0] = 0.0
@@ -136,10 +137,10 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     """Drop-in for reference search.beam_search (search.py:19).  `encoding_fn(source) -> state`,
     `decoding_fn(target [B*beam,1], state, time) -> (logits fp32 [B*beam,V], state)` as returned by
     zero_b200's infer_fn; `state.reorder(parent)` replaces the gather_nd over the tiled state."""
-    if bool(getattr(params, "enable_noise_beam_search", False)):
-        # search.py:144-145 adds tf.random_uniform Gumbel noise to the logits: a sampling mode, not reproducible
-        # across frameworks and outside the parity-checked path
-        raise NotImplementedError("enable_noise_beam_search (Gumbel top-k sampling) is not on the CUDA path")
+    # search.py:143-145: Gumbel noise on the step logits turns the beam into top-k sampling without replacement.  The
+    # draws come from the library's counter-based generator (seeded from random_seed, advanced per search), so runs
+    # are reproducible here but — like any sampler — not draw-for-draw comparable with TF's tf.random_uniform.
+    noise = bool(getattr(params, "enable_noise_beam_search", False))
     source = features["source"]
     state = encoding_fn(source)
     eng = state.engine
@@ -148,7 +149,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     B = src.shape[0]
     K = int(params.beam_size)
     cap = int(src.shape[1]) + int(params.decode_length) + 2
-    key = (B, K, state.vocab, cap, float(params.decode_alpha), int(params.decode_length))
+    key = (B, K, state.vocab, cap, float(params.decode_alpha), int(params.decode_length), noise)
     cache = eng.__dict__.setdefault("_beam_states", {})
     st = cache.get(key)
     if st is None:
@@ -156,8 +157,11 @@ def beam_search(features, encoding_fn, decoding_fn, params):
                        getattr(params, "beam_search_temperature", 1.0), getattr(params, "dtype_inf", 1e8), dev,
                        eos_id=params.tgt_vocab.eos(), pad_id=params.tgt_vocab.pad(), cap=cap)
         cache[key] = st
+        st.noise_seed.fill_(int(getattr(params, "random_seed", 1234)))
     else:
         st.reset(src)
+    if noise:
+        st.noise_seed.add_(1)          # a device-side value: replayed step graphs read the new seed
     state.begin_search(K, cap)
     # CUDA-graph replay is only valid for the engine's own decoding_fn (a wrapped one may have side effects)
     own = getattr(decoding_fn, "__self__", None) is eng and getattr(decoding_fn, "__func__", None) is type(eng).decoding_fn
@@ -168,6 +172,8 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     def run_step(t):
         nonlocal state
         logits, state = decoding_fn(st.last_tokens(t), state, t)
+        if noise:
+            ops.gumbel_add(logits, st.noise_seed, t, eps=float(getattr(params, "dtype_epsilon", 1e-8)))
         parent = st.step(logits, t)
         state.reorder(parent, t)
 
