@@ -124,3 +124,34 @@ def test_empty_tower_contributes_zero_loss_and_no_launches(monkeypatch):
     src, tgt = _batch()
     eng.forward_backward(src, tgt)
     assert collections.Counter(calls)["softmax_ce"] == 1
+
+
+@pytest.mark.parametrize("family", [FAMILIES[0], FAMILIES[3]], ids=["transformer", "transformer_aan"])
+def test_vocabulary_sizes_need_not_be_multiples_of_8(family, monkeypatch):
+    """Real vocabularies are 3 specials + N words.  Logit rows get a pitch rounded up to 8 elements (TMA), the kernels
+    see n = V columns (real argument builders: strided views accepted), decoding_fn still returns dense [rows, V]."""
+    import zero_b200.engine as E
+    import zero_b200.ops as ops
+    calls = _mock_ops(monkeypatch)
+    seen = []
+    real = ops.gemm_args
+    monkeypatch.setattr(ops, "gemm", lambda *a, **k: seen.append(real(*a, **k)))
+    hp = transformer_base(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=1,
+                          num_decoder_layer=1, **family)
+    eng = E.Engine(hp, 203, 205, device="cpu")
+    eng.ps.init_random(3)
+    assert eng.cfg.vt == 205 and eng.cfg.vt_pitch == 208
+    src, tgt = _batch()
+    src, tgt = src.clamp(max=202), tgt.clamp(max=204)
+    eng.forward_backward(src, tgt)
+    vocab_gemms = [a for a in seen if 205 in (a.m, a.n, a.k)]
+    assert len(vocab_gemms) == 3                                   # logits, dE (m = V), dfeat (k = V)
+    fwd = next(a for a in vocab_gemms if a.n == 205)
+    assert fwd.ldd == 208 and fwd.k == 128
+    assert any(a.k == 205 and a.lda == 208 for a in vocab_gemms)   # d_logits read with its padded pitch
+    assert any(a.m == 205 and a.lda == 208 for a in vocab_gemms)
+    state = eng.encoding_fn(src)
+    state.begin_search(2, cap=12)
+    logits, state = eng.decoding_fn(torch.zeros(8, 1, dtype=torch.int32), state, 0)
+    assert tuple(logits.shape) == (8, 205) and logits.is_contiguous()
+    assert tuple(eng.score(src, tgt).shape) == (4,)

@@ -329,3 +329,67 @@ def test_noise_beam_search_samples_reproducibly():
     again = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)["seq"].cpu()
     assert again.shape == runs[-1].shape and torch.equal(again, runs[-1])
     assert base["seq"].shape[0] == src.shape[0]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
+                    reason="path not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("model", ["transformer", "transformer_aan"])
+def test_vocabulary_size_not_a_multiple_of_8_matches_oracle(model):
+    """Vocabularies of 203 / 205 words (3 specials + N): loss, logits, every gradient and the per-sentence scores
+    against the oracle on the same weights; beam search bit-exact when the oracle replays the same step logits."""
+    from oracle import zero_oracle as zo
+    from zero_b200 import search
+    from zero_b200.engine import Engine
+    from zero_b200.params import SimpleVocab, transformer_base
+    hp = transformer_base(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=2,
+                          num_decoder_layer=2, model_name=model, scope_name=model, decode_length=6, beam_size=3)
+    vs, vt = 203, 205
+    eng = Engine(hp, vs, vt)
+    eng.ps.init_random(21)
+    c = zo.Cfg(hp, vs, vt)
+    P = {k: v.clone().requires_grad_(True) for k, v in eng.ps.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    src = torch.randint(3, vs, (5, 9), generator=g)
+    tgt = torch.randint(3, vt, (5, 7), generator=g)
+    src[1, 6:] = 0
+    tgt[3, 4:] = 0
+    tgt[:, -1] = torch.where(tgt[:, -1] != 0, torch.full_like(tgt[:, -1], 2), tgt[:, -1])
+    tgt[0, 2] = vt - 1                                             # the last word of the vocabulary is a real class
+    loss = eng.forward_backward(src, tgt)
+    torch.cuda.synchronize()
+    want_loss, want_logits, want_ps, _ = zo.train_loss(c, P, src, tgt)
+    assert abs(float(loss[0]) - float(want_loss)) < 2e-2
+    _, per_sample, logits = eng.train_loss(src, tgt)
+    assert tuple(logits.shape) == (5 * 7, vt)
+    scale = max(1.0, float(want_logits.abs().max()))
+    assert float((logits.cpu() - want_logits.detach().reshape(-1, vt)).abs().max()) <= 4e-2 * scale
+    grads = torch.autograd.grad(want_loss, [P[k] for k in sorted(P)], allow_unused=True)
+    got = eng.ps.grad_dict()
+    for k, gr in zip(sorted(P), grads):
+        if gr is None or float(gr.abs().max()) < 1e-6:
+            continue
+        cos = torch.nn.functional.cosine_similarity(got[k].double().flatten(), gr.double().flatten(), dim=0)
+        assert cos > 0.98, "%s: cosine %.4f" % (k, float(cos))
+    np.testing.assert_allclose(eng.score(src, tgt).cpu().numpy(), zo.score(c, P, src, tgt).detach().numpy(),
+                               atol=3e-2, rtol=1e-2)
+    hp.add_hparam("src_vocab", SimpleVocab(vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(vt))
+    eng.decode_length = hp.decode_length
+    recorded = []
+
+    def dec_fn(tok, state, t):
+        lg, st = eng.decoding_fn(tok, state, t)
+        assert lg.is_contiguous() and tuple(lg.shape) == (5 * 3, vt)
+        recorded.append(lg.detach().float().cpu().clone())
+        return lg, st
+
+    out = search.beam_search({"source": src}, eng.encoding_fn, dec_fn, hp)
+    calls = {"n": 0}
+
+    def dec_replay(tok, state, time):
+        i = max(calls["n"] - 1, 0)
+        calls["n"] += 1
+        return recorded[min(i, len(recorded) - 1)], {"dummy": state["dummy"], "decoder": {"state": {}}}
+
+    want = zo.beam_search(c, src, lambda s: {"dummy": torch.zeros(s.shape[0], 1)}, dec_replay)
+    np.testing.assert_array_equal(out["seq"].cpu().numpy(), want["seq"].numpy())

@@ -92,3 +92,52 @@ def test_dump_tanslation_orders_by_corpus_index(tmp_path):
     assert out.read_text() == "a\n0.5\nb c\n"
     evalu.dump_tanslation([["x", "y"], []], str(out))
     assert out.read_text() == "x y\n\n"
+
+
+def test_score_mode_restores_the_averaged_checkpoint_and_dumps_scores(tmp_path, monkeypatch):
+    """run.py --mode score (main.scorer, main.py:548-621): vocabularies, dataset, restore of output_dir's latest
+    checkpoint with the moving averages assigned (ema_decay > 0), one score per corpus line written to test_output.
+    Host glue only: every launching function of zero_b200.ops is a no-op here, so the scores themselves are
+    whatever the planned buffer holds — their parity is tests/test_model_gpu.py's job."""
+    import zero_b200.engine as E
+    import zero_b200.ops as ops
+    from zero_b200 import run
+    from zero_b200.models import transformer as plugins
+    from zero_b200.train import Trainer
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if callable(fn) and not name.startswith("_") and getattr(fn, "__module__", "") == ops.__name__ \
+                and name not in ("attention_args", "gemm_args", "wgrad_args", "beam_args", "cast_f32_bf16"):
+            monkeypatch.setattr(ops, name, lambda *a, **k: None)
+    words = ["w%d" % i for i in range(30)]
+    (tmp_path / "vocab.txt").write_text("\n".join(words) + "\n")
+    src_lines = ["w1 w2 w3", "w4 w5", "w6 w7 w8 w9", "w2", "w10 w11 w12"]
+    tgt_lines = ["w3 w2 w1", "w5 w4", "w9 w8", "w2 w2", "w12"]
+    (tmp_path / "test.src").write_text("\n".join(src_lines) + "\n")
+    (tmp_path / "test.tgt").write_text("\n".join(tgt_lines) + "\n")
+    out_dir = tmp_path / "model"
+    params = run.build_params(parameters=(
+        "model_name=transformer,scope_name=transformer,hidden_size=64,embed_size=64,filter_size=128,num_heads=2,"
+        "num_encoder_layer=1,num_decoder_layer=1,ema_decay=0.99,eval_batch_size=2,output_dir=%s,test_output=%s,"
+        "src_vocab_file=%s,tgt_vocab_file=%s,src_test_file=%s,tgt_test_file=%s" % (
+            out_dir, tmp_path / "scores.txt", tmp_path / "vocab.txt", tmp_path / "vocab.txt",
+            tmp_path / "test.src", tmp_path / "test.tgt")))
+    # a "trained" checkpoint whose moving averages differ from its raw parameters
+    trained = E.Engine(params, 33, 33, device="cpu")
+    trained.ps.init_random(11)
+    tr = Trainer(trained, params, use_graph=False, side_stream=False)
+    tr.ema.copy_(trained.ps.master * 0.5)
+    Saver(output_dir=str(out_dir)).save(trained, 3, trainer=tr)
+    # the engine the plugins will find for these parameters (Engine(params) itself would ask for a CUDA device)
+    fresh = E.Engine(params, 33, 33, device="cpu")
+    fresh.ps.init_random(12)
+    plugins.reset_engines()
+    monkeypatch.setitem(plugins._engines, (params.scope_name, "transformer"), fresh)
+    logs = []
+    res = run.run("score", params, log=logs.append)
+    plugins.reset_engines()
+    assert torch.equal(fresh.ps.master, tr.ema)                      # ema_assign_op after the restore
+    assert any("Restored parameters" in m for m in logs) and any(m.startswith("Scores") for m in logs)
+    lines = (tmp_path / "scores.txt").read_text().splitlines()
+    assert len(lines) == len(src_lines) == len(res["scores"])
+    assert [float(x) for x in lines] == pytest.approx(res["scores"], nan_ok=True)

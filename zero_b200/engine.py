@@ -66,8 +66,11 @@ class ModelConfig(object):
             raise L.ZeroB200Error("embed_size must equal hidden_size on the Transformer path")
         if self.d % self.h or (self.d // self.h) not in (16, 32, 64):
             raise L.ZeroB200Error("head size %d unsupported (16/32/64)" % (self.d // max(self.h, 1)))
-        if self.d % 8 or self.f % 8 or self.vs % 8 or self.vt % 8:
-            raise L.ZeroB200Error("hidden/filter/vocab sizes must be multiples of 8 (16-byte TMA pitch)")
+        if self.d % 8 or self.f % 8:
+            raise L.ZeroB200Error("hidden/filter sizes must be multiples of 8 (16-byte TMA pitch)")
+        # any vocabulary size (real vocabularies are 3 specials + N words): [rows, V] logits / d_logits rows are laid
+        # out with a pitch rounded up to 8 elements, the kernels see n = V columns of it
+        self.vt_pitch = (self.vt + 7) // 8 * 8
         known = ("transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse")
         if self.model not in known:
             raise L.ZeroB200Error("model %r is outside the hot path (supported: %s)" % (self.model, ", ".join(known)))
@@ -683,12 +686,12 @@ class Engine(object):
             layers.append(sv)
         feat = x
         table = ps.w(self._softmax_table())
-        logits = ws.get(tag + ".logits", (N, c.vt), f32)
+        logits = self._vocab_rows(tag + ".logits", N, f32)
         ops.gemm(feat, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)  # feature @ E^T, cast fp32 (transformer.py:194-196)
         nll = ws.get(tag + ".nll", (N,), f32)
         per_sample = ws.get(tag + ".per_sample", (B,), f32)
         loss = ws.get(tag + ".loss", (1,), f32)
-        dlogits = ws.get(tag + ".dlogits", (N, c.vt)) if want_grad else None
+        dlogits = self._vocab_rows(tag + ".dlogits", N) if want_grad else None
         ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
                        loss_scale=c.loss_scale)
         if save is not None:
@@ -743,6 +746,22 @@ class Engine(object):
         ops.embed_bwd(save["target"], d1, ps.g(self._tgt_table()), ps.g("emb_bias"), mult=c.d ** 0.5, shift=1, d_out2=d2)
 
     # ================================================================================== public steps
+    def _vocab_rows(self, tag, rows, dtype=bf16):
+        """[rows, V] buffer over the target vocabulary; its row pitch is a multiple of 8 elements (TMA), so for a
+        vocabulary size that is not it is a strided view of a slightly wider buffer."""
+        c = self.cfg
+        buf = self.ws.get(tag, (rows, c.vt_pitch), dtype)
+        return buf if c.vt_pitch == c.vt else buf[:, :c.vt]
+
+    def _dense_logits(self, logits):
+        """decoding_fn hands out contiguous fp32 [rows, V] (models/transformer.py:267-283; zb_beam_step indexes it
+        densely): a plain copy when the pitch had to be padded."""
+        if logits.is_contiguous():
+            return logits
+        dense = self.ws.get("dec.logits_dense", tuple(logits.shape), f32)
+        dense.copy_(logits)
+        return dense
+
     @staticmethod
     def _prep_ids(ids, device, compact=True):
         ids = torch.as_tensor(ids)
@@ -920,9 +939,9 @@ def _engine_decoding_fn(self, target, state, time):
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
         ops.linear_fwd(h, ps.w(key + ".ffn.w2.W"), ps.p(key + ".ffn.w2.b"), y)
         ops.add_ln_fwd(xc, y, x, ps.p(key + ".ffn.ln.scale"), ps.p(key + ".ffn.ln.offset"), eps=c.eps)
-    logits = ws.get("dec.logits", (R, c.vt), f32)
+    logits = self._vocab_rows("dec.logits", R, f32)
     ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
-    return logits, state
+    return self._dense_logits(logits), state
 
 
 def _engine_post_attn(self, key, ctx, rows):

@@ -100,12 +100,12 @@ def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=Non
         sv["xc"] = xc
         layers.append(sv)
     feat = x
-    logits = ws.get(tag + ".logits", (N, c.vt), f32)
+    logits = self._vocab_rows(tag + ".logits", N, f32)
     ops.gemm(feat, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
     nll = ws.get(tag + ".nll", (N,), f32)
     per_sample = ws.get(tag + ".per_sample", (B,), f32)
     loss = ws.get(tag + ".loss", (1,), f32)
-    dlogits = ws.get(tag + ".dlogits", (N, c.vt)) if want_grad else None
+    dlogits = self._vocab_rows(tag + ".dlogits", N) if want_grad else None
     ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
                    loss_scale=c.loss_scale)
     if save is not None:
@@ -251,9 +251,9 @@ def _decoding_fn_avg(self, target, state, time):
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
         ops.linear_fwd(h, ps.w(key + ".ffn.w2.W"), ps.p(key + ".ffn.w2.b"), y)
         ops.add_ln_fwd(xc, y, x, ps.p(key + ".ffn.ln.scale"), ps.p(key + ".ffn.ln.offset"), eps=c.eps)
-    logits = ws.get("dec.logits", (R, c.vt), f32)
+    logits = self._vocab_rows("dec.logits", R, f32)
     ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
-    return logits, state
+    return self._dense_logits(logits), state
 
 
 # ---- DecodeState: running sums instead of K/V caches
