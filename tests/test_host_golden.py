@@ -86,6 +86,12 @@ def test_shard_for_rank_takes_every_nth_batch():
     assert list(shard_for_rank(range(7), 2, 1)) == [1, 3, 5]
 
 
+def test_distributed_env_reads_the_torchrun_variables():
+    from zero_b200 import run
+    assert run.distributed_env({}) == (1, 0, 0)
+    assert run.distributed_env({"WORLD_SIZE": "8", "RANK": "5", "LOCAL_RANK": "5"}) == (8, 5, 5)
+
+
 def test_run_parameter_precedence_and_param_json(tmp_path):
     """run.py:367-376: command line > saved param.json > --config file > defaults; param.json round trip."""
     from zero_b200 import run, saver

@@ -74,9 +74,33 @@ def restore_for_eval(params, log=print):
     return ok
 
 
+def distributed_env(environ=None):
+    """(world_size, rank, local_rank) of this process.  The reference replicates the graph over `params.gpus` inside
+    one process (utils/parallel.py:79-118); here every GPU is its own process, started by
+    `python -m torch.distributed.run --nproc-per-node N -m zero_b200.run ...`, which exports these variables."""
+    env = os.environ if environ is None else environ
+    return int(env.get("WORLD_SIZE", "1")), int(env.get("RANK", "0")), int(env.get("LOCAL_RANK", "0"))
+
+
+def init_distributed(log=print):
+    """One rank per GPU of one box, NCCL over NVLink; a no-op for a single process."""
+    world, rank, local = distributed_env()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        log("Rank %d of %d on cuda:%d" % (rank, world, local))
+    return world, rank
+
+
 def run(mode, params, log=print):
     random.seed(params.random_seed)
     np.random.seed(params.random_seed)
+    world, rank = init_distributed(log)
+    if rank != 0:
+        log = lambda *a, **k: None      # noqa: E731 — the reference has one process, hence one log
     t0 = time.time()
     for key, f in (("src_vocab", params.src_vocab_file), ("tgt_vocab", params.tgt_vocab_file)):
         if key in params:
@@ -91,19 +115,20 @@ def run(mode, params, log=print):
                        params.data_leak_ratio)
 
     if mode == "train":
-        saver.save_parameters(params, params.output_dir)
+        if rank == 0:
+            saver.save_parameters(params, params.output_dir)
         params = saver.setup_recorder(params)
         dev = dataset(params.src_dev_file, params.src_dev_file, params.eval_max_len) if params.src_dev_file else None
         refs = _refs(params.tgt_dev_file) if params.tgt_dev_file else None
         return graph.train(params, dataset(params.src_train_file, params.tgt_train_file, params.max_len), dev, refs,
-                           log=log)
+                           world_size=world, rank=rank, log=log)
     if mode in ("test", "score"):
         restore_for_eval(params, log)
     if mode == "test":
         from . import evalu
         test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len)
         res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log)
-        if params.test_output:
+        if params.test_output and rank == 0:
             evalu.dump_tanslation(res["translations"], params.test_output)      # main.py:543
         return res
     if mode == "score":
@@ -112,7 +137,7 @@ def run(mode, params, log=print):
         ds = dataset(params.src_test_file, params.tgt_test_file, params.eval_max_len)
         scores, ppl = evalu.scoring(registry.get_model(params.model_name).score_fn, ds, params)
         log("Scores %.4f, PPL %.4f" % (float(np.mean(scores)), ppl))
-        if params.test_output:
+        if params.test_output and rank == 0:
             evalu.dump_tanslation(scores, params.test_output)                   # main.py:619
         return {"scores": scores, "ppl": ppl}
     raise ValueError("Invalid mode: {}".format(mode))
