@@ -685,6 +685,8 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
     const long long w128 = (tiles_for(128) + pairs_hw - 1) / pairs_hw * 128;
     if (w128 < w256) bn = 128;
   }
+  static const char* force_bn = getenv("ZB_GEMM2_BN");   // calibration: 128 / 256 for every problem wide enough
+  if (force_bn && a->n > 128) bn = atoi(force_bn) == 128 ? 128 : 256;
   Gemm2Group<1> G;
   Gemm2Params& p = G.prob[0];
   int rc = setup_problem(a, bn, p, G.maps);
