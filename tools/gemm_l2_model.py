@@ -7,6 +7,7 @@ tile shape fixes an upper bound on the GEMM rate independent of the tensor pipe:
 
     python tools/gemm_l2_model.py            # the step's 201 GEMM problems under the current tile choice
     python tools/gemm_l2_model.py 256        # ... with 256-wide tiles forced (ZB_GEMM2_BN=256)
+    python tools/gemm_l2_model.py l2         # ... with the byte-weighted wave rule (ZB_GEMM2_TILE_MODEL=l2)
 """
 import sys
 
@@ -17,14 +18,18 @@ def tiles(m, n, bn):
     return -(-m // 256) * -(-n // bn)
 
 
-def choose_bn(m, n, force=None):
-    """gemm2_launch's wave-quantisation rule (csrc/gemm2_tcgen05.cu)."""
+def choose_bn(m, n, force=None, accum=False):
+    """gemm2_launch's wave-quantisation rule (csrc/gemm2_tcgen05.cu); force = 128 / 256 (ZB_GEMM2_BN) or "l2"
+    (ZB_GEMM2_TILE_MODEL=l2: a wave costs its operand bytes, 256 + bn, instead of its flops)."""
     if n <= 128:
         return 128
-    if force:
+    if force in (128, 256):
         return force
-    w256 = -(-tiles(m, n, 256) // PAIRS) * 256
-    w128 = -(-tiles(m, n, 128) // PAIRS) * 128
+    if accum:          # weight gradients: split-K fills the machine, the widest tile is kept
+        return 256
+    c256, c128 = (512, 384) if force == "l2" else (256, 128)
+    w256 = -(-tiles(m, n, 256) // PAIRS) * c256
+    w128 = -(-tiles(m, n, 128) // PAIRS) * c128
     return 128 if w128 < w256 else 256
 
 
@@ -34,15 +39,16 @@ def step_problems(T=4096, d=512, f=2048, V=32000):
     out = []
     for _ in range(6):
         for fw in (enc, dec):
-            out += fw + [(m, k, n) for m, n, k in fw] + [(k, n, m) for m, n, k in fw]     # fwd, dgrad, wgrad
-    return out + [(T, V, d), (T, d, V), (V, d, T)]
+            out += [p + (False,) for p in fw] + [(m, k, n, False) for m, n, k in fw]      # forward, dgrad
+            out += [(k, n, m, True) for m, n, k in fw]                                   # wgrad (accumulating)
+    return out + [(T, V, d, False), (T, d, V, True), (V, d, T, True)]
 
 
 def main():
-    force = int(sys.argv[1]) if len(sys.argv) > 1 else None
+    force = (sys.argv[1] if sys.argv[1] == "l2" else int(sys.argv[1])) if len(sys.argv) > 1 else None
     rows = {}
-    for m, n, k in step_problems():
-        bn = choose_bn(m, n, force)
+    for m, n, k, accum in step_problems():
+        bn = choose_bn(m, n, force, accum)
         traffic = tiles(m, n, bn) * (256 + bn) * k * 2
         r = rows.setdefault((m, n, k, bn), [0, 0.0, 0.0])
         r[0] += 1
