@@ -32,6 +32,10 @@ if grep -q "=== batched_memory rc=0" gpurun_out/${tag}_tests_unvalidated.log; th
   ZB_BATCH_MEM_PROJ=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_batchmem.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_batchmem.json
 fi
+# GEMM tile width: byte-weighted wave rule / 256-wide tiles everywhere (validated kernels, only the choice differs)
+ZB_GEMM2_TILE_MODEL=l2 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_tile_l2.json 2>/dev/null
+ZB_GEMM2_BN=256 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_bn256.json 2>/dev/null
+cut -c1-200 gpurun_out/${tag}_bench_tile_l2.json gpurun_out/${tag}_bench_bn256.json
 # add+LN backward with 16 rows per CTA: parity test under the switch, then the training bench
 ZB_LN1P_WARPS=16 timeout 60 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "add_ln" > gpurun_out/${tag}_tests_ln16.log 2>&1
 if tail -1 gpurun_out/${tag}_tests_ln16.log | grep -q passed && ! grep -q failed gpurun_out/${tag}_tests_ln16.log; then
