@@ -32,6 +32,8 @@ if grep -q "=== batched_memory rc=0" gpurun_out/${tag}_tests_unvalidated.log; th
   ZB_BATCH_MEM_PROJ=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_batchmem.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_batchmem.json
 fi
+# L2 -> SM ingest cap and TMA multicast at cluster sizes 2 / 4 / 8 (decides whether shared-A clusters are worth building)
+timeout 60 tools/tma_l2_probe > gpurun_out/${tag}_tma_l2_probe.log 2>&1; tail -12 gpurun_out/${tag}_tma_l2_probe.log
 # GEMM tile width: byte-weighted wave rule / 256-wide tiles everywhere (validated kernels, only the choice differs)
 ZB_GEMM2_TILE_MODEL=l2 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_tile_l2.json 2>/dev/null
 ZB_GEMM2_BN=256 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_bn256.json 2>/dev/null
