@@ -44,6 +44,12 @@ if tail -1 gpurun_out/${tag}_tests_ln16.log | grep -q passed && ! grep -q failed
   ZB_LN1P_WARPS=16 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_ln16.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_ln16.json
 fi
+# add+LN backward with 4 rows per warp, 8 warps per CTA (column partials in registers): same protocol
+ZB_LN1P_WARPS=8 timeout 60 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "add_ln" > gpurun_out/${tag}_tests_ln8.log 2>&1
+if tail -1 gpurun_out/${tag}_tests_ln8.log | grep -q passed && ! grep -q failed gpurun_out/${tag}_tests_ln8.log; then
+  ZB_LN1P_WARPS=8 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_ln8.json 2>/dev/null
+  cut -c1-200 gpurun_out/${tag}_bench_ln8.json
+fi
 if [ -z "$SKIP_NCU" ]; then
 ZB_DECODE_GRAPH=0 timeout 90 ncu --set full --clock-control none --import-source on -k regex:"beam_row|beam_part" \
   --launch-skip 70 -c 2 -f -o gpurun_out/${tag}_beam_full python tools/decode_ab.py 1 > gpurun_out/${tag}_ncu_beam.log 2>&1

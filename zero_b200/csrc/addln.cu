@@ -320,6 +320,159 @@ add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
   }
 }
 
+// Rows-per-warp variant (opt-in, ZB_LN1P_WARPS=8, untimed): 8 warps per CTA, R consecutive rows per warp.  A lane owns
+// the same columns in every row, so the three column sums of a warp's R rows accumulate in registers for free and only
+// one partial per WARP (not per row) goes through shared memory: R x less shared-memory traffic, a 256-thread CTA with
+// 48 KB (d = 512) that can share an SM with its neighbours under programmatic launch, the same bytes in flight per SM
+// (all R rows' loads are issued before the first reduction).  Same arithmetic per element as the kernel above; the
+// column sums are taken in a different order (rows of a warp first).
+constexpr int kLnRowsWarps = 8;
+template <int NV, int R>
+__global__ void __launch_bounds__(kLnRowsWarps * 32)
+add_ln_bwd_rows_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                       const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
+                       const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ scale, __nv_bfloat16* __restrict__ ds, float* __restrict__ dscale,
+                       float* __restrict__ doffset, float* __restrict__ dbias, long long rows, int cols) {
+  grid_dep_wait();
+  constexpr int W = kLnRowsWarps;
+  extern __shared__ __align__(16) float red[];  // [3][W][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  const long long row0 = ((long long)blockIdx.x * W + warp) * R;
+  float mu[R], rs[R], sg[R], sgs[R];
+  float sc[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sc[i][e] = 0.f;
+    if (v < nvec) {
+      const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + v * 8)),
+                   sc1 = __ldg(reinterpret_cast<const float4*>(scale + v * 8) + 1);
+      sc[i][0] = sc0.x; sc[i][1] = sc0.y; sc[i][2] = sc0.z; sc[i][3] = sc0.w;
+      sc[i][4] = sc1.x; sc[i][5] = sc1.y; sc[i][6] = sc1.z; sc[i][7] = sc1.w;
+    }
+  }
+  // every load of the warp's R rows is in flight before anything is consumed; the rows stay packed (bf16) in
+  // registers and are unpacked once for the row statistics and once for the outputs
+  uint4 px[R][NV], py[R][NV], pd[R][NV], pd2[R][NV];
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+    const bool live = row < rows;
+    mu[r] = live ? mean[row] : 0.f;
+    rs[r] = live ? rstd[row] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      const bool on = live && v < nvec;
+      const long long off = row * cols + v * 8;
+      px[r][i] = on ? __ldg(reinterpret_cast<const uint4*>(x + off)) : zero4;
+      pd[r][i] = on ? __ldg(reinterpret_cast<const uint4*>(d_out + off)) : zero4;
+      py[r][i] = (on && y) ? __ldg(reinterpret_cast<const uint4*>(y + off)) : zero4;
+      pd2[r][i] = (on && d_out2) ? __ldg(reinterpret_cast<const uint4*>(d_out2 + off)) : zero4;
+    }
+  }
+  // xhat = (x + y - mu) * rstd and d = d_out + d_out2 of vector (r, i), same operation order as the kernel above
+  auto unpack = [&](int r, int i, float (&xh)[8], float (&dd)[8]) {
+    const uint32_t wx[4] = {px[r][i].x, px[r][i].y, px[r][i].z, px[r][i].w};
+    const uint32_t wy[4] = {py[r][i].x, py[r][i].y, py[r][i].z, py[r][i].w};
+    const uint32_t wd[4] = {pd[r][i].x, pd[r][i].y, pd[r][i].z, pd[r][i].w};
+    const uint32_t w2[4] = {pd2[r][i].x, pd2[r][i].y, pd2[r][i].z, pd2[r][i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = unpack_bf16x2(wx[e]), b = unpack_bf16x2(wy[e]), c = unpack_bf16x2(wd[e]), g = unpack_bf16x2(w2[e]);
+      xh[2 * e] = (a.x + b.x - mu[r]) * rs[r];
+      xh[2 * e + 1] = (a.y + b.y - mu[r]) * rs[r];
+      dd[2 * e] = c.x + g.x;
+      dd[2 * e + 1] = c.y + g.y;
+    }
+  };
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    sg[r] = sgs[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float xh[8], dd[8];
+      unpack(r, i, xh, dd);
+      if (row0 + r < rows && lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float g = dd[e] * sc[i][e];
+          sg[r] += g;
+          sgs[r] += g * xh[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {   // 2 R independent butterfly reductions in flight
+    sg[r] = warp_sum(sg[r]) / cols;
+    sgs[r] = warp_sum(sgs[r]) / cols;
+  }
+  // per-lane column partials over the warp's rows: dscale += d * xhat, doffset += d, dbias += ds
+  float cs[NV][8], co[NV][8], cb[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[i][e] = co[i][e] = cb[i][e] = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const long long row = row0 + r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (row < rows && v < nvec) {
+        float xh[8], dd[8], o[8];
+        unpack(r, i, xh, dd);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = rs[r] * (dd[e] * sc[i][e] - sg[r] - xh[e] * sgs[r]);
+          cs[i][e] += dd[e] * xh[e];
+          co[i][e] += dd[e];
+          cb[i][e] += o[e];
+        }
+        store8(ds + row * cols + v * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float4* ws = reinterpret_cast<float4*>(red + (size_t)warp * cols + v * 8);
+      float4* wo = reinterpret_cast<float4*>(red + (size_t)(W + warp) * cols + v * 8);
+      ws[0] = make_float4(cs[i][0], cs[i][1], cs[i][2], cs[i][3]);
+      ws[1] = make_float4(cs[i][4], cs[i][5], cs[i][6], cs[i][7]);
+      wo[0] = make_float4(co[i][0], co[i][1], co[i][2], co[i][3]);
+      wo[1] = make_float4(co[i][4], co[i][5], co[i][6], co[i][7]);
+      if (dbias) {
+        float4* wb = reinterpret_cast<float4*>(red + (size_t)(2 * W + warp) * cols + v * 8);
+        wb[0] = make_float4(cb[i][0], cb[i][1], cb[i][2], cb[i][3]);
+        wb[1] = make_float4(cb[i][4], cb[i][5], cb[i][6], cb[i][7]);
+      }
+    }
+  }
+  __syncthreads();
+  // (quantity q, 4 columns) pairs are dealt round-robin to the CTA's 256 threads
+  const int c4n = cols >> 2;
+  const int items = (dbias ? 3 : 2) * c4n;
+  for (int it = threadIdx.x; it < items; it += W * 32) {
+    const int q = it / c4n, c4 = it % c4n;
+    const float* src = red + (size_t)q * W * cols + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const float4 t = *reinterpret_cast<const float4*>(src + (size_t)w * cols);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float* dst = (q == 0 ? dscale : (q == 1 ? doffset : dbias)) + c4 * 4;
+    red_add_f32x4(dst, acc);
+  }
+}
+
 static int check(const zb_add_ln_args* a, const char* who) {
   ZB_REQUIRE(a && a->x && a->scale, "%s: null pointer", who);
   ZB_REQUIRE(a->rows >= 0 && a->cols > 0 && a->cols % 8 == 0 && a->cols <= 8 * 32 * kLnMaxVec,
@@ -369,6 +522,28 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(a->dscale) | reinterpret_cast<uintptr_t>(a->doffset) |
                         reinterpret_cast<uintptr_t>(a->dbias)) & 15) == 0;
   static const bool w16 = getenv("ZB_LN1P_WARPS") != nullptr && atoi(getenv("ZB_LN1P_WARPS")) == 16;
+  static const bool rows8 = getenv("ZB_LN1P_WARPS") != nullptr && atoi(getenv("ZB_LN1P_WARPS")) == 8;
+  if (!no_1pass && rows8 && nv <= 2 && vec_ok && a->rows <= (long long)num_sms() * 64) {
+    constexpr int R = 4;
+    const int grid = (int)((a->rows + kLnRowsWarps * R - 1) / (kLnRowsWarps * R));
+    const size_t smem1 = (size_t)3 * kLnRowsWarps * a->cols * sizeof(float);
+#define CALLR(N)                                                                                             \
+  do {                                                                                                       \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      cudaFuncSetAttribute(add_ln_bwd_rows_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                           3 * kLnRowsWarps * 512 * (int)sizeof(float));                                     \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    ZB_LAUNCH((add_ln_bwd_rows_kernel<N, R>), grid, kLnRowsWarps * 32, smem1, st,                            \
+        (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
+        (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
+        a->doffset, a->dbias, a->rows, (int)a->cols);                                                        \
+  } while (0)
+    if (nv <= 1) CALLR(1); else CALLR(2);
+#undef CALLR
+    return check_launch("zb_add_ln_bwd(rows per warp)");
+  }
   if (!no_1pass && w16 && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= 16 * 32 && a->rows <= (long long)num_sms() * 32) {
     const int grid = (int)((a->rows + 15) / 16);
     const size_t smem1 = (size_t)3 * 16 * a->cols * sizeof(float);
