@@ -9,6 +9,7 @@ clip_by_global_norm factor are folded into the fused TF-semantics Adam kernel.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -63,7 +64,6 @@ class Trainer(object):
         # rank's compute copy as ONE kernel per rank over NVLink peer memory (zero_b200/shard_opt.py) instead of the
         # NCCL all-reduce + replicated Adam below.  safe_nan needs the summed gradients on the host BEFORE the update
         # (main.py:320-332), which the fused step never materialises: that mode keeps the all-reduce.
-        import os
         self.shard = None
         mode = os.environ.get("ZB_SHARD_OPT", "0")
         if shard_transport is not None or (self.world > 1 and mode in ("1", "p2p")
