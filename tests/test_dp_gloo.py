@@ -125,3 +125,30 @@ def test_batched_memory_projection_layout(monkeypatch):
         assert k_map.data_ptr() == w.data_ptr() and tuple(k_map.shape) == (d, d)
     assert ps1.slots["dec.kvall.W"][0] % 64 == 0 and (nd * 2 * d) % 8 == 0
     assert ps1.slots["dec.kvall.W"][0] >= ps1.dec_offset               # stays in the decoder-side all-reduce bucket
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from zero_b200 import evalu
+    local = ([["r%d" % rank, "a"], ["b"]] if rank == 0 else [["c", "d", "e"]],
+             [0.5, 0.25] if rank == 0 else [0.75], [0, 2] if rank == 0 else [1], 5 + rank, 0.1 * (rank + 1))
+    got = evalu.gather_decoded(local, world)
+    torch.save(got, os.path.join(out_dir, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_rank_sharded_decoding_results_reach_every_rank(tmp_path):
+    """evalu.decoding with world_size 2: rank r decodes every second batch, both ranks end up with all hypotheses
+    (rank order; `indices` restore the corpus order) — so BLEU-driven decisions agree across ranks."""
+    from zero_b200 import evalu
+    mp.spawn(_gather_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    assert a == b
+    trans, scores, indices, tokens, seconds = a
+    assert trans == [["r0", "a"], ["b"], ["c", "d", "e"]] and scores == [0.5, 0.25, 0.75] and indices == [0, 2, 1]
+    assert tokens == 11 and abs(seconds - 0.2) < 1e-12
+    assert evalu.in_corpus_order(trans, indices) == [["r0", "a"], ["c", "d", "e"], ["b"]]
+    assert evalu.gather_decoded((["x"], [1.0], [0], 1, 0.5), 1) == (["x"], [1.0], [0], 1, 0.5)

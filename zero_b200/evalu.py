@@ -46,15 +46,38 @@ def decode_hypothesis(seqs, scores, params, mask=None):
 
 
 # ---------------------------------------------------------------------------------------------- drivers
-def decoding(infer_fns, dataset, params, log=None):
+def gather_decoded(local, world_size):
+    """Every rank's (translations, scores, indices, tokens, seconds) -> the whole corpus on every rank (so that all
+    ranks take the same BLEU-driven decisions): lists concatenated in rank order, tokens summed, seconds = the
+    slowest rank's.  The reference's towers decode consecutive batches in one session.run (evalu.py:66-104)."""
+    if world_size <= 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world_size
+    dist.all_gather_object(parts, local)
+    translations, scores, indices, tokens, seconds = [], [], [], 0, 0.0
+    for tr, sc, ix, tk, sec in parts:
+        translations.extend(tr)
+        scores.extend(sc)
+        indices.extend(ix)
+        tokens += tk
+        seconds = max(seconds, sec)
+    return translations, scores, indices, tokens, seconds
+
+
+def decoding(infer_fns, dataset, params, log=None, world_size=1, rank=0):
     """Beam-search the dev/test set batch by batch (evalu.py:49-139).  Returns translations, scores, sample
     indices and a timing record {sentences, tokens, seconds}: tokens = top-1 hypothesis lengths + 1 (<eos>),
-    seconds = device time of beam_search only (the reference's per-batch wall clock around session.run)."""
+    seconds = device time of beam_search only (the reference's per-batch wall clock around session.run).
+    With world_size > 1 rank r decodes every world_size-th batch (what tower r is fed, evalu.py:66-92) and the
+    results are exchanged at the end; the order of the returned lists is then by rank, `indices` restores the corpus."""
     encoding_fn, decoding_fn = infer_fns
     translations, scores, indices = [], [], []
     tokens, seconds = 0, 0.0
     for bidx, data in enumerate(dataset.batcher(params.eval_batch_size, buffer_size=params.buffer_size,
                                                 shuffle=False, train=False)):
+        if bidx % world_size != rank:
+            continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = search.beam_search({"source": torch.from_numpy(data["src"])}, encoding_fn, decoding_fn, params)
@@ -70,6 +93,8 @@ def decoding(infer_fns, dataset, params, log=None):
         if log:
             log("Decoding Batch %d using %.3f s, translating %d sentences using %.3f s in total" % (
                 bidx, dt, len(translations), seconds))
+    translations, scores, indices, tokens, seconds = gather_decoded(
+        (translations, scores, [int(i) for i in indices], tokens, seconds), world_size)
     return translations, scores, indices, {"sentences": len(translations), "tokens": tokens, "seconds": seconds}
 
 

@@ -30,10 +30,12 @@ def _log(msg):
     print(msg, flush=True)
 
 
-def evaluate(params, dataset, references=None, log=_log):
-    """main.evaluate (main.py:473-545): beam-search `dataset`, BLEU against `references` (list of corpora)."""
+def evaluate(params, dataset, references=None, log=_log, world_size=1, rank=0):
+    """main.evaluate (main.py:473-545): beam-search `dataset`, BLEU against `references` (list of corpora).  With
+    world_size > 1 the batches are dealt to the ranks and every rank ends up with the whole result."""
     graph = model_registry.get_model(params.model_name)
-    trans, scores, indices, timing = evalu.decoding(graph.infer_fn(params), dataset, params, log=None)
+    trans, scores, indices, timing = evalu.decoding(graph.infer_fn(params), dataset, params, log=None,
+                                                    world_size=world_size, rank=rank)
     bleu = evalu.eval_metric(trans, references, indices=indices) if references else 0.0
     log("Scores %.4f, BLEU %.4f, %d sentences, %d tokens in %.3f s (%.0f tok/s)" % (
         float(np.mean(scores)) if scores else 0.0, bleu, timing["sentences"], timing["tokens"], timing["seconds"],
@@ -109,7 +111,8 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
             if dev_dataset is not None and gstep > 0 and gstep % params.eval_freq == 0:
                 trainer.ema_assign()
                 t0 = time.time()
-                res = evaluate(params, dev_dataset, dev_references, log=lambda m: None)
+                res = evaluate(params, dev_dataset, dev_references, log=lambda m: None, world_size=world_size,
+                               rank=rank)
                 trainer.ema_restore()
                 bleu = res["bleu"]
                 log("GStep %d, Scores %.4f, BLEU %.4f, Duration %.3f s" % (

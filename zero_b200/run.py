@@ -127,7 +127,8 @@ def run(mode, params, log=print):
     if mode == "test":
         from . import evalu
         test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len)
-        res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log)
+        res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log,
+                             world_size=world, rank=rank)
         if params.test_output and rank == 0:
             evalu.dump_tanslation(res["translations"], params.test_output)      # main.py:543
         return res
