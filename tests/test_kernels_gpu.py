@@ -686,7 +686,7 @@ def test_gumbel_add_noise_statistics_and_reproducibility():
     x = torch.zeros(n + 1, device=dev())[:n]                      # odd tail handled too
     base = torch.full((n,), 3.0, device=dev())
     a = ops.gumbel_add(base.clone(), seed, 5) - 3.0
-    assert abs(float(a.mean()) - 0.5772) < 5e-3 and abs(float(a.var()) - math.pi ** 2 / 6) < 2e-2
+    assert abs(float(a.mean()) - 0.5772) < 8e-3 and abs(float(a.var()) - math.pi ** 2 / 6) < 2.5e-2
     assert float(a.max()) < 18.5 and float(a.min()) > -3.0        # -log(eps) = 18.4 caps the right tail
     b = ops.gumbel_add(base.clone(), seed, 5) - 3.0
     assert torch.equal(a, b)
@@ -694,7 +694,7 @@ def test_gumbel_add_noise_statistics_and_reproducibility():
     seed.add_(1)
     d = ops.gumbel_add(base.clone(), seed, 5) - 3.0
     assert not torch.equal(a, c) and not torch.equal(a, d)
-    assert abs(float((a * c).mean()) - 0.5772 ** 2) < 5e-3        # different sites are uncorrelated
+    assert abs(float((a * c).mean()) - 0.5772 ** 2) < 1.2e-2      # different sites are uncorrelated (6 sigma)
     odd = torch.zeros(1001, device=dev())
     ops.gumbel_add(odd, seed, 1)
     assert bool(torch.isfinite(odd).all()) and float(odd.abs().sum()) > 0
