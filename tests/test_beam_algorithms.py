@@ -79,3 +79,36 @@ def test_threshold_keeps_every_tied_candidate():
     s, i, passed = part_lists_with_threshold(score, 4, 1000, 8)
     np.testing.assert_array_equal(i, np.arange(8))
     assert passed == 4000
+
+
+def test_gumbel_generator_statistics():
+    """The counter-based generator behind zb_gumbel_add (csrc/elementwise.cu gumbel_add_kernel; the splitmix64 hash of
+    the dropout masks, 24 bits per element), restated in numpy integer arithmetic: Gumbel(0, 1) has mean 0.5772 and
+    variance pi^2 / 6 (util.gumbel_noise, utils/util.py:189-195); sites, seeds and neighbours are uncorrelated."""
+    import math
+
+    def hash4(seed, site, idx):
+        with np.errstate(over="ignore"):
+            z = np.uint64(seed) + np.uint64(site) * np.uint64(0x9E3779B97F4A7C15) + idx * np.uint64(0xD1B54A32D192ED03)
+            z ^= z >> np.uint64(30)
+            z *= np.uint64(0xBF58476D1CE4E5B9)
+            z ^= z >> np.uint64(27)
+            z *= np.uint64(0x94D049BB133111EB)
+            z ^= z >> np.uint64(31)
+        return z
+
+    def gumbel(n, seed, site, eps=1e-8):
+        h = hash4(seed, site ^ 0x6A09E667, np.arange((n + 1) // 2, dtype=np.uint64))
+        u = np.empty(2 * len(h), np.float32)
+        u[0::2] = ((h & np.uint64(0xFFFFFFFF)) >> np.uint64(8)).astype(np.float32) * np.float32(1 / 16777216)
+        u[1::2] = (h >> np.uint64(40)).astype(np.float32) * np.float32(1 / 16777216)
+        u = u[:n]
+        assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+        return -np.log(-np.log(u + np.float32(eps)) + np.float32(eps))
+
+    n = 1 << 20
+    a, c, d = gumbel(n, 77, 5), gumbel(n, 77, 6), gumbel(n, 78, 5)
+    assert abs(float(a.mean()) - 0.5772) < 8e-3 and abs(float(a.var()) - math.pi ** 2 / 6) < 2.5e-2
+    assert -3.0 < float(a.min()) and float(a.max()) < 18.5
+    assert abs(float((a * c).mean()) - 0.5772 ** 2) < 1.2e-2 and abs(float((a * d).mean()) - 0.5772 ** 2) < 1.2e-2
+    assert abs(float(np.corrcoef(a[:-1], a[1:])[0, 1])) < 5e-3
