@@ -1,0 +1,163 @@
+"""Host side of main.train on the CPU (every kernel entry point is a no-op): the training record, checkpoints and
+resume-by-batch-index of the reference's loop (main.py:133-470, utils/recorder.py, utils/queuer.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+@pytest.fixture
+def host_only(monkeypatch):
+    import zero_b200.engine as E
+    import zero_b200.main as M
+    import zero_b200.ops as ops
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if callable(fn) and not name.startswith("_") and getattr(fn, "__module__", "") == ops.__name__ \
+                and name not in ("attention_args", "gemm_args", "wgrad_args", "beam_args"):
+            monkeypatch.setattr(ops, name, lambda *a, **k: None)
+    monkeypatch.setattr(ops, "cast_f32_bf16", lambda src, dst: dst.copy_(src))
+
+    def ce(logits, labels, nll, smooth, d_logits=None, per_sample=None, loss=None, loss_scale=1.0):
+        if loss is not None:
+            loss.fill_(1.5)
+    monkeypatch.setattr(ops, "softmax_ce", ce)
+    monkeypatch.setattr(E.Engine, "enable_side_stream", lambda self, on=True: None)
+    monkeypatch.setattr(M, "pin", lambda d: (torch.from_numpy(d["src"]), torch.from_numpy(d["tgt"])))
+
+
+def _params(tmp_path, **over):
+    from zero_b200.params import global_params
+    from zero_b200.vocab import Vocab
+    p = global_params()
+    words = ["w%d" % i for i in range(29)]
+    p.override_from_dict(dict(model_name="transformer", scope_name="transformer", hidden_size=64, embed_size=64,
+                              filter_size=128, num_heads=2, num_encoder_layer=1, num_decoder_layer=1,
+                              batch_or_token="batch", batch_size=2, shuffle_batch=False, buffer_size=100, epoches=3,
+                              disp_freq=1, save_freq=2, eval_freq=10 ** 6, sample_freq=10 ** 6,
+                              max_training_steps=10 ** 6, output_dir=str(tmp_path / "model"), clip_grad_norm=0.0,
+                              lrate_strategy="noam", checkpoints=3))
+    p.override_from_dict(over)
+    for key in ("src_vocab", "tgt_vocab"):
+        p.add_hparam(key, Vocab(tokens=words))
+    return p
+
+
+def _corpus(n=10):
+    g = np.random.RandomState(0)
+    src = [["w%d" % int(t) for t in g.randint(0, 29, size=int(g.randint(2, 7)))] for _ in range(n)]
+    return src, [list(reversed(s)) for s in src]
+
+
+def _engine_for(params):
+    import zero_b200.engine as E
+    from zero_b200.models import transformer as plugins
+    eng = E.Engine(params, device="cpu")
+    eng.ps.init_random(5)
+    plugins.reset_engines()
+    plugins._engines[(params.scope_name, "transformer")] = eng
+    return eng
+
+
+def test_record_checkpoints_and_resume_by_batch_index(tmp_path, host_only):
+    from zero_b200 import main, saver
+    from zero_b200.data import Dataset
+    from zero_b200.models import transformer as plugins
+    src, tgt = _corpus()
+
+    class Crash(Exception):
+        pass
+
+    def crash_at_3(gstep, loss):
+        if gstep == 3:
+            raise Crash()
+
+    # first run: 10 pairs -> 5 batches per epoch; "crashes" during update 3, after the checkpoint of update 2
+    p1 = saver.setup_recorder(_params(tmp_path))
+    _engine_for(p1)
+    logs = []
+    with pytest.raises(Crash):
+        main.train(p1, Dataset(src, tgt, p1.src_vocab, p1.tgt_vocab, 100, "batch"), log=logs.append,
+                   on_step=crash_at_3)
+    out = tmp_path / "model"
+    assert sorted(f for f in os.listdir(out) if f.startswith("model-")) == ["model-2.npz"]
+    rec = json.load(open(out / "record.json"))
+    # written with the checkpoint of update 2: batch index 1 consumed, `step` still the previous update (main.py:351-353
+    # comes before :430), epoch 1
+    assert rec["lidx"] == 1 and rec["step"] == 1 and rec["epoch"] == 1 and rec["estop"] is False
+    # second run: record.json + the checkpoint put the loop back where the checkpoint was taken
+    p2 = saver.setup_recorder(_params(tmp_path, max_training_steps=7))
+    assert p2.recorder.lidx == 1
+    eng2 = _engine_for(p2)
+    logs2, seen = [], []
+    state = main.train(p2, Dataset(src, tgt, p2.src_vocab, p2.tgt_vocab, 100, "batch"), log=logs2.append,
+                       on_step=lambda g, l: seen.append(g))
+    assert any("Restored parameters" in m and "global step 2" in m for m in logs2)
+    assert sum("Passing" in m for m in logs2) == 2                      # batches 0 and 1 of the interrupted epoch
+    assert seen == [3, 4, 5, 6, 7]                                       # 3 left in epoch 1, then epoch 2
+    assert state["estop"] and state["epoch"] == 2 and [g for g, _ in state["losses"]] == seen
+    assert any(m.startswith("Epoch 2") for m in logs2) and any("Your training is finished" in m for m in logs2)
+    rec = json.load(open(out / "record.json"))
+    assert rec["epoch"] == 2 and rec["lidx"] == 0 and rec["step"] == 5   # record of the checkpoint of update 6
+    assert sorted(f for f in os.listdir(out) if f.startswith("model-")) == ["model-2.npz", "model-4.npz", "model-6.npz"]
+    # third run: the stop flag was not written (the loop ended on max_training_steps after the last record), but the
+    # step count past max_training_steps stops a later run at once once it is recorded
+    p3 = saver.setup_recorder(_params(tmp_path, max_training_steps=4))
+    assert p3.recorder.step == 5
+    state3 = main.train(p3, Dataset(src, tgt, p3.src_vocab, p3.tgt_vocab, 100, "batch"), log=lambda m: None)
+    assert state3.get("finished") and state3["losses"] == []
+    plugins.reset_engines()
+    del eng2
+
+
+def test_prefetch_queue_keeps_the_order_and_forwards_errors():
+    from zero_b200.queuer import EnQueuer
+    assert list(EnQueuer(iter(range(50)), lambda x: x * 2, worker_processes_num=1, output_queue_size=3)) == \
+        [2 * i for i in range(50)]
+    assert list(EnQueuer(iter(range(5)), worker_processes_num=0)) == list(range(5))
+    with pytest.raises(ValueError):
+        EnQueuer(iter(()), worker_processes_num=-1)
+
+    def bad():
+        yield 1
+        raise RuntimeError("reader failed")
+    it = iter(EnQueuer(bad(), worker_processes_num=1))
+    assert next(it) == 1
+    with pytest.raises(RuntimeError):
+        next(it)
+    # a consumer that stops early releases the worker (bounded queue, endless reader)
+    import itertools
+    import threading
+    before = threading.active_count()
+    for i, x in enumerate(EnQueuer(itertools.count(), worker_processes_num=1, output_queue_size=2)):
+        if i == 3:
+            break
+    import time
+    for _ in range(50):
+        if threading.active_count() <= before:
+            break
+        time.sleep(0.05)
+    assert threading.active_count() <= before
+
+
+def test_same_batches_with_and_without_the_worker():
+    """The batcher shuffles with the global numpy RNG: the order must not depend on who runs the generator."""
+    from zero_b200.data import Dataset
+    from zero_b200.queuer import EnQueuer
+    from zero_b200.vocab import Vocab
+    v = Vocab(tokens=["w%d" % i for i in range(29)])
+    src, tgt = _corpus(200)
+    runs = []
+    for workers in (0, 1):
+        np.random.seed(1234)
+        ds = Dataset(src, tgt, v, v, 100, "token")
+        got = []
+        for _ in range(2):      # two epochs: the leak buffer carries over
+            got += [b["index"] for b in EnQueuer(ds.batcher(40, buffer_size=64, shuffle=True, train=True),
+                                                 worker_processes_num=workers, output_queue_size=100)]
+        runs.append(got)
+    assert runs[0] == runs[1] and len(runs[0]) > 10

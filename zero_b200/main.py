@@ -13,14 +13,16 @@ what record.json would (run.py:276-296).
 from __future__ import annotations
 
 import math
+import os
 import time
 
 import numpy as np
 import torch
 
-from . import evalu, lrs
+from . import evalu, lrs, search
 from . import saver as ckpt
 from .data import pin, shard_for_rank
+from .queuer import EnQueuer
 from .models import model as model_registry
 from .models.transformer import get_engine
 from .train import Trainer
@@ -43,33 +45,86 @@ def evaluate(params, dataset, references=None, log=_log, world_size=1, rank=0):
     return {"bleu": bleu, "translations": evalu.in_corpus_order(trans, indices), "scores": scores, "timing": timing}
 
 
+def _recorder(params):
+    """The training record (utils/recorder.py; fields of run.py:276-296): the one run.py restored from record.json,
+    else a fresh in-memory one."""
+    rec = params.recorder if "recorder" in params else None
+    if rec is None:
+        rec = ckpt.Recorder()
+        rec.bad_counter, rec.estop, rec.lidx, rec.step, rec.epoch = 0, False, -1, 0, 1
+        rec.lrate, rec.history_scores, rec.valid_script_scores = params.lrate, [], []
+    return rec
+
+
 def train(params, train_dataset, dev_dataset=None, dev_references=None, world_size=1, rank=0, use_graph=False,
           log=_log, on_step=None):
     """main.train (main.py:133-470).  Returns the training record: {"step", "epoch", "losses": [(gstep, loss)],
-    "valid_script_scores": [(gstep, bleu)], "estop", "tokens_per_sec": [...] }."""
+    "valid_script_scores": [(gstep, bleu)], "estop", "tokens_per_sec": [...] }.
+    Resuming: `params.recorder` (record.json, written next to every checkpoint) carries epoch, batch index, step,
+    learning rate, early-stopping state and the score history; with `train_continue` the batches up to the recorded
+    index of the interrupted epoch are skipped (main.py:256-266), weights / Adam slots / global step come from the
+    latest checkpoint.  The batch index counts this rank's batches, i.e. groups of `world_size` batches of the corpus."""
+    rec = _recorder(params)
+    if rec.estop or rec.epoch > params.epoches or rec.step > params.max_training_steps:      # main.py:135-139
+        log("Stop condition reached, you have finished training your model.")
+        return {"step": int(rec.step), "epoch": int(rec.epoch), "losses": [], "estop": bool(rec.estop),
+                "valid_script_scores": [tuple(v) for v in rec.valid_script_scores],
+                "history_scores": [tuple(v) for v in rec.history_scores], "bad_counter": int(rec.bad_counter),
+                "tokens_per_sec": [], "finished": True}
     np.random.seed(int(params.random_seed))            # run.py:379-381 (batch shuffling uses the numpy RNG)
     eng = get_engine(params)
+    params.lrate = rec.lrate                            # main.py:229: a decayed rate survives a restart
     schedule = lrs.get_lr(params)
     trainer = Trainer(eng, params, world_size=world_size, use_graph=use_graph, lr_schedule=schedule)
     # checkpoints (utils/saver.py) only when an output directory is configured; rank 0 writes
     saver = None
-    if getattr(params, "output_dir", ""):
-        saver = ckpt.Saver(checkpoints=params.checkpoints, output_dir=params.output_dir,
+    out_dir = getattr(params, "output_dir", "")
+    if out_dir:
+        saver = ckpt.Saver(checkpoints=params.checkpoints, output_dir=out_dir,
                            best_checkpoints=params.best_checkpoints)
         if getattr(params, "train_continue", True) and saver.restore(eng, trainer=trainer):
             log("Restored parameters from %s (global step %d)" % (saver.latest(), trainer.global_step))
-    state = {"step": 0, "epoch": 0, "losses": [], "valid_script_scores": [], "history_scores": [], "estop": False,
-             "bad_counter": 0, "tokens_per_sec": []}
+
+    def save_record():
+        if saver is not None and rank == 0:
+            rec.save_to_json(os.path.join(out_dir, "record.json"))
+
+    def dev_eval(gstep):
+        """Evaluation on the dev set with the averaged weights swapped in (main.py:355-383, 439-466)."""
+        trainer.ema_assign()
+        t0 = time.time()
+        res = evaluate(params, dev_dataset, dev_references, log=lambda m: None, world_size=world_size, rank=rank)
+        trainer.ema_restore()
+        mean_score = float(np.mean(res["scores"])) if res["scores"] else 0.0
+        log("GStep %d, Scores %.4f, BLEU %.4f, Duration %.3f s" % (gstep, mean_score, res["bleu"], time.time() - t0))
+        if out_dir and rank == 0:
+            evalu.dump_tanslation(res["translations"], os.path.join(out_dir, "eval-%d.trans.txt" % gstep))
+        return res, mean_score
+
+    state = {"step": int(rec.step), "epoch": int(rec.epoch), "losses": [],
+             "valid_script_scores": [tuple(v) for v in rec.valid_script_scores],
+             "history_scores": [tuple(v) for v in rec.history_scores], "estop": False,
+             "bad_counter": int(rec.bad_counter), "tokens_per_sec": []}
     size = params.batch_size if params.batch_or_token == "batch" else params.token_size
     cum_tokens, start_time = 0, time.time()
-    for epoch in range(1, int(params.epoches) + 1):
-        state["epoch"] = epoch
+    for epoch in range(int(rec.epoch), int(params.epoches) + 1):
+        rec.epoch = state["epoch"] = epoch
         log("Training the model for epoch %d" % epoch)
         schedule.before_epoch(eidx=epoch)
         batches = train_dataset.batcher(size, buffer_size=params.buffer_size, shuffle=params.shuffle_batch,
                                         train=True)
+        train_queue = EnQueuer(shard_for_rank(batches, world_size, rank),               # main.py:242-250
+                               worker_processes_num=getattr(params, "process_num", 1),
+                               input_queue_size=getattr(params, "input_queue_size", 5),
+                               output_queue_size=getattr(params, "output_queue_size", 5))
         lidx = -1
-        for lidx, data in enumerate(shard_for_rank(batches, world_size, rank)):
+        for lidx, data in enumerate(train_queue):
+            if getattr(params, "train_continue", True) and lidx <= rec.lidx:          # main.py:256-264
+                segments = max(rec.lidx // 5, 1)
+                if rec.lidx < 5 or lidx % segments == 0:
+                    log("Passing %d-th index according to record" % lidx)
+                continue
+            rec.lidx = lidx
             src, tgt = pin(data)
             cum_tokens += int(np.sum(data["tgt"] > 0))          # main.py:297
             loss_t = trainer.compute(src, tgt)
@@ -88,7 +143,7 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                 loss, gnorm = float(loss_t.item()), trainer.gradient_norm()
                 if not (math.isfinite(loss) and math.isfinite(gnorm)):
                     log("Nan or Inf raised! Loss %s GNorm %s." % (loss, gnorm))
-                    state["estop"] = True
+                    state["estop"] = rec.estop = True
                     break
             gstep = trainer.global_step
             state["step"] = gstep
@@ -108,15 +163,14 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                 trainer.sync_full_state()                       # every rank (collective when the step is sharded)
                 if rank == 0:
                     saver.save(eng, gstep, trainer=trainer)
+                save_record()                                   # main.py:351-353
             if dev_dataset is not None and gstep > 0 and gstep % params.eval_freq == 0:
-                trainer.ema_assign()
-                t0 = time.time()
-                res = evaluate(params, dev_dataset, dev_references, log=lambda m: None, world_size=world_size,
-                               rank=rank)
-                trainer.ema_restore()
+                res, mean_score = dev_eval(gstep)
                 bleu = res["bleu"]
-                log("GStep %d, Scores %.4f, BLEU %.4f, Duration %.3f s" % (
-                    gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0, bleu, time.time() - t0))
+                if saver is not None:
+                    trainer.sync_full_state()
+                    if rank == 0:
+                        saver.save(eng, gstep, metric_score=bleu, trainer=trainer)
                 prev = [v[1] for v in state["valid_script_scores"]]
                 if not prev or bleu > max(prev):
                     state["bad_counter"] = 0
@@ -124,22 +178,49 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                     state["bad_counter"] += 1
                     if state["bad_counter"] > params.estop_patience:
                         state["estop"] = True
-                state["history_scores"].append((gstep, float(np.mean(res["scores"])) if res["scores"] else 0.0))
+                state["history_scores"].append((gstep, mean_score))
                 state["valid_script_scores"].append((gstep, float(bleu)))
-                if saver is not None:
-                    trainer.sync_full_state()
-                    if rank == 0:
-                        saver.save(eng, gstep, metric_score=bleu, trainer=trainer)
+                rec.bad_counter, rec.estop = state["bad_counter"], bool(state["estop"])
+                rec.history_scores = [list(v) for v in state["history_scores"]]
+                rec.valid_script_scores = [list(v) for v in state["valid_script_scores"]]
+                save_record()                                   # main.py:399-401
                 schedule.after_eval(float(bleu))
                 if state["estop"]:
                     break
+            if getattr(params, "sample_freq", 0) and dev_dataset is not None and gstep > 0 \
+                    and gstep % params.sample_freq == 0:
+                _sample(params, data, log)                      # main.py:406-422
             if gstep >= params.max_training_steps:
-                state["estop"] = True
+                state["estop"] = rec.estop = True
                 break
+            rec.step = int(gstep)                               # main.py:430
         if state["estop"]:
             log("Early Stopped!")
             break
+        rec.lidx = -1                                           # main.py:437
         schedule.after_epoch(eidx=epoch)
+    # final evaluation (main.py:439-466)
+    if dev_dataset is not None and getattr(params, "final_eval", True):
+        res, _ = dev_eval(int(rec.step) + 1)
+        state["final_bleu"] = float(res["bleu"])
     torch.cuda.synchronize()
+    log("Your training is finished :)")
     state["trainer"] = trainer
+    state["best_score"] = saver.best_score if saver is not None else None
     return state
+
+
+def _sample(params, data, log):
+    """Translate the first five sentences of the current batch and log source / target / translation
+    (main.py:406-422)."""
+    graph = model_registry.get_model(params.model_name)
+    encoding_fn, decoding_fn = graph.infer_fn(params)
+    log("Start Sampling")
+    out = search.beam_search({"source": torch.from_numpy(np.ascontiguousarray(data["src"][:5]))}, encoding_fn,
+                             decoding_fn, params)
+    hyps, _ = evalu.decode_hypothesis([out["seq"].cpu().numpy()], [out["score"].cpu().numpy()], params)
+    for sidx in range(min(5, len(hyps))):
+        log("%d-th Source: %s" % (sidx, " ".join(evalu.decode_target_token(data["src"][sidx], params.src_vocab))))
+        log("%d-th Target: %s" % (sidx, " ".join(evalu.decode_target_token(data["tgt"][sidx], params.tgt_vocab))))
+        log("%d-th Translation: %s" % (sidx, " ".join(hyps[sidx])))
+    log("End Sampling")
