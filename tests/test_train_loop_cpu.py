@@ -161,3 +161,28 @@ def test_same_batches_with_and_without_the_worker():
                                                  worker_processes_num=workers, output_queue_size=100)]
         runs.append(got)
     assert runs[0] == runs[1] and len(runs[0]) > 10
+
+
+def test_pretrained_model_is_loaded_by_name_before_the_run_starts(tmp_path, host_only):
+    """main.py:221-222 + utils/saver.py:150-171: `pretrained_model` (file or checkpoint directory) initialises the
+    variables it has under the same name and shape; the rest keep their initial values."""
+    import zero_b200.engine as E
+    from zero_b200 import main, saver
+    from zero_b200.data import Dataset
+    from zero_b200.models import transformer as plugins
+    src, tgt = _corpus(4)
+    donor_p = _params(tmp_path / "donor")
+    donor = E.Engine(donor_p, device="cpu")
+    donor.ps.init_random(77)
+    saver.Saver(output_dir=str(tmp_path / "pre")).save(donor, 9)
+    assert saver.resolve_checkpoint(str(tmp_path / "pre")).endswith("model-9.npz")
+    assert saver.resolve_checkpoint(str(tmp_path / "nothing")) is None and saver.resolve_checkpoint("") is None
+    p = _params(tmp_path / "run", pretrained_model=str(tmp_path / "pre"), max_training_steps=1, output_dir="")
+    eng = _engine_for(p)
+    assert not torch.equal(eng.ps.master, donor.ps.master)
+    logs = []
+    main.train(p, Dataset(src, tgt, p.src_vocab, p.tgt_vocab, 100, "batch"), log=logs.append)
+    assert torch.equal(eng.ps.master, donor.ps.master)          # optimizer kernels are no-ops here: weights = loaded
+    assert any("Total trainable variables size" in m for m in logs)
+    assert any("Trying restore pretrained parameters" in m for m in logs)
+    plugins.reset_engines()

@@ -77,8 +77,15 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
     schedule = lrs.get_lr(params)
     trainer = Trainer(eng, params, world_size=world_size, use_graph=use_graph, lr_schedule=schedule)
     # checkpoints (utils/saver.py) only when an output directory is configured; rank 0 writes
+    ckpt.variable_printer(eng, log)                     # main.py:205-206
     saver = None
     out_dir = getattr(params, "output_dir", "")
+    pretrained = ckpt.resolve_checkpoint(getattr(params, "pretrained_model", ""))
+    if pretrained is not None:                          # main.py:221-222: name-matched, before the run's own restore
+        log("Trying restore pretrained parameters")
+        with np.load(pretrained) as z:
+            loaded, skipped = ckpt.Saver.restore_state_dict(eng, {k: z[k] for k in z.files})
+        log("Restored %d variables from %s (%d not found there)" % (len(loaded), pretrained, len(skipped)))
     if out_dir:
         saver = ckpt.Saver(checkpoints=params.checkpoints, output_dir=out_dir,
                            best_checkpoints=params.best_checkpoints)

@@ -172,6 +172,40 @@ class Saver(object):
         return True
 
 
+def resolve_checkpoint(path):
+    """A checkpoint file, or the newest checkpoint of a checkpoint directory (its checkpoint.json index, else the
+    model-<step>.npz with the largest step); None when there is nothing to load (utils/saver.py:105-125)."""
+    if not path:
+        return None
+    if os.path.isfile(path):
+        return path
+    if os.path.isdir(path):
+        index = os.path.join(path, "checkpoint.json")
+        if os.path.exists(index):
+            names = json.load(open(index)).get("all", [])
+            if names and os.path.exists(os.path.join(path, names[-1])):
+                return os.path.join(path, names[-1])
+        found = []
+        for f in os.listdir(path):
+            if f.startswith("model-") and f.endswith(".npz") and f[6:-4].isdigit():
+                found.append((int(f[6:-4]), f))
+        if found:
+            return os.path.join(path, max(found)[1])
+    return None
+
+
+def variable_printer(engine, log=print):
+    """util.variable_printer (utils/util.py:211-222): every trainable variable with its shape, then the total."""
+    ps = engine.ps
+    total = 0
+    for name in sorted(ps.tf_names()):
+        shape = tuple(ps.tf_view(ps.master, name).shape)
+        log("%s\tshape    %s" % (name.ljust(80), str(shape).ljust(20)))
+        total += int(np.prod(shape))
+    log("Total trainable variables size: %d" % total)
+    return total
+
+
 def average_checkpoints(path, checkpoints, output):
     """scripts/checkpoint_averaging.py:31-125: arithmetic mean of the newest `checkpoints` checkpoints under `path`
     (every variable except global_step, which restarts at 0; accumulated in float64 like the script's np.zeros),
