@@ -144,3 +144,22 @@ def test_checkpoint_averaging_follows_the_reference_script(tmp_path):
         np.testing.assert_array_equal(z["transformer/bias"], vals[300]["transformer/bias"])
     with pytest.raises(ValueError):
         saver.average_checkpoints(str(tmp_path / "nowhere"), 2, str(out))
+
+
+def test_vocabulary_builder_matches_reference(tmp_path):
+    """`python -m zero_b200.vocab [--size N] corpus out` against the file the reference's vocab.py writes for the
+    same corpus (tests/golden/vocab_golden.json, make_vocab_golden.py): frequency order, ties by first appearance,
+    specials first, truncation."""
+    import json
+    import os
+    from zero_b200 import vocab
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vocab_golden.json")))
+    src = tmp_path / "corpus.txt"
+    src.write_text("\n".join(gold["lines"]) + "\n")
+    for run in gold["runs"]:
+        out = tmp_path / ("vocab_%d.txt" % run["size"])
+        v = vocab.main(["--size", str(run["size"]), str(src), str(out)])
+        assert out.read_text().splitlines() == run["file"]
+        assert v.size() == run["vocab_size"]
+        loaded = vocab.Vocab(str(out))
+        assert loaded.size() == len(run["file"]) and loaded.get_id(run["file"][3]) == 3

@@ -13,6 +13,7 @@ class Vocab(object):
     def __init__(self, vocab_file=None, tokens=None):
         self._tok2id = {}
         self._id2tok = []
+        self._count = {}
         for t in (PAD, UNK, EOS):
             self.insert(t)
         if vocab_file is not None:
@@ -26,6 +27,18 @@ class Vocab(object):
         if token not in self._tok2id:
             self._tok2id[token] = len(self._id2tok)
             self._id2tok.append(token)
+            self._count[token] = 0
+        self._count[token] += 1
+
+    def sort_vocab(self):
+        """Most frequent first behind the three specials (vocab.py:54-62; Python's sort is stable, so equally
+        frequent tokens keep their order of first appearance, as in the reference)."""
+        ranked = sorted(self._count.items(), key=lambda x: -x[1])
+        self._tok2id, self._id2tok = {}, []
+        for t in (PAD, UNK, EOS):
+            self.insert(t)
+        for tok, _ in ranked:
+            self.insert(tok)
 
     def load_vocab(self, vocab_file):
         with open(vocab_file, "r") as f:
@@ -68,3 +81,26 @@ class Vocab(object):
     @staticmethod
     def eos():
         return 2
+
+
+def main(argv=None):
+    """`python -m zero_b200.vocab [--size N] corpus vocab_file` (vocab.py:86-103): count, sort, save."""
+    import argparse
+    ap = argparse.ArgumentParser("Vocabulary Preparison")
+    ap.add_argument("--size", type=int, default=10 ** 6, help="maximum vocabulary size")
+    ap.add_argument("input", type=str, help="the input file path")
+    ap.add_argument("output", type=str, help="the output file name")
+    a = ap.parse_args(argv)
+    vocab = Vocab()
+    with open(a.input, "r") as reader:
+        for line in reader:
+            for token in line.strip().split():
+                vocab.insert(token)
+    vocab.sort_vocab()
+    vocab.save_vocab(a.output, a.size)
+    print("Loading {} tokens from {}".format(vocab.size(), a.input))
+    return vocab
+
+
+if __name__ == "__main__":
+    main()
