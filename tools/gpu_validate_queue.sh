@@ -21,9 +21,9 @@ done
   ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
   ZB_BEAM_PARTS=1 ZB_GEMM_BM64=1 ZB_DECODE_FUSED_SMALL=1 timeout 60 python tools/decode_ab.py
 } > gpurun_out/${tag}_decode_ab.jsonl 2> gpurun_out/${tag}_decode_ab.err
-# training step with / without the tcgen05 attention forward (only if its parity test passed)
+# training bench: the default first (the baseline of every A/B below), then each switch whose parity test passed
+timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_default.json 2>/dev/null
 if grep -q "=== attention_tcgen05 rc=0" gpurun_out/${tag}_tests_unvalidated.log; then
-  timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_default.json 2>/dev/null
   ZB_ATTN_TC=1 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_attn_tc.json 2>/dev/null
   cut -c1-200 gpurun_out/${tag}_bench_default.json gpurun_out/${tag}_bench_attn_tc.json
 fi
@@ -68,3 +68,4 @@ for l in open("gpurun_out/${tag}_decode_ab.jsonl"):
         print("bad line", l[:100])
 PY
 tail -3 gpurun_out/${tag}_decode_ab.err
+python tools/summarize_queue.py ${tag}
