@@ -765,6 +765,10 @@ class Engine(object):
     @staticmethod
     def _prep_ids(ids, device, compact=True):
         ids = torch.as_tensor(ids)
+        if compact and ids.device.type == "cpu":
+            # host-resident ids (the data pipeline's pinned batches): drop the all-pad columns before the copy — the
+            # same result without the device -> host round trip compact_columns needs for a device tensor
+            ids, compact = compact_columns(ids), False
         if ids.device != device:
             ids = ids.to(device, non_blocking=True)
         ids = ids.to(torch.int32)
