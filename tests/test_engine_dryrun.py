@@ -155,3 +155,33 @@ def test_vocabulary_sizes_need_not_be_multiples_of_8(family, monkeypatch):
     logits, state = eng.decoding_fn(torch.zeros(8, 1, dtype=torch.int32), state, 0)
     assert tuple(logits.shape) == (8, 205) and logits.is_contiguous()
     assert tuple(eng.score(src, tgt).shape) == (4,)
+
+
+def test_workspace_footprint_is_the_largest_batch_not_the_sum_of_shapes(monkeypatch):
+    """Token-budget batching gives a new (B, S, T) almost every step (data.py:67-117): the planned buffers must be
+    reused across shapes.  Static addresses per name for a repeated shape (CUDA graphs), growth only for a larger
+    batch, and a generation counter that tells graph holders when an allocation they point into was replaced."""
+    import zero_b200.engine as E
+    ws = E.Workspace(torch.device("cpu"))
+    a = ws.get("x", (4, 8))
+    assert tuple(a.shape) == (4, 8) and a.is_contiguous() and a.dtype == torch.bfloat16
+    assert ws.get("x", (4, 8)).data_ptr() == a.data_ptr() and ws.get("x", (2, 16)).data_ptr() == a.data_ptr()
+    assert ws.get("x", (3, 5)).data_ptr() == a.data_ptr()              # smaller: a view of the same storage
+    assert ws.get("x", (4, 8), torch.float32).data_ptr() != a.data_ptr()   # one pool per (name, dtype)
+    before, gen = ws.nbytes(), ws.generation
+    assert gen == 0                                                    # first allocations do not count
+    b = ws.get("x", (8, 8))                                            # larger: replaced, graph holders are told
+    assert b.data_ptr() != a.data_ptr() and ws.nbytes() == before + (64 - 32) * 2 and ws.generation == gen + 1
+    c = ws.get("x", (9, 8))                                            # geometric growth: room for 80 elements
+    assert ws.generation == gen + 2 and ws.get("x", (10, 8)).data_ptr() == c.data_ptr() and ws.generation == gen + 2
+    # a real schedule over many batch shapes: the footprint stops growing once the largest has been seen
+    eng, calls = _dry_engine(monkeypatch, model_name="transformer", scope_name="transformer")
+    g = torch.Generator().manual_seed(1)
+
+    def batch(b_, s_, t_):
+        return torch.randint(3, 208, (b_, s_), generator=g), torch.randint(3, 208, (b_, t_), generator=g)
+    eng.forward_backward(*batch(6, 12, 11))
+    peak = eng.ws.nbytes()
+    for shape in ((2, 5, 7), (5, 12, 3), (6, 11, 11), (3, 9, 10), (4, 12, 11), (1, 1, 1)):
+        eng.forward_backward(*batch(*shape))
+    assert eng.ws.nbytes() <= peak * 1.3, (eng.ws.nbytes(), peak)

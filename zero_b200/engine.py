@@ -289,20 +289,41 @@ class ParamStore(object):
 
 # ------------------------------------------------------------------------------------------------ workspace
 class Workspace(object):
-    """Named device buffers, allocated once per shape signature (static addresses for CUDA graphs)."""
+    """Named device buffers.  One flat allocation per (name, dtype), sized for the largest request seen so far; `get`
+    returns its leading `prod(shape)` elements viewed as `shape`.  With one batch shape (the benchmark, a captured CUDA
+    graph) that is one allocation per name at a static address, exactly as large as needed; with the reference's
+    token-budget batches — a new (B, S, T) almost every step — the footprint stays that of the largest batch instead of
+    growing with every distinct shape.  Contract: a buffer's contents are valid until the next `get` of the same name
+    (whatever its shape); callers that keep results across steps clone them.
+    `generation` counts the times an existing buffer had to be replaced by a larger one: a captured CUDA graph holds raw
+    pointers into the buffers of its generation, so whoever caches graphs drops them when the generation has moved
+    (growth is geometric, so this happens a handful of times at the start of a run and never for a fixed shape)."""
+
+    GROW = 1.25
 
     def __init__(self, device):
         self.device = device
-        self.bufs = {}
+        self.pool = {}          # (name, dtype) -> flat tensor
+        self.generation = 0
 
     def get(self, name, shape, dtype=bf16, zero=False):
-        key = (name, tuple(shape), dtype)
-        t = self.bufs.get(key)
-        if t is None:
-            t = torch.zeros(shape, dtype=dtype, device=self.device) if zero else \
-                torch.empty(shape, dtype=dtype, device=self.device)
-            self.bufs[key] = t
-        return t
+        n = 1
+        for s in shape:
+            n *= int(s)
+        key = (name, dtype)
+        flat = self.pool.get(key)
+        if flat is None or flat.numel() < n:
+            cap = n
+            if flat is not None:
+                cap = max(n, int(flat.numel() * self.GROW))
+                self.generation += 1
+            flat = torch.zeros(max(cap, 1), dtype=dtype, device=self.device) if zero else \
+                torch.empty(max(cap, 1), dtype=dtype, device=self.device)
+            self.pool[key] = flat
+        return flat[:n].view(tuple(shape))
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.pool.values())
 
 
 def dropout_site(name):

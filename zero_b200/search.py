@@ -168,6 +168,12 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     use_graph = own and bool(getattr(params, "decode_graph", True))
     graphs = eng.__dict__.setdefault("_decode_graphs", {})
     seen = eng.__dict__.setdefault("_decode_seen", {})
+    if eng.__dict__.get("_decode_graphs_gen", 0) != eng.ws.generation:
+        # the encoder pass / begin_search above (or an earlier, larger batch) replaced a workspace buffer by a larger
+        # one: the captured steps point into the old allocation
+        graphs.clear()
+        seen.clear()
+        eng.__dict__["_decode_graphs_gen"] = eng.ws.generation
 
     def run_step(t):
         nonlocal state

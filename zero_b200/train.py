@@ -58,6 +58,7 @@ class Trainer(object):
         self.lr_schedule = lr_schedule
         self.use_graph = use_graph
         self._graphs = {}
+        self._graphs_gen = engine.ws.generation
         self._micro = 0
         self._pending = None
         # opt-in (ZB_SHARD_OPT=1; =p2p: without the multicast mappings): gradient aggregation + Adam + refresh of every
@@ -96,6 +97,10 @@ class Trainer(object):
         eng.advance_dropout_seed()
         key = (tuple(source.shape), tuple(target.shape), bool(zero_grad))
         graphable = self.use_graph and source.shape[0] > 0      # an empty tower launches nothing (engine guard)
+        if self._graphs_gen != eng.ws.generation:
+            # a workspace buffer was replaced by a larger one since the capture: the graphs' pointers are stale
+            self._graphs.clear()
+            self._graphs_gen = eng.ws.generation
         entry = self._graphs.get(key) if graphable else None
         if graphable and entry is None and len(self._graphs) < self.MAX_GRAPHS:
             s_src = torch.empty(source.shape, dtype=torch.int32, device=eng.device)
@@ -113,6 +118,11 @@ class Trainer(object):
             torch.cuda.synchronize()
             if keep is not None:
                 eng.ps.grad.copy_(keep)
+            if self._graphs_gen != eng.ws.generation:
+                # the warm-up grew a workspace buffer: graphs captured for earlier (smaller) batches point into the
+                # allocation it replaced
+                self._graphs.clear()
+                self._graphs_gen = eng.ws.generation
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 loss = eng.forward_backward_decoder(s_src, s_tgt, zero_grad=zero_grad, compact=False)
