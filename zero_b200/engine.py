@@ -305,12 +305,14 @@ class Workspace(object):
         self.device = device
         self.pool = {}          # (name, dtype) -> flat tensor
         self.generation = 0
+        self.shared = os.environ.get("ZB_WS_POOL", "1") != "0"
 
     def get(self, name, shape, dtype=bf16, zero=False):
         n = 1
         for s in shape:
             n *= int(s)
-        key = (name, dtype)
+        # ZB_WS_POOL=0 (debugging aid): one allocation per distinct shape, nothing shared between shapes
+        key = (name, dtype) if self.shared else (name, dtype, tuple(int(s) for s in shape))
         flat = self.pool.get(key)
         if flat is None or flat.numel() < n:
             cap = n
