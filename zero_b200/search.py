@@ -133,6 +133,13 @@ class BeamState(object):
         return {"seq": seq[:, :, 1:].clone(), "score": score.clone()}
 
 
+# Captured decode steps kept per engine (one graph per batch shape and step index); past this many, further shapes run
+# their steps eagerly.  A dev set decoded at every evaluation repeats its batch shapes, so its steps are all captured
+# after the second evaluation; a one-off test set never reaches the second visit a capture needs.
+MAX_DECODE_GRAPHS = 8192
+MAX_BEAM_STATES = 256
+
+
 def beam_search(features, encoding_fn, decoding_fn, params):
     """Drop-in for reference search.beam_search (search.py:19).  `encoding_fn(source) -> state`,
     `decoding_fn(target [B*beam,1], state, time) -> (logits fp32 [B*beam,V], state)` as returned by
@@ -156,6 +163,8 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         st = BeamState(B, K, state.vocab, src, params.decode_length, params.decode_alpha,
                        getattr(params, "beam_search_temperature", 1.0), getattr(params, "dtype_inf", 1e8), dev,
                        eos_id=params.tgt_vocab.eos(), pad_id=params.tgt_vocab.pad(), cap=cap)
+        if len(cache) >= MAX_BEAM_STATES:       # bookkeeping buffers of batch shapes not seen for the longest time
+            cache.pop(next(iter(cache)))
         cache[key] = st
         st.noise_seed.fill_(int(getattr(params, "random_seed", 1234)))
     else:
@@ -196,7 +205,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         if g is not None:
             g.replay()
             state.swap_buffers()
-        elif use_graph and seen.get(gkey):
+        elif use_graph and seen.get(gkey) and len(graphs) < MAX_DECODE_GRAPHS:
             # second visit: every workspace buffer exists, capture this step (capture does not execute it)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
