@@ -163,8 +163,13 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         st = BeamState(B, K, state.vocab, src, params.decode_length, params.decode_alpha,
                        getattr(params, "beam_search_temperature", 1.0), getattr(params, "dtype_inf", 1e8), dev,
                        eos_id=params.tgt_vocab.eos(), pad_id=params.tgt_vocab.pad(), cap=cap)
-        if len(cache) >= MAX_BEAM_STATES:       # bookkeeping buffers of batch shapes not seen for the longest time
-            cache.pop(next(iter(cache)))
+        if len(cache) >= MAX_BEAM_STATES:
+            # drop the oldest batch shape's bookkeeping buffers — and the captured steps that point into them
+            old = next(iter(cache))
+            cache.pop(old)
+            for store in (eng.__dict__.get("_decode_graphs", {}), eng.__dict__.get("_decode_seen", {})):
+                for gk in [gk for gk in store if gk[:len(old)] == old]:
+                    del store[gk]
         cache[key] = st
         st.noise_seed.fill_(int(getattr(params, "random_seed", 1234)))
     else:
