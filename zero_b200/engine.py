@@ -97,6 +97,7 @@ class ParamStore(object):
         self.device = device
         self.slots = OrderedDict()     # engine tensor name -> (offset, shape)
         self.alias = {}                # engine tensor name -> (parent slot, slicer): a strided window of another slot
+        self._wc, self._pc, self._gc = {}, {}, {}   # name -> (arena, view) of the compute copy / master / gradient
         self.tf_views = OrderedDict()  # TF variable name -> (engine name, slicer)
         self._plan()
         n = self.total
@@ -217,14 +218,23 @@ class ParamStore(object):
             n *= s
         return arena[off:off + n].view(shape)
 
+    # The step asks for ~500 parameter views; building one (slice + view) costs a few microseconds of Python, which adds
+    # up to milliseconds per eager step, so w / p / g remember theirs.  An entry is tied to the arena OBJECT it was
+    # taken from: rebinding an arena (the sharded optimizer step moves them into symmetric memory) refreshes it.
+    def _cached(self, cache, arena, name):
+        hit = cache.get(name)
+        if hit is None or hit[0] is not arena:
+            hit = cache[name] = (arena, self._view(arena, name))
+        return hit[1]
+
     def w(self, name):      # bf16 compute copy
-        return self._view(self.mirror, name)
+        return self._cached(self._wc, self.mirror, name)
 
     def p(self, name):      # fp32 master
-        return self._view(self.master, name)
+        return self._cached(self._pc, self.master, name)
 
     def g(self, name):      # fp32 gradient
-        return self._view(self.grad, name)
+        return self._cached(self._gc, self.grad, name)
 
     def tf_names(self):
         return list(self.tf_views.keys())
@@ -304,6 +314,7 @@ class Workspace(object):
     def __init__(self, device):
         self.device = device
         self.pool = {}          # (name, dtype) -> flat tensor
+        self.views = {}         # ((name, dtype), shape) -> view of the flat tensor
         self.generation = 0
         self.shared = os.environ.get("ZB_WS_POOL", "1") != "0"
 
@@ -319,10 +330,18 @@ class Workspace(object):
             if flat is not None:
                 cap = max(n, int(flat.numel() * self.GROW))
                 self.generation += 1
+                self.views = {k: v for k, v in self.views.items() if k[0] != key}   # they alias the old allocation
             flat = torch.zeros(max(cap, 1), dtype=dtype, device=self.device) if zero else \
                 torch.empty(max(cap, 1), dtype=dtype, device=self.device)
             self.pool[key] = flat
-        return flat[:n].view(tuple(shape))
+        # the view itself is remembered per shape (hundreds of requests per step, a few microseconds each to rebuild)
+        vkey = (key, shape if type(shape) is tuple else tuple(shape))
+        view = self.views.get(vkey)
+        if view is None:
+            if len(self.views) > 65536:
+                self.views.clear()
+            view = self.views[vkey] = flat[:n].view(vkey[1])
+        return view
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.pool.values())
