@@ -186,3 +186,15 @@ def test_pretrained_model_is_loaded_by_name_before_the_run_starts(tmp_path, host
     assert any("Total trainable variables size" in m for m in logs)
     assert any("Trying restore pretrained parameters" in m for m in logs)
     plugins.reset_engines()
+
+
+def test_bucketed_padding_for_graph_replay():
+    """ZB_GRAPH_BUCKET: columns are zero-padded to a multiple, rows and contents untouched."""
+    from zero_b200.train import Trainer
+    x = torch.arange(1, 13).view(3, 4)
+    assert Trainer.bucketed(x, 0) is x and Trainer.bucketed(x, 4) is x
+    y = Trainer.bucketed(x, 8)
+    assert tuple(y.shape) == (3, 8) and torch.equal(y[:, :4], x) and int(y[:, 4:].abs().sum()) == 0
+    assert y.dtype == x.dtype
+    shapes = {tuple(Trainer.bucketed(torch.ones(2, n, dtype=torch.int32), 8).shape) for n in range(1, 65)}
+    assert shapes == {(2, 8 * k) for k in range(1, 9)}

@@ -8,7 +8,7 @@ t0=$SECONDS
 timeout 120 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$? in $((SECONDS-t0)) s" >> gpurun_out/${tag}_tests.log
 # one process per group: a kernel that traps (every mbarrier wait is bounded) poisons its CUDA context, not the others
 : > gpurun_out/${tag}_tests_unvalidated.log
-for grp in beam_part gemm_bm64 fused_small opt_in_decode attention_tcgen05 batched_memory "gumbel or noise_beam" "shard_adam_kernel or shard_adam_rejects" vocabulary_size; do
+for grp in beam_part gemm_bm64 fused_small opt_in_decode attention_tcgen05 batched_memory "gumbel or noise_beam" "shard_adam_kernel or shard_adam_rejects" vocabulary_size bucketed_graph; do
   t0=$SECONDS
   echo "=== $grp" >> gpurun_out/${tag}_tests_unvalidated.log
   ZB_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests -m gpu -q -k "$grp" >> gpurun_out/${tag}_tests_unvalidated.log 2>&1

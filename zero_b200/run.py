@@ -121,7 +121,8 @@ def run(mode, params, log=print):
         dev = dataset(params.src_dev_file, params.src_dev_file, params.eval_max_len) if params.src_dev_file else None
         refs = _refs(params.tgt_dev_file) if params.tgt_dev_file else None
         return graph.train(params, dataset(params.src_train_file, params.tgt_train_file, params.max_len), dev, refs,
-                           world_size=world, rank=rank, log=log)
+                           world_size=world, rank=rank, log=log,
+                           use_graph=os.environ.get("ZB_TRAIN_GRAPH", "0") == "1")
     if mode in ("test", "score"):
         restore_for_eval(params, log)
     if mode == "test":

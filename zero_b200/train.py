@@ -35,6 +35,22 @@ class Trainer(object):
 
     MAX_GRAPHS = 24   # captured (shape, zero_grad) variants kept; further shapes run eagerly
 
+    @staticmethod
+    def bucketed(ids, multiple):
+        """`ids` [B, L] zero-padded on the right to the next multiple of `multiple` columns (pad id 0: masked keys,
+        zero-weight targets — the result of the step does not change, models/transformer.py:16,208-210).  Token-budget
+        batches then fall into a few dozen (S, T) classes per batch size instead of a new shape every step, which is
+        what lets captured graphs be replayed (opt-in: ZB_GRAPH_BUCKET=8 with use_graph)."""
+        if multiple <= 1:
+            return ids
+        cols = ids.shape[1]
+        want = (cols + multiple - 1) // multiple * multiple
+        if want == cols:
+            return ids
+        out = ids.new_zeros((ids.shape[0], want))
+        out[:, :cols] = ids
+        return out
+
     def __init__(self, engine: Engine, hp, world_size=1, use_graph=False, side_stream=True, lr_schedule=None,
                  early_adam=False, shard_transport=None):
         self.eng = engine
@@ -59,6 +75,9 @@ class Trainer(object):
         self.use_graph = use_graph
         self._graphs = {}
         self._graphs_gen = engine.ws.generation
+        self.bucket = int(os.environ.get("ZB_GRAPH_BUCKET", "0") or 0)
+        if self.bucket > 1:
+            self.MAX_GRAPHS = 512      # the workspace is shared between shapes: a captured shape costs no buffers
         self._micro = 0
         self._pending = None
         # opt-in (ZB_SHARD_OPT=1; =p2p: without the multicast mappings): gradient aggregation + Adam + refresh of every
@@ -95,6 +114,9 @@ class Trainer(object):
         """Runs phase 1 (forward + decoder backward) and returns (loss, phase-2 callable)."""
         eng = self.eng
         eng.advance_dropout_seed()
+        if self.use_graph and self.bucket > 1:
+            source, target = self.bucketed(torch.as_tensor(source), self.bucket), \
+                self.bucketed(torch.as_tensor(target), self.bucket)
         key = (tuple(source.shape), tuple(target.shape), bool(zero_grad))
         graphable = self.use_graph and source.shape[0] > 0      # an empty tower launches nothing (engine guard)
         if self._graphs_gen != eng.ws.generation:
