@@ -48,7 +48,7 @@ def evaluate(params, dataset, references=None, log=_log, world_size=1, rank=0):
 def _recorder(params):
     """The training record (utils/recorder.py; fields of run.py:276-296): the one run.py restored from record.json,
     else a fresh in-memory one."""
-    rec = params.recorder if "recorder" in params else None
+    rec = getattr(params, "recorder", None)
     if rec is None:
         rec = ckpt.Recorder()
         rec.bad_counter, rec.estop, rec.lidx, rec.step, rec.epoch = 0, False, -1, 0, 1
