@@ -185,3 +185,31 @@ def test_workspace_footprint_is_the_largest_batch_not_the_sum_of_shapes(monkeypa
     for shape in ((2, 5, 7), (5, 12, 3), (6, 11, 11), (3, 9, 10), (4, 12, 11), (1, 1, 1)):
         eng.forward_backward(*batch(*shape))
     assert eng.ws.nbytes() <= peak * 1.3, (eng.ws.nbytes(), peak)
+
+
+@pytest.mark.parametrize("family", FAMILIES, ids=lambda f: f["model_name"] + ("+ffn" if f.get("use_ffn") else ""))
+def test_fixed_shapes_never_replace_a_workspace_buffer(family, monkeypatch):
+    """Captured CUDA graphs are dropped when the workspace generation moves, so a fixed batch shape must never move it:
+    no buffer name is requested with a growing shape along the decode steps, across searches, or across training /
+    scoring steps of the same shape."""
+    eng, calls = _dry_engine(monkeypatch, **family)
+    src, tgt = _batch()
+    for _ in range(2):
+        state = eng.encoding_fn(src)
+        state.begin_search(2, cap=12)
+        tok = torch.zeros(8, 1, dtype=torch.int32)
+        for t in range(8):
+            _, state = eng.decoding_fn(tok, state, t)
+            state.reorder(torch.arange(8, dtype=torch.int32), t)
+    for _ in range(2):
+        eng.forward_backward(src, tgt)
+        eng.score(src, tgt)
+    assert eng.ws.generation == 0
+    # a larger batch does move it (and only then)
+    big = torch.cat([src, src]), torch.cat([tgt, tgt])
+    eng.forward_backward(*big)
+    assert eng.ws.generation > 0
+    g = eng.ws.generation
+    eng.forward_backward(src, tgt)
+    eng.forward_backward(*big)
+    assert eng.ws.generation == g
