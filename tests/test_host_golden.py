@@ -163,3 +163,23 @@ def test_vocabulary_builder_matches_reference(tmp_path):
         assert v.size() == run["vocab_size"]
         loaded = vocab.Vocab(str(out))
         assert loaded.size() == len(run["file"]) and loaded.get_id(run["file"][3]) == 3
+
+
+def test_plugin_registry_keeps_the_reference_surface():
+    """models/model.py:14-41: lower-cased names, duplicate registration and unknown names raise Exception with the
+    reference's messages, ModelWrapper exposes train_fn / score_fn / infer_fn."""
+    import zero_b200.models  # noqa: F401  (registers the five Transformer plugins)
+    from zero_b200.models import model
+    assert {"transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse"} <= \
+        set(model._total_models)
+    w = model.get_model("Transformer_AAN")
+    assert w._fields == ("train_fn", "score_fn", "infer_fn") and callable(w.train_fn) and callable(w.infer_fn)
+    with pytest.raises(Exception, match="Conflict Model Name: transformer"):
+        model.model_register("TRANSFORMER", None, None, None)
+    with pytest.raises(Exception, match="No supported model rnnsearch"):
+        model.get_model("RNNsearch")
+    f = lambda *a: None      # noqa: E731
+    try:
+        assert model.model_register("Zb_Test_Plugin", f, f, f) is model.get_model("zb_test_plugin")
+    finally:
+        model._total_models.pop("zb_test_plugin", None)

@@ -84,21 +84,23 @@ class Vocab(object):
 
 
 def main(argv=None):
-    """`python -m zero_b200.vocab [--size N] corpus vocab_file` (vocab.py:86-103): count, sort, save."""
+    """`python -m zero_b200.vocab [--size N] corpus vocab_file`: the command-line form of the reference's vocabulary
+    builder (vocab.py:86-103) — count the whitespace tokens of `corpus`, order them by frequency behind the three
+    specials, write at most N entries, one per line."""
     import argparse
-    ap = argparse.ArgumentParser("Vocabulary Preparison")
-    ap.add_argument("--size", type=int, default=10 ** 6, help="maximum vocabulary size")
-    ap.add_argument("input", type=str, help="the input file path")
-    ap.add_argument("output", type=str, help="the output file name")
-    a = ap.parse_args(argv)
+    cli = argparse.ArgumentParser(prog="zero_b200.vocab", description="build a vocabulary file from a tokenised corpus")
+    cli.add_argument("--size", type=int, default=10 ** 6, help="keep at most this many entries (specials included)")
+    cli.add_argument("input", help="tokenised text, one sentence per line")
+    cli.add_argument("output", help="vocabulary file to write")
+    opt = cli.parse_args(argv)
     vocab = Vocab()
-    with open(a.input, "r") as reader:
-        for line in reader:
-            for token in line.strip().split():
-                vocab.insert(token)
+    with open(opt.input, "r") as corpus:
+        for sentence in corpus:
+            for word in sentence.split():
+                vocab.insert(word)
     vocab.sort_vocab()
-    vocab.save_vocab(a.output, a.size)
-    print("Loading {} tokens from {}".format(vocab.size(), a.input))
+    vocab.save_vocab(opt.output, opt.size)
+    print("%d distinct tokens (specials included) in %s -> %s" % (vocab.size(), opt.input, opt.output))
     return vocab
 
 
