@@ -198,3 +198,65 @@ def test_bucketed_padding_for_graph_replay():
     assert y.dtype == x.dtype
     shapes = {tuple(Trainer.bucketed(torch.ones(2, n, dtype=torch.int32), 8).shape) for n in range(1, 65)}
     assert shapes == {(2, 8 * k) for k in range(1, 9)}
+
+
+def test_run_builds_dev_test_score_datasets_in_sentence_batches(tmp_path, monkeypatch):
+    """main.py:148-151, 477-480: whatever `batch_or_token` says for training, the dev / test / score datasets count
+    their batches in sentences — with 'token' a dev batch must still hold eval_batch_size sentences."""
+    from zero_b200 import run as R
+    from zero_b200.params import global_params
+    words = ["w%d" % i for i in range(29)]
+    vocab = tmp_path / "vocab.txt"
+    vocab.write_text("\n".join(["<pad>", "<unk>", "<eos>"] + words) + "\n")
+    lines = [" ".join(words[(i + j) % 29] for j in range(3 + i % 5)) for i in range(40)]
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(lines) + "\n")
+    p = global_params()
+    p.override_from_dict(dict(src_vocab_file=str(vocab), tgt_vocab_file=str(vocab), src_train_file=str(corpus),
+                              tgt_train_file=str(corpus), src_dev_file=str(corpus), tgt_dev_file=str(corpus),
+                              src_test_file=str(corpus), tgt_test_file=str(corpus), batch_or_token="token",
+                              token_size=64, eval_batch_size=8, output_dir=str(tmp_path / "out"), test_output=""))
+    seen = {}
+
+    def fake_train(params, train_ds, dev_ds, refs, **kw):
+        seen["train"], seen["dev"] = train_ds, dev_ds
+        return {}
+
+    def fake_evaluate(params, ds, refs, **kw):
+        seen["test"] = ds
+        return {"translations": [], "scores": [], "bleu": 0.0}
+
+    monkeypatch.setattr(R.graph, "train", fake_train)
+    monkeypatch.setattr(R.graph, "evaluate", fake_evaluate)
+    monkeypatch.setattr(R, "restore_for_eval", lambda params, log=print: False)
+    R.run("train", p, log=lambda *a: None)
+    R.run("test", p, log=lambda *a: None)
+    assert seen["train"].batch_or_token == "token"
+    for which in ("dev", "test"):
+        ds = seen[which]
+        assert ds.batch_or_token == "batch"
+        sizes = [len(b["src"]) for b in ds.batcher(p.eval_batch_size, buffer_size=1000, shuffle=False, train=False)]
+        assert sizes and max(sizes) == 8 and sum(sizes) == 40 and all(s == 8 for s in sizes[:-1]), sizes
+
+
+def test_saver_resumes_best_score_writes_atomically_and_best_dir_is_self_contained(tmp_path, host_only):
+    from zero_b200 import saver
+    p = _params(tmp_path)
+    eng = _engine_for(p)
+    out = tmp_path / "model"
+    saver.save_parameters(p, str(out))
+    sv = saver.Saver(checkpoints=2, output_dir=str(out), best_checkpoints=1)
+    sv.save(eng, 1, metric_score=11.5)
+    sv.save(eng, 2, metric_score=9.0)
+    assert sv.best_score == 11.5
+    # no temporary files are left behind, and best/ carries what a model directory needs
+    assert not [f for f in os.listdir(out) if ".tmp" in f]
+    best = os.listdir(out / "best")
+    assert "model-1.npz" in best and "param.json" in best and "metric.log" in best and "checkpoint.json" in best
+    assert saver.resolve_checkpoint(str(out / "best")).endswith("model-1.npz")
+    # a resumed run starts from the best score reached so far
+    assert saver.Saver(checkpoints=2, output_dir=str(out)).best_score == 11.5
+    # read-only use (test / score modes) creates nothing
+    ro = tmp_path / "nothing_here"
+    saver.Saver(output_dir=str(ro), readonly=True)
+    assert not ro.exists()

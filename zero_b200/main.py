@@ -138,6 +138,11 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
             if not trainer.cycle_ready():
                 continue                                        # collect_op: accumulate, no update (main.py:300-302)
             loss_t = trainer.cycle_loss() if trainer.cycle > 1 else loss_t
+            if world_size > 1:
+                # the reference's loss is the tower average inside one process (main.py:42); every rank must take the
+                # SAME skip / stop decision below, so the decision is made on the all-reduced loss (a non-finite
+                # value on any rank makes the mean non-finite everywhere)
+                loss_t = trainer.mean_over_ranks(loss_t)
             if params.safe_nan:
                 loss, gnorm = float(loss_t.item()), trainer.gradient_norm(before_apply=True)
                 if not (math.isfinite(loss) and math.isfinite(gnorm)) or gnorm > params.gnorm_upper_bound:
@@ -194,8 +199,7 @@ def train(params, train_dataset, dev_dataset=None, dev_references=None, world_si
                 schedule.after_eval(float(bleu))
                 if state["estop"]:
                     break
-            if getattr(params, "sample_freq", 0) and dev_dataset is not None and gstep > 0 \
-                    and gstep % params.sample_freq == 0:
+            if getattr(params, "sample_freq", 0) and gstep > 0 and gstep % params.sample_freq == 0:
                 _sample(params, data, log)                      # main.py:406-422
             if gstep >= params.max_training_steps:
                 state["estop"] = rec.estop = True

@@ -64,13 +64,16 @@ def restore_for_eval(params, log=print):
     initial values, as tf.global_variables_initializer leaves them in the reference."""
     from .models.transformer import get_engine
     eng = get_engine(params)
-    if not getattr(params, "output_dir", ""):
-        return False
-    log("Trying restore existing parameters")
-    ok = saver.Saver(checkpoints=params.checkpoints, output_dir=params.output_dir).restore(
-        eng, use_ema=float(getattr(params, "ema_decay", -1.0)) > 0.0)
+    out = getattr(params, "output_dir", "")
+    ok = False
+    if out and os.path.isdir(out):
+        log("Trying restore existing parameters")
+        ok = saver.Saver(checkpoints=params.checkpoints, output_dir=out, readonly=True).restore(
+            eng, use_ema=float(getattr(params, "ema_decay", -1.0)) > 0.0)
     if ok:
-        log("Restored parameters from %s" % params.output_dir)
+        log("Restored parameters from %s" % out)
+    else:   # utils/saver.py:118 logs the same situation and carries on with the initial values
+        log("WARNING: No Existing Model detected in %r: evaluating the randomly initialised model" % out)
     return ok
 
 
@@ -110,15 +113,17 @@ def run(mode, params, log=print):
     log("End Loading Vocabulary, Source Vocab Size %d, Target Vocab Size %d, within %.3f seconds" % (
         params.src_vocab.size(), params.tgt_vocab.size(), time.time() - t0))
 
-    def dataset(src, tgt, max_len):
-        return Dataset(src, tgt, params.src_vocab, params.tgt_vocab, max_len, params.batch_or_token,
-                       params.data_leak_ratio)
+    def dataset(src, tgt, max_len, batch_or_token=None):
+        return Dataset(src, tgt, params.src_vocab, params.tgt_vocab, max_len,
+                       batch_or_token or params.batch_or_token, params.data_leak_ratio)
 
     if mode == "train":
         if rank == 0:
             saver.save_parameters(params, params.output_dir)
         params = saver.setup_recorder(params)
-        dev = dataset(params.src_dev_file, params.src_dev_file, params.eval_max_len) if params.src_dev_file else None
+        # dev / test / score batches are counted in sentences whatever the training mode (main.py:148-151, 477-480)
+        dev = dataset(params.src_dev_file, params.src_dev_file, params.eval_max_len, "batch") \
+            if params.src_dev_file else None
         refs = _refs(params.tgt_dev_file) if params.tgt_dev_file else None
         return graph.train(params, dataset(params.src_train_file, params.tgt_train_file, params.max_len), dev, refs,
                            world_size=world, rank=rank, log=log,
@@ -127,7 +132,7 @@ def run(mode, params, log=print):
         restore_for_eval(params, log)
     if mode == "test":
         from . import evalu
-        test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len)
+        test = dataset(params.src_test_file, params.src_test_file, params.eval_max_len, "batch")
         res = graph.evaluate(params, test, _refs(params.tgt_test_file) if params.tgt_test_file else None, log=log,
                              world_size=world, rank=rank)
         if params.test_output and rank == 0:
@@ -136,7 +141,7 @@ def run(mode, params, log=print):
     if mode == "score":
         from . import evalu
         from .models import model as registry
-        ds = dataset(params.src_test_file, params.tgt_test_file, params.eval_max_len)
+        ds = dataset(params.src_test_file, params.tgt_test_file, params.eval_max_len, "batch")
         scores, ppl = evalu.scoring(registry.get_model(params.model_name).score_fn, ds, params)
         log("Scores %.4f, PPL %.4f" % (float(np.mean(scores)), ppl))
         if params.test_output and rank == 0:

@@ -72,16 +72,21 @@ def load_parameters(params, output_dir):
 
 
 class Saver(object):
-    def __init__(self, checkpoints=5, output_dir=None, best_score=-1, best_checkpoints=1):
+    def __init__(self, checkpoints=5, output_dir=None, best_score=-1, best_checkpoints=1, readonly=False):
         self.output_dir = output_dir or "./output"
         self.best_dir = os.path.join(self.output_dir, "best")
         self.checkpoints, self.best_checkpoints = int(checkpoints), int(best_checkpoints)
         self.best_score = best_score
-        os.makedirs(self.best_dir, exist_ok=True)
+        if not readonly:      # test / score modes only read: they must not create directories as a side effect
+            os.makedirs(self.best_dir, exist_ok=True)
         self._index = os.path.join(self.output_dir, "checkpoint.json")
         self._meta = {"all": [], "best": []}
         if os.path.exists(self._index):
             self._meta = json.load(open(self._index))
+        if self._meta.get("best"):
+            # a resumed run continues from the best dev score reached so far (the reference re-reads
+            # best/metric.log, utils/saver.py:27-40)
+            self.best_score = max([float(s) for _, s in self._meta["best"]] + [float(best_score)])
 
     # -- state <-> arrays --------------------------------------------------------------------------------
     @staticmethod
@@ -135,7 +140,7 @@ class Saver(object):
         arrays = self.state_of(engine, trainer)
         name = "model-%d.npz" % int(step)
         path = os.path.join(self.output_dir, name)
-        np.savez(path, **arrays)
+        _atomic_savez(path, arrays)
         if name not in self._meta["all"]:
             self._meta["all"].append(name)
         while len(self._meta["all"]) > self.checkpoints:
@@ -145,7 +150,14 @@ class Saver(object):
         if metric_score is not None and self.best_checkpoints > 0:
             best = self._meta["best"]
             if len(best) < self.best_checkpoints or metric_score > min(s for _, s in best):
-                shutil.copy(path, os.path.join(self.best_dir, name))
+                shutil.copy(path, os.path.join(self.best_dir, name + ".tmp"))
+                os.replace(os.path.join(self.best_dir, name + ".tmp"), os.path.join(self.best_dir, name))
+                # best/ is usable as a model directory on its own: parameters, record and the score log go along
+                for extra in ("param.json", "record.json"):
+                    if os.path.exists(os.path.join(self.output_dir, extra)):
+                        shutil.copy(os.path.join(self.output_dir, extra), os.path.join(self.best_dir, extra))
+                with open(os.path.join(self.best_dir, "metric.log"), "a") as f:
+                    f.write("%s\t%s\n" % (name, float(metric_score)))       # utils/saver.py:88-92
                 best.append([name, float(metric_score)])
                 best.sort(key=lambda p: -p[1])
                 for old, _ in best[self.best_checkpoints:]:
@@ -153,7 +165,8 @@ class Saver(object):
                         os.remove(os.path.join(self.best_dir, old))
                 del best[self.best_checkpoints:]
                 self.best_score = best[0][1]
-        json.dump(self._meta, open(self._index, "w"))
+                _atomic_json({"all": [n for n, _ in best], "best": best}, os.path.join(self.best_dir, "checkpoint.json"))
+        _atomic_json(self._meta, self._index)
         return path
 
     def latest(self, directory=None):
@@ -170,6 +183,20 @@ class Saver(object):
         with np.load(path) as z:
             self.restore_state_dict(engine, {k: z[k] for k in z.files}, trainer, use_ema=use_ema)
         return True
+
+
+def _atomic_savez(path, arrays):
+    """Write next to the target and rename: a crash mid-write never leaves a truncated model-N.npz behind."""
+    tmp = path + ".tmp.npz"
+    np.savez(tmp, **arrays)
+    os.replace(tmp, path)
+
+
+def _atomic_json(obj, path):
+    tmp = path + ".tmp"
+    with open(tmp, "w") as f:
+        json.dump(obj, f)
+    os.replace(tmp, path)
 
 
 def resolve_checkpoint(path):

@@ -156,7 +156,11 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     B = src.shape[0]
     K = int(params.beam_size)
     cap = int(src.shape[1]) + int(params.decode_length) + 2
-    key = (B, K, state.vocab, cap, float(params.decode_alpha), int(params.decode_length), noise)
+    # Everything a captured step or the bookkeeping buffers bake in: encoding_fn compacts all-pad columns, so the
+    # memory width is state.S (NOT the padded width of `source`); temperature / inf / eos / pad are kernel arguments.
+    key = (B, K, state.vocab, cap, int(state.S), float(params.decode_alpha), int(params.decode_length), noise,
+           float(getattr(params, "beam_search_temperature", 1.0)), float(getattr(params, "dtype_inf", 1e8)),
+           int(params.tgt_vocab.eos()), int(params.tgt_vocab.pad()))
     cache = eng.__dict__.setdefault("_beam_states", {})
     st = cache.get(key)
     if st is None:
@@ -205,7 +209,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     speculate = own and os.environ.get("ZB_DECODE_SPEC", "1") != "0"
 
     def enqueue_step(t):
-        gkey = key + (int(src.shape[1]), t)
+        gkey = key + (t,)
         g = graphs.get(gkey) if use_graph else None
         if g is not None:
             g.replay()

@@ -249,6 +249,15 @@ class Trainer(object):
         """Mean loss of the finished cycle (utils/cycle.py:90-92), device tensor."""
         return self.loss_acc / float(self.cycle)
 
+    def mean_over_ranks(self, loss):
+        """The tower-averaged loss of main.py:42 (one 4-byte all-reduce): every rank sees the same value, so the
+        NaN / Inf decisions taken on it (main.py:316-332) agree across the job."""
+        if self.world <= 1:
+            return loss
+        out = loss.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        return out / float(self.world)
+
     def skip(self):
         """Drop the collected gradients without updating (safe_nan, main.py:326-330: the step is 'passed')."""
         self._pending = False
