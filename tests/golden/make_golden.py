@@ -65,13 +65,13 @@ def synth_batch(rng, batch, smax, tmax, vs, vt):
     return src, tgt
 
 
-def run(model_name, out_name=None, seed=7, **kw):
+def run(model_name, out_name=None, seed=7, shape=(5, 11, 9), **kw):
     tf.reset_default_graph(seed=1000 + seed)
     ref_dtype.set_floatx("float32")
     p = make_params(model_name, **kw)
     rng = np.random.default_rng(seed)
     vs, vt = p.src_vocab.size(), p.tgt_vocab.size()
-    src, tgt = synth_batch(rng, 5, 11, 9, vs, vt)
+    src, tgt = synth_batch(rng, shape[0], shape[1], shape[2], vs, vt)
     feats = {"source": tf.constant(src), "target": tf.constant(tgt)}
     graph = ref_model.get_model(model_name)
     init = ref_init.get_initializer(p.initializer, p.initializer_gain)
@@ -134,7 +134,7 @@ def run(model_name, out_name=None, seed=7, **kw):
         os.path.relpath(path, ROOT)))
 
 
-if __name__ == "__main__":
+def main_small():
     small = dict(hidden_size=64, embed_size=64, filter_size=128, num_heads=2)   # dh = 32
     run("transformer")                                                          # d = 128, dh = 64
     run("transformer", out_name="transformer_h4", seed=11, **dict(small, num_heads=4))  # dh = 16
@@ -143,3 +143,21 @@ if __name__ == "__main__":
     run("transformer_rpr", **small)
     run("transformer_rela", **small)
     run("transformer_fuse", **small)
+
+
+def main_long():
+    """Sequences longer than 16 tokens with dh = 64: the tensor-core attention kernels of the training step (which
+    the library only selects from 16 query rows on) run inside a reference-executed model test, masks included."""
+    long = dict(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=1,
+                num_decoder_layer=1, decode_length=8)
+    for name, model, extra in (("transformer_len40", "transformer", {}),
+                               ("transformer_rpr_len40", "transformer_rpr", dict(max_relative_position=6)),
+                               ("transformer_rela_len40", "transformer_rela", {}),
+                               ("transformer_fuse_len40", "transformer_fuse", {})):
+        run(model, out_name=name, seed=21, shape=(4, 40, 36), **dict(long, **extra))
+
+
+if __name__ == "__main__":
+    if "--long-only" not in sys.argv:
+        main_small()
+    main_long()

@@ -9,7 +9,9 @@ from zero_b200.params import HParams
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODELS = ["transformer", "transformer_h4", "transformer_aan", "transformer_aan_cumsum", "transformer_rpr",
-          "transformer_rela", "transformer_fuse"]
+          "transformer_rela", "transformer_fuse",
+          # lengths up to 40 / 36 tokens, dh = 64 (the tensor-core attention kernels of the training step)
+          "transformer_len40", "transformer_rpr_len40", "transformer_rela_len40", "transformer_fuse_len40"]
 
 
 def load_golden(name):

@@ -11,7 +11,8 @@ from tests.golden_util import load_golden
 pytestmark = pytest.mark.gpu
 
 TRAIN_MODELS = ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela", "transformer_aan",
-                "transformer_aan_cumsum", "transformer_fuse"]
+                "transformer_aan_cumsum", "transformer_fuse",
+                "transformer_len40", "transformer_rpr_len40", "transformer_rela_len40", "transformer_fuse_len40"]
 SCORE_MODELS = TRAIN_MODELS
 DECODE_MODELS = SCORE_MODELS
 
