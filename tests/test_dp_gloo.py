@@ -79,9 +79,8 @@ def test_param_store_layout_is_tma_legal_and_name_complete():
     hp = transformer_base()
     cfg = ModelConfig(hp, 32000, 32000)
     ps = ParamStore.__new__(ParamStore)
-    ps.cfg, ps.slots, ps.tf_views = cfg, {}, {}
     from collections import OrderedDict
-    ps.slots, ps.tf_views = OrderedDict(), OrderedDict()
+    ps.cfg, ps.slots, ps.alias, ps.tf_views = cfg, OrderedDict(), {}, OrderedDict()
     ps._plan()
     c = zo.Cfg(hp, 32000, 32000)
     shapes = zo.param_shapes(c)
@@ -105,6 +104,7 @@ def test_batched_memory_projection_layout(monkeypatch):
         ps.cfg, ps.slots, ps.alias, ps.tf_views = cfg, OrderedDict(), {}, OrderedDict()
         ps._plan()
         return cfg, ps
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "0")
     cfg0, ps0 = plan()
     monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "1")
     cfg1, ps1 = plan()

@@ -61,8 +61,9 @@ FAMILIES = [dict(model_name="transformer", scope_name="transformer"),
 @pytest.mark.parametrize("family", FAMILIES, ids=lambda f: f["model_name"] + ("+ffn" if f.get("use_ffn") else ""))
 @pytest.mark.parametrize("switch", [None, "ZB_BATCH_MEM_PROJ", "ZB_DECODE_FUSED_SMALL"])
 def test_schedule_runs_for_every_family_and_switch(family, switch, monkeypatch):
-    if switch:
-        monkeypatch.setenv(switch, "1")
+    # both switches are on by default since round 2; "None" is the schedule with both turned off
+    for name in ("ZB_BATCH_MEM_PROJ", "ZB_DECODE_FUSED_SMALL"):
+        monkeypatch.setenv(name, "1" if name == switch else "0")
     eng, calls = _dry_engine(monkeypatch, **family)
     src, tgt = _batch()
     loss = eng.forward_backward(src, tgt)
@@ -95,6 +96,7 @@ def test_batched_memory_projection_changes_the_launch_count(monkeypatch):
     """One memory-projection GEMM forward and one dgrad backward for all decoder layers instead of one per layer."""
     src, tgt = _batch()
     calls = _mock_ops(monkeypatch)
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "0")
     eng0 = _engine()
     del calls[:]
     eng0.forward_backward(src, tgt)

@@ -175,8 +175,6 @@ def test_checkpoint_round_trip_with_tf_variable_names(tmp_path):
     assert abs(float(tr2.step(src, tgt)[0]) - loss3) < 1e-4
 
 
-@pytest.mark.skipif(os.environ.get("ZB_TEST_UNVALIDATED") != "1",
-                    reason="path not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
 def test_bucketed_graph_training_equals_eager(monkeypatch):
     """ZB_GRAPH_BUCKET=8 + use_graph: batches of different widths are zero-padded to multiples of 8 columns and
     replayed from captured graphs (a handful of shapes instead of one per batch); losses and weights follow the
@@ -184,7 +182,9 @@ def test_bucketed_graph_training_equals_eager(monkeypatch):
     from zero_b200.engine import Engine
     from zero_b200.train import Trainer
     z, hp, variables, grads, vs, vt = load_golden("transformer")
-    hp.override_from_dict(dict(lrate=1.0, warmup_steps=10, beta1=0.9, beta2=0.98, epsilon=1e-8, clip_grad_norm=0.0,
+    # a learning rate at which the trajectory is stable: at lrate 1.0 / warmup 10 the loss bounces (2.5 -> 3.6) and the
+    # round-off differences between padded and un-padded reductions are amplified step over step (first GPU run)
+    hp.override_from_dict(dict(lrate=0.1, warmup_steps=10, beta1=0.9, beta2=0.98, epsilon=1e-8, clip_grad_norm=0.0,
                                lrate_strategy="noam"))
     src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
     widths = [(src.shape[1], tgt.shape[1]), (max(2, src.shape[1] - 2), max(2, tgt.shape[1] - 3)),

@@ -236,8 +236,6 @@ def test_full_size_properties_c5_deep_encoder_len1024():
     torch.testing.assert_close(ps[:4].clone(), ps[4:].clone(), atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
-                    reason="switches not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("switch", ["ZB_DECODE_FUSED_SMALL", "ZB_BEAM_PARTS", "ZB_GEMM_BM64"])
 def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     """transformer_aan golden model: beam search with an opt-in decode-path switch returns the same sequences as
@@ -250,6 +248,7 @@ def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     hp.add_hparam("decode_graph", False)
     eng.decode_length = hp.decode_length
     src = torch.from_numpy(z["source"])
+    monkeypatch.setenv(switch, "0")
     ref = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
     monkeypatch.setenv(switch, "1")
     got = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
@@ -257,8 +256,6 @@ def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     np.testing.assert_allclose(got["score"].cpu().numpy(), ref["score"].cpu().numpy(), rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
-                    reason="switch not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("name", ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela"])
 def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch):
     """ZB_BATCH_MEM_PROJ=1 (one GEMM for every decoder layer's k_map | v_map, one dgrad / wgrad pair backward):
@@ -266,7 +263,9 @@ def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch)
     the default layout's to bf16 round-off."""
     from zero_b200 import search
     from zero_b200.params import SimpleVocab
+    monkeypatch.setenv("ZB_BATCH_MEM_PROJ", "0")
     eng0, z, hp, variables, grads = _engine(name)
+    assert not eng0.cfg.batch_mem
     src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
     loss0 = float(eng0.forward_backward(src, tgt)[0])
     got0 = eng0.ps.grad_dict()
@@ -292,8 +291,6 @@ def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch)
     np.testing.assert_array_equal(a["seq"].cpu().numpy(), b["seq"].cpu().numpy())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
-                    reason="kernel not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
 def test_noise_beam_search_samples_reproducibly():
     """enable_noise_beam_search (search.py:143-145): Gumbel noise on the step logits.  The bookkeeping stays the
     oracle's when it is replayed on the SAME (noised) logits; a re-run from the same seed repeats the beams; the next
@@ -332,8 +329,6 @@ def test_noise_beam_search_samples_reproducibly():
     assert base["seq"].shape[0] == src.shape[0]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ZB_TEST_UNVALIDATED") != "1",
-                    reason="path not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("model", ["transformer", "transformer_aan"])
 def test_vocabulary_size_not_a_multiple_of_8_matches_oracle(model):
     """Vocabularies of 203 / 205 words (3 specials + N): loss, logits, every gradient and the per-sentence scores

@@ -1,5 +1,4 @@
-"""zb_shard_adam (csrc/shard_opt.cu) on the GPU.  Written after the round's last GPU visit: opt-in
-(ZB_TEST_UNVALIDATED=1) until a GPU run has seen it pass; the product only reaches it under ZB_SHARD_OPT=1.
+"""zb_shard_adam (csrc/shard_opt.cu) on the GPU; the product reaches it under ZB_SHARD_OPT=1.
 
 1. One device, N emulated ranks: peer pointers are just device addresses, so N gradient / mirror / master arenas on the
    same GPU exercise the whole unicast path of the kernel (reduce in rank order, Adam, bf16 + fp32 fan-out, norm
@@ -13,9 +12,7 @@ import socket
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ZB_TEST_UNVALIDATED") != "1",
-                                 reason="kernel not yet validated on a GPU (set ZB_TEST_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 f32, bf16 = torch.float32, torch.bfloat16
 

@@ -818,7 +818,8 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const char* parts_env = getenv("ZB_BEAM_PARTS");   // per call: the parity test flips it inside one process
   const int vp = (((a->vocab + kParts - 1) / kParts) + 3) & ~3;   // elements per part, 16-byte granular
-  if (a->row_ws && parts_env && parts_env[0] == '1' && (size_t)vp * sizeof(float) <= 64 * 1024) {
+  // default since the r02a A/B (decode step 0.589 -> 0.563 ms); ZB_BEAM_PARTS=0 keeps the one-CTA-per-row kernel
+  if (a->row_ws && !(parts_env && parts_env[0] == '0') && (size_t)vp * sizeof(float) <= 64 * 1024) {
     static bool part_attr = false;
     if (!part_attr) {
       cudaFuncSetAttribute(beam_part_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);

@@ -681,10 +681,11 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   if (!accum && bn == 256) {
     // wave quantisation: cost ~ (#waves of pair tiles) x (tile width); e.g. N = 1536 at M = 4096 is 96 tiles of 256
     // (2 waves of 74 pairs) but 192 tiles of 128 (3 waves of half the work each)
-    // ZB_GEMM2_TILE_MODEL=l2 (opt-in, untimed): the k-loop of these kernels runs at the L2 -> SM ingest cap, where a
-    // tile costs its operand bytes (256 + bn) * K * 2 rather than its flops (tools/gemm_l2_model.py), so a wave of
-    // 256-wide tiles costs 512 / 384 of a wave of 128-wide ones, not 2x
-    static const bool l2_model = getenv("ZB_GEMM2_TILE_MODEL") != nullptr && getenv("ZB_GEMM2_TILE_MODEL")[0] == 'l';
+    // The k-loop of these kernels runs at the L2 -> SM ingest cap, where a tile costs its operand bytes
+    // (256 + bn) * K * 2 rather than its flops (tools/gemm_l2_model.py), so a wave of 256-wide tiles costs 512 / 384
+    // of a wave of 128-wide ones, not 2x: +1.2 % tokens/s at configs[1] against the flop-weighted rule
+    // (profiles/r02a_summary.txt).  ZB_GEMM2_TILE_MODEL=flops restores the latter.
+    static const bool l2_model = !(getenv("ZB_GEMM2_TILE_MODEL") != nullptr && getenv("ZB_GEMM2_TILE_MODEL")[0] == 'f');
     const long long c256 = l2_model ? 256 + 256 : 256, c128 = l2_model ? 256 + 128 : 128;
     const long long w256 = (tiles_for(256) + pairs_hw - 1) / pairs_hw * c256;
     const long long w128 = (tiles_for(128) + pairs_hw - 1) / pairs_hw * c128;

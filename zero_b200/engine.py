@@ -74,10 +74,11 @@ class ModelConfig(object):
         known = ("transformer", "transformer_aan", "transformer_rpr", "transformer_rela", "transformer_fuse")
         if self.model not in known:
             raise L.ZeroB200Error("model %r is outside the hot path (supported: %s)" % (self.model, ", ".join(known)))
-        # opt-in (ZB_BATCH_MEM_PROJ=1, untimed): the k_map | v_map weights of ALL decoder layers live side by side in
-        # one [d, ndec * 2d] matrix, so the memory projections of a training step are ONE GEMM forward (n = ndec * 2d)
-        # and ONE dgrad / wgrad pair backward (k = ndec * 2d) instead of ndec small ones each
-        self.batch_mem = os.environ.get("ZB_BATCH_MEM_PROJ") == "1" and self.model not in (
+        # the k_map | v_map weights of ALL decoder layers live side by side in one [d, ndec * 2d] matrix, so the memory
+        # projections of a training step are ONE GEMM forward (n = ndec * 2d) and ONE dgrad / wgrad pair backward
+        # (k = ndec * 2d) instead of ndec small ones each: +1.3 % tokens/s at configs[1] (profiles/r02a_summary.txt);
+        # ZB_BATCH_MEM_PROJ=0 restores one projection per layer
+        self.batch_mem = os.environ.get("ZB_BATCH_MEM_PROJ", "1") != "0" and self.model not in (
             "transformer_aan", "transformer_fuse")
 
     rpr = property(lambda s: s.model == "transformer_rpr")

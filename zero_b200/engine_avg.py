@@ -198,7 +198,7 @@ def _decoding_fn_avg(self, target, state, time):
                   zero_if_all_pad=True, time=t)
     y = ws.get("dec.y", (R, c.d))
     ctx = ws.get("dec.ctx", (R, c.d))
-    fused_small = os.environ.get("ZB_DECODE_FUSED_SMALL") == "1"
+    fused_small = os.environ.get("ZB_DECODE_FUSED_SMALL", "1") != "0"
     for l in range(c.ndec):
         key = "dec%d" % l
         kc = key + ".cross"
