@@ -160,7 +160,9 @@ def test_checkpoint_round_trip_with_tf_variable_names(tmp_path):
         sv.save(eng, step, metric_score=[0.2, 0.5, 0.3][step - 1], trainer=tr)
     files = sorted(f for f in os.listdir(tmp_path) if f.startswith("model-"))
     assert files == ["model-2.npz", "model-3.npz"]                       # keep the newest two
-    assert os.listdir(tmp_path / "best") == ["model-2.npz"] and sv.best_score == 0.5
+    best = sorted(os.listdir(tmp_path / "best"))
+    assert [f for f in best if f.endswith(".npz")] == ["model-2.npz"] and sv.best_score == 0.5
+    assert "metric.log" in best and "checkpoint.json" in best           # best/ is a model directory of its own
     with np.load(tmp_path / "model-3.npz") as ck:
         assert set(variables) <= set(ck.files) and int(ck["global_step"]) == 3
         k = sorted(variables)[0]
