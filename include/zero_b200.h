@@ -24,7 +24,7 @@ extern "C" {
 
 typedef struct CUstream_st* zb_stream_t; /* == cudaStream_t */
 
-#define ZB_ABI_VERSION 2
+#define ZB_ABI_VERSION 3
 
 typedef enum {
   ZB_OK = 0,
@@ -52,7 +52,7 @@ typedef enum {
   ZB_PATH_BEAM_ROWS = 7,      /* beam.cu one CTA per (sentence, beam) row */
   ZB_PATH_BEAM_PARTS = 8,     /* beam.cu a 4-CTA cluster per row with a threshold pass, opt-in */
   ZB_PATH_GEMM_BM64 = 9,      /* single-CTA tcgen05 GEMM with 64-row tiles, opt-in (also counted as GEMM_TCGEN05) */
-  ZB_PATH_ATTN_TC = 10,       /* attention_mma.cu tcgen05 forward for 64-token head pairs, opt-in */
+  ZB_PATH_ATTN_TC = 10,       /* attention_tc.cu: tcgen05 / TMEM / TMA attention forward and backward (dh = 64) */
   ZB_PATH_COUNT_ = 11
 } zb_path;
 int64_t zb_path_launch_count(int32_t which);
@@ -138,9 +138,16 @@ typedef struct {
   float dropout_rate;
   uint32_t dropout_site;
   const uint64_t* dropout_seed;       /* device pointer */
+  /* caller-owned scratch of zb_attention_bwd (device, 16-byte aligned, contents undefined on return); may be NULL /
+     0, which only narrows the choice of kernels: the tcgen05 backward reduces dq of sequences longer than one
+     128-key block in fp32 there.  Size: zb_attention_bwd_workspace_bytes. */
+  void* workspace;
+  int64_t workspace_bytes;
 } zb_attention_args;
 int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream);
 int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream);
+/* bytes of `workspace` that let zb_attention_bwd use every kernel for this problem (0: none needed) */
+int64_t zb_attention_bwd_workspace_bytes(const zb_attention_args* a);
 
 /* ------------------------------------------------------------------------------------------------ K4
  * zb_add_ln_{fwd,bwd}: out = scale * (s - mean(s)) * rsqrt(var(s) + eps) + offset with s = x (+ y).

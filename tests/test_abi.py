@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), "libzero_b200.so does not export %s" % sym
     assert sorted(L.EXPORTS) == declared
     lib.zb_abi_version.restype = ctypes.c_int
-    assert lib.zb_abi_version() == 2
+    assert lib.zb_abi_version() == 3
 
 
 def test_ctypes_struct_sizes_match_header_layout():

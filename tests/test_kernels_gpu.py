@@ -621,25 +621,38 @@ def test_fused_small_decode_kernels_equal_the_unfused_pairs(rows, d):
     assert float((out2.float() - out.float()).abs().max()) <= 0.0625   # at most an ulp of bf16 at |v| < 8
 
 
-@unvalidated
-@pytest.mark.parametrize("B,h,causal,klen,fused", [(4, 8, False, True, True), (4, 8, True, False, True),
-                                                     (64, 8, False, True, True), (3, 2, True, True, False)])
-def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
-    """ZB_ATTN_TC=1: the tcgen05 forward for 64-token head pairs (S and O in TMEM, P through shared memory) against
-    the torch restatement and against the mma.sync tile kernel it replaces, reading q / k / v in place from a fused
-    [tokens, 3d] buffer (fused=True) or from separate tensors."""
+@pytest.mark.parametrize("B,h,Lq,Lk,causal,klen,fused", [
+    (4, 8, 64, 64, False, True, True),        # the 64-token training batches: two heads stacked per 128-row block
+    (4, 8, 64, 64, True, False, True),
+    (64, 8, 64, 64, False, True, True),       # BASELINE configs[1]: 256 units over the persistent grid
+    (3, 2, 64, 64, True, True, False),
+    (3, 4, 40, 33, False, True, False),       # ragged pair blocks (zero-filled rows / keys)
+    (3, 3, 40, 64, False, True, False),       # odd head count: one head per block
+    (2, 8, 128, 128, True, False, True),      # BASELINE configs[3] lengths: one 128 x 128 block per (batch, head)
+    (2, 4, 128, 128, False, True, True),
+    (2, 4, 100, 100, True, False, False),
+    (2, 2, 17, 200, False, True, False),      # cross attention over two key blocks: fp32 dq reduction
+    (2, 2, 300, 300, True, True, True),       # three blocks each way, causal block skipping
+    (1, 8, 64, 1024, False, True, False),     # BASELINE configs[4] decoder cross attention
+    (1, 2, 1024, 1024, False, True, True),    # BASELINE configs[4] encoder self attention: online softmax over 8 blocks
+])
+def test_attention_tcgen05(B, h, Lq, Lk, causal, klen, fused, monkeypatch):
+    """attention_tc.cu (the default for dh = 64): tcgen05 forward / backward against the torch restatement of
+    func.dot_attention and against the mma.sync kernels it replaced (ZB_ATTN_TC=0), reading q / k / v in place from a
+    fused [tokens, 3d] buffer (fused=True, self attention) or from separate tensors."""
     from zero_b200 import ops
     import zero_b200.lib as L
-    D, Lq = h * 64, 64
+    D = h * 64
     if fused:
+        assert Lq == Lk
         qkv = rnd(B, Lq, 3 * D, seed=41)
         q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
     else:
-        q, k, v = rnd(B, Lq, D, seed=42), rnd(B, Lq, D, seed=43), rnd(B, Lq, D, seed=44)
+        q, k, v = rnd(B, Lq, D, seed=42), rnd(B, Lk, D, seed=43), rnd(B, Lk, D, seed=44)
     key_len = None
     if klen:
-        key_len = torch.randint(1, Lq + 1, (B,), dtype=torch.int32, device=dev())
-        key_len[0] = Lq
+        key_len = torch.randint(1, Lk + 1, (B,), dtype=torch.int32, device=dev())
+        key_len[0] = Lk
     outs, lses = [], []
     for tc in ("0", "1"):
         monkeypatch.setenv("ZB_ATTN_TC", tc)
@@ -655,7 +668,6 @@ def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
     torch.testing.assert_close(outs[1].float(), ref.detach(), atol=3e-2, rtol=3e-2)
     torch.testing.assert_close(outs[1].float(), outs[0].float(), atol=2e-2, rtol=2e-2)
     torch.testing.assert_close(lses[1], lses[0], atol=1e-3, rtol=1e-3)
-    # backward: five tcgen05 MMAs per head pair against autograd and against the mma.sync tile kernel
     d_o = rnd(B, Lq, D, seed=45)
     ref.backward(d_o.float())
     grads = []
@@ -669,12 +681,52 @@ def test_attention_tcgen05_forward(B, h, causal, klen, fused, monkeypatch):
             dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
         a = ops.attention_args(q, k, v, outs[0], h, key_len=key_len, causal=causal, lse=lses[0])
         delta = torch.empty(B, h, Lq, device=dev())
-        ops.attention_bwd(a, d_o, dq, dk, dv, delta, None, None)
+        ops.attention_bwd(a, d_o, dq, dk, dv, delta, None, None,
+                          workspace=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev()))
         assert L.path_launch_count("attn_tc") == before + int(tc)
         grads.append((dq, dk, dv))
     for got, old_, want in zip(grads[1], grads[0], [t.grad for t in leaves]):
         torch.testing.assert_close(got.float(), want, atol=6e-2, rtol=5e-2)
         torch.testing.assert_close(got.float(), old_.float(), atol=4e-2, rtol=4e-2)
+    # without a workspace a multi-block backward is declined by the tcgen05 path and served by the mma.sync kernels
+    if Lk > 128:
+        monkeypatch.setenv("ZB_ATTN_TC", "1")
+        before = L.path_launch_count("attn_tc")
+        a = ops.attention_args(q, k, v, outs[0], h, key_len=key_len, causal=causal, lse=lses[0])
+        assert ops.attention_bwd_workspace_bytes(a) == B * Lq * D * 4
+        dq2, dk2, dv2 = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        ops.attention_bwd(a, d_o, dq2, dk2, dv2, torch.empty(B, h, Lq, device=dev()), None, None)
+        assert L.path_launch_count("attn_tc") == before
+        torch.testing.assert_close(dq2.float(), grads[0][0].float(), atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("B,h,Lq,Lk,causal", [(4, 8, 64, 64, True), (2, 4, 128, 128, False), (2, 2, 200, 200, True)])
+def test_attention_tcgen05_dropout_matches_the_mma_kernels(B, h, Lq, Lk, causal, monkeypatch):
+    """Attention dropout (func.py:245): the keep mask is a pure function of (seed, site, [b, h, i, j]) shared by every
+    attention kernel, so the tcgen05 path must reproduce the mma.sync path's outputs and gradients to round-off."""
+    from zero_b200 import ops
+    D = h * 64
+    q, k, v, d_o = rnd(B, Lq, D, seed=51), rnd(B, Lk, D, seed=52), rnd(B, Lk, D, seed=53), rnd(B, Lq, D, seed=54)
+    seed = torch.tensor([12345], dtype=torch.int64, device=dev())
+    res = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("ZB_ATTN_TC", tc)
+        o = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+        lse = torch.empty(B, h, Lq, device=dev())
+        a = ops.attention_args(q, k, v, o, h, causal=causal, lse=lse, dropout=(0.3, 77, seed))
+        ops.attention_fwd(a)
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        ops.attention_bwd(a, d_o, dq, dk, dv, torch.empty(B, h, Lq, device=dev()), None, None,
+                          workspace=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev()))
+        res.append((o, lse, dq, dk, dv))
+    assert float((res[0][0].float() - rnd(B, Lq, D, seed=51).float()).abs().max()) > 0   # sanity: something was computed
+    for x0, x1 in zip(res[0], res[1]):
+        torch.testing.assert_close(x1.float(), x0.float(), atol=4e-2, rtol=4e-2)
+    # ... and the mask really drops: the no-dropout output differs
+    monkeypatch.setenv("ZB_ATTN_TC", "1")
+    o2 = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+    ops.attention_fwd(ops.attention_args(q, k, v, o2, h, causal=causal, lse=torch.empty(B, h, Lq, device=dev())))
+    assert float((o2.float() - res[1][0].float()).abs().max()) > 0.05
 
 
 @unvalidated

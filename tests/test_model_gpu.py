@@ -321,7 +321,7 @@ def test_noise_beam_search_samples_reproducibly():
     for _ in range(4):                                # eager, eager (marks steps seen), captured, replayed
         runs.append(search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)["seq"].cpu())
     assert any(r.shape != runs[0].shape or not torch.equal(r, runs[0]) for r in runs[1:])     # fresh noise per search
-    st = next(v for k, v in eng.__dict__["_beam_states"].items() if k[-1] is True)
+    st = next(v for k, v in eng.__dict__["_beam_states"].items() if k[7] is True)   # key[7] = noise
     seed_now = int(st.noise_seed)
     st.noise_seed.fill_(seed_now - 1)                 # re-run the last search from its seed (add_(1) happens inside)
     again = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)["seq"].cpu()

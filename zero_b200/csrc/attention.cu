@@ -10,6 +10,10 @@ int attention_decode_fwd(const zb_attention_args* a, cudaStream_t st);
 bool attention_mma_supported(const zb_attention_args* a, bool bwd);
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st);
 int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st);
+bool attention_tc_supported(const zb_attention_args* a, bool bwd);   // attention_tc.cu (tcgen05 / TMEM / TMA)
+int attention_tc_fwd(const zb_attention_args* a, cudaStream_t st);
+int attention_tc_bwd(const zb_attention_args* a, cudaStream_t st);
+long long attention_tc_bwd_workspace_bytes(const zb_attention_args* a);
 
 static int validate(const zb_attention_args* a, bool bwd) {
   ZB_REQUIRE(a && a->q && a->k && a->v && a->o, "zb_attention: null pointer");
@@ -33,6 +37,7 @@ extern "C" int zb_attention_fwd(const zb_attention_args* a, zb_stream_t stream) 
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (attention_decode_supported(a)) return attention_decode_fwd(a, st);
+  if (attention_tc_supported(a, false)) return attention_tc_fwd(a, st);
   if (attention_mma_supported(a, false)) return attention_mma_fwd(a, st);
   return attention_generic_fwd(a, st);
 }
@@ -43,6 +48,11 @@ extern "C" int zb_attention_bwd(const zb_attention_args* a, zb_stream_t stream) 
   if (rc) return rc;
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (attention_tc_supported(a, true)) return attention_tc_bwd(a, st);
   if (attention_mma_supported(a, true)) return attention_mma_bwd(a, st);
   return attention_generic_bwd(a, st);
+}
+
+extern "C" int64_t zb_attention_bwd_workspace_bytes(const zb_attention_args* a) {
+  return zb::attention_tc_bwd_workspace_bytes(a);
 }

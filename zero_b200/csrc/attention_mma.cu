@@ -1,14 +1,14 @@
-// attention_mma.cu — K2/K3 fast path: flash-style fused attention on the warp-level tensor cores (mma.sync
-// m16n8k16 bf16 -> fp32) for the plain softmax case with dh = 64 (every attention of Transformer-base: encoder
-// self, decoder causal self, decoder cross; func.py:218-256).  Logits / probabilities live only in registers;
+// attention_mma.cu — K2/K3 on the warp-level tensor cores (mma.sync m16n8k16 bf16 -> fp32) for the plain softmax
+// case with dh = 64 (func.py:218-256).  Since round 2 the DEFAULT for these problems is attention_tc.cu (tcgen05 /
+// TMEM / TMA); this file is what ZB_ATTN_TC=0 selects (the A/B baseline) and what serves the shapes the tcgen05
+// kernels decline (unaligned views, causal with a query offset, no workspace for a multi-block backward).  Logits / probabilities live only in registers;
 // the backward recomputes them from q, k and the saved log-sum-exp.
 //   fwd : CTA = 64 query rows of one (batch, head), 4 warps x 16 rows, 64-key tiles, online softmax
 //   bwd : dq kernel (CTA per 64 queries, loops over key tiles) + dk/dv kernel (CTA per 64 keys, loops over
 //         query tiles); no atomics, deterministic
 // Shared-memory tiles are [64][64] bf16 with a 16-byte-chunk XOR swizzle (chunk ^= row & 7) so ldmatrix is
 // bank-conflict free.  Masks come from key lengths / causal index (func.attention_bias, func.py:372-388) with the
-// reference's additive -inf_value.  (A tcgen05/TMEM version is future work: at S = 64 the QK^T / PV tiles are
-// 64x64x64 and attention is ~2% of the layer FLOPs; the dense contractions run on tcgen05 in gemm_tcgen05.cu.)
+// reference's additive -inf_value.
 #include <math.h>
 #include <stdlib.h>
 
@@ -620,362 +620,6 @@ __global__ void __launch_bounds__(NT, 4) bwd64_kernel(const Params p, const int 
   }
 }
 
-// ================================================================================================ tcgen05 path
-// (opt-in, ZB_ATTN_TC=1 — written after the round's last GPU visit; parity test opt-in, not yet timed.)
-// Forward attention of the 64-token training batches on the 5th-generation tensor cores: one CTA per PAIR of heads
-// (h, h + 1) of one batch element, so the two 64 x 64 problems fill one 128-row tcgen05.mma:
-//   S[128 x 128] = [Q_h ; Q_h+1] [K_h ; K_h+1]^T       (fp32 in TMEM; only the two diagonal 64 x 64 blocks are used)
-//   P[128 x 128] = softmax rows of the diagonal blocks, zero elsewhere (bf16, written to shared memory in the
-//                  canonical K-major SWIZZLE_128B layout a TMA load would produce)
-//   O[128 x 64]  = P [V_h ; V_h+1]                     (the zero blocks cancel the other head's values)
-// Q / K / V tiles arrive by TMA (two 64 x 64 boxes each, read in place from the fused [tokens, 3d] buffer), one
-// elected thread issues both MMAs, four warps own one S / O row per thread (tcgen05.ld), logits and probabilities
-// never touch HBM.  Everything is single-shot per CTA (every mbarrier is used once, phase 0): 80 KB of shared memory
-// and 256 TMEM columns let two CTAs share an SM, which is where the overlap of one pair's softmax with another pair's
-// loads and MMAs comes from.  Requires lq = lk = 64, an even head count, no dropout, batch-contiguous q / k / v views.
-constexpr int TC_THREADS = 160;  // warp 0: TMEM allocation, TMA, MMA issue; warps 1-4: one S / O row per thread
-struct TcSmem {
-  __nv_bfloat16 q[128 * 64], k[128 * 64], v[128 * 64];   // two 64-row boxes each (head h, head h + 1)
-  __nv_bfloat16 p[2][128 * 64];                            // A operand of the second MMA: two 64-wide k atoms
-  uint64_t bar_full, bar_s, bar_p, bar_o;
-  uint32_t tmem_slot;
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 2)
-fwd_tc64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                const __grid_constant__ CUtensorMap tma_v, const Params p) {
-  extern __shared__ uint8_t tc_raw[];
-  TcSmem& T = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pairs = p.heads >> 1;
-  const int b = blockIdx.x / pairs, h0 = (blockIdx.x % pairs) * 2;
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tma_q);
-      tma_prefetch_desc(&tma_k);
-      tma_prefetch_desc(&tma_v);
-      mbar_init(&T.bar_full, 1);
-      mbar_init(&T.bar_s, 1);
-      mbar_init(&T.bar_p, 4);   // one arrival per softmax warp
-      mbar_init(&T.bar_o, 1);
-      mbar_fence_init();
-    }
-    __syncwarp();
-    tmem_alloc(&T.tmem_slot, 256);   // S: columns [0, 128), O: columns [128, 192)
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = T.tmem_slot;
-  grid_dep_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&T.bar_full, 3 * 128 * 64 * 2);
-      const int qrow = b * 64, krow = b * 64;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {   // box {64 channels of head h0 + i, 64 rows}
-        tma_load_2d(T.q + i * 64 * 64, &tma_q, &T.bar_full, (h0 + i) * 64, qrow);
-        tma_load_2d(T.k + i * 64 * 64, &tma_k, &T.bar_full, (h0 + i) * 64, krow);
-        tma_load_2d(T.v + i * 64 * 64, &tma_v, &T.bar_full, (h0 + i) * 64, krow);
-      }
-      mbar_wait(&T.bar_full, 0);
-      tc_fence_after();
-      {  // S = Q K^T : A = Q [128 m][64 k] K-major, B = K [128 n][64 k] K-major
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0u, 0u);
-        const uint32_t sa = smem_u32(T.q), sb = smem_u32(T.k);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ss(tmem_base, umma_smem_desc(sa + kk * 32, 0, 1024), umma_smem_desc(sb + kk * 32, 0, 1024), idesc,
-                       kk > 0 ? 1u : 0u);
-        umma_commit(&T.bar_s);
-      }
-      mbar_wait(&T.bar_p, 0);
-      tc_fence_after();
-      {  // O = P V : A = P [128 m][128 k] K-major (two 64-wide k atoms), B = V [128 k][64 n] MN-major
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0u, 1u);
-        const uint32_t sb = smem_u32(T.v);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t sa = smem_u32(T.p[kk >> 2]) + (kk & 3) * 32;
-          umma_bf16_ss(tmem_base + 128, umma_smem_desc(sa, 0, 1024), umma_smem_desc(sb + kk * 2048, 64 * 128, 1024), idesc,
-                       kk > 0 ? 1u : 0u);
-        }
-        umma_commit(&T.bar_o);
-      }
-    }
-  } else {
-    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;             // row of the stacked problem
-    const int item = row >> 6, r = row & 63;      // which head of the pair, query position
-    const int h = h0 + item;
-    const int kl = p.key_len ? p.key_len[b] : p.lk;
-    mbar_wait(&T.bar_s, 0);
-    tc_fence_after();
-    uint32_t ra[32], rb[32];
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + item * 64;
-    tmem_ld_32x32b_x32(t_s, ra);
-    tmem_ld_32x32b_x32(t_s + 32, rb);
-    tmem_ld_wait();
-    float sv[64];
-    const int i_abs = r + p.q_offset;
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      float v = __uint_as_float(j < 32 ? ra[j] : rb[j - 32]) * p.scale;
-      const bool valid = j < kl && (!p.causal || j <= i_abs);
-      v = valid ? v : v - p.inf_value;
-      sv[j] = v;
-      m = fmaxf(m, v);
-    }
-    float l = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      sv[j] = __expf(sv[j] - m);
-      l += sv[j];
-    }
-    // P row: 16 chunks of 8 bf16; chunk c of atom a lives at row * 128 B + ((c ^ (row & 7)) * 16 B) of T.p[a]
-    uint8_t* prow0 = reinterpret_cast<uint8_t*>(T.p[0]) + row * 128;
-    uint8_t* prow1 = reinterpret_cast<uint8_t*>(T.p[1]) + row * 128;
-    uint8_t* mine = item ? prow1 : prow0;
-    uint8_t* other = item ? prow0 : prow1;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 u;
-      u.x = pack_bf16x2(sv[8 * c + 0], sv[8 * c + 1]);
-      u.y = pack_bf16x2(sv[8 * c + 2], sv[8 * c + 3]);
-      u.z = pack_bf16x2(sv[8 * c + 4], sv[8 * c + 5]);
-      u.w = pack_bf16x2(sv[8 * c + 6], sv[8 * c + 7]);
-      const int pc = (c ^ (row & 7)) * 16;
-      *reinterpret_cast<uint4*>(mine + pc) = u;
-      *reinterpret_cast<uint4*>(other + pc) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async_smem();    // generic-proxy writes -> visible to the tensor core's async-proxy reads
-    tc_fence_before();           // this thread's tcgen05.ld of S are complete (waited) before the MMA warp proceeds
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&T.bar_p);
-    mbar_wait(&T.bar_o, 0);
-    tc_fence_after();
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 128;
-    tmem_ld_32x32b_x32(t_o, ra);
-    tmem_ld_32x32b_x32(t_o + 32, rb);
-    tmem_ld_wait();
-    const float inv = 1.f / l;
-    __nv_bfloat16* op = p.out + (long long)b * p.bso + (long long)r * p.ldo + h * DH;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 u;
-      const uint32_t* src = c < 4 ? ra + 8 * c : rb + 8 * (c - 4);
-      u.x = pack_bf16x2(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-      u.y = pack_bf16x2(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-      u.z = pack_bf16x2(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-      u.w = pack_bf16x2(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-      reinterpret_cast<uint4*>(op)[c] = u;
-    }
-    if (p.lse) p.lse[((long long)b * p.heads + h) * p.lq + r] = m + __logf(l);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// Backward of the same head pair on tcgen05 (opt-in with the forward, ZB_ATTN_TC=1; untimed, parity test opt-in).
-// Five MMAs around one element-wise phase, all 128 rows tall through the same block-diagonal stacking:
-//   S  = [Q][K]^T,  dP = [dO][V]^T                      (128 x 128 fp32 each, diagonal 64 x 64 blocks used)
-//   P  = exp(S * scale + mask - lse),  dS = P * (dP - delta),  delta = rowsum(dO * O)     (one row per thread)
-//   dQ = dS [K]      dK = dS^T [Q]      dV = P^T [dO]   (128 x 64 fp32 each; dQ, dK scaled by `scale` on the way out)
-// P and dS are written once to shared memory as two [128 rows][64 columns] SWIZZLE_128B atoms (zeros off the
-// diagonal); that one image is read as a K-major A operand (rows = m, for dS K) and as an MN-major A operand
-// (rows = k, for dS^T Q and P^T dO) — only the descriptors differ.  TMEM: 2 * 128 + 3 * 64 = 448 columns.
-struct TcSmemBwd {
-  __nv_bfloat16 q[128 * 64], k[128 * 64], v[128 * 64], d_o[128 * 64];
-  __nv_bfloat16 p[2][128 * 64], ds[2][128 * 64];
-  uint64_t bar_full, bar_s, bar_p, bar_o;
-  uint32_t tmem_slot;
-};
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-bwd_tc64_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do, const Params p) {
-  extern __shared__ uint8_t tc_raw[];
-  TcSmemBwd& T = *reinterpret_cast<TcSmemBwd*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pairs = p.heads >> 1;
-  const int b = blockIdx.x / pairs, h0 = (blockIdx.x % pairs) * 2;
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tma_q);
-      tma_prefetch_desc(&tma_k);
-      tma_prefetch_desc(&tma_v);
-      tma_prefetch_desc(&tma_do);
-      mbar_init(&T.bar_full, 1);
-      mbar_init(&T.bar_s, 1);
-      mbar_init(&T.bar_p, 4);
-      mbar_init(&T.bar_o, 1);
-      mbar_fence_init();
-    }
-    __syncwarp();
-    tmem_alloc(&T.tmem_slot, 512);   // S [0,128)  dP [128,256)  dQ [256,320)  dK [320,384)  dV [384,448)
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = T.tmem_slot;
-  grid_dep_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&T.bar_full, 4 * 128 * 64 * 2);
-      const int row0 = b * 64;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        tma_load_2d(T.q + i * 64 * 64, &tma_q, &T.bar_full, (h0 + i) * 64, row0);
-        tma_load_2d(T.k + i * 64 * 64, &tma_k, &T.bar_full, (h0 + i) * 64, row0);
-        tma_load_2d(T.v + i * 64 * 64, &tma_v, &T.bar_full, (h0 + i) * 64, row0);
-        tma_load_2d(T.d_o + i * 64 * 64, &tma_do, &T.bar_full, (h0 + i) * 64, row0);
-      }
-      mbar_wait(&T.bar_full, 0);
-      tc_fence_after();
-      {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0u, 0u);
-        const uint32_t sq = smem_u32(T.q), sk = smem_u32(T.k), sv = smem_u32(T.v), sdo = smem_u32(T.d_o);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // S = Q K^T
-          umma_bf16_ss(tmem_base, umma_smem_desc(sq + kk * 32, 0, 1024), umma_smem_desc(sk + kk * 32, 0, 1024), idesc,
-                       kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)   // dP = dO V^T
-          umma_bf16_ss(tmem_base + 128, umma_smem_desc(sdo + kk * 32, 0, 1024), umma_smem_desc(sv + kk * 32, 0, 1024),
-                       idesc, kk > 0 ? 1u : 0u);
-        umma_commit(&T.bar_s);
-      }
-      mbar_wait(&T.bar_p, 0);
-      tc_fence_after();
-      {
-        const uint32_t sq = smem_u32(T.q), sk = smem_u32(T.k), sdo = smem_u32(T.d_o);
-        const uint32_t sp = smem_u32(T.p[0]), sds = smem_u32(T.ds[0]);
-        constexpr uint32_t id_kmaj = umma_idesc_bf16(128, 64, 0u, 1u);   // A K-major,  B MN-major
-        constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1u, 1u);     // A MN-major, B MN-major
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // dQ = dS K : k = keys; A atom (kk / 4), 32 B per k-step inside an atom
-          umma_bf16_ss(tmem_base + 256, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
-                       umma_smem_desc(sk + kk * 2048, 64 * 128, 1024), id_kmaj, kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // dK = dS^T Q : k = queries (16 rows = 2048 B per k-step), m atoms 16 KB apart
-          umma_bf16_ss(tmem_base + 320, umma_smem_desc(sds + kk * 2048, 16384, 1024),
-                       umma_smem_desc(sq + kk * 2048, 64 * 128, 1024), id_mn, kk > 0 ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // dV = P^T dO
-          umma_bf16_ss(tmem_base + 384, umma_smem_desc(sp + kk * 2048, 16384, 1024),
-                       umma_smem_desc(sdo + kk * 2048, 64 * 128, 1024), id_mn, kk > 0 ? 1u : 0u);
-        umma_commit(&T.bar_o);
-      }
-    }
-  } else {
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int item = row >> 6, r = row & 63;
-    const int h = h0 + item;
-    const int kl = p.key_len ? p.key_len[b] : p.lk;
-    // delta = rowsum(dO * O) and the row's log-sum-exp, straight from global memory while the tiles are in flight
-    float delta = 0.f;
-    {
-      const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)b * p.bso + (long long)r * p.ldo + h * DH);
-      const uint4* drow = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.bsdo + (long long)r * p.lddo + h * DH);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 a = __ldg(orow + c), d = __ldg(drow + c);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-          delta += x.x * y.x + x.y * y.y;
-        }
-      }
-    }
-    const float lse = p.lse[((long long)b * p.heads + h) * p.lq + r];
-    const int i_abs = r + p.q_offset;
-    mbar_wait(&T.bar_s, 0);
-    tc_fence_after();
-    uint8_t* p_mine = reinterpret_cast<uint8_t*>(T.p[item]) + row * 128;
-    uint8_t* p_other = reinterpret_cast<uint8_t*>(T.p[item ^ 1]) + row * 128;
-    uint8_t* ds_mine = reinterpret_cast<uint8_t*>(T.ds[item]) + row * 128;
-    uint8_t* ds_other = reinterpret_cast<uint8_t*>(T.ds[item ^ 1]) + row * 128;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {       // 32 key columns at a time: 64 live accumulator values
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32b_x32(t_row + item * 64 + half * 32, rs);
-      tmem_ld_32x32b_x32(t_row + 128 + item * 64 + half * 32, rp);
-      tmem_ld_wait();
-      float pv[32], dsv[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = half * 32 + j;
-        const bool valid = col < kl && (!p.causal || col <= i_abs);
-        float v = __uint_as_float(rs[j]) * p.scale;
-        v = valid ? v : v - p.inf_value;
-        pv[j] = __expf(v - lse);
-        dsv[j] = pv[j] * (__uint_as_float(rp[j]) - delta);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u, w;
-        u.x = pack_bf16x2(pv[8 * c + 0], pv[8 * c + 1]);
-        u.y = pack_bf16x2(pv[8 * c + 2], pv[8 * c + 3]);
-        u.z = pack_bf16x2(pv[8 * c + 4], pv[8 * c + 5]);
-        u.w = pack_bf16x2(pv[8 * c + 6], pv[8 * c + 7]);
-        w.x = pack_bf16x2(dsv[8 * c + 0], dsv[8 * c + 1]);
-        w.y = pack_bf16x2(dsv[8 * c + 2], dsv[8 * c + 3]);
-        w.z = pack_bf16x2(dsv[8 * c + 4], dsv[8 * c + 5]);
-        w.w = pack_bf16x2(dsv[8 * c + 6], dsv[8 * c + 7]);
-        const int pc = (((half * 4 + c) ^ (row & 7))) * 16;
-        *reinterpret_cast<uint4*>(p_mine + pc) = u;
-        *reinterpret_cast<uint4*>(ds_mine + pc) = w;
-        *reinterpret_cast<uint4*>(p_other + pc) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(ds_other + pc) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&T.bar_p);
-    mbar_wait(&T.bar_o, 0);
-    tc_fence_after();
-    // row r of dQ belongs to query r; rows r of dK / dV belong to key r of the same head
-    __nv_bfloat16* outs[3] = {p.dq + (long long)b * p.bsdq + (long long)r * p.lddq + h * DH,
-                              p.dk + (long long)b * p.bsdk + (long long)r * p.lddk + h * DH,
-                              p.dv + (long long)b * p.bsdv + (long long)r * p.lddv + h * DH};
-#pragma unroll
-    for (int which = 0; which < 3; ++which) {
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(t_row + 256 + which * 64, ra);
-      tmem_ld_32x32b_x32(t_row + 256 + which * 64 + 32, rb);
-      tmem_ld_wait();
-      const float mul = which < 2 ? p.scale : 1.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 u;
-        const uint32_t* src = c < 4 ? ra + 8 * c : rb + 8 * (c - 4);
-        u.x = pack_bf16x2(__uint_as_float(src[0]) * mul, __uint_as_float(src[1]) * mul);
-        u.y = pack_bf16x2(__uint_as_float(src[2]) * mul, __uint_as_float(src[3]) * mul);
-        u.z = pack_bf16x2(__uint_as_float(src[4]) * mul, __uint_as_float(src[5]) * mul);
-        u.w = pack_bf16x2(__uint_as_float(src[6]) * mul, __uint_as_float(src[7]) * mul);
-        reinterpret_cast<uint4*>(outs[which])[c] = u;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 static Params to_params(const zb_attention_args* a) {
   Params p;
   p.q = (const __nv_bfloat16*)a->q; p.k = (const __nv_bfloat16*)a->k; p.v = (const __nv_bfloat16*)a->v;
@@ -1019,40 +663,9 @@ static bool tile64_ok(const zb_attention_args* a) {
   return !off && a->lq <= 64 && a->lk <= 64 && a->kv_group <= 1;
 }
 
-int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);  // gemm_tcgen05.cu
-
-// lq = lk = 64, head pairs, batch-contiguous 2-D views (row pitch ld, batch pitch 64 * ld), no dropout
-static bool tc64_ok(const zb_attention_args* a, const fa::Params& p) {
-  const char* e = getenv("ZB_ATTN_TC");   // per call: the parity test flips it inside one process
-  if (!(e && e[0] == '1')) return false;
-  if (a->lq != 64 || a->lk != 64 || (a->heads & 1) || p.drop_rate > 0.f || a->kv_group > 1) return false;
-  if (a->bsq != 64 * a->ldq || a->bsk != 64 * a->ldk || a->bsv != 64 * a->ldv) return false;
-  if (a->ldo % 8 || a->bso % 8) return false;
-  return true;
-}
-
-static int attention_tc_fwd(const zb_attention_args* a, const fa::Params& p, cudaStream_t st) {
-  CUtensorMap mq, mk, mv;
-  const uint64_t width = (uint64_t)a->heads * 64, rows = (uint64_t)a->batch * 64;
-  int rc = make_map(&mq, a->q, width, rows, a->ldq, 64);
-  if (!rc) rc = make_map(&mk, a->k, width, rows, a->ldk, 64);
-  if (!rc) rc = make_map(&mv, a->v, width, rows, a->ldv, 64);
-  if (rc) return rc;
-  const int smem = (int)sizeof(fa::TcSmem) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(fa::fwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
-  ZB_LAUNCH(fa::fwd_tc64_kernel, a->batch * (a->heads / 2), fa::TC_THREADS, smem, st, mq, mk, mv, p);
-  note_path(ZB_PATH_ATTN_TC);
-  return check_launch("zb_attention_fwd(tcgen05)");
-}
-
 int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   const bool drop = p.drop_rate > 0.f;
-  if (tile64_ok(a) && tc64_ok(a, p)) return attention_tc_fwd(a, p, st);
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
     const int smem = (int)sizeof(fa::Tile64Fwd);
@@ -1075,31 +688,9 @@ int attention_mma_fwd(const zb_attention_args* a, cudaStream_t st) {
   return check_launch("zb_attention_fwd(mma)");
 }
 
-static int attention_tc_bwd(const zb_attention_args* a, const fa::Params& p, cudaStream_t st) {
-  CUtensorMap mq, mk, mv, mdo;
-  const uint64_t width = (uint64_t)a->heads * 64, rows = (uint64_t)a->batch * 64;
-  int rc = make_map(&mq, a->q, width, rows, a->ldq, 64);
-  if (!rc) rc = make_map(&mk, a->k, width, rows, a->ldk, 64);
-  if (!rc) rc = make_map(&mv, a->v, width, rows, a->ldv, 64);
-  if (!rc) rc = make_map(&mdo, a->d_o, width, rows, a->lddo, 64);
-  if (rc) return rc;
-  const int smem = (int)sizeof(fa::TcSmemBwd) + 1024;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(fa::bwd_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
-  ZB_LAUNCH(fa::bwd_tc64_kernel, a->batch * (a->heads / 2), fa::TC_THREADS, smem, st, mq, mk, mv, mdo, p);
-  note_path(ZB_PATH_ATTN_TC);
-  return check_launch("zb_attention_bwd(tcgen05)");
-}
-
 int attention_mma_bwd(const zb_attention_args* a, cudaStream_t st) {
   const fa::Params p = fa::to_params(a);
   const bool drop = p.drop_rate > 0.f;
-  if (tile64_ok(a) && tc64_ok(a, p) && a->bsdo == 64 * a->lddo && a->lddq % 8 == 0 && a->lddk % 8 == 0 &&
-      a->lddv % 8 == 0 && a->bsdq % 8 == 0 && a->bsdk % 8 == 0 && a->bsdv % 8 == 0)
-    return attention_tc_bwd(a, p, st);
   if (tile64_ok(a)) {
     const int items = a->batch * a->heads;
     const int smem = (int)sizeof(fa::Tile64Bwd);

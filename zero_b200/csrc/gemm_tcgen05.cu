@@ -410,6 +410,59 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint
   return ZB_OK;
 }
 
+// 3-D bf16 tensor map over a [batch, len, width] view (width contiguous, row pitch `ld`, batch pitch `bs` elements);
+// box {64 channels, box1 positions, 1 batch element}; SWIZZLE_128B.  Positions past `len` read as zeros (the tile
+// never runs into the next batch element), which is what the attention kernels rely on for ragged lengths.
+int make_map_3d(CUtensorMap* m, const void* ptr, uint64_t width, uint64_t len, uint64_t batch, uint64_t ld, uint64_t bs,
+                uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return ZB_ECUDA;
+  }
+  cuuint64_t dims[3] = {width, len, batch};
+  cuuint64_t strides[2] = {ld * 2, (batch > 1 ? bs : ld * len) * 2};
+  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d): dims %llu x %llu x %llu ld %llu bs %llu", (int)r,
+              (unsigned long long)width, (unsigned long long)len, (unsigned long long)batch, (unsigned long long)ld,
+              (unsigned long long)bs);
+    return ZB_ECUDA;
+  }
+  return ZB_OK;
+}
+
+// 4-D bf16 tensor map over a [batch, len, heads * 64] view seen as {64 channels, len, heads, batch} (row pitch `ld`,
+// head pitch 64, batch pitch `bs` elements); box {64, box_rows, box_heads, 1}; SWIZZLE_128B.  A box lands in shared
+// memory as [box_heads][box_rows][64 channels]: the stacked-heads operand layout of the attention kernels in ONE copy.
+// Positions past `len` read as zeros and are not written by stores.
+int make_map_heads(CUtensorMap* m, const void* ptr, uint64_t len, uint64_t heads, uint64_t batch, uint64_t ld,
+                   uint64_t bs, uint32_t box_rows, uint32_t box_heads) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return ZB_ECUDA;
+  }
+  cuuint64_t dims[4] = {64, len, heads, batch};
+  cuuint64_t strides[3] = {ld * 2, 128, (batch > 1 ? bs : ld * len) * 2};
+  cuuint32_t box[4] = {64, box_rows, box_heads, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (heads) failed (%d): len %llu heads %llu batch %llu ld %llu bs %llu", (int)r,
+              (unsigned long long)len, (unsigned long long)heads, (unsigned long long)batch, (unsigned long long)ld,
+              (unsigned long long)bs);
+    return ZB_ECUDA;
+  }
+  return ZB_OK;
+}
+
 // fp32 output tiles for the epilogue's TMA stores: box {32 floats = 128 B, box1 rows}, 128B swizzle
 int make_map_f32(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1) {
   PFN_encodeTiled enc = get_encode();

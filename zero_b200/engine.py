@@ -503,7 +503,8 @@ class Engine(object):
         d3 = dqkv.view(B, Lq, 3 * c.d)
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), d3[:, :, :c.d], d3[:, :, c.d:2 * c.d], d3[:, :, 2 * c.d:],
-                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
+                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None,
+                          workspace=self._attn_scratch)
         self._wgrad(x, dqkv, ps.g(key + ".qkv.W"), ps.g(key + ".qkv.b"))
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dqkv, ps.w(key + ".qkv.W"), dx)
@@ -551,7 +552,8 @@ class Engine(object):
         dkv3 = dkv.view(B, S, 2 * c.d)
         delta = ws.get(tag + ".delta", (B, c.h, Lq), f32)
         ops.attention_bwd(sv["attn"], dctx.view(B, Lq, c.d), dq.view(B, Lq, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:],
-                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None)
+                          delta, ps.g(key + ".rpr_k") if c.rpr else None, ps.g(key + ".rpr_v") if c.rpr else None,
+                          workspace=self._attn_scratch)
         self._wgrad(x, dq, ps.g(key + ".q.W"), ps.g(key + ".q.b"))
         if not batched:
             self._wgrad(enc, dkv, ps.g(key + ".kv.W"), ps.g(key + ".kv.b"))
@@ -560,6 +562,11 @@ class Engine(object):
         dx = ws.get(tag + ".dx", (N, c.d))
         ops.linear_dgrad(dq, ps.w(key + ".q.W"), dx)
         return dx
+
+    def _attn_scratch(self, nbytes):
+        """Scratch of zb_attention_bwd (the fp32 dq reduction of sequences longer than one 128-key block): one buffer
+        per engine, reused by every attention backward of the step (they run in stream order)."""
+        return self.ws.get("attn.bwd_scratch", ((nbytes + 3) // 4,), f32)
 
     def _post_fwd(self, key, ctx, N, sv, tag):
         """ReLA's gated RMS norm between the merged heads and o_map (modules/rela.py:78-81); identity otherwise."""

@@ -168,7 +168,8 @@ def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
     dkv = ws.get(bw + ".dkv", (B * S, 2 * c.d))
     dkv3 = dkv.view(B, S, 2 * c.d)
     delta = ws.get(bw + ".delta", (B, c.h, T), f32)
-    ops.attention_bwd(sub["attn"], do.view(B, T, c.d), dq.view(B, T, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:], delta)
+    ops.attention_bwd(sub["attn"], do.view(B, T, c.d), dq.view(B, T, c.d), dkv3[:, :, :c.d], dkv3[:, :, c.d:], delta,
+                      workspace=self._attn_scratch)
     self._side(lambda: (ops.linear_wgrad(x, dq, ps.g(kc + ".q.W")), ops.colsum(dq, ps.g(kc + ".q.b")),
                         ops.linear_wgrad(enc, dkv, ps.g(kc + ".kv.W")), ops.colsum(dkv, ps.g(kc + ".kv.b"))))
     ops.linear_dgrad(dkv, ps.w(kc + ".kv.W"), d_enc_f32, accum=True)

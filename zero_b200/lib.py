@@ -41,7 +41,8 @@ class AttentionArgs(C.Structure):
                 ("lddo", i64), ("lddq", i64), ("lddk", i64), ("lddv", i64),
                 ("bsdo", i64), ("bsdq", i64), ("bsdk", i64), ("bsdv", i64),
                 ("d_rpr_k", vp), ("d_rpr_v", vp), ("delta", vp), ("kv_group", i32),
-                ("dropout_rate", f32), ("dropout_site", C.c_uint32), ("dropout_seed", vp)]
+                ("dropout_rate", f32), ("dropout_site", C.c_uint32), ("dropout_seed", vp),
+                ("workspace", vp), ("workspace_bytes", i64)]
 
 
 class AddLnArgs(C.Structure):
@@ -103,6 +104,7 @@ EXPORTS = [
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
     "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam", "zb_gumbel_add",
+    "zb_attention_bwd_workspace_bytes",
 ]
 
 _lib = None
@@ -163,7 +165,9 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argt
         fn.restype = C.c_int
-    if lib.zb_abi_version() != 2:
+    lib.zb_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttentionArgs)]
+    lib.zb_attention_bwd_workspace_bytes.restype = C.c_int64
+    if lib.zb_abi_version() != 3:
         raise ZeroB200Error("libzero_b200.so ABI version mismatch")
     lib.zb_abi_struct_size.argtypes = [i32]
     lib.zb_abi_struct_size.restype = C.c_int64

@@ -147,7 +147,20 @@ def attention_fwd(a):
     L.check(L.load().zb_attention_fwd(C.byref(a), _stream()), "zb_attention_fwd")
 
 
-def attention_bwd(a, d_o, dq, dk, dv, delta, d_rpr_k=None, d_rpr_v=None):
+def attention_bwd_workspace_bytes(a):
+    """Bytes of scratch that let zb_attention_bwd pick any kernel for the problem `a` (0: none needed)."""
+    return int(L.load().zb_attention_bwd_workspace_bytes(C.byref(a)))
+
+
+def attention_bwd(a, d_o, dq, dk, dv, delta, d_rpr_k=None, d_rpr_v=None, workspace=None):
+    """`workspace`: caller-owned scratch tensor (any dtype, >= attention_bwd_workspace_bytes(a) bytes), or a callable
+    bytes -> tensor that is asked only when the problem needs one."""
+    need = attention_bwd_workspace_bytes(a)
+    if need and callable(workspace):
+        workspace = workspace(need)
+    if need and workspace is not None:
+        assert workspace.numel() * workspace.element_size() >= need
+        a.workspace, a.workspace_bytes = _p(workspace), workspace.numel() * workspace.element_size()
     a.d_o, a.dq, a.dk, a.dv = _p(d_o), _p(dq), _p(dk), _p(dv)
     a.lddo, a.lddq, a.lddk, a.lddv = d_o.stride(1), dq.stride(1), dk.stride(1), dv.stride(1)
     a.bsdo, a.bsdq, a.bsdk, a.bsdv = d_o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0)
