@@ -5,12 +5,17 @@
 // over the [batch, len, heads * dh] views, read in place from the fused [tokens, 3d] projection buffer; positions past
 // the sequence end arrive as zeros), logits and probabilities never touch HBM.
 //
-// Both kernels are PERSISTENT and warp-specialised (192 threads, one CTA per SM):
+// Both kernels are PERSISTENT and warp-specialised (352 threads, one CTA per SM):
 //   warp 0     TMA producer: runs up to two 128 x 128 blocks ahead of the math through a two-stage shared-memory ring
+//              (4-D tensor maps {64 channels, position, head, batch}: one copy per operand, also for stacked heads)
 //   warp 1     TMEM allocation + MMA issue (one elected thread)
-//   warps 2-5  one query row (forward; backward: one query row of S / dP, one key row of dK / dV) per thread:
-//              tcgen05.ld, masks, exp, dropout, P / dS written to shared memory in the canonical SWIZZLE_128B K-major
-//              layout a TMA load would produce (so they feed the next MMA as the A operand), epilogues
+//   warps 2-9  two threads per row of the block (forward: a query row; backward: a query row of S / dP, a key row of
+//              dK / dV), each owning half of the row's columns: tcgen05.ld, masks, exp2, dropout, P / dS written to
+//              shared memory in the canonical SWIZZLE_128B K-major layout a TMA load would produce (so they feed the
+//              next MMA as the A operand); results staged as bf16 rows in shared memory
+//   warp 10    TMA tile stores of the staged results (rows past the sequence end are clipped by the copy engine)
+// In-kernel timelines (ZB_ATTN_TRACE=1, profiles/r02*_attn_trace.log) shaped this: one thread per row with 4 row warps
+// spent 5 us per block in the row arithmetic and 3 us in 16-byte-per-lane global stores.
 //
 // A 128-row block is either 128 consecutive positions of ONE head, or — when lq, lk <= 64, the reference's 64-token
 // training batches — the stacked 64 + 64 positions of TWO heads (h, h + 1): S = [Q_h; Q_h+1][K_h; K_h+1]^T fills one
@@ -41,7 +46,8 @@ int make_map_heads(CUtensorMap* m, const void* ptr, uint64_t len, uint64_t heads
 
 namespace fat {
 
-constexpr int kThreads = 224;  // warp 0 TMA loads, warp 1 MMA, warps 2-5 rows, warp 6 TMA stores
+constexpr int kRowWarps = 8;   // two threads per row of a 128-row block
+constexpr int kThreads = 32 * (2 + kRowWarps + 1);  // warp 0 TMA loads, warp 1 MMA, warps 2-9 rows, warp 10 TMA stores
 constexpr int kTile = 128 * 64;  // elements of a [128 rows][64 channels] bf16 tile (16 KB)
 
 struct Params {
@@ -185,13 +191,29 @@ __device__ __forceinline__ void stage_row_bf16(uint32_t tile_saddr, int row, con
 
 // Logits of one row, one 32-column chunk, in base-2 units: t = raw * sl2 (sl2 = scale * log2 e), minus inf2 where the
 // key is masked (columns [nv, nb) of the chunk), -inf where the column is no key of this row at all (>= nb).
-// `fast` (warp-uniform): every row of the warp has the whole chunk valid — no per-element mask work.
-__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], bool fast, int nv, int nb, float sl2, float inf2) {
-  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains: one warp per scheduler needs ILP
-  if (fast) {
+// The mode is warp-uniform:
+//   kFast  every row of the warp has the whole chunk visible: no per-element mask work
+//   kMid   the chunk is in bounds for every row and every row has a visible key elsewhere (in the block for the
+//          forward's running maximum, in the sequence for the backward's log-sum-exp), so a masked logit's weight
+//          2^(t - inf2 - m) is exactly 0 in fp32 and it cannot be the maximum: masked columns are simply dropped
+//   kSlow  the reference's arithmetic literally (rows whose keys are all masked, ragged last block)
+enum { kFast = 0, kMid = 1, kSlow = 2 };
+__device__ __forceinline__ int chunk_mode(int nv, int nb, bool row_has_visible) {
+  if (__all_sync(0xffffffffu, nv >= 32)) return kFast;
+  if (__all_sync(0xffffffffu, nb >= 32 && row_has_visible)) return kMid;
+  return kSlow;
+}
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], int mode, int nv, int nb, float sl2, float inf2) {
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains: few warps per scheduler need ILP
+  if (mode == kFast) {
 #pragma unroll
     for (int jj = 0; jj < 32; ++jj) m[jj & 3] = fmaxf(m[jj & 3], __uint_as_float(r[jj]));
     return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * sl2;  // sl2 > 0
+  }
+  if (mode == kMid) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) m[jj & 3] = fmaxf(m[jj & 3], jj < nv ? __uint_as_float(r[jj]) : -INFINITY);
+    return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * sl2;
   }
 #pragma unroll
   for (int jj = 0; jj < 32; ++jj) {
@@ -203,13 +225,20 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], bool fast, i
   return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
 }
 // e[jj] = 2^(t[jj] - off) of the same chunk; returns the sum of e
-__device__ __forceinline__ float chunk_exp(const uint32_t (&r)[32], float (&e)[32], bool fast, int nv, int nb, float sl2,
+__device__ __forceinline__ float chunk_exp(const uint32_t (&r)[32], float (&e)[32], int mode, int nv, int nb, float sl2,
                                            float inf2, float off) {
   float l[4] = {0.f, 0.f, 0.f, 0.f};
-  if (fast) {
+  if (mode == kFast) {
 #pragma unroll
     for (int jj = 0; jj < 32; ++jj) {
       e[jj] = ex2(fmaf(__uint_as_float(r[jj]), sl2, -off));
+      l[jj & 3] += e[jj];
+    }
+  } else if (mode == kMid) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const float x = ex2(fmaf(__uint_as_float(r[jj]), sl2, -off));
+      e[jj] = jj < nv ? x : 0.f;
       l[jj & 3] += e[jj];
     }
   } else {
@@ -223,6 +252,8 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&r)[32], float (&e)[3
   }
   return (l[0] + l[1]) + (l[2] + l[3]);
 }
+// barrier among the 8 row warps (named barrier 1; barrier 0 is __syncthreads)
+__device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ================================================================================================ forward
 struct FwdStage {
@@ -232,6 +263,8 @@ struct FwdSmem {
   FwdStage st[2];
   __nv_bfloat16 p[2][kTile];    // A operand of O = P V: two 64-key atoms of [128 rows][64 keys]
   __nv_bfloat16 ostage[kTile];  // O rows of a finished unit on their way out (TMA tile store)
+  float xmax[2][2][128];        // [item parity][column half][row]: the two threads of a row exchange their maxima
+  float xl[2][2][128];          // [store parity][column half][row]: ... and their partial normalisers
   uint64_t full[2], empty[2], bar_s[2], bar_p, bar_o, ost_full, ost_free;
   uint32_t tmem_slot;
 };
@@ -256,9 +289,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       mbar_init(&T.empty[s], 1);
       mbar_init(&T.bar_s[s], 1);
     }
-    mbar_init(&T.bar_p, 4);  // one arrival per row warp
+    mbar_init(&T.bar_p, kRowWarps);  // one arrival per row warp
     mbar_init(&T.bar_o, 1);
-    mbar_init(&T.ost_full, 4);
+    mbar_init(&T.ost_full, kRowWarps);
     mbar_init(&T.ost_free, 1);
     mbar_fence_init();
   }
@@ -344,7 +377,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         FAT_TRACE_ITEM(n - 1, 5);
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2 + kRowWarps) {
     // ------------------------------------------------------------------ store warp: finished units leave by TMA
     if (lane == 0) {
       Walk w(p, true);
@@ -361,17 +394,22 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       bulk_wait_all();
     }
   } else {
-    // ------------------------------------------------------------------ row warps: softmax + accumulation
+    // ------------------------------------------------------------------ row warps: softmax + accumulation.
+    // Two threads per row (warps w and w + 4 share a TMEM lane quadrant): each owns half of the row's key columns
+    // of S and half of the 64 output channels of O.
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;   // which half of the row's columns
     const int row = quad * 32 + lane;   // row of the 128-row block
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int item_r = p.pair ? (row >> 6) : 0;
+    // 32-column chunks of S owned by this thread: one of its head's two (pair mode), or two of the block's four
+    const int c_begin = p.pair ? 2 * item_r + half : 2 * half, c_cnt = p.pair ? 1 : 2;
     const uint32_t p_atom0 = smem_u32(T.p[0]), p_atom1 = smem_u32(T.p[1]), ost = smem_u32(T.ostage);
     const float sl2 = p.scale * kLog2e, inf2 = p.inf_value * kLog2e;
     grid_dep_wait();
     const Drop<DROP> drop(p);
-    float m_run = -INFINITY, l_run = 0.f;  // base-2 running maximum, normaliser
-    float acc[64];
+    float m_run = -INFINITY, l_run = 0.f;  // base-2 running maximum (whole row), normaliser (this thread's columns)
+    float acc[32];                          // channels [32 half, 32 half + 32) of the row's output
     float m_acc = 0.f;
     bool acc_empty = true;
     long stores = 0;
@@ -385,33 +423,31 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       mbar_wait(&T.bar_o, (uint32_t)(pend_n & 1));
       tc_fence_after();
       if (threadIdx.x == 64) FAT_TRACE_ITEM(pend_n, 6);
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(t_lane + 256, ra);
-      tmem_ld_32x32b_x32(t_lane + 256 + 32, rb);
+      uint32_t ra[32];
+      tmem_ld_32x32b_x32(t_lane + 256 + 32 * half, ra);
       tmem_ld_wait();
       if (acc_empty) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          acc[c] = __uint_as_float(ra[c]);
-          acc[32 + c] = __uint_as_float(rb[c]);
-        }
+        for (int c = 0; c < 32; ++c) acc[c] = __uint_as_float(ra[c]);
         acc_empty = false;
       } else {
         const float corr = ex2(m_acc - pend_m);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          acc[c] = fmaf(acc[c], corr, __uint_as_float(ra[c]));
-          acc[32 + c] = fmaf(acc[32 + c], corr, __uint_as_float(rb[c]));
-        }
+        for (int c = 0; c < 32; ++c) acc[c] = fmaf(acc[c], corr, __uint_as_float(ra[c]));
       }
       m_acc = pend_m;
       if (pend_last) {
-        // the unit's rows are complete: bf16 into the staging tile, out by one TMA tile store (rows past lq are clipped)
+        // the unit's rows are complete: normaliser = both halves' sums; bf16 into the staging tile, out by one TMA
+        // tile store (rows past lq are clipped)
+        float* xl = &T.xl[stores & 1][0][0];
+        xl[half * 128 + row] = pend_l;
         mbar_wait(&T.ost_free, (uint32_t)((stores & 1) ^ 1));
-        const float inv = 1.f / pend_l;
+        row_warps_sync();
+        const float l_tot = xl[row] + xl[128 + row];
+        const float inv = 1.f / l_tot;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          sts128(ost + swz_off(row, c), pack_bf16x2(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv),
+        for (int c = 0; c < 4; ++c)
+          sts128(ost + swz_off(row, 4 * half + c), pack_bf16x2(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv),
                  pack_bf16x2(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv),
                  pack_bf16x2(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv),
                  pack_bf16x2(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv));
@@ -419,8 +455,8 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&T.ost_full);
         ++stores;
-        if (pend_i < p.lq && p.lse)
-          p.lse[((long long)pend_b * p.heads + pend_h) * p.lq + pend_i] = pend_m * kLn2 + __logf(pend_l);
+        if (half == 0 && pend_i < p.lq && p.lse)
+          p.lse[((long long)pend_b * p.heads + pend_h) * p.lq + pend_i] = pend_m * kLn2 + __logf(l_tot);
         acc_empty = true;
       }
       if (threadIdx.x == 64) FAT_TRACE_ITEM(pend_n, 7);
@@ -434,27 +470,31 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       const int h = p.pair ? w.hs * 2 + item_r : w.hs;
       const int i = p.pair ? (row & 63) : w.qblock() * 128 + row;  // query position of this thread's row
       const int kbase = p.pair ? 0 : w.kblock() * 128;
-      const int kl = p.key_len ? p.key_len[b] : p.lk;
+      const int kl = p.key_len ? __ldg(p.key_len + b) : p.lk;
       // keys [0, jv) are visible to this row, [jv, lk) are masked (func.attention_bias), >= lk do not exist
       const int jv = min(kl, p.causal ? i + p.q_offset + 1 : p.lk);
+      const bool vis = jv - kbase >= 1;  // the row sees at least one key of this block
       const uint32_t t_s = t_lane + (uint32_t)(n & 1) * 128;
-      // the 32-column chunks this row owns: all four, or the two of its own head in pair mode
-      const int c_begin = p.pair ? 2 * item_r : 0, c_end = p.pair ? c_begin + 2 : 4;
       mbar_wait(&T.bar_s[n & 1], (uint32_t)((n >> 1) & 1));
       tc_fence_after();
       if (threadIdx.x == 64) FAT_TRACE_ITEM(n, 3);
-      // ---- pass 1: the row maximum of this block
+      // ---- pass 1: the maximum of this thread's columns, then of the row
       float mt = -INFINITY;
 #pragma unroll 1
-      for (int c32 = c_begin; c32 < c_end; c32 += 2) {
-        uint32_t ra[32], rb[32];
+      for (int cc = 0; cc < c_cnt; ++cc) {
+        const int c32 = c_begin + cc;
+        uint32_t ra[32];
         tmem_ld_32x32b_x32(t_s + c32 * 32, ra);
-        tmem_ld_32x32b_x32(t_s + c32 * 32 + 32, rb);
         tmem_ld_wait();
-        const int base = p.pair ? 0 : kbase + c32 * 32;  // key position of the pair of chunks' first column
+        const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;  // key position of the chunk's first column
         const int nv = jv - base, nb = p.lk - base;
-        const bool fast_a = __all_sync(0xffffffffu, nv >= 32), fast_b = __all_sync(0xffffffffu, nv >= 64);
-        mt = fmaxf(mt, fmaxf(chunk_max(ra, fast_a, nv, nb, sl2, inf2), chunk_max(rb, fast_b, nv - 32, nb - 32, sl2, inf2)));
+        mt = fmaxf(mt, chunk_max(ra, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2));
+      }
+      {
+        float* xm = &T.xmax[n & 1][0][0];
+        xm[half * 128 + row] = mt;
+        row_warps_sync();
+        mt = fmaxf(xm[row], xm[128 + row]);
       }
       // ---- the previous block's O is complete by now (its P V ran under pass 1): fold it, finish its row if last
       if (pend) fold_pending();
@@ -463,34 +503,22 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       l_run = first ? 0.f : l_run * ex2(m_run - m_new);
       m_run = m_new;
       // ---- pass 2: P = 2^(t - m) (bf16, dropout applied) -> shared memory; l += sum of the undropped weights
-      if (p.pair) {  // the other head's keys: zeros
-        const uint32_t other = item_r ? p_atom0 : p_atom1;
-        store_chunk_zero(other, row, 0);
-        store_chunk_zero(other, row, 4);
-      }
+      if (p.pair) store_chunk_zero(item_r ? p_atom0 : p_atom1, row, 4 * half);  // the other head's keys: zeros
 #pragma unroll 1
-      for (int c32 = c_begin; c32 < c_end; c32 += 2) {
-        uint32_t ra[32], rb[32];
+      for (int cc = 0; cc < c_cnt; ++cc) {
+        const int c32 = c_begin + cc;
+        uint32_t ra[32];
         tmem_ld_32x32b_x32(t_s + c32 * 32, ra);
-        tmem_ld_32x32b_x32(t_s + c32 * 32 + 32, rb);
         tmem_ld_wait();
-        const uint32_t atom = (c32 >> 1) ? p_atom1 : p_atom0;
-        const int base = p.pair ? 0 : kbase + c32 * 32;
+        const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;
         const int nv = jv - base, nb = p.lk - base;
-        const bool fast_a = __all_sync(0xffffffffu, nv >= 32), fast_b = __all_sync(0xffffffffu, nv >= 64);
         float e[32];
-        l_run += chunk_exp(ra, e, fast_a, nv, nb, sl2, inf2, m_run);
+        l_run += chunk_exp(ra, e, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2, m_run);
         if (DROP) {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) e[jj] *= drop.mul(p, b, h, i, base + jj);
         }
-        store_chunk_bf16(atom, row, 0, e);
-        l_run += chunk_exp(rb, e, fast_b, nv - 32, nb - 32, sl2, inf2, m_run);
-        if (DROP) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) e[jj] *= drop.mul(p, b, h, i, base + 32 + jj);
-        }
-        store_chunk_bf16(atom, row, 4, e);
+        store_chunk_bf16((c32 >> 1) ? p_atom1 : p_atom0, row, (c32 & 1) * 4, e);
       }
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the tensor core's async-proxy reads
       tc_fence_before();         // this thread's tcgen05.ld of S / O are complete before the MMA warp proceeds
@@ -524,6 +552,7 @@ struct BwdStage {
 struct BwdSmem {
   BwdStage st[2];
   __nv_bfloat16 p[2][kTile], ds[2][kTile];  // two 64-key atoms of [128 query rows][64 keys] each
+  float xdelta[2][2][128];                   // [item parity][channel half][row]: partial rowsum(dO * O)
   uint64_t full[2], empty[2], bar_s, bar_p, bar_o, stg_full;
   uint32_t tmem_slot;
 };
@@ -553,9 +582,9 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       mbar_init(&T.empty[s], 1);  // released by the store warp once the outputs staged in the slot have left
     }
     mbar_init(&T.bar_s, 1);
-    mbar_init(&T.bar_p, 4);
+    mbar_init(&T.bar_p, kRowWarps);
     mbar_init(&T.bar_o, 1);
-    mbar_init(&T.stg_full, 4);
+    mbar_init(&T.stg_full, kRowWarps);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(&T.tmem_slot, kBwdTmemCols);
@@ -638,7 +667,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         if (stage == 0) phase ^= 1;
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2 + kRowWarps) {
     // ------------------------------------------------------------------ store warp: dQ / dK / dV leave by TMA from
     // the slot's own q / k / v buffers, then the slot goes back to the producer
     if (lane == 0) {
@@ -661,11 +690,14 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       bulk_wait_all();
     }
   } else {
-    // ------------------------------------------------------------------ row warps
+    // ------------------------------------------------------------------ row warps: two threads per row, each owns
+    // half of the row's key columns of S / dP and half of the 64 channels of dQ / dK / dV
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int item_r = p.pair ? (row >> 6) : 0;
+    const int c_begin = p.pair ? 2 * item_r + half : 2 * half, c_cnt = p.pair ? 1 : 2;
     const uint32_t p_atom0 = smem_u32(T.p[0]), p_atom1 = smem_u32(T.p[1]);
     const uint32_t ds_atom0 = smem_u32(T.ds[0]), ds_atom1 = smem_u32(T.ds[1]);
     const float sl2 = p.scale * kLog2e, inf2 = p.inf_value * kLog2e;
@@ -679,18 +711,20 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       const int h = p.pair ? w.hs * 2 + item_r : w.hs;
       const int i = p.pair ? (row & 63) : w.qblock() * 128 + row;   // query position of row `row` of S / dP / dQ
       const int kbase = p.pair ? 0 : w.kblock() * 128;
-      const int kl = p.key_len ? p.key_len[b] : p.lk;
+      const int kl = p.key_len ? __ldg(p.key_len + b) : p.lk;
       const bool row_ok = i < p.lq;
       const int jv = row_ok ? min(kl, p.causal ? i + p.q_offset + 1 : p.lk) : 0;
       const int jb = row_ok ? p.lk : 0;  // rows past lq hold zeros (TMA fill): P = dS = 0
-      // delta = rowsum(dO * O) and the row's log-sum-exp, from global memory while the tiles are in flight
+      // delta = rowsum(dO * O) (this thread: 32 of the 64 channels) and the row's log-sum-exp, from global memory
+      // while the tiles are in flight
       float delta = 0.f, lse2 = 0.f;
       if (row_ok) {
-        const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)b * p.bso + (long long)i * p.ldo + h * 64);
-        const uint4* drow = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.bsdo + (long long)i * p.lddo + h * 64);
+        const long long ch = h * 64 + 32 * half;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)b * p.bso + (long long)i * p.ldo + ch);
+        const uint4* drow = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.bsdo + (long long)i * p.lddo + ch);
         float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           const uint4 a = __ldg(orow + c), d = __ldg(drow + c);
           const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -702,28 +736,30 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
         lse2 = p.lse[((long long)b * p.heads + h) * p.lq + i] * kLog2e;
       }
-      const int c_begin = p.pair ? 2 * item_r : 0, c_end = p.pair ? c_begin + 2 : 4;
+      {
+        float* xd = &T.xdelta[n & 1][0][0];
+        xd[half * 128 + row] = delta;
+        row_warps_sync();
+        delta = xd[row] + xd[128 + row];
+      }
       mbar_wait(&T.bar_s, (uint32_t)(n & 1));
       tc_fence_after();
       if (threadIdx.x == 64) FAT_TRACE_ITEM(n, 3);
       if (p.pair) {  // the other head's keys: zeros
-        const uint32_t op = item_r ? p_atom0 : p_atom1, ods = item_r ? ds_atom0 : ds_atom1;
-        store_chunk_zero(op, row, 0);
-        store_chunk_zero(op, row, 4);
-        store_chunk_zero(ods, row, 0);
-        store_chunk_zero(ods, row, 4);
+        store_chunk_zero(item_r ? p_atom0 : p_atom1, row, 4 * half);
+        store_chunk_zero(item_r ? ds_atom0 : ds_atom1, row, 4 * half);
       }
 #pragma unroll 1
-      for (int c32 = c_begin; c32 < c_end; ++c32) {
+      for (int cc = 0; cc < c_cnt; ++cc) {
+        const int c32 = c_begin + cc;
         uint32_t rs[32], rp[32];
         tmem_ld_32x32b_x32(t_lane + c32 * 32, rs);
         tmem_ld_32x32b_x32(t_lane + 128 + c32 * 32, rp);
         tmem_ld_wait();
         const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;
         const int nv = jv - base, nb = jb - base;
-        const bool fast = __all_sync(0xffffffffu, nv >= 32);
         float e[32];
-        chunk_exp(rs, e, fast, nv, nb, sl2, inf2, lse2);  // P = 2^(t - lse2)
+        chunk_exp(rs, e, chunk_mode(nv, nb, jv >= 1), nv, nb, sl2, inf2, lse2);  // P = 2^(t - lse2)
         float dsv[32];
         if (DROP) {
 #pragma unroll
@@ -749,33 +785,36 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       tc_fence_after();
       if (threadIdx.x == 64) FAT_TRACE_ITEM(n, 6);
       // the MMAs that read this slot's q / k / v are complete: the buffers now stage dQ / dK / dV (bf16, swizzled rows)
+      auto stage_half = [&](uint32_t tile, const uint32_t (&r)[32], float mul) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(tile + swz_off(row, 4 * half + c),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 0]) * mul, __uint_as_float(r[8 * c + 1]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul));
+      };
       {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32b_x32(t_lane + 256, ra);
-        tmem_ld_32x32b_x32(t_lane + 256 + 32, rb);
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_lane + 256 + 32 * half, ra);
         tmem_ld_wait();
         if (p.nk == 1) {
-          stage_row_bf16(smem_u32(T.st[stage].q), row, ra, rb, p.scale);
+          stage_half(smem_u32(T.st[stage].q), ra, p.scale);
         } else if (row_ok) {
-          float* dst = p.dq32 + (((long long)b * p.lq + i) * p.heads + h) * 64;
+          float* dst = p.dq32 + (((long long)b * p.lq + i) * p.heads + h) * 64 + 32 * half;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const uint32_t* s = c < 8 ? ra + 4 * c : rb + 4 * (c - 8);
-            red_add_v4(dst + 4 * c, __uint_as_float(s[0]) * p.scale, __uint_as_float(s[1]) * p.scale,
-                       __uint_as_float(s[2]) * p.scale, __uint_as_float(s[3]) * p.scale);
-          }
+          for (int c = 0; c < 8; ++c)
+            red_add_v4(dst + 4 * c, __uint_as_float(ra[4 * c]) * p.scale, __uint_as_float(ra[4 * c + 1]) * p.scale,
+                       __uint_as_float(ra[4 * c + 2]) * p.scale, __uint_as_float(ra[4 * c + 3]) * p.scale);
         }
       }
       if (w.last()) {  // the unit's dK / dV are complete: rows are keys
         uint32_t ra[32], rb[32];
-        tmem_ld_32x32b_x32(t_lane + 320, ra);
-        tmem_ld_32x32b_x32(t_lane + 320 + 32, rb);
+        tmem_ld_32x32b_x32(t_lane + 320 + 32 * half, ra);
+        tmem_ld_32x32b_x32(t_lane + 384 + 32 * half, rb);
         tmem_ld_wait();
-        stage_row_bf16(smem_u32(T.st[stage].k), row, ra, rb, p.scale);
-        tmem_ld_32x32b_x32(t_lane + 384, ra);
-        tmem_ld_32x32b_x32(t_lane + 384 + 32, rb);
-        tmem_ld_wait();
-        stage_row_bf16(smem_u32(T.st[stage].v), row, ra, rb, 1.f);
+        stage_half(smem_u32(T.st[stage].k), ra, p.scale);
+        stage_half(smem_u32(T.st[stage].v), rb, 1.f);
       }
       fence_proxy_async_smem();
       __syncwarp();
