@@ -233,6 +233,144 @@ def decode_bench(device, batches=3):
             "config": "transformer_aan 6+6 d=512, beam 4, batch 64, src len 64, max target len 64 (BASELINE configs[2])"}
 
 
+# ---------------------------------------------------------------------------------------------- secondary legs
+def model_flops_per_step(hp, B, S, T, V, rpr_k=0):
+    """Algorithmic fwd + bwd FLOPs of one step (multiply-add = 2, backward = 2 x forward, attention
+    recompute not counted).  Encoder layer per source token 8d^2 + 4df + 4Sd; decoder layer per target token
+    8d^2 + 4Td (self) + 4d^2 + 4Sd (cross q / o + logits / context) + 4df, plus the memory projection 4d^2 per SOURCE
+    token; vocabulary projection 2dV per target token; relative positions as bucket GEMMs 2 (2k + 1) d per token and
+    attention, keys and values."""
+    d, f = int(hp.hidden_size), int(hp.filter_size)
+    ne, nd = int(hp.num_encoder_layer), int(hp.num_decoder_layer)
+    rp = 2 * 2 * (2 * rpr_k + 1) * d if rpr_k else 0
+    enc = B * S * ne * (8 * d * d + 4 * d * f + 4 * S * d + rp)
+    dec = B * T * nd * (8 * d * d + 4 * T * d + 4 * d * d + 4 * S * d + 4 * d * f + 2 * rp) + B * S * nd * 4 * d * d
+    return 3.0 * (enc + dec + B * T * 2 * d * V)
+
+
+def config_leg(name, hp, B, S, T, steps, peaks, rpr_k=0):
+    """Training throughput of another BASELINE config on this GPU: same Trainer / CUDA-graph path as the headline leg,
+    device-resident batches, CUDA-event timing.  Reports tokens/s, ms/step and the step-level fraction of the measured
+    sustained bf16 peak (whole-model FLOPs / time: everything in the step counts as time, only the model's algorithmic
+    FLOPs count as work)."""
+    import torch
+    from zero_b200.engine import Engine
+    from zero_b200.train import Trainer
+    eng = Engine(hp, VOCAB, VOCAB, device="cuda")
+    eng.ps.init_random(1234)
+    trainer = Trainer(eng, hp, world_size=1, use_graph=True)
+    g = torch.Generator().manual_seed(99)
+    batches = []
+    for i in range(4):
+        src = torch.randint(3, VOCAB, (B, S), generator=g, dtype=torch.int32)
+        tgt = torch.randint(3, VOCAB, (B, T), generator=g, dtype=torch.int32)
+        src[:, -1] = 2
+        tgt[:, -1] = 2
+        batches.append((src.cuda(), tgt.cuda()))
+    for i in range(3):
+        trainer.step(*batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = trainer.step(*batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = model_flops_per_step(hp, B, S, T, VOCAB, rpr_k)
+    tf = flops / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    out = {"config": name, "metric": METRIC, "value": B * T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "batch": B, "src_len": S, "tgt_len": T, "final_loss": float(loss.item()),
+           "model_tflop_per_step": flops / 1e12,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                        "note": "step-level: whole-model algorithmic FLOPs over the whole step time"}}
+    del trainer, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def layer_peak_leg(peaks, iters=5):
+    """The north-star kernel shape: ONE Transformer encoder layer (models/transformer.py:45-69: self-attention ->
+    residual + LN -> FFN -> residual + LN) forward + backward on [4096, 64, 512] bf16 = 262 144 tokens, 5.051 TFLOP
+    algorithmic, timed with CUDA events; target >= 40 % of the bf16 tensor peak."""
+    import torch
+    from zero_b200.engine import Engine
+    from zero_b200.params import transformer_base
+    hp = transformer_base(num_encoder_layer=1, num_decoder_layer=1)
+    eng = Engine(hp, 1024, 1024)
+    eng.ps.init_random(1)
+    eng.enable_side_stream(True)
+    c = eng.cfg
+    B, S = 4096, 64
+    N = B * S
+    x = torch.randn(N, c.d, device="cuda").to(torch.bfloat16)
+    d_out = (torch.randn(N, c.d, device="cuda") * 0.01).to(torch.bfloat16)
+    src_len = torch.full((B,), S, dtype=torch.int32, device="cuda")
+
+    def step():
+        sv = {"att": {}, "ln1": {}, "ffn": {}, "ln2": {}}
+        y = eng._self_attn_fwd("enc0.self", x, B, S, src_len, False, sv["att"], "L.att")
+        x1 = eng._ln_fwd("enc0.self.ln", x, y, N, sv["ln1"], "L.ln1")
+        y2 = eng._ffn_fwd("enc0.ffn", x1, N, sv["ffn"], "L.ffn")
+        eng._ln_fwd("enc0.ffn.ln", x1, y2, N, sv["ln2"], "L.ln2")
+        ds2, dy2 = eng._ln_bwd("enc0.ffn.ln", d_out, None, N, sv["ln2"], "L.bw.ln2", eng.ps.g("enc0.ffn.w2.b"))
+        dx1 = eng._ffn_bwd("enc0.ffn", x1, dy2, N, sv["ffn"], "L.bw.ffn")
+        ds1, dy1 = eng._ln_bwd("enc0.self.ln", ds2, dx1, N, sv["ln1"], "L.bw.ln1", eng.ps.g("enc0.self.o.b"))
+        eng._self_attn_bwd("enc0.self", x, dy1, B, S, sv["att"], "L.bw.att")
+        eng._side_join()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 19267584.0 * N
+    tf = flops / (ms * 1e-3) / 1e12
+    burst = float(peaks.get("bf16_tflops", 1590.0))
+    out = {"shape": [B, S, c.d], "tokens": N, "ms_fwd_bwd": ms, "algorithmic_tflop": flops / 1e12,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if "bf16_tflops" in peaks else "fallback"},
+           "frac_of_nominal_2250": tf / 2250.0,
+           "frac_of_measured_sustained": tf / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+           "target": "north_star: >= 0.40 of the sm_100a tensor-pipe peak"}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_legs(peaks):
+    """BASELINE configs[3] and [4] as training-throughput legs + the encoder-layer peak shape (N = 1 only)."""
+    from zero_b200.params import transformer_base
+    legs = {}
+    try:
+        legs["layer_peak"] = layer_peak_leg(peaks)
+    except Exception as e:      # a secondary leg must not take the headline line down with it
+        legs["layer_peak"] = {"error": repr(e)[:300]}
+    try:
+        hp = transformer_base(model_name="transformer_rpr", scope_name="transformer_rpr", max_relative_position=16)
+        legs["configs3_rpr_len128"] = config_leg(
+            "transformer_rpr 6+6 d=512, src / tgt len 128, max_relative_position 16, 32 sentences = 4096 target tokens "
+            "per GPU per step (BASELINE configs[3])", hp, 32, 128, 128, 20, peaks, rpr_k=16)
+    except Exception as e:
+        legs["configs3_rpr_len128"] = {"error": repr(e)[:300]}
+    try:
+        hp = transformer_base(num_encoder_layer=24, num_decoder_layer=6, deep_transformer_init=True,
+                              initializer="uniform_unit_scaling", initializer_gain=1.0)
+        legs["configs4_deep_len1024"] = config_leg(
+            "24-layer DS-Init encoder + 6-layer decoder d=512, src len 1024 (token ids in place of the speech "
+            "front-end, which is not in the reference checkout), tgt len 64, 8 sentences per GPU per step "
+            "(BASELINE configs[4])", hp, 8, 1024, 64, 10, peaks)
+    except Exception as e:
+        legs["configs4_deep_len1024"] = {"error": repr(e)[:300]}
+    return legs
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def gemm_roofline(eng, src, tgt, peaks):
     """Dominant kernel = zb_gemm (tcgen05, 201 launches per step).  The GEMM launches of one real step are recorded
@@ -427,9 +565,14 @@ def run_ours(args):
         "model_tflops_per_gpu": model_flops / (ms / args.steps * 1e-3) / 1e12,
         "cpu_baseline": cpu_baseline,
         "decode": decode_bench("cuda:%d" % local) if (world == 1 and not args.no_decode) else None,
+        "legs": None,
         "clocks": clocks,
         "final_loss": final_loss,
     }
+    if world == 1 and not args.no_extra:
+        del trainer, eng
+        torch.cuda.empty_cache()
+        out["legs"] = extra_legs(peaks)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -444,6 +587,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] / configs[4] / layer-peak legs")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else min(args.steps, 50)

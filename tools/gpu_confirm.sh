@@ -11,5 +11,5 @@ timeout 200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_
 timeout 60 python tools/trace_step.py --decode --csv gpurun_out/${tag}_decode_timeline.csv > gpurun_out/${tag}_decode_trace.log 2>&1
 timeout 150 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
   -k regex:gemm2_bf16_tcgen05 --csv --log-file gpurun_out/${tag}_gemm_traffic.csv \
-  python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-decode > gpurun_out/${tag}_ncu_traffic.log 2>&1
+  python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-decode --no-extra > gpurun_out/${tag}_ncu_traffic.log 2>&1
 tail -4 gpurun_out/${tag}_tests.log; cut -c1-400 gpurun_out/${tag}_bench.json; tail -2 gpurun_out/${tag}_bench.err; head -30 gpurun_out/${tag}_decode_trace.log

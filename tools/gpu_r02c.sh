@@ -14,6 +14,6 @@ timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_tests.log 2>
 echo "suite rc=$?"; tail -5 gpurun_out/${tag}_tests.log | cut -c1-300
 timeout 120 python tools/trace_step.py --steps 3 --csv gpurun_out/${tag}_timeline.csv > gpurun_out/${tag}_timeline.log 2>&1
 grep -E "span|fa" gpurun_out/${tag}_timeline.log
-ZB_ATTN_TC=0 timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_mma.json 2>/dev/null
-timeout 100 python bench.py --no-cpu-baseline --no-decode --steps 50 > gpurun_out/${tag}_bench_tc.json 2>/dev/null
+ZB_ATTN_TC=0 timeout 100 python bench.py --no-cpu-baseline --no-decode --no-extra --steps 50 > gpurun_out/${tag}_bench_mma.json 2>/dev/null
+timeout 100 python bench.py --no-cpu-baseline --no-decode --no-extra --steps 50 > gpurun_out/${tag}_bench_tc.json 2>/dev/null
 cut -c1-200 gpurun_out/${tag}_bench_mma.json gpurun_out/${tag}_bench_tc.json

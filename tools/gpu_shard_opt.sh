@@ -11,7 +11,7 @@ tail -5 gpurun_out/${tag}_shard_tests.log
 if grep -q "^rc=0" gpurun_out/${tag}_shard_tests.log; then
   for mode in 0 1 p2p; do
     ZB_SHARD_OPT=$mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
-      --master-port $((29500 + RANDOM % 1000)) bench.py --gpus $n --steps 50 --warmup 5 --no-cpu-baseline --no-decode \
+      --master-port $((29500 + RANDOM % 1000)) bench.py --gpus $n --steps 50 --warmup 5 --no-cpu-baseline --no-decode --no-extra \
       > gpurun_out/${tag}_bench_n${n}_shard_${mode}.json 2> gpurun_out/${tag}_bench_n${n}_shard_${mode}.err
     cut -c1-160 gpurun_out/${tag}_bench_n${n}_shard_${mode}.json
   done
