@@ -700,6 +700,62 @@ def test_attention_tcgen05(B, h, Lq, Lk, causal, klen, fused, monkeypatch):
         torch.testing.assert_close(dq2.float(), grads[0][0].float(), atol=1e-6, rtol=0)
 
 
+@pytest.mark.parametrize("B,h,Lq,Lk,causal,klen,R,drop", [
+    (2, 8, 128, 128, False, True, 16, 0.0),    # BASELINE configs[3]: encoder self attention
+    (2, 8, 128, 128, True, False, 16, 0.0),    # ... decoder self attention
+    (3, 2, 100, 128, False, True, 16, 0.0),    # ... cross attention with ragged lengths
+    (2, 2, 40, 36, False, True, 6, 0.0),       # the len-40 golden model's shapes
+    (2, 4, 20, 45, False, True, 16, 0.0),
+    (2, 2, 128, 128, True, False, 1, 0.0),     # three buckets: almost everything is clipped
+    (2, 4, 128, 128, True, True, 16, 0.25),    # with attention dropout (same keep mask as the generic kernels)
+])
+def test_attention_tcgen05_relative_positions(B, h, Lq, Lk, causal, klen, R, drop, monkeypatch):
+    """modules/rpr.py:10-75 on the tensor cores (attention_tc.cu: bucket GEMMs Q E_k^T / W E_v and their gradients)
+    against the torch restatement (einsum over the gathered [L, L, dh] tensor, as the reference does) and against
+    the generic CUDA-core kernels (ZB_ATTN_TC=0), including d_rpr_keys / d_rpr_values."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    D = h * 64
+    q, k, v = rnd(B, Lq, D, seed=61), rnd(B, Lk, D, seed=62), rnd(B, Lk, D, seed=63)
+    ek, ev = rnd(2 * R + 1, 64, scale=0.5, seed=64), rnd(2 * R + 1, 64, scale=0.5, seed=65)
+    d_o = rnd(B, Lq, D, seed=66)
+    key_len = None
+    if klen:
+        key_len = torch.randint(1, Lk + 1, (B,), dtype=torch.int32, device=dev())
+        key_len[0] = Lk
+    seed = torch.tensor([4242], dtype=torch.int64, device=dev())
+    res = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("ZB_ATTN_TC", tc)
+        before = L.path_launch_count("attn_tc")
+        o = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+        lse = torch.empty(B, h, Lq, device=dev())
+        a = ops.attention_args(q, k, v, o, h, key_len=key_len, causal=causal, lse=lse, rpr_k=ek, rpr_v=ev, max_rel=R,
+                               dropout=(drop, 9, seed) if drop else None)
+        ops.attention_fwd(a)
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        dek, dev_ = torch.zeros(2 * R + 1, 64, device=dev()), torch.zeros(2 * R + 1, 64, device=dev())
+        ops.attention_bwd(a, d_o, dq, dk, dv, torch.empty(B, h, Lq, device=dev()), dek, dev_)
+        assert L.path_launch_count("attn_tc") == before + 2 * int(tc)
+        res.append((o, lse, dq, dk, dv, dek, dev_))
+    for x0, x1 in zip(res[0][:5], res[1][:5]):
+        torch.testing.assert_close(x1.float(), x0.float(), atol=4e-2, rtol=4e-2)
+    for x0, x1 in zip(res[0][5:], res[1][5:]):
+        torch.testing.assert_close(x1, x0, atol=0.15, rtol=5e-2)
+    if drop:
+        return
+    leaves = [t.float().detach().clone().requires_grad_(True) for t in (q, k, v)]
+    ekf, evf = ek.float().requires_grad_(True), ev.float().requires_grad_(True)
+    ref = _attn_ref(leaves[0], leaves[1], leaves[2], h, key_len, causal, 0, 1e8, ekf, evf, R, False)
+    o, lse, dq, dk, dv, dek, dev_ = res[1]
+    torch.testing.assert_close(o.float(), ref.detach(), atol=3e-2, rtol=3e-2)
+    ref.backward(d_o.float())
+    for got, want in zip((dq, dk, dv), [t.grad for t in leaves]):
+        torch.testing.assert_close(got.float(), want, atol=6e-2, rtol=5e-2)
+    torch.testing.assert_close(dek, ekf.grad, atol=0.15, rtol=5e-2)
+    torch.testing.assert_close(dev_, evf.grad, atol=0.15, rtol=5e-2)
+
+
 @pytest.mark.parametrize("B,h,Lq,Lk,causal", [(4, 8, 64, 64, True), (2, 4, 128, 128, False), (2, 2, 200, 200, True)])
 def test_attention_tcgen05_dropout_matches_the_mma_kernels(B, h, Lq, Lk, causal, monkeypatch):
     """Attention dropout (func.py:245): the keep mask is a pure function of (seed, site, [b, h, i, j]) shared by every

@@ -43,6 +43,7 @@ namespace zb {
 
 int make_map_heads(CUtensorMap* m, const void* ptr, uint64_t len, uint64_t heads, uint64_t batch, uint64_t ld,
                    uint64_t bs, uint32_t box_rows, uint32_t box_heads);  // gemm_tcgen05.cu
+int make_map(CUtensorMap* m, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box1);
 
 namespace fat {
 
@@ -831,6 +832,651 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
   if (threadIdx.x == 0) FAT_TRACE(3);
 }
 
+// ================================================================================================ relative positions
+// modules/rpr.py:10-75 (Shaw et al.) on the tensor cores, for blocks of one head with lq, lk <= 128 (BASELINE
+// configs[3]) and max_relative_position <= 16.  The reference gathers z[i, j, :] = E[clip(i - j, -R, R) + R] into an
+// [L, L, dh] tensor and runs two extra batched matmuls over it; here the 2R + 1 rows of E are a GEMM operand:
+//   logits   S[i, j] += QE[i, u(i, j)]      with QE = Q E_k^T          [128 x 64 slots]  one more MMA per block
+//   context  O[i, :] += sum_u W[i, u] E_v[u]  with W[i, u] = sum of the (dropped) weights of bucket u: P is
+//            bucket-summed per row into a [128 x 64 slots] bf16 A operand, O = P V + W E_v is ONE accumulation
+//   backward dP[i, j] += (dO E_v^T)[i, u],  dQ += DSb E_k,  dE_k = DSb^T Q,  dE_v = W^T dO  with DSb = bucket-summed dS
+// A row's buckets 1 .. 2R - 1 hold exactly one key each (j = i - u + R): the bucket sum is a skewed copy, done by the
+// row's two threads with 2-byte shared-memory stores; the clipped buckets 0 / 2R collect everything further away and are
+// summed in registers.  Each of the row's two threads has its own pair of clipped slots (0, 2R for the first half of
+// the columns; 2R + 1, 2R + 2 for the second, rows 2R + 1 / 2R + 2 of the E tiles being copies of rows 0 / 2R), so the
+// halves never have to be added.  QE is staged once per block as fp32 [128][36] in shared memory (row pitch 36 words:
+// the skewed read row * 36 + (row + c) is bank-conflict free).
+constexpr int kQeStride = 36;   // >= 2 * 16 + 3 slots; 4 * odd: conflict-free 16-byte row writes and skewed reads
+constexpr int kMaxRel = 16;
+
+struct RprGeom {
+  int R, i_abs, ibase;  // max_rel; absolute position of this thread's row; of its warp's first row
+};
+// out[jj] = tab[clip(i_abs - (base + jj), -R, R) + R] for the chunk's 32 keys; lo / hi = tab[0] / tab[2R]
+__device__ __forceinline__ void rpr_gather(float (&out)[32], const float* tab, float lo, float hi, const RprGeom& g,
+                                           int base) {
+  const int dmin = g.ibase - base - 31, dmax = g.ibase + 31 - base;  // over the warp's rows x the chunk's keys
+  if (dmin >= g.R) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) out[jj] = hi;
+  } else if (dmax <= -g.R) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) out[jj] = lo;
+  } else {
+    const int u0 = g.i_abs - base + g.R;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int u = u0 - jj;
+      out[jj] = u <= 0 ? lo : (u >= 2 * g.R ? hi : tab[u]);
+    }
+  }
+}
+// bucket sums of one chunk's values: in-band buckets are 2-byte stores into row `row` of the [128][64 slots] bf16 atom,
+// the clipped ones accumulate in lo / hi
+__device__ __forceinline__ void rpr_scatter(uint32_t atom, int row, const float (&val)[32], float& lo, float& hi,
+                                            const RprGeom& g, int base) {
+  const int dmin = g.ibase - base - 31, dmax = g.ibase + 31 - base;
+  if (dmin >= g.R) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) hi += val[jj];
+  } else if (dmax <= -g.R) {
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) lo += val[jj];
+  } else {
+    const int u0 = g.i_abs - base + g.R;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int u = u0 - jj;
+      if (u <= 0) lo += val[jj];
+      else if (u >= 2 * g.R) hi += val[jj];
+      else {
+        const __nv_bfloat16 hv = __float2bfloat16(val[jj]);
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(atom + swz_off(row, u >> 3) + (uint32_t)((u & 7) * 2)),
+                     "h"(*reinterpret_cast<const unsigned short*>(&hv))
+                     : "memory");
+      }
+    }
+  }
+}
+__device__ __forceinline__ void rpr_store_slot(uint32_t atom, int row, int u, float v) {
+  const __nv_bfloat16 hv = __float2bfloat16(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(atom + swz_off(row, u >> 3) + (uint32_t)((u & 7) * 2)),
+               "h"(*reinterpret_cast<const unsigned short*>(&hv))
+               : "memory");
+}
+// rows 2R + 1 / 2R + 2 of an E tile ([64 slots][64 channels] bf16, swizzled) = copies of rows 0 / 2R (one warp)
+__device__ __forceinline__ void rpr_dup_rows(uint8_t* tile, int R, int lane) {
+  if (lane < 16) {
+    const int u = lane & 7, src = lane < 8 ? 0 : 2 * R, dst = lane < 8 ? 2 * R + 1 : 2 * R + 2;
+    *reinterpret_cast<uint4*>(tile + swz_off(dst, u)) = *reinterpret_cast<const uint4*>(tile + swz_off(src, u));
+  }
+}
+// 32 + 4 fp32 values of one TMEM row (columns [col, col + 36)) -> tab[0 .. 36)
+__device__ __forceinline__ void rpr_stage_row(float* tab, uint32_t taddr) {
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(taddr, ra);
+  tmem_ld_32x32b_x32(taddr + 32, rb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(tab + 4 * c) = make_float4(__uint_as_float(ra[4 * c]), __uint_as_float(ra[4 * c + 1]),
+                                                           __uint_as_float(ra[4 * c + 2]), __uint_as_float(ra[4 * c + 3]));
+  *reinterpret_cast<float4*>(tab + 32) =
+      make_float4(__uint_as_float(rb[0]), __uint_as_float(rb[1]), __uint_as_float(rb[2]), __uint_as_float(rb[3]));
+}
+
+struct RprFwdSmem {
+  __nv_bfloat16 q[kTile], k[kTile], v[kTile];
+  __nv_bfloat16 p[2][kTile];
+  __nv_bfloat16 w[kTile];                      // bucket-summed weights [128 rows][64 slots]
+  __nv_bfloat16 ek[kTile / 2], ev[kTile / 2];  // [64 slots][64 channels]; slots past 2R + 2 are zero
+  __nv_bfloat16 ostage[kTile];
+  float qe[128 * kQeStride];
+  float xmax[2][128], xl[2][128];
+  uint64_t full, empty, bar_tab, bar_dup, bar_s, bar_p, bar_o, ost_full, ost_free;
+  uint32_t tmem_slot;
+};
+// TMEM columns: S 0..127, O 128..191, QE 192..255
+
+template <bool DROP>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_tc_rpr_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                  const __grid_constant__ CUtensorMap tma_ek, const __grid_constant__ CUtensorMap tma_ev, const Params p,
+                  const int R) {
+  extern __shared__ uint8_t fat_raw[];
+  RprFwdSmem& T = *reinterpret_cast<RprFwdSmem*>((reinterpret_cast<uintptr_t>(fat_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_o);
+    tma_prefetch_desc(&tma_ek);
+    tma_prefetch_desc(&tma_ev);
+    mbar_init(&T.full, 1);
+    mbar_init(&T.empty, 1);
+    mbar_init(&T.bar_tab, 1);
+    mbar_init(&T.bar_dup, kRowWarps);
+    mbar_init(&T.bar_s, 1);
+    mbar_init(&T.bar_p, kRowWarps);
+    mbar_init(&T.bar_o, 1);
+    mbar_init(&T.ost_full, kRowWarps);
+    mbar_init(&T.ost_free, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&T.tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = T.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Walk w(p, true);
+      bool ok = w.start();
+      grid_dep_wait();
+      mbar_arrive_expect_tx(&T.bar_tab, 2 * (kTile / 2) * 2);
+      tma_load_2d(T.ek, &tma_ek, &T.bar_tab, 0, 0);
+      tma_load_2d(T.ev, &tma_ev, &T.bar_tab, 0, 0);
+      long n = 0;
+      for (; ok; ok = w.next(), ++n) {
+        mbar_wait(&T.empty, (uint32_t)((n & 1) ^ 1));
+        mbar_arrive_expect_tx(&T.full, 3 * kTile * 2);
+        tma_load_4d(T.q, &tma_q, &T.full, 0, 0, w.hs, w.b);
+        tma_load_4d(T.k, &tma_k, &T.full, 0, 0, w.hs, w.b);
+        tma_load_4d(T.v, &tma_v, &T.full, 0, 0, w.hs, w.b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0u, 0u);
+      constexpr uint32_t id_qe = umma_idesc_bf16(128, 64, 0u, 0u);  // QE = Q E_k^T: both K-major
+      constexpr uint32_t id_o = umma_idesc_bf16(128, 64, 0u, 1u);
+      const uint32_t sq = smem_u32(T.q), sk = smem_u32(T.k), sv = smem_u32(T.v), sw = smem_u32(T.w),
+                     sek = smem_u32(T.ek), sev = smem_u32(T.ev);
+      mbar_wait(&T.bar_dup, 0);  // implies the tables have landed and their duplicate rows are written
+      Walk w(p, true);
+      long n = 0;
+      for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+        mbar_wait(&T.full, (uint32_t)(n & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem_base, umma_smem_desc(sq + kk * 32, 0, 1024), umma_smem_desc(sk + kk * 32, 0, 1024), id_s,
+                       kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ss(tmem_base + 192, umma_smem_desc(sq + kk * 32, 0, 1024), umma_smem_desc(sek + kk * 32, 0, 1024),
+                       id_qe, kk > 0 ? 1u : 0u);
+        umma_commit(&T.bar_s);
+        mbar_wait(&T.bar_p, (uint32_t)(n & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // O = P V
+          umma_bf16_ss(tmem_base + 128, umma_smem_desc(smem_u32(T.p[kk >> 2]) + (kk & 3) * 32, 0, 1024),
+                       umma_smem_desc(sv + kk * 2048, 64 * 128, 1024), id_o, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // O += W E_v (k = slots)
+          umma_bf16_ss(tmem_base + 128, umma_smem_desc(sw + kk * 32, 0, 1024),
+                       umma_smem_desc(sev + kk * 2048, 64 * 128, 1024), id_o, 1u);
+        umma_commit(&T.bar_o);
+        umma_commit(&T.empty);
+      }
+    }
+  } else if (warp == 2 + kRowWarps) {
+    if (lane == 0) {
+      Walk w(p, true);
+      long n = 0;
+      for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+        mbar_wait(&T.ost_full, (uint32_t)(n & 1));
+        tma_store_4d(&tma_o, T.ostage, 0, 0, w.hs, w.b);
+        bulk_commit_group();
+        bulk_wait_read_all();
+        mbar_arrive(&T.ost_free);
+      }
+      bulk_wait_all();
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t p_atom0 = smem_u32(T.p[0]), p_atom1 = smem_u32(T.p[1]), w_atom = smem_u32(T.w), ost = smem_u32(T.ostage);
+    const float sl2 = p.scale * kLog2e, inf2 = p.inf_value * kLog2e;
+    float* qrow = T.qe + row * kQeStride;
+    grid_dep_wait();
+    const Drop<DROP> drop(p);
+    mbar_wait(&T.bar_tab, 0);
+    if (warp == 2) {
+      rpr_dup_rows(reinterpret_cast<uint8_t*>(T.ek), R, lane);
+      rpr_dup_rows(reinterpret_cast<uint8_t*>(T.ev), R, lane);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&T.bar_dup);
+    Walk w(p, true);
+    long n = 0;
+    for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+      const int b = w.b, h = w.hs, i = row;
+      const int kl = p.key_len ? __ldg(p.key_len + b) : p.lk;
+      const int jv = min(kl, p.causal ? i + p.q_offset + 1 : p.lk);
+      const bool vis = jv >= 1;
+      RprGeom g;
+      g.R = R;
+      g.i_abs = i + p.q_offset;
+      g.ibase = quad * 32 + p.q_offset;
+      mbar_wait(&T.bar_s, (uint32_t)(n & 1));
+      tc_fence_after();
+      // this row's QE: the first thread stages slots 0..31, the second 32..35; both clear their half of W
+      if (half == 0) {
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_lane + 192, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(qrow + 4 * c) = make_float4(__uint_as_float(ra[4 * c]), __uint_as_float(ra[4 * c + 1]),
+                                                                  __uint_as_float(ra[4 * c + 2]), __uint_as_float(ra[4 * c + 3]));
+      } else {
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_lane + 192 + 32, ra);
+        tmem_ld_wait();
+        *reinterpret_cast<float4*>(qrow + 32) =
+            make_float4(__uint_as_float(ra[0]), __uint_as_float(ra[1]), __uint_as_float(ra[2]), __uint_as_float(ra[3]));
+      }
+      store_chunk_zero(w_atom, row, 4 * half);
+      row_warps_sync();
+      const float qlo = qrow[0], qhi = qrow[2 * R];
+      // ---- pass 1: the maximum of this thread's two chunks, then of the row
+      float mt = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c32 = 2 * half + cc, base = c32 * 32;
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_lane + c32 * 32, ra);
+        tmem_ld_wait();
+        float bias[32];
+        rpr_gather(bias, qrow, qlo, qhi, g, base);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) ra[jj] = __float_as_uint(__uint_as_float(ra[jj]) + bias[jj]);
+        const int nv = jv - base, nb = p.lk - base;
+        mt = fmaxf(mt, chunk_max(ra, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2));
+      }
+      {
+        float* xm = &T.xmax[0][0];
+        xm[half * 128 + row] = mt;
+        row_warps_sync();
+        mt = fmaxf(xm[row], xm[128 + row]);
+      }
+      // ---- pass 2: weights, bucket sums
+      float l_run = 0.f, wlo = 0.f, whi = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c32 = 2 * half + cc, base = c32 * 32;
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_lane + c32 * 32, ra);
+        tmem_ld_wait();
+        float e[32];
+        rpr_gather(e, qrow, qlo, qhi, g, base);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) ra[jj] = __float_as_uint(__uint_as_float(ra[jj]) + e[jj]);
+        const int nv = jv - base, nb = p.lk - base;
+        l_run += chunk_exp(ra, e, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2, mt);
+        if (DROP) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) e[jj] *= drop.mul(p, b, h, i, base + jj);
+        }
+        store_chunk_bf16((c32 >> 1) ? p_atom1 : p_atom0, row, (c32 & 1) * 4, e);
+        rpr_scatter(w_atom, row, e, wlo, whi, g, base);
+      }
+      rpr_store_slot(w_atom, row, half ? 2 * R + 1 : 0, wlo);
+      rpr_store_slot(w_atom, row, half ? 2 * R + 2 : 2 * R, whi);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&T.bar_p);
+      // ---- O = P V + W E_v
+      mbar_wait(&T.bar_o, (uint32_t)(n & 1));
+      tc_fence_after();
+      uint32_t ro[32];
+      tmem_ld_32x32b_x32(t_lane + 128 + 32 * half, ro);
+      tmem_ld_wait();
+      {
+        float* xl = &T.xl[0][0];
+        xl[half * 128 + row] = l_run;
+        mbar_wait(&T.ost_free, (uint32_t)((n & 1) ^ 1));
+        row_warps_sync();
+        const float l_tot = xl[row] + xl[128 + row];
+        const float inv = 1.f / l_tot;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(ost + swz_off(row, 4 * half + c),
+                 pack_bf16x2(__uint_as_float(ro[8 * c + 0]) * inv, __uint_as_float(ro[8 * c + 1]) * inv),
+                 pack_bf16x2(__uint_as_float(ro[8 * c + 2]) * inv, __uint_as_float(ro[8 * c + 3]) * inv),
+                 pack_bf16x2(__uint_as_float(ro[8 * c + 4]) * inv, __uint_as_float(ro[8 * c + 5]) * inv),
+                 pack_bf16x2(__uint_as_float(ro[8 * c + 6]) * inv, __uint_as_float(ro[8 * c + 7]) * inv));
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&T.ost_full);
+        if (half == 0 && i < p.lq && p.lse) p.lse[((long long)b * p.heads + h) * p.lq + i] = mt * kLn2 + __logf(l_tot);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+struct RprBwdSmem {
+  __nv_bfloat16 q[kTile], k[kTile], v[kTile], d_o[kTile];
+  __nv_bfloat16 p[2][kTile], ds[2][kTile];
+  __nv_bfloat16 w[kTile], dsb[kTile];          // bucket-summed dropped weights / logit gradients [128 rows][64 slots]
+  __nv_bfloat16 ek[kTile / 2], ev[kTile / 2];
+  float qe[128 * kQeStride], dov[128 * kQeStride];
+  float xdelta[2][128];
+  uint64_t full, empty, bar_tab, bar_dup, bar_s, bar_p, bar_o, stg_full, bar_tfree;
+  uint32_t tmem_slot;
+};
+// TMEM columns: S 0..127, dP 128..255, QE 256..319 (then dQ), dO E_v^T 320..383 (then dK), dV 384..447;
+// after the row warps have written P / dS: dE_k 0..63 and dE_v 64..127 (M = 64: rows 16 q + t in lanes t < 16 of quadrant q)
+
+template <bool DROP>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_tc_rpr_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                  const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ CUtensorMap tma_dk,
+                  const __grid_constant__ CUtensorMap tma_dv, const __grid_constant__ CUtensorMap tma_ek,
+                  const __grid_constant__ CUtensorMap tma_ev, const Params p, const int R, float* __restrict__ d_ek,
+                  float* __restrict__ d_ev) {
+  extern __shared__ uint8_t fat_raw[];
+  RprBwdSmem& T = *reinterpret_cast<RprBwdSmem*>((reinterpret_cast<uintptr_t>(fat_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    tma_prefetch_desc(&tma_do);
+    tma_prefetch_desc(&tma_dq);
+    tma_prefetch_desc(&tma_dk);
+    tma_prefetch_desc(&tma_dv);
+    tma_prefetch_desc(&tma_ek);
+    tma_prefetch_desc(&tma_ev);
+    mbar_init(&T.full, 1);
+    mbar_init(&T.empty, 1);
+    mbar_init(&T.bar_tab, 1);
+    mbar_init(&T.bar_dup, kRowWarps);
+    mbar_init(&T.bar_s, 1);
+    mbar_init(&T.bar_p, kRowWarps);
+    mbar_init(&T.bar_o, 1);
+    mbar_init(&T.stg_full, kRowWarps);
+    mbar_init(&T.bar_tfree, kRowWarps);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(&T.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = T.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Walk w(p, false);
+      bool ok = w.start();
+      grid_dep_wait();
+      mbar_arrive_expect_tx(&T.bar_tab, 2 * (kTile / 2) * 2);
+      tma_load_2d(T.ek, &tma_ek, &T.bar_tab, 0, 0);
+      tma_load_2d(T.ev, &tma_ev, &T.bar_tab, 0, 0);
+      long n = 0;
+      for (; ok; ok = w.next(), ++n) {
+        mbar_wait(&T.empty, (uint32_t)((n & 1) ^ 1));
+        mbar_arrive_expect_tx(&T.full, 4 * kTile * 2);
+        tma_load_4d(T.q, &tma_q, &T.full, 0, 0, w.hs, w.b);
+        tma_load_4d(T.k, &tma_k, &T.full, 0, 0, w.hs, w.b);
+        tma_load_4d(T.d_o, &tma_do, &T.full, 0, 0, w.hs, w.b);
+        tma_load_4d(T.v, &tma_v, &T.full, 0, 0, w.hs, w.b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_s = umma_idesc_bf16(128, 128, 0u, 0u);
+      constexpr uint32_t id_qe = umma_idesc_bf16(128, 64, 0u, 0u);
+      constexpr uint32_t id_kmaj = umma_idesc_bf16(128, 64, 0u, 1u);
+      constexpr uint32_t id_mn = umma_idesc_bf16(128, 64, 1u, 1u);
+      constexpr uint32_t id_mn64 = umma_idesc_bf16(64, 64, 1u, 1u);  // dE = (bucket sums)^T x rows: 64 slots tall
+      const uint32_t sq = smem_u32(T.q), sk = smem_u32(T.k), sv = smem_u32(T.v), sdo = smem_u32(T.d_o);
+      const uint32_t sp = smem_u32(T.p[0]), sds = smem_u32(T.ds[0]), sw = smem_u32(T.w), sdsb = smem_u32(T.dsb);
+      const uint32_t sek = smem_u32(T.ek), sev = smem_u32(T.ev);
+      mbar_wait(&T.bar_dup, 0);
+      Walk w(p, false);
+      long n = 0;
+      for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+        mbar_wait(&T.full, (uint32_t)(n & 1));
+        if (n > 0) mbar_wait(&T.bar_tfree, (uint32_t)((n - 1) & 1));  // the row warps have drained dE_k / dE_v
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // S = Q K^T
+          umma_bf16_ss(tmem_base, umma_smem_desc(sq + kk * 32, 0, 1024), umma_smem_desc(sk + kk * 32, 0, 1024), id_s,
+                       kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dP = dO V^T
+          umma_bf16_ss(tmem_base + 128, umma_smem_desc(sdo + kk * 32, 0, 1024), umma_smem_desc(sv + kk * 32, 0, 1024),
+                       id_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // QE = Q E_k^T
+          umma_bf16_ss(tmem_base + 256, umma_smem_desc(sq + kk * 32, 0, 1024), umma_smem_desc(sek + kk * 32, 0, 1024),
+                       id_qe, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dO E_v^T
+          umma_bf16_ss(tmem_base + 320, umma_smem_desc(sdo + kk * 32, 0, 1024), umma_smem_desc(sev + kk * 32, 0, 1024),
+                       id_qe, kk > 0 ? 1u : 0u);
+        umma_commit(&T.bar_s);
+        mbar_wait(&T.bar_p, (uint32_t)(n & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dQ = dS K
+          umma_bf16_ss(tmem_base + 256, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 0, 1024),
+                       umma_smem_desc(sk + kk * 2048, 64 * 128, 1024), id_kmaj, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // dQ += DSb E_k (k = slots)
+          umma_bf16_ss(tmem_base + 256, umma_smem_desc(sdsb + kk * 32, 0, 1024),
+                       umma_smem_desc(sek + kk * 2048, 64 * 128, 1024), id_kmaj, 1u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dK = dS^T Q
+          umma_bf16_ss(tmem_base + 320, umma_smem_desc(sds + kk * 2048, 16384, 1024),
+                       umma_smem_desc(sq + kk * 2048, 64 * 128, 1024), id_mn, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dV = P^T dO
+          umma_bf16_ss(tmem_base + 384, umma_smem_desc(sp + kk * 2048, 16384, 1024),
+                       umma_smem_desc(sdo + kk * 2048, 64 * 128, 1024), id_mn, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dE_k = DSb^T Q (k = the block's 128 query rows)
+          umma_bf16_ss(tmem_base, umma_smem_desc(sdsb + kk * 2048, 16384, 1024),
+                       umma_smem_desc(sq + kk * 2048, 64 * 128, 1024), id_mn64, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dE_v = W^T dO
+          umma_bf16_ss(tmem_base + 64, umma_smem_desc(sw + kk * 2048, 16384, 1024),
+                       umma_smem_desc(sdo + kk * 2048, 64 * 128, 1024), id_mn64, kk > 0 ? 1u : 0u);
+        umma_commit(&T.bar_o);
+      }
+    }
+  } else if (warp == 2 + kRowWarps) {
+    if (lane == 0) {
+      Walk w(p, false);
+      long n = 0;
+      for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+        mbar_wait(&T.stg_full, (uint32_t)(n & 1));
+        tma_store_4d(&tma_dq, T.q, 0, 0, w.hs, w.b);
+        tma_store_4d(&tma_dk, T.k, 0, 0, w.hs, w.b);
+        tma_store_4d(&tma_dv, T.v, 0, 0, w.hs, w.b);
+        bulk_commit_group();
+        bulk_wait_read_all();
+        mbar_arrive(&T.empty);
+      }
+      bulk_wait_all();
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2, row = quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t p_atom0 = smem_u32(T.p[0]), p_atom1 = smem_u32(T.p[1]);
+    const uint32_t ds_atom0 = smem_u32(T.ds[0]), ds_atom1 = smem_u32(T.ds[1]);
+    const uint32_t w_atom = smem_u32(T.w), dsb_atom = smem_u32(T.dsb);
+    const float sl2 = p.scale * kLog2e, inf2 = p.inf_value * kLog2e;
+    float* qrow = T.qe + row * kQeStride;
+    float* vrow = T.dov + row * kQeStride;
+    grid_dep_wait();
+    const Drop<DROP> drop(p);
+    mbar_wait(&T.bar_tab, 0);
+    if (warp == 2) {
+      rpr_dup_rows(reinterpret_cast<uint8_t*>(T.ek), R, lane);
+      rpr_dup_rows(reinterpret_cast<uint8_t*>(T.ev), R, lane);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&T.bar_dup);
+    Walk w(p, false);
+    long n = 0;
+    for (bool ok = w.start(); ok; ok = w.next(), ++n) {
+      const int b = w.b, h = w.hs, i = row;
+      const int kl = p.key_len ? __ldg(p.key_len + b) : p.lk;
+      const bool row_ok = i < p.lq;
+      const int jv = row_ok ? min(kl, p.causal ? i + p.q_offset + 1 : p.lk) : 0;
+      const int jb = row_ok ? p.lk : 0;
+      RprGeom g;
+      g.R = R;
+      g.i_abs = i + p.q_offset;
+      g.ibase = quad * 32 + p.q_offset;
+      float delta = 0.f, lse2 = 0.f;
+      if (row_ok) {
+        const long long ch = h * 64 + 32 * half;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.o + (long long)b * p.bso + (long long)i * p.ldo + ch);
+        const uint4* drow = reinterpret_cast<const uint4*>(p.d_o + (long long)b * p.bsdo + (long long)i * p.lddo + ch);
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 a = __ldg(orow + c), d = __ldg(drow + c);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+            d4[e] = fmaf(x.x, y.x, fmaf(x.y, y.y, d4[e]));
+          }
+        }
+        delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        lse2 = p.lse[((long long)b * p.heads + h) * p.lq + i] * kLog2e;
+      }
+      T.xdelta[half][row] = delta;
+      mbar_wait(&T.bar_s, (uint32_t)(n & 1));
+      tc_fence_after();
+      // stage this row's QE (first thread) / dO E_v^T (second thread); clear the bucket-sum rows
+      if (half == 0) rpr_stage_row(qrow, t_lane + 256);
+      else rpr_stage_row(vrow, t_lane + 320);
+      store_chunk_zero(w_atom, row, 4 * half);
+      store_chunk_zero(dsb_atom, row, 4 * half);
+      row_warps_sync();
+      delta = T.xdelta[0][row] + T.xdelta[1][row];
+      const float qlo = qrow[0], qhi = qrow[2 * R], vlo = vrow[0], vhi = vrow[2 * R];
+      float wlo = 0.f, whi = 0.f, dlo = 0.f, dhi = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c32 = 2 * half + cc, base = c32 * 32;
+        uint32_t rs[32], rp[32];
+        tmem_ld_32x32b_x32(t_lane + c32 * 32, rs);
+        tmem_ld_32x32b_x32(t_lane + 128 + c32 * 32, rp);
+        tmem_ld_wait();
+        float e[32], dsv[32];
+        rpr_gather(e, qrow, qlo, qhi, g, base);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) rs[jj] = __float_as_uint(__uint_as_float(rs[jj]) + e[jj]);
+        rpr_gather(dsv, vrow, vlo, vhi, g, base);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) rp[jj] = __float_as_uint(__uint_as_float(rp[jj]) + dsv[jj]);
+        const int nv = jv - base, nb = jb - base;
+        chunk_exp(rs, e, chunk_mode(nv, nb, jv >= 1), nv, nb, sl2, inf2, lse2);
+        if (DROP) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float dm = drop.mul(p, b, h, i, base + jj);
+            dsv[jj] = e[jj] * fmaf(__uint_as_float(rp[jj]), dm, -delta);
+            e[jj] *= dm;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) dsv[jj] = e[jj] * (__uint_as_float(rp[jj]) - delta);
+        }
+        const int u0 = (c32 & 1) * 4;
+        store_chunk_bf16((c32 >> 1) ? p_atom1 : p_atom0, row, u0, e);
+        store_chunk_bf16((c32 >> 1) ? ds_atom1 : ds_atom0, row, u0, dsv);
+        rpr_scatter(w_atom, row, e, wlo, whi, g, base);
+        rpr_scatter(dsb_atom, row, dsv, dlo, dhi, g, base);
+      }
+      rpr_store_slot(w_atom, row, half ? 2 * R + 1 : 0, wlo);
+      rpr_store_slot(w_atom, row, half ? 2 * R + 2 : 2 * R, whi);
+      rpr_store_slot(dsb_atom, row, half ? 2 * R + 1 : 0, dlo);
+      rpr_store_slot(dsb_atom, row, half ? 2 * R + 2 : 2 * R, dhi);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&T.bar_p);
+      mbar_wait(&T.bar_o, (uint32_t)(n & 1));
+      tc_fence_after();
+      auto stage_half = [&](uint32_t tile, const uint32_t (&r)[32], float mul) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          sts128(tile + swz_off(row, 4 * half + c),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 0]) * mul, __uint_as_float(r[8 * c + 1]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 2]) * mul, __uint_as_float(r[8 * c + 3]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 4]) * mul, __uint_as_float(r[8 * c + 5]) * mul),
+                 pack_bf16x2(__uint_as_float(r[8 * c + 6]) * mul, __uint_as_float(r[8 * c + 7]) * mul));
+      };
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(t_lane + 256 + 32 * half, ra);
+        tmem_ld_32x32b_x32(t_lane + 320 + 32 * half, rb);
+        tmem_ld_wait();
+        stage_half(smem_u32(T.q), ra, p.scale);
+        stage_half(smem_u32(T.k), rb, p.scale);
+        tmem_ld_32x32b_x32(t_lane + 384 + 32 * half, ra);
+        tmem_ld_wait();
+        stage_half(smem_u32(T.v), ra, 1.f);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&T.stg_full);
+      {
+        // dE_k / dE_v of this block: slot u = 16 quad + lane lives in the lanes < 16 of the quadrant
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32b_x32(t_lane + 32 * half, ra);
+        tmem_ld_32x32b_x32(t_lane + 64 + 32 * half, rb);
+        tmem_ld_wait();
+        const int u = 16 * quad + lane;
+        if (lane < 16 && u < 2 * R + 3) {
+          const int bucket = u <= 2 * R ? u : (u == 2 * R + 1 ? 0 : 2 * R);
+          float* dk_ = d_ek + bucket * 64 + 32 * half;
+          float* dv_ = d_ev + bucket * 64 + 32 * half;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            red_add_v4(dk_ + 4 * c, __uint_as_float(ra[4 * c]) * p.scale, __uint_as_float(ra[4 * c + 1]) * p.scale,
+                       __uint_as_float(ra[4 * c + 2]) * p.scale, __uint_as_float(ra[4 * c + 3]) * p.scale);
+            red_add_v4(dv_ + 4 * c, __uint_as_float(rb[4 * c]), __uint_as_float(rb[4 * c + 1]),
+                       __uint_as_float(rb[4 * c + 2]), __uint_as_float(rb[4 * c + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&T.bar_tfree);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dq (bf16, strided) = dq32 (fp32 [batch, lq, heads * 64], already scaled)
 __global__ void dq_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long lddq,
                                long long bsdq, int lq, int width, long long total4) {
@@ -866,7 +1512,12 @@ long long attention_tc_bwd_workspace_bytes(const zb_attention_args* a) {
 
 bool attention_tc_supported(const zb_attention_args* a, bool bwd) {
   if (!tc_enabled()) return false;
-  if (a->dh != 64 || a->rpr_k || a->relu_attn || a->kv_group > 1) return false;
+  if (a->dh != 64 || a->relu_attn || a->kv_group > 1) return false;
+  if (a->rpr_k) {
+    // relative positions: one 128 x 128 block per (batch, head), at most 2 * 16 + 1 buckets (attention_tc.cu)
+    if (a->max_rel > fat::kMaxRel || a->lq > 128 || a->lk > 128) return false;
+    if (!al16(a->rpr_k) || !al16(a->rpr_v)) return false;
+  }
   if (a->lq < 16) return false;  // decode steps (lq = 1) are served by the warp-per-row kernel
   if (a->causal && (a->q_offset != 0 || a->lq != a->lk)) return false;
   if (a->ldq % 8 || a->ldk % 8 || a->ldv % 8 || a->ldo % 8 || a->bsq % 8 || a->bsk % 8 || a->bsv % 8 || a->bso % 8)
@@ -917,7 +1568,7 @@ static fat::Params tc_params(const zb_attention_args* a, bool bwd) {
   p.ldo = a->ldo; p.bso = a->bso; p.lddo = a->lddo; p.bsdo = a->bsdo;
   p.lddq = a->lddq; p.bsdq = a->bsdq; p.lddk = a->lddk; p.bsdk = a->bsdk; p.lddv = a->lddv; p.bsdv = a->bsdv;
   p.batch = a->batch; p.heads = a->heads; p.lq = a->lq; p.lk = a->lk; p.causal = a->causal; p.q_offset = a->q_offset;
-  p.pair = (a->lq <= 64 && a->lk <= 64 && (a->heads & 1) == 0) ? 1 : 0;
+  p.pair = (a->lq <= 64 && a->lk <= 64 && (a->heads & 1) == 0 && !a->rpr_k) ? 1 : 0;
   p.nq = p.pair ? 1 : (a->lq + 127) / 128;
   p.nk = p.pair ? 1 : (a->lk + 127) / 128;
   p.hsel = p.pair ? a->heads / 2 : a->heads;
@@ -939,6 +1590,27 @@ int attention_tc_fwd(const zb_attention_args* a, cudaStream_t st) {
   if (!rc) rc = make_map_heads(&mv, a->v, a->lk, a->heads, a->batch, a->ldv, a->bsv, br, bh);
   if (!rc) rc = make_map_heads(&mo, a->o, a->lq, a->heads, a->batch, a->ldo, a->bso, br, bh);
   if (rc) return rc;
+  if (a->rpr_k) {
+    CUtensorMap mek, mev;
+    const uint64_t nbk = 2 * (uint64_t)a->max_rel + 1;
+    rc = make_map(&mek, a->rpr_k, 64, nbk, 64, 64);
+    if (!rc) rc = make_map(&mev, a->rpr_v, 64, nbk, 64, 64);
+    if (rc) return rc;
+    const int smem_r = (int)sizeof(fat::RprFwdSmem) + 1024;
+    static bool attr_r = false;
+    if (!attr_r) {
+      cudaFuncSetAttribute(fat::fwd_tc_rpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+      cudaFuncSetAttribute(fat::fwd_tc_rpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+      attr_r = true;
+    }
+    const int grid_r = p.units < num_sms() ? p.units : num_sms();
+    if (p.drop_rate > 0.f)
+      ZB_LAUNCH(fat::fwd_tc_rpr_kernel<true>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mo, mek, mev, p, (int)a->max_rel);
+    else
+      ZB_LAUNCH(fat::fwd_tc_rpr_kernel<false>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mo, mek, mev, p, (int)a->max_rel);
+    note_path(ZB_PATH_ATTN_TC);
+    return check_launch("zb_attention_fwd(tcgen05, relative positions)");
+  }
   const int smem = (int)sizeof(fat::FwdSmem) + 1024;
   static bool attr = false;
   if (!attr) {
@@ -967,6 +1639,29 @@ int attention_tc_bwd(const zb_attention_args* a, cudaStream_t st) {
   if (!rc) rc = make_map_heads(&mdk, a->dk, a->lk, a->heads, a->batch, a->lddk, a->bsdk, br, bh);
   if (!rc) rc = make_map_heads(&mdv, a->dv, a->lk, a->heads, a->batch, a->lddv, a->bsdv, br, bh);
   if (rc) return rc;
+  if (a->rpr_k) {
+    CUtensorMap mek, mev;
+    const uint64_t nbk = 2 * (uint64_t)a->max_rel + 1;
+    rc = make_map(&mek, a->rpr_k, 64, nbk, 64, 64);
+    if (!rc) rc = make_map(&mev, a->rpr_v, 64, nbk, 64, 64);
+    if (rc) return rc;
+    const int smem_r = (int)sizeof(fat::RprBwdSmem) + 1024;
+    static bool attr_r = false;
+    if (!attr_r) {
+      cudaFuncSetAttribute(fat::bwd_tc_rpr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+      cudaFuncSetAttribute(fat::bwd_tc_rpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
+      attr_r = true;
+    }
+    const int grid_r = p.units < num_sms() ? p.units : num_sms();
+    if (p.drop_rate > 0.f)
+      ZB_LAUNCH(fat::bwd_tc_rpr_kernel<true>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mdo, mdq, mdk, mdv, mek, mev, p,
+                (int)a->max_rel, a->d_rpr_k, a->d_rpr_v);
+    else
+      ZB_LAUNCH(fat::bwd_tc_rpr_kernel<false>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mdo, mdq, mdk, mdv, mek, mev,
+                p, (int)a->max_rel, a->d_rpr_k, a->d_rpr_v);
+    note_path(ZB_PATH_ATTN_TC);
+    return check_launch("zb_attention_bwd(tcgen05, relative positions)");
+  }
   const int smem = (int)sizeof(fat::BwdSmem) + 1024;
   static bool attr = false;
   if (!attr) {
