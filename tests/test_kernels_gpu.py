@@ -756,6 +756,52 @@ def test_attention_tcgen05_relative_positions(B, h, Lq, Lk, causal, klen, R, dro
     torch.testing.assert_close(dev_, evf.grad, atol=0.15, rtol=5e-2)
 
 
+@pytest.mark.parametrize("B,h,Lq,Lk,causal,klen,drop", [
+    (4, 8, 64, 64, False, True, 0.0), (4, 8, 64, 64, True, False, 0.0), (2, 4, 128, 128, True, True, 0.0),
+    (2, 2, 40, 36, False, True, 0.0), (1, 2, 300, 300, True, True, 0.0), (2, 4, 64, 200, False, True, 0.0),
+    (2, 4, 64, 64, True, True, 0.2),
+])
+def test_attention_tcgen05_rela(B, h, Lq, Lk, causal, klen, drop, monkeypatch):
+    """ReLA (modules/rela.py:52-75: relu(logits * keep) instead of softmax, no normaliser) on the tcgen05 kernels against
+    the torch restatement and against the generic CUDA-core kernels (ZB_ATTN_TC=0)."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    D = h * 64
+    q, k, v = rnd(B, Lq, D, seed=71), rnd(B, Lk, D, seed=72), rnd(B, Lk, D, seed=73)
+    d_o = rnd(B, Lq, D, seed=74)
+    key_len = None
+    if klen:
+        key_len = torch.randint(1, Lk + 1, (B,), dtype=torch.int32, device=dev())
+        key_len[0] = Lk
+    seed = torch.tensor([777], dtype=torch.int64, device=dev())
+    res = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("ZB_ATTN_TC", tc)
+        before = L.path_launch_count("attn_tc")
+        o = torch.empty(B, Lq, D, dtype=bf16, device=dev())
+        lse = torch.empty(B, h, Lq, device=dev())
+        a = ops.attention_args(q, k, v, o, h, key_len=key_len, causal=causal, lse=lse, relu_attn=True,
+                               dropout=(drop, 5, seed) if drop else None)
+        ops.attention_fwd(a)
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        ops.attention_bwd(a, d_o, dq, dk, dv, torch.empty(B, h, Lq, device=dev()), None, None,
+                          workspace=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev()))
+        assert L.path_launch_count("attn_tc") == before + 2 * int(tc)
+        res.append((o, dq, dk, dv))
+    # the unnormalised weights make large sums: compare relative to each tensor's scale
+    for x0, x1 in zip(res[0], res[1]):
+        scale = float(x0.float().abs().max()) + 1e-6
+        assert float((x1.float() - x0.float()).abs().max()) <= 4e-2 * scale
+    if drop:
+        return
+    leaves = [t.float().detach().clone().requires_grad_(True) for t in (q, k, v)]
+    ref = _attn_ref(leaves[0], leaves[1], leaves[2], h, key_len, causal, 0, 1e8, None, None, 0, True)
+    ref.backward(d_o.float())
+    for got, want in zip(res[1], [ref.detach()] + [t.grad for t in leaves]):
+        scale = float(want.abs().max()) + 1e-6
+        assert float((got.float() - want).abs().max()) <= 5e-2 * scale
+
+
 @pytest.mark.parametrize("B,h,Lq,Lk,causal", [(4, 8, 64, 64, True), (2, 4, 128, 128, False), (2, 2, 200, 200, True)])
 def test_attention_tcgen05_dropout_matches_the_mma_kernels(B, h, Lq, Lk, causal, monkeypatch):
     """Attention dropout (func.py:245): the keep mask is a pure function of (seed, site, [b, h, i, j]) shared by every

@@ -57,6 +57,7 @@ struct Params {
   float* dq32;  // fp32 [batch, lq, heads * 64] reduction workspace (backward, more than one key block)
   long long ldo, bso, lddo, bsdo, lddq, bsdq, lddk, bsdk, lddv, bsdv;
   int batch, heads, lq, lk, causal, q_offset;
+  int relu;   // 1: ReLA (modules/rela.py:52-75): weights = relu(logits * keep), no normaliser
   int pair;   // 1: two heads stacked per 128-row block (lq, lk <= 64)
   int nq, nk; // 128-row query / key blocks per (batch, head selector); 1 in pair mode
   int hsel;   // head selectors per batch element: heads, or heads / 2 in pair mode
@@ -253,6 +254,12 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&r)[32], float (&e)[3
   }
   return (l[0] + l[1]) + (l[2] + l[3]);
 }
+// ReLA (modules/rela.py:65-70): e[jj] = relu(raw * scale) where the key is visible, 0 elsewhere (multiplicative 0 / 1
+// mask); `g` (optional) = 1 where the weight is positive — the gate of its gradient
+__device__ __forceinline__ void chunk_relu(const uint32_t (&r)[32], float (&e)[32], int nv, float scale) {
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) e[jj] = jj < nv ? fmaxf(__uint_as_float(r[jj]) * scale, 0.f) : 0.f;
+}
 // barrier among the 8 row warps (named barrier 1; barrier 0 is __syncthreads)
 __device__ __forceinline__ void row_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -444,7 +451,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         xl[half * 128 + row] = pend_l;
         mbar_wait(&T.ost_free, (uint32_t)((stores & 1) ^ 1));
         row_warps_sync();
-        const float l_tot = xl[row] + xl[128 + row];
+        const float l_tot = p.relu ? 1.f : xl[row] + xl[128 + row];
         const float inv = 1.f / l_tot;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -457,7 +464,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         if (lane == 0) mbar_arrive(&T.ost_full);
         ++stores;
         if (half == 0 && pend_i < p.lq && p.lse)
-          p.lse[((long long)pend_b * p.heads + pend_h) * p.lq + pend_i] = pend_m * kLn2 + __logf(l_tot);
+          p.lse[((long long)pend_b * p.heads + pend_h) * p.lq + pend_i] = p.relu ? 0.f : pend_m * kLn2 + __logf(l_tot);
         acc_empty = true;
       }
       if (threadIdx.x == 64) FAT_TRACE_ITEM(pend_n, 7);
@@ -479,19 +486,19 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
       mbar_wait(&T.bar_s[n & 1], (uint32_t)((n >> 1) & 1));
       tc_fence_after();
       if (threadIdx.x == 64) FAT_TRACE_ITEM(n, 3);
-      // ---- pass 1: the maximum of this thread's columns, then of the row
-      float mt = -INFINITY;
+      // ---- pass 1: the maximum of this thread's columns, then of the row (ReLA: no normalisation, m = 0 throughout)
+      float mt = p.relu ? 0.f : -INFINITY;
+      if (!p.relu) {
 #pragma unroll 1
-      for (int cc = 0; cc < c_cnt; ++cc) {
-        const int c32 = c_begin + cc;
-        uint32_t ra[32];
-        tmem_ld_32x32b_x32(t_s + c32 * 32, ra);
-        tmem_ld_wait();
-        const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;  // key position of the chunk's first column
-        const int nv = jv - base, nb = p.lk - base;
-        mt = fmaxf(mt, chunk_max(ra, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2));
-      }
-      {
+        for (int cc = 0; cc < c_cnt; ++cc) {
+          const int c32 = c_begin + cc;
+          uint32_t ra[32];
+          tmem_ld_32x32b_x32(t_s + c32 * 32, ra);
+          tmem_ld_wait();
+          const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;  // key position of the chunk's first column
+          const int nv = jv - base, nb = p.lk - base;
+          mt = fmaxf(mt, chunk_max(ra, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2));
+        }
         float* xm = &T.xmax[n & 1][0][0];
         xm[half * 128 + row] = mt;
         row_warps_sync();
@@ -514,7 +521,8 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;
         const int nv = jv - base, nb = p.lk - base;
         float e[32];
-        l_run += chunk_exp(ra, e, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2, m_run);
+        if (p.relu) chunk_relu(ra, e, nv, p.scale);
+        else l_run += chunk_exp(ra, e, chunk_mode(nv, nb, vis), nv, nb, sl2, inf2, m_run);
         if (DROP) {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) e[jj] *= drop.mul(p, b, h, i, base + jj);
@@ -760,18 +768,29 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__
         const int base = p.pair ? (c32 & 1) * 32 : kbase + c32 * 32;
         const int nv = jv - base, nb = jb - base;
         float e[32];
-        chunk_exp(rs, e, chunk_mode(nv, nb, jv >= 1), nv, nb, sl2, inf2, lse2);  // P = 2^(t - lse2)
         float dsv[32];
-        if (DROP) {
+        if (p.relu) {
+          // weights relu(s) where visible; their gradient passes where the weight is positive (modules/rela.py:65-70)
+          chunk_relu(rs, e, nv, p.scale);
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const float dm = drop.mul(p, b, h, i, base + jj);
-            dsv[jj] = e[jj] * fmaf(__uint_as_float(rp[jj]), dm, -delta);
+            const float dm = DROP ? drop.mul(p, b, h, i, base + jj) : 1.f;
+            dsv[jj] = e[jj] > 0.f ? __uint_as_float(rp[jj]) * dm : 0.f;
             e[jj] *= dm;
           }
         } else {
+          chunk_exp(rs, e, chunk_mode(nv, nb, jv >= 1), nv, nb, sl2, inf2, lse2);  // P = 2^(t - lse2)
+          if (DROP) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) dsv[jj] = e[jj] * (__uint_as_float(rp[jj]) - delta);
+            for (int jj = 0; jj < 32; ++jj) {
+              const float dm = drop.mul(p, b, h, i, base + jj);
+              dsv[jj] = e[jj] * fmaf(__uint_as_float(rp[jj]), dm, -delta);
+              e[jj] *= dm;
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) dsv[jj] = e[jj] * (__uint_as_float(rp[jj]) - delta);
+          }
         }
         const int u0 = (c32 & 1) * 4;
         store_chunk_bf16((c32 >> 1) ? p_atom1 : p_atom0, row, u0, e);
@@ -1512,7 +1531,7 @@ long long attention_tc_bwd_workspace_bytes(const zb_attention_args* a) {
 
 bool attention_tc_supported(const zb_attention_args* a, bool bwd) {
   if (!tc_enabled()) return false;
-  if (a->dh != 64 || a->relu_attn || a->kv_group > 1) return false;
+  if (a->dh != 64 || a->kv_group > 1) return false;
   if (a->rpr_k) {
     // relative positions: one 128 x 128 block per (batch, head), at most 2 * 16 + 1 buckets (attention_tc.cu)
     if (a->max_rel > fat::kMaxRel || a->lq > 128 || a->lk > 128) return false;
@@ -1568,6 +1587,7 @@ static fat::Params tc_params(const zb_attention_args* a, bool bwd) {
   p.ldo = a->ldo; p.bso = a->bso; p.lddo = a->lddo; p.bsdo = a->bsdo;
   p.lddq = a->lddq; p.bsdq = a->bsdq; p.lddk = a->lddk; p.bsdk = a->bsdk; p.lddv = a->lddv; p.bsdv = a->bsdv;
   p.batch = a->batch; p.heads = a->heads; p.lq = a->lq; p.lk = a->lk; p.causal = a->causal; p.q_offset = a->q_offset;
+  p.relu = a->relu_attn ? 1 : 0;
   p.pair = (a->lq <= 64 && a->lk <= 64 && (a->heads & 1) == 0 && !a->rpr_k) ? 1 : 0;
   p.nq = p.pair ? 1 : (a->lq + 127) / 128;
   p.nk = p.pair ? 1 : (a->lk + 127) / 128;
