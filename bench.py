@@ -400,11 +400,21 @@ def gemm_roofline(eng, src, tgt, peaks):
         return real_grouped(problems)
 
     nprob = [0]
+    real_vce = ops.vocab_ce
+
+    def recording_vce(feat, table, labels, nll, smooth, workspace, **kw):
+        # K6: one algorithmic logits GEMM (the recomputation inside the fused op is its own cost, not extra work)
+        flops[0] += 2.0 * feat.shape[0] * table.shape[0] * feat.shape[1]
+        nsingle[0] += 1
+        calls.append(lambda: real_vce(feat, table, labels, nll, smooth, workspace, **kw))
+        return real_vce(feat, table, labels, nll, smooth, workspace, **kw)
+
     from zero_b200 import lib as L
     side = getattr(eng, "side", None)
     eng.side = None  # record the launches in program order on one stream
     ops.gemm = recording
     ops.gemm_grouped = recording_grouped
+    ops.vocab_ce = recording_vce
     c0 = L.launch_count()
     try:
         eng.forward_backward(src, tgt, compact=False)
@@ -413,6 +423,7 @@ def gemm_roofline(eng, src, tgt, peaks):
         step_launches = L.launch_count() - c0  # every kernel of one eager fwd+bwd (graph replays bypass the counter)
         ops.gemm = real
         ops.gemm_grouped = real_grouped
+        ops.vocab_ce = real_vce
         eng.side = side
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):

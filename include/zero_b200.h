@@ -216,6 +216,24 @@ typedef struct {
 } zb_ce_args;
 int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream);
 
+/* zb_vocab_ce: K6 fused — logits = feat @ table^T are reduced to the loss inside the GEMM epilogue and never
+ * written ([rows, vocab] fp32 = 524 MB at BASELINE configs[1], models/transformer.py:186-211); with d_logits != NULL the
+ * GEMM is run a second time and its epilogue emits d_logits = (softmax - soft_label) * row_weight in bf16.
+ * Same outputs as zb_gemm + zb_softmax_ce.  vocab >= 128; d, ldf, ldt, ldd multiples of 8. */
+typedef struct {
+  const void* feat; int64_t ldf;     /* bf16 [rows, d], rows = batch * seq_len */
+  const void* table; int64_t ldt;    /* bf16 [vocab, d]: the (tied) softmax embedding */
+  const int32_t* labels;             /* [batch, seq_len] target ids */
+  int32_t batch, seq_len, d, vocab;
+  float smooth, loss_scale;
+  float* nll;                        /* [rows] */
+  float* per_sample; float* loss;    /* [batch], [1]; optional */
+  void* d_logits; int64_t ldd;       /* bf16 [rows, ldd] or NULL (forward only) */
+  void* workspace; int64_t workspace_bytes; /* caller-owned scratch, zb_vocab_ce_workspace_bytes, 16-byte aligned */
+} zb_vocab_ce_args;
+int zb_vocab_ce(const zb_vocab_ce_args* a, zb_stream_t stream);
+int64_t zb_vocab_ce_workspace_bytes(const zb_vocab_ce_args* a);
+
 /* ------------------------------------------------------------------------------------------------ misc
  * zb_colsum: out[n] += sum_m x[m,n] (bias gradients; tf.nn.bias_add grad).  x bf16, out fp32. */
 int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream);

@@ -72,7 +72,8 @@ def test_every_mirrored_field_offset_matches_the_header(tmp_path):
         pytest.skip("no C compiler")
     pairs = [("zb_gemm_args", L.GemmArgs), ("zb_attention_args", L.AttentionArgs), ("zb_add_ln_args", L.AddLnArgs),
              ("zb_embed_args", L.EmbedArgs), ("zb_ce_args", L.CeArgs), ("zb_adam_args", L.AdamArgs),
-             ("zb_beam_args", L.BeamArgs), ("zb_colsum_args", L.ColsumArgs), ("zb_shard_adam_args", L.ShardAdamArgs)]
+             ("zb_beam_args", L.BeamArgs), ("zb_colsum_args", L.ColsumArgs), ("zb_shard_adam_args", L.ShardAdamArgs),
+             ("zb_vocab_ce_args", L.VocabCeArgs)]
     assert [c for _, c in pairs] == L.STRUCTS
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % os.path.join(ROOT, "include", "zero_b200.h"),
              'int main(void) {']

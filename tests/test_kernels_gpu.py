@@ -232,6 +232,59 @@ def test_softmax_ce(V):
     torch.testing.assert_close(nll, ce0, atol=2e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,T,V,d,smooth", [(64, 64, 32000, 512, 0.1), (5, 9, 1000, 128, 0.1), (3, 7, 208, 64, 0.1),
+                                            (11, 64, 40000, 512, 0.0), (2, 300, 1304, 256, 0.1), (4, 9, 128, 64, 0.1)])
+def test_vocab_ce_fused_matches_gemm_plus_softmax_ce(B, T, V, d, smooth):
+    """K6 (zb_vocab_ce: the vocabulary projection with the label-smoothed CE in the GEMM epilogue, logits never
+    written) against the two-kernel path it replaces (zb_gemm into fp32 logits + zb_softmax_ce) and against the oracle
+    (util.label_smooth + softmax_cross_entropy_with_logits_v2, models/transformer.py:186-211): per-token NLL, per-sentence
+    and batch means, d_logits.  Covers the BASELINE configs[1] shape, ragged row / vocabulary tiles (45 rows, V = 1000,
+    1304, 208 — the last tile partly or wholly past V), the minimum vocabulary, smoothing off (score_fn)."""
+    from oracle import zero_oracle as zo
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    N = B * T
+    feat = rnd(N, d, seed=81)
+    table = rnd(V, d, scale=d ** -0.5 * 2, seed=82)
+    labels = torch.randint(3, V, (B, T), dtype=torch.int32, device=dev())
+    labels[1, T // 2:] = 0
+    labels[-1, 2:] = 0
+    labels[0, 0] = V - 1
+    pitch = (V + 7) // 8 * 8
+    outs = []
+    for fused in (False, True):
+        nll, per, loss = torch.empty(N, device=dev()), torch.empty(B, device=dev()), torch.empty(1, device=dev())
+        dl = torch.zeros(N, pitch, dtype=bf16, device=dev())[:, :V]
+        if fused:
+            assert ops.vocab_ce_supported(N, d, V, feat, table, dl)
+            ops.vocab_ce(feat, table, labels, nll, smooth, lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev()),
+                         d_logits=dl, per_sample=per, loss=loss, loss_scale=2.0)
+        else:
+            logits = torch.empty(N, pitch, device=dev())[:, :V]
+            ops.gemm(feat, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
+            ops.softmax_ce(logits, labels, nll, smooth, d_logits=dl, per_sample=per, loss=loss, loss_scale=2.0)
+        outs.append((nll, per, loss, dl))
+    (nll0, per0, loss0, dl0), (nll1, per1, loss1, dl1) = outs
+    torch.testing.assert_close(nll1, nll0, atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(per1, per0, atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(loss1, loss0, atol=2e-3, rtol=1e-4)
+    scale = float(dl0.float().abs().max())
+    assert float((dl1.float() - dl0.float()).abs().max()) <= 2e-2 * scale + 1e-7
+    # ... and against the oracle on the same bf16-rounded operands (fp32 logits)
+    lg = (feat.float() @ table.float().t()).requires_grad_(True)
+    ce = zo.smoothed_ce(lg, labels.reshape(-1), smooth).reshape(B, T)
+    m = (labels != 0).float()
+    ps = (ce * m).sum(-1) / m.sum(-1)
+    (ps.mean() * 2.0).backward()
+    torch.testing.assert_close(nll1, ce.detach().reshape(-1), atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(loss1[0], ps.mean().detach(), atol=2e-3, rtol=1e-4)
+    assert float((dl1.float() - lg.grad).abs().max()) <= 2e-2 * float(lg.grad.abs().max()) + 1e-7
+    # forward only (score_fn): no d_logits
+    nll2 = torch.empty(N, device=dev())
+    ops.vocab_ce(feat, table, labels, nll2, 0.0, lambda nbytes: torch.empty(nbytes, dtype=torch.uint8, device=dev()))
+    torch.testing.assert_close(nll2, zo.smoothed_ce(lg.detach(), labels.reshape(-1), 0.0), atol=2e-3, rtol=1e-4)
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, heads, key_len, causal, q_off, inf, ek, ev, max_rel, relu):
     from oracle import zero_oracle as zo

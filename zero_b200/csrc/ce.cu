@@ -283,6 +283,13 @@ __global__ void ce_reduce_kernel(const float* __restrict__ nll, const int32_t* _
   }
 }
 
+// per-sentence / batch means of the per-token NLL (also used by vocab_ce.cu)
+int ce_reduce_launch(const float* nll, const int32_t* labels, int batch, int seq_len, float* per_sample, float* loss,
+                     cudaStream_t st) {
+  ZB_LAUNCH(ce_reduce_kernel, 1, 256, 0, st, nll, labels, batch, seq_len, per_sample, loss);
+  return check_launch("zb_ce_reduce");
+}
+
 }  // namespace zb
 
 extern "C" int zb_softmax_ce(const zb_ce_args* a, zb_stream_t stream) {

@@ -36,6 +36,15 @@ struct Gemm2Params {
   int tile_begin;  // first work unit of this problem in the launch (grouped launches)
   int d_tma;  // output written through shared memory + TMA tile stores (full 128 B lines): 1 = bf16, 2 = fp32,
               // 3 = fp32 bulk reduce-add
+  // K6 (vocab_ce.cu): the vocabulary projection fused with the label-smoothed cross-entropy.
+  //   ce_mode 1: nothing is stored; every epilogue thread reduces its columns of its row to {max, sum exp(x - max),
+  //              sum x, x[gold]} and writes them to ce_stats[(n_blk * 2 + column half) * M + row]
+  //   ce_mode 2: the tile is turned into d_logits = (exp(x - lse[row]) - soft_label) * weight[row] before the store
+  int ce_mode;
+  const float* ce_aux;        // mode 2: [M][2] = {log-sum-exp, d loss / d nll} per row
+  const int32_t* ce_labels;   // [M] gold class per row
+  float4* ce_stats;           // mode 1
+  float ce_p, ce_q;           // smoothed target: p on the gold class, q elsewhere
 };
 
 // One launch may carry several independent problems of the same operand layouts (the weight-gradient GEMMs of a
@@ -165,6 +174,11 @@ __device__ __forceinline__ void tile2_coords(const Gemm2Params& p, int tile, int
   n_blk = pn * p.gn + (r - m_blk * w);
 }
 
+__device__ __forceinline__ float ex2_(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -179,7 +193,9 @@ __device__ __forceinline__ int find_problem(const Gemm2Group<NP>& G, int tile) {
   return pi;
 }
 
-template <int BN, bool A_MN, bool B_MN, int NP>
+// CE: 0 = the plain GEMM; 1 / 2 = the K6 cross-entropy epilogues (Gemm2Params::ce_mode), separate instantiations so that
+// the plain kernels keep their register allocation
+template <int BN, bool A_MN, bool B_MN, int NP, int CE = 0>
 __global__ void __launch_bounds__(k2Threads, 1)
 gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
   using Cfg = Gemm2Cfg<BN>;
@@ -362,6 +378,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       }
       store_pending = true;
     };
+    // K6 state of this thread's row in this tile
+    float ce_m = -INFINITY, ce_s = 0.f, ce_t = 0.f, ce_g = 0.f, ce_lse = 0.f, ce_w = 0.f;
+    int ce_gold = -1;
     auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4],
                             int cpar) {
       if (col0 >= p.N) {
@@ -372,17 +391,62 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * alpha;
-      if (flags & ZB_EPI_BIAS) {
+      if constexpr (CE == 1) {
+        // running {max, sum exp, sum, gold logit} over this thread's columns (four chains each)
+        float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, ct[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full_cols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            cm[j & 3] = fmaxf(cm[j & 3], v[j]);
+            ct[j & 3] += v[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool on = col0 + j < p.N;
+            v[j] = on ? v[j] : -INFINITY;  // exp(-inf - m) = 0 below
+            cm[j & 3] = fmaxf(cm[j & 3], v[j]);
+            ct[j & 3] += on ? v[j] : 0.f;
+          }
+        }
+        ce_t += (ct[0] + ct[1]) + (ct[2] + ct[3]);
+        const int gj = ce_gold - col0;
+        if (gj >= 0 && gj < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == gj) ce_g = v[j];
+        }
+        const float nm = fmaxf(ce_m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        const float nm2 = nm * 1.4426950408889634f;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc4[j & 3] += ex2_(fmaf(v[j], 1.4426950408889634f, -nm2));
+        ce_s = ce_s * __expf(ce_m - nm) + ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+        ce_m = nm;
+        return;
+      }
+      if constexpr (CE == 2) {
+        const float l2 = ce_lse * 1.4426950408889634f, qw = p.ce_q * ce_w;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(ex2_(fmaf(v[j], 1.4426950408889634f, -l2)), ce_w, -qw);
+        const int gj = ce_gold - col0;
+        if (gj >= 0 && gj < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == gj) v[j] -= (p.ce_p - p.ce_q) * ce_w;
+        }
+      }
+      if (CE == 0 && (flags & ZB_EPI_BIAS)) {
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bias_lane, j);
       }
-      if (flags & ZB_EPI_RELU) {
+      if (CE == 0 && (flags & ZB_EPI_RELU)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (!row_ok && !d_tma) return;
-      if ((flags & ZB_EPI_RELU_MASK) && row_ok) {
+      if (CE == 0 && (flags & ZB_EPI_RELU_MASK) && row_ok) {
         if (full_cols) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -467,6 +531,7 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
     };
     auto prefetch_chunk = [&](int row, bool row_ok, int col0, float& bias_lane, uint4 (&mk)[4]) {
       bias_lane = 0.f;
+      if constexpr (CE != 0) return;  // the cross-entropy epilogues take no bias / mask
       if ((flags & ZB_EPI_BIAS) && col0 + lane < p.N) bias_lane = __ldg(p.bias + col0 + lane);
       if ((flags & ZB_EPI_RELU_MASK) && row_ok && col0 + 32 <= p.N) {
         const uint4* mrow = reinterpret_cast<const uint4*>(p.mask + static_cast<long long>(row) * p.ldmask + col0);
@@ -483,6 +548,16 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       uint4 mk_a[4], mk_b[4];
       constexpr int NCH = BN / 64;
       const int c0 = half * NCH;
+      if constexpr (CE != 0) {
+        ce_m = -INFINITY;
+        ce_s = ce_t = ce_g = 0.f;
+        ce_gold = row_ok ? __ldg(p.ce_labels + row) : -1;
+        if (CE == 2 && row_ok) {
+          const float2 aux = __ldg(reinterpret_cast<const float2*>(p.ce_aux) + row);
+          ce_lse = aux.x;
+          ce_w = aux.y;
+        }
+      }
       prefetch_chunk(row, row_ok, n0 + c0 * 32, bias_a, mk_a);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -514,6 +589,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
           if (tr && c == 0) G.trace[13] = globaltimer_ns();
         }
       }
+      if (CE == 1 && row_ok)
+        p.ce_stats[(static_cast<long long>(n_blk) * 2 + half) * p.M + row] = make_float4(ce_m, ce_s, ce_t, ce_g);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(acc == 0 ? leader_tempty0 : leader_tempty1);
@@ -538,9 +615,9 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
   if (tracing && threadIdx.x == 0) G.trace[9] = globaltimer_ns();
 }
 
-template <int BN, bool A_MN, bool B_MN, int NP>
+template <int BN, bool A_MN, bool B_MN, int NP, int CE = 0>
 static int launch2(const Gemm2Group<NP>& G, int grid, cudaStream_t st) {
-  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, NP>;
+  auto kern = gemm2_bf16_tcgen05<BN, A_MN, B_MN, NP, CE>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BN>::SMEM_BYTES);
@@ -624,6 +701,7 @@ static int setup_problem(const zb_gemm_args* a, int bn, Gemm2Params& p, CUtensor
   p.d = a->d; p.ldd = a->ldd; p.bias = a->bias;
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
   p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
+  p.ce_mode = 0; p.ce_aux = nullptr; p.ce_labels = nullptr; p.ce_stats = nullptr; p.ce_p = 1.f; p.ce_q = 0.f;
   p.kb_total = (p.K + k2BK - 1) / k2BK;
   p.mt = (p.M + 255) / 256;
   p.nt = (p.N + bn - 1) / bn;
@@ -644,7 +722,7 @@ static int setup_problem(const zb_gemm_args* a, int bn, Gemm2Params& p, CUtensor
   static const char* no_tma_red = getenv("ZB_GEMM_NO_TMA_REDUCE");
   maps[2] = maps[0];
   p.d_tma = 0;
-  const bool d_al = (reinterpret_cast<uintptr_t>(a->d) & 15) == 0;
+  const bool d_al = a->d != nullptr && (reinterpret_cast<uintptr_t>(a->d) & 15) == 0;   // no output tensor: K6 mode 1
   if (accum && p.d_f32 && !no_tma_d && !no_tma_red && d_al && (a->ldd * 4) % 16 == 0) {
     rc = make_map_f32(&maps[2], a->d, p.N, p.M, a->ldd, 32);
     if (rc) return rc;
@@ -733,6 +811,32 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
             d(12), d(13));
   }
   return lrc;
+}
+
+// K6: logits = a @ b^T (both K-major, 256-wide tiles) with one of the cross-entropy epilogues (vocab_ce.cu).
+// mode 1 needs no output tensor (a->d is ignored); mode 2 writes bf16 d_logits to a->d.
+int gemm2_launch_ce(const zb_gemm_args* a, int mode, const float* aux, const int32_t* labels, float4* stats, float ce_p,
+                    float ce_q, cudaStream_t st) {
+  const int pairs_hw = num_sms() / 2;
+  Gemm2Group<1> G;
+  Gemm2Params& p = G.prob[0];
+  zb_gemm_args b = *a;
+  if (mode == 1) b.d = nullptr;  // nothing is stored: no output tensor map
+  int rc = setup_problem(&b, 256, p, G.maps);
+  if (rc) return rc;
+  if (mode == 1) p.d_tma = 0;
+  else if (p.d_tma != 1) {
+    set_error("zb_vocab_ce: d_logits must be 16-byte aligned with a pitch that is a multiple of 8 elements");
+    return ZB_EINVAL;
+  }
+  p.ce_mode = mode; p.ce_aux = aux; p.ce_labels = labels; p.ce_stats = stats; p.ce_p = ce_p; p.ce_q = ce_q;
+  set_splits(p, 1);
+  const long long total = (long long)p.mt * p.nt;
+  G.count = 1;
+  G.total_tiles = (int)total;
+  G.trace = nullptr;
+  const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
+  return mode == 1 ? launch2<256, false, false, 1, 1>(G, grid, st) : launch2<256, false, false, 1, 2>(G, grid, st);
 }
 
 // One launch for several accumulate-into-fp32 problems with MN-major operands (the weight gradients of a layer).

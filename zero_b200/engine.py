@@ -704,11 +704,38 @@ class Engine(object):
             return "src_emb"
         return "tgt_emb" if c.share_ts else "softmax_emb"
 
-    def decode_train(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D"):
-        """models/transformer.py:87-218 in training mode.  Returns (loss[1], per_sample[B], logits fp32 [N,V])."""
+    def _vocab_loss(self, feat, target, smooth, want_grad, want_logits, tag):
+        """Tied-softmax projection + label-smoothed CE (models/transformer.py:186-211).  Returns
+        (loss [1], per_sample [B], logits fp32 [N, V] or None, d_logits bf16 [N, V] or None).
+        Unless the caller asks for the logits themselves they are never materialised: zb_vocab_ce reduces them to
+        the loss inside the GEMM epilogue and, for training, emits only the bf16 d_logits (K6).  ZB_FUSED_CE=0 keeps
+        the two-kernel path (fp32 logits + zb_softmax_ce)."""
+        c, ps, ws = self.cfg, self.ps, self.ws
+        B, T = target.shape
+        N = B * T
+        table = ps.w(self._softmax_table())
+        nll = ws.get(tag + ".nll", (N,), f32)
+        per_sample = ws.get(tag + ".per_sample", (B,), f32)
+        loss = ws.get(tag + ".loss", (1,), f32)
+        dlogits = self._vocab_rows(tag + ".dlogits", N) if want_grad else None
+        fused = (not want_logits and os.environ.get("ZB_FUSED_CE", "1") != "0"
+                 and ops.vocab_ce_supported(N, c.d, c.vt, feat, table, dlogits))
+        if fused:
+            ops.vocab_ce(feat, table, target, nll, smooth, lambda nbytes: ws.get("ce.scratch", ((nbytes + 3) // 4,), f32),
+                         d_logits=dlogits, per_sample=per_sample, loss=loss, loss_scale=c.loss_scale)
+            return loss, per_sample, None, dlogits
+        logits = self._vocab_rows(tag + ".logits", N, f32)
+        ops.gemm(feat, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)  # feature @ E^T, cast fp32 (transformer.py:194-196)
+        ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
+                       loss_scale=c.loss_scale)
+        return loss, per_sample, logits, dlogits
+
+    def decode_train(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D", want_logits=True):
+        """models/transformer.py:87-218 in training mode.  Returns (loss[1], per_sample[B], logits fp32 [N,V] — None
+        unless want_logits)."""
         c, ps, ws = self.cfg, self.ps, self.ws
         if c.aan or c.fuse:
-            return self._decode_train_avg(target, enc, src_len, S, smooth, want_grad, save, tag)
+            return self._decode_train_avg(target, enc, src_len, S, smooth, want_grad, save, tag, want_logits)
         B, T = target.shape
         N = B * T
         x = ws.get(tag + ".x0", (N, c.d))
@@ -735,15 +762,7 @@ class Engine(object):
             sv.update(x1=x1, xc=xc)
             layers.append(sv)
         feat = x
-        table = ps.w(self._softmax_table())
-        logits = self._vocab_rows(tag + ".logits", N, f32)
-        ops.gemm(feat, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)  # feature @ E^T, cast fp32 (transformer.py:194-196)
-        nll = ws.get(tag + ".nll", (N,), f32)
-        per_sample = ws.get(tag + ".per_sample", (B,), f32)
-        loss = ws.get(tag + ".loss", (1,), f32)
-        dlogits = self._vocab_rows(tag + ".dlogits", N) if want_grad else None
-        ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
-                       loss_scale=c.loss_scale)
+        loss, per_sample, logits, dlogits = self._vocab_loss(feat, target, smooth, want_grad, want_logits, tag)
         if save is not None:
             save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
                         emb_rate=r_emb)
@@ -849,7 +868,7 @@ class Engine(object):
         self._training = True     # dropout is part of train_fn only (score_fn / infer_fn close it)
         try:
             enc, src_len = self.encode(source, esave)
-            loss, per_sample, _ = self.decode_train(target, enc, src_len, S, c.smooth, True, dsave)
+            loss, per_sample, _ = self.decode_train(target, enc, src_len, S, c.smooth, True, dsave, want_logits=False)
         finally:
             self._training = False
         d_enc32 = ws.get("d_enc32", (B * S, c.d), f32)
@@ -884,7 +903,7 @@ class Engine(object):
         if source.shape[0] == 0:
             return torch.zeros(0, dtype=f32, device=self.device)
         enc, src_len = self.encode(source)
-        return self.decode_train(target, enc, src_len, source.shape[1], 0.0, False)[1]
+        return self.decode_train(target, enc, src_len, source.shape[1], 0.0, False, want_logits=False)[1]
 
 
 # ------------------------------------------------------------------------------------------------ cached decode

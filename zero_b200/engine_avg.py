@@ -73,7 +73,7 @@ def _fuse_sublayer_fwd(eng, key, x, enc, B, T, S, src_len, tgt_len, sv, tag):
     return eng._ln_fwd(kc + ".ln", x, yc, N, sv["ln"], tag + ".ln")
 
 
-def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D"):
+def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=None, tag="D", want_logits=True):
     c, ps, ws = self.cfg, self.ps, self.ws
     B, T = target.shape
     N = B * T
@@ -100,14 +100,7 @@ def _decode_train_avg(self, target, enc, src_len, S, smooth, want_grad, save=Non
         sv["xc"] = xc
         layers.append(sv)
     feat = x
-    logits = self._vocab_rows(tag + ".logits", N, f32)
-    ops.gemm(feat, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
-    nll = ws.get(tag + ".nll", (N,), f32)
-    per_sample = ws.get(tag + ".per_sample", (B,), f32)
-    loss = ws.get(tag + ".loss", (1,), f32)
-    dlogits = self._vocab_rows(tag + ".dlogits", N) if want_grad else None
-    ops.softmax_ce(logits, target, nll, smooth, d_logits=dlogits, per_sample=per_sample, loss=loss,
-                   loss_scale=c.loss_scale)
+    loss, per_sample, logits, dlogits = self._vocab_loss(feat, target, smooth, want_grad, want_logits, tag)
     if save is not None:
         save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
                     tgt_len=tgt_len, emb_rate=r_emb)

@@ -64,6 +64,13 @@ class CeArgs(C.Structure):
                 ("per_sample", vp), ("loss", vp)]
 
 
+class VocabCeArgs(C.Structure):
+    _fields_ = [("feat", vp), ("ldf", i64), ("table", vp), ("ldt", i64), ("labels", vp),
+                ("batch", i32), ("seq_len", i32), ("d", i32), ("vocab", i32), ("smooth", f32), ("loss_scale", f32),
+                ("nll", vp), ("per_sample", vp), ("loss", vp), ("d_logits", vp), ("ldd", i64),
+                ("workspace", vp), ("workspace_bytes", i64)]
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("param", vp), ("m", vp), ("v", vp), ("grad", vp), ("param_bf16", vp), ("n", i64),
                 ("beta1", f32), ("beta2", f32), ("eps", f32), ("lr_t", f32), ("grad_scale", f32),
@@ -95,7 +102,8 @@ class ShardAdamArgs(C.Structure):
 
 # every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
 # order = the index zb_abi_struct_size() understands
-STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs, ShardAdamArgs]
+STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs, ShardAdamArgs,
+           VocabCeArgs]
 
 EXPORTS = [
     "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_path_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
@@ -104,7 +112,7 @@ EXPORTS = [
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
     "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam", "zb_gumbel_add",
-    "zb_attention_bwd_workspace_bytes",
+    "zb_attention_bwd_workspace_bytes", "zb_vocab_ce", "zb_vocab_ce_workspace_bytes",
 ]
 
 _lib = None
@@ -140,6 +148,7 @@ def load():
         ("zb_embed_fwd", [C.POINTER(EmbedArgs), vp]),
         ("zb_embed_bwd", [C.POINTER(EmbedArgs), vp]),
         ("zb_softmax_ce", [C.POINTER(CeArgs), vp]),
+        ("zb_vocab_ce", [C.POINTER(VocabCeArgs), vp]),
         ("zb_colsum", [vp, i64, i64, i64, vp, vp]),
         ("zb_cast_f32_bf16", [vp, vp, i64, vp]),
         ("zb_cast_bf16_f32", [vp, vp, i64, vp]),
@@ -167,6 +176,8 @@ def load():
         fn.restype = C.c_int
     lib.zb_attention_bwd_workspace_bytes.argtypes = [C.POINTER(AttentionArgs)]
     lib.zb_attention_bwd_workspace_bytes.restype = C.c_int64
+    lib.zb_vocab_ce_workspace_bytes.argtypes = [C.POINTER(VocabCeArgs)]
+    lib.zb_vocab_ce_workspace_bytes.restype = C.c_int64
     if lib.zb_abi_version() != 3:
         raise ZeroB200Error("libzero_b200.so ABI version mismatch")
     lib.zb_abi_struct_size.argtypes = [i32]

@@ -215,6 +215,31 @@ def softmax_ce(logits, labels, nll, smooth, d_logits=None, per_sample=None, loss
     L.check(L.load().zb_softmax_ce(C.byref(a), _stream()), "zb_softmax_ce")
 
 
+def vocab_ce(feat, table, labels, nll, smooth, workspace, d_logits=None, per_sample=None, loss=None, loss_scale=1.0):
+    """K6: tied-softmax projection + label-smoothed CE without materialising the logits (models/transformer.py:186-211).
+    feat bf16 [rows, d]; table bf16 [V, d]; labels int32 [B, T]; workspace: callable bytes -> tensor, or a tensor."""
+    a = L.VocabCeArgs()
+    a.feat, a.ldf, a.table, a.ldt = _p(feat), feat.stride(0), _p(table), table.stride(0)
+    a.labels, a.batch, a.seq_len = _p(labels), labels.shape[0], labels.shape[1]
+    a.d, a.vocab = feat.shape[1], table.shape[0]
+    a.smooth, a.loss_scale = float(smooth), float(loss_scale)
+    a.nll, a.per_sample, a.loss = _p(nll), _p(per_sample), _p(loss)
+    a.d_logits, a.ldd = _p(d_logits), (d_logits.stride(0) if d_logits is not None else 0)
+    need = int(L.load().zb_vocab_ce_workspace_bytes(C.byref(a)))
+    ws = workspace(need) if callable(workspace) else workspace
+    a.workspace, a.workspace_bytes = _p(ws), ws.numel() * ws.element_size()
+    L.check(L.load().zb_vocab_ce(C.byref(a), _stream()), "zb_vocab_ce")
+
+
+def vocab_ce_supported(rows, d, vocab, feat=None, table=None, d_logits=None):
+    """Shapes the fused kernel takes (the caller otherwise materialises the logits: zb_gemm + zb_softmax_ce)."""
+    ok = vocab >= 128 and d % 8 == 0
+    for t in (feat, table, d_logits):
+        if t is not None:
+            ok = ok and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0
+    return ok
+
+
 def cast_f32_bf16(src, dst):
     L.check(L.load().zb_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()), "zb_cast_f32_bf16")
 
