@@ -260,3 +260,63 @@ def test_saver_resumes_best_score_writes_atomically_and_best_dir_is_self_contain
     ro = tmp_path / "nothing_here"
     saver.Saver(output_dir=str(ro), readonly=True)
     assert not ro.exists()
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3, 6, 9])
+def test_data_parallel_buckets_cover_the_gradient_arena_exactly_once(tmp_path, host_only, monkeypatch, groups):
+    """utils/parallel.py:134-208 as overlapped all-reduces: the decoder-side bucket after the decoder backward, one bucket
+    per group of encoder layers as the staged encoder backward proceeds (last layers first), the source embedding +
+    shared bias last — reduced while Adam already updates the rest.  Every arena element is reduced exactly once, each
+    bucket only after the backward stage that completes it, and the late bucket is waited for before its Adam slice."""
+    import torch.distributed as dist
+    import zero_b200.ops as ops
+    from zero_b200.train import Trainer
+    monkeypatch.setenv("ZB_ENC_BUCKETS", str(groups))
+    p = _params(tmp_path, num_encoder_layer=3, num_decoder_layer=2, clip_grad_norm=0.0)
+    eng = _engine_for(p)
+    events = []
+
+    class Work(object):
+        def __init__(self, lo, hi):
+            self.lo, self.hi = lo, hi
+
+        def wait(self):
+            events.append(("wait", self.lo, self.hi))
+
+    base = eng.ps.grad.data_ptr()
+
+    def fake_all_reduce(t, op=None, async_op=False):
+        lo = (t.data_ptr() - base) // 4
+        events.append(("reduce", lo, lo + t.numel()))
+        return Work(lo, lo + t.numel())
+
+    def fake_bwd(self, stop_layer=0):
+        events.append(("stage", stop_layer))
+    monkeypatch.setattr(dist, "all_reduce", fake_all_reduce)
+    monkeypatch.setattr(type(eng), "backward_encoder", fake_bwd)
+    monkeypatch.setattr(ops, "adam_tf", lambda param, *a, **k: events.append(
+        ("adam", (param.data_ptr() - eng.ps.master.data_ptr()) // 4,
+         (param.data_ptr() - eng.ps.master.data_ptr()) // 4 + param.numel())))
+    tr = Trainer(eng, p, world_size=2, use_graph=False, side_stream=False)
+    src = torch.randint(3, 20, (2, 5), dtype=torch.int32)
+    tr.step(src, src)
+    reduced = sorted((e[1], e[2]) for e in events if e[0] == "reduce")
+    assert reduced[0][0] == 0 and reduced[-1][1] == eng.ps.total
+    assert all(a[1] == b[0] for a, b in zip(reduced, reduced[1:]))            # contiguous, disjoint, complete
+    g = min(max(groups, 1), 3)
+    stages = [e for e in events if e[0] == "stage"]
+    assert len(stages) == g and stages[-1][1] == 0
+    # a layer group's bucket follows its stage; the decoder-side bucket precedes every stage
+    order = [e for e in events if e[0] in ("stage", "reduce")]
+    assert order[0] == ("reduce", eng.ps.dec_offset, eng.ps.total)
+    for k, st in enumerate(stages):
+        i = order.index(st)
+        assert order[i + 1][0] == "reduce" and order[i + 1][1] == (eng.ps.enc_layer_offset[st[1]] if g > 1 else 0)
+    adams = [e for e in events if e[0] == "adam"]
+    if g > 1:
+        cut = eng.ps.enc_layer_offset[0]
+        assert [(a[1], a[2]) for a in adams] == [(cut, eng.ps.total), (0, cut)]
+        i_late_wait = events.index(("wait", 0, cut))
+        assert events.index(adams[0]) < i_late_wait < events.index(adams[1])      # the embedding bucket hides under Adam
+    else:
+        assert [(a[1], a[2]) for a in adams] == [(0, eng.ps.total)]

@@ -216,7 +216,7 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, const float4 v) {
 // W = warps (= rows) per CTA: 32 is the measured default; 16 (ZB_LN1P_WARPS=16, opt-in, untimed) halves the shared
 // memory per CTA (two CTAs per SM, twice the CTAs) at the price of twice the vector reductions per column.
 template <int NV, int W = kLn1pWarps>
-__global__ void __launch_bounds__(W * 32, 1)
+__global__ void __launch_bounds__(W * 32)
 add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                         const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ d_out2,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -306,8 +306,8 @@ add_ln_bwd_1pass_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
   __syncthreads();
   // thread (q, c4): quantity q in {dscale, doffset, dbias}, 4 columns; sums the CTA's 32 row partials
   const int c4n = cols >> 2;
-  const int q = threadIdx.x / c4n, c4 = threadIdx.x % c4n;
-  if (q < (dbias ? 3 : 2)) {
+  for (int idx = threadIdx.x; idx < (dbias ? 3 : 2) * c4n; idx += W * 32) {
+    const int q = idx / c4n, c4 = idx - q * c4n;
     const float* src = red + (size_t)q * W * cols + c4 * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -521,7 +521,6 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
   static const bool no_1pass = getenv("ZB_LN_BWD_LOOP") != nullptr;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(a->dscale) | reinterpret_cast<uintptr_t>(a->doffset) |
                         reinterpret_cast<uintptr_t>(a->dbias)) & 15) == 0;
-  static const bool w16 = getenv("ZB_LN1P_WARPS") != nullptr && atoi(getenv("ZB_LN1P_WARPS")) == 16;
   static const bool rows8 = getenv("ZB_LN1P_WARPS") != nullptr && atoi(getenv("ZB_LN1P_WARPS")) == 8;
   if (!no_1pass && rows8 && nv <= 2 && vec_ok && a->rows <= (long long)num_sms() * 64) {
     constexpr int R = 4;
@@ -544,25 +543,29 @@ extern "C" int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream) {
 #undef CALLR
     return check_launch("zb_add_ln_bwd(rows per warp)");
   }
-  if (!no_1pass && w16 && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= 16 * 32 && a->rows <= (long long)num_sms() * 32) {
-    const int grid = (int)((a->rows + 15) / 16);
-    const size_t smem1 = (size_t)3 * 16 * a->cols * sizeof(float);
-#define CALL16(N)                                                                                            \
+  // ZB_LN1P_WARPS = 16 / 4 (calibration): fewer rows per CTA -> less shared memory, several CTAs per SM in different
+  // phases, more vector reductions per column (rows8 above is the rows-per-warp kernel)
+  static const int wsel = getenv("ZB_LN1P_WARPS") ? atoi(getenv("ZB_LN1P_WARPS")) : 0;
+  if (!no_1pass && (wsel == 16 || wsel == 4 || wsel == 2) && nv <= 2 && vec_ok && a->rows <= (long long)num_sms() * 64) {
+#define CALLW(N, WW)                                                                                         \
   do {                                                                                                       \
     static bool attr = false;                                                                                \
     if (!attr) {                                                                                             \
-      cudaFuncSetAttribute(add_ln_bwd_1pass_kernel<N, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                           3 * 16 * 512 * (int)sizeof(float));                                               \
+      cudaFuncSetAttribute(add_ln_bwd_1pass_kernel<N, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           3 * WW * 512 * (int)sizeof(float));                                               \
       attr = true;                                                                                           \
     }                                                                                                        \
-    ZB_LAUNCH((add_ln_bwd_1pass_kernel<N, 16>), grid, 16 * 32, smem1, st,                                    \
+    ZB_LAUNCH((add_ln_bwd_1pass_kernel<N, WW>), (int)((a->rows + WW - 1) / WW), WW * 32,                     \
+        (size_t)3 * WW * a->cols * sizeof(float), st,                                                        \
         (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (const __nv_bfloat16*)a->d_out,              \
         (const __nv_bfloat16*)a->d_out2, a->mean, a->rstd, a->scale, (__nv_bfloat16*)a->ds, a->dscale,       \
         a->doffset, a->dbias, a->rows, (int)a->cols);                                                        \
   } while (0)
-    if (nv <= 1) CALL16(1); else CALL16(2);
-#undef CALL16
-    return check_launch("zb_add_ln_bwd(1pass, 16 rows)");
+    if (wsel == 16) { if (nv <= 1) CALLW(1, 16); else CALLW(2, 16); }
+    else if (wsel == 4) { if (nv <= 1) CALLW(1, 4); else CALLW(2, 4); }
+    else { if (nv <= 1) CALLW(1, 2); else CALLW(2, 2); }
+#undef CALLW
+    return check_launch("zb_add_ln_bwd(1pass, W rows)");
   }
   if (!no_1pass && nv <= 2 && vec_ok && 3 * (a->cols / 4) <= kLn1pWarps * 32 &&
       a->rows <= (long long)num_sms() * kLn1pWarps) {

@@ -175,8 +175,10 @@ class ParamStore(object):
             lin(key + ".w1", tfp + "/ffn_layer/enlarge", c.d, c.f)
             lin(key + ".w2", tfp + "/ffn_layer/output", c.f, c.d)
 
+        self.enc_layer_offset = []     # arena offset of every encoder layer's first parameter (all-reduce buckets)
         for l in range(c.nenc):
             key, tfp = "enc%d" % l, "%s/encoder/layer_%d" % (s, l)
+            self.enc_layer_offset.append(self.total)
             self_attn(key + ".self", tfp + "/self_attention")
             ffn(key + ".ffn", tfp + "/feed_forward")
             ln(key + ".ffn.ln", tfp + "/feed_forward")
@@ -667,13 +669,16 @@ class Engine(object):
             save.update(layers=layers, source=source, src_len=src_len, B=B, S=S, emb_rate=r_emb)
         return x, src_len
 
-    def encode_bwd(self, d_enc, save, tag="E"):
-        """d_enc: bf16 [B*S, d] gradient wrt the encoder output."""
+    def encode_bwd(self, d_enc, save, tag="E", stop_layer=0, carry=None):
+        """d_enc: bf16 [B*S, d] gradient wrt the encoder output.  `stop_layer` > 0 processes the layers down to it
+        and returns the (d1, d2) pair to hand back as `carry` for the remaining ones: the trainer all-reduces a group
+        of layers' gradients while the next group's backward runs."""
         c, ps = self.cfg, self.ps
         B, S = save["B"], save["S"]
         N = B * S
-        d1, d2 = d_enc, None
-        for l in reversed(range(c.nenc)):
+        d1, d2 = (d_enc, None) if carry is None else carry[:2]
+        top = c.nenc if carry is None else carry[2]
+        for l in reversed(range(stop_layer, top)):
             key, bw = "enc%d" % l, "%s.bw%d" % (tag, l & 1)   # backward temporaries: two sets, by layer parity
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
@@ -683,8 +688,11 @@ class Engine(object):
             dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, S, sv["att"], bw + ".att")
             self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
+        if stop_layer > 0:
+            return (d1, d2, stop_layer)
         d1, d2 = self._embed_dropout_bwd(d1, d2, save.get("emb_rate", 0.0), "enc.emb", tag)
         ops.embed_bwd(save["source"], d1, ps.g("src_emb"), ps.g("emb_bias"), mult=c.d ** 0.5, d_out2=d2)
+        return None
 
     def _embed_dropout_bwd(self, d1, d2, rate, site, tag):
         """Gradient through the embedding dropout: the two addends are summed, masked and rescaled in one pass."""
@@ -880,14 +888,31 @@ class Engine(object):
         self._pending = (d_enc, esave)
         return loss
 
-    def backward_encoder(self):
-        """Phase 2: backward of the encoder (finalises ps.grad[:ps.dec_offset])."""
+    def backward_encoder(self, stop_layer=0):
+        """Phase 2: backward of the encoder (finalises ps.grad[:ps.dec_offset]).  With stop_layer > 0 only the layers
+        from the current position down to `stop_layer` run (their gradients — arena [enc_layer_offset[stop_layer], end
+        of the previous group) — are final when the call returns in stream order); call again to continue."""
         if self._pending is None:      # empty tower (see forward_backward_decoder)
             return
-        d_enc, esave = self._pending
-        self._pending = None
-        self.encode_bwd(d_enc, esave)
+        d_enc, esave = self._pending[:2]
+        carry = self._pending[2] if len(self._pending) > 2 else None
+        carry = self.encode_bwd(d_enc, esave, stop_layer=stop_layer, carry=carry)
         self._side_join()
+        self._pending = None if carry is None else (d_enc, esave, carry)
+
+    def encoder_buckets(self, groups):
+        """Arena ranges [(stop_layer, lo, hi)] of `groups` groups of encoder layers, last layers first, followed by
+        (0, 0, first layer offset) for the source embedding + shared bias, whose gradients are the last to complete."""
+        c, ps = self.cfg, self.ps
+        groups = max(1, min(int(groups), c.nenc))
+        per = (c.nenc + groups - 1) // groups
+        out, hi, top = [], ps.dec_offset, c.nenc
+        while top > 0:
+            stop = max(0, top - per)
+            out.append((stop, ps.enc_layer_offset[stop], hi))
+            hi, top = ps.enc_layer_offset[stop], stop
+        out.append((0, 0, ps.enc_layer_offset[0]))
+        return out
 
     def train_loss(self, source, target):
         """train_fn forward only -> (loss, per_sample, logits)."""

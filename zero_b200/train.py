@@ -97,6 +97,13 @@ class Trainer(object):
         # split optimizer step (see _step_split); ZB_EARLY_ADAM=0 keeps the single fused pass after the backward
         self.early_adam = (early_adam or os.environ.get("ZB_EARLY_ADAM", "0") == "1") and self.shard is None
         self._opt_stream = None
+        # Data parallel without the sharded step: the encoder backward runs in `enc_groups` groups of layers (last
+        # layers first) and every group's slice of the gradient arena is all-reduced while the next group's backward
+        # runs; the source embedding + shared bias, whose gradients complete last, go out as their own bucket and are
+        # reduced WHILE Adam already updates everything else (no global quantity is needed when clipping is off).
+        # ZB_ENC_BUCKETS=1 restores the two-bucket scheme of round 1.
+        self.enc_groups = int(os.environ.get("ZB_ENC_BUCKETS", "3")) if (self.world > 1 and self.shard is None) else 1
+        self._late = None
 
     # ------------------------------------------------------------------------------------------ lr
     def lr(self):
@@ -111,7 +118,8 @@ class Trainer(object):
 
     # ------------------------------------------------------------------------------------------ step
     def _phases(self, source, target, zero_grad=True):
-        """Runs phase 1 (forward + decoder backward) and returns (loss, phase-2 callable)."""
+        """Runs phase 1 (forward + decoder backward) and returns (loss, stages): the encoder backward as a list of
+        callables, one per group of layers (Engine.encoder_buckets order), the last one including the embedding."""
         eng = self.eng
         eng.advance_dropout_seed()
         if self.use_graph and self.bucket > 1:
@@ -145,23 +153,31 @@ class Trainer(object):
                 # allocation it replaced
                 self._graphs.clear()
                 self._graphs_gen = eng.ws.generation
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 loss = eng.forward_backward_decoder(s_src, s_tgt, zero_grad=zero_grad, compact=False)
-            with torch.cuda.graph(g2, pool=g1.pool()):
-                eng.backward_encoder()
+            g2 = []
+            for stop in self._stage_stops():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=g1.pool()):
+                    eng.backward_encoder(stop_layer=stop)
+                g2.append(g)
             if keep is not None:
                 eng.ps.grad.copy_(keep)   # capture does not execute, but stay safe against future changes
             entry = self._graphs[key] = (g1, g2, s_src, s_tgt, loss)
         if entry is None:
             loss = eng.forward_backward_decoder(source, target, zero_grad=zero_grad,
                                                 compact=not self.use_graph)
-            return loss, eng.backward_encoder
+            return loss, [(lambda stop=stop: eng.backward_encoder(stop_layer=stop)) for stop in self._stage_stops()]
         g1, g2, s_src, s_tgt, loss = entry
         s_src.copy_(source, non_blocking=True)
         s_tgt.copy_(target, non_blocking=True)
         g1.replay()
-        return loss, g2.replay
+        return loss, [g.replay for g in g2]
+
+    def _stage_stops(self):
+        """stop_layer of every encoder-backward stage (the last stage runs to layer 0 and the embedding)."""
+        return [b[0] for b in self.eng.encoder_buckets(self.enc_groups)[:-1]]
 
     def step(self, source, target):
         """One micro-batch.  Returns the device loss tensor [1] of this micro-batch (no host sync).  The parameters
@@ -184,7 +200,11 @@ class Trainer(object):
         (Trainer(early_adam=True) / the ab_bench tools keep the experiment reproducible)."""
         eng, ps = self.eng, self.eng.ps
         first = self._micro == 0
-        loss, phase2 = self._phases(source, target, zero_grad=first)
+        loss, stages = self._phases(source, target, zero_grad=first)
+
+        def phase2():
+            for st in stages:
+                st()
         if self.cycle > 1:
             if first:
                 self.loss_acc.zero_()
@@ -224,18 +244,30 @@ class Trainer(object):
         eng, ps = self.eng, self.eng.ps
         first = self._micro == 0
         last = self._micro == self.cycle - 1
-        loss, phase2 = self._phases(source, target, zero_grad=first)
+        loss, stages = self._phases(source, target, zero_grad=first)
         if self.cycle > 1:
             if first:
                 self.loss_acc.zero_()
             self.loss_acc += loss
         works = []
         reduce_now = last and self.world > 1 and self.shard is None   # sharded step: the sum is taken in apply()
+        buckets = eng.encoder_buckets(self.enc_groups)
         if reduce_now:
             works.append(dist.all_reduce(ps.grad[ps.dec_offset:], op=dist.ReduceOp.SUM, async_op=True))
-        phase2()
+        for (stop, lo, hi), stage in zip(buckets[:-1], stages):
+            stage()
+            if reduce_now and self.enc_groups > 1:
+                works.append(dist.all_reduce(ps.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
         if reduce_now:
-            works.append(dist.all_reduce(ps.grad[:ps.dec_offset], op=dist.ReduceOp.SUM, async_op=True))
+            if self.enc_groups > 1:
+                # source embedding + shared bias: reduced while apply() updates the rest (when nothing global is needed)
+                late = dist.all_reduce(ps.grad[:buckets[-1][2]], op=dist.ReduceOp.SUM, async_op=True)
+                if self.clip is None and not bool(getattr(self.hp, "safe_nan", False)):
+                    self._late = (late, buckets[-1][2])
+                else:
+                    works.append(late)
+            else:
+                works.append(dist.all_reduce(ps.grad[:ps.dec_offset], op=dist.ReduceOp.SUM, async_op=True))
             for w in works:
                 w.wait()
         self._micro = 0 if last else self._micro + 1
@@ -261,6 +293,9 @@ class Trainer(object):
     def skip(self):
         """Drop the collected gradients without updating (safe_nan, main.py:326-330: the step is 'passed')."""
         self._pending = False
+        if self._late is not None:
+            self._late[0].wait()
+            self._late = None
 
     def apply(self):
         """clip_by_global_norm + TF Adam on the averaged gradients (utils/cycle.py:94-105) + EMA."""
@@ -291,8 +326,17 @@ class Trainer(object):
             torch.div(self.clip, torch.clamp(gn, min=self.clip), out=self.clip_scale[0])
             clip_scale = self.clip_scale
             self.norms.zero_()
-        ops.adam_tf(ps.master, ps.adam_m, ps.adam_v, ps.grad, ps.mirror, self.beta1, self.beta2, self.eps,
-                    lr_t, gscale, clip_scale, self.norms)
+        if self._late is not None:
+            work, cut = self._late
+            self._late = None
+            ops.adam_tf(ps.master[cut:], ps.adam_m[cut:], ps.adam_v[cut:], ps.grad[cut:], ps.mirror[cut:], self.beta1,
+                        self.beta2, self.eps, lr_t, gscale, clip_scale, self.norms)
+            work.wait()
+            ops.adam_tf(ps.master[:cut], ps.adam_m[:cut], ps.adam_v[:cut], ps.grad[:cut], ps.mirror[:cut], self.beta1,
+                        self.beta2, self.eps, lr_t, gscale, clip_scale, self.norms)
+        else:
+            ops.adam_tf(ps.master, ps.adam_m, ps.adam_v, ps.grad, ps.mirror, self.beta1, self.beta2, self.eps,
+                        lr_t, gscale, clip_scale, self.norms)
         self._ema_update()
 
     def _ema_update(self):
