@@ -36,6 +36,9 @@ typedef enum {
 typedef enum { ZB_BF16 = 0, ZB_F32 = 1 } zb_dtype;
 
 int zb_abi_version(void);
+/* SMs left free by the persistent tensor-core kernels (GEMM, attention) for a collective that runs next to them
+ * (NCCL all-reduce kernels during the backward pass); 0 (default) on a single GPU.  Process-wide. */
+int zb_set_sm_reserve(int32_t n);
 const char* zb_last_error_string(void);
 /* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 int64_t zb_launch_count(void);

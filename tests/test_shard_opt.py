@@ -318,4 +318,4 @@ def test_safe_nan_keeps_the_all_reduce_path(monkeypatch, host_only):
     assert tr.shard is None
     monkeypatch.delenv("ZB_SHARD_OPT")
     tr = Trainer(eng, _hp(), world_size=2, use_graph=False, side_stream=False)
-    assert tr.shard is None                            # opt-in only
+    assert tr.shard is None                            # "auto" needs an initialised process group to set it up

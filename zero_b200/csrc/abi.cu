@@ -50,7 +50,26 @@ int num_sms() {
   return sms;
 }
 
+// SMs the persistent tensor-core kernels (GEMM, attention) size their grids for.  A data-parallel job runs NCCL's
+// all-reduce kernels (one CTA per channel) next to the backward pass; a persistent grid of exactly num_sms() CTAs
+// then cannot be co-resident and runs in two rounds (measured: the overlapped GEMMs take up to 2x).  Leaving a few
+// SMs to the collective (zb_set_sm_reserve, set by the trainer when world_size > 1) costs reserve / num_sms instead.
+static std::atomic<int> g_sm_reserve{0};
+int num_sms_compute() {
+  const int n = num_sms() - g_sm_reserve.load(std::memory_order_relaxed);
+  return n < 8 ? 8 : (n & ~1);   // even: the CTA-pair GEMM launches whole pairs
+}
+
 }  // namespace zb
+
+extern "C" int zb_set_sm_reserve(int32_t n) {
+  if (n < 0 || n > 64) {
+    zb::set_error("zb_set_sm_reserve: %d outside [0, 64]", (int)n);
+    return ZB_EINVAL;
+  }
+  zb::g_sm_reserve.store(n, std::memory_order_relaxed);
+  return ZB_OK;
+}
 
 extern "C" int zb_abi_version(void) { return ZB_ABI_VERSION; }
 extern "C" const char* zb_last_error_string(void) { return zb::g_err; }

@@ -1623,7 +1623,7 @@ int attention_tc_fwd(const zb_attention_args* a, cudaStream_t st) {
       cudaFuncSetAttribute(fat::fwd_tc_rpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
       attr_r = true;
     }
-    const int grid_r = p.units < num_sms() ? p.units : num_sms();
+    const int grid_r = p.units < num_sms_compute() ? p.units : num_sms_compute();
     if (p.drop_rate > 0.f)
       ZB_LAUNCH(fat::fwd_tc_rpr_kernel<true>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mo, mek, mev, p, (int)a->max_rel);
     else
@@ -1638,7 +1638,7 @@ int attention_tc_fwd(const zb_attention_args* a, cudaStream_t st) {
     cudaFuncSetAttribute(fat::fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  const int grid = p.units < num_sms() ? p.units : num_sms();
+  const int grid = p.units < num_sms_compute() ? p.units : num_sms_compute();
   if (p.drop_rate > 0.f) ZB_LAUNCH(fat::fwd_tc_kernel<true>, grid, fat::kThreads, smem, st, mq, mk, mv, mo, p);
   else ZB_LAUNCH(fat::fwd_tc_kernel<false>, grid, fat::kThreads, smem, st, mq, mk, mv, mo, p);
   note_path(ZB_PATH_ATTN_TC);
@@ -1672,7 +1672,7 @@ int attention_tc_bwd(const zb_attention_args* a, cudaStream_t st) {
       cudaFuncSetAttribute(fat::bwd_tc_rpr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r);
       attr_r = true;
     }
-    const int grid_r = p.units < num_sms() ? p.units : num_sms();
+    const int grid_r = p.units < num_sms_compute() ? p.units : num_sms_compute();
     if (p.drop_rate > 0.f)
       ZB_LAUNCH(fat::bwd_tc_rpr_kernel<true>, grid_r, fat::kThreads, smem_r, st, mq, mk, mv, mdo, mdq, mdk, mdv, mek, mev, p,
                 (int)a->max_rel, a->d_rpr_k, a->d_rpr_v);
@@ -1697,7 +1697,7 @@ int attention_tc_bwd(const zb_attention_args* a, cudaStream_t st) {
       return ZB_ECUDA;
     }
   }
-  const int grid = p.units < num_sms() ? p.units : num_sms();
+  const int grid = p.units < num_sms_compute() ? p.units : num_sms_compute();
   if (p.drop_rate > 0.f)
     ZB_LAUNCH(fat::bwd_tc_kernel<true>, grid, fat::kThreads, smem, st, mq, mk, mv, mdo, mdq, mdk, mdv, p);
   else

@@ -751,7 +751,7 @@ static void set_splits(Gemm2Params& p, int splits) {
 
 int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
   const bool accum = a->flags & ZB_EPI_ACCUM;
-  const int pairs_hw = num_sms() / 2;
+  const int pairs_hw = num_sms_compute() / 2;
   const int mt = (int)((a->m + 255) / 256);
   int bn = 256;
   auto tiles_for = [&](int b) { return (long long)mt * ((a->n + b - 1) / b); };
@@ -817,7 +817,7 @@ int gemm2_launch(const zb_gemm_args* a, cudaStream_t st) {
 // mode 1 needs no output tensor (a->d is ignored); mode 2 writes bf16 d_logits to a->d.
 int gemm2_launch_ce(const zb_gemm_args* a, int mode, const float* aux, const int32_t* labels, float4* stats, float ce_p,
                     float ce_q, cudaStream_t st) {
-  const int pairs_hw = num_sms() / 2;
+  const int pairs_hw = num_sms_compute() / 2;
   Gemm2Group<1> G;
   Gemm2Params& p = G.prob[0];
   zb_gemm_args b = *a;
@@ -851,7 +851,7 @@ int gemm2_launch_group(const zb_gemm_args* args, int count, cudaStream_t st) {
         a->d_dtype != ZB_F32 || a->split_k > 0 || a->n < 256 || a->m < 256 || !gemm2_wanted(a))
       return 1;
   }
-  const int pairs_hw = num_sms() / 2;
+  const int pairs_hw = num_sms_compute() / 2;
   Gemm2Group<k2MaxGroup> G;
   long long tiles = 0;
   int kb_min = 1 << 30, kb_max = 0;

@@ -604,7 +604,7 @@ extern "C" int zb_gemm(const zb_gemm_args* a, zb_stream_t stream) {
   const int bm = bm64 ? 64 : kBM;
   p.mt = (p.M + bm - 1) / bm;
 
-  const int sms = num_sms();
+  const int sms = num_sms_compute();
   // Tile width: the widest BN whose tile count still fills the machine (wave quantisation dominates at the
   // reference's 4096-token batches); 256 when there is plenty of work.
   int bn = 256;

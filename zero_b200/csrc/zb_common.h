@@ -26,6 +26,7 @@ inline int check_launch(const char* what) {
 }
 
 int num_sms();
+int num_sms_compute();   // num_sms() minus the SMs reserved for a concurrent collective (zb_set_sm_reserve)
 
 // Every kernel of the library starts with griddepcontrol.wait and is launched with programmatic stream
 // serialisation, so its launch latency and prologue overlap the tail of its predecessor in the stream (or in the

@@ -112,7 +112,7 @@ EXPORTS = [
     "zb_beam_step", "zb_gather_rows", "zb_prefix_mean_fwd", "zb_prefix_mean_bwd", "zb_aan_step",
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
     "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam", "zb_gumbel_add",
-    "zb_attention_bwd_workspace_bytes", "zb_vocab_ce", "zb_vocab_ce_workspace_bytes",
+    "zb_attention_bwd_workspace_bytes", "zb_vocab_ce", "zb_vocab_ce_workspace_bytes", "zb_set_sm_reserve",
 ]
 
 _lib = None
@@ -149,6 +149,7 @@ def load():
         ("zb_embed_bwd", [C.POINTER(EmbedArgs), vp]),
         ("zb_softmax_ce", [C.POINTER(CeArgs), vp]),
         ("zb_vocab_ce", [C.POINTER(VocabCeArgs), vp]),
+        ("zb_set_sm_reserve", [i32]),
         ("zb_colsum", [vp, i64, i64, i64, vp, vp]),
         ("zb_cast_f32_bf16", [vp, vp, i64, vp]),
         ("zb_cast_bf16_f32", [vp, vp, i64, vp]),

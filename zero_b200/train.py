@@ -85,11 +85,18 @@ class Trainer(object):
         # NCCL all-reduce + replicated Adam below.  safe_nan needs the summed gradients on the host BEFORE the update
         # (main.py:320-332), which the fused step never materialises: that mode keeps the all-reduce.
         self.shard = None
-        mode = os.environ.get("ZB_SHARD_OPT", "0")
-        if shard_transport is not None or (self.world > 1 and mode in ("1", "p2p")
-                                           and not bool(getattr(hp, "safe_nan", False))):
-            from .shard_opt import ShardedStep, SymmMemTransport
-            self.shard = ShardedStep(engine, shard_transport or SymmMemTransport(), use_multicast=mode != "p2p")
+        # ZB_SHARD_OPT: "auto" (default) = the fused step, over unicast peer mappings on two GPUs and over the NVSwitch
+        # multicast mapping from three on (measured at N = 2: 3.87 ms/step against 4.01 for the bucketed all-reduce; at
+        # N = 8: 4.19 against 4.34 — profiles/r02_scaling_ab.log); "0" = NCCL all-reduce + replicated Adam; "1" / "p2p"
+        # force a transport.  If the symmetric-memory set-up fails on ANY rank, every rank falls back to the all-reduce.
+        mode = os.environ.get("ZB_SHARD_OPT", "auto")
+        if mode == "auto":
+            mode = "0" if self.world <= 1 else ("p2p" if self.world == 2 else "1")
+        if shard_transport is not None:
+            from .shard_opt import ShardedStep
+            self.shard = ShardedStep(engine, shard_transport, use_multicast=mode != "p2p")
+        elif self.world > 1 and mode in ("1", "p2p") and not bool(getattr(hp, "safe_nan", False)):
+            self.shard = self._try_sharded_step(engine, mode)
         # exponential moving average of the parameters (utils/cycle.py:114-127), off unless ema_decay > 0
         self.ema_decay = float(getattr(hp, "ema_decay", -1.0))
         self.ema = engine.ps.master.clone() if self.ema_decay > 0.0 else None
@@ -102,8 +109,40 @@ class Trainer(object):
         # runs; the source embedding + shared bias, whose gradients complete last, go out as their own bucket and are
         # reduced WHILE Adam already updates everything else (no global quantity is needed when clipping is off).
         # ZB_ENC_BUCKETS=1 restores the two-bucket scheme of round 1.
-        self.enc_groups = int(os.environ.get("ZB_ENC_BUCKETS", "3")) if (self.world > 1 and self.shard is None) else 1
+        # (measured: three groups win on two GPUs, 4.01 vs 4.11 ms/step; at N = 8 NCCL's per-call cost makes the
+        # two-bucket scheme the faster one, 4.34 vs 4.40 ms/step)
+        groups = os.environ.get("ZB_ENC_BUCKETS") or ("3" if self.world == 2 else "1")
+        self.enc_groups = int(groups) if (self.world > 1 and self.shard is None) else 1
         self._late = None
+        # NCCL's all-reduce kernels run next to the backward pass: the persistent GEMM / attention grids leave them a
+        # few SMs instead of being split into two rounds (csrc/abi.cu num_sms_compute)
+        # (measured at N = 8: no gain from reserving 8 / 16 / 32 SMs — 4.34 / 4.36 / 4.37 / 4.52 ms/step — so the default
+        # is 0; ZB_SM_RESERVE keeps the experiment reproducible)
+        if self.world > 1 and self.shard is None and os.environ.get("ZB_SM_RESERVE"):
+            L.check(L.load().zb_set_sm_reserve(int(os.environ["ZB_SM_RESERVE"])), "zb_set_sm_reserve")
+
+    def _try_sharded_step(self, engine, mode):
+        """ShardedStep over symmetric memory, or None (on every rank) when any rank could not set it up."""
+        from .shard_opt import ShardedStep, SymmMemTransport
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        shard, err = None, None
+        keep = {name: getattr(engine.ps, name) for name in ("grad", "mirror", "master")}
+        try:
+            shard = ShardedStep(engine, SymmMemTransport(), use_multicast=mode != "p2p")
+        except Exception as e:     # noqa: BLE001 — whatever the plumbing raises, the all-reduce path still works
+            err = e
+        ok = torch.tensor([0 if shard is None else 1], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            return shard
+        if dist.get_rank() == 0:
+            print("zero_b200: sharded optimizer step unavailable (%r); using the NCCL all-reduce" % (err,), flush=True)
+        for name, t in keep.items():      # undo the rebinding of the arenas a partial set-up may have done
+            if getattr(engine.ps, name) is not t:
+                t.copy_(getattr(engine.ps, name))
+                setattr(engine.ps, name, t)
+        return None
 
     # ------------------------------------------------------------------------------------------ lr
     def lr(self):
