@@ -235,7 +235,13 @@ def test_sharded_step_equals_replicated_adam_on_the_mean_gradient(world_size, cl
 
         def one(r):
             trainers[r]._pending = True
+            if clip == 0.0 and step >= 2:
+                # what Trainer.compute does after the decoder backward: the decoder-side region goes first (on the GPU
+                # on a second stream, under the encoder backward), apply() then finishes with the encoder side
+                trainers[r]._shard_early()
+                assert trainers[r].shard._early_done
             trainers[r].apply()
+            assert not trainers[r].shard._early_done
         _run_ranks(world_size, one)
 
         g = sum(grads) / world_size                                  # utils/parallel.py:196: mean over the towers
@@ -252,20 +258,26 @@ def test_sharded_step_equals_replicated_adam_on_the_mean_gradient(world_size, cl
         d = min(0.9, (1.0 + step) / (10.0 + step))
         ema_ref = ema_ref + (p_ref - ema_ref) * (1.0 - d)
         wide = shard_opt.wide_slot_mask(engines[0].ps).bool().repeat_interleave(64)
-        owned = torch.cat([engines[r].ps.master[lo:lo + n] for r, (lo, n) in enumerate(trainers[0].shard.shards)])
+        # the arena is sharded as one region (clipping) or two (decoder side / encoder side): assemble the owners' state
+        owned = torch.zeros(total)
+        for plan in trainers[0].shard.plans:
+            for r, (lo, n) in enumerate(plan):
+                owned[lo:lo + n] = engines[r].ps.master[lo:lo + n]
+        assert (len(trainers[0].shard.plans) == 2) == (clip == 0.0)
         for r in range(world_size):
             ps, tr = engines[r].ps, trainers[r]
-            lo, n = tr.shard.lo, tr.shard.n
+            mine = torch.zeros(total, dtype=torch.bool)
+            for lo, n in tr.shard.ranges:
+                mine[lo:lo + n] = True
             assert tr.global_step == step
             # every rank's compute copy is whole and identical; own shard of the fp32 state is current
             assert torch.equal(ps.mirror, owned.to(bf16)) and torch.equal(ps.mirror, engines[0].ps.mirror)
             torch.testing.assert_close(ps.mirror.float(), p_ref, atol=1e-2, rtol=1e-2)
-            torch.testing.assert_close(ps.master[lo:lo + n], p_ref[lo:lo + n], atol=1e-6, rtol=1e-5)
-            torch.testing.assert_close(ps.adam_m[lo:lo + n], m_ref[lo:lo + n], atol=1e-7, rtol=1e-5)
+            torch.testing.assert_close(ps.master[mine], p_ref[mine], atol=1e-6, rtol=1e-5)
+            torch.testing.assert_close(ps.adam_m[mine], m_ref[mine], atol=1e-7, rtol=1e-5)
             # fp32-read variables are current everywhere, the rest of the foreign master is untouched (stale)
             torch.testing.assert_close(ps.master[wide], p_ref[wide], atol=1e-6, rtol=1e-5)
-            foreign = torch.ones(total, dtype=torch.bool)
-            foreign[lo:lo + n] = False
+            foreign = ~mine
             assert torch.equal(ps.master[foreign & ~wide], stale_before[r][foreign & ~wide])
             # tf.global_norm of the averaged gradients / pre-update parameters, no extra collective
             assert abs(tr.gradient_norm() - gn) < 1e-4 * max(gn, 1.0)

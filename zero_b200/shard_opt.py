@@ -43,6 +43,11 @@ def plan_shards(total, world):
     return out
 
 
+def plan_region(lo, hi, world):
+    """plan_shards over the arena range [lo, hi) (both 64-element granular)."""
+    return [(lo + a, n) for a, n in plan_shards(hi - lo, world)]
+
+
 def wide_slot_mask(ps):
     """uint8 per 64-element slot: 1 where the slot belongs to a 1-D variable (biases, LayerNorm scale / offset, the
     shared embedding bias, ReLA gates): engine code reads those through ParamStore.p(), i.e. from the fp32 master."""
@@ -90,9 +95,10 @@ class SymmMemTransport(object):
             mc += t.data_ptr() - int(h.buffer_ptrs[self.rank])
         return ptrs, mc
 
-    def barrier(self):
-        """Enqueued on the current stream: returns (on the device) once every rank has reached it."""
-        self._handles[0].barrier(channel=0)
+    def barrier(self, channel=0):
+        """Enqueued on the current stream: returns (on the device) once every rank has reached it.  Barriers that may
+        be in flight on different streams at the same time use different channels."""
+        self._handles[0].barrier(channel=channel)
 
     def broadcast(self, t, src):
         import torch.distributed as dist
@@ -103,7 +109,10 @@ class ShardedStep(object):
     """Owns the symmetric arenas of one rank and issues the fused step.  `trainer` supplies the hyper-parameters and
     the local scalars (norms, clip_scale)."""
 
-    def __init__(self, engine, transport, use_multicast=True):
+    def __init__(self, engine, transport, use_multicast=True, split=None):
+        """`split` (an arena offset, normally ParamStore.dec_offset): the arena is sharded as TWO regions,
+        [split, total) — whose gradients are final after the decoder backward — and [0, split); `step_early` reduces
+        and updates the first one on a second stream while the encoder backward still runs."""
         ps = engine.ps
         if ps.adam_m is None or ps.adam_v is None:
             raise L.ZeroB200Error("ShardedStep needs the Adam slots (create it from a Trainer)")
@@ -112,8 +121,13 @@ class ShardedStep(object):
         if self.world > L.SHARD_MAX_WORLD:
             raise L.ZeroB200Error("sharded optimizer step: at most %d ranks" % L.SHARD_MAX_WORLD)
         dev = ps.device
-        self.shards = plan_shards(ps.total, self.world)
-        self.lo, self.n = self.shards[self.rank]
+        self.split = int(split) if split else None
+        regions = [(0, ps.total)] if not self.split else [(self.split, ps.total), (0, self.split)]
+        self.plans = [plan_region(a, b, self.world) for a, b in regions]
+        self.ranges = [plan[self.rank] for plan in self.plans]          # this rank's (lo, n) per region
+        self.shards = self.plans[0]                                      # single-region view (clip flow, tests)
+        self.lo, self.n = self.ranges[0]
+        self._early_done = False
         # the three arenas peers touch move into symmetric memory; views are taken from ps.* on every use
         # (ParamStore._view), so rebinding before the first captured step is enough
         for name, dtype in (("grad", f32), ("mirror", bf16), ("master", f32)):
@@ -134,14 +148,15 @@ class ShardedStep(object):
         self.steps = 0
 
     # ---------------------------------------------------------------------------------------------- the step
-    def _launch(self, tr, lr_t, gscale, flags, clip_scale=None, local_grad=None):
+    def _launch(self, tr, lr_t, gscale, flags, clip_scale=None, local_grad=None, region=0):
         ps = self.ps
+        lo, n = self.ranges[region]
         if local_grad is None:
             gptrs, gmc, sources = self.grad_ptrs, self.grad_mc, self.world
         else:
             # second pass of the clip flow: the summed gradients already sit in `local_grad` (indexed like the arena)
             gptrs, gmc, sources = [local_grad], 0, 1
-        ops.shard_adam(self.lo, self.n, self.world, self.rank, gptrs, self.mirror_ptrs, ps.master, ps.adam_m, ps.adam_v,
+        ops.shard_adam(lo, n, self.world, self.rank, gptrs, self.mirror_ptrs, ps.master, ps.adam_m, ps.adam_v,
                        tr.beta1, tr.beta2, tr.eps, lr_t, gscale, flags=flags, grad_mc=gmc, mirror_mc=self.mirror_mc,
                        grad_out=None if not (flags & L.ZB_SHARD_STORE_GRAD) else self._reduced_base(),
                        clip_scale=clip_scale, norms=tr.norms, norm_parts_ptrs=self.parts_ptrs, done_counter=self.done,
@@ -158,10 +173,25 @@ class ShardedStep(object):
         clip_by_global_norm (utils/cycle.py:94-101) the factor needs the norm of the SUMMED gradients first:
         pass 1 reduces the shard into a local buffer and exchanges sum g^2, pass 2 updates from that buffer."""
         tp = self.tp
+        full = L.ZB_SHARD_UPDATE | L.ZB_SHARD_NORM_G | L.ZB_SHARD_NORM_P
+        if self.split:
+            if tr.clip is not None:
+                raise L.ZeroB200Error("the two-region sharded step has no clip flow (construct without split)")
+            if not self._early_done:            # nobody ran step_early: both regions now
+                tr.norms.zero_()
+                tp.barrier()
+                self._launch(tr, lr_t, gscale, full, region=0)
+            else:
+                tp.barrier()                    # every rank's encoder backward has finished
+            self._launch(tr, lr_t, gscale, full, region=1)
+            tp.barrier()
+            self._early_done = False
+            self.steps += 1
+            return
         tr.norms.zero_()
         tp.barrier()
         if tr.clip is None:
-            self._launch(tr, lr_t, gscale, L.ZB_SHARD_UPDATE | L.ZB_SHARD_NORM_G | L.ZB_SHARD_NORM_P)
+            self._launch(tr, lr_t, gscale, full)
         else:
             self._launch(tr, lr_t, gscale, L.ZB_SHARD_STORE_GRAD | L.ZB_SHARD_NORM_G)
             tp.barrier()
@@ -171,6 +201,16 @@ class ShardedStep(object):
                          local_grad=self._reduced_base())
         tp.barrier()
         self.steps += 1
+
+    def step_early(self, tr, lr_t, gscale):
+        """First region of a split plan (the decoder side).  The caller has made the current stream wait for this rank's
+        decoder backward; the barrier makes it wait for every other rank's too — the kernel then reads their decoder-
+        side gradients and overwrites their decoder-side weights while their encoder backward runs."""
+        assert self.split and not self._early_done
+        tr.norms.zero_()
+        self.tp.barrier(1) if isinstance(self.tp, SymmMemTransport) else self.tp.barrier()
+        self._launch(tr, lr_t, gscale, L.ZB_SHARD_UPDATE | L.ZB_SHARD_NORM_G | L.ZB_SHARD_NORM_P, region=0)
+        self._early_done = True
 
     def norms(self):
         """fp32 [2] device tensor: {sum (g * gscale)^2, sum p^2} over the whole arena (all ranks' shards)."""
@@ -182,6 +222,7 @@ class ShardedStep(object):
         `extra`, e.g. the EMA shadow) from its owner; afterwards the local copies are complete and identical."""
         ps = self.ps
         for arena in (ps.master, ps.adam_m, ps.adam_v) + tuple(extra):
-            for r, (lo, n) in enumerate(self.shards):
-                if n:
-                    self.tp.broadcast(arena[lo:lo + n], r)
+            for plan in self.plans:
+                for r, (lo, n) in enumerate(plan):
+                    if n:
+                        self.tp.broadcast(arena[lo:lo + n], r)

@@ -92,9 +92,13 @@ class Trainer(object):
         mode = os.environ.get("ZB_SHARD_OPT", "auto")
         if mode == "auto":
             mode = "0" if self.world <= 1 else ("p2p" if self.world == 2 else "1")
+        # two regions (decoder side first, under the encoder backward) unless clipping needs the global norm first
+        self._shard_split = engine.ps.dec_offset if (self.clip is None and os.environ.get("ZB_SHARD_OVERLAP", "1") != "0"
+                                                     and 0 < engine.ps.dec_offset < engine.ps.total) else None
+        self._early = None
         if shard_transport is not None:
             from .shard_opt import ShardedStep
-            self.shard = ShardedStep(engine, shard_transport, use_multicast=mode != "p2p")
+            self.shard = ShardedStep(engine, shard_transport, use_multicast=mode != "p2p", split=self._shard_split)
         elif self.world > 1 and mode in ("1", "p2p") and not bool(getattr(hp, "safe_nan", False)):
             self.shard = self._try_sharded_step(engine, mode)
         # exponential moving average of the parameters (utils/cycle.py:114-127), off unless ema_decay > 0
@@ -129,7 +133,7 @@ class Trainer(object):
         shard, err = None, None
         keep = {name: getattr(engine.ps, name) for name in ("grad", "mirror", "master")}
         try:
-            shard = ShardedStep(engine, SymmMemTransport(), use_multicast=mode != "p2p")
+            shard = ShardedStep(engine, SymmMemTransport(), use_multicast=mode != "p2p", split=self._shard_split)
         except Exception as e:     # noqa: BLE001 — whatever the plumbing raises, the all-reduce path still works
             err = e
         ok = torch.tensor([0 if shard is None else 1], dtype=torch.int32, device=engine.device)
@@ -290,6 +294,8 @@ class Trainer(object):
             self.loss_acc += loss
         works = []
         reduce_now = last and self.world > 1 and self.shard is None   # sharded step: the sum is taken in apply()
+        if last and self.shard is not None and self.shard.split:
+            self._shard_early()
         buckets = eng.encoder_buckets(self.enc_groups)
         if reduce_now:
             works.append(dist.all_reduce(ps.grad[ps.dec_offset:], op=dist.ReduceOp.SUM, async_op=True))
@@ -312,6 +318,26 @@ class Trainer(object):
         self._micro = 0 if last else self._micro + 1
         self._pending = last
         return loss
+
+    def _step_scalars(self):
+        """(lr_t, gscale) of the update that completes this cycle (utils/cycle.py:94-105; TF Adam's bias-corrected rate)."""
+        t = self.global_step + 1
+        lr_t = self.lr() * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        return lr_t, 1.0 / (self.world * self.cycle * self.loss_scale)
+
+    def _shard_early(self):
+        """Decoder-side region of the fused step on a second stream, under the encoder backward (shard_opt.step_early)."""
+        self._early = self._step_scalars()
+        if self.eng.device.type != "cuda":           # host-only tests: no streams
+            self.shard.step_early(self, *self._early)
+            return
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(device=self.eng.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._opt_stream):
+            self._opt_stream.wait_event(ev)
+            self.shard.step_early(self, *self._early)
 
     def cycle_ready(self):
         return bool(self._pending)
@@ -341,11 +367,12 @@ class Trainer(object):
         ps = self.eng.ps
         self._pending = False
         if self.shard is not None:
-            lr = self.lr()
+            lr_t, gscale = self._early if self._early is not None else self._step_scalars()
+            if self._early is not None and self._opt_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._opt_stream)
+            self._early = None
             self.global_step += 1
-            t = self.global_step
-            lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
-            self.shard.step(self, lr_t, 1.0 / (self.world * self.cycle * self.loss_scale))
+            self.shard.step(self, lr_t, gscale)
             self._ema_update()
             return
         # tf.global_norm of gradients and parameters (utils/cycle.py:94-95): a separate pass only when the clip
@@ -383,9 +410,9 @@ class Trainer(object):
             # tf.train.ExponentialMovingAverage(decay, num_updates=global_step): decay' = min(decay, (1+n)/(10+n))
             n = float(self.global_step)
             d = min(self.ema_decay, (1.0 + n) / (10.0 + n))
-            if self.shard is not None:   # only the own shard of the master is current
-                lo, hi = self.shard.lo, self.shard.lo + self.shard.n
-                self.ema[lo:hi].lerp_(self.eng.ps.master[lo:hi], 1.0 - d)
+            if self.shard is not None:   # only the own shards of the master are current
+                for lo, n in self.shard.ranges:
+                    self.ema[lo:lo + n].lerp_(self.eng.ps.master[lo:lo + n], 1.0 - d)
             else:
                 self.ema.lerp_(self.eng.ps.master, 1.0 - d)
 
