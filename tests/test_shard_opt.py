@@ -219,6 +219,7 @@ def test_wide_mask_marks_exactly_the_fp32_read_variables(host_only):
 @pytest.mark.parametrize("world_size,clip", [(2, 0.0), (3, 0.0), (3, 0.05), (4, 1e9)])
 def test_sharded_step_equals_replicated_adam_on_the_mean_gradient(world_size, clip, monkeypatch, host_only):
     hp = _hp(clip_grad_norm=clip, ema_decay=0.9)
+    monkeypatch.setenv("ZB_SHARD_OVERLAP", "1")     # the two-region plan wherever clipping allows it
     world, engines, trainers = _setup(world_size, monkeypatch, hp)
     total = engines[0].ps.total
     assert (trainers[0].clip is None) == (clip == 0.0)

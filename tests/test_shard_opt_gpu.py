@@ -122,10 +122,10 @@ def _worker(rank, world, port, mode, out_dir):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    if mode == "allreduce":
-        os.environ.pop("ZB_SHARD_OPT", None)
-    else:
-        os.environ["ZB_SHARD_OPT"] = mode
+    # "allreduce": bucketed NCCL all-reduce + replicated Adam; "1" / "p2p": the fused step over the multicast / unicast
+    # mappings in two regions (decoder side under the encoder backward); "p2p-flat": one region after the backward
+    os.environ["ZB_SHARD_OPT"] = "0" if mode == "allreduce" else mode.split("-")[0]
+    os.environ["ZB_SHARD_OVERLAP"] = "0" if mode.endswith("-flat") else "1"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from tests.golden_util import load_golden
@@ -138,6 +138,8 @@ def _worker(rank, world, port, mode, out_dir):
     eng.ps.load_state_dict(variables)
     tr = Trainer(eng, hp, world_size=world, use_graph=False)
     assert (tr.shard is not None) == (mode != "allreduce")
+    if tr.shard is not None:
+        assert (tr.shard.split is not None) == (not mode.endswith("-flat"))
     src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
     if rank == 1:                                   # a different batch per tower (main.py:268-273)
         src, tgt = torch.flip(src, [0]), torch.flip(tgt, [0])
@@ -158,11 +160,11 @@ def _worker(rank, world, port, mode, out_dir):
 def test_two_rank_training_fused_step_equals_allreduce_path(tmp_path):
     import torch.multiprocessing as mp
     out = str(tmp_path)
-    for mode in ("allreduce", "1", "p2p"):
+    for mode in ("allreduce", "1", "p2p", "p2p-flat"):
         mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
     ref = [torch.load(os.path.join(out, "allreduce_%d.pt" % r)) for r in range(2)]
     assert torch.equal(ref[0]["master"], ref[1]["master"])
-    for mode in ("1", "p2p"):
+    for mode in ("1", "p2p", "p2p-flat"):
         got = [torch.load(os.path.join(out, "%s_%d.pt" % (mode, r))) for r in range(2)]
         assert torch.equal(got[0]["master"], got[1]["master"]) and torch.equal(got[0]["mirror"], got[1]["mirror"])
         assert torch.equal(got[0]["mirror"], got[0]["master"].to(bf16))
@@ -174,4 +176,4 @@ def test_two_rank_training_fused_step_equals_allreduce_path(tmp_path):
         # same arithmetic up to the summation order of two addends (exact) and bf16 forward noise between runs
         d = (got[0]["master"] - ref[0]["master"]).abs().max()
         assert float(d) < 5e-2, float(d)
-        assert (mode == "p2p" and got[0]["mc"] is False) or mode == "1"
+        assert (mode.startswith("p2p") and got[0]["mc"] is False) or mode == "1"

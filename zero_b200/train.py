@@ -92,8 +92,11 @@ class Trainer(object):
         mode = os.environ.get("ZB_SHARD_OPT", "auto")
         if mode == "auto":
             mode = "0" if self.world <= 1 else ("p2p" if self.world == 2 else "1")
-        # two regions (decoder side first, under the encoder backward) unless clipping needs the global norm first
-        self._shard_split = engine.ps.dec_offset if (self.clip is None and os.environ.get("ZB_SHARD_OVERLAP", "1") != "0"
+        # ZB_SHARD_OVERLAP=1 (opt-in): two regions, the decoder side reduced / updated on a second stream UNDER the encoder
+        # backward.  Validated (tests/test_shard_opt_gpu.py) and measured SLOWER than the flat step — 3.93 vs 3.85 ms/step
+        # at N = 2, 4.30 vs 4.20 at N = 8 (profiles/r02_scaling_ab.log): the concurrent kernel costs the backward's GEMMs
+        # more than the communication it hides, the same outcome as overlapping Adam (ZB_EARLY_ADAM) in round 1.
+        self._shard_split = engine.ps.dec_offset if (self.clip is None and os.environ.get("ZB_SHARD_OVERLAP", "0") == "1"
                                                      and 0 < engine.ps.dec_offset < engine.ps.total) else None
         self._early = None
         if shard_transport is not None:
