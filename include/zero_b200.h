@@ -170,6 +170,10 @@ typedef struct {
   void* ds; float* dscale; float* doffset;
   float* dbias; /* optional fp32 [cols], accumulated: column sums of ds = the bias gradient of the linear layer
                    that produced y (tf.nn.bias_add grad, func.py:59) */
+  /* forward only, optional: the branch output as an fp32 split-K accumulator [rows, cols] (+ its bias [cols], added
+     here because a split-K GEMM cannot): s = x + y32 + ybias (y must be NULL).  The kernel writes zeros back into y32,
+     so the next projection of the decode step accumulates into a clean buffer without a memset. */
+  float* y32; const float* ybias;
 } zb_add_ln_args;
 int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream);
 int zb_add_ln_bwd(const zb_add_ln_args* a, zb_stream_t stream);

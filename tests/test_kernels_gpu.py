@@ -285,6 +285,29 @@ def test_vocab_ce_fused_matches_gemm_plus_softmax_ce(B, T, V, d, smooth):
     torch.testing.assert_close(nll2, zo.smoothed_ce(lg.detach(), labels.reshape(-1), 0.0), atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("rows,k,n", [(256, 2048, 512), (256, 512, 512), (37, 1024, 512), (8, 256, 128)])
+def test_decode_split_k_projection_into_add_ln(rows, k, n):
+    """The decode step's out = LN(res + inp @ W + b) with the k dimension split over CTAs (fp32 partial tiles reduce-added
+    into one accumulator, consumed and CLEARED by zb_add_ln_fwd's y32 path) against the unsplit projection + bf16 y."""
+    from zero_b200 import ops
+    import zero_b200.lib as L
+    inp, w, b = rnd(rows, k, seed=91), rnd(k, n, scale=k ** -0.5, seed=92), rnd(n, seed=93).float()
+    res = rnd(rows, n, seed=94)
+    scale, offset = (1 + 0.1 * rnd(n, seed=95).float()), 0.1 * rnd(n, seed=96).float()
+    y = torch.empty(rows, n, dtype=bf16, device=dev())
+    ops.linear_fwd(inp, w, b, y)
+    want = torch.empty(rows, n, dtype=bf16, device=dev())
+    ops.add_ln_fwd(res, y, want, scale, offset, eps=1e-8)
+    y32 = torch.zeros(rows, n, device=dev())
+    for _ in range(2):            # twice: the second pass relies on the accumulator having been cleared
+        got = torch.empty(rows, n, dtype=bf16, device=dev())
+        ops.gemm(inp, w, y32, L.ZB_K_MAJOR, L.ZB_MN_MAJOR, accum=True, split_k=max(2, min(8, k // 128)))
+        ops.add_ln_fwd(res, None, got, scale, offset, eps=1e-8, y32=y32, ybias=b)
+        assert float(y32.abs().max()) == 0.0
+        torch.testing.assert_close(got.float(), want.float(), atol=3e-2, rtol=2e-2)
+        assert float((got.float() - want.float()).abs().mean()) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, heads, key_len, causal, q_off, inf, ek, ev, max_rel, relu):
     from oracle import zero_oracle as zo

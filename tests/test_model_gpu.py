@@ -236,7 +236,7 @@ def test_full_size_properties_c5_deep_encoder_len1024():
     torch.testing.assert_close(ps[:4].clone(), ps[4:].clone(), atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("switch", ["ZB_DECODE_FUSED_SMALL", "ZB_BEAM_PARTS", "ZB_GEMM_BM64"])
+@pytest.mark.parametrize("switch", ["ZB_DECODE_FUSED_SMALL", "ZB_BEAM_PARTS", "ZB_GEMM_BM64", "ZB_DECODE_SPLITK"])
 def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     """transformer_aan golden model: beam search with an opt-in decode-path switch returns the same sequences as
     the default path (and as the reference-executed golden beams checked in test_cached_decode_and_beam_search)."""

@@ -37,6 +37,79 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Decode-step variant: the branch output arrives as the fp32 accumulator of a split-K projection (+ the projection's
+// bias, which a split-K GEMM cannot add): s = x + y32 + ybias.  The accumulator is cleared on the way (zeros written
+// back), so the next split-K projection of the step finds a clean buffer without a memset in between.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32, NV <= 2 ? 6 : 2)
+add_ln_fwd_acc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y32, const float* __restrict__ ybias,
+                      __nv_bfloat16* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
+                      const float* __restrict__ scale, const float* __restrict__ offset, long long rows, int cols,
+                      float eps) {
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = cols >> 3;
+  for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows; row += (long long)gridDim.x * kLnWarps) {
+    float s[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        load8(x + row * cols + v * 8, s[i]);
+        float4* yp = reinterpret_cast<float4*>(y32 + row * cols + v * 8);
+        const float4 y0 = yp[0], y1 = yp[1];
+        yp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b0 = ybias ? __ldg(reinterpret_cast<const float4*>(ybias + v * 8)) : make_float4(0.f, 0.f, 0.f, 0.f),
+                     b1 = ybias ? __ldg(reinterpret_cast<const float4*>(ybias + v * 8) + 1)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        // the projection's output is bf16 in the unsplit path (GEMM epilogue): round the same way, so both paths agree
+        const float t[8] = {y0.x + b0.x, y0.y + b0.y, y0.z + b0.z, y0.w + b0.w,
+                            y1.x + b1.x, y1.y + b1.y, y1.z + b1.z, y1.w + b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[i][e] += __bfloat162float(__float2bfloat16(t[e]));
+          sum += s[i][e];
+        }
+      }
+    }
+    const float mu = warp_sum(sum) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = s[i][e] - mu;
+          sq += d * d;
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(sq) / cols + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float o[8];
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + v * 8)),
+                     sc1 = __ldg(reinterpret_cast<const float4*>(scale + v * 8) + 1),
+                     of0 = __ldg(reinterpret_cast<const float4*>(offset + v * 8)),
+                     of1 = __ldg(reinterpret_cast<const float4*>(offset + v * 8) + 1);
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float of[8] = {of0.x, of0.y, of0.z, of0.w, of1.x, of1.y, of1.z, of1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = sc[e] * (s[i][e] - mu) * rs + of[e];
+        store8(out + row * cols + v * 8, o);
+      }
+    }
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32, NV <= 2 ? 6 : 2)
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
@@ -501,6 +574,17 @@ extern "C" int zb_add_ln_fwd(const zb_add_ln_args* a, zb_stream_t stream) {
   long long blocks = (a->rows + kLnWarps - 1) / kLnWarps;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
+  if (a->y32) {
+    ZB_REQUIRE(!a->y && (reinterpret_cast<uintptr_t>(a->y32) & 15) == 0 &&
+                   (!a->ybias || (reinterpret_cast<uintptr_t>(a->ybias) & 15) == 0),
+               "zb_add_ln_fwd: y32 excludes y and needs 16-byte aligned y32 / ybias");
+#define CALLA(N)                                                                                             \
+  ZB_LAUNCH(add_ln_fwd_acc_kernel<N>, (int)blocks, kLnWarps * 32, 0, st, (const __nv_bfloat16*)a->x, a->y32, \
+            a->ybias, (__nv_bfloat16*)a->out, a->mean, a->rstd, a->scale, a->offset, a->rows, (int)a->cols, a->eps)
+    ZB_LN_DISPATCH(nv, CALLA);
+#undef CALLA
+    return check_launch("zb_add_ln_fwd(fp32 accumulator)");
+  }
 #define CALL(N)                                                                                              \
   ZB_LAUNCH(add_ln_fwd_kernel<N>, (int)blocks, kLnWarps * 32, 0, st,                                                \
       (const __nv_bfloat16*)a->x, (const __nv_bfloat16*)a->y, (__nv_bfloat16*)a->out, a->mean, a->rstd, a->scale, \

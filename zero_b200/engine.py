@@ -1016,10 +1016,8 @@ def _engine_decoding_fn(self, target, state, time):
                                relu_attn=c.rela)
         ops.attention_fwd(a)
         ctx = self._post_attn(key + ".self", ctx, R)
-        y = ws.get("dec.y", (R, c.d))
-        ops.linear_fwd(ctx, ps.w(key + ".self.o.W"), ps.p(key + ".self.o.b"), y)
         x1 = ws.get("dec.x1", (R, c.d))
-        ops.add_ln_fwd(x, y, x1, ps.p(key + ".self.ln.scale"), ps.p(key + ".self.ln.offset"), eps=c.eps)
+        self._decode_proj_ln(ctx, key + ".self.o", x, x1, key + ".self.ln", R)
         q = ws.get("dec.q", (R, c.d))
         ops.linear_fwd(x1, ps.w(key + ".cross.q.W"), ps.p(key + ".cross.q.b"), q)
         mem = state.mem[l]
@@ -1030,16 +1028,41 @@ def _engine_decoding_fn(self, target, state, time):
                                relu_attn=c.rela)
         ops.attention_fwd(a)
         ctx = self._post_attn(key + ".cross", ctx, R)
-        ops.linear_fwd(ctx, ps.w(key + ".cross.o.W"), ps.p(key + ".cross.o.b"), y)
         xc = ws.get("dec.xc", (R, c.d))
-        ops.add_ln_fwd(x1, y, xc, ps.p(key + ".cross.ln.scale"), ps.p(key + ".cross.ln.offset"), eps=c.eps)
+        self._decode_proj_ln(ctx, key + ".cross.o", x1, xc, key + ".cross.ln", R)
         h = ws.get("dec.h", (R, c.f))
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
-        ops.linear_fwd(h, ps.w(key + ".ffn.w2.W"), ps.p(key + ".ffn.w2.b"), y)
-        ops.add_ln_fwd(xc, y, x, ps.p(key + ".ffn.ln.scale"), ps.p(key + ".ffn.ln.offset"), eps=c.eps)
+        self._decode_proj_ln(h, key + ".ffn.w2", xc, x, key + ".ffn.ln", R)
     logits = self._vocab_rows("dec.logits", R, f32)
     ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
     return self._dense_logits(logits), state
+
+
+def _engine_decode_proj_ln(self, inp, lin, res, out, ln, rows):
+    """out = LayerNorm(res + inp @ W + b) of a decode step (func.linear + residual_fn + layer_norm on [rows, .] with
+    rows = batch * beam).  A 256-row projection makes only rows / 128 x n / 64 output tiles — 16 CTAs for n = 512, each
+    walking the whole k dimension at the SM's L2 ingest rate (0.26 us per 64-k block: 8.6 us for the k = 2048 FFN
+    output projection, profiles/r02t_decode_gemm_trace.log) — so the k dimension is split over ~8x as many CTAs, which
+    add their fp32 partial tiles into one accumulator by TMA reduce-add; the residual + LayerNorm kernel that consumes
+    it adds the bias, rounds like the unsplit epilogue does, and clears the accumulator for the next projection.
+    MEASURED (configs[2], profiles/r02u_decode_splitk_ab.log): 0.548-0.554 ms/step against 0.542-0.543 for the unsplit
+    projection + bf16 round trip — the reduce-adds and the fp32 traffic cost what the shorter k loops save — so the
+    split is opt-in (ZB_DECODE_SPLITK=1); parity-tested either way."""
+    c, ps, ws = self.cfg, self.ps, self.ws
+    w, b = ps.w(lin + ".W"), ps.p(lin + ".b")
+    k, n = w.shape
+    kb = (k + 63) // 64
+    tiles = ((rows + 127) // 128) * ((n + 63) // 64)
+    splits = min(kb // 2, max(1, 148 // tiles))
+    if rows > 512 or splits < 2 or os.environ.get("ZB_DECODE_SPLITK", "0") != "1":
+        y = ws.get("dec.y", (rows, n))
+        ops.linear_fwd(inp, w, b, y)
+        ops.add_ln_fwd(res, y, out, ps.p(ln + ".scale"), ps.p(ln + ".offset"), eps=c.eps)
+        return out
+    y32 = ws.get("dec.y32", (rows, n), f32, zero=True)    # zero when allocated; kept clean by its consumer
+    ops.gemm(inp, w, y32, L.ZB_K_MAJOR, L.ZB_MN_MAJOR, accum=True, split_k=splits)
+    ops.add_ln_fwd(res, None, out, ps.p(ln + ".scale"), ps.p(ln + ".offset"), eps=c.eps, y32=y32, ybias=b)
+    return out
 
 
 def _engine_post_attn(self, key, ctx, rows):
@@ -1055,5 +1078,6 @@ def _engine_post_attn(self, key, ctx, rows):
 Engine.encoding_fn = _engine_encoding_fn
 Engine.decoding_fn = _engine_decoding_fn
 Engine._post_attn = _engine_post_attn
+Engine._decode_proj_ln = _engine_decode_proj_ln
 
 from . import engine_avg  # noqa: E402,F401  (registers the average-attention family on Engine / DecodeState)

@@ -238,13 +238,11 @@ def _decoding_fn_avg(self, target, state, time):
             av = ws.get("dec.av", (R, c.d))
             ops.aan_step(vq, state.sums[l], av, t)
             ops.add2d(ctx, av, ctx)
-        ops.linear_fwd(ctx, ps.w(kc + ".o.W"), ps.p(kc + ".o.b"), y)
         xc = ws.get("dec.xc", (R, c.d))
-        ops.add_ln_fwd(x1, y, xc, ps.p(kc + ".ln.scale"), ps.p(kc + ".ln.offset"), eps=c.eps)
+        self._decode_proj_ln(ctx, kc + ".o", x1, xc, kc + ".ln", R)
         h = ws.get("dec.h", (R, c.f))
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
-        ops.linear_fwd(h, ps.w(key + ".ffn.w2.W"), ps.p(key + ".ffn.w2.b"), y)
-        ops.add_ln_fwd(xc, y, x, ps.p(key + ".ffn.ln.scale"), ps.p(key + ".ffn.ln.offset"), eps=c.eps)
+        self._decode_proj_ln(h, key + ".ffn.w2", xc, x, key + ".ffn.ln", R)
     logits = self._vocab_rows("dec.logits", R, f32)
     ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
     return self._dense_logits(logits), state

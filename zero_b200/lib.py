@@ -48,7 +48,8 @@ class AttentionArgs(C.Structure):
 class AddLnArgs(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("out", vp), ("mean", vp), ("rstd", vp), ("scale", vp), ("offset", vp),
                 ("rows", i64), ("cols", i64), ("eps", f32),
-                ("d_out", vp), ("d_out2", vp), ("ds", vp), ("dscale", vp), ("doffset", vp), ("dbias", vp)]
+                ("d_out", vp), ("d_out2", vp), ("ds", vp), ("dscale", vp), ("doffset", vp), ("dbias", vp),
+                ("y32", vp), ("ybias", vp)]
 
 
 class EmbedArgs(C.Structure):

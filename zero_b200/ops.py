@@ -169,10 +169,12 @@ def attention_bwd(a, d_o, dq, dk, dv, delta, d_rpr_k=None, d_rpr_v=None, workspa
     L.check(L.load().zb_attention_bwd(C.byref(a), _stream()), "zb_attention_bwd")
 
 
-def add_ln_fwd(x, y, out, scale, offset, mean=None, rstd=None, eps=1e-8):
-    """func.residual_fn + func.layer_norm (func.py:321-324, 289-303)."""
+def add_ln_fwd(x, y, out, scale, offset, mean=None, rstd=None, eps=1e-8, y32=None, ybias=None):
+    """func.residual_fn + func.layer_norm (func.py:321-324, 289-303).  y32 / ybias: the branch output as the fp32
+    accumulator of a split-K projection plus that projection's bias (cleared by the kernel after it is read)."""
     a = L.AddLnArgs()
     a.x, a.y, a.out, a.mean, a.rstd = _p(x), _p(y), _p(out), _p(mean), _p(rstd)
+    a.y32, a.ybias = _p(y32), _p(ybias)
     a.scale, a.offset = _p(scale), _p(offset)
     a.rows, a.cols, a.eps = x.numel() // x.shape[-1], x.shape[-1], float(eps)
     L.check(L.load().zb_add_ln_fwd(C.byref(a), _stream()), "zb_add_ln_fwd")
