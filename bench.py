@@ -344,6 +344,85 @@ def layer_peak_leg(peaks, iters=5):
     return out
 
 
+def variable_shape_leg(steps=60):
+    """The reference's REAL usage (main.py:242-312): length-sorted, token-budget batches from the data pipeline — a new
+    (B, S, T) almost every step — through the same public step with HOST (pinned) batches.  CUDA graphs are replayed
+    per shape class (S / T zero-padded to multiples of 8, ZB_GRAPH_BUCKET) over the shared workspace; reports tokens/s
+    once every class of the corpus has been captured (second epoch), the number of classes and the eager rate (no
+    graphs) for comparison."""
+    import numpy as np
+    import torch
+    from zero_b200.data import pin
+    from zero_b200.engine import Engine
+    from zero_b200.params import transformer_base
+    from zero_b200.train import Trainer
+    rng = np.random.default_rng(7)
+    src, tgt = [], []
+    for _ in range(6000):             # only the lengths matter here; ids are drawn when the matrices are built
+        src.append([0] * int(rng.integers(8, 64)))
+        tgt.append([0] * int(rng.integers(8, 64)))
+    out = {}
+    for mode in ("graphs", "eager"):
+        os.environ["ZB_GRAPH_BUCKET"] = "8" if mode == "graphs" else "0"
+        hp = transformer_base()
+        eng = Engine(hp, VOCAB, VOCAB, device="cuda")
+        eng.ps.init_random(1234)
+        trainer = Trainer(eng, hp, world_size=1, use_graph=(mode == "graphs"))
+        g = np.random.default_rng(3)
+        batches = []
+        # token-budget batches of ~4096 target tokens from length-sorted buckets (utils/util.py:30-65)
+        order = np.argsort([max(len(a), len(b)) for a, b in zip(src, tgt)], kind="stable")
+        cur, width = [], 0
+        for i in order:
+            w = max(len(src[i]), len(tgt[i])) + 1
+            if cur and (len(cur) + 1) * max(width, w) > 4096:
+                batches.append(cur)
+                cur, width = [], 0
+            cur.append(i)
+            width = max(width, w)
+        if cur:
+            batches.append(cur)
+        g.shuffle(batches)
+
+        def matrix(idx, corpus):
+            width = max(len(corpus[i]) for i in idx) + 1
+            m = np.zeros((len(idx), width), dtype=np.int32)
+            for r, i in enumerate(idx):
+                ids = g.integers(3, VOCAB, len(corpus[i]))
+                m[r, :len(ids)] = ids
+                m[r, len(ids)] = 2
+            return m
+        host = [pin({"src": matrix(b, src), "tgt": matrix(b, tgt)}) for b in batches]
+        for s, t in host:                      # epoch 1: allocate the workspace, capture every shape class
+            trainer.step(s, t)
+        torch.cuda.synchronize()
+        if mode == "graphs":
+            for s, t in host:
+                trainer.step(s, t)
+            torch.cuda.synchronize()
+        n = min(steps, len(host))
+        toks = sum(int((t != 0).sum()) for _, t in host[:n])
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s, t in host[:n]:
+            loss = trainer.step(s, t)
+        _ = loss.item()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[mode] = {"value": toks / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / n, "steps": n,
+                     "host_wall_ms_per_step": 1000 * (time.perf_counter() - t0) / n,
+                     "mean_target_tokens_per_step": toks / n, "distinct_batches": len(host),
+                     "captured_shape_classes": len(trainer._graphs) if mode == "graphs" else 0}
+        del trainer, eng
+        torch.cuda.empty_cache()
+    os.environ.pop("ZB_GRAPH_BUCKET", None)
+    out["workload"] = ("6000 synthetic pairs, lengths ~U[8,64), length-sorted token-budget batches of <= 4096 padded "
+                       "target tokens (main.py:242-312), pinned host ids in, configs[1] model")
+    return out
+
+
 def extra_legs(peaks):
     """BASELINE configs[3] and [4] as training-throughput legs + the encoder-layer peak shape (N = 1 only)."""
     from zero_b200.params import transformer_base
@@ -359,6 +438,10 @@ def extra_legs(peaks):
             "per GPU per step (BASELINE configs[3])", hp, 32, 128, 128, 20, peaks, rpr_k=16)
     except Exception as e:
         legs["configs3_rpr_len128"] = {"error": repr(e)[:300]}
+    try:
+        legs["variable_shape_token_batches"] = variable_shape_leg()
+    except Exception as e:
+        legs["variable_shape_token_batches"] = {"error": repr(e)[:300]}
     try:
         hp = transformer_base(num_encoder_layer=24, num_decoder_layer=6, deep_transformer_init=True,
                               initializer="uniform_unit_scaling", initializer_gain=1.0)

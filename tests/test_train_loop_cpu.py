@@ -320,3 +320,15 @@ def test_data_parallel_buckets_cover_the_gradient_arena_exactly_once(tmp_path, h
         assert events.index(adams[0]) < i_late_wait < events.index(adams[1])      # the embedding bucket hides under Adam
     else:
         assert [(a[1], a[2]) for a in adams] == [(0, eng.ps.total)]
+
+
+def test_default_dtype_names_follow_the_reference_and_unknown_ones_are_rejected(tmp_path, host_only):
+    """utils/dtype.py:42 accepts float16 / float32 / float64 names and raises on anything else; this path has one
+    numerics contract (bf16 compute, fp32 accumulation / master weights): the reference's names are accepted with a
+    notice, anything else is an error instead of being silently ignored."""
+    import zero_b200.engine as E
+    from zero_b200.lib import ZeroB200Error
+    for ok in ("float32", "float16", "bfloat16"):
+        E.Engine(_params(tmp_path, default_dtype=ok), device="cpu")
+    with pytest.raises(ZeroB200Error):
+        E.Engine(_params(tmp_path, default_dtype="int8"), device="cpu")

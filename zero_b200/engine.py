@@ -13,6 +13,7 @@ is projected by one GEMM; their TF names are strided views into the fused tensor
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 import zlib
@@ -372,6 +373,12 @@ def compact_columns(ids):
 
 # ------------------------------------------------------------------------------------------------ engine
 class Engine(object):
+    _dtype_notice = False
+
+    def _range(self, name):
+        """NVTX range around a sublayer (ZB_NVTX=1), else a no-op context."""
+        return torch.cuda.nvtx.range(name) if self._nvtx else contextlib.nullcontext()
+
     def __init__(self, hp, src_vocab=None, tgt_vocab=None, device="cuda"):
         if not torch.cuda.is_available():
             raise L.ZeroB200Error("zero_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -392,6 +399,19 @@ class Engine(object):
             if not 0.0 <= r < 1.0:
                 raise L.ZeroB200Error("%s dropout rate %r outside [0, 1)" % (k, r))
         self._training = False
+        # compute dtype (utils/dtype.py:12-44, run.py:397-399).  The reference computes in float32 by default and in
+        # float16 with fp32 master variables on request; this path has ONE numerics contract — bf16 operands, fp32
+        # accumulation, fp32 master weights / optimizer state / logits statistics — whatever `default_dtype` says
+        # (north_star: outputs within 1e-2 of the reference's fp32 path).  Unknown names are rejected like set_floatx.
+        dt = str(_hp(hp, "default_dtype", "float32") or "float32")
+        if dt not in ("float32", "float16", "bfloat16"):
+            raise L.ZeroB200Error("default_dtype %r: expected float32, float16 or bfloat16 (utils/dtype.py:42)" % dt)
+        if dt != "bfloat16" and not Engine._dtype_notice:
+            Engine._dtype_notice = True
+            print("zero_b200: default_dtype=%s requested; the sm_100a path computes in bfloat16 with fp32 accumulation "
+                  "and fp32 master weights (there is no fp32 / fp16 kernel set)" % dt, flush=True)
+        # ZB_NVTX=1: one NVTX range per sublayer and direction (nsys / ncu --nvtx filtering); off: no overhead
+        self._nvtx = os.environ.get("ZB_NVTX") == "1"
         seed0 = (int(_hp(hp, "random_seed", 1234)) * 0x9E3779B97F4A7C15 + 0x1234567) % (1 << 62)
         self.drop_seed = torch.tensor([seed0], dtype=torch.int64, device=self.device)
 
@@ -659,10 +679,12 @@ class Engine(object):
         for l in range(c.nenc):
             key, t = "enc%d" % l, "%s.L%d" % (tag, l)
             sv = {"att": {}, "ln1": {}, "ffn": {}, "ln2": {}, "x_in": x}
-            y = self._self_attn_fwd(key + ".self", x, B, S, src_len, False, sv["att"], t + ".att")
-            x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
-            y2 = self._ffn_fwd(key + ".ffn", x1, N, sv["ffn"], t + ".ffn")
-            x = self._ln_fwd(key + ".ffn.ln", x1, y2, N, sv["ln2"], t + ".ln2")
+            with self._range(key + ".self_attention.fwd"):
+                y = self._self_attn_fwd(key + ".self", x, B, S, src_len, False, sv["att"], t + ".att")
+                x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
+            with self._range(key + ".feed_forward.fwd"):
+                y2 = self._ffn_fwd(key + ".ffn", x1, N, sv["ffn"], t + ".ffn")
+                x = self._ln_fwd(key + ".ffn.ln", x1, y2, N, sv["ln2"], t + ".ln2")
             sv["x1"] = x1
             layers.append(sv)
         if save is not None:
@@ -682,10 +704,12 @@ class Engine(object):
             key, bw = "enc%d" % l, "%s.bw%d" % (tag, l & 1)   # backward temporaries: two sets, by layer parity
             sv = save["layers"][l]
             self._side_layer_begin(tag, l)
-            ds2, dy2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
-            dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], dy2, N, sv["ffn"], bw + ".ffn")
-            ds1, dy1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
-            dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, S, sv["att"], bw + ".att")
+            with self._range(key + ".feed_forward.bwd"):
+                ds2, dy2 = self._ln_bwd(key + ".ffn.ln", d1, d2, N, sv["ln2"], bw + ".ln2", ps.g(key + ".ffn.w2.b"))
+                dx1 = self._ffn_bwd(key + ".ffn", sv["x1"], dy2, N, sv["ffn"], bw + ".ffn")
+            with self._range(key + ".self_attention.bwd"):
+                ds1, dy1 = self._ln_bwd(key + ".self.ln", ds2, dx1, N, sv["ln1"], bw + ".ln1", ps.g(key + ".self.o.b"))
+                dx = self._self_attn_bwd(key + ".self", sv["x_in"], dy1, B, S, sv["att"], bw + ".att")
             self._side_layer_end(tag, l)
             d1, d2 = ds1, dx
         if stop_layer > 0:
@@ -760,17 +784,21 @@ class Engine(object):
             key, t = "dec%d" % l, "%s.L%d" % (tag, l)
             sv = {"att": {}, "ln1": {}, "cross": {}, "lnc": {}, "ffn": {}, "ln2": {}, "x_in": x}
             # decoder self-attention: causal bias only, no key-padding mask (models/transformer.py:136)
-            y = self._self_attn_fwd(key + ".self", x, B, T, None, True, sv["att"], t + ".att")
-            x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
-            yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross",
-                                      kv=None if kv_all is None else kv_all[:, l * 2 * c.d:(l + 1) * 2 * c.d])
-            xc = self._ln_fwd(key + ".cross.ln", x1, yc, N, sv["lnc"], t + ".lnc")
-            y2 = self._ffn_fwd(key + ".ffn", xc, N, sv["ffn"], t + ".ffn")
-            x = self._ln_fwd(key + ".ffn.ln", xc, y2, N, sv["ln2"], t + ".ln2")
+            with self._range(key + ".self_attention.fwd"):
+                y = self._self_attn_fwd(key + ".self", x, B, T, None, True, sv["att"], t + ".att")
+                x1 = self._ln_fwd(key + ".self.ln", x, y, N, sv["ln1"], t + ".ln1")
+            with self._range(key + ".cross_attention.fwd"):
+                yc = self._cross_attn_fwd(key + ".cross", x1, enc, B, T, S, src_len, sv["cross"], t + ".cross",
+                                          kv=None if kv_all is None else kv_all[:, l * 2 * c.d:(l + 1) * 2 * c.d])
+                xc = self._ln_fwd(key + ".cross.ln", x1, yc, N, sv["lnc"], t + ".lnc")
+            with self._range(key + ".feed_forward.fwd"):
+                y2 = self._ffn_fwd(key + ".ffn", xc, N, sv["ffn"], t + ".ffn")
+                x = self._ln_fwd(key + ".ffn.ln", xc, y2, N, sv["ln2"], t + ".ln2")
             sv.update(x1=x1, xc=xc)
             layers.append(sv)
         feat = x
-        loss, per_sample, logits, dlogits = self._vocab_loss(feat, target, smooth, want_grad, want_logits, tag)
+        with self._range("vocab_projection_ce"):
+            loss, per_sample, logits, dlogits = self._vocab_loss(feat, target, smooth, want_grad, want_logits, tag)
         if save is not None:
             save.update(layers=layers, target=target, B=B, T=T, S=S, feat=feat, dlogits=dlogits, enc=enc,
                         emb_rate=r_emb)
