@@ -408,8 +408,9 @@ class Engine(object):
             raise L.ZeroB200Error("default_dtype %r: expected float32, float16 or bfloat16 (utils/dtype.py:42)" % dt)
         if dt != "bfloat16" and not Engine._dtype_notice:
             Engine._dtype_notice = True
+            import sys
             print("zero_b200: default_dtype=%s requested; the sm_100a path computes in bfloat16 with fp32 accumulation "
-                  "and fp32 master weights (there is no fp32 / fp16 kernel set)" % dt, flush=True)
+                  "and fp32 master weights (there is no fp32 / fp16 kernel set)" % dt, file=sys.stderr, flush=True)
         # ZB_NVTX=1: one NVTX range per sublayer and direction (nsys / ncu --nvtx filtering); off: no overhead
         self._nvtx = os.environ.get("ZB_NVTX") == "1"
         seed0 = (int(_hp(hp, "random_seed", 1234)) * 0x9E3779B97F4A7C15 + 0x1234567) % (1 << 62)
