@@ -2,6 +2,8 @@
 reference's own code, and against the CPU oracle.  Tolerances: the build computes in bf16 with fp32
 accumulation, so logits are held to the north-star's bf16 bound (1e-2, relative to the logit scale);
 beam-search indices are bit-exact when both sides consume the same logits."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -143,6 +145,55 @@ def test_graph_replayed_decode_equals_eager(name):
     hp.decode_graph = False
     b = search.beam_search({"source": src2}, eng.encoding_fn, eng.decoding_fn, hp)
     np.testing.assert_array_equal(a["seq"].cpu().numpy(), b["seq"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["transformer", "transformer_len40", "transformer_rpr", "transformer_aan",
+                                  "transformer_aan_cumsum", "transformer_fuse", "transformer_rela"])
+def test_search_mode_dev_matches_the_cached_search(name):
+    """The reference's self-check (search.py:129-140, models/transformer.py:272-281): decoding with
+    search_mode = "dev" — the whole decoder re-run, teacher-forced, on the partial target at every step, no caches —
+    must give the cached search's step logits (within the bf16 bound; the two paths run different kernels: the training
+    attention / prefix-mean kernels against the lq = 1 / running-sum ones) and, ties aside, its beams."""
+    from zero_b200 import search
+    from zero_b200.models import model as registry
+    from zero_b200.models import transformer as plugins
+    from zero_b200.params import SimpleVocab
+    eng, z, hp, variables, grads = _engine(name)
+    hp.add_hparam("src_vocab", SimpleVocab(eng.cfg.vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(eng.cfg.vt))
+    hp.add_hparam("decode_graph", False)
+    eng.decode_length = hp.decode_length
+    src = torch.from_numpy(z["source"])
+    rec = {"cache": [], "dev": []}
+
+    def wrap(fn, store):
+        def inner(tok, state, t):
+            lg, st = fn(tok, state, t)
+            store.append(lg.detach().float().cpu().clone())
+            return lg, st
+        return inner
+
+    hp.search_mode = "cache"
+    a = search.beam_search({"source": src}, eng.encoding_fn, wrap(eng.decoding_fn, rec["cache"]), hp)
+    hp.search_mode = "dev"
+    b = search.beam_search({"source": src}, eng.encoding_fn, wrap(eng.decoding_fn_dev, rec["dev"]), hp)
+    # step 0 and 1: same prefixes on both sides whatever the later tie-breaks do
+    for t in (0, 1):
+        if t == 1 and not torch.equal(a["seq"][:, :, :1].cpu(), b["seq"][:, :, :1].cpu()):
+            continue
+        want, got = rec["cache"][t], rec["dev"][t]
+        scale = max(1.0, float(want.abs().max()))
+        rows = slice(0, None, int(hp.beam_size)) if t == 0 else slice(None)      # at t = 0 only beam 0 is alive
+        assert float((got[rows] - want[rows]).abs().max()) <= 4e-2 * scale, (name, t)
+    same = [bool(torch.equal(a["seq"][i, 0], b["seq"][i, 0])) for i in range(src.shape[0])] \
+        if a["seq"].shape == b["seq"].shape else [False]
+    np.testing.assert_allclose(b["score"][:, 0].cpu().numpy(), a["score"][:, 0].cpu().numpy(), atol=5e-2, rtol=2e-2)
+    assert sum(same) * 2 > len(same), (name, same)
+    # the registered plugin hands out the dev decoding_fn when asked for it
+    plugins.reset_engines()
+    hp2 = copy.copy(hp)
+    enc_fn, dec_fn = registry.get_model(hp.model_name).infer_fn(hp2)
+    assert dec_fn.__func__ is type(eng).decoding_fn_dev
 
 
 def test_full_size_properties_c2_shapes():

@@ -1067,6 +1067,30 @@ def _engine_decoding_fn(self, target, state, time):
     return self._dense_logits(logits), state
 
 
+def _engine_decoding_fn_dev(self, target, state, time):
+    """decoding_fn of search_mode = "dev" (models/transformer.py:276-281, search.py:129-140): no caches — the whole
+    decoder is re-run, teacher-forced, on the partial target [R, t + 1] (the tokens generated so far followed by a
+    placeholder), and the logits of the last position are returned (models/transformer.py:183-184).  A development aid
+    in the reference ("at the cost of slower decoding") and here the cache-independent check of the cached path."""
+    c = self.cfg
+    target = self._prep_ids(target, self.device, compact=False)
+    R, T = target.shape
+    K = max(1, R // max(state.B, 1))
+    S = state.S
+    enc = state.enc.view(state.B, S, c.d)
+    if K > 1:       # every beam of a sentence reads the same memory: tile it (the reference tiles its whole state)
+        enc_r = self.ws.get("dev.enc", (R * S, c.d))
+        enc_r.view(state.B, K, S, c.d).copy_(enc.unsqueeze(1).expand(state.B, K, S, c.d))
+        src_len = state.src_len.repeat_interleave(K)
+    else:
+        enc_r, src_len = state.enc, state.src_len
+    # the placeholder in the last column must count as a real token for the models that mask by target id (AAN / fuse)
+    _, _, logits = self.decode_train(target, enc_r, src_len, S, 0.0, False, tag="V", want_logits=True)
+    last = self.ws.get("dev.logits", (R, c.vt), f32)
+    last.copy_(logits.view(R, T, -1)[:, T - 1, :])
+    return last, state
+
+
 def _engine_decode_proj_ln(self, inp, lin, res, out, ln, rows):
     """out = LayerNorm(res + inp @ W + b) of a decode step (func.linear + residual_fn + layer_norm on [rows, .] with
     rows = batch * beam).  A 256-row projection makes only rows / 128 x n / 64 output tiles — 16 CTAs for n = 512, each
@@ -1106,6 +1130,7 @@ def _engine_post_attn(self, key, ctx, rows):
 
 Engine.encoding_fn = _engine_encoding_fn
 Engine.decoding_fn = _engine_decoding_fn
+Engine.decoding_fn_dev = _engine_decoding_fn_dev
 Engine._post_attn = _engine_post_attn
 Engine._decode_proj_ln = _engine_decode_proj_ln
 

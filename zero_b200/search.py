@@ -119,6 +119,12 @@ class BeamState(object):
         self.tok_buf.copy_(self.alive_seq[:, :, t].reshape(self.B * self.K, 1))
         return self.tok_buf
 
+    def prefix_tokens(self, t):
+        """search_mode = "dev" (search.py:131-140): the partial target [B*beam, t + 1] — the tokens generated so far
+        (the leading start column dropped) followed by one placeholder token (id 1)."""
+        seq = self.alive_seq[:, :, 1:t + 1].reshape(self.B * self.K, t)
+        return torch.cat([seq, torch.ones(self.B * self.K, 1, dtype=seq.dtype, device=seq.device)], 1).contiguous()
+
     def step(self, logits, t):
         ops.beam_step(self._args(logits, t))
         self.time = t + 1
@@ -183,7 +189,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     state.begin_search(K, cap)
     # CUDA-graph replay is only valid for the engine's own decoding_fn (a wrapped one may have side effects)
     own = getattr(decoding_fn, "__self__", None) is eng and getattr(decoding_fn, "__func__", None) is type(eng).decoding_fn
-    use_graph = own and bool(getattr(params, "decode_graph", True))
+    use_graph = own and bool(getattr(params, "decode_graph", True)) and not dev_mode
     graphs = eng.__dict__.setdefault("_decode_graphs", {})
     seen = eng.__dict__.setdefault("_decode_seen", {})
     if eng.__dict__.get("_decode_graphs_gen", 0) != eng.ws.generation:
@@ -193,9 +199,11 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         seen.clear()
         eng.__dict__["_decode_graphs_gen"] = eng.ws.generation
 
+    dev_mode = str(getattr(params, "search_mode", "cache")) != "cache"
+
     def run_step(t):
         nonlocal state
-        logits, state = decoding_fn(st.last_tokens(t), state, t)
+        logits, state = decoding_fn(st.prefix_tokens(t) if dev_mode else st.last_tokens(t), state, t)
         if noise:
             ops.gumbel_add(logits, st.noise_seed, t, eps=float(getattr(params, "dtype_epsilon", 1e-8)))
         parent = st.step(logits, t)
