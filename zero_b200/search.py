@@ -187,6 +187,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     if noise:
         st.noise_seed.add_(1)          # a device-side value: replayed step graphs read the new seed
     state.begin_search(K, cap)
+    dev_mode = str(getattr(params, "search_mode", "cache")) != "cache"
     # CUDA-graph replay is only valid for the engine's own decoding_fn (a wrapped one may have side effects)
     own = getattr(decoding_fn, "__self__", None) is eng and getattr(decoding_fn, "__func__", None) is type(eng).decoding_fn
     use_graph = own and bool(getattr(params, "decode_graph", True)) and not dev_mode
@@ -198,8 +199,6 @@ def beam_search(features, encoding_fn, decoding_fn, params):
         graphs.clear()
         seen.clear()
         eng.__dict__["_decode_graphs_gen"] = eng.ws.generation
-
-    dev_mode = str(getattr(params, "search_mode", "cache")) != "cache"
 
     def run_step(t):
         nonlocal state
