@@ -136,7 +136,10 @@ def test_c5_deep_init_encoder_len1024_against_the_oracle():
     mask = (src != 0)
     err = float((enc - want)[mask].abs().max())
     print("C5: encoder output max-abs err %.4f (values up to %.2f)" % (err, float(want.abs().max())))
-    assert err < 1e-2 * max(1.0, float(want.abs().max())) * 4    # unit-variance LN outputs: 4e-2 absolute
+    # measured 0.060 on values up to 4.94 (1.2e-2 of the range, profiles/r02_golden_logit_errors.log): the encoder output
+    # is a bf16 tensor, two of its ulps at that magnitude; the bound is 1.5x the measurement rather than the 1e-2 that
+    # the logits of the same run meet (2.4e-3)
+    assert err < 1.8e-2 * max(1.0, float(want.abs().max()))
 
 
 def test_c3_average_attention_beam4_vocab32k_against_the_oracle():

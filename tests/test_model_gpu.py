@@ -19,6 +19,19 @@ SCORE_MODELS = TRAIN_MODELS
 DECODE_MODELS = SCORE_MODELS
 
 
+# Bound on max |logit error| / logit range against the reference-executed fp32 goldens.  The north-star bound for bf16
+# compute is 1e-2; it is asserted as such at the BASELINE shapes (tests/test_baseline_shapes_gpu.py) and for every
+# golden model that meets it (10 of 11: 2.1e-3 .. 7.5e-3, profiles/r02_golden_logit_errors.log).  The one exception is
+# listed with a bound 1.5x above the error measured on the B200: the short-sentence ReLA model (1.09e-2; rectified
+# attention has no softmax normalisation to damp the bf16 rounding of the scores, and the 40-token ReLA model and the
+# BASELINE-shape ReLA run are inside 1e-2).
+LOGIT_BOUND = {"transformer_rela": 1.6e-2}
+# the same for single decode-step logits (first step against the reference's own step logits: 4.6e-3 .. 9.0e-3, the
+# short-sentence rpr model 1.09e-2; the device-resident search against the cached one: identical bits on the B200)
+STEP_BOUND = 1e-2
+STEP_BOUND_BY_MODEL = {"transformer_rpr": 1.6e-2}
+
+
 def _engine(name):
     from zero_b200.engine import Engine
     z, hp, variables, grads, vs, vt = load_golden(name)
@@ -43,7 +56,9 @@ def test_train_loss_logits_grads_vs_golden(name):
     want = torch.from_numpy(z["logits"])
     scale = max(1.0, float(want.abs().max()))
     err = float((logits.cpu() - want).abs().max())
-    assert err <= 1e-2 * scale * 4, "logits max abs err %.4f (scale %.2f)" % (err, scale)
+    print("%s: loss %.5f (reference %.5f), logits max-abs err %.4f = %.2e of the logit range %.2f" % (
+        name, float(loss[0]), float(z["loss"]), err, err / scale, scale))
+    assert err <= LOGIT_BOUND.get(name, 1e-2) * scale, "logits max abs err %.4f (scale %.2f)" % (err, scale)
     assert _rel(logits.cpu(), want) < 2e-2
     np.testing.assert_allclose(per_sample.cpu().numpy(), z["per_sample_loss"], atol=3e-2, rtol=1e-2)
     got = eng.ps.grad_dict()
@@ -101,7 +116,9 @@ def test_cached_decode_and_beam_search(name):
         want = torch.from_numpy(z["step_logits_%d" % (t + 1)])
         if t == 0:  # at t = 0 every beam holds the same prefix
             scale = max(1.0, float(want.abs().max()))
-            assert float((recorded[t] - want).abs().max()) <= 4e-2 * scale
+            err = float((recorded[t] - want).abs().max())
+            print("%s: first decode-step logits max-abs err %.4f = %.2e of the logit range %.2f" % (name, err, err / scale, scale))
+            assert err <= STEP_BOUND_BY_MODEL.get(name, STEP_BOUND) * scale
     # (2) bit-exact bookkeeping: the oracle's beam search replayed on the SAME logits gives the same beams
     c = zo.Cfg(hp, eng.cfg.vs, eng.cfg.vt)
     calls = {"n": 0}
@@ -184,7 +201,9 @@ def test_search_mode_dev_matches_the_cached_search(name):
         want, got = rec["cache"][t], rec["dev"][t]
         scale = max(1.0, float(want.abs().max()))
         rows = slice(0, None, int(hp.beam_size)) if t == 0 else slice(None)      # at t = 0 only beam 0 is alive
-        assert float((got[rows] - want[rows]).abs().max()) <= 4e-2 * scale, (name, t)
+        err = float((got[rows] - want[rows]).abs().max())
+        print("%s: dev vs cache step %d logits max-abs err %.4f = %.2e of the logit range %.2f" % (name, t, err, err / scale, scale))
+        assert err <= STEP_BOUND * scale, (name, t)
     same = [bool(torch.equal(a["seq"][i, 0], b["seq"][i, 0])) for i in range(src.shape[0])] \
         if a["seq"].shape == b["seq"].shape else [False]
     np.testing.assert_allclose(b["score"][:, 0].cpu().numpy(), a["score"][:, 0].cpu().numpy(), atol=5e-2, rtol=2e-2)
@@ -409,7 +428,9 @@ def test_vocabulary_size_not_a_multiple_of_8_matches_oracle(model):
     _, per_sample, logits = eng.train_loss(src, tgt)
     assert tuple(logits.shape) == (5 * 7, vt)
     scale = max(1.0, float(want_logits.abs().max()))
-    assert float((logits.cpu() - want_logits.detach().reshape(-1, vt)).abs().max()) <= 4e-2 * scale
+    err = float((logits.cpu() - want_logits.detach().reshape(-1, vt)).abs().max())
+    print("odd-vocabulary model: logits max-abs err %.4f = %.2e of the logit range %.2f" % (err, err / scale, scale))
+    assert err <= STEP_BOUND * scale
     grads = torch.autograd.grad(want_loss, [P[k] for k in sorted(P)], allow_unused=True)
     got = eng.ps.grad_dict()
     for k, gr in zip(sorted(P), grads):
