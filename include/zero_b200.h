@@ -24,7 +24,7 @@ extern "C" {
 
 typedef struct CUstream_st* zb_stream_t; /* == cudaStream_t */
 
-#define ZB_ABI_VERSION 3
+#define ZB_ABI_VERSION 4
 
 typedef enum {
   ZB_OK = 0,
@@ -56,11 +56,12 @@ typedef enum {
   ZB_PATH_BEAM_PARTS = 8,     /* beam.cu a 4-CTA cluster per row with a threshold pass, opt-in */
   ZB_PATH_GEMM_BM64 = 9,      /* single-CTA tcgen05 GEMM with 64-row tiles, opt-in (also counted as GEMM_TCGEN05) */
   ZB_PATH_ATTN_TC = 10,       /* attention_tc.cu: tcgen05 / TMEM / TMA attention forward and backward (dh = 64) */
-  ZB_PATH_COUNT_ = 11
+  ZB_PATH_BEAM_CAND = 11,     /* beam.cu candidate kernel after zb_vocab_topk (no logits) */
+  ZB_PATH_COUNT_ = 12
 } zb_path;
 int64_t zb_path_launch_count(int32_t which);
 /* sizeof() of the argument records, by index: 0 gemm, 1 attention, 2 add_ln, 3 embed, 4 ce, 5 adam, 6 beam,
- * 7 colsum, 8 shard_adam; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
+ * 7 colsum, 8 shard_adam, 9 vocab_ce, 10 vocab_topk; -1 for an unknown index.  Lets a binding check its mirrored struct layouts at load time. */
 int64_t zb_abi_struct_size(int32_t which);
 
 /* ------------------------------------------------------------------------------------------------ K1
@@ -241,6 +242,25 @@ typedef struct {
 int zb_vocab_ce(const zb_vocab_ce_args* a, zb_stream_t stream);
 int64_t zb_vocab_ce_workspace_bytes(const zb_vocab_ce_args* a);
 
+/* zb_vocab_topk: K8 fused — the decode step's logits = feat @ table^T / temperature (models/transformer.py:186-196,
+ * search.py:147) are reduced inside the GEMM epilogue to what the beam step needs and never written: per row and
+ * 128-column part {max, sum exp(x - max)} and the part's 8 largest logits with their columns (ties -> lower column,
+ * like tf.nn.top_k).  The workspace is handed to zb_beam_step as zb_beam_args.cand (layout: csrc/vocab_topk.cu).
+ * skip_col: a column that is never offered as a candidate — EOS at time 0 (search.py:152-155 pushes it below every
+ * other word of the row; with vocab - 1 >= 2 * beam it cannot be chosen) — or -1.  vocab >= 128; d, ldf, ldt
+ * multiples of 8. */
+typedef struct {
+  const void* feat; int64_t ldf;     /* bf16 [rows, d], rows = batch * beam */
+  const void* table; int64_t ldt;    /* bf16 [vocab, d] */
+  int32_t rows, d, vocab;
+  int32_t skip_col;
+  float temperature;                 /* beam_search_temperature (search.py:147) */
+  void* workspace; int64_t workspace_bytes; /* caller-owned, zb_vocab_topk_workspace_bytes, 16-byte aligned */
+} zb_vocab_topk_args;
+int zb_vocab_topk(const zb_vocab_topk_args* a, zb_stream_t stream);
+int64_t zb_vocab_topk_workspace_bytes(const zb_vocab_topk_args* a);
+int32_t zb_vocab_topk_parts(int32_t vocab);
+
 /* ------------------------------------------------------------------------------------------------ misc
  * zb_colsum: out[n] += sum_m x[m,n] (bias gradients; tf.nn.bias_add grad).  x bf16, out fp32. */
 int zb_colsum(const void* x, int64_t m, int64_t n, int64_t ld, float* out, zb_stream_t stream);
@@ -330,7 +350,7 @@ int zb_shard_adam(const zb_shard_adam_args* a, zb_stream_t stream);
  * flat index like tf.nn.top_k.
  */
 typedef struct {
-  const float* logits;   /* [batch*beam, vocab] fp32 */
+  const float* logits;   /* [batch*beam, vocab] fp32; NULL when `cand` is given */
   int32_t batch, beam, vocab;
   int32_t time;          /* 0-based step */
   int32_t eos_id, pad_id;
@@ -358,6 +378,10 @@ typedef struct {
   /* optional scratch of the row-parallel kernel (one CTA per (sentence, beam) row): batch * (4 * beam^2 + 1) 4-byte
    * words, zeroed ONCE by the caller (the kernel leaves it zeroed); NULL = one CTA per sentence */
   float* row_ws;
+  /* instead of `logits`: the workspace zb_vocab_topk wrote for these batch * beam rows with this step's temperature and
+   * (time == 0) skip_col = eos_id; needs row_ws, beam <= 4 and vocab - 1 >= 2 * beam.  `temperature` is not applied
+   * again.  Same result as the logits path (the candidates are a superset of every row's 2 * beam best). */
+  const void* cand;
 } zb_beam_args;
 int zb_beam_cond(const zb_beam_args* a, zb_stream_t stream);
 int zb_beam_step(const zb_beam_args* a, zb_stream_t stream);

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), "libzero_b200.so does not export %s" % sym
     assert sorted(L.EXPORTS) == declared
     lib.zb_abi_version.restype = ctypes.c_int
-    assert lib.zb_abi_version() == 3
+    assert lib.zb_abi_version() == 4
 
 
 def test_ctypes_struct_sizes_match_header_layout():
@@ -73,7 +73,7 @@ def test_every_mirrored_field_offset_matches_the_header(tmp_path):
     pairs = [("zb_gemm_args", L.GemmArgs), ("zb_attention_args", L.AttentionArgs), ("zb_add_ln_args", L.AddLnArgs),
              ("zb_embed_args", L.EmbedArgs), ("zb_ce_args", L.CeArgs), ("zb_adam_args", L.AdamArgs),
              ("zb_beam_args", L.BeamArgs), ("zb_colsum_args", L.ColsumArgs), ("zb_shard_adam_args", L.ShardAdamArgs),
-             ("zb_vocab_ce_args", L.VocabCeArgs)]
+             ("zb_vocab_ce_args", L.VocabCeArgs), ("zb_vocab_topk_args", L.VocabTopkArgs)]
     assert [c for _, c in pairs] == L.STRUCTS
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % os.path.join(ROOT, "include", "zero_b200.h"),
              'int main(void) {']

@@ -626,6 +626,107 @@ def test_beam_part_kernel_equals_sentence_kernel(B, K, V, monkeypatch):
     assert t >= 3 and L.path_launch_count("beam_parts") == before + t
 
 
+def _topk_problem(R, V, d, seed):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(R, d, generator=g).to(bf16).to(dev())
+    pitch = (d + 7) // 8 * 8
+    table = (torch.randn(V, pitch, generator=g) * 0.2).to(bf16).to(dev())[:, :d]
+    logits = torch.zeros(R, (V + 7) // 8 * 8, dtype=f32, device=dev())[:, :V]
+    from zero_b200 import ops
+    ops.gemm(feat, table, logits, 0, 0)
+    return feat, table, logits.contiguous()
+
+
+@pytest.mark.parametrize("R,V,d,skip,temp", [(256, 32000, 512, -1, 1.0), (256, 32000, 512, 2, 1.0), (20, 1000, 128, 2, 0.7),
+                                             (7, 256, 64, 5, 1.0), (33, 208, 128, 2, 1.0), (130, 1003, 72, -1, 1.0), (300, 4099, 512, 2, 1.3)])
+def test_vocab_topk_candidates_hold_every_rows_top8_and_its_logsumexp(R, V, d, skip, temp):
+    """zb_vocab_topk (K8 fused, the tcgen05 GEMM's ce_mode 3 epilogue) against zb_gemm's fp32 logits: per row, the union
+    of the parts' candidates contains the row's 8 largest logits / T (skip column left out) with their columns in
+    tf.nn.top_k's order, every candidate is the logit of its column, and the parts' statistics fold into the row's
+    log-sum-exp.  Ragged rows (7, 20, 130, 300), a vocabulary that leaves the last part partly / wholly empty, K = 72."""
+    from zero_b200 import ops
+    feat, table, logits = _topk_problem(R, V, d, 5 + V)
+    cands = ops.vocab_topk(feat, table, lambda n: torch.full(((n + 3) // 4,), float("nan"), dtype=f32, device=dev()),
+                           skip_col=skip, temperature=temp)
+    torch.cuda.synchronize()
+    stats, vals, cols = cands.unpack()
+    assert cands.parts == 2 * ((V + 255) // 256) and tuple(vals.shape) == (cands.parts, R, 8)
+    x = logits / temp
+    # statistics
+    m, s = stats[:, :, 0], stats[:, :, 1]
+    lse = torch.logsumexp(torch.where(m > -float("inf"), m + torch.log(s), m), 0)
+    torch.testing.assert_close(lse, torch.logsumexp(x, 1), rtol=1e-5, atol=2e-5)
+    part_max = torch.stack([x[:, p * 128:(p + 1) * 128].max(1).values if p * 128 < V else
+                            torch.full((R,), -float("inf"), device=dev()) for p in range(cands.parts)])
+    torch.testing.assert_close(m, part_max, rtol=0, atol=1e-5)
+    # candidates: valid slots are real (column, logit) pairs of their own part, sorted, never the skip column
+    valid = vals > -float("inf")
+    pv, pc = vals.permute(1, 0, 2).reshape(R, -1), cols.permute(1, 0, 2).reshape(R, -1).long()
+    pvalid = valid.permute(1, 0, 2).reshape(R, -1)
+    assert bool((pc[pvalid] >= 0).all()) and bool((pc[pvalid] < V).all()) and not bool((pc[pvalid] == skip).any())
+    got_x = torch.gather(x, 1, pc.clamp(0, V - 1))
+    torch.testing.assert_close(pv[pvalid], got_x[pvalid], rtol=1e-5, atol=1e-5)
+    part_of = torch.arange(cands.parts, device=dev()).repeat_interleave(8)[None, :].expand(R, -1)
+    assert bool(((pc // 128) == part_of)[pvalid].all())
+    assert bool((vals[:, :, :-1] >= vals[:, :, 1:]).all())
+    n_valid = valid.sum(2)
+    for p in range(cands.parts):
+        width = max(0, min(V, (p + 1) * 128) - p * 128) - (1 if p * 128 <= skip < (p + 1) * 128 else 0)
+        assert bool((n_valid[p] == min(8, width)).all()), p
+    # the row's top-8 from the candidates == top-8 of the logits (skip column removed)
+    xs = x.clone()
+    if skip >= 0:
+        xs[:, skip] = -float("inf")
+    want_v, want_c = torch.topk(xs, 8, dim=1)
+    key = torch.where(pvalid, pv, torch.full_like(pv, -float("inf")))
+    order = torch.argsort(key, dim=1, descending=True, stable=True)[:, :8]     # parts are in column order: stable = lower col
+    got_v, got_c = torch.gather(key, 1, order), torch.gather(pc, 1, order)
+    torch.testing.assert_close(got_v, want_v, rtol=1e-5, atol=1e-5)
+    gap_ok = (want_v[:, :-1] - want_v[:, 1:]).min(1).values > 1e-4            # rows without a near-tie in the top 8
+    assert int(gap_ok.sum()) >= R * 3 // 4
+    assert torch.equal(got_c[gap_ok], want_c[gap_ok])
+
+
+@pytest.mark.parametrize("B,K,V,d", [(64, 4, 32000, 512), (5, 4, 1000, 128), (3, 2, 300, 64), (4, 1, 4099, 256), (6, 4, 208, 128)])
+def test_beam_step_from_candidates_equals_the_logits_step(B, K, V, d, monkeypatch):
+    """zb_beam_step fed by zb_vocab_topk's candidates (no logits in memory) against the same step fed by the logits of
+    the same features, step for step over a whole search: sequences / parents / flags bit-exact, scores to fp32
+    round-off (the two log-sum-exps add the same terms in a different order).  Temperature 0.7 for V = 1000."""
+    import zero_b200.lib as L
+    from zero_b200 import ops
+    from zero_b200.search import BeamState
+    g = torch.Generator().manual_seed(V + K)
+    src = torch.randint(3, 50, (B, 6), generator=g)
+    src[0, 3:] = 0
+    temp = 0.7 if V == 1000 else 1.0
+    ref = BeamState(B, K, V, src.to(dev()), 4, 0.6, temp, 1e8, dev())
+    new = BeamState(B, K, V, src.to(dev()), 4, 0.6, temp, 1e8, dev())
+    before = L.path_launch_count("beam_cand")
+    ws = {}
+    t = 0
+    while True:
+        nf = [ref.not_finished(t), new.not_finished(t)]
+        assert nf[0] == nf[1]
+        if not nf[0]:
+            break
+        feat, table, logits = _topk_problem(B * K, V, d, 100 * t + V)
+        if t % 3 == 2:
+            table[2] = feat[0] * 0.5            # EOS scores high for some rows: beams finish
+            logits = torch.zeros(B * K, (V + 7) // 8 * 8, dtype=f32, device=dev())[:, :V]
+            ops.gemm(feat, table, logits, 0, 0)
+            logits = logits.contiguous()
+        ref.step(logits, t)
+        cands = ops.vocab_topk(feat, table, lambda n: ws.setdefault(n, torch.zeros((n + 3) // 4, dtype=f32, device=dev())),
+                               **new.candidate_request(t))
+        new.step(cands, t)
+        for name in ("alive_seq", "fin_seq", "fin_flag", "parent"):
+            assert torch.equal(getattr(ref, name), getattr(new, name)), (name, t)
+        for name in ("alive_logp", "alive_score", "fin_score"):
+            torch.testing.assert_close(getattr(ref, name), getattr(new, name), rtol=1e-5, atol=1e-5)
+        t += 1
+    assert t >= 3 and L.path_launch_count("beam_cand") == before + t
+
+
 @unvalidated
 @pytest.mark.parametrize("m,n,k", [(256, 512, 512), (256, 2048, 512), (256, 512, 2048), (256, 1024, 1024),
                                    (1, 64, 64), (37, 136, 72), (100, 1000, 520), (300, 2048, 512), (511, 384, 128)])

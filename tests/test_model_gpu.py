@@ -326,6 +326,32 @@ def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     np.testing.assert_allclose(got["score"].cpu().numpy(), ref["score"].cpu().numpy(), rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("name", ["transformer", "transformer_aan", "transformer_fuse", "transformer_rpr_len40"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_vocabulary_candidates_keep_the_beams(name, graph, monkeypatch):
+    """ZB_BEAM_FUSED=1 (K8 fused: the step's vocabulary projection hands the beam step per-part top-8 candidates, the
+    logits are never written) returns the beams of the logits path on the golden models, eagerly and through the
+    captured step graphs (two searches: the second replays)."""
+    import zero_b200.lib as L
+    from zero_b200 import search
+    from zero_b200.params import SimpleVocab
+    eng, z, hp, variables, grads = _engine(name)
+    hp.add_hparam("src_vocab", SimpleVocab(eng.cfg.vs))
+    hp.add_hparam("tgt_vocab", SimpleVocab(eng.cfg.vt))
+    hp.add_hparam("decode_graph", graph)
+    eng.decode_length = hp.decode_length
+    src = torch.from_numpy(z["source"])
+    monkeypatch.setenv("ZB_BEAM_FUSED", "0")
+    ref = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+    monkeypatch.setenv("ZB_BEAM_FUSED", "1")
+    before = L.path_launch_count("beam_cand")
+    for _ in range(3 if graph else 1):
+        got = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
+        np.testing.assert_array_equal(got["seq"].cpu().numpy(), ref["seq"].cpu().numpy())
+        np.testing.assert_allclose(got["score"].cpu().numpy(), ref["score"].cpu().numpy(), rtol=1e-4, atol=1e-4)
+    assert L.path_launch_count("beam_cand") > before
+
+
 @pytest.mark.parametrize("name", ["transformer", "transformer_h4", "transformer_rpr", "transformer_rela"])
 def test_batched_memory_projection_matches_golden_and_default(name, monkeypatch):
     """ZB_BATCH_MEM_PROJ=1 (one GEMM for every decoder layer's k_map | v_map, one dgrad / wgrad pair backward):

@@ -89,6 +89,7 @@ extern "C" int64_t zb_abi_struct_size(int32_t which) {
     case 7: return sizeof(zb_colsum_args);
     case 8: return sizeof(zb_shard_adam_args);
     case 9: return sizeof(zb_vocab_ce_args);
+    case 10: return sizeof(zb_vocab_topk_args);
     default: return -1;
   }
 }

@@ -778,6 +778,133 @@ __global__ void __launch_bounds__(kPartThreads) beam_part_kernel(const zb_beam_a
   beam_sentence_tail<N2, kPartThreads>(a, b, ws_s, ws_i, ticket);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Candidate kernel: the step after zb_vocab_topk (vocab_topk.cu).  One CTA per (sentence, beam) row; the row's V
+// logits were reduced by the GEMM epilogue to `parts` x {max, sum exp, top-8 (x, column)} with x = logit / T.  The row's
+// log-sum-exp is the fold of the parts' statistics; every candidate is scored like the logits kernels score every word
+// (search.py:148-170) and the row's top-2k goes to the sentence's last arriver exactly as in beam_part_kernel.
+constexpr int kCandThreads = 256;
+
+template <int N2>
+__global__ void __launch_bounds__(kCandThreads) beam_cand_kernel(const zb_beam_args a, const int parts) {
+  grid_dep_wait();
+  if (a.active && a.active[0] == 0) return;
+  const int K = a.beam, V = a.vocab;
+  const int row = blockIdx.x;                   // b * K + k
+  const int b = row / K, k = row % K;
+  const long long rows = (long long)a.batch * K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kCandThreads / 32;
+  const int n2 = 2 * K;
+  __shared__ float red_m[NW], red_s[NW];
+  __shared__ float bcast;
+  __shared__ float wl_s[NW * N2];
+  __shared__ int wl_i[NW * N2];
+  __shared__ float row_s[2 * kMaxBeam];
+  __shared__ int row_i[2 * kMaxBeam];
+  __shared__ int is_last;
+  const float4* stats = reinterpret_cast<const float4*>(a.cand);
+  const float* cval = reinterpret_cast<const float*>(stats + (long long)parts * rows);
+  const int* cidx = reinterpret_cast<const int*>(cval + (long long)parts * rows * 8);
+  // ---- log-sum-exp of the row: fold the parts in a fixed order (thread-strided, butterfly, warps in order)
+  float m = -INFINITY, s = 0.f;
+  for (int p = tid; p < parts; p += kCandThreads) {
+    const float4 t = __ldcg(stats + (long long)p * rows + row);
+    if (t.x > -INFINITY) {
+      const float nm = fmaxf(m, t.x);
+      s = s * expf(m - nm) + t.y * expf(t.x - nm);
+      m = nm;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, m2);
+    const float sa = m > -INFINITY ? s * expf(m - nm) : 0.f, sb = m2 > -INFINITY ? s2 * expf(m2 - nm) : 0.f;
+    // both lanes of a pair must add in the same order to agree bit for bit: the lower lane's term first
+    s = (lane & o) ? sb + sa : sa + sb;
+    m = nm;
+  }
+  if (lane == 0) {
+    red_m[warp] = m;
+    red_s[warp] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float M = -INFINITY;
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, red_m[w]);
+    float S = 0.f;
+    for (int w = 0; w < NW; ++w)
+      if (red_m[w] > -INFINITY) S += red_s[w] * expf(red_m[w] - M);
+    bcast = M + logf(S);
+  }
+  __syncthreads();
+  const float l = bcast;
+  // ---- the row's top-2k among the 8 * parts candidates
+  const float pen = a.length_penalty;
+  const float lp_prev = a.alive_logp[row];
+  float ls[N2];
+  int li[N2];
+#pragma unroll
+  for (int c = 0; c < N2; ++c) {
+    ls[c] = -INFINITY;
+    li[c] = 0x7fffffff;
+  }
+  // A beam that is not really alive (score float32.min: beams 1.. at t = 0; -inf: a sentence past its max_len) absorbs
+  // every log-probability: all V continuations tie at prev / penalty and top_k keeps the lowest columns, whatever the
+  // logits are.  The logits kernels get that from the arithmetic; here it has to be said.
+  const bool dead = !(lp_prev > F32_MIN);
+  if (dead && tid < n2) list_insert<N2>(ls, li, lp_prev / pen, k * V + tid);
+  for (int p = tid; p < (dead ? 0 : parts); p += kCandThreads) {
+    const long long slot = ((long long)p * rows + row) * 8;
+    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(cval + slot));
+    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(cval + slot) + 1);
+    const int4 i0 = __ldcg(reinterpret_cast<const int4*>(cidx + slot));
+    const int4 i1 = __ldcg(reinterpret_cast<const int4*>(cidx + slot) + 1);
+    const float xv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const int xi[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (xv[c] > -INFINITY) {
+        const float lp = xv[c] - l;
+        list_insert<N2>(ls, li, (lp_prev + lp) / pen, k * V + xi[c]);
+      }
+    }
+  }
+  warp_pop<N2>(ls, li, n2, wl_s + warp * N2, wl_i + warp * N2);
+  __syncthreads();
+  float* ws_s = a.row_ws + (long long)b * (4 * K * K + 1);
+  int* ws_i = reinterpret_cast<int*>(ws_s) + 2 * K * K;
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws_s) + 4 * K * K;
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < N2; ++c) {
+      ls[c] = -INFINITY;
+      li[c] = 0x7fffffff;
+    }
+    for (int c = lane; c < NW * n2; c += 32) {
+      const int w = c / n2, r = c % n2;
+      list_insert<N2>(ls, li, wl_s[w * N2 + r], wl_i[w * N2 + r]);
+    }
+    __syncwarp();
+    warp_pop<N2>(ls, li, n2, row_s, row_i);
+    __syncwarp();
+    if (lane < n2) {
+      ws_s[k * n2 + lane] = row_s[lane];
+      ws_i[k * n2 + lane] = row_i[lane];
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned prev = atomicAdd(ticket, 1u);
+      is_last = prev == (unsigned)(K - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  beam_sentence_tail<N2, kCandThreads>(a, b, ws_s, ws_i, ticket);
+}
+
 // search.py:85-113 _not_finished(time): not(all_b(worst finished > best alive bound)) and any_b(time < max_len)
 __global__ void beam_cond_kernel(const zb_beam_args a) {
   grid_dep_wait();
@@ -808,7 +935,7 @@ __global__ void beam_cond_kernel(const zb_beam_args a) {
 
 extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   using namespace zb;
-  ZB_REQUIRE(a && a->logits && a->max_len && a->alive_seq && a->alive_logp && a->alive_score && a->fin_seq &&
+  ZB_REQUIRE(a && (a->logits || a->cand) && a->max_len && a->alive_seq && a->alive_logp && a->alive_score && a->fin_seq &&
                  a->fin_score && a->fin_flag && a->parent && a->tmp_seq,
              "zb_beam_step: null pointer");
   ZB_REQUIRE(a->beam >= 1 && a->beam <= kMaxBeam, "zb_beam_step: beam must be in [1, %d]", kMaxBeam);
@@ -816,6 +943,15 @@ extern "C" int zb_beam_step(const zb_beam_args* a, zb_stream_t stream) {
   ZB_REQUIRE((long long)a->beam * a->vocab < (1ll << 31), "zb_beam_step: beam * vocab overflows int32");
   if (a->batch == 0) return ZB_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->cand) {
+    ZB_REQUIRE(!a->logits, "zb_beam_step: give logits or cand, not both");
+    ZB_REQUIRE(a->row_ws && 2 * a->beam <= 8 && a->vocab >= 128 && a->vocab - 1 >= 2 * a->beam,
+               "zb_beam_step(cand): needs row_ws, beam <= 4 and vocab >= 128");
+    ZB_REQUIRE((reinterpret_cast<uintptr_t>(a->cand) & 15) == 0, "zb_beam_step(cand): workspace must be 16-byte aligned");
+    ZB_LAUNCH(beam_cand_kernel<8>, a->batch * a->beam, kCandThreads, 0, st, *a, 2 * ((a->vocab + 255) / 256));
+    note_path(ZB_PATH_BEAM_CAND);
+    return check_launch("zb_beam_step(cand)");
+  }
   const char* parts_env = getenv("ZB_BEAM_PARTS");   // per call: the parity test flips it inside one process
   const int vp = (((a->vocab + kParts - 1) / kParts) + 3) & ~3;   // elements per part, 16-byte granular
   // default since the r02a A/B (decode step 0.589 -> 0.563 ms); ZB_BEAM_PARTS=0 keeps the one-CTA-per-row kernel

@@ -40,11 +40,18 @@ struct Gemm2Params {
   //   ce_mode 1: nothing is stored; every epilogue thread reduces its columns of its row to {max, sum exp(x - max),
   //              sum x, x[gold]} and writes them to ce_stats[(n_blk * 2 + column half) * M + row]
   //   ce_mode 2: the tile is turned into d_logits = (exp(x - lse[row]) - soft_label) * weight[row] before the store
+  // K8 (vocab_topk.cu): the decode step's vocabulary projection reduced to what the beam step needs.
+  //   ce_mode 3: nothing is stored; x = acc / ce_p (the temperature); per (row, column half) {max, sum exp(x - max), 0, 0}
+  //              go to ce_stats as in mode 1 and the half's 8 largest x (ties -> lower column; column ce_skip left out)
+  //              with their columns to ce_cval / ce_cidx[((n_blk * 2 + half) * M + row) * 8 ...]
   int ce_mode;
   const float* ce_aux;        // mode 2: [M][2] = {log-sum-exp, d loss / d nll} per row
   const int32_t* ce_labels;   // [M] gold class per row
   float4* ce_stats;           // mode 1
-  float ce_p, ce_q;           // smoothed target: p on the gold class, q elsewhere
+  float ce_p, ce_q;           // smoothed target: p on the gold class, q elsewhere (mode 3: ce_p = temperature)
+  float* ce_cval;             // mode 3
+  int32_t* ce_cidx;           // mode 3
+  int ce_skip;                // mode 3: -1 = none
 };
 
 // One launch may carry several independent problems of the same operand layouts (the weight-gradient GEMMs of a
@@ -381,6 +388,8 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
     // K6 state of this thread's row in this tile
     float ce_m = -INFINITY, ce_s = 0.f, ce_t = 0.f, ce_g = 0.f, ce_lse = 0.f, ce_w = 0.f;
     int ce_gold = -1;
+    float tk_v[CE == 3 ? 8 : 1];   // K8: this thread's row, this column half: the 8 largest so far, descending
+    int tk_i[CE == 3 ? 8 : 1];
     auto finish_chunk = [&](uint32_t (&r)[32], int row, bool row_ok, int col0, float bias_lane, const uint4 (&mk)[4],
                             int cpar) {
       if (col0 >= p.N) {
@@ -423,6 +432,49 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
         for (int j = 0; j < 32; ++j) acc4[j & 3] += ex2_(fmaf(v[j], 1.4426950408889634f, -nm2));
         ce_s = ce_s * __expf(ce_m - nm) + ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
         ce_m = nm;
+        return;
+      }
+      if constexpr (CE == 3) {
+        if (p.ce_p != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] / p.ce_p;   // the beam kernels' logits / temperature
+        }
+        float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (!full_cols && col0 + j >= p.N) v[j] = -INFINITY;   // exp(-inf - m) = 0; never a candidate
+          cm[j & 3] = fmaxf(cm[j & 3], v[j]);
+        }
+        const float nm = fmaxf(ce_m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+        const float nm2 = nm * 1.4426950408889634f;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc4[j & 3] += ex2_(fmaf(v[j], 1.4426950408889634f, -nm2));
+        ce_s = ce_s * __expf(ce_m - nm) + ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+        ce_m = nm;
+        const int gj = p.ce_skip - col0;   // the soft-max statistics above keep the column, the candidates do not
+        if (gj >= 0 && gj < 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j == gj) v[j] = -INFINITY;
+        }
+        // sorted insertion without branches: columns arrive in ascending order and `>` is strict, so equal values
+        // keep the lower column first (tf.nn.top_k's order); -inf never displaces the empty slots
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j];
+          int xi = col0 + j;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const bool gt = x > tk_v[c];
+            const float ov = tk_v[c];
+            const int oi = tk_i[c];
+            tk_v[c] = gt ? x : ov;
+            tk_i[c] = gt ? xi : oi;
+            x = gt ? ov : x;
+            xi = gt ? oi : xi;
+          }
+        }
         return;
       }
       if constexpr (CE == 2) {
@@ -548,7 +600,15 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       uint4 mk_a[4], mk_b[4];
       constexpr int NCH = BN / 64;
       const int c0 = half * NCH;
-      if constexpr (CE != 0) {
+      if constexpr (CE == 3) {
+        ce_m = -INFINITY;
+        ce_s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          tk_v[c] = -INFINITY;
+          tk_i[c] = 0x7fffffff;
+        }
+      } else if constexpr (CE != 0) {
         ce_m = -INFINITY;
         ce_s = ce_t = ce_g = 0.f;
         ce_gold = row_ok ? __ldg(p.ce_labels + row) : -1;
@@ -591,6 +651,18 @@ gemm2_bf16_tcgen05(const __grid_constant__ Gemm2Group<NP> G) {
       }
       if (CE == 1 && row_ok)
         p.ce_stats[(static_cast<long long>(n_blk) * 2 + half) * p.M + row] = make_float4(ce_m, ce_s, ce_t, ce_g);
+      if constexpr (CE == 3) {
+        if (row_ok) {
+          const long long slot = (static_cast<long long>(n_blk) * 2 + half) * p.M + row;
+          p.ce_stats[slot] = make_float4(ce_m, ce_s, 0.f, 0.f);
+          float4* cv = reinterpret_cast<float4*>(p.ce_cval + slot * 8);
+          int4* ci = reinterpret_cast<int4*>(p.ce_cidx + slot * 8);
+          cv[0] = make_float4(tk_v[0], tk_v[1], tk_v[2], tk_v[3]);
+          cv[1] = make_float4(tk_v[4], tk_v[5], tk_v[6], tk_v[7]);
+          ci[0] = make_int4(tk_i[0], tk_i[1], tk_i[2], tk_i[3]);
+          ci[1] = make_int4(tk_i[4], tk_i[5], tk_i[6], tk_i[7]);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(acc == 0 ? leader_tempty0 : leader_tempty1);
@@ -702,6 +774,7 @@ static int setup_problem(const zb_gemm_args* a, int bn, Gemm2Params& p, CUtensor
   p.mask = reinterpret_cast<const __nv_bfloat16*>(a->mask); p.ldmask = a->ldmask;
   p.alpha = a->alpha; p.flags = a->flags; p.d_f32 = a->d_dtype == ZB_F32;
   p.ce_mode = 0; p.ce_aux = nullptr; p.ce_labels = nullptr; p.ce_stats = nullptr; p.ce_p = 1.f; p.ce_q = 0.f;
+  p.ce_cval = nullptr; p.ce_cidx = nullptr; p.ce_skip = -1;
   p.kb_total = (p.K + k2BK - 1) / k2BK;
   p.mt = (p.M + 255) / 256;
   p.nt = (p.N + bn - 1) / bn;
@@ -837,6 +910,28 @@ int gemm2_launch_ce(const zb_gemm_args* a, int mode, const float* aux, const int
   G.trace = nullptr;
   const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
   return mode == 1 ? launch2<256, false, false, 1, 1>(G, grid, st) : launch2<256, false, false, 1, 2>(G, grid, st);
+}
+
+// K8: logits = a @ b^T / temperature reduced to per-(row, 128-column half tile) soft-max statistics and top-8 candidates
+// (vocab_topk.cu); a->d is ignored.
+int gemm2_launch_topk(const zb_gemm_args* a, float4* stats, float* cval, int32_t* cidx, int skip_col, float temperature,
+                      cudaStream_t st) {
+  const int pairs_hw = num_sms_compute() / 2;
+  Gemm2Group<1> G;
+  Gemm2Params& p = G.prob[0];
+  zb_gemm_args b = *a;
+  b.d = nullptr;
+  int rc = setup_problem(&b, 256, p, G.maps);
+  if (rc) return rc;
+  p.d_tma = 0;
+  p.ce_mode = 3; p.ce_stats = stats; p.ce_cval = cval; p.ce_cidx = cidx; p.ce_skip = skip_col; p.ce_p = temperature;
+  set_splits(p, 1);
+  const long long total = (long long)p.mt * p.nt;
+  G.count = 1;
+  G.total_tiles = (int)total;
+  G.trace = nullptr;
+  const int grid = 2 * (int)(total < pairs_hw ? total : pairs_hw);
+  return launch2<256, false, false, 1, 3>(G, grid, st);
 }
 
 // One launch for several accumulate-into-fp32 problems with MN-major operands (the weight gradients of a layer).

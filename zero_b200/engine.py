@@ -1020,13 +1020,26 @@ def _engine_encoding_fn(self, source):
     return DecodeState(self, enc, src_len_static, source.shape[0], source.shape[1])
 
 
-def _engine_decoding_fn(self, target, state, time):
-    """decoding_fn(target [R,1], state, time) -> (logits fp32 [R, V], state)  (models/transformer.py:267-283)."""
+def _engine_step_logits(self, x, R, candidates):
+    """The decode step's vocabulary projection (models/transformer.py:186-196): fp32 [R, V] logits, or — when the
+    search asked for `candidates` = {skip_col, temperature} — the K8 fused reduction of them (ops.vocab_topk)."""
+    c, ps, ws = self.cfg, self.ps, self.ws
+    table = ps.w(self._softmax_table())
+    if candidates is not None:
+        return ops.vocab_topk(x, table, lambda nbytes: ws.get("dec.cand", ((nbytes + 3) // 4,), f32), **candidates)
+    logits = self._vocab_rows("dec.logits", R, f32)
+    ops.gemm(x, table, logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
+    return self._dense_logits(logits)
+
+
+def _engine_decoding_fn(self, target, state, time, candidates=None):
+    """decoding_fn(target [R,1], state, time) -> (logits fp32 [R, V], state)  (models/transformer.py:267-283).
+    `candidates` (search.beam_search's own fused path only): return ops.BeamCandidates instead of the logits."""
     c, ps, ws = self.cfg, self.ps, self.ws
     if state.mem is None:
         state.begin_search(state.K)
     if c.aan or c.fuse:
-        return self._decoding_fn_avg(target, state, time)
+        return self._decoding_fn_avg(target, state, time, candidates)
     t = int(time)
     R = target.shape[0]
     K = state.K
@@ -1062,9 +1075,7 @@ def _engine_decoding_fn(self, target, state, time):
         h = ws.get("dec.h", (R, c.f))
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
         self._decode_proj_ln(h, key + ".ffn.w2", xc, x, key + ".ffn.ln", R)
-    logits = self._vocab_rows("dec.logits", R, f32)
-    ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
-    return self._dense_logits(logits), state
+    return self._step_logits(x, R, candidates), state
 
 
 def _engine_decoding_fn_dev(self, target, state, time):
@@ -1129,6 +1140,7 @@ def _engine_post_attn(self, key, ctx, rows):
 
 
 Engine.encoding_fn = _engine_encoding_fn
+Engine._step_logits = _engine_step_logits
 Engine.decoding_fn = _engine_decoding_fn
 Engine.decoding_fn_dev = _engine_decoding_fn_dev
 Engine._post_attn = _engine_post_attn

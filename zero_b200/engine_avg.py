@@ -180,7 +180,7 @@ def _avg_layer_bwd(self, key, bw, sv, ds2, dxc, enc, d_enc_f32, B, T, S, save):
 
 
 # ------------------------------------------------------------------------------------------------ cached decode
-def _decoding_fn_avg(self, target, state, time):
+def _decoding_fn_avg(self, target, state, time, candidates=None):
     """Cached decode step of transformer_aan / transformer_fuse: the growing K/V cache of self-attention is
     replaced by one fp32 running sum per layer (transformer_aan.py:110-112; func.py:262-272)."""
     c, ps, ws = self.cfg, self.ps, self.ws
@@ -243,9 +243,7 @@ def _decoding_fn_avg(self, target, state, time):
         h = ws.get("dec.h", (R, c.f))
         ops.linear_fwd(xc, ps.w(key + ".ffn.w1.W"), ps.p(key + ".ffn.w1.b"), h, relu=True)
         self._decode_proj_ln(h, key + ".ffn.w2", xc, x, key + ".ffn.ln", R)
-    logits = self._vocab_rows("dec.logits", R, f32)
-    ops.gemm(x, ps.w(self._softmax_table()), logits, L.ZB_K_MAJOR, L.ZB_K_MAJOR)
-    return self._dense_logits(logits), state
+    return self._step_logits(x, R, candidates), state
 
 
 # ---- DecodeState: running sums instead of K/V caches

@@ -84,7 +84,12 @@ class BeamArgs(C.Structure):
                 ("length_penalty", f32), ("max_len", vp), ("max_penalty", vp), ("seq_cap", i32),
                 ("alive_seq", vp), ("alive_logp", vp), ("alive_score", vp),
                 ("fin_seq", vp), ("fin_score", vp), ("fin_flag", vp), ("parent", vp), ("tmp_seq", vp),
-                ("active", vp), ("row_ws", vp)]
+                ("active", vp), ("row_ws", vp), ("cand", vp)]
+
+
+class VocabTopkArgs(C.Structure):
+    _fields_ = [("feat", vp), ("ldf", i64), ("table", vp), ("ldt", i64), ("rows", i32), ("d", i32), ("vocab", i32),
+                ("skip_col", i32), ("temperature", f32), ("workspace", vp), ("workspace_bytes", i64)]
 
 
 SHARD_MAX_WORLD = 16
@@ -104,7 +109,7 @@ class ShardAdamArgs(C.Structure):
 # every symbol include/zero_b200.h declares (tests/test_abi.py checks the library exports all of them)
 # order = the index zb_abi_struct_size() understands
 STRUCTS = [GemmArgs, AttentionArgs, AddLnArgs, EmbedArgs, CeArgs, AdamArgs, BeamArgs, ColsumArgs, ShardAdamArgs,
-           VocabCeArgs]
+           VocabCeArgs, VocabTopkArgs]
 
 EXPORTS = [
     "zb_abi_version", "zb_last_error_string", "zb_launch_count", "zb_path_launch_count", "zb_abi_struct_size", "zb_dropout", "zb_gemm", "zb_attention_fwd",
@@ -114,6 +119,7 @@ EXPORTS = [
     "zb_aan_gate_fwd", "zb_aan_gate_bwd", "zb_gated_rms_fwd", "zb_gated_rms_bwd", "zb_add2d",
     "zb_gemm_grouped", "zb_colsum_grouped", "zb_aan_cat_step", "zb_aan_gate_ln", "zb_shard_adam", "zb_gumbel_add",
     "zb_attention_bwd_workspace_bytes", "zb_vocab_ce", "zb_vocab_ce_workspace_bytes", "zb_set_sm_reserve",
+    "zb_vocab_topk", "zb_vocab_topk_workspace_bytes", "zb_vocab_topk_parts",
 ]
 
 _lib = None
@@ -150,6 +156,7 @@ def load():
         ("zb_embed_bwd", [C.POINTER(EmbedArgs), vp]),
         ("zb_softmax_ce", [C.POINTER(CeArgs), vp]),
         ("zb_vocab_ce", [C.POINTER(VocabCeArgs), vp]),
+        ("zb_vocab_topk", [C.POINTER(VocabTopkArgs), vp]),
         ("zb_set_sm_reserve", [i32]),
         ("zb_colsum", [vp, i64, i64, i64, vp, vp]),
         ("zb_cast_f32_bf16", [vp, vp, i64, vp]),
@@ -180,7 +187,11 @@ def load():
     lib.zb_attention_bwd_workspace_bytes.restype = C.c_int64
     lib.zb_vocab_ce_workspace_bytes.argtypes = [C.POINTER(VocabCeArgs)]
     lib.zb_vocab_ce_workspace_bytes.restype = C.c_int64
-    if lib.zb_abi_version() != 3:
+    lib.zb_vocab_topk_workspace_bytes.argtypes = [C.POINTER(VocabTopkArgs)]
+    lib.zb_vocab_topk_workspace_bytes.restype = C.c_int64
+    lib.zb_vocab_topk_parts.argtypes = [i32]
+    lib.zb_vocab_topk_parts.restype = i32
+    if lib.zb_abi_version() != 4:
         raise ZeroB200Error("libzero_b200.so ABI version mismatch")
     lib.zb_abi_struct_size.argtypes = [i32]
     lib.zb_abi_struct_size.restype = C.c_int64
@@ -199,7 +210,7 @@ def check(rc, what):
 
 
 PATHS = {"gemm_tcgen05": 0, "gemm_pair": 1, "gemm_skinny": 2, "attn_mma": 3, "attn_generic": 4, "attn_decode": 5,
-         "beam_sentence": 6, "beam_rows": 7, "beam_parts": 8, "gemm_bm64": 9, "attn_tc": 10}
+         "beam_sentence": 6, "beam_rows": 7, "beam_parts": 8, "gemm_bm64": 9, "attn_tc": 10, "beam_cand": 11}
 
 
 def path_launch_count(name) -> int:

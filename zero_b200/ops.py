@@ -233,6 +233,49 @@ def vocab_ce(feat, table, labels, nll, smooth, workspace, d_logits=None, per_sam
     L.check(L.load().zb_vocab_ce(C.byref(a), _stream()), "zb_vocab_ce")
 
 
+class BeamCandidates(object):
+    """What zb_vocab_topk leaves for zb_beam_step in place of the [rows, V] logits (csrc/vocab_topk.cu): `buffer` holds
+    per (row, 128-column part) the soft-max statistics and the 8 largest logits with their columns."""
+
+    def __init__(self, buffer, rows, vocab, parts, skip_col, temperature):
+        self.buffer, self.rows, self.vocab, self.parts = buffer, rows, vocab, parts
+        self.skip_col, self.temperature = skip_col, temperature
+
+    def unpack(self):
+        """(stats [parts, rows, 4], values [parts, rows, 8], columns [parts, rows, 8]) views, for tests."""
+        n = self.parts * self.rows
+        flat = self.buffer.view(torch.float32).reshape(-1)
+        stats = flat[:4 * n].view(self.parts, self.rows, 4)
+        vals = flat[4 * n:12 * n].view(self.parts, self.rows, 8)
+        cols = flat[12 * n:20 * n].view(torch.int32).view(self.parts, self.rows, 8)
+        return stats, vals, cols
+
+
+def vocab_topk(feat, table, workspace, skip_col=-1, temperature=1.0):
+    """K8 fused: the decode step's vocabulary projection reduced to beam-search candidates inside the GEMM epilogue
+    (models/transformer.py:186-196 + search.py:147-176); the logits are never written.  feat bf16 [rows, d]; table bf16
+    [V, d]; workspace: callable bytes -> tensor, or a tensor.  Returns BeamCandidates for BeamState.step."""
+    a = L.VocabTopkArgs()
+    a.feat, a.ldf, a.table, a.ldt = _p(feat), feat.stride(0), _p(table), table.stride(0)
+    a.rows, a.d, a.vocab = feat.shape[0], feat.shape[1], table.shape[0]
+    a.skip_col, a.temperature = int(skip_col), float(temperature)
+    need = int(L.load().zb_vocab_topk_workspace_bytes(C.byref(a)))
+    ws = workspace(need) if callable(workspace) else workspace
+    a.workspace, a.workspace_bytes = _p(ws), ws.numel() * ws.element_size()
+    L.check(L.load().zb_vocab_topk(C.byref(a), _stream()), "zb_vocab_topk")
+    return BeamCandidates(ws, int(a.rows), int(a.vocab), int(L.load().zb_vocab_topk_parts(a.vocab)), int(skip_col),
+                          float(temperature))
+
+
+def vocab_topk_supported(d, vocab, beam, feat=None, table=None):
+    """Shapes the candidate path takes (the caller otherwise materialises the logits: zb_gemm + zb_beam_step)."""
+    ok = vocab >= 128 and d % 8 == 0 and 2 * beam <= 8 and vocab - 1 >= 2 * beam
+    for t in (feat, table):
+        if t is not None:
+            ok = ok and t.stride(0) % 8 == 0 and t.stride(1) == 1 and t.data_ptr() % 16 == 0
+    return bool(ok)
+
+
 def vocab_ce_supported(rows, d, vocab, feat=None, table=None, d_logits=None):
     """Shapes the fused kernel takes (the caller otherwise materialises the logits: zb_gemm + zb_softmax_ce)."""
     ok = vocab >= 128 and d % 8 == 0

@@ -81,8 +81,14 @@ class BeamState(object):
 
     def _args(self, logits, t):
         pen = float(torch.pow(torch.tensor((5.0 + float(t + 1)) / 6.0, dtype=torch.float32), self.alpha))
+        cand = None
+        if isinstance(logits, ops.BeamCandidates):
+            # the vocabulary projection already applied this step's temperature and EOS ban (csrc/vocab_topk.cu)
+            assert logits.rows == self.B * self.K and logits.vocab == self.V
+            assert logits.temperature == self.temperature and logits.skip_col == (self.eos_id if t < 1 else -1)
+            logits, cand = None, logits.buffer
         return ops.beam_args(
-            logits=logits, batch=self.B, beam=self.K, vocab=self.V, time=int(t), eos_id=self.eos_id,
+            cand=cand, logits=logits, batch=self.B, beam=self.K, vocab=self.V, time=int(t), eos_id=self.eos_id,
             pad_id=self.pad_id, temperature=self.temperature, inf_value=self.inf_value, length_penalty=pen,
             max_len=self.max_len, max_penalty=self.max_penalty, seq_cap=self.cap, alive_seq=self.alive_seq,
             alive_logp=self.alive_logp, alive_score=self.alive_score, fin_seq=self.fin_seq,
@@ -125,7 +131,12 @@ class BeamState(object):
         seq = self.alive_seq[:, :, 1:t + 1].reshape(self.B * self.K, t)
         return torch.cat([seq, torch.ones(self.B * self.K, 1, dtype=seq.dtype, device=seq.device)], 1).contiguous()
 
+    def candidate_request(self, t):
+        """What decoding_fn(..., candidates=) needs to reduce step t's logits for this search (ops.vocab_topk)."""
+        return {"skip_col": self.eos_id if t < 1 else -1, "temperature": self.temperature}
+
     def step(self, logits, t):
+        """`logits`: fp32 [B*beam, V], or the ops.BeamCandidates the fused vocabulary projection left instead."""
         ops.beam_step(self._args(logits, t))
         self.time = t + 1
         return self.parent
@@ -191,6 +202,12 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     # CUDA-graph replay is only valid for the engine's own decoding_fn (a wrapped one may have side effects)
     own = getattr(decoding_fn, "__self__", None) is eng and getattr(decoding_fn, "__func__", None) is type(eng).decoding_fn
     use_graph = own and bool(getattr(params, "decode_graph", True)) and not dev_mode
+    # K8 fused (csrc/vocab_topk.cu): the engine's own cached step hands the beam step per-part top-8 candidates
+    # instead of [B*beam, V] logits.  Needs the logits themselves for nothing else: not with Gumbel noise on them,
+    # not through a wrapped decoding_fn (it expects logits), not in "dev" mode.  Default since the r02ae A/B (0.542 -> 0.503 ms/step); ZB_BEAM_FUSED=0 keeps the logits path.
+    fused = (own and not noise and not dev_mode and st.row_ws is not None
+             and os.environ.get("ZB_BEAM_FUSED", "1") != "0"
+             and ops.vocab_topk_supported(eng.cfg.d, state.vocab, K))
     graphs = eng.__dict__.setdefault("_decode_graphs", {})
     seen = eng.__dict__.setdefault("_decode_seen", {})
     if eng.__dict__.get("_decode_graphs_gen", 0) != eng.ws.generation:
@@ -202,7 +219,10 @@ def beam_search(features, encoding_fn, decoding_fn, params):
 
     def run_step(t):
         nonlocal state
-        logits, state = decoding_fn(st.prefix_tokens(t) if dev_mode else st.last_tokens(t), state, t)
+        if fused:
+            logits, state = decoding_fn(st.last_tokens(t), state, t, candidates=st.candidate_request(t))
+        else:
+            logits, state = decoding_fn(st.prefix_tokens(t) if dev_mode else st.last_tokens(t), state, t)
         if noise:
             ops.gumbel_add(logits, st.noise_seed, t, eps=float(getattr(params, "dtype_epsilon", 1e-8)))
         parent = st.step(logits, t)
@@ -216,7 +236,7 @@ def beam_search(features, encoding_fn, decoding_fn, params):
     speculate = own and os.environ.get("ZB_DECODE_SPEC", "1") != "0"
 
     def enqueue_step(t):
-        gkey = key + (t,)
+        gkey = key + (t, fused)
         g = graphs.get(gkey) if use_graph else None
         if g is not None:
             g.replay()
