@@ -318,6 +318,8 @@ def test_opt_in_decode_switches_keep_the_beams(switch, monkeypatch):
     hp.add_hparam("decode_graph", False)
     eng.decode_length = hp.decode_length
     src = torch.from_numpy(z["source"])
+    if switch == "ZB_BEAM_PARTS":
+        monkeypatch.setenv("ZB_BEAM_FUSED", "0")      # the beam kernels over logits are what this switch chooses between
     monkeypatch.setenv(switch, "0")
     ref = search.beam_search({"source": src}, eng.encoding_fn, eng.decoding_fn, hp)
     monkeypatch.setenv(switch, "1")
