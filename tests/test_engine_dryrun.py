@@ -12,6 +12,7 @@ import torch
 from zero_b200.params import transformer_base
 
 BUILDERS = ("attention_args", "gemm_args", "wgrad_args", "beam_args")
+PURE = ("vocab_topk_supported",)          # shape predicates that launch nothing: kept real
 
 
 def _mock_ops(monkeypatch):
@@ -21,8 +22,8 @@ def _mock_ops(monkeypatch):
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     for name in dir(ops):
         fn = getattr(ops, name)
-        if callable(fn) and not name.startswith("_") and getattr(fn, "__module__", "") == ops.__name__ \
-                and name not in BUILDERS:
+        if callable(fn) and not isinstance(fn, type) and not name.startswith("_") \
+                and getattr(fn, "__module__", "") == ops.__name__ and name not in BUILDERS and name not in PURE:
             monkeypatch.setattr(ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
     return calls
 
@@ -215,3 +216,52 @@ def test_fixed_shapes_never_replace_a_workspace_buffer(family, monkeypatch):
     eng.forward_backward(src, tgt)
     eng.forward_backward(*big)
     assert eng.ws.generation == g
+
+
+@pytest.mark.parametrize("case", ["default", "ZB_BEAM_FUSED=0", "noise", "wrapped", "beam5", "dev", "aan"])
+def test_search_hands_candidates_to_the_beam_step_only_on_its_own_plain_path(case, monkeypatch):
+    """search.beam_search asks the engine's decode step for beam candidates instead of logits (K8 fused:
+    ops.vocab_topk -> zb_beam_step(cand)) exactly when nothing else needs the logits: the engine's own cached
+    decoding_fn, no Gumbel noise, beam <= 4.  Every other case keeps the logits path (zb_gemm -> zb_beam_step(logits))."""
+    import zero_b200.ops as ops
+    from zero_b200 import search
+    from zero_b200.params import SimpleVocab
+    family = dict(model_name="transformer_aan", scope_name="transformer_aan") if case == "aan" else \
+        dict(model_name="transformer", scope_name="transformer")
+    eng, calls = _dry_engine(monkeypatch, **family)
+    hp = transformer_base(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=2,
+                          num_decoder_layer=3, beam_size=5 if case == "beam5" else 4, decode_length=3, **family)
+    hp.add_hparam("tgt_vocab", SimpleVocab(208))
+    hp.add_hparam("decode_graph", False)
+    if case == "noise":
+        hp.enable_noise_beam_search = True
+    if case == "dev":
+        hp.search_mode = "dev"
+    monkeypatch.setenv("ZB_BEAM_FUSED", "0" if case == "ZB_BEAM_FUSED=0" else "1")
+    steps = []
+
+    def fake_topk(feat, table, workspace, skip_col=-1, temperature=1.0):
+        calls.append("vocab_topk")
+        return ops.BeamCandidates(torch.zeros(4), feat.shape[0], table.shape[0], 2, skip_col, temperature)
+
+    def fake_beam_step(a):
+        steps.append((bool(a.cand), bool(a.logits), int(a.time)))
+
+    monkeypatch.setattr(ops, "vocab_topk", fake_topk)
+    monkeypatch.setattr(ops, "beam_step", fake_beam_step)
+    # the loop condition lives on the device: here three steps, then stop
+    monkeypatch.setattr(search.BeamState, "cond_async", lambda self, t: t if t < 3 else None)
+    monkeypatch.setattr(search.BeamState, "cond_wait", lambda self, slot: True)
+    src, _ = _batch()
+    decoding_fn = eng.decoding_fn_dev if case == "dev" else eng.decoding_fn
+    if case == "wrapped":
+        inner = decoding_fn
+        decoding_fn = lambda tok, state, t: inner(tok, state, t)     # noqa: E731  (a user's hook around the step)
+    out = search.beam_search({"source": src}, eng.encoding_fn, decoding_fn, hp)
+    assert tuple(out["seq"].shape[:2]) == (4, int(hp.beam_size))
+    fused = case in ("default", "aan")
+    assert [s[2] for s in steps] == [0, 1, 2]
+    assert all(s[0] == fused and s[1] == (not fused) for s in steps), steps
+    n = collections.Counter(calls)
+    assert n["vocab_topk"] == (3 if fused else 0)
+    assert n["gumbel_add"] == (3 if case == "noise" else 0)
