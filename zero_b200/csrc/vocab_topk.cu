@@ -11,6 +11,14 @@
 // row into its log-sum-exp, scores the 8 * parts candidates exactly as the logits kernels score all V, and carries on
 // with the same bookkeeping.
 //
+// Exactness.  The beam step orders continuations by (score desc, flat index asc) like tf.nn.top_k; the epilogue orders a
+// part's columns by (logit desc, column asc).  The two agree wherever scores are strictly monotone in the logit, and for
+// equal logits.  They can differ only where two DIFFERENT logits round to the same fp32 score, the larger one in the
+// higher column, at the 8th / 9th place of one part — and that changes the result only if the sentence's whole top-2k
+// lies in that part of that row.  tests/test_beam_candidates_cpu.py checks the algorithm against the oracle's restatement
+// of search.py (first step with the EOS ban, dead beams, temperature, a frequency-sorted vocabulary, exact ties);
+// tests/test_kernels_gpu.py checks the kernels against the logits path step for step.
+//
 // Workspace layout (parts = 2 * ceil(V / 256), rows = batch * beam):
 //   float4 stats[parts][rows]      {max, sum exp(x - max), 0, 0}; {-inf, 0, 0, 0} for a part past V
 //   float  cval [parts][rows][8]   descending, ties -> lower column; -inf = empty slot
