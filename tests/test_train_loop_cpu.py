@@ -332,3 +332,69 @@ def test_default_dtype_names_follow_the_reference_and_unknown_ones_are_rejected(
         E.Engine(_params(tmp_path, default_dtype=ok), device="cpu")
     with pytest.raises(ZeroB200Error):
         E.Engine(_params(tmp_path, default_dtype="int8"), device="cpu")
+
+
+@pytest.mark.parametrize("init,gain", [("uniform_unit_scaling", 1.0), ("uniform", 0.08), ("normal", 0.05),
+                                       ("normal_unit_scaling", 1.0), ("no_such_initializer", 0.3)])
+@pytest.mark.parametrize("deep", [False, True])
+def test_random_init_follows_the_references_initializers(init, gain, deep, monkeypatch):
+    """ParamStore.init_random draws from the distributions the reference's variables get (modules/initializer.py:11-32
+    under the model scope, main.py; the embeddings' own normal(0, d^-0.5), models/transformer.py:18,24,99,190; zeros
+    for linear biases func.py:58, ones / zeros for layer norm func.py:297-298; with deep_transformer_init a layer's
+    variance-scaling initializer with gain * (layer + 1)^-0.5, models/transformer.py:38-45) — checked by their moments
+    and supports, tensor by tensor."""
+    import math
+    import zero_b200.engine as E
+    import zero_b200.ops as ops
+    from zero_b200.params import transformer_base
+    # no CPU path in the product: bypass the device check, the bf16 mirror refresh is a torch copy here
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(ops, "cast_f32_bf16", lambda src, dst: dst.copy_(src))
+    hp = transformer_base(hidden_size=128, embed_size=128, filter_size=512, num_heads=2, num_encoder_layer=3,
+                          num_decoder_layer=2, initializer=init, initializer_gain=gain, deep_transformer_init=deep)
+    eng = E.Engine(hp, 300, 300, device="cpu")
+    eng.ps.init_random(7)
+    seen = set()
+    for k in eng.ps.tf_views:
+        t = eng.ps.tf_view(eng.ps.master, k).float()
+        leaf = k.rsplit("/", 1)[1]
+        if leaf.endswith("embedding"):
+            assert abs(float(t.std()) - 128 ** -0.5) < 0.03 * 128 ** -0.5, k
+            seen.add("embedding")
+            continue
+        if leaf in ("b_0", "offset"):
+            assert float(t.abs().max()) == 0.0, k
+            continue
+        if leaf == "scale":
+            assert float((t - 1).abs().max()) == 0.0, k
+            continue
+        fi, fo = (t.shape[0], t.shape[0]) if t.dim() == 1 else (t.shape[0], t.shape[1])
+        layered = "/layer_" in k
+        scale = gain
+        kind = init
+        if deep and layered:
+            scale, kind = gain * (int(k.split("/layer_")[1].split("/")[0]) + 1) ** -0.5, "uniform_unit_scaling"
+        elif init == "no_such_initializer":
+            scale, kind = 1.0, "uniform_unit_scaling"
+        seen.add(kind)
+        if kind == "uniform":
+            lim, std = gain, gain / math.sqrt(3.0)
+        elif kind == "normal":
+            lim, std = 6.0 * gain, gain
+        elif kind == "normal_unit_scaling":
+            std = math.sqrt(scale / ((fi + fo) / 2.0))
+            lim = 2.0 * std / 0.87962566103423978
+        else:
+            lim = math.sqrt(3.0 * scale / ((fi + fo) / 2.0))
+            std = lim / math.sqrt(3.0)
+        assert float(t.abs().max()) <= lim * (1 + 1e-6), k
+        if t.numel() >= 4096:
+            assert abs(float(t.std()) - std) < 0.04 * std, (k, float(t.std()), std)
+            assert abs(float(t.mean())) < 0.05 * std, k
+            if kind != "normal":
+                assert float(t.abs().max()) > 0.9 * lim, k     # the support is used up to its edge
+    assert "embedding" in seen and (init if init != "no_such_initializer" else "uniform_unit_scaling") in seen
+    if deep:
+        first = eng.ps.tf_view(eng.ps.master, [k for k in eng.ps.tf_views if "/encoder/layer_0/" in k and "W_0_0" in k][0])
+        third = eng.ps.tf_view(eng.ps.master, [k for k in eng.ps.tf_views if "/encoder/layer_2/" in k and "W_0_0" in k][0])
+        assert abs(float(first.std()) / float(third.std()) - 3 ** 0.25) < 0.05

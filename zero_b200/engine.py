@@ -289,12 +289,26 @@ class ParamStore(object):
                 layered = "/layer_" in k
                 if c.deep_init and layered:
                     scale = c.init_gain * (int(k.split("/layer_")[1].split("/")[0]) + 1) ** -0.5
-                if c.init == "uniform" and not (c.deep_init and layered):
+                scoped = not (c.deep_init and layered)     # a layer's own variance-scaling initializer wins
+                fi, fo = (shape[0], shape[0]) if len(shape) == 1 else (shape[0], shape[1])
+                if c.init == "uniform" and scoped:
                     t = (torch.rand(shape, generator=g) * 2 - 1) * c.init_gain
-                elif c.init == "normal" and not (c.deep_init and layered):
+                elif c.init == "normal" and scoped:
                     t = torch.randn(shape, generator=g) * c.init_gain
+                elif c.init == "normal_unit_scaling" and scoped:
+                    # tf.variance_scaling_initializer(distribution="normal"): a normal truncated at two standard
+                    # deviations, its stddev corrected by 0.8796... so that the truncated variance is scale / fan_avg
+                    std = math.sqrt(scale / ((fi + fo) / 2.0)) / 0.87962566103423978
+                    t = torch.randn(shape, generator=g)
+                    for _ in range(64):
+                        bad = t.abs() > 2.0
+                        if not bool(bad.any()):
+                            break
+                        t = torch.where(bad, torch.randn(shape, generator=g), t)
+                    t = t.clamp_(-2.0, 2.0) * std
                 else:
-                    fi, fo = (shape[0], shape[0]) if len(shape) == 1 else (shape[0], shape[1])
+                    if scoped and c.init != "uniform_unit_scaling":
+                        scale = 1.0                        # unrecognised name: glorot_uniform (initializer.py:29-32)
                     lim = math.sqrt(3.0 * scale / ((fi + fo) / 2.0))
                     t = (torch.rand(shape, generator=g) * 2 - 1) * lim
             v.copy_(t.to(self.device))
