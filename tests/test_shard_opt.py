@@ -7,7 +7,6 @@ emulation of the semantics include/zero_b200.h documents.  What is checked is ev
 plan, arena rebinding, argument plumbing (addresses, offsets, flags), the two-pass clip flow, the norm exchange,
 EMA on the own shard, whole-state sync — against the oracle's replicated Adam on the mean gradient
 (utils/parallel.py:184-196 + main.py:178-181).  The kernel itself is the GPU tests' job."""
-import math
 import threading
 
 import pytest

@@ -8,7 +8,6 @@ import os
 
 import torch
 
-from . import lib as L
 from . import ops
 from .engine import DecodeState, Engine, _lens, dropout_site
 
