@@ -215,9 +215,11 @@ def decode_bench(device, batches=3):
         tot_ms += e0.elapsed_time(e1)
     # HBM roofline of one decode step: decoder weights 6 x (gate 1.05 M + cross q/o 0.52 M + FFN 2.10 M)
     # params + the tied vocabulary table 16.4 M, bf16, + the projected memories [64, 64, 1024] x 6 layers read once per
-    # sentence, + the fp32 logits [256, 32000] written and read back once by the beam step
+    # sentence.  The step logits are not algorithmic traffic: K8 fused reduces them to beam candidates in the GEMM
+    # epilogue; only with ZB_BEAM_FUSED=0 are the fp32 [256, 32000] logits written and read back by the beam step.
+    logits_path = os.environ.get("ZB_BEAM_FUSED", "1") == "0"
     step_bytes = 2.0 * (6 * (1024 * 1024 + 2 * 512 * 512 + 2 * 512 * 2048) + VOCAB * 512) \
-        + 2.0 * 64 * 64 * 1024 * 6 + 2 * 4.0 * 256 * VOCAB
+        + 2.0 * 64 * 64 * 1024 * 6 + (2 * 4.0 * 256 * VOCAB if logits_path else 0.0)
     ms_step = tot_ms / max(tot_steps, 1)
     peak = None
     try:
@@ -226,7 +228,8 @@ def decode_bench(device, batches=3):
         pass
     roof = {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
             "peak": peak, "unit": "GB/s", "frac": (step_bytes / (ms_step * 1e-3) / 1e9 / peak) if peak else None,
-            "note": "the step is ~100 dependent launches of 256-row problems: latency-bound, not bandwidth-bound"}
+            "note": "the step is ~100 dependent launches of 256-row problems: latency-bound, not bandwidth-bound",
+            "vocabulary_projection": "logits + beam kernels" if logits_path else "beam candidates from the GEMM epilogue"}
     return {"metric": "beam4_decode_tokens_per_sec", "value": tot_tok / (tot_ms * 1e-3), "unit": "top-1 tokens/s",
             "roofline": roof,
             "row_steps_per_sec": tot_steps * 256 / (tot_ms * 1e-3), "steps": tot_steps, "ms_per_step": tot_ms / max(tot_steps, 1),
