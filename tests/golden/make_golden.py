@@ -46,7 +46,7 @@ def make_params(model_name, **kw):
         initializer="uniform_unit_scaling", initializer_gain=1.0,
         dropout=0.0, relu_dropout=0.0, residual_dropout=0.0, attention_dropout=0.0, label_smooth=0.1,
         beam_size=4, decode_length=6, decode_alpha=0.6, max_relative_position=4))
-    p.override_from_dict(kw)
+    p.override_from_dict({k: v for k, v in kw.items() if not k.startswith("_")})   # _vs / _vt: vocabulary sizes
     p.add_hparam("src_vocab", SimpleVocab(kw.get("_vs", 200)))
     p.add_hparam("tgt_vocab", SimpleVocab(kw.get("_vt", 208)))
     return p
@@ -157,7 +157,22 @@ def main_long():
         run(model, out_name=name, seed=21, shape=(4, 40, 36), **dict(long, **extra))
 
 
+def main_embeddings():
+    """The two embedding-sharing switches away from their defaults (models/transformer.py:21-22,96-97,186-189): one
+    table for source, target and soft-max ("embedding"), and a soft-max table of its own ("softmax_embedding")."""
+    small = dict(hidden_size=64, embed_size=64, filter_size=128, num_heads=2)   # dh = 32
+    run("transformer", out_name="transformer_shared_emb", seed=31, shared_source_target_embedding=True,
+        _vs=208, _vt=208, **small)
+    run("transformer", out_name="transformer_softmax_emb", seed=32, shared_target_softmax_embedding=False, **small)
+    run("transformer_aan", out_name="transformer_aan_shared_emb", seed=33, shared_source_target_embedding=True,
+        _vs=208, _vt=208, **small)
+
+
 if __name__ == "__main__":
+    if "--embeddings-only" in sys.argv:
+        main_embeddings()
+        sys.exit(0)
     if "--long-only" not in sys.argv:
         main_small()
+        main_embeddings()
     main_long()

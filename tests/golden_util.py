@@ -11,7 +11,10 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODELS = ["transformer", "transformer_h4", "transformer_aan", "transformer_aan_cumsum", "transformer_rpr",
           "transformer_rela", "transformer_fuse",
           # lengths up to 40 / 36 tokens, dh = 64 (the tensor-core attention kernels of the training step)
-          "transformer_len40", "transformer_rpr_len40", "transformer_rela_len40", "transformer_fuse_len40"]
+          "transformer_len40", "transformer_rpr_len40", "transformer_rela_len40", "transformer_fuse_len40",
+          # the embedding-sharing switches away from their defaults: one table for source / target / soft-max, and a
+          # soft-max table of its own
+          "transformer_shared_emb", "transformer_softmax_emb", "transformer_aan_shared_emb"]
 
 
 def load_golden(name):

@@ -265,3 +265,45 @@ def test_search_hands_candidates_to_the_beam_step_only_on_its_own_plain_path(cas
     n = collections.Counter(calls)
     assert n["vocab_topk"] == (3 if fused else 0)
     assert n["gumbel_add"] == (3 if case == "noise" else 0)
+
+
+@pytest.mark.parametrize("name", ["transformer_shared_emb", "transformer_softmax_emb", "transformer_aan_shared_emb"])
+def test_embedding_sharing_switches_plan_the_references_variables(name, monkeypatch):
+    """shared_source_target_embedding / shared_target_softmax_embedding away from their defaults
+    (models/transformer.py:21-22, 96-97, 186-189): the parameter store holds exactly the variables the reference
+    created (by TF name and shape, from the reference-executed golden), loads them, and the schedule — forward,
+    backward, score, one cached decode step — runs with the embedding gradients routed to the right tables."""
+    import zero_b200.engine as E
+    import zero_b200.ops as ops
+    from tests.golden_util import load_golden
+    calls = _mock_ops(monkeypatch)
+    z, hp, variables, grads, vs, vt = load_golden(name)
+    eng = E.Engine(hp, vs, vt, device="cpu")
+    assert set(eng.ps.tf_views) == set(variables), sorted(set(eng.ps.tf_views) ^ set(variables))
+    for k, v in variables.items():
+        assert tuple(eng.ps.tf_view(eng.ps.master, k).shape) == tuple(v.shape), k
+    eng.ps.load_state_dict(variables)
+    for k, v in variables.items():
+        assert torch.equal(eng.ps.tf_view(eng.ps.master, k), v), k
+    shared = bool(hp.shared_source_target_embedding)
+    assert eng._tgt_table() == ("src_emb" if shared else "tgt_emb")
+    assert eng._softmax_table() == ("src_emb" if shared else ("tgt_emb" if hp.shared_target_softmax_embedding
+                                                             else "softmax_emb"))
+    tables = []
+    real_p = ops._p
+
+    def embed_bwd(ids, dy, d_table, *a, **k):
+        calls.append("embed_bwd")
+        tables.append(d_table.data_ptr())
+    monkeypatch.setattr(ops, "embed_bwd", embed_bwd)
+    src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
+    loss = eng.forward_backward(src, tgt)
+    assert tuple(loss.shape) == (1,) and real_p is ops._p
+    # target embedding gradient first (decoder backward), source embedding gradient last
+    want = [eng.ps.g(eng._tgt_table()).data_ptr(), eng.ps.g("src_emb").data_ptr()]
+    assert tables == want and (tables[0] == tables[1]) == shared
+    assert tuple(eng.score(src, tgt).shape) == (src.shape[0],)
+    state = eng.encoding_fn(src)
+    state.begin_search(2, cap=20)
+    logits, state = eng.decoding_fn(torch.zeros(2 * src.shape[0], 1, dtype=torch.int32), state, 0)
+    assert tuple(logits.shape) == (2 * src.shape[0], vt)
