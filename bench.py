@@ -31,8 +31,9 @@ def workload_config(n):
                         "dropout=0, batch 64x(src 64, tgt 64)=4096 target tokens per GPU per step, "
                         "fwd+bwd+allreduce+Adam (BASELINE.json configs[1])",
             "global_batch_tokens": 4096 * n, "src_len": SRC_LEN, "tgt_len": TGT_LEN,
-            "parallelism": "dp%d" % n, "l2": "working set (1.2 GB of weights/optimizer state + 0.8 GB logits per "
-                                             "step) exceeds the 126 MB L2; no explicit flush"}
+            "parallelism": "dp%d" % n, "l2": "working set (1.2 GB of weights / optimizer state + 0.26 GB of "
+                                             "bf16 d_logits + 0.4 GB of activations per step) exceeds the 126 MB L2; "
+                                             "no explicit flush"}
 
 
 def make_batch(seed, batch):
