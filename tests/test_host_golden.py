@@ -183,3 +183,29 @@ def test_plugin_registry_keeps_the_reference_surface():
         assert model.model_register("Zb_Test_Plugin", f, f, f) is model.get_model("zb_test_plugin")
     finally:
         model._total_models.pop("zb_test_plugin", None)
+
+
+def test_committed_bench_line_carries_the_contracts_keys():
+    """The last full bench line committed under profiles/ has every key the measurement contract names (base contract +
+    roofline + cpu_baseline + e2e + clocks), with the metric / unit of BASELINE.json and self-consistent numbers."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r02z_bench_n1_final.json")))
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "train_tokens_per_sec" and base["metric"].startswith("train tokens/sec")
+    assert d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["sample"] and c["unit"] == d["unit"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.001
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
+    tokens_per_step = d["config"]["global_batch_tokens"]
+    assert abs(d["value"] - tokens_per_step / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
