@@ -662,11 +662,16 @@ def run_ours(args):
         "roofline": roof,
         "model_tflops_per_gpu": model_flops / (ms / args.steps * 1e-3) / 1e12,
         "cpu_baseline": cpu_baseline,
-        "decode": decode_bench("cuda:%d" % local) if (world == 1 and not args.no_decode) else None,
+        "decode": None,
         "legs": None,
         "clocks": clocks,
         "final_loss": final_loss,
     }
+    if world == 1 and not args.no_decode:
+        try:
+            out["decode"] = decode_bench("cuda:%d" % local)
+        except Exception as e:      # a secondary leg must not take the headline line down with it
+            out["decode"] = {"error": repr(e)[:300]}
     if world == 1 and not args.no_extra:
         del trainer, eng
         torch.cuda.empty_cache()
