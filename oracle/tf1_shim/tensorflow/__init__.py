@@ -41,11 +41,11 @@ class DType(object):
 
     @property
     def min(self):
-        return float(torch.finfo(self.t).min) if self.t.is_floating_point else int(torch.iinfo(self.t).min)
+        return float(torch.finfo(self.t).min) if self.t.is_floating_point else int(np.iinfo(self.name).min)
 
     @property
     def max(self):
-        return float(torch.finfo(self.t).max) if self.t.is_floating_point else int(torch.iinfo(self.t).max)
+        return float(torch.finfo(self.t).max) if self.t.is_floating_point else int(np.iinfo(self.name).max)
 
     def __eq__(self, other):
         return isinstance(other, DType) and other.t == self.t
@@ -350,8 +350,16 @@ def variance_scaling_initializer(scale=1.0, mode="fan_in", distribution="truncat
             limit = math.sqrt(3.0 * s)
             return ((torch.rand(shape_, generator=_RNG, dtype=torch.float64) * 2 - 1) * limit).to(_td(dtype))
         std = math.sqrt(s)
-        if distribution in ("truncated_normal",):
+        if distribution in ("normal", "truncated_normal"):
+            # TF 1.13: "normal" is an alias of "truncated_normal" — a normal truncated at two standard deviations
+            # (out-of-range draws are redrawn), its stddev divided by 0.8796... so that the variance stays `s`
             std /= 0.87962566103423978
+            z = torch.randn(shape_, generator=_RNG, dtype=torch.float64)
+            bad = z.abs() > 2.0
+            while builtins_bool(bad.any()):
+                z[bad] = torch.randn(int(bad.sum()), generator=_RNG, dtype=torch.float64)
+                bad = z.abs() > 2.0
+            return (z * std).to(_td(dtype))
         return (torch.randn(shape_, generator=_RNG, dtype=torch.float64) * std).to(_td(dtype))
     return init
 
