@@ -306,3 +306,51 @@ def test_dtype_objects_follow_the_reference_usage(tf):
     assert _np(tf.constant(1.5, dtype=tf.float64)).dtype == np.float64
     # int32 ids / indices are carried as int64 (same values; torch indexing wants int64), the limits are int32's
     assert _np(tf.ones([2], dtype=tf.int32)).dtype == np.int64 and tf.int32.min == -2 ** 31
+
+
+def test_bias_add_pow_unary_ops_and_random_initializers(tf):
+    x = tf.constant(np.arange(6, dtype=np.float32).reshape(1, 2, 3))
+    np.testing.assert_array_equal(_np(tf.nn.bias_add(x, tf.constant([10.0, 20.0, 30.0])))[0, 1], [13, 24, 35])
+    np.testing.assert_allclose(_np(tf.pow(tf.constant([2.0, 3.0]), 2.0)), [4, 9])
+    np.testing.assert_allclose(_np(tf.pow(10000.0, tf.constant([0.0, 0.5]))), [1, 100], rtol=1e-6)   # timing signal scales
+    v = np.array([0.25, 1.0, 4.0], np.float32)
+    for name, fn in [("exp", np.exp), ("log", np.log), ("sin", np.sin), ("cos", np.cos), ("tanh", np.tanh),
+                     ("rsqrt", lambda a: 1 / np.sqrt(a)), ("sigmoid", lambda a: 1 / (1 + np.exp(-a)))]:
+        np.testing.assert_allclose(_np(getattr(tf, name)(tf.constant(v))), fn(v), rtol=1e-6, err_msg=name)
+    np.testing.assert_array_equal(_np(tf.nn.relu(tf.constant([-1.0, 0.0, 2.0]))), [0, 0, 2])
+    np.testing.assert_allclose(_np(tf.nn.sigmoid(tf.constant([0.0]))), [0.5])
+    tf.reset_default_graph(seed=9)
+    n = _np(tf.random_normal_initializer(0.5, 0.1)([400, 400])).astype(np.float64)
+    assert abs(n.mean() - 0.5) < 1e-3 and abs(n.std() - 0.1) < 1e-3
+    u = _np(tf.random_uniform_initializer(-0.3, 0.3)([400, 400])).astype(np.float64)
+    assert u.min() >= -0.3 and u.max() < 0.3 and abs(u.std() - 0.6 / math.sqrt(12.0)) < 1e-3
+    r = _np(tf.random_uniform([1000], minval=2, maxval=5))
+    assert r.min() >= 2 and r.max() < 5
+    assert bool((tf.zeros_initializer()([3]) == 0).all()) and bool((tf.ones_initializer()([3]) == 1).all())
+
+
+def test_the_shim_answers_every_tf_name_the_reference_path_uses(tf):
+    """`grep -oh "tf\\.[A-Za-z_.0-9]*"` over func.py, models/transformer{,_aan,_rpr,_rela,_fuse}.py, modules/rpr.py,
+    modules/rela.py, modules/initializer.py, search.py, utils/util.py, utils/dtype.py of the reference checkout."""
+    names = """variable_scope cast get_variable as_dtype shape reshape AUTO_REUSE float32 expand_dims matmul concat
+        reduce_sum equal bool variance_scaling_initializer cond random_normal_initializer nn.bias_add gather zeros
+        reduce_mean constant TensorShape zeros_like pad reduce_all range ones_like int32 gather_nd
+        nn.softmax_cross_entropy_with_logits_v2 transpose stack reduce_any nn.softmax name_scope log where squeeze split
+        rsqrt ones_initializer one_hot nn.top_k logging.warn gfile.Exists fill cumsum zeros_initializer tile sigmoid
+        random_uniform pow nn.relu logging.info boolean_mask add_n while_loop trainable_variables to_float tanh sin
+        reduce_min reduce_logsumexp random_uniform_initializer ones nn.sigmoid nn.dropout mod matrix_band_part
+        logical_or logical_not logical_and less_equal less greater_equal greater glorot_uniform_initializer float32.min
+        eye exp cos convert_to_tensor clip_by_value Session ConfigProto""".split()
+    for name in names:
+        obj = tf
+        for part in name.split("."):
+            assert hasattr(obj, part), "tf.%s is missing from the shim" % name
+            obj = getattr(obj, part)
+    ref = "/root/reference"
+    if os.path.isdir(ref):          # build container only: the list above is complete
+        import re
+        used = set()
+        for rel in ["func.py", "search.py", "utils/util.py", "utils/dtype.py", "modules/rpr.py", "modules/rela.py",
+                    "modules/initializer.py"] + ["models/transformer%s.py" % s for s in ("", "_aan", "_rpr", "_rela", "_fuse")]:
+            used |= set(re.findall(r"tf\.([A-Za-z_.0-9]*)", open(os.path.join(ref, rel)).read()))
+        assert used <= set(names), sorted(used - set(names))
