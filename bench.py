@@ -136,7 +136,7 @@ def cpu_reference_step_fn(sample_batch):
             for (k, p), g in zip(P.items(), grads):
                 newp, M[k], Vv[k] = zo.adam_tf_step(p, M[k], Vv[k], g, state["t"], 1e-4, 0.9, 0.98, 1e-8)
                 p.copy_(newp)
-        return float(loss), int((tgt != 0).sum())
+        return float(loss.detach()), int((tgt != 0).sum())
 
     return step, cores
 

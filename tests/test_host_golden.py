@@ -209,3 +209,49 @@ def test_committed_bench_line_carries_the_contracts_keys():
     tokens_per_step = d["config"]["global_batch_tokens"]
     assert abs(d["value"] - tokens_per_step / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_reference_arm_of_the_bench_prints_its_line_on_rank_zero_only():
+    """`bench.py --impl reference`: the oracle port on the host cores at the benchmarked batch — one JSON line with the
+    GPU arm's metric / unit / workload, `impl`, a `cpu_baseline` describing the run and an `e2e` without copies; under
+    torchrun every rank but 0 exits 0 without work or output."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_tokens_per_sec" and d["unit"] == "target tokens/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["config"]["global_batch_tokens"] == 4096 and "configs[1]" in d["config"]["workload"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] == (os.cpu_count() or 1) and c["value"] == d["value"] and "64 sentences" in c["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["value"] - 4096 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"] and d["value"] > 50
+
+
+def test_bench_flop_model_is_the_surveys():
+    """encoder layer fwd + bwd 19 267 584 FLOP per token; the whole configs[1] model 369 623 040 per
+    (source, target) token pair = 1.514 TFLOP per 4096-token step."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from zero_b200.params import transformer_base
+    hp = transformer_base()
+    assert bench.model_flops_per_step(hp, 64, 64, 64, 32000) == 369623040.0 * 4096
+    d, f, S = 512, 2048, 64
+    assert 3 * (8 * d * d + 4 * d * f + 4 * S * d) == 19267584
+    enc_only = transformer_base(num_encoder_layer=1, num_decoder_layer=0)
+    assert bench.model_flops_per_step(enc_only, 1, 64, 0, 0) == 19267584.0 * 64
