@@ -229,7 +229,7 @@ def decode_bench(device, batches=3):
         pass
     roof = {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
             "peak": peak, "unit": "GB/s", "frac": (step_bytes / (ms_step * 1e-3) / 1e9 / peak) if peak else None,
-            "note": "the step is ~100 dependent launches of 256-row problems: latency-bound, not bandwidth-bound",
+            "note": "the step is ~75 dependent launches of 256-row problems: latency-bound, not bandwidth-bound",
             "vocabulary_projection": "logits + beam kernels" if logits_path else "beam candidates from the GEMM epilogue"}
     return {"metric": "beam4_decode_tokens_per_sec", "value": tot_tok / (tot_ms * 1e-3), "unit": "top-1 tokens/s",
             "roofline": roof,
