@@ -307,3 +307,32 @@ def test_embedding_sharing_switches_plan_the_references_variables(name, monkeypa
     state.begin_search(2, cap=20)
     logits, state = eng.decoding_fn(torch.zeros(2 * src.shape[0], 1, dtype=torch.int32), state, 0)
     assert tuple(logits.shape) == (2 * src.shape[0], vt)
+
+
+def test_configurations_outside_the_path_fail_loudly_and_there_is_no_cpu_fallback(monkeypatch):
+    """No silent degradation: a model family, head size, width or dropout rate the kernels do not serve raises a
+    ZeroB200Error that names the limit; without a CUDA device the engine refuses to exist (there is no CPU path)."""
+    import zero_b200.engine as E
+    from zero_b200.lib import ZeroB200Error
+    small = dict(hidden_size=128, embed_size=128, filter_size=256, num_heads=2, num_encoder_layer=1, num_decoder_layer=1)
+    assert not torch.cuda.is_available()
+    with pytest.raises(ZeroB200Error, match="no CPU path"):
+        E.Engine(transformer_base(**small), 50, 50)
+    for over, msg in [(dict(embed_size=64), "embed_size must equal hidden_size"),
+                      (dict(num_heads=16), "head size 8 unsupported"),
+                      (dict(num_heads=3), "head size"),
+                      (dict(filter_size=250), "multiples of 8"),
+                      (dict(model_name="rnnsearch"), "outside the hot path"),
+                      (dict(model_name="transformer_l0drop"), "outside the hot path")]:
+        with pytest.raises(ZeroB200Error, match=msg):
+            E.ModelConfig(transformer_base(**dict(small, **over)), 50, 50)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    with pytest.raises(ZeroB200Error, match="dropout rate"):
+        E.Engine(transformer_base(attention_dropout=1.0, **small), 50, 50, device="cpu")
+    with pytest.raises(ZeroB200Error, match="default_dtype"):
+        E.Engine(transformer_base(default_dtype="float8", **small), 50, 50, device="cpu")
+    eng = E.Engine(transformer_base(**small), 50, 50, device="cpu")
+    sd = eng.ps.state_dict()
+    sd.pop(next(iter(sd)))
+    with pytest.raises(ZeroB200Error, match="state dict mismatch"):
+        eng.ps.load_state_dict(sd)
