@@ -17,7 +17,7 @@ def test_train_loss_grads_logits(name):
     P = {k: v.clone().requires_grad_(True) for k, v in variables.items()}
     src, tgt = torch.from_numpy(z["source"]), torch.from_numpy(z["target"])
     loss, logits, per_sample, enc = zo.train_loss(c, P, src, tgt)
-    assert abs(float(loss) - float(z["loss"])) < 2e-5
+    assert abs(float(loss.detach()) - float(z["loss"])) < 2e-5
     np.testing.assert_allclose(enc["encodes"].detach().numpy(), z["encodes"], atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(logits.detach().numpy(), z["logits"], atol=1e-4, rtol=1e-5)
     np.testing.assert_allclose(per_sample.detach().numpy(), z["per_sample_loss"], atol=2e-5, rtol=1e-5)
