@@ -576,7 +576,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(args.warmup):
         trainer.step(*devb[i % n_batches])
     barrier()
 
@@ -698,7 +698,7 @@ def main():
         run_reference(args)
     else:
         args.steps = 100 if args.steps is None else args.steps
-        args.warmup = 10 if args.warmup is None else args.warmup
+        args.warmup = 10 if args.warmup is None else max(args.warmup, 3)   # timing rule: never fewer than 3 warm-up steps
         run_ours(args)
 
 
