@@ -188,3 +188,17 @@ def test_smoothed_cross_entropy_equals_torch_label_smoothing_after_the_change_of
     assert abs(float(zo.smoothed_ce(torch.log(soft), torch.tensor([5]), eps))) < 1e-9
     torch.testing.assert_close(zo.smoothed_ce(logits, labels, 0.0),
                                torch.nn.functional.cross_entropy(logits, labels, reduction="none"), atol=1e-10, rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["transformer", "transformer_aan", "transformer_fuse"])
+def test_empty_tower_has_zero_loss_and_zero_gradients(name):
+    """models/transformer.py:213-216: a tower that received no sentence (fewer batches than devices at the end of an
+    epoch, main.py:287-294) contributes a loss of exactly 0 — and therefore nothing to the averaged gradients."""
+    c = _cfg(name)
+    P = {k: v.requires_grad_(True) for k, v in _params(c).items()}
+    src = torch.zeros(0, 5, dtype=torch.long)
+    tgt = torch.zeros(0, 4, dtype=torch.long)
+    loss, logits, per_sample, _ = zo.train_loss(c, P, src, tgt, F64)
+    assert float(loss.detach()) == 0.0 and per_sample.numel() == 0 and logits.shape[0] == 0
+    grads = torch.autograd.grad(loss, list(P.values()), allow_unused=True)
+    assert all(g is None or float(g.abs().max()) == 0.0 for g in grads)
