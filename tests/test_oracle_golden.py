@@ -76,3 +76,34 @@ def test_dropout_hook_and_restated_keep_mask():
     finally:
         zo.DROP = None
     assert abs(base - float(z["loss"])) < 2e-5 and abs(dropped - base) > 1e-3
+
+
+def _search_variants():
+    import json
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "search_variants.npz"), allow_pickle=False)
+    variants = json.loads(str(z["variants_json"]))
+    return z, [(m, v, variants[v]) for m in json.loads(str(z["models_json"])) for v in sorted(variants)]
+
+
+@pytest.mark.parametrize("model,variant,over", _search_variants()[1], ids=lambda x: x if isinstance(x, str) else "")
+def test_beam_search_hyper_parameters_away_from_the_defaults(model, variant, over):
+    """tests/golden/make_search_golden.py: the reference's search.py on the golden models' weights with greedy search,
+    beam widths 2 / 3 / 5, decode_alpha 0 / 0.2 / 1, temperatures 0.7 / 1.5, decode_length 0 / 3 / 10 — the oracle's
+    beam_search must return the same sequences (bit-exact), scores and number of decoder calls."""
+    from zero_b200.params import HParams
+    zs, _ = _search_variants()
+    z, hp, variables, _, vs, vt = load_golden(model)
+    hp = HParams(**dict(hp.values(), **over))
+    c = zo.Cfg(hp, vs, vt)
+    assert (c.beam, c.alpha, c.decode_length, c.temperature) == (
+        over.get("beam_size", 4), over.get("decode_alpha", 0.6), over.get("decode_length", 6),
+        over.get("beam_search_temperature", 1.0))
+    with torch.no_grad():
+        enc_fn, dec_fn = zo.make_infer_fns(c, variables)
+        out = zo.beam_search(c, torch.from_numpy(z["source"]), enc_fn, dec_fn)
+    key = "%s:%s" % (model, variant)
+    np.testing.assert_array_equal(out["seq"].numpy(), zs[key + ":seq"])
+    np.testing.assert_allclose(out["score"].numpy(), zs[key + ":score"], atol=2e-5, rtol=1e-5)
+    assert out["steps"] + 1 == int(zs[key + ":calls"])       # + the cache_init dummy call (search.py:56-77)
