@@ -71,7 +71,7 @@ def run(model_name, out_name=None, seed=7, shape=(5, 11, 9), **kw):
     p = make_params(model_name, **kw)
     rng = np.random.default_rng(seed)
     vs, vt = p.src_vocab.size(), p.tgt_vocab.size()
-    src, tgt = synth_batch(rng, shape[0], shape[1], shape[2], vs, vt)
+    src, tgt = kw["_batch"] if "_batch" in kw else synth_batch(rng, shape[0], shape[1], shape[2], vs, vt)
     feats = {"source": tf.constant(src), "target": tf.constant(tgt)}
     graph = ref_model.get_model(model_name)
     init = ref_init.get_initializer(p.initializer, p.initializer_gain)
@@ -168,11 +168,27 @@ def main_embeddings():
         _vs=208, _vt=208, **small)
 
 
+def main_edge():
+    """Edge cases of the data: sentences of ONE token (the end-of-sentence mark alone) on either side next to full-
+    length ones, a batch of one sentence, and label_smooth = 0 (utils/util.py:88-103 takes its one-hot branch)."""
+    small = dict(hidden_size=64, embed_size=64, filter_size=128, num_heads=2)   # dh = 32
+    src = np.array([[5, 9, 7, 4, 11, 2], [2, 0, 0, 0, 0, 0], [8, 6, 2, 0, 0, 0], [12, 13, 14, 15, 2, 0]], np.int64)
+    tgt = np.array([[2, 0, 0, 0, 0], [6, 7, 8, 9, 2], [10, 2, 0, 0, 0], [3, 3, 3, 2, 0]], np.int64)
+    run("transformer", out_name="transformer_edge", seed=41, _batch=(src, tgt), **small)
+    run("transformer_aan", out_name="transformer_aan_edge", seed=42, _batch=(src, tgt), **small)
+    run("transformer", out_name="transformer_edge_b1_nosmooth", seed=43, label_smooth=0.0,
+        _batch=(src[3:4, :5], tgt[1:2]), **small)
+
+
 if __name__ == "__main__":
+    if "--edge-only" in sys.argv:
+        main_edge()
+        sys.exit(0)
     if "--embeddings-only" in sys.argv:
         main_embeddings()
         sys.exit(0)
     if "--long-only" not in sys.argv:
         main_small()
         main_embeddings()
+        main_edge()
     main_long()

@@ -14,7 +14,11 @@ MODELS = ["transformer", "transformer_h4", "transformer_aan", "transformer_aan_c
           "transformer_len40", "transformer_rpr_len40", "transformer_rela_len40", "transformer_fuse_len40",
           # the embedding-sharing switches away from their defaults: one table for source / target / soft-max, and a
           # soft-max table of its own
-          "transformer_shared_emb", "transformer_softmax_emb", "transformer_aan_shared_emb"]
+          "transformer_shared_emb", "transformer_softmax_emb", "transformer_aan_shared_emb",
+          # edge cases of the data: one-token sentences (the end-of-sentence mark alone) on either side, a batch of one
+          # sentence, label_smooth = 0.  Oracle pin only: generated after the round's last GPU visit, so the CUDA
+          # path's own lists (tests/test_model_gpu.py) do not include them
+          "transformer_edge", "transformer_aan_edge", "transformer_edge_b1_nosmooth"]
 
 
 def load_golden(name):
